@@ -1,0 +1,156 @@
+/* persia_b200.h — C ABI of libpersia_b200.so: PERSIA's sparse-embedding hot path on B200 (sm_100a).
+ *
+ * The reference (PersiaML/PERSIA @ ff754b8) has no FFI for this path: its NN-worker engine
+ * (rust/persia-core) talks to an embedding worker and R parameter servers over HTTP.  These entry
+ * points are what a Rust `extern "C"` block in persia-core (or the C++/Python host side shipped in
+ * this repo) binds instead of those RPC clients; each one names the reference interface it replaces.
+ * Plain pointers and sizes only; every call is ordered on the given CUDA stream (passed as void*,
+ * i.e. a cudaStream_t), never synchronises the device unless its comment says so, and returns 0 or a
+ * negative pb_status; pb_last_error() gives the message for the calling thread.
+ *
+ * Conventions: `d_` = device pointer, `h_` = host pointer.  A "sign" is a prefixed u64 feature id
+ * (embedding_worker_service/mod.rs:402-429).  One pb_table is one parameter-server shard resident in
+ * one GPU's HBM, fixed embedding dim (the host side keeps one table per distinct dim).
+ */
+#ifndef PERSIA_B200_H_
+#define PERSIA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_MAX_SLOTS 128
+
+typedef enum {
+  PB_OK = 0,
+  PB_ERR_INVALID = -1,   /* bad argument */
+  PB_ERR_CUDA = -2,      /* CUDA runtime error (message in pb_last_error) */
+  PB_ERR_STATE = -3,     /* optimizer / hyper-parameters not configured (reference: OptimizerNotFoundError, NotConfiguredError) */
+  PB_ERR_CAPACITY = -4,  /* workspace too small for this batch */
+  PB_ERR_BATCH = -5      /* batch size > 65535 (persia-common/src/lib.rs:49-51 panics) */
+} pb_status;
+
+typedef enum { PB_OPT_SGD = 0, PB_OPT_ADAGRAD = 1, PB_OPT_ADAGRAD_VW = 2, PB_OPT_ADAM = 3 } pb_optim_kind;
+
+typedef struct pb_table pb_table; /* one shard: hash index + row store, owned by the library */
+typedef struct pb_ctx pb_ctx;     /* per-batch device context: what the EW keeps in post_forward_buffer */
+
+/* EmbeddingParameterServerConfig.capacity (persia-embedding-config/src/lib.rs:389-468) + slot dim. */
+typedef struct {
+  uint32_t dim;
+  uint64_t capacity; /* max resident rows of this shard */
+} pb_table_cfg;
+
+/* OptimizerConfig (persia-common/src/optim.rs:11-41). */
+typedef struct {
+  int kind; /* pb_optim_kind */
+  float lr, wd, g_square_momentum, initialization, eps, beta1, beta2;
+} pb_optim_cfg;
+
+/* PersiaEmbeddingModelHyperparameters: configure_embedding_parameter_servers (persia-core/src/nats.rs:355-384
+ * -> embedding_parameter_service/mod.rs:440-451). */
+typedef struct {
+  float init_lower, init_upper, admit_probability;
+  int enable_weight_bound;
+  float weight_bound;
+} pb_hyper_cfg;
+
+const char* pb_last_error(void);
+int pb_version(void);
+
+/* ---- table lifetime / configuration ------------------------------------------------------------ */
+/* PersiaEmbeddingHolder::get (persia-embedding-holder/src/lib.rs:36-71). Allocation is deferred to the
+ * first use, once the optimizer (hence the per-row state size, optim.rs:84) is known. */
+int pb_table_create(int device, const pb_table_cfg* cfg, pb_table** out);
+int pb_table_destroy(pb_table* t);
+/* register_optimizer (embedding_parameter_service/mod.rs:429-438). Must precede the first insert. */
+int pb_table_set_optimizer(pb_table* t, const pb_optim_cfg* cfg);
+/* configure (embedding_parameter_service/mod.rs:440-451). */
+int pb_table_configure(pb_table* t, const pb_hyper_cfg* cfg);
+/* num_total_signs (persia-embedding-holder/src/lib.rs:73-79); synchronises `stream`. */
+int pb_table_size(pb_table* t, uint64_t* h_out, void* stream);
+/* clear (persia-embedding-holder/src/lib.rs:95-97). */
+int pb_table_clear(pb_table* t, void* stream);
+/* floats per resident row: dim + optimizer state (emb_entry.rs:17-25 `inner`). */
+int pb_table_entry_len(pb_table* t, uint32_t* h_out);
+/* counters since creation: [0] rows admitted, [1] lookups that missed (infer) or were not admitted,
+ * [2] gradient ids not found (gradient_id_miss_count), [3] admissions refused because the shard is full.
+ * Synchronises `stream`. */
+int pb_table_counters(pb_table* t, uint64_t h_out[4], void* stream);
+
+/* ---- single-request entry points (the PS RPCs) ------------------------------------------------- */
+/* lookup_mixed -> batched_lookup (embedding_parameter_service/mod.rs:162-262, 344-357).
+ * d_signs[n] -> d_out[n*dim] f32.  training!=0: hit refreshes recency, miss admits + initialises;
+ * training==0: read-only, zeros on miss. */
+int pb_lookup(pb_table* t, const uint64_t* d_signs, uint32_t n, int training, float* d_out, void* stream);
+/* update_gradient_mixed (embedding_parameter_service/mod.rs:359-427): one optimizer step per sign in
+ * request order, d_grads[n*dim] f32; absent signs are counted and skipped.  Signs must be distinct
+ * within one call (the EW sends each sign once per slot; see pb_backward for the batched form). */
+int pb_update(pb_table* t, const uint64_t* d_signs, const float* d_grads, uint32_t n, void* stream);
+/* set_embedding (embedding_parameter_service/mod.rs:287-306; persia-core/src/lib.rs:433-449):
+ * d_entries[n*entry_len] = emb ++ optimizer state. */
+int pb_set_rows(pb_table* t, const uint64_t* d_signs, const float* d_entries, uint32_t n, void* stream);
+/* debug read-back of full entries (zeros + found=0 when absent); does not touch recency. */
+int pb_get_rows(pb_table* t, const uint64_t* d_signs, uint32_t n, float* d_entries, uint8_t* d_found, void* stream);
+
+/* ---- id preprocessing (the EW's lookup_batched_all_slots_preprocess) --------------------------- */
+/* indices_add_prefix (embedding_worker_service/mod.rs:402-429): out[i] = ids[i] % spacing + prefix of
+ * the slot owning occurrence i; h_slot_occ_off[n_slots+1] are the slot boundaries in the flat id array. */
+int pb_add_prefix(const uint64_t* d_ids, uint32_t n, const uint32_t* h_slot_occ_off, const uint64_t* h_prefix,
+                  uint32_t n_slots, uint32_t prefix_bit, uint64_t* d_out, void* stream);
+/* sign_to_shard_modulo (embedding_worker_service/mod.rs:341-345): farmhash64(sign LE bytes) % R. */
+int pb_shard_of(const uint64_t* d_signs, uint32_t n, uint32_t R, uint32_t* d_shard, void* stream);
+/* farmhash64 of each 8-byte little-endian value (hash-stack building block, :364). */
+int pb_farmhash64(const uint64_t* d_in, uint32_t n, uint64_t* d_out, void* stream);
+/* indices_to_sharded_indices (embedding_worker_service/mod.rs:454-479) as a stable partition:
+ * d_perm[n] lists input positions grouped by shard (input order kept inside a shard),
+ * d_counts[R] the group sizes.  d_work: pb_partition_workspace(n) bytes. */
+int pb_partition_by_shard(const uint64_t* d_signs, uint32_t n, uint32_t R, uint32_t* d_perm, uint32_t* d_counts,
+                          void* d_work, uint64_t work_bytes, void* stream);
+uint64_t pb_partition_workspace(uint32_t n);
+
+/* ---- batched path: forward_batched_direct / update_gradient_batched ---------------------------- */
+/* Slot semantics of one batch stream (persia-embedding-config/src/lib.rs:528-550). */
+typedef struct {
+  uint32_t n_slots;
+  uint32_t prefix_bit;               /* feature_index_prefix_bit */
+  uint64_t prefix[PB_MAX_SLOTS];     /* SlotConfig.index_prefix (0 = none) */
+  uint8_t sqrt_scaling[PB_MAX_SLOTS];
+} pb_slots_cfg;
+
+int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, pb_ctx** out);
+int pb_ctx_destroy(pb_ctx* c);
+int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg);
+
+/* EmbeddingWorker::forward_batched_direct for summation slots
+ * (embedding_worker_service/mod.rs:1076-1107 -> :874-942 -> PS :162-262 -> :486-629).
+ * d_ids: flat raw ids, slot-major then sample-major; d_row_off[n_slots*batch+1] CSR offsets, or NULL
+ * when every sample holds exactly one id per slot (then n_occ == n_slots*batch).
+ * h_slot_occ_off[n_slots+1]: slot boundaries in d_ids.  d_out: n_slots*batch rows of `dim` f16
+ * (slot s, sample b at row s*batch+b).  training!=0 keeps the deduplicated ids in `c` for pb_backward. */
+int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
+               const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream);
+
+/* EmbeddingWorker::update_gradient_batched (embedding_worker_service/mod.rs:1109-1129 -> :703-872 ->
+ * PS :359-427).  h_grads[s]: device pointer to slot s's [batch, dim] gradient (GradientBatch::add_gradient,
+ * persia-core/src/backward.rs:86-105), NULL = add_skipped_gradient; is_f16 as there; h_scale[s] the loss
+ * scale.  A slot whose gradient holds a NaN is skipped whole (:731-746); d_slot_status[n_slots] (optional)
+ * receives 0 applied / 1 skipped / 2 NaN. */
+int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, const float* h_scale,
+                int32_t* d_slot_status, void* stream);
+
+/* Number of kernels the library has launched on behalf of the caller since load (bench bookkeeping). */
+uint64_t pb_launch_count(void);
+/* Bench instrumentation: when enabled every kernel launch is bracketed by CUDA events on its stream.
+ * pb_profile_read synchronises the device and returns summed milliseconds and launch counts per kernel
+ * family: 0 probe/admit, 1 row init, 2 gather+pool, 3 NaN scan, 4 radix grouping, 5 reduce+update, 6 other. */
+#define PB_PROFILE_FAMILIES 7
+int pb_profile_enable(int on);
+int pb_profile_read(double* h_ms, uint64_t* h_count, int n_families);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERSIA_B200_H_ */

@@ -26,6 +26,7 @@
 //        (-ffp-contract=off matters: Rust never contracts a*b+c into an FMA.)
 
 #include <immintrin.h>
+#include <malloc.h>
 
 #include <algorithm>
 #include <atomic>
@@ -1055,6 +1056,9 @@ int po_worker_backward(void* w, void* ctx, const void* grads, int is_f16, const 
 double po_worker_bench(void* w, const uint64_t* ids, const uint32_t* row_off, uint32_t B, uint64_t ids_per_batch,
                        uint32_t n_batches, const uint16_t* grads_f16, uint32_t n_threads) {
   auto* W = (Worker*)w;
+  // keep the per-request arrays in the heap instead of fresh mmaps (page-fault storms would handicap the baseline)
+  static bool tuned = (mallopt(M_MMAP_THRESHOLD, 32 << 20), mallopt(M_TRIM_THRESHOLD, 1 << 30), true);
+  (void)tuned;
   size_t out_elems = 0;
   for (auto& s : W->slots) out_elems += (size_t)B * s.dim;
   std::atomic<uint32_t> next{0};

@@ -1,0 +1,610 @@
+// pb_api.cu — the C ABI of libpersia_b200.so (include/persia_b200.h): object lifetime, argument checks,
+// kernel sequencing.  No torch types, no allocation on the hot path after the first call of a given size.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "pb_kernels.cuh"
+
+using namespace pb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PB_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(PB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+uint32_t next_pow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return (uint32_t)p;
+}
+
+// rand 0.8 UniformFloat::new: shrink the scale until the largest draw stays below `hi`
+float uniform_scale(float lo, float hi) {
+  float scale = hi - lo;
+  uint32_t mb = (0xFFFFFFFFu >> 9) | 0x3f800000u;
+  float max_rand;
+  std::memcpy(&max_rand, &mb, 4);
+  max_rand -= 1.0f;
+  if (!(hi > lo)) return 0.0f;
+  while (!(scale * max_rand + lo < hi)) {
+    uint32_t b;
+    std::memcpy(&b, &scale, 4);
+    b -= 1;
+    std::memcpy(&scale, &b, 4);
+  }
+  return scale;
+}
+
+}  // namespace
+
+struct pb_table {
+  int device = 0;
+  pb_table_cfg cfg{};
+  OptimDev op{};
+  bool has_op = false;
+  HyperDev hy{};
+  bool has_hy = false;
+  TableDev d{};
+  bool allocated = false;
+  uint32_t* scratch = nullptr;  // index cells of a single-request call
+  uint32_t scratch_cap = 0;
+  float b1p[PB_MAX_SLOTS], b2p[PB_MAX_SLOTS];  // Adam: accumulated beta powers per slot (optim.rs:155-197)
+  float b1p_direct = 1.0f, b2p_direct = 1.0f;
+};
+
+struct pb_ctx {
+  int device = 0;
+  uint32_t max_occ = 0, max_out = 0;
+  pb_slots_cfg slots{};
+  bool has_slots = false;
+  // forward -> backward state (the EW's post_forward_buffer entry, mod.rs:1087-1098)
+  uint32_t* occ_cell = nullptr;
+  uint8_t* occ_slot = nullptr;
+  uint32_t* occ_outrow = nullptr;
+  uint32_t* row_off = nullptr;
+  bool multi_id = false;
+  uint32_t n_occ = 0, batch = 0;
+  uint32_t* dev_tick = nullptr;  // batch number of the pending forward
+  uint32_t occ_off[PB_MAX_SLOTS + 1];
+  bool pending = false;
+  // backward workspace
+  uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *hist = nullptr;
+  uint32_t* nan_tick = nullptr;
+  float* vw_stage = nullptr;
+  size_t vw_stage_floats = 0;
+};
+
+namespace {
+
+int ensure_alloc(pb_table* t) {
+  if (t->allocated) return PB_OK;
+  if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered (OptimizerNotFoundError)");
+  uint32_t dim = t->cfg.dim;
+  uint32_t state = 0;
+  switch (t->op.kind) {
+    case PB_OPT_ADAGRAD: state = dim; break;
+    case PB_OPT_ADAGRAD_VW: state = 1; break;
+    case PB_OPT_ADAM: state = 2 * dim; break;
+    default: state = 0;
+  }
+  TableDev& d = t->d;
+  d.dim = dim;
+  d.state_floats = state;
+  d.stride = (dim + state + 3u) & ~3u;
+  if (t->cfg.capacity >= 0xFFFFFFF0ull) return fail(PB_ERR_INVALID, "capacity must be < 2^32 - 16 rows per shard");
+  d.capacity = (uint32_t)t->cfg.capacity;
+  uint64_t want = (uint64_t)d.capacity + d.capacity / 2;
+  if (want < 1024) want = 1024;
+  if (want > (1ull << 31)) return fail(PB_ERR_INVALID, "capacity too large for a 2^31-cell index");
+  d.n_cells = next_pow2(want);
+  d.cell_mask = d.n_cells - 1;
+  d.new_list_cap = d.capacity < (1u << 22) ? d.capacity : (1u << 22);
+  if (d.new_list_cap < 1024) d.new_list_cap = 1024;
+  PB_CUDA(cudaMalloc(&d.cells, sizeof(Cell) * ((size_t)d.n_cells + 1)));
+  PB_CUDA(cudaMalloc(&d.rows, sizeof(float) * (size_t)d.capacity * d.stride));
+  PB_CUDA(cudaMalloc(&d.counters, sizeof(uint32_t) * CTR_COUNT));
+  PB_CUDA(cudaMalloc(&d.new_list, sizeof(uint32_t) * (size_t)d.new_list_cap));
+  PB_CUDA(cudaMemset(d.counters, 0, sizeof(uint32_t) * CTR_COUNT));
+  launch_fill_cells(d.cells, (uint64_t)d.n_cells + 1, 0);
+  PB_CUDA(cudaDeviceSynchronize());
+  t->allocated = true;
+  return PB_OK;
+}
+
+int ensure_scratch(pb_table* t, uint32_t n) {
+  if (n <= t->scratch_cap) return PB_OK;
+  if (t->scratch) cudaFree(t->scratch);
+  t->scratch = nullptr;
+  t->scratch_cap = 0;
+  uint32_t cap = next_pow2(n);
+  PB_CUDA(cudaMalloc(&t->scratch, sizeof(uint32_t) * (size_t)cap));
+  t->scratch_cap = cap;
+  return PB_OK;
+}
+
+int ensure_new_list(pb_table* t, uint32_t n, cudaStream_t st) {
+  if (n <= t->d.new_list_cap) return PB_OK;
+  PB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(t->d.new_list);
+  t->d.new_list = nullptr;
+  uint32_t cap = next_pow2(n);
+  PB_CUDA(cudaMalloc(&t->d.new_list, sizeof(uint32_t) * (size_t)cap));
+  t->d.new_list_cap = cap;
+  return PB_OK;
+}
+
+int ready_for_training(pb_table* t) {
+  if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered (OptimizerNotFoundError)");
+  if (!t->has_hy) return fail(PB_ERR_STATE, "embedding server not configured (NotConfiguredError)");
+  return PB_OK;
+}
+
+SlotsDev no_slots() {
+  SlotsDev s;
+  std::memset(&s, 0, sizeof(s));
+  s.n_slots = 1;
+  s.spacing = ~0ULL;
+  return s;
+}
+
+int make_slots(const pb_slots_cfg& cfg, const uint32_t* h_occ_off, SlotsDev& s) {
+  std::memset(&s, 0, sizeof(s));
+  if (cfg.n_slots == 0 || cfg.n_slots > PB_MAX_SLOTS) return fail(PB_ERR_INVALID, "n_slots must be in 1..PB_MAX_SLOTS");
+  s.n_slots = cfg.n_slots;
+  s.spacing = cfg.prefix_bit > 0 ? ((1ULL << (64 - cfg.prefix_bit)) - 1) : ~0ULL;
+  for (uint32_t i = 0; i < cfg.n_slots; ++i) {
+    s.prefix[i] = cfg.prefix[i];
+    s.sqrt_scaling[i] = cfg.sqrt_scaling[i];
+    s.occ_off[i] = h_occ_off[i];
+  }
+  s.occ_off[cfg.n_slots] = h_occ_off[cfg.n_slots];
+  return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pb_last_error(void) { return g_err.c_str(); }
+int pb_version(void) { return 100; }
+uint64_t pb_launch_count(void) { return launch_count(); }
+int pb_profile_enable(int on) {
+  profile_enable(on != 0);
+  return PB_OK;
+}
+int pb_profile_read(double* h_ms, uint64_t* h_count, int n) {
+  if (!h_ms || !h_count || n <= 0) return fail(PB_ERR_INVALID, "bad argument");
+  PB_CUDA(cudaDeviceSynchronize());
+  profile_read(h_ms, h_count, n < FAM_COUNT ? n : FAM_COUNT);
+  for (int i = FAM_COUNT; i < n; ++i) {
+    h_ms[i] = 0;
+    h_count[i] = 0;
+  }
+  return PB_OK;
+}
+
+int pb_table_create(int device, const pb_table_cfg* cfg, pb_table** out) {
+  if (!cfg || !out) return fail(PB_ERR_INVALID, "null argument");
+  if (cfg->dim == 0 || cfg->dim > 4096) return fail(PB_ERR_INVALID, "dim must be in 1..4096");
+  if (cfg->capacity == 0) return fail(PB_ERR_INVALID, "capacity must be > 0");
+  int ndev = 0;
+  PB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(PB_ERR_INVALID, "no such CUDA device");
+  pb_table* t = new pb_table();
+  t->device = device;
+  t->cfg = *cfg;
+  for (int i = 0; i < PB_MAX_SLOTS; ++i) t->b1p[i] = t->b2p[i] = 1.0f;
+  *out = t;
+  return PB_OK;
+}
+
+int pb_table_destroy(pb_table* t) {
+  if (!t) return PB_OK;
+  DeviceGuard g(t->device);
+  if (t->allocated) {
+    cudaDeviceSynchronize();
+    cudaFree(t->d.cells);
+    cudaFree(t->d.rows);
+    cudaFree(t->d.counters);
+    cudaFree(t->d.new_list);
+  }
+  if (t->scratch) cudaFree(t->scratch);
+  delete t;
+  return PB_OK;
+}
+
+int pb_table_set_optimizer(pb_table* t, const pb_optim_cfg* c) {
+  if (!t || !c) return fail(PB_ERR_INVALID, "null argument");
+  if (c->kind < PB_OPT_SGD || c->kind > PB_OPT_ADAM) return fail(PB_ERR_INVALID, "unknown optimizer kind");
+  if (t->allocated && c->kind != t->op.kind)
+    return fail(PB_ERR_STATE, "optimizer kind cannot change once rows are resident (row layout is fixed)");
+  t->op.kind = c->kind;
+  t->op.lr = c->lr;
+  t->op.wd = c->wd;
+  t->op.mom = c->g_square_momentum;
+  t->op.init_acc = c->initialization;
+  t->op.eps = c->eps;
+  t->op.b1 = c->beta1;
+  t->op.b2 = c->beta2;
+  if (!t->has_op) {
+    for (int i = 0; i < PB_MAX_SLOTS; ++i) {  // AdamPowerOfBetas starts at (beta1, beta2) (optim.rs:118-124)
+      t->b1p[i] = c->beta1;
+      t->b2p[i] = c->beta2;
+    }
+    t->b1p_direct = c->beta1;
+    t->b2p_direct = c->beta2;
+  }
+  t->has_op = true;
+  return PB_OK;
+}
+
+int pb_table_configure(pb_table* t, const pb_hyper_cfg* c) {
+  if (!t || !c) return fail(PB_ERR_INVALID, "null argument");
+  t->hy.lo = c->init_lower;
+  t->hy.scale = uniform_scale(c->init_lower, c->init_upper);
+  t->hy.admit_p = c->admit_probability;
+  t->hy.enable_wb = c->enable_weight_bound;
+  t->hy.wb = c->weight_bound;
+  t->has_hy = true;
+  return PB_OK;
+}
+
+int pb_table_entry_len(pb_table* t, uint32_t* h_out) {
+  if (!t || !h_out) return fail(PB_ERR_INVALID, "null argument");
+  if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered");
+  uint32_t dim = t->cfg.dim;
+  *h_out = dim + (t->op.kind == PB_OPT_ADAGRAD ? dim : t->op.kind == PB_OPT_ADAGRAD_VW ? 1 : t->op.kind == PB_OPT_ADAM ? 2 * dim : 0);
+  return PB_OK;
+}
+
+int pb_table_counters(pb_table* t, uint64_t h_out[4], void* stream) {
+  if (!t || !h_out) return fail(PB_ERR_INVALID, "null argument");
+  h_out[0] = h_out[1] = h_out[2] = h_out[3] = 0;
+  if (!t->allocated) return PB_OK;
+  DeviceGuard g(t->device);
+  uint32_t c[CTR_COUNT];
+  PB_CUDA(cudaMemcpyAsync(c, t->d.counters, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  h_out[0] = c[CTR_ADMIT];
+  h_out[1] = c[CTR_MISS];
+  h_out[2] = c[CTR_GRAD_MISS];
+  h_out[3] = c[CTR_FULL];
+  return PB_OK;
+}
+
+int pb_table_size(pb_table* t, uint64_t* h_out, void* stream) {
+  if (!t || !h_out) return fail(PB_ERR_INVALID, "null argument");
+  uint64_t c[4];
+  int rc = pb_table_counters(t, c, stream);
+  if (rc) return rc;
+  *h_out = c[0];
+  return PB_OK;
+}
+
+int pb_table_clear(pb_table* t, void* stream) {
+  if (!t) return fail(PB_ERR_INVALID, "null argument");
+  if (!t->allocated) return PB_OK;
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_fill_cells(t->d.cells, (uint64_t)t->d.n_cells + 1, st);
+  PB_CUDA(cudaMemsetAsync(t->d.counters, 0, sizeof(uint32_t) * CTR_COUNT, st));
+  return PB_OK;
+}
+
+int pb_lookup(pb_table* t, const uint64_t* d_signs, uint32_t n, int training, float* d_out, void* stream) {
+  if (!t || (n && (!d_signs || !d_out))) return fail(PB_ERR_INVALID, "null argument");
+  if (training) {
+    int rc = ready_for_training(t);
+    if (rc) return rc;
+  } else if (!t->has_op) {  // nothing can be resident yet: zeros
+    DeviceGuard g(t->device);
+    PB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)n * t->cfg.dim, (cudaStream_t)stream));
+    return PB_OK;
+  }
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_alloc(t);
+  if (rc) return rc;
+  if ((rc = ensure_scratch(t, n))) return rc;
+  SlotsDev sl = no_slots();
+  if (training) {
+    if ((rc = ensure_new_list(t, n, st))) return rc;
+    launch_begin_batch(t->d, nullptr, st);
+    launch_probe(MODE_TRAIN, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+    launch_init_new(t->d, t->hy, t->op, n, st);
+  } else {
+    launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+  }
+  launch_gather(t->d, sl, t->scratch, nullptr, n, 0, d_out, true, st);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_update(pb_table* t, const uint64_t* d_signs, const float* d_grads, uint32_t n, void* stream) {
+  if (!t || (n && (!d_signs || !d_grads))) return fail(PB_ERR_INVALID, "null argument");
+  int rc = ready_for_training(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_alloc(t))) return rc;
+  if ((rc = ensure_scratch(t, n))) return rc;
+  SlotsDev sl = no_slots();
+  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+  if (t->op.kind == PB_OPT_ADAM) {  // get_batch_level_state: one power step per request (optim.rs:155-197)
+    t->b1p_direct *= t->op.b1;
+    t->b2p_direct *= t->op.b2;
+  }
+  launch_update_direct(t->d, t->op, t->hy, t->scratch, d_grads, n, t->b1p_direct, t->b2p_direct, st);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_set_rows(pb_table* t, const uint64_t* d_signs, const float* d_entries, uint32_t n, void* stream) {
+  if (!t || (n && (!d_signs || !d_entries))) return fail(PB_ERR_INVALID, "null argument");
+  if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered: entry length unknown");
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_alloc(t);
+  if (rc) return rc;
+  if ((rc = ensure_scratch(t, n))) return rc;
+  SlotsDev sl = no_slots();
+  launch_probe(MODE_SET, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+  launch_copy_entries(true, t->d, t->scratch, n, const_cast<float*>(d_entries), nullptr, st);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_get_rows(pb_table* t, const uint64_t* d_signs, uint32_t n, float* d_entries, uint8_t* d_found, void* stream) {
+  if (!t || (n && (!d_signs || !d_entries))) return fail(PB_ERR_INVALID, "null argument");
+  if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered: entry length unknown");
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_alloc(t);
+  if (rc) return rc;
+  if ((rc = ensure_scratch(t, n))) return rc;
+  SlotsDev sl = no_slots();
+  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+  launch_copy_entries(false, t->d, t->scratch, n, d_entries, d_found, st);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_add_prefix(const uint64_t* d_ids, uint32_t n, const uint32_t* h_slot_occ_off, const uint64_t* h_prefix,
+                  uint32_t n_slots, uint32_t prefix_bit, uint64_t* d_out, void* stream) {
+  if (n && (!d_ids || !d_out)) return fail(PB_ERR_INVALID, "null argument");
+  if (!h_slot_occ_off || !h_prefix) return fail(PB_ERR_INVALID, "null argument");
+  pb_slots_cfg cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.n_slots = n_slots;
+  cfg.prefix_bit = prefix_bit;
+  if (n_slots == 0 || n_slots > PB_MAX_SLOTS) return fail(PB_ERR_INVALID, "n_slots must be in 1..PB_MAX_SLOTS");
+  for (uint32_t i = 0; i < n_slots; ++i) cfg.prefix[i] = h_prefix[i];
+  SlotsDev sl;
+  int rc = make_slots(cfg, h_slot_occ_off, sl);
+  if (rc) return rc;
+  launch_add_prefix(sl, d_ids, n, d_out, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_shard_of(const uint64_t* d_signs, uint32_t n, uint32_t R, uint32_t* d_shard, void* stream) {
+  if (n && (!d_signs || !d_shard)) return fail(PB_ERR_INVALID, "null argument");
+  if (R == 0) return fail(PB_ERR_INVALID, "replica size must be > 0");
+  launch_shard_of(d_signs, n, R, d_shard, nullptr, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_farmhash64(const uint64_t* d_in, uint32_t n, uint64_t* d_out, void* stream) {
+  if (n && (!d_in || !d_out)) return fail(PB_ERR_INVALID, "null argument");
+  launch_shard_of(d_in, n, 1, nullptr, d_out, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+uint64_t pb_partition_workspace(uint32_t n) {
+  uint32_t tile = radix_tile(n ? n : 1);
+  uint32_t nb = (uint32_t)(((uint64_t)(n ? n : 1) + tile - 1) / tile);
+  return (uint64_t)256 * nb * sizeof(uint32_t);
+}
+
+int pb_partition_by_shard(const uint64_t* d_signs, uint32_t n, uint32_t R, uint32_t* d_perm, uint32_t* d_counts,
+                          void* d_work, uint64_t work_bytes, void* stream) {
+  if ((n && (!d_signs || !d_perm)) || !d_counts || !d_work) return fail(PB_ERR_INVALID, "null argument");
+  if (R == 0 || R > 256) return fail(PB_ERR_INVALID, "replica size must be in 1..256");
+  if (work_bytes < pb_partition_workspace(n)) return fail(PB_ERR_CAPACITY, "workspace smaller than pb_partition_workspace(n)");
+  launch_partition_by_shard(d_signs, n, R, d_perm, d_counts, (uint32_t*)d_work, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, pb_ctx** out) {
+  if (!out || max_occurrences == 0 || max_out_rows == 0) return fail(PB_ERR_INVALID, "bad argument");
+  DeviceGuard g(device);
+  pb_ctx* c = new pb_ctx();
+  c->device = device;
+  c->max_occ = max_occurrences;
+  c->max_out = max_out_rows;
+  size_t n = max_occurrences;
+  uint32_t tile = radix_tile(max_occurrences);
+  size_t nb = (n + tile - 1) / tile;
+  // smaller batches pick smaller tiles: size the histogram for the worst case (n/2048 tiles, capped at 128)
+  size_t hist_elems = 256 * (nb > 128 ? nb : 128);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  A((void**)&c->occ_cell, 4 * n);
+  A((void**)&c->occ_slot, n);
+  A((void**)&c->occ_outrow, 4 * n);
+  A((void**)&c->row_off, 4 * ((size_t)max_out_rows + 1));
+  A((void**)&c->keys_a, 4 * n);
+  A((void**)&c->vals_a, 4 * n);
+  A((void**)&c->keys_b, 4 * n);
+  A((void**)&c->vals_b, 4 * n);
+  A((void**)&c->hist, 4 * hist_elems);
+  A((void**)&c->nan_tick, 4 * PB_MAX_SLOTS);
+  A((void**)&c->dev_tick, 4);
+  if (e == cudaSuccess) e = cudaMemset(c->nan_tick, 0, 4 * PB_MAX_SLOTS);
+  if (e == cudaSuccess) e = cudaMemset(c->dev_tick, 0, 4);
+  if (e != cudaSuccess) {
+    pb_ctx_destroy(c);
+    return fail(PB_ERR_CUDA, std::string("pb_ctx_create: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return PB_OK;
+}
+
+int pb_ctx_destroy(pb_ctx* c) {
+  if (!c) return PB_OK;
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {c->occ_cell, c->occ_slot, c->occ_outrow, c->row_off, c->keys_a, c->vals_a,
+                  c->keys_b,   c->vals_b,   c->hist,       c->nan_tick, c->vw_stage, c->dev_tick};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete c;
+  return PB_OK;
+}
+
+int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg) {
+  if (!c || !cfg) return fail(PB_ERR_INVALID, "null argument");
+  if (cfg->n_slots == 0 || cfg->n_slots > PB_MAX_SLOTS) return fail(PB_ERR_INVALID, "n_slots must be in 1..PB_MAX_SLOTS");
+  if (cfg->prefix_bit == 0 || cfg->prefix_bit > 63)  // parse_embedding_config asserts > 0 (config lib.rs:624-627)
+    return fail(PB_ERR_INVALID, "feature_index_prefix_bit must be in 1..63");
+  c->slots = *cfg;
+  c->has_slots = true;
+  return PB_OK;
+}
+
+int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
+               const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream) {
+  if (!t || !c || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
+  if (!c->has_slots) return fail(PB_ERR_STATE, "pb_ctx_set_slots not called");
+  if (t->device != c->device) return fail(PB_ERR_INVALID, "table and context live on different devices");
+  if (batch > 65535) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
+  uint32_t S = c->slots.n_slots;
+  uint64_t n_out = (uint64_t)S * batch;
+  if (n_occ > c->max_occ || n_out > c->max_out) return fail(PB_ERR_CAPACITY, "batch exceeds the context's capacity");
+  if (!d_row_off && n_occ != n_out) return fail(PB_ERR_INVALID, "row offsets are required unless every sample has one id per slot");
+  if (h_slot_occ_off[0] != 0 || h_slot_occ_off[S] != n_occ) return fail(PB_ERR_INVALID, "slot offsets do not span the id array");
+  for (uint32_t s = 0; s < S; ++s)
+    if (h_slot_occ_off[s] > h_slot_occ_off[s + 1]) return fail(PB_ERR_INVALID, "slot offsets must ascend");
+  int rc;
+  if (training) {
+    if ((rc = ready_for_training(t))) return rc;
+  } else if (!t->has_op) {
+    DeviceGuard g(t->device);
+    PB_CUDA(cudaMemsetAsync(d_out_f16, 0, 2 * n_out * t->cfg.dim, (cudaStream_t)stream));
+    return PB_OK;
+  }
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_alloc(t))) return rc;
+  SlotsDev sl;
+  if ((rc = make_slots(c->slots, h_slot_occ_off, sl))) return rc;
+  if (training) {
+    if ((rc = ensure_new_list(t, n_occ, st))) return rc;
+    launch_begin_batch(t->d, c->dev_tick, st);
+    launch_probe(MODE_TRAIN, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, c->occ_slot, st);
+    launch_init_new(t->d, t->hy, t->op, n_occ, st);
+  } else {
+    launch_probe(MODE_FIND, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, c->occ_slot, st);
+  }
+  launch_gather(t->d, sl, c->occ_cell, d_row_off, (uint32_t)n_out, batch, d_out_f16, false, st);
+  if (training) {
+    c->n_occ = n_occ;
+    c->batch = batch;
+    c->multi_id = d_row_off != nullptr;
+    std::memcpy(c->occ_off, h_slot_occ_off, sizeof(uint32_t) * (S + 1));
+    if (d_row_off) {
+      PB_CUDA(cudaMemcpyAsync(c->row_off, d_row_off, 4 * (n_out + 1), cudaMemcpyDeviceToDevice, st));
+      launch_expand_rows(c->row_off, (uint32_t)n_out, c->occ_outrow, st);
+    }
+    c->pending = true;
+  }
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, const float* h_scale,
+                int32_t* d_slot_status, void* stream) {
+  if (!t || !c || !h_grads) return fail(PB_ERR_INVALID, "null argument");
+  if (!c->pending) return fail(PB_ERR_STATE, "no forward batch is pending in this context (backward_ref_id not found)");
+  int rc = ready_for_training(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t S = c->slots.n_slots;
+  SlotsDev sl;
+  if ((rc = make_slots(c->slots, c->occ_off, sl))) return rc;
+  GradsDev gr;
+  std::memset(&gr, 0, sizeof(gr));
+  for (uint32_t s = 0; s < S; ++s) {
+    gr.ptr[s] = h_grads[s];
+    float sc = h_scale ? h_scale[s] : 1.0f;
+    gr.do_scale[s] = std::fabs(sc - 1.0f) > 1.1920929e-07f;
+    float inv = 1.0f / sc;
+    if (gr.do_scale[s] && !std::isfinite(inv)) return fail(PB_ERR_INVALID, "scale on gradient must be finite");
+    gr.inv_scale[s] = inv;
+    if (t->op.kind == PB_OPT_ADAM && h_grads[s]) {  // one power step per request and feature group
+      t->b1p[s] *= t->op.b1;
+      t->b2p[s] *= t->op.b2;
+    }
+    gr.b1p[s] = t->b1p[s];
+    gr.b2p[s] = t->b2p[s];
+  }
+  uint32_t elems = c->batch * t->d.dim;
+  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
+  uint32_t bits = 1;
+  while ((1ull << bits) <= (uint64_t)t->d.n_cells + 1) ++bits;
+  int which = launch_radix_sort_u32(c->occ_cell, c->n_occ, bits, c->keys_a, c->vals_a, c->keys_b, c->vals_b, c->hist, st);
+  const uint32_t* skey = which == 0 ? c->keys_a : c->keys_b;
+  const uint32_t* socc = which == 0 ? c->vals_a : c->vals_b;
+  float* vw = nullptr;
+  if (t->op.kind == PB_OPT_ADAGRAD_VW) {
+    size_t need = (size_t)c->n_occ * t->d.dim;
+    if (need > c->vw_stage_floats) {
+      PB_CUDA(cudaStreamSynchronize(st));
+      if (c->vw_stage) cudaFree(c->vw_stage);
+      c->vw_stage = nullptr;
+      c->vw_stage_floats = 0;
+      PB_CUDA(cudaMalloc(&c->vw_stage, sizeof(float) * need));
+      c->vw_stage_floats = need;
+    }
+    vw = c->vw_stage;
+  }
+  launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, skey, socc, c->occ_slot,
+                       c->multi_id ? c->occ_outrow : nullptr, c->multi_id ? c->row_off : nullptr, c->n_occ, c->batch,
+                       c->dev_tick, c->nan_tick, vw, st);
+  c->pending = false;
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+}  // extern "C"

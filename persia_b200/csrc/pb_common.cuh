@@ -1,0 +1,83 @@
+// pb_common.cuh — shared device helpers for libpersia_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "persia_b200.h"
+
+namespace pb {
+
+constexpr uint64_t KEY_EMPTY = ~0ULL;          // hash-index cell holds no key
+constexpr uint32_t ROW_PENDING = 0xFFFFFFFFu;  // key claimed, row not yet published (never visible across kernels)
+constexpr uint32_t ROW_NONE = 0xFFFFFFFEu;     // key present but no storage (shard was full when it was admitted)
+
+// One cell of the open-addressing index: 16 B, one 32 B sector holds two.
+struct __align__(16) Cell {
+  unsigned long long key;
+  uint32_t row;
+  uint32_t tick;  // batch number of the last training touch (recency for eviction)
+};
+
+// farmhash 1.1.5 hash64 of an 8-byte LE value (FarmHash HashLen0to16, 8..16 branch).
+// Reference call sites: embedding_worker_service/mod.rs:341-345, :364.  Bit-exact.
+__host__ __device__ __forceinline__ uint64_t farmhash64_u64(uint64_t x) {
+  const uint64_t k2 = 0x9ae16a3b2f90404fULL;
+  const uint64_t mul = k2 + 16;
+  uint64_t a = x + k2;
+  uint64_t b = x;
+  uint64_t c = ((b >> 37) | (b << 27)) * mul + a;
+  uint64_t d = (((a >> 25) | (a << 39)) + b) * mul;
+  uint64_t h = (c ^ d) * mul;
+  h ^= (h >> 47);
+  uint64_t g = (d ^ h) * mul;
+  g ^= (g >> 47);
+  return g * mul;
+}
+
+// placement hash inside a shard (independent of the shard-selection hash above)
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+
+struct TableDev {
+  Cell* cells;         // n_cells + 1 entries; the last one is reserved for sign == KEY_EMPTY
+  float* rows;         // capacity * stride floats: emb(dim) ++ optimizer state ++ pad
+  uint32_t* counters;  // see CTR_* below
+  uint32_t* new_list;  // cells admitted by the running request
+  uint64_t cell_mask;  // n_cells - 1
+  uint32_t n_cells;
+  uint32_t capacity;
+  uint32_t dim, stride, state_floats;
+  uint32_t new_list_cap;
+};
+
+enum {
+  CTR_ROWS = 0,      // bump allocator of row storage
+  CTR_NEW = 1,       // cells admitted by the current request (reset by k_begin_batch)
+  CTR_TICK = 2,      // batch number: bumped on the device by every training request (CUDA-graph safe)
+  CTR_MISS = 3,      // infer misses / refused admissions
+  CTR_GRAD_MISS = 4, // gradient ids not found
+  CTR_FULL = 5,      // admissions refused for lack of capacity
+  CTR_ADMIT = 6,     // rows admitted
+  CTR_COUNT = 8
+};
+
+struct OptimDev {
+  int kind;
+  float lr, wd, mom, init_acc, eps, b1, b2;
+};
+
+struct HyperDev {
+  float lo, scale;  // init = u01 * scale + lo (scale from rand's UniformFloat::new loop)
+  float admit_p;
+  int enable_wb;
+  float wb;
+};
+
+}  // namespace pb

@@ -1,0 +1,58 @@
+// pb_kernels.cuh — kernel-side parameter blocks and launcher prototypes (internal).
+#pragma once
+#include <atomic>
+
+#include "pb_common.cuh"
+
+namespace pb {
+
+// per-batch slot table, passed by value in kernel-parameter memory
+struct SlotsDev {
+  uint64_t prefix[PB_MAX_SLOTS];
+  uint32_t occ_off[PB_MAX_SLOTS + 1];  // slot boundaries in the flat id array
+  uint8_t sqrt_scaling[PB_MAX_SLOTS];
+  uint32_t n_slots;
+  uint64_t spacing;  // 2^(64-prefix_bit) - 1
+};
+
+// per-batch gradient table (GradientBatch, persia-core/src/backward.rs:74-106)
+struct GradsDev {
+  const void* ptr[PB_MAX_SLOTS];  // nullptr = skipped slot
+  float inv_scale[PB_MAX_SLOTS];  // 1/scale_factor
+  uint8_t do_scale[PB_MAX_SLOTS]; // |scale-1| > f32::EPSILON (mod.rs:751)
+  float b1p[PB_MAX_SLOTS], b2p[PB_MAX_SLOTS];  // Adam accumulated beta powers of the slot's feature group
+};
+
+void launch_fill_cells(Cell* cells, uint64_t n, cudaStream_t st);
+void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, cudaStream_t st);
+void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const SlotsDev& sl, const uint64_t* ids,
+                  uint32_t n, uint32_t* occ_cell, uint8_t* occ_slot, cudaStream_t st);
+void launch_init_new(const TableDev& t, const HyperDev& hy, const OptimDev& op, uint32_t max_new, cudaStream_t st);
+void launch_gather(const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell, const uint32_t* row_off,
+                   uint32_t n_out, uint32_t batch, void* out, bool out_f32, cudaStream_t st);
+void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell, uint32_t n, float* entries,
+                         uint8_t* found, cudaStream_t st);
+void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,
+                     uint32_t* nan_tick, int32_t* status, cudaStream_t st);
+void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
+                          const GradsDev& gr, bool f16, const uint32_t* skey, const uint32_t* socc,
+                          const uint8_t* occ_slot, const uint32_t* occ_outrow, const uint32_t* row_off, uint32_t n,
+                          uint32_t batch, const uint32_t* tick, const uint32_t* nan_tick, float* vw_stage, cudaStream_t st);
+void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
+                          const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st);
+uint32_t radix_tile(uint32_t n);
+int launch_radix_sort_u32(const uint32_t* keys_in, uint32_t n, uint32_t bits, uint32_t* keys_a, uint32_t* vals_a,
+                          uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, cudaStream_t st);
+void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* perm, uint32_t* counts,
+                               uint32_t* hist, cudaStream_t st);
+void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_outrow, cudaStream_t st);
+void launch_add_prefix(const SlotsDev& sl, const uint64_t* ids, uint32_t n, uint64_t* out, cudaStream_t st);
+void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st);
+uint64_t launch_count();
+enum { FAM_PROBE = 0, FAM_INIT, FAM_GATHER, FAM_NAN, FAM_SORT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
+void profile_enable(bool on);
+void profile_read(double* ms, uint64_t* count, int n_families);
+
+enum { MODE_FIND = 0, MODE_TRAIN = 1, MODE_SET = 2 };
+
+}  // namespace pb

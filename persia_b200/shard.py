@@ -1,0 +1,219 @@
+"""EmbeddingShard / BatchContext: thin torch-facing wrappers over the C ABI.
+
+`EmbeddingShard` is one embedding-parameter-server replica resident in one GPU's HBM
+(reference: rust/persia-embedding-server/src/embedding_parameter_service/mod.rs +
+rust/persia-embedding-holder).  `BatchContext` is what the embedding worker keeps between the forward
+and the backward of one batch (embedding_worker_service/mod.rs:1087-1119).  torch only owns device
+memory and the current stream here; all compute is in libpersia_b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import native as N
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _as_i64_bits(t):
+    """uint64 ids travel as int64 bit patterns inside torch (torch has no full uint64 support)."""
+    if t.dtype == torch.uint64:
+        t = t.view(torch.int64)
+    assert t.dtype == torch.int64, "ids must be uint64/int64 bit patterns"
+    return t.contiguous()
+
+
+class EmbeddingShard:
+    def __init__(self, dim, capacity, device=0):
+        self.lib = N.load()
+        self.dim, self.capacity = int(dim), int(capacity)
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        h = C.c_void_p()
+        cfg = N.TableCfg(self.dim, self.capacity)
+        N.check(self.lib.pb_table_create(self.device.index or 0, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self._entry_len = None
+
+    # register_optimizer (PS mod.rs:429-438)
+    def set_optimizer(self, kind, lr=0.01, wd=0.0, g_square_momentum=1.0, initialization=0.01, eps=1e-10,
+                      beta1=0.9, beta2=0.999):
+        cfg = N.OptimCfg(kind, lr, wd, g_square_momentum, initialization, eps, beta1, beta2)
+        N.check(self.lib.pb_table_set_optimizer(self.h, C.byref(cfg)))
+        self._entry_len = None
+
+    # configure (PS mod.rs:440-451)
+    def configure(self, init_lower=-0.01, init_upper=0.01, admit_probability=1.0, enable_weight_bound=True,
+                  weight_bound=10.0):
+        cfg = N.HyperCfg(init_lower, init_upper, admit_probability, int(enable_weight_bound), weight_bound)
+        N.check(self.lib.pb_table_configure(self.h, C.byref(cfg)))
+
+    @property
+    def entry_len(self):
+        if self._entry_len is None:
+            v = C.c_uint32()
+            N.check(self.lib.pb_table_entry_len(self.h, C.byref(v)))
+            self._entry_len = v.value
+        return self._entry_len
+
+    def counters(self):
+        out = (C.c_uint64 * 4)()
+        N.check(self.lib.pb_table_counters(self.h, C.byref(out), _stream(self.device)))
+        return {"admitted": out[0], "lookup_miss": out[1], "gradient_id_miss": out[2], "capacity_refused": out[3]}
+
+    def __len__(self):
+        return int(self.counters()["admitted"])
+
+    def clear(self):
+        N.check(self.lib.pb_table_clear(self.h, _stream(self.device)))
+
+    # lookup_mixed (PS mod.rs:344-357)
+    def lookup(self, signs, training=True, out=None):
+        signs = _as_i64_bits(signs)
+        n = signs.numel()
+        if out is None:
+            out = torch.empty((n, self.dim), dtype=torch.float32, device=self.device)
+        N.check(self.lib.pb_lookup(self.h, _ptr(signs), n, int(training), _ptr(out), _stream(self.device)))
+        return out
+
+    # update_gradient_mixed (PS mod.rs:359-427); signs must be distinct within one call
+    def update(self, signs, grads):
+        signs = _as_i64_bits(signs)
+        grads = grads.contiguous()
+        assert grads.dtype == torch.float32 and grads.numel() == signs.numel() * self.dim
+        N.check(self.lib.pb_update(self.h, _ptr(signs), _ptr(grads), signs.numel(), _stream(self.device)))
+
+    # set_embedding (PS mod.rs:287-306)
+    def set_entries(self, signs, entries):
+        signs = _as_i64_bits(signs)
+        entries = entries.contiguous()
+        assert entries.dtype == torch.float32 and entries.numel() == signs.numel() * self.entry_len
+        N.check(self.lib.pb_set_rows(self.h, _ptr(signs), _ptr(entries), signs.numel(), _stream(self.device)))
+
+    def get_entries(self, signs):
+        signs = _as_i64_bits(signs)
+        n = signs.numel()
+        ent = torch.empty((n, self.entry_len), dtype=torch.float32, device=self.device)
+        found = torch.empty(n, dtype=torch.uint8, device=self.device)
+        N.check(self.lib.pb_get_rows(self.h, _ptr(signs), n, _ptr(ent), _ptr(found), _stream(self.device)))
+        return ent, found.bool()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pb_table_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchContext:
+    """Device-side per-batch context + workspace for the batched forward/backward of one shard."""
+
+    def __init__(self, max_occurrences, max_out_rows, prefixes, sqrt_scaling=None, prefix_bit=8, device=0):
+        self.lib = N.load()
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.n_slots = len(prefixes)
+        h = C.c_void_p()
+        N.check(self.lib.pb_ctx_create(self.device.index or 0, int(max_occurrences), int(max_out_rows), C.byref(h)))
+        self.h = h
+        cfg = N.SlotsCfg()
+        cfg.n_slots, cfg.prefix_bit = self.n_slots, prefix_bit
+        for i, p in enumerate(prefixes):
+            cfg.prefix[i] = int(p)
+            cfg.sqrt_scaling[i] = int(bool(sqrt_scaling[i])) if sqrt_scaling is not None else 0
+        N.check(self.lib.pb_ctx_set_slots(self.h, C.byref(cfg)))
+
+    def forward(self, shard, ids, slot_occ_off, batch, row_off=None, training=True, out=None):
+        """ids: flat device int64-bit ids (slot-major); slot_occ_off: host list, n_slots+1;
+        row_off: device int32 CSR offsets [n_slots*batch+1] or None (one id per sample per slot).
+        Returns f16 [n_slots, batch, dim]."""
+        ids = _as_i64_bits(ids)
+        if out is None:
+            out = torch.empty((self.n_slots, batch, shard.dim), dtype=torch.float16, device=self.device)
+        off = (C.c_uint32 * (self.n_slots + 1))(*[int(x) for x in slot_occ_off])
+        if row_off is not None:
+            assert row_off.dtype == torch.int32 and row_off.is_contiguous()
+        N.check(self.lib.pb_forward(shard.h, self.h, _ptr(ids), ids.numel(), _ptr(row_off), off, int(batch),
+                                    int(training), _ptr(out), _stream(self.device)))
+        return out
+
+    def backward(self, shard, grads, scales=None, want_status=False):
+        """grads: list (per slot) of device tensors [batch, dim] (all f16 or all f32) or None (skipped)."""
+        ptrs = (C.c_void_p * self.n_slots)()
+        is_f16 = None
+        for i, g in enumerate(grads):
+            if g is None:
+                ptrs[i] = None
+                continue
+            assert g.is_contiguous()
+            f16 = g.dtype == torch.float16
+            assert f16 or g.dtype == torch.float32
+            assert is_f16 is None or is_f16 == f16, "all slot gradients of one request share a dtype"
+            is_f16 = f16
+            ptrs[i] = g.data_ptr()
+        sc = None
+        if scales is not None:
+            sc = (C.c_float * self.n_slots)(*[float(s) for s in scales])
+        status = torch.empty(self.n_slots, dtype=torch.int32, device=self.device) if want_status else None
+        N.check(self.lib.pb_backward(shard.h, self.h, ptrs, int(bool(is_f16)), sc, _ptr(status), _stream(self.device)))
+        return status
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def add_prefix(ids, slot_occ_off, prefixes, prefix_bit=8):
+    lib = N.load()
+    ids = _as_i64_bits(ids)
+    out = torch.empty_like(ids)
+    S = len(prefixes)
+    off = (C.c_uint32 * (S + 1))(*[int(x) for x in slot_occ_off])
+    pf = (C.c_uint64 * S)(*[int(p) for p in prefixes])
+    N.check(lib.pb_add_prefix(_ptr(ids), ids.numel(), off, pf, S, prefix_bit, _ptr(out), _stream(ids.device)))
+    return out
+
+
+def shard_of(signs, R):
+    lib = N.load()
+    signs = _as_i64_bits(signs)
+    out = torch.empty(signs.numel(), dtype=torch.int32, device=signs.device)
+    N.check(lib.pb_shard_of(_ptr(signs), signs.numel(), R, _ptr(out), _stream(signs.device)))
+    return out
+
+
+def farmhash64(x):
+    lib = N.load()
+    x = _as_i64_bits(x)
+    out = torch.empty_like(x)
+    N.check(lib.pb_farmhash64(_ptr(x), x.numel(), _ptr(out), _stream(x.device)))
+    return out
+
+
+def partition_by_shard(signs, R):
+    """Stable partition: returns (perm int32[n], counts int32[R])."""
+    lib = N.load()
+    signs = _as_i64_bits(signs)
+    n = signs.numel()
+    perm = torch.empty(n, dtype=torch.int32, device=signs.device)
+    counts = torch.empty(R, dtype=torch.int32, device=signs.device)
+    wb = int(lib.pb_partition_workspace(n))
+    work = torch.empty(wb, dtype=torch.uint8, device=signs.device)
+    N.check(lib.pb_partition_by_shard(_ptr(signs), n, R, _ptr(perm), _ptr(counts), _ptr(work), wb, _stream(signs.device)))
+    return perm, counts

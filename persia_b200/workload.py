@@ -1,0 +1,76 @@
+"""Criteo-1TB-shaped synthetic workload (BASELINE.json configs 2-4): 26 categorical slots, one id per
+sample per slot, per-slot cardinalities shaped like the public Criteo-Terabyte vocabulary sizes rescaled
+to a target total, ids Zipf(alpha)-distributed per slot.  numpy only (host side; seeds fixed by callers).
+"""
+import numpy as np
+
+# per-field vocabulary sizes of the Criteo Terabyte click logs as used by the MLPerf DLRM benchmark
+CRITEO_1TB_CARDINALITIES = [
+    39884406, 39043, 17289, 7420, 20263, 3, 7120, 1543, 63, 38532951, 2953546, 403346, 10, 2208, 11938, 155, 4,
+    976, 14, 39979771, 25641295, 39664984, 585935, 12972, 108, 36,
+]
+
+
+def scaled_cardinalities(total_rows, n_slots=26):
+    """Rescale the large fields so the table holds `total_rows` rows in all; small fields keep their size."""
+    base = np.array((CRITEO_1TB_CARDINALITIES * ((n_slots + 25) // 26))[:n_slots], dtype=np.float64)
+    small = base <= 1000
+    budget = float(total_rows) - base[small].sum()
+    if budget <= 0:  # tiny test tables: shrink everything
+        card = np.maximum(1, np.floor(base * (total_rows / base.sum()))).astype(np.int64)
+    else:
+        card = base.copy()
+        card[~small] = np.maximum(1001, np.floor(base[~small] * (budget / base[~small].sum())))
+        card = card.astype(np.int64)
+    card[int(np.argmax(card))] += int(total_rows) - int(card.sum())
+    assert card.sum() == int(total_rows) and card.min() >= 1
+    return card
+
+
+def zipf_ids(rng, cardinality, size, alpha=1.05):
+    """Bounded Zipf over [0, cardinality) by inverting the continuous power-law CDF (rank 0 = hottest)."""
+    u = rng.random(size)
+    n = float(cardinality)
+    if abs(alpha - 1.0) < 1e-9:
+        x = np.exp(u * np.log(n + 1.0))
+    else:
+        a = 1.0 - alpha
+        x = ((np.power(n + 1.0, a) - 1.0) * u + 1.0) ** (1.0 / a)
+    return np.minimum(np.floor(x).astype(np.int64) - 1, cardinality - 1).clip(0).astype(np.uint64)
+
+
+def make_batches(seed, cardinalities, batch, n_batches, alpha=1.05, scramble=True):
+    """Returns ids u64 [n_batches, n_slots*batch] (slot-major inside a batch).
+    scramble: map the Zipf rank through a fixed bijection-ish multiplicative hash inside the slot so hot rows
+    are not the first rows of the table."""
+    rng = np.random.default_rng(seed)
+    S = len(cardinalities)
+    out = np.empty((n_batches, S * batch), np.uint64)
+    for s, card in enumerate(cardinalities):
+        card = int(card)
+        ids = zipf_ids(rng, card, n_batches * batch, alpha).reshape(n_batches, batch)
+        if scramble and card > 1:
+            ids = (ids * np.uint64(2654435761) + np.uint64(s * 97 + 13)) % np.uint64(card)
+        out[:, s * batch:(s + 1) * batch] = ids
+    return out
+
+
+def index_prefixes(n_slots, prefix_bit=8):
+    """parse_embedding_config: every slot is its own feature group (persia-embedding-config lib.rs:600-650)."""
+    return [(g + 1) << (64 - prefix_bit) for g in range(n_slots)]
+
+
+def algorithmic_bytes_per_id(dim, state_floats, phase="total"):
+    """SURVEY.md §8(d) per-occurrence figures at U=N, single-id slots, fp32 table, f16 activations/grads."""
+    D, S = dim, state_floats
+    parts = {
+        "partition": 20,
+        "lookup": 16 + 4 * D,
+        "pool_out": 2 * D,
+        "grad_in": 2 * D,
+        "update": 16 + 8 * (D + S),
+    }
+    parts["forward"] = parts["lookup"] + parts["pool_out"]
+    parts["backward"] = parts["grad_in"] + parts["update"]
+    parts["total"] = parts["partition"] + parts["forward"] + parts["backward"]
+    return parts[phase]
