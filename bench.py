@@ -267,7 +267,8 @@ def single_gpu(args, torch, lib):
     ids_dev = [ids_pinned[k].to(dev) for k in range(n_sets)]
     g = torch.Generator(device=dev)
     g.manual_seed(5)
-    grads = [[(torch.randn((B, dim), generator=g, device=dev) * 1e-2).half() for _ in range(S)] for _ in range(n_sets)]
+    grads_all = (torch.randn((n_sets, S, B, dim), generator=g, device=dev) * 1e-2).half()
+    grads = [[grads_all[k, s] for s in range(S)] for k in range(n_sets)]
     outs = [torch.empty((S, B, dim), dtype=torch.float16, device=dev) for _ in range(n_sets)]
     uniq = float(np.mean([np.unique(ids_host[k].reshape(S, B) + (np.arange(S, dtype=np.uint64) << np.uint64(56))[:, None]).size
                           for k in range(min(4, n_sets))])) / n_occ

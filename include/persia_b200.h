@@ -123,6 +123,11 @@ typedef struct {
 int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, pb_ctx** out);
 int pb_ctx_destroy(pb_ctx* c);
 int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg);
+/* Gradient reduction order of pb_backward.  Default (0): a sign repeated more than 32 times in one slot of a
+ * batch is reduced piecewise (deterministic, f32 association differs from the reference's sequential sum);
+ * on (1): strictly sequential in occurrence order for any multiplicity, bit-identical to
+ * embedding_worker_service/mod.rs:799-811, slower on tiny-cardinality slots. */
+int pb_ctx_set_strict_reduce(pb_ctx* c, int on);
 
 /* EmbeddingWorker::forward_batched_direct for summation slots
  * (embedding_worker_service/mod.rs:1076-1107 -> :874-942 -> PS :162-262 -> :486-629).

@@ -84,7 +84,6 @@ struct pb_ctx {
   bool has_slots = false;
   // forward -> backward state (the EW's post_forward_buffer entry, mod.rs:1087-1098)
   uint32_t* occ_cell = nullptr;
-  uint8_t* occ_slot = nullptr;
   uint32_t* occ_outrow = nullptr;
   uint32_t* row_off = nullptr;
   bool multi_id = false;
@@ -97,6 +96,10 @@ struct pb_ctx {
   uint32_t* nan_tick = nullptr;
   float* vw_stage = nullptr;
   size_t vw_stage_floats = 0;
+  float* partials = nullptr;  // 2 rows per PIECE-block of the sorted occurrence list
+  size_t partials_floats = 0;
+  bool strict_reduce = false;
+  bool shared_groups = false;  // two slots carry the same non-zero prefix (one feature group)
 };
 
 namespace {
@@ -335,10 +338,10 @@ int pb_lookup(pb_table* t, const uint64_t* d_signs, uint32_t n, int training, fl
   if (training) {
     if ((rc = ensure_new_list(t, n, st))) return rc;
     launch_begin_batch(t->d, nullptr, st);
-    launch_probe(MODE_TRAIN, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+    launch_probe(MODE_TRAIN, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
     launch_init_new(t->d, t->hy, t->op, n, st);
   } else {
-    launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+    launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
   }
   launch_gather(t->d, sl, t->scratch, nullptr, n, 0, d_out, true, st);
   PB_CUDA(cudaGetLastError());
@@ -354,7 +357,7 @@ int pb_update(pb_table* t, const uint64_t* d_signs, const float* d_grads, uint32
   if ((rc = ensure_alloc(t))) return rc;
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
-  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
   if (t->op.kind == PB_OPT_ADAM) {  // get_batch_level_state: one power step per request (optim.rs:155-197)
     t->b1p_direct *= t->op.b1;
     t->b2p_direct *= t->op.b2;
@@ -373,7 +376,7 @@ int pb_set_rows(pb_table* t, const uint64_t* d_signs, const float* d_entries, ui
   if (rc) return rc;
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
-  launch_probe(MODE_SET, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+  launch_probe(MODE_SET, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
   launch_copy_entries(true, t->d, t->scratch, n, const_cast<float*>(d_entries), nullptr, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
@@ -388,7 +391,7 @@ int pb_get_rows(pb_table* t, const uint64_t* d_signs, uint32_t n, float* d_entri
   if (rc) return rc;
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
-  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, nullptr, st);
+  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
   launch_copy_entries(false, t->d, t->scratch, n, d_entries, d_found, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
@@ -445,6 +448,7 @@ int pb_partition_by_shard(const uint64_t* d_signs, uint32_t n, uint32_t R, uint3
 
 int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, pb_ctx** out) {
   if (!out || max_occurrences == 0 || max_out_rows == 0) return fail(PB_ERR_INVALID, "bad argument");
+  if (max_occurrences > (1u << 24)) return fail(PB_ERR_INVALID, "at most 2^24 id occurrences per batch");
   DeviceGuard g(device);
   pb_ctx* c = new pb_ctx();
   c->device = device;
@@ -454,13 +458,13 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   uint32_t tile = radix_tile(max_occurrences);
   size_t nb = (n + tile - 1) / tile;
   // smaller batches pick smaller tiles: size the histogram for the worst case (n/2048 tiles, capped at 128)
-  size_t hist_elems = 256 * (nb > 128 ? nb : 128);
+  size_t hist_elems = 4 * 65536;  // four passes x (<= 256 tiles x 256 digits)
+  (void)nb;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
   A((void**)&c->occ_cell, 4 * n);
-  A((void**)&c->occ_slot, n);
   A((void**)&c->occ_outrow, 4 * n);
   A((void**)&c->row_off, 4 * ((size_t)max_out_rows + 1));
   A((void**)&c->keys_a, 4 * n);
@@ -484,8 +488,8 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (!c) return PB_OK;
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {c->occ_cell, c->occ_slot, c->occ_outrow, c->row_off, c->keys_a, c->vals_a,
-                  c->keys_b,   c->vals_b,   c->hist,       c->nan_tick, c->vw_stage, c->dev_tick};
+  void* ptrs[] = {c->occ_cell, c->occ_outrow, c->row_off, c->keys_a, c->vals_a,
+                  c->keys_b,   c->vals_b,   c->hist,       c->nan_tick, c->vw_stage, c->dev_tick, c->partials};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete c;
@@ -499,6 +503,16 @@ int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg) {
     return fail(PB_ERR_INVALID, "feature_index_prefix_bit must be in 1..63");
   c->slots = *cfg;
   c->has_slots = true;
+  c->shared_groups = false;
+  for (uint32_t i = 0; i < cfg->n_slots; ++i)
+    for (uint32_t k = i + 1; k < cfg->n_slots; ++k)
+      if (cfg->prefix[i] == cfg->prefix[k]) c->shared_groups = true;  // same key space: a sign may sit in both
+  return PB_OK;
+}
+
+int pb_ctx_set_strict_reduce(pb_ctx* c, int on) {
+  if (!c) return fail(PB_ERR_INVALID, "null argument");
+  c->strict_reduce = on != 0;
   return PB_OK;
 }
 
@@ -531,10 +545,10 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   if (training) {
     if ((rc = ensure_new_list(t, n_occ, st))) return rc;
     launch_begin_batch(t->d, c->dev_tick, st);
-    launch_probe(MODE_TRAIN, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, c->occ_slot, st);
+    launch_probe(MODE_TRAIN, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, st);
     launch_init_new(t->d, t->hy, t->op, n_occ, st);
   } else {
-    launch_probe(MODE_FIND, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, c->occ_slot, st);
+    launch_probe(MODE_FIND, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, st);
   }
   launch_gather(t->d, sl, c->occ_cell, d_row_off, (uint32_t)n_out, batch, d_out_f16, false, st);
   if (training) {
@@ -583,7 +597,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
   launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
   uint32_t bits = 1;
   while ((1ull << bits) <= (uint64_t)t->d.n_cells + 1) ++bits;
-  int which = launch_radix_sort_u32(c->occ_cell, c->n_occ, bits, c->keys_a, c->vals_a, c->keys_b, c->vals_b, c->hist, st);
+  int which = launch_radix_sort_u32(c->occ_cell, c->n_occ, bits, sl, c->keys_a, c->vals_a, c->keys_b, c->vals_b, c->hist, st);
   const uint32_t* skey = which == 0 ? c->keys_a : c->keys_b;
   const uint32_t* socc = which == 0 ? c->vals_a : c->vals_b;
   float* vw = nullptr;
@@ -599,9 +613,34 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     }
     vw = c->vw_stage;
   }
-  launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, skey, socc, c->occ_slot,
-                       c->multi_id ? c->occ_outrow : nullptr, c->multi_id ? c->row_off : nullptr, c->n_occ, c->batch,
-                       c->dev_tick, c->nan_tick, vw, st);
+  SegArgs a;
+  a.skey = skey;
+  a.sval = socc;
+  a.occ_outrow = c->multi_id ? c->occ_outrow : nullptr;
+  a.row_off = c->multi_id ? c->row_off : nullptr;
+  a.tick_ptr = c->dev_tick;
+  a.nan_tick = c->nan_tick;
+  a.vw_stage = vw;
+  a.n = c->n_occ;
+  a.batch = c->batch;
+  a.piece = c->strict_reduce ? 0 : PB_PIECE;
+  a.shared_groups = c->shared_groups ? 1 : 0;
+  a.partials = nullptr;
+  if (a.piece) {
+    size_t need = 2 * (((size_t)c->n_occ + a.piece - 1) / a.piece) * t->d.dim;
+    if (need > c->partials_floats) {
+      PB_CUDA(cudaStreamSynchronize(st));
+      if (c->partials) cudaFree(c->partials);
+      c->partials = nullptr;
+      c->partials_floats = 0;
+      size_t cap = 2 * (((size_t)c->max_occ + a.piece - 1) / a.piece) * t->d.dim;
+      if (cap < need) cap = need;
+      PB_CUDA(cudaMalloc(&c->partials, sizeof(float) * cap));
+      c->partials_floats = cap;
+    }
+    a.partials = c->partials;
+  }
+  launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st);
   c->pending = false;
   PB_CUDA(cudaGetLastError());
   return PB_OK;

@@ -6,6 +6,7 @@
 // All of it is HBM-bound integer / fp32 work: no tensor cores on purpose.
 #include "pb_kernels.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace pb {
@@ -35,40 +36,41 @@ __device__ __forceinline__ uint32_t slot_of_occ(const SlotsDev& s, uint32_t occ)
 // Output: the index cell of every occurrence (h_none when the sign has no storage).  The row number is
 // read from the cell by the kernels that follow, so nothing here ever waits on another thread.
 // ------------------------------------------------------------------------------------------------
-template <int MODE, bool PREFIX>
-__global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, SlotsDev sl, const uint64_t* __restrict__ ids,
-                                               uint32_t n, uint32_t* __restrict__ occ_cell,
-                                               uint8_t* __restrict__ occ_slot) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t tick = t.counters[CTR_TICK];
-  uint64_t sign = ids[i];
-  if (PREFIX) {
-    uint32_t s = slot_of_occ(sl, i);
-    if (occ_slot) occ_slot[i] = (uint8_t)s;
-    uint64_t p = sl.prefix[s];
-    if (p) sign = sign % sl.spacing + p;  // indices_add_prefix, mod.rs:402-429
-  }
-  const uint32_t h_none = t.n_cells + 1;
-  uint32_t h;
-  unsigned long long stored;
-  bool special = (sign == KEY_EMPTY);
-  if (special) {  // the one sign that collides with the empty marker lives in its own cell
-    h = t.n_cells;
-    stored = 0ULL;
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+  if (VEC == 4) {
+    float4 x = *reinterpret_cast<const float4*>(p);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
   } else {
-    h = (uint32_t)(mix64(sign) & t.cell_mask);
-    stored = sign;
+    v[0] = p[0];
   }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
+  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else p[0] = v[0];
+}
+
+// One occurrence: find (or admit) the sign's index cell.  `first` is the already loaded home cell.
+template <int MODE>
+__device__ __forceinline__ uint32_t probe_one(const TableDev& t, const HyperDev& hy, uint64_t sign, uint32_t tick,
+                                              uint32_t hh, uint4 first) {
+  const uint32_t h_none = t.n_cells + 1;
+  const bool special = (sign == KEY_EMPTY);
+  const unsigned long long stored = special ? 0ULL : sign;
   uint32_t result = h_none;
+  uint32_t seen_tick = tick;  // tick of the cell when it was found by a plain read (== tick: no refresh needed)
+  uint4 cur = first;
   for (uint32_t probes = 0; probes <= t.n_cells; ++probes) {
-    Cell* c = t.cells + h;
-    unsigned long long k = ld_key(c);
-    if (k == stored) {
-      result = h;
+    Cell* c = t.cells + hh;
+    if (probes) cur = __ldcg(reinterpret_cast<const uint4*>(c));
+    unsigned long long kk = (unsigned long long)cur.x | ((unsigned long long)cur.y << 32);
+    if (kk == stored) {
+      result = hh;
+      seen_tick = cur.w;
       break;
     }
-    if (k == KEY_EMPTY) {
+    if (kk == KEY_EMPTY) {
       if (MODE == MODE_FIND) break;
       if (MODE == MODE_TRAIN && hy.admit_p < 1.0f) {  // reference: unseeded thread_rng draw (unpinned)
         float u = (float)(mix64(sign ^ (0x9E3779B97F4A7C15ULL * (tick + 1))) >> 40) * (1.0f / 16777216.0f);
@@ -84,29 +86,62 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, SlotsDev
           atomicAdd(&t.counters[CTR_ADMIT], 1u);
           if (MODE == MODE_TRAIN) {
             uint32_t li = atomicAdd(&t.counters[CTR_NEW], 1u);
-            if (li < t.new_list_cap) t.new_list[li] = h;
+            if (li < t.new_list_cap) t.new_list[li] = hh;
           }
         }
         *reinterpret_cast<volatile uint32_t*>(&c->row) = row;
         *reinterpret_cast<volatile uint32_t*>(&c->tick) = tick;
-        result = (row == ROW_NONE) ? h_none : h;
+        result = (row == ROW_NONE) ? h_none : hh;
         break;
       }
       if (old == stored) {  // a duplicate occurrence won the race
-        result = h;
+        result = hh;
         break;
       }
       // another sign took the cell: keep probing from the next one
     }
     if (special) break;
-    h = (h + 1) & (uint32_t)t.cell_mask;
+    hh = (hh + 1) & (uint32_t)t.cell_mask;
   }
-  if (MODE == MODE_TRAIN && result != h_none) {
-    Cell* c = t.cells + result;
-    if (c->tick != tick) *reinterpret_cast<volatile uint32_t*>(&c->tick) = tick;  // get_refresh (eviction_map.rs:48-60)
-  }
+  if (MODE == MODE_TRAIN && result != h_none && seen_tick != tick)  // get_refresh (eviction_map.rs:48-60)
+    *reinterpret_cast<volatile uint32_t*>(&t.cells[result].tick) = tick;
   if (MODE != MODE_SET && result == h_none) atomicAdd(&t.counters[CTR_MISS], 1u);
-  occ_cell[i] = result;
+  return result;
+}
+
+// One thread per occurrence.  Occurrences of one sign that sit in the same warp (tiny-cardinality slots
+// repeat a handful of ids thousands of times) are probed once: the lowest lane holding the sign probes
+// and the others take its answer.
+template <int MODE, bool PREFIX, bool DEDUP>
+__global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, SlotsDev sl, const uint64_t* __restrict__ ids,
+                                               uint32_t n, uint32_t* __restrict__ occ_cell) {
+  const uint32_t tick = t.counters[CTR_TICK];
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = i < n;
+  uint64_t sign = valid ? ids[i] : (0x8000000000000000ULL | threadIdx.x);
+  if (PREFIX && valid) {
+    uint64_t p = sl.prefix[slot_of_occ(sl, i)];
+    if (p) sign = sign % sl.spacing + p;  // indices_add_prefix, mod.rs:402-429
+  }
+  bool leader = valid;
+  uint32_t src = threadIdx.x & 31;
+  if (DEDUP) {
+    uint32_t peers = __match_any_sync(0xffffffffu, sign);
+    src = __ffs(peers) - 1;
+    leader = valid && src == (threadIdx.x & 31);
+  }
+  uint32_t result = t.n_cells + 1;
+  if (leader) {
+    uint32_t h = (sign == KEY_EMPTY) ? t.n_cells : (uint32_t)(mix64(sign) & t.cell_mask);
+    uint4 first = __ldcg(reinterpret_cast<const uint4*>(t.cells + h));
+    result = probe_one<MODE>(t, hy, sign, tick, h, first);
+  }
+  if (DEDUP) {
+    result = __shfl_sync(0xffffffffu, result, src);
+    // every occurrence counts as a miss in the reference's index_miss_count; keep the counter per lookup
+    if (MODE != MODE_SET && valid && !leader && result == t.n_cells + 1) atomicAdd(&t.counters[CTR_MISS], 1u);
+  }
+  if (valid) occ_cell[i] = result;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -165,19 +200,70 @@ __global__ void __launch_bounds__(128) k_init_new(TableDev t, HyperDev hy, Optim
 // VEC-float chunks of the embedding.  f32 accumulate in sample order, optional 1/sqrt(max(n,1)), RNE to
 // f16 (mod.rs:547-579, persia-common lib.rs:157-161).  OUT_F32 writes plain f32 rows (pb_lookup).
 // ------------------------------------------------------------------------------------------------
+template <int VEC, bool OUT_F32>
+__device__ __forceinline__ void store_out(void* out, size_t o, const float (&acc)[VEC], float scale) {
+  if (OUT_F32) {
+    float* dst = reinterpret_cast<float*>(out) + o;
+    if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[VEC > 1 ? 2 : 0], acc[VEC > 1 ? 3 : 0]);
+    else dst[0] = acc[0];
+  } else {
+    __half* dst = reinterpret_cast<__half*>(out) + o;
+    if (VEC == 4) {
+      __half2 a = __floats2half2_rn(__fmul_rn(acc[0], scale), __fmul_rn(acc[VEC > 1 ? 1 : 0], scale));
+      __half2 b = __floats2half2_rn(__fmul_rn(acc[VEC > 1 ? 2 : 0], scale), __fmul_rn(acc[VEC > 1 ? 3 : 0], scale));
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(dst) = pk;
+    } else {
+      dst[0] = __float2half_rn(__fmul_rn(acc[0], scale));
+    }
+  }
+}
+
+constexpr int GATHER_ROWS = 4;  // output rows per group in the one-id-per-sample layout (independent loads in flight)
+
 template <int VEC, int G, bool OUT_F32>
 __global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, const uint32_t* __restrict__ occ_cell,
                                                      const uint32_t* __restrict__ row_off, uint32_t n_out,
                                                      uint32_t batch, void* __restrict__ out) {
-  uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  uint32_t lane = threadIdx.x % G;
-  if (gid >= n_out) return;
-  uint32_t beg = gid, end = gid + 1;
-  if (row_off) {
-    beg = row_off[gid];
-    end = row_off[gid + 1];
-  }
+  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const uint32_t lane = threadIdx.x % G;
   const uint32_t nvec = t.dim / VEC;
+  if (!row_off) {
+    // one occurrence per output row: GATHER_ROWS rows per group, every stage issued for all rows before use
+    const uint32_t r0 = group * GATHER_ROWS;
+    if (r0 >= n_out) return;
+    uint32_t cell[GATHER_ROWS], row[GATHER_ROWS];
+#pragma unroll
+    for (int k = 0; k < GATHER_ROWS; ++k) cell[k] = (r0 + k < n_out) ? occ_cell[r0 + k] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < GATHER_ROWS; ++k) row[k] = (cell[k] <= t.n_cells) ? t.cells[cell[k]].row : ROW_NONE;
+    for (uint32_t c = lane; c < nvec; c += G) {
+      float v[GATHER_ROWS][VEC];
+#pragma unroll
+      for (int k = 0; k < GATHER_ROWS; ++k) {
+        if (row[k] < t.capacity) {
+          load_vec<VEC>(t.rows + (size_t)row[k] * t.stride + c * VEC, v[k]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) v[k][e] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < GATHER_ROWS; ++k)
+        if (r0 + k < n_out) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (!OUT_F32) v[k][e] = __fadd_rn(0.0f, v[k][e]);  // the EW adds into a zeroed row (mod.rs:555-561)
+          store_out<VEC, OUT_F32>(out, (size_t)(r0 + k) * t.dim + c * VEC, v[k], 1.0f);  // 1/sqrt(max(1,1)) = 1
+        }
+    }
+    return;
+  }
+  const uint32_t gid = group;
+  if (gid >= n_out) return;
+  const uint32_t beg = row_off[gid], end = row_off[gid + 1];
   float scale = 1.0f;
   if (!OUT_F32 && batch && sl.sqrt_scaling[gid / batch]) {
     uint32_t cnt = end - beg;
@@ -192,35 +278,12 @@ __global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, co
       if (h > t.n_cells) continue;
       uint32_t row = t.cells[h].row;
       if (row >= t.capacity) continue;
-      const float* src = t.rows + (size_t)row * t.stride + c * VEC;
-      if (VEC == 4) {
-        float4 v = *reinterpret_cast<const float4*>(src);
-        acc[0] = __fadd_rn(acc[0], v.x);
-        acc[1] = __fadd_rn(acc[1], v.y);
-        acc[2] = __fadd_rn(acc[2], v.z);
-        acc[3] = __fadd_rn(acc[3], v.w);
-      } else {
-        acc[0] = __fadd_rn(acc[0], src[0]);
-      }
+      float v[VEC];
+      load_vec<VEC>(t.rows + (size_t)row * t.stride + c * VEC, v);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], v[k]);
     }
-    size_t o = (size_t)gid * t.dim + c * VEC;
-    if (OUT_F32) {
-      float* dst = reinterpret_cast<float*>(out) + o;
-      if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      else dst[0] = acc[0];
-    } else {
-      __half* dst = reinterpret_cast<__half*>(out) + o;
-      if (VEC == 4) {
-        __half2 a = __floats2half2_rn(__fmul_rn(acc[0], scale), __fmul_rn(acc[1], scale));
-        __half2 b = __floats2half2_rn(__fmul_rn(acc[2], scale), __fmul_rn(acc[3], scale));
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&a);
-        pk.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(dst) = pk;
-      } else {
-        dst[0] = __float2half_rn(__fmul_rn(acc[0], scale));
-      }
-    }
+    store_out<VEC, OUT_F32>(out, (size_t)gid * t.dim + c * VEC, acc, scale);
   }
 }
 
@@ -297,21 +360,6 @@ __device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g,
   w = fused ? __fmaf_rn(-op.lr, descent, w) : __fsub_rn(w, __fmul_rn(op.lr, descent));
   m = um;
   v = uv;
-}
-
-template <int VEC>
-__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
-  if (VEC == 4) {
-    float4 x = *reinterpret_cast<const float4*>(p);
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-  } else {
-    v[0] = p[0];
-  }
-}
-template <int VEC>
-__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
-  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  else p[0] = v[0];
 }
 
 // Apply the optimizer to chunk c of a row given its reduced gradient g[VEC].
@@ -421,108 +469,271 @@ __global__ void k_slot_status(GradsDev gr, uint32_t n_slots, const uint32_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// A8 + A9 fused: one group of G lanes per position of the cell-sorted occurrence list; only the group
-// sitting on the first occurrence of an index cell works.  Occurrences of one cell are ordered by slot,
-// then by ascending position (the order FeatureBatch::new pushed them), so the group walks its run slot
-// by slot: it sums one slot's gradients in reference order (mod.rs:799-811) with 1/scale and the
-// sqrt-scaling mirror applied per occurrence (:751-778), performs the optimizer step and weight bound on
-// the resident row (PS mod.rs:380-398) with the reduced gradient still in registers, then moves to the
-// next slot sharing the sign (same feature group): those steps are sequential in slot order, as in the
-// reference where the EW appends slot after slot to the same PS request.
+// A8 + A9.  Input: the occurrence list sorted by index cell (stable), so the occurrences of one sign are
+// adjacent, ordered by slot and then by ascending position — the order FeatureBatch::new pushed them.
+// A "segment" is one (sign, slot) run: the reference reduces it to one gradient (mod.rs:786-812) and the PS
+// performs one optimizer step with it (PS mod.rs:380-398).
+//
+// k_reduce_update — one group of G lanes per list position; only groups sitting on the head of a
+//   "piece" work.  Pieces cut segments at multiples of PIECE positions so that a sign repeated thousands
+//   of times in a batch (tiny-cardinality slots) is reduced by many groups at once.  A segment that fits
+//   in one piece (the vast majority) is summed in reference order and the optimizer step + weight bound
+//   are applied with the reduced gradient still in registers: bit-exact w.r.t. the reference order.
+//   Other pieces store their partial sum (<= 2 per PIECE-block).
+// k_combine_update — one group per PIECE boundary; the group on the first boundary of a multi-piece
+//   segment adds the partials in position order and performs the step.  Deterministic, but the f32
+//   association differs from the reference's strictly sequential sum (documented tolerance); piece == 0
+//   ("strict") disables cutting and restores the sequential order for any length.
+// k_update_shared — only when two slots of one feature group can hold the same sign: such a sign gets
+//   one step per slot, sequentially in slot order (mod.rs:720-822); one group walks the whole run.
 // ------------------------------------------------------------------------------------------------
-template <int VEC, int G, bool F16>
-__global__ void __launch_bounds__(256) k_reduce_update(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
-                                                       const uint32_t* __restrict__ skey,
-                                                       const uint32_t* __restrict__ socc,
-                                                       const uint8_t* __restrict__ occ_slot,
-                                                       const uint32_t* __restrict__ occ_outrow,
-                                                       const uint32_t* __restrict__ row_off, uint32_t n, uint32_t batch,
-                                                       const uint32_t* __restrict__ tick_ptr,
-                                                       const uint32_t* __restrict__ nan_tick,
-                                                       float* __restrict__ vw_stage) {
-  uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  uint32_t lane = threadIdx.x % G;
-  if (gid >= n) return;
-  uint32_t key = skey[gid];
-  if (gid > 0 && skey[gid - 1] == key) return;  // not the head of its cell's run
-  const uint32_t tick = *tick_ptr;
-  uint32_t row = (key <= t.n_cells) ? t.cells[key].row : ROW_NONE;
+__device__ __forceinline__ uint32_t val_occ(uint32_t v) { return v & 0x00FFFFFFu; }
+__device__ __forceinline__ uint32_t val_slot(uint32_t v) { return v >> 24; }
+
+__device__ __forceinline__ bool same_seg(const SegArgs& a, uint32_t j, uint32_t key, uint32_t slot) {
+  return a.skey[j] == key && val_slot(a.sval[j]) == slot;
+}
+
+// sum of the (scaled) gradients of occurrences [j0, j1) of `slot`, chunk c, in position order
+template <int VEC, bool F16>
+__device__ __forceinline__ void reduce_piece(float (&acc)[VEC], const SegArgs& a, const TableDev& t, const SlotsDev& sl,
+                                             const GradsDev& gr, uint32_t slot, uint32_t j0, uint32_t j1, uint32_t c) {
+  const void* gbase = gr.ptr[slot];
+  const float inv_scale = gr.inv_scale[slot];
+  const bool do_scale = gr.do_scale[slot];
+  const bool sqrt_sc = sl.sqrt_scaling[slot];
+  const uint32_t slot_row0 = slot * a.batch;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.0f;
+  constexpr int U = 8;  // the loads of U occurrences are issued together; the adds stay sequential
+  for (uint32_t j = j0; j < j1; j += U) {
+    uint32_t orow[U];
+    float g[U][VEC];
+    float f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t occ = (j + u < j1) ? val_occ(a.sval[j + u]) : 0u;
+      orow[u] = occ;
+    }
+    if (a.occ_outrow) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j + u < j1) orow[u] = a.occ_outrow[orow[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      f[u] = 1.0f;
+      if (j + u < j1) {
+        size_t off = (size_t)(orow[u] - slot_row0) * t.dim + c * VEC;
+        if (F16) {
+          const __half* gp = reinterpret_cast<const __half*>(gbase) + off;
+          if (VEC == 4) {
+            uint2 raw = *reinterpret_cast<const uint2*>(gp);
+            float2 x = __half22float2(*reinterpret_cast<__half2*>(&raw.x));
+            float2 y = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
+            g[u][0] = x.x; g[u][VEC > 1 ? 1 : 0] = x.y; g[u][VEC > 1 ? 2 : 0] = y.x; g[u][VEC > 1 ? 3 : 0] = y.y;
+          } else {
+            g[u][0] = __half2float(gp[0]);
+          }
+        } else {
+          load_vec<VEC>(reinterpret_cast<const float*>(gbase) + off, g[u]);
+        }
+        if (sqrt_sc) {  // mirror of the forward scaling, without its max(.,1) (mod.rs:757-768)
+          uint32_t cnt = a.row_off ? a.row_off[orow[u] + 1] - a.row_off[orow[u]] : 1u;
+          f[u] = __fdiv_rn(1.0f, __fsqrt_rn((float)cnt));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[u][k] = 0.0f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j + u < j1) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          float v = g[u][k];
+          if (F16) v = isinf(v) ? copysignf(65504.0f, v) : v;  // persia-common lib.rs:163-180
+          if (do_scale) v = __fmul_rn(v, inv_scale);           // x 1/scale_factor (mod.rs:751-755)
+          if (sqrt_sc) v = __fmul_rn(v, f[u]);
+          acc[k] = __fadd_rn(acc[k], v);
+        }
+      }
+    }
+  }
+}
+
+// the optimizer step of one segment given per-lane reduced chunks produced by `reduce(c, acc)`
+template <int VEC, int G, typename REDUCE>
+__device__ __forceinline__ void step_segment(const TableDev& t, const OptimDev& op, const HyperDev& hy, const GradsDev& gr,
+                                             uint32_t slot, uint32_t row, uint32_t lane, float* stage, REDUCE reduce) {
   float* prow = t.rows + (size_t)row * t.stride;
   const uint32_t nvec = t.dim / VEC;
-  float* stage = vw_stage ? vw_stage + (size_t)gid * t.dim : nullptr;
-  const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  float vw_state = 0.0f, r1 = 0.0f, r2 = 0.0f;
+  if (op.kind == PB_OPT_ADAGRAD_VW) vw_state = prow[t.dim];
+  if (op.kind == PB_OPT_ADAM) {
+    r1 = __fdiv_rn(1.0f, __fsub_rn(1.0f, gr.b1p[slot]));
+    r2 = __fdiv_rn(1.0f, __fsub_rn(1.0f, gr.b2p[slot]));
+  }
+  for (uint32_t c = lane; c < nvec; c += G) {
+    float acc[VEC];
+    reduce(c, acc);
+    if (op.kind == PB_OPT_ADAGRAD_VW) store_vec<VEC>(stage + c * VEC, acc);
+    apply_chunk<VEC>(prow, c, acc, t, op, hy, vw_state, r1, r2);
+  }
+  if (op.kind == PB_OPT_ADAGRAD_VW) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
+    const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    __syncwarp(gmask);  // the staged gradient of every lane of the group is visible to lane 0
+    if (lane == 0) {
+      float gs = __fdiv_rn(vw_dot(stage, t.dim), (float)t.dim);
+      prow[t.dim] = __fadd_rn(__fmul_rn(vw_state, op.mom), gs);
+    }
+    __syncwarp(gmask);
+  }
+}
 
-  uint32_t j0 = gid;
-  while (j0 < n && skey[j0] == key) {
-    uint32_t slot = occ_slot[socc[j0]];
-    uint32_t j1 = j0 + 1;  // end of this slot's sub-run
-    while (j1 < n && skey[j1] == key && occ_slot[socc[j1]] == slot) ++j1;
-    const void* gbase = gr.ptr[slot];
-    bool active = gbase && nan_tick[slot] != tick;  // skipped / NaN slot: nothing is applied
-    if (active && row >= t.capacity) {
+__device__ __forceinline__ float* partial_slot(const SegArgs& a, const TableDev& t, uint32_t head) {
+  uint32_t blk = head / a.piece;
+  return a.partials + ((size_t)2 * blk + (head % a.piece ? 1 : 0)) * t.dim;
+}
+
+template <int VEC, int G, bool F16>
+__global__ void __launch_bounds__(256) k_reduce_update(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                       SegArgs a) {
+  uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  uint32_t lane = threadIdx.x % G;
+  if (j >= a.n) return;
+  uint32_t key = a.skey[j];
+  uint32_t slot = val_slot(a.sval[j]);
+  bool seg_start = j == 0 || !same_seg(a, j - 1, key, slot);
+  // A boundary (multiple of PIECE) cuts a segment only if the segment holds at least two boundaries, i.e.
+  // also the one before or after: segments of <= PIECE occurrences are never cut and keep reference order.
+  if (!seg_start) {
+    if (a.piece == 0 || j % a.piece != 0) return;
+    bool cut = same_seg(a, j - a.piece, key, slot) || (j + a.piece < a.n && same_seg(a, j + a.piece, key, slot));
+    if (!cut) return;  // not the head of a piece
+  }
+  uint32_t e = j + 1;
+  while (e < a.n && same_seg(a, e, key, slot)) {
+    if (a.piece && e % a.piece == 0) {
+      bool cut = (e - j >= a.piece) || (e + a.piece < a.n && same_seg(a, e + a.piece, key, slot));
+      if (cut) break;
+    }
+    ++e;
+  }
+  bool seg_end = e == a.n || !same_seg(a, e, key, slot);
+  bool whole = seg_start && seg_end;
+  if (!gr.ptr[slot] || a.nan_tick[slot] == *a.tick_ptr) return;  // skipped / NaN slot: nothing is applied
+  if (whole) {
+    if (a.shared_groups && ((j > 0 && a.skey[j - 1] == key) || (e < a.n && a.skey[e] == key))) return;  // k_update_shared
+    uint32_t row = (key <= t.n_cells) ? t.cells[key].row : ROW_NONE;
+    if (row >= t.capacity) {
       if (lane == 0) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
+      return;
+    }
+    float* stage = a.vw_stage ? a.vw_stage + (size_t)j * t.dim : nullptr;
+    step_segment<VEC, G>(t, op, hy, gr, slot, row, lane, stage,
+                         [&](uint32_t c, float (&acc)[VEC]) { reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j, e, c); });
+  } else {
+    if (key > t.n_cells) return;  // counted once by k_combine_update
+    float* dst = partial_slot(a, t, j);
+    const uint32_t nvec = t.dim / VEC;
+    for (uint32_t c = lane; c < nvec; c += G) {
+      float acc[VEC];
+      reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j, e, c);
+      store_vec<VEC>(dst + c * VEC, acc);
+    }
+  }
+}
+
+template <int VEC, int G>
+__global__ void __launch_bounds__(256) k_combine_update(TableDev t, OptimDev op, HyperDev hy, GradsDev gr, SegArgs a) {
+  uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) / G;  // boundary number (position m * PIECE)
+  uint32_t lane = threadIdx.x % G;
+  uint64_t b64 = (uint64_t)m * a.piece;
+  if (b64 >= a.n) return;
+  uint32_t b = (uint32_t)b64;
+  uint32_t key = a.skey[b];
+  uint32_t slot = val_slot(a.sval[b]);
+  // this group owns the segment holding b iff b is its first boundary and it holds a second one
+  if (b + a.piece >= a.n || !same_seg(a, b + a.piece, key, slot)) return;  // <= 1 boundary: done whole by k_reduce_update
+  if (b >= a.piece && same_seg(a, b - a.piece, key, slot)) return;          // an earlier boundary owns it
+  uint32_t j0 = b;
+  while (j0 > 0 && j0 + a.piece > b + 1 && same_seg(a, j0 - 1, key, slot)) --j0;
+  if (!gr.ptr[slot] || a.nan_tick[slot] == *a.tick_ptr) return;
+  // last boundary of the segment: the list is sorted by (cell, slot), so binary-search the boundaries
+  uint32_t lo = b / a.piece + 1, hi = (a.n - 1) / a.piece;  // boundary numbers; lo is known to be inside
+  while (lo < hi) {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    uint32_t p = mid * a.piece;
+    uint32_t k2 = a.skey[p], s2 = val_slot(a.sval[p]);
+    bool inside = (k2 < key) || (k2 == key && s2 <= slot);  // positions > b never sort before the segment
+    if (inside) lo = mid; else hi = mid - 1;
+  }
+  const uint32_t q_last = lo * a.piece;
+  if (a.shared_groups) {  // a run holding several slots belongs to k_update_shared
+    uint32_t e = q_last + 1;
+    while (e < a.n && same_seg(a, e, key, slot)) ++e;
+    if ((j0 > 0 && a.skey[j0 - 1] == key) || (e < a.n && a.skey[e] == key)) return;
+  }
+  uint32_t row = (key <= t.n_cells) ? t.cells[key].row : ROW_NONE;
+  if (row >= t.capacity) {
+    if (lane == 0) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+    return;
+  }
+  const uint32_t q0 = (j0 < b) ? b : b + a.piece;  // first boundary after the first piece
+  float* first = partial_slot(a, t, j0);
+  step_segment<VEC, G>(t, op, hy, gr, slot, row, lane, first, [&](uint32_t c, float (&acc)[VEC]) {
+    load_vec<VEC>(first + c * VEC, acc);
+    constexpr int U = 8;
+    for (uint32_t q = q0; q <= q_last; q += U * a.piece) {
+      float p[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t qq = q + u * a.piece;
+        if (qq <= q_last) load_vec<VEC>(a.partials + (size_t)2 * (qq / a.piece) * t.dim + c * VEC, p[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (q + u * a.piece <= q_last) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], p[u][k]);
+        }
+    }
+  });
+}
+
+template <int VEC, int G, bool F16>
+__global__ void __launch_bounds__(256) k_update_shared(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                       SegArgs a) {
+  uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  uint32_t lane = threadIdx.x % G;
+  if (j >= a.n) return;
+  uint32_t key = a.skey[j];
+  if (j > 0 && a.skey[j - 1] == key) return;  // not the head of its sign's run
+  uint32_t slot0 = val_slot(a.sval[j]);
+  uint32_t end = j + 1;
+  bool multi = false;
+  while (end < a.n && a.skey[end] == key) {
+    multi |= val_slot(a.sval[end]) != slot0;
+    ++end;
+  }
+  if (!multi) return;  // single-slot runs were handled by the two kernels above
+  uint32_t row = (key <= t.n_cells) ? t.cells[key].row : ROW_NONE;
+  uint32_t j0 = j;
+  while (j0 < end) {
+    uint32_t slot = val_slot(a.sval[j0]);
+    uint32_t j1 = j0 + 1;
+    while (j1 < end && val_slot(a.sval[j1]) == slot) ++j1;
+    bool active = gr.ptr[slot] && a.nan_tick[slot] != *a.tick_ptr;
+    if (active && row >= t.capacity) {
+      if (lane == 0) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
       active = false;
     }
     if (active) {
-      float inv_scale = gr.inv_scale[slot];
-      bool do_scale = gr.do_scale[slot];
-      bool sqrt_sc = sl.sqrt_scaling[slot];
-      uint32_t slot_row0 = slot * batch;
-      float vw_state = 0.0f, r1 = 0.0f, r2 = 0.0f;
-      if (op.kind == PB_OPT_ADAGRAD_VW) vw_state = prow[t.dim];
-      if (op.kind == PB_OPT_ADAM) {
-        r1 = __fdiv_rn(1.0f, __fsub_rn(1.0f, gr.b1p[slot]));
-        r2 = __fdiv_rn(1.0f, __fsub_rn(1.0f, gr.b2p[slot]));
-      }
-      for (uint32_t c = lane; c < nvec; c += G) {
-        float acc[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] = 0.0f;
-        for (uint32_t j = j0; j < j1; ++j) {
-          uint32_t occ = socc[j];
-          uint32_t orow = occ_outrow ? occ_outrow[occ] : occ;
-          size_t off = (size_t)(orow - slot_row0) * t.dim + c * VEC;
-          float g[VEC];
-          if (F16) {
-            const __half* gp = reinterpret_cast<const __half*>(gbase) + off;
-            if (VEC == 4) {
-              uint2 raw = *reinterpret_cast<const uint2*>(gp);
-              float2 a = __half22float2(*reinterpret_cast<__half2*>(&raw.x));
-              float2 b = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
-              g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
-            } else {
-              g[0] = __half2float(gp[0]);
-            }
-#pragma unroll
-            for (int k = 0; k < VEC; ++k)  // persia-common lib.rs:163-180: +-inf -> +-65504
-              g[k] = isinf(g[k]) ? copysignf(65504.0f, g[k]) : g[k];
-          } else {
-            load_vec<VEC>(reinterpret_cast<const float*>(gbase) + off, g);
-          }
-          if (do_scale) {
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) g[k] = __fmul_rn(g[k], inv_scale);
-          }
-          if (sqrt_sc) {  // mirror of the forward scaling, without its max(.,1) (mod.rs:757-768)
-            uint32_t cnt = row_off ? row_off[orow + 1] - row_off[orow] : 1u;
-            float f = __fdiv_rn(1.0f, __fsqrt_rn((float)cnt));
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) g[k] = __fmul_rn(g[k], f);
-          }
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], g[k]);
-        }
-        if (stage) store_vec<VEC>(stage + c * VEC, acc);
-        apply_chunk<VEC>(prow, c, acc, t, op, hy, vw_state, r1, r2);
-      }
-      if (op.kind == PB_OPT_ADAGRAD_VW) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
-        __syncwarp(gmask);  // the staged gradient of every lane of the group is visible to lane 0
-        if (lane == 0) {
-          float gs = __fdiv_rn(vw_dot(stage, t.dim), (float)t.dim);
-          prow[t.dim] = __fadd_rn(__fmul_rn(vw_state, op.mom), gs);
-        }
-        __syncwarp(gmask);
-      }
+      float* stage = a.vw_stage ? a.vw_stage + (size_t)j0 * t.dim : nullptr;
+      step_segment<VEC, G>(t, op, hy, gr, slot, row, lane, stage,
+                           [&](uint32_t c, float (&acc)[VEC]) { reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j0, j1, c); });
     }
     j0 = j1;
   }
@@ -566,9 +777,12 @@ __global__ void __launch_bounds__(256) k_update_direct(TableDev t, OptimDev op, 
 // ------------------------------------------------------------------------------------------------
 // Stable LSD radix partition, 8-bit digits ("warp-radix partition": ranks inside a warp come from
 // __match_any_sync, across warps from per-warp digit counters in shared memory, across blocks from a
-// scanned digit-major histogram).  KEYOP maps the stored key to the sort key:
+// block-major digit histogram that every scatter block folds itself — no separate scan kernel).  A scatter
+// pass also builds the histogram of the next pass (global REDs on the element's destination tile), so a
+// k-pass sort is 1 + k launches.  KEYOP maps the stored key to the sort key:
 //   KeyIdentity        — index cell of an occurrence (grouping for the backward pass)
 //   KeyShard{R}        — farmhash64(sign) % R (indices_to_sharded_indices, mod.rs:454-479)
+// VALOP gives the payload of pass 0: ValIdentity (position) or ValOccSlot (position | slot << 24).
 // ------------------------------------------------------------------------------------------------
 struct KeyIdentity {
   __device__ __forceinline__ uint32_t operator()(uint32_t k) const { return k; }
@@ -577,108 +791,132 @@ struct KeyShard {
   uint32_t R;
   __device__ __forceinline__ uint32_t operator()(uint64_t sign) const { return (uint32_t)(farmhash64_u64(sign) % R); }
 };
+struct ValIdentity {
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i; }
+};
+struct ValOccSlot {
+  SlotsDev sl;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i | (slot_of_occ(sl, i) << 24); }
+};
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;                     // keys per thread held in registers
+constexpr int RS_SUB = RS_THREADS * RS_ITEMS;   // 2048 keys per sub-tile
 
+// pass-0 histogram, block-major: hist[block][digit]; also clears this block's rows of the later passes
 template <typename KT, typename KEYOP>
 __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const KT* __restrict__ keys, uint32_t n, uint32_t shift,
-                                                           uint32_t tile, KEYOP op, uint32_t* __restrict__ hist) {
+                                                           uint32_t tile, KEYOP op, uint32_t* __restrict__ hist,
+                                                           uint32_t* __restrict__ z1, uint32_t* __restrict__ z2,
+                                                           uint32_t* __restrict__ z3) {
   __shared__ uint32_t cnt[256];
   cnt[threadIdx.x] = 0;
   __syncthreads();
   uint32_t beg = blockIdx.x * tile, end = min(n, beg + tile);
   for (uint32_t i = beg + threadIdx.x; i < end; i += RS_THREADS) atomicAdd(&cnt[(op(keys[i]) >> shift) & 255u], 1u);
   __syncthreads();
-  hist[threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];  // digit-major
+  uint32_t o = blockIdx.x * 256 + threadIdx.x;
+  hist[o] = cnt[threadIdx.x];
+  if (z1) z1[o] = 0;
+  if (z2) z2[o] = 0;
+  if (z3) z3[o] = 0;
 }
 
-// exclusive scan of a u32 array by one block (sizes here are 256 * #tiles, a few thousand entries)
-__global__ void __launch_bounds__(1024) k_scan_excl(uint32_t* __restrict__ data, uint32_t n) {
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < n; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = (i < n) ? data[i] : 0;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) wsum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = wsum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += y;
-      }
-      wsum[lane] = w;
-    }
-    __syncthreads();
-    uint32_t carry = carry_s;
-    uint32_t excl = carry + (warp ? wsum[warp - 1] : 0) + x - v;
-    if (i < n) data[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + wsum[31];
-    __syncthreads();
-  }
-}
-
-template <typename KT, typename KEYOP>
+template <typename KT, typename KEYOP, typename VALOP>
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const KT* __restrict__ keys_in,
                                                               const uint32_t* __restrict__ vals_in,
                                                               KT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                               uint32_t n, uint32_t shift, uint32_t tile, KEYOP op,
-                                                              const uint32_t* __restrict__ hist) {
+                                                              VALOP vop, const uint32_t* __restrict__ hist,
+                                                              uint32_t* __restrict__ hist_next, uint32_t next_shift) {
   __shared__ uint32_t base[256];
   __shared__ uint32_t wcnt[RS_WARPS][256];
-  uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  base[threadIdx.x] = hist[threadIdx.x * gridDim.x + blockIdx.x];
+  __shared__ uint32_t wsum[RS_WARPS];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, d = threadIdx.x;
+  // this block's first output slot per digit = (keys of smaller digits anywhere) + (same digit in earlier blocks)
+  uint32_t below = 0, total = 0;
+  const uint32_t nb = gridDim.x;
+  for (uint32_t b0 = 0; b0 < nb; b0 += 4) {
+    uint32_t v[4];
 #pragma unroll
-  for (int w = 0; w < RS_WARPS; ++w) wcnt[w][threadIdx.x] = 0;
+    for (int u = 0; u < 4; ++u) v[u] = (b0 + u < nb) ? hist[(b0 + u) * 256 + d] : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      total += v[u];
+      if (b0 + u < blockIdx.x) below += v[u];
+    }
+  }
+  uint32_t x = total;  // exclusive scan of `total` over the 256 digits
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) wcnt[w][d] = 0;
   __syncthreads();
-  uint32_t beg = blockIdx.x * tile, end = min(n, beg + tile);
-  for (uint32_t r = beg; r < end; r += RS_THREADS) {
-    uint32_t i = r + threadIdx.x;
-    bool valid = i < end;
-    KT key = valid ? keys_in[i] : KT(0);
-    uint32_t digit = valid ? ((op(key) >> shift) & 255u) : 256u + lane;  // invalid lanes match nobody
-    uint32_t peers = __match_any_sync(0xffffffffu, digit);
-    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank == 0) wcnt[warp][digit] = __popc(peers);
-    __syncthreads();
-    if (valid) {
-      uint32_t pos = base[digit] + rank;
-      for (uint32_t w = 0; w < warp; ++w) pos += wcnt[w][digit];
-      if (keys_out) keys_out[pos] = key;
-      vals_out[pos] = vals_in ? vals_in[i] : i;
-    }
-    __syncthreads();
-    uint32_t tot = 0;
+  uint32_t woff = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      tot += wcnt[w][threadIdx.x];
-      wcnt[w][threadIdx.x] = 0;
+  for (int w = 0; w < RS_WARPS; ++w)
+    if (w < (int)warp) woff += wsum[w];
+  base[d] = woff + x - total + below;
+  __syncthreads();
+
+  const uint32_t beg = blockIdx.x * tile, end = min(n, beg + tile);
+  for (uint32_t sub = beg; sub < end; sub += RS_SUB) {
+    KT key[RS_ITEMS];
+    uint32_t val[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {  // all loads of the sub-tile are in flight together
+      uint32_t i = sub + r * RS_THREADS + threadIdx.x;
+      if (i < end) {
+        key[r] = keys_in[i];
+        val[r] = vals_in ? vals_in[i] : vop(i);
+      } else {
+        key[r] = KT(0);
+        val[r] = 0;
+      }
     }
-    base[threadIdx.x] += tot;
-    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      uint32_t i = sub + r * RS_THREADS + threadIdx.x;
+      bool valid = i < end;
+      uint32_t sk = op(key[r]);
+      uint32_t digit = valid ? ((sk >> shift) & 255u) : 256u + lane;  // invalid lanes match nobody
+      uint32_t peers = __match_any_sync(0xffffffffu, digit);
+      uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      if (valid && rank == 0) wcnt[warp][digit] = __popc(peers);
+      __syncthreads();
+      if (valid) {
+        uint32_t pos = base[digit] + rank;
+        for (uint32_t w = 0; w < warp; ++w) pos += wcnt[w][digit];
+        if (keys_out) keys_out[pos] = key[r];
+        vals_out[pos] = val[r];
+        if (hist_next) atomicAdd(&hist_next[(pos / tile) * 256 + ((sk >> next_shift) & 255u)], 1u);
+      }
+      __syncthreads();
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; ++w) {
+        tot += wcnt[w][d];
+        wcnt[w][d] = 0;
+      }
+      base[d] += tot;
+      __syncthreads();
+    }
   }
 }
 
-// per-shard group sizes out of the scanned digit-major histogram of a single-pass partition
-__global__ void k_counts_from_hist(const uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t R, uint32_t n,
+// per-shard group sizes of a single-pass partition: column sums of the block-major histogram
+__global__ void k_counts_from_hist(const uint32_t* __restrict__ hist, uint32_t n_blocks, uint32_t R,
                                    uint32_t* __restrict__ counts) {
   uint32_t d = threadIdx.x;
   if (d >= R) return;
-  uint32_t lo = hist[d * n_blocks];
-  uint32_t hi = (d + 1 < 256) ? hist[(d + 1) * n_blocks] : n;
-  counts[d] = hi - lo;
+  uint32_t t = 0;
+  for (uint32_t b = 0; b < n_blocks; ++b) t += hist[b * 256 + d];
+  counts[d] = t;
 }
 
 // CSR row offsets -> output row of every occurrence (multi-id slots)
@@ -798,19 +1036,32 @@ void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, cudaStream_t st) 
   PB_LAUNCH(k_begin_batch, 1, 1, 0, st, t.counters, ctx_tick);
 }
 
+static int probe_variant() {
+  static int v = [] {
+    const char* e = getenv("PB_PROBE_DEDUP");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const SlotsDev& sl, const uint64_t* ids,
-                  uint32_t n, uint32_t* occ_cell, uint8_t* occ_slot, cudaStream_t st) {
+                  uint32_t n, uint32_t* occ_cell, cudaStream_t st) {
   if (!n) return;
   uint32_t g = cdiv(n, 256);
+  const bool dd = probe_variant() != 0;
+#define PB_P(M, P)                                                                                              \
+  do {                                                                                                          \
+    if (dd) PB_LAUNCH_F(FAM_PROBE, (k_probe<M, P, true>), g, 256, 0, st, t, hy, sl, ids, n, occ_cell);          \
+    else PB_LAUNCH_F(FAM_PROBE, (k_probe<M, P, false>), g, 256, 0, st, t, hy, sl, ids, n, occ_cell);            \
+  } while (0)
   if (mode == MODE_FIND) {
-    if (prefix) PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_FIND, true>), g, 256, 0, st, t, hy, sl, ids, n, occ_cell, occ_slot);
-    else PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_FIND, false>), g, 256, 0, st, t, hy, sl, ids, n, occ_cell, occ_slot);
+    if (prefix) PB_P(MODE_FIND, true); else PB_P(MODE_FIND, false);
   } else if (mode == MODE_TRAIN) {
-    if (prefix) PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_TRAIN, true>), g, 256, 0, st, t, hy, sl, ids, n, occ_cell, occ_slot);
-    else PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_TRAIN, false>), g, 256, 0, st, t, hy, sl, ids, n, occ_cell, occ_slot);
+    if (prefix) PB_P(MODE_TRAIN, true); else PB_P(MODE_TRAIN, false);
   } else {
-    PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_SET, false>), g, 256, 0, st, t, hy, sl, ids, n, occ_cell, occ_slot);
+    PB_P(MODE_SET, false);
   }
+#undef PB_P
 }
 
 void launch_init_new(const TableDev& t, const HyperDev& hy, const OptimDev& op, uint32_t max_new, cudaStream_t st) {
@@ -826,7 +1077,7 @@ static void gather_dispatch(int G, const TableDev& t, const SlotsDev& sl, const 
   uint32_t grid;
 #define PB_G(GG)                                                                                              \
   case GG:                                                                                                    \
-    grid = cdiv((uint64_t)n_out * GG, 256);                                                                   \
+    grid = cdiv((uint64_t)(row_off ? n_out : cdiv(n_out, GATHER_ROWS)) * GG, 256);                             \
     PB_LAUNCH_F(FAM_GATHER, (k_gather_pool<VEC, GG, F32>), grid, 256, 0, st, t, sl, occ_cell, row_off, n_out, batch, out);  \
     break;
   switch (G) {
@@ -877,15 +1128,18 @@ void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_sl
 
 template <int VEC, bool F16>
 static void reduce_dispatch(int G, const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                            const GradsDev& gr, const uint32_t* skey, const uint32_t* socc, const uint8_t* occ_slot,
-                            const uint32_t* occ_outrow, const uint32_t* row_off, uint32_t n, uint32_t batch,
-                            const uint32_t* tick, const uint32_t* nan_tick, float* vw_stage, cudaStream_t st) {
-  uint32_t grid;
+                            const GradsDev& gr, const SegArgs& a, cudaStream_t st) {
+  uint32_t grid, gridc;
+  uint32_t n_bound = a.piece ? (uint32_t)(((uint64_t)a.n + a.piece - 1) / a.piece) : 0;  // boundaries 0..n_bound-1
 #define PB_G(GG)                                                                                                   \
   case GG:                                                                                                         \
-    grid = cdiv((uint64_t)n * GG, 256);                                                                            \
-    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_update<VEC, GG, F16>), grid, 256, 0, st, t, op, hy, sl, gr, skey, socc, occ_slot,          \
-              occ_outrow, row_off, n, batch, tick, nan_tick, vw_stage);                                            \
+    grid = cdiv((uint64_t)a.n * GG, 256);                                                                          \
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_update<VEC, GG, F16>), grid, 256, 0, st, t, op, hy, sl, gr, a);              \
+    if (n_bound > 1) {                                                                                             \
+      gridc = cdiv((uint64_t)n_bound * GG, 256);                                                             \
+      PB_LAUNCH_F(FAM_UPDATE, (k_combine_update<VEC, GG>), gridc, 256, 0, st, t, op, hy, gr, a);                   \
+    }                                                                                                              \
+    if (a.shared_groups) PB_LAUNCH_F(FAM_UPDATE, (k_update_shared<VEC, GG, F16>), grid, 256, 0, st, t, op, hy, sl, gr, a); \
     break;
   switch (G) {
     PB_G(1) PB_G(2) PB_G(4) PB_G(8) PB_G(16) PB_G(32)
@@ -894,18 +1148,16 @@ static void reduce_dispatch(int G, const TableDev& t, const OptimDev& op, const 
 }
 
 void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                          const GradsDev& gr, bool f16, const uint32_t* skey, const uint32_t* socc,
-                          const uint8_t* occ_slot, const uint32_t* occ_outrow, const uint32_t* row_off, uint32_t n,
-                          uint32_t batch, const uint32_t* tick, const uint32_t* nan_tick, float* vw_stage, cudaStream_t st) {
-  if (!n) return;
+                          const GradsDev& gr, bool f16, const SegArgs& a, cudaStream_t st) {
+  if (!a.n) return;
   int vec, G;
   vec_group(t.dim, vec, G);
   if (vec == 4) {
-    if (f16) reduce_dispatch<4, true>(G, t, op, hy, sl, gr, skey, socc, occ_slot, occ_outrow, row_off, n, batch, tick, nan_tick, vw_stage, st);
-    else reduce_dispatch<4, false>(G, t, op, hy, sl, gr, skey, socc, occ_slot, occ_outrow, row_off, n, batch, tick, nan_tick, vw_stage, st);
+    if (f16) reduce_dispatch<4, true>(G, t, op, hy, sl, gr, a, st);
+    else reduce_dispatch<4, false>(G, t, op, hy, sl, gr, a, st);
   } else {
-    if (f16) reduce_dispatch<1, true>(G, t, op, hy, sl, gr, skey, socc, occ_slot, occ_outrow, row_off, n, batch, tick, nan_tick, vw_stage, st);
-    else reduce_dispatch<1, false>(G, t, op, hy, sl, gr, skey, socc, occ_slot, occ_outrow, row_off, n, batch, tick, nan_tick, vw_stage, st);
+    if (f16) reduce_dispatch<1, true>(G, t, op, hy, sl, gr, a, st);
+    else reduce_dispatch<1, false>(G, t, op, hy, sl, gr, a, st);
   }
 }
 
@@ -924,31 +1176,37 @@ void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev&
 }
 
 uint32_t radix_tile(uint32_t n) {
-  // keep the digit-major histogram (256 x tiles) small enough for the one-block scan
-  uint32_t tile = 2048;
-  while (cdiv(n, tile) > 128) tile <<= 1;
+  // tiles are multiples of the 2048-key sub-tile; at most 256 of them so that folding the block-major
+  // histogram inside every scatter block stays cheap
+  uint32_t tile = RS_SUB;
+  while (cdiv(n, tile) > 256) tile += RS_SUB;
   return tile;
 }
 
-// Sorts (keys, vals=position) by the low `bits` bits of the key, stable.  Ping-pongs between the two
-// buffer pairs; returns which pair holds the result (0 = a, 1 = b).  First pass reads `keys_in`.
-int launch_radix_sort_u32(const uint32_t* keys_in, uint32_t n, uint32_t bits, uint32_t* keys_a, uint32_t* vals_a,
-                          uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, cudaStream_t st) {
+// Sorts (key = index cell, payload = position | slot << 24) by the low `bits` bits of the key, stable.
+// Ping-pongs between the two buffer pairs; returns which pair holds the result (0 = a, 1 = b).
+// hist: 4 x 256 x 256 u32.
+int launch_radix_sort_u32(const uint32_t* keys_in, uint32_t n, uint32_t bits, const SlotsDev& sl, uint32_t* keys_a,
+                          uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, cudaStream_t st) {
   if (!n) return 0;
   uint32_t tile = radix_tile(n), nb = cdiv(n, tile);
-  const uint32_t* kin = keys_in;
-  const uint32_t* vin = nullptr;
-  int cur = 1;  // next output pair: 0 -> a, 1 -> b ; start by writing a
   uint32_t passes = (bits + 7) / 8;
   if (passes == 0) passes = 1;
+  if (passes > 4) passes = 4;
+  uint32_t* h[4] = {hist, hist + 65536, hist + 2 * 65536, hist + 3 * 65536};
+  PB_LAUNCH_F(FAM_SORT, (k_radix_hist<uint32_t, KeyIdentity>), nb, RS_THREADS, 0, st, keys_in, n, 0u, tile, KeyIdentity(),
+              h[0], passes > 1 ? h[1] : nullptr, passes > 2 ? h[2] : nullptr, passes > 3 ? h[3] : nullptr);
+  const uint32_t* kin = keys_in;
+  const uint32_t* vin = nullptr;
+  ValOccSlot vop{sl};
+  int cur = 1;
   for (uint32_t p = 0; p < passes; ++p) {
     cur ^= 1;
     uint32_t* kout = cur == 0 ? keys_a : keys_b;
     uint32_t* vout = cur == 0 ? vals_a : vals_b;
-    PB_LAUNCH_F(FAM_SORT, (k_radix_hist<uint32_t, KeyIdentity>), nb, RS_THREADS, 0, st, kin, n, p * 8, tile, KeyIdentity(), hist);
-    PB_LAUNCH_F(FAM_SORT, k_scan_excl, 1, 1024, 0, st, hist, 256 * nb);
-    PB_LAUNCH_F(FAM_SORT, (k_radix_scatter<uint32_t, KeyIdentity>), nb, RS_THREADS, 0, st, kin, vin, kout, vout, n, p * 8, tile,
-              KeyIdentity(), hist);
+    uint32_t* hn = (p + 1 < passes) ? h[p + 1] : nullptr;
+    PB_LAUNCH_F(FAM_SORT, (k_radix_scatter<uint32_t, KeyIdentity, ValOccSlot>), nb, RS_THREADS, 0, st, kin, vin, kout, vout,
+                n, p * 8, tile, KeyIdentity(), vop, h[p], hn, (p + 1) * 8);
     kin = kout;
     vin = vout;
   }
@@ -959,12 +1217,12 @@ void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, ui
                                uint32_t* hist, cudaStream_t st) {
   uint32_t tile = radix_tile(n ? n : 1), nb = cdiv(n ? n : 1, tile);
   KeyShard op{R};
-  PB_LAUNCH((k_radix_hist<uint64_t, KeyShard>), nb, RS_THREADS, 0, st, signs, n, 0, tile, op, hist);
-  PB_LAUNCH(k_scan_excl, 1, 1024, 0, st, hist, 256 * nb);
-  PB_LAUNCH(k_counts_from_hist, 1, 256, 0, st, hist, nb, R, n, counts);
+  PB_LAUNCH((k_radix_hist<uint64_t, KeyShard>), nb, RS_THREADS, 0, st, signs, n, 0u, tile, op, hist, (uint32_t*)nullptr,
+            (uint32_t*)nullptr, (uint32_t*)nullptr);
+  PB_LAUNCH(k_counts_from_hist, 1, 256, 0, st, hist, nb, R, counts);
   if (n)
-    PB_LAUNCH((k_radix_scatter<uint64_t, KeyShard>), nb, RS_THREADS, 0, st, signs, (const uint32_t*)nullptr,
-              (uint64_t*)nullptr, perm, n, 0, tile, op, hist);
+    PB_LAUNCH((k_radix_scatter<uint64_t, KeyShard, ValIdentity>), nb, RS_THREADS, 0, st, signs, (const uint32_t*)nullptr,
+              (uint64_t*)nullptr, perm, n, 0u, tile, op, ValIdentity(), hist, (uint32_t*)nullptr, 0u);
 }
 
 void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_outrow, cudaStream_t st) {

@@ -23,10 +23,24 @@ struct GradsDev {
   float b1p[PB_MAX_SLOTS], b2p[PB_MAX_SLOTS];  // Adam accumulated beta powers of the slot's feature group
 };
 
+// arguments of the backward segment kernels (see pb_kernels.cu)
+struct SegArgs {
+  const uint32_t* skey;
+  const uint32_t* sval;        // occurrence position | slot << 24
+  const uint32_t* occ_outrow;  // nullptr: one id per sample per slot (output row == occurrence)
+  const uint32_t* row_off;
+  const uint32_t* tick_ptr;
+  const uint32_t* nan_tick;
+  float* partials;  // 2 rows of dim floats per PIECE-block
+  float* vw_stage;
+  uint32_t n, batch, piece, shared_groups;
+};
+constexpr uint32_t PB_PIECE = 32;
+
 void launch_fill_cells(Cell* cells, uint64_t n, cudaStream_t st);
 void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, cudaStream_t st);
 void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const SlotsDev& sl, const uint64_t* ids,
-                  uint32_t n, uint32_t* occ_cell, uint8_t* occ_slot, cudaStream_t st);
+                  uint32_t n, uint32_t* occ_cell, cudaStream_t st);
 void launch_init_new(const TableDev& t, const HyperDev& hy, const OptimDev& op, uint32_t max_new, cudaStream_t st);
 void launch_gather(const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell, const uint32_t* row_off,
                    uint32_t n_out, uint32_t batch, void* out, bool out_f32, cudaStream_t st);
@@ -35,14 +49,12 @@ void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell
 void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,
                      uint32_t* nan_tick, int32_t* status, cudaStream_t st);
 void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                          const GradsDev& gr, bool f16, const uint32_t* skey, const uint32_t* socc,
-                          const uint8_t* occ_slot, const uint32_t* occ_outrow, const uint32_t* row_off, uint32_t n,
-                          uint32_t batch, const uint32_t* tick, const uint32_t* nan_tick, float* vw_stage, cudaStream_t st);
+                          const GradsDev& gr, bool f16, const SegArgs& a, cudaStream_t st);
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
                           const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st);
 uint32_t radix_tile(uint32_t n);
-int launch_radix_sort_u32(const uint32_t* keys_in, uint32_t n, uint32_t bits, uint32_t* keys_a, uint32_t* vals_a,
-                          uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, cudaStream_t st);
+int launch_radix_sort_u32(const uint32_t* keys_in, uint32_t n, uint32_t bits, const SlotsDev& sl, uint32_t* keys_a,
+                          uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, cudaStream_t st);
 void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* perm, uint32_t* counts,
                                uint32_t* hist, cudaStream_t st);
 void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_outrow, cudaStream_t st);

@@ -132,6 +132,10 @@ class BatchContext:
             cfg.sqrt_scaling[i] = int(bool(sqrt_scaling[i])) if sqrt_scaling is not None else 0
         N.check(self.lib.pb_ctx_set_slots(self.h, C.byref(cfg)))
 
+    def set_strict_reduce(self, on=True):
+        """Sequential (reference-order) gradient reduction for any multiplicity; see persia_b200.h."""
+        N.check(self.lib.pb_ctx_set_strict_reduce(self.h, int(on)))
+
     def forward(self, shard, ids, slot_occ_off, batch, row_off=None, training=True, out=None):
         """ids: flat device int64-bit ids (slot-major); slot_occ_off: host list, n_slots+1;
         row_off: device int32 CSR offsets [n_slots*batch+1] or None (one id per sample per slot).
