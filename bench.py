@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--sets", type=int, default=16, help="rotating input/grad/output buffer sets (> L2 in total)")
     ap.add_argument("--cpu-seconds", type=float, default=float(os.environ.get("PB_BENCH_CPU_SECONDS", 12)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--equal-card", action="store_true", help="diagnostic: every slot gets rows/slots ids (no tiny slots)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
 
@@ -235,6 +236,9 @@ def single_gpu(args, torch, lib):
     S, B, K, Wm = args.slots, args.batch, args.steps, max(args.warmup, 3)
     rows = int(args.rows)
     card = W.scaled_cardinalities(rows, S)
+    if args.equal_card:
+        card = np.full(S, rows // S, np.int64)
+        card[0] += rows - int(card.sum())
     pf = W.index_prefixes(S)
     slot_off = [s * B for s in range(S + 1)]
     n_occ = S * B

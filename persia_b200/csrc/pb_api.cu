@@ -2,6 +2,7 @@
 // kernel sequencing.  No torch types, no allocation on the hot path after the first call of a given size.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -84,6 +85,7 @@ struct pb_ctx {
   bool has_slots = false;
   // forward -> backward state (the EW's post_forward_buffer entry, mod.rs:1087-1098)
   uint32_t* occ_cell = nullptr;
+  uint32_t* occ_row = nullptr;
   uint32_t* occ_outrow = nullptr;
   uint32_t* row_off = nullptr;
   bool multi_id = false;
@@ -96,6 +98,9 @@ struct pb_ctx {
   uint32_t* nan_tick = nullptr;
   float* vw_stage = nullptr;
   size_t vw_stage_floats = 0;
+  uint2* heads = nullptr;       // compacted piece heads of the sorted occurrence list
+  uint2* owners = nullptr;      // (first boundary, segment start) of cut segments
+  uint32_t* seg_counts = nullptr;
   float* partials = nullptr;  // 2 rows per PIECE-block of the sorted occurrence list
   size_t partials_floats = 0;
   bool strict_reduce = false;
@@ -126,12 +131,12 @@ int ensure_alloc(pb_table* t) {
   if (want > (1ull << 31)) return fail(PB_ERR_INVALID, "capacity too large for a 2^31-cell index");
   d.n_cells = next_pow2(want);
   d.cell_mask = d.n_cells - 1;
-  d.new_list_cap = d.capacity < (1u << 22) ? d.capacity : (1u << 22);
-  if (d.new_list_cap < 1024) d.new_list_cap = 1024;
+  d.bucket_mask = d.n_cells / BUCKET - 1;
   PB_CUDA(cudaMalloc(&d.cells, sizeof(Cell) * ((size_t)d.n_cells + 1)));
   PB_CUDA(cudaMalloc(&d.rows, sizeof(float) * (size_t)d.capacity * d.stride));
   PB_CUDA(cudaMalloc(&d.counters, sizeof(uint32_t) * CTR_COUNT));
-  PB_CUDA(cudaMalloc(&d.new_list, sizeof(uint32_t) * (size_t)d.new_list_cap));
+  PB_CUDA(cudaMalloc(&d.row_lead, sizeof(unsigned long long) * (size_t)d.capacity));
+  PB_CUDA(cudaMemset(d.row_lead, 0, sizeof(unsigned long long) * (size_t)d.capacity));
   PB_CUDA(cudaMemset(d.counters, 0, sizeof(uint32_t) * CTR_COUNT));
   launch_fill_cells(d.cells, (uint64_t)d.n_cells + 1, 0);
   PB_CUDA(cudaDeviceSynchronize());
@@ -150,17 +155,6 @@ int ensure_scratch(pb_table* t, uint32_t n) {
   return PB_OK;
 }
 
-int ensure_new_list(pb_table* t, uint32_t n, cudaStream_t st) {
-  if (n <= t->d.new_list_cap) return PB_OK;
-  PB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(t->d.new_list);
-  t->d.new_list = nullptr;
-  uint32_t cap = next_pow2(n);
-  PB_CUDA(cudaMalloc(&t->d.new_list, sizeof(uint32_t) * (size_t)cap));
-  t->d.new_list_cap = cap;
-  return PB_OK;
-}
-
 int ready_for_training(pb_table* t) {
   if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered (OptimizerNotFoundError)");
   if (!t->has_hy) return fail(PB_ERR_STATE, "embedding server not configured (NotConfiguredError)");
@@ -172,6 +166,7 @@ SlotsDev no_slots() {
   std::memset(&s, 0, sizeof(s));
   s.n_slots = 1;
   s.spacing = ~0ULL;
+  s.spacing_bits = 64;
   return s;
 }
 
@@ -180,6 +175,7 @@ int make_slots(const pb_slots_cfg& cfg, const uint32_t* h_occ_off, SlotsDev& s) 
   if (cfg.n_slots == 0 || cfg.n_slots > PB_MAX_SLOTS) return fail(PB_ERR_INVALID, "n_slots must be in 1..PB_MAX_SLOTS");
   s.n_slots = cfg.n_slots;
   s.spacing = cfg.prefix_bit > 0 ? ((1ULL << (64 - cfg.prefix_bit)) - 1) : ~0ULL;
+  s.spacing_bits = 64 - cfg.prefix_bit;
   for (uint32_t i = 0; i < cfg.n_slots; ++i) {
     s.prefix[i] = cfg.prefix[i];
     s.sqrt_scaling[i] = cfg.sqrt_scaling[i];
@@ -234,7 +230,7 @@ int pb_table_destroy(pb_table* t) {
     cudaFree(t->d.cells);
     cudaFree(t->d.rows);
     cudaFree(t->d.counters);
-    cudaFree(t->d.new_list);
+    cudaFree(t->d.row_lead);
   }
   if (t->scratch) cudaFree(t->scratch);
   delete t;
@@ -316,6 +312,7 @@ int pb_table_clear(pb_table* t, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   launch_fill_cells(t->d.cells, (uint64_t)t->d.n_cells + 1, st);
   PB_CUDA(cudaMemsetAsync(t->d.counters, 0, sizeof(uint32_t) * CTR_COUNT, st));
+  PB_CUDA(cudaMemsetAsync(t->d.row_lead, 0, sizeof(unsigned long long) * (size_t)t->d.capacity, st));
   return PB_OK;
 }
 
@@ -336,14 +333,12 @@ int pb_lookup(pb_table* t, const uint64_t* d_signs, uint32_t n, int training, fl
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
   if (training) {
-    if ((rc = ensure_new_list(t, n, st))) return rc;
     launch_begin_batch(t->d, nullptr, st);
-    launch_probe(MODE_TRAIN, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
-    launch_init_new(t->d, t->hy, t->op, n, st);
+    launch_probe(MODE_TRAIN, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   } else {
-    launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
+    launch_probe(MODE_FIND, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   }
-  launch_gather(t->d, sl, t->scratch, nullptr, n, 0, d_out, true, st);
+  launch_gather(t->d, sl, t->scratch, nullptr, n, 0, d_out, true, nullptr, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
 }
@@ -357,7 +352,7 @@ int pb_update(pb_table* t, const uint64_t* d_signs, const float* d_grads, uint32
   if ((rc = ensure_alloc(t))) return rc;
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
-  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
+  launch_probe(MODE_FIND, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   if (t->op.kind == PB_OPT_ADAM) {  // get_batch_level_state: one power step per request (optim.rs:155-197)
     t->b1p_direct *= t->op.b1;
     t->b2p_direct *= t->op.b2;
@@ -376,7 +371,7 @@ int pb_set_rows(pb_table* t, const uint64_t* d_signs, const float* d_entries, ui
   if (rc) return rc;
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
-  launch_probe(MODE_SET, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
+  launch_probe(MODE_SET, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   launch_copy_entries(true, t->d, t->scratch, n, const_cast<float*>(d_entries), nullptr, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
@@ -391,7 +386,7 @@ int pb_get_rows(pb_table* t, const uint64_t* d_signs, uint32_t n, float* d_entri
   if (rc) return rc;
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
-  launch_probe(MODE_FIND, false, t->d, t->hy, sl, d_signs, n, t->scratch, st);
+  launch_probe(MODE_FIND, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   launch_copy_entries(false, t->d, t->scratch, n, d_entries, d_found, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
@@ -430,11 +425,7 @@ int pb_farmhash64(const uint64_t* d_in, uint32_t n, uint64_t* d_out, void* strea
   return PB_OK;
 }
 
-uint64_t pb_partition_workspace(uint32_t n) {
-  uint32_t tile = radix_tile(n ? n : 1);
-  uint32_t nb = (uint32_t)(((uint64_t)(n ? n : 1) + tile - 1) / tile);
-  return (uint64_t)256 * nb * sizeof(uint32_t);
-}
+uint64_t pb_partition_workspace(uint32_t n) { return partition_workspace_bytes(n); }
 
 int pb_partition_by_shard(const uint64_t* d_signs, uint32_t n, uint32_t R, uint32_t* d_perm, uint32_t* d_counts,
                           void* d_work, uint64_t work_bytes, void* stream) {
@@ -458,13 +449,14 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   uint32_t tile = radix_tile(max_occurrences);
   size_t nb = (n + tile - 1) / tile;
   // smaller batches pick smaller tiles: size the histogram for the worst case (n/2048 tiles, capped at 128)
-  size_t hist_elems = 4 * 65536;  // four passes x (<= 256 tiles x 256 digits)
+  size_t hist_elems = 4 * (size_t)radix_hist_words();  // four passes x (<= 256 tiles x 512 bins)
   (void)nb;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
   A((void**)&c->occ_cell, 4 * n);
+  A((void**)&c->occ_row, 4 * n);
   A((void**)&c->occ_outrow, 4 * n);
   A((void**)&c->row_off, 4 * ((size_t)max_out_rows + 1));
   A((void**)&c->keys_a, 4 * n);
@@ -473,6 +465,9 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   A((void**)&c->vals_b, 4 * n);
   A((void**)&c->hist, 4 * hist_elems);
   A((void**)&c->nan_tick, 4 * PB_MAX_SLOTS);
+  A((void**)&c->heads, 8 * n);
+  A((void**)&c->owners, 8 * (n / PB_PIECE + 2));
+  A((void**)&c->seg_counts, 16);
   A((void**)&c->dev_tick, 4);
   if (e == cudaSuccess) e = cudaMemset(c->nan_tick, 0, 4 * PB_MAX_SLOTS);
   if (e == cudaSuccess) e = cudaMemset(c->dev_tick, 0, 4);
@@ -488,8 +483,9 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (!c) return PB_OK;
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {c->occ_cell, c->occ_outrow, c->row_off, c->keys_a, c->vals_a,
-                  c->keys_b,   c->vals_b,   c->hist,       c->nan_tick, c->vw_stage, c->dev_tick, c->partials};
+  void* ptrs[] = {c->occ_cell, c->occ_row, c->occ_outrow, c->row_off, c->keys_a, c->vals_a,
+                  c->keys_b,   c->vals_b,   c->hist,       c->nan_tick, c->vw_stage, c->dev_tick, c->partials,
+                  c->heads,    c->owners,   c->seg_counts};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete c;
@@ -543,14 +539,13 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   SlotsDev sl;
   if ((rc = make_slots(c->slots, h_slot_occ_off, sl))) return rc;
   if (training) {
-    if ((rc = ensure_new_list(t, n_occ, st))) return rc;
     launch_begin_batch(t->d, c->dev_tick, st);
-    launch_probe(MODE_TRAIN, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, st);
-    launch_init_new(t->d, t->hy, t->op, n_occ, st);
+    launch_probe(MODE_TRAIN, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
   } else {
-    launch_probe(MODE_FIND, true, t->d, t->hy, sl, d_ids, n_occ, c->occ_cell, st);
+    launch_probe(MODE_FIND, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
   }
-  launch_gather(t->d, sl, c->occ_cell, d_row_off, (uint32_t)n_out, batch, d_out_f16, false, st);
+  launch_gather(t->d, sl, c->occ_cell, d_row_off, (uint32_t)n_out, batch, d_out_f16, false,
+                training ? c->occ_row : nullptr, st);
   if (training) {
     c->n_occ = n_occ;
     c->batch = batch;
@@ -594,10 +589,10 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     gr.b2p[s] = t->b2p[s];
   }
   uint32_t elems = c->batch * t->d.dim;
-  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
-  uint32_t bits = 1;
-  while ((1ull << bits) <= (uint64_t)t->d.n_cells + 1) ++bits;
-  int which = launch_radix_sort_u32(c->occ_cell, c->n_occ, bits, sl, c->keys_a, c->vals_a, c->keys_b, c->vals_b, c->hist, st);
+  const uint32_t sort_tiles = (c->n_occ + radix_tile(c->n_occ ? c->n_occ : 1) - 1) / radix_tile(c->n_occ ? c->n_occ : 1);
+  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, c->hist, sort_tiles * 512u, st);
+  int which = launch_radix_sort_leader(t->d, c->occ_row, c->n_occ, sl, c->keys_a, c->vals_a, c->keys_b, c->vals_b, c->hist,
+                                     c->seg_counts, st);
   const uint32_t* skey = which == 0 ? c->keys_a : c->keys_b;
   const uint32_t* socc = which == 0 ? c->vals_a : c->vals_b;
   float* vw = nullptr;
@@ -616,6 +611,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
   SegArgs a;
   a.skey = skey;
   a.sval = socc;
+  a.occ_row = c->occ_row;
   a.occ_outrow = c->multi_id ? c->occ_outrow : nullptr;
   a.row_off = c->multi_id ? c->row_off : nullptr;
   a.tick_ptr = c->dev_tick;
@@ -640,7 +636,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     }
     a.partials = c->partials;
   }
-  launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st);
+  launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, c->heads, c->owners, c->seg_counts, st);
   c->pending = false;
   PB_CUDA(cudaGetLastError());
   return PB_OK;

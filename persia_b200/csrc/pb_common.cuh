@@ -11,12 +11,15 @@ namespace pb {
 constexpr uint64_t KEY_EMPTY = ~0ULL;          // hash-index cell holds no key
 constexpr uint32_t ROW_PENDING = 0xFFFFFFFFu;  // key claimed, row not yet published (never visible across kernels)
 constexpr uint32_t ROW_NONE = 0xFFFFFFFEu;     // key present but no storage (shard was full when it was admitted)
+constexpr uint32_t BUCKET = 8;                 // cells per bucket
 
-// One cell of the open-addressing index: 16 B, one 32 B sector holds two.
+// One cell of the index: 16 B.  Cells are grouped in buckets of BUCKET = 8 (one 128 B line): a sign's home
+// bucket is mix64(sign) & bucket_mask; a lookup reads whole buckets with 8 lanes, so the probe length is
+// counted in lines (almost always one), not cells.
 struct __align__(16) Cell {
   unsigned long long key;
   uint32_t row;
-  uint32_t tick;  // batch number of the last training touch (recency for eviction)
+  uint32_t aux;   // reserved (recency lives in TableDev::row_lead)
 };
 
 // farmhash 1.1.5 hash64 of an 8-byte LE value (FarmHash HashLen0to16, 8..16 branch).
@@ -49,17 +52,17 @@ struct TableDev {
   Cell* cells;         // n_cells + 1 entries; the last one is reserved for sign == KEY_EMPTY
   float* rows;         // capacity * stride floats: emb(dim) ++ optimizer state ++ pad
   uint32_t* counters;  // see CTR_* below
-  uint32_t* new_list;  // cells admitted by the running request
-  uint64_t cell_mask;  // n_cells - 1
+  unsigned long long* row_lead;  // per row: (batch number << 32) | ~(first occurrence of the sign in that batch)
+  uint64_t cell_mask;    // n_cells - 1
+  uint32_t bucket_mask;  // n_cells / BUCKET - 1
   uint32_t n_cells;
   uint32_t capacity;
   uint32_t dim, stride, state_floats;
-  uint32_t new_list_cap;
 };
 
 enum {
   CTR_ROWS = 0,      // bump allocator of row storage
-  CTR_NEW = 1,       // cells admitted by the current request (reset by k_begin_batch)
+  CTR_SPARE = 1,
   CTR_TICK = 2,      // batch number: bumped on the device by every training request (CUDA-graph safe)
   CTR_MISS = 3,      // infer misses / refused admissions
   CTR_GRAD_MISS = 4, // gradient ids not found

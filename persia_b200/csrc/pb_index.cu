@@ -1,0 +1,453 @@
+// pb_index.cu — the shard's hash index and row store: find-or-admit, row initialisation, gather + pool
+//  and the small id-preprocessing kernels (A2, A3 hash).
+#include "pb_device.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------------------------------------
+// A4 (admission part): initialise a newly admitted row, eight lanes cooperating.
+// emb_entry.rs:28-68 + optim.rs:299-302.  The value stream restates rand 0.8.4 SmallRng (Xoshiro256++
+// seeded through rand_core's PCG32 expansion) + UniformFloat<f32> — PARITY UNPINNED (no reference test
+// asserts an initial value); the oracle carries the same restatement.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void init_row(const TableDev& t, const HyperDev& hy, const OptimDev& op, uint64_t seed,
+                                      uint32_t row_idx, uint32_t sub) {
+  // rand_core::SeedableRng::seed_from_u64 (PCG32 stream) -> 4 x u64 state
+  uint64_t st = seed;
+  uint32_t wds[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    st = st * 6364136223846793005ULL + 11634580027462260723ULL;
+    uint32_t xs = (uint32_t)(((st >> 18) ^ st) >> 27);
+    uint32_t rot = (uint32_t)(st >> 59);
+    wds[k] = (xs >> rot) | (xs << ((32 - rot) & 31));
+  }
+  uint64_t s0 = wds[0] | ((uint64_t)wds[1] << 32), s1 = wds[2] | ((uint64_t)wds[3] << 32);
+  uint64_t s2 = wds[4] | ((uint64_t)wds[5] << 32), s3 = wds[6] | ((uint64_t)wds[7] << 32);
+  float* row = t.rows + (size_t)row_idx * t.stride;
+  // every lane walks the whole stream (it is sequential) and keeps the elements it owns
+  for (uint32_t e = 0; e < t.dim; ++e) {
+    uint64_t sum = s0 + s3;
+    uint64_t r = ((sum << 23) | (sum >> 41)) + s0;
+    uint64_t tt = s1 << 17;
+    s2 ^= s0;
+    s3 ^= s1;
+    s1 ^= s2;
+    s0 ^= s3;
+    s2 ^= tt;
+    s3 = (s3 << 45) | (s3 >> 19);
+    if ((e & (BUCKET - 1)) == sub) {
+      uint32_t bits = ((uint32_t)(r >> 32) >> 9) | 0x3f800000u;
+      float v01 = __fsub_rn(__uint_as_float(bits), 1.0f);
+      row[e] = __fadd_rn(__fmul_rn(v01, hy.scale), hy.lo);
+    }
+  }
+  float sv = (op.kind == PB_OPT_ADAGRAD || op.kind == PB_OPT_ADAGRAD_VW) ? op.init_acc : 0.0f;
+  for (uint32_t e = t.dim + sub; e < t.stride; e += BUCKET) row[e] = (e < t.dim + t.state_floats) ? sv : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A2 + A4 (index part): eight lanes per id occurrence; a group reads one 128 B bucket per step.
+//   MODE_FIND   read-only probe (inference lookup, update, get_rows)
+//   MODE_TRAIN  find, refresh recency, admit on miss (training lookup)
+//   MODE_SET    find or force-admit without initialisation (set_embedding)
+// Output: the index cell of every occurrence (n_cells + 1 when the sign has no storage).  The row number
+// is read from the cell by the kernels that follow, so nothing here ever waits on another thread.
+// The group that admits a sign also initialises its row (emb_entry.rs:28-68 + optim.rs:299-302).
+// Recency (get_refresh, eviction_map.rs:48-60) is not written here: thousands of occurrences of one hot
+// sign would all store to the same cell; the gather kernel records it per row after a block-level dedup.
+// Invariant that makes "an empty cell in the bucket => the sign is absent" true: a sign is always stored
+// in the first bucket of its probe sequence that had a free cell when it was admitted, and cells are
+// never freed in place.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool PREFIX>
+__global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev op, SlotsDev sl,
+                                               const uint64_t* __restrict__ ids, uint32_t n,
+                                               uint32_t* __restrict__ occ_cell) {
+  const uint32_t tick = t.counters[CTR_TICK];
+  const uint32_t i = (blockIdx.x * 256 + threadIdx.x) / BUCKET;
+  const uint32_t sub = threadIdx.x % BUCKET;
+  const uint32_t gshift = (threadIdx.x & 31) & ~(BUCKET - 1);  // this group's bit offset in a warp ballot
+  const uint32_t h_none = t.n_cells + 1;
+  const bool valid = i < n;
+  // lane 0 of the group derives the sign (prefix arithmetic, hash); the other seven take it by shuffle
+  uint64_t sign = 0ULL;
+  uint32_t bucket = 0;
+  if (valid && sub == 0) {
+    sign = ids[i];
+    if (PREFIX) {
+      uint64_t p = sl.prefix[slot_of_occ(sl, i)];
+      if (p) sign = mod_mersenne(sign, sl.spacing_bits) + p;  // indices_add_prefix, mod.rs:402-429
+    }
+    bucket = (uint32_t)(mix64(sign)) & t.bucket_mask;
+  }
+  sign = __shfl_sync(0xffffffffu, sign, gshift);
+  bucket = __shfl_sync(0xffffffffu, bucket, gshift);
+  const bool special = (sign == KEY_EMPTY);  // the one sign that collides with the empty marker has its own cell
+  const unsigned long long stored = special ? 0ULL : sign;
+  bool admit = true;
+  if (MODE == MODE_TRAIN && hy.admit_p < 1.0f) {  // reference: unseeded thread_rng draw (unpinned)
+    float u = (float)(mix64(sign ^ (0x9E3779B97F4A7C15ULL * (tick + 1))) >> 40) * (1.0f / 16777216.0f);
+    admit = u < hy.admit_p;
+  }
+  uint32_t result = h_none;
+  bool done = !valid;
+  for (uint32_t step = 0; step <= t.bucket_mask + 1u; ++step) {
+    if (!__any_sync(0xffffffffu, !done)) break;
+    const bool look = !done && (!special || sub == 0);
+    const uint32_t cell = special ? t.n_cells : bucket * BUCKET + sub;
+    uint4 c = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, ROW_PENDING, 0u);
+    if (look) c = __ldcg(reinterpret_cast<const uint4*>(t.cells + cell));
+    const unsigned long long kk = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
+    const uint32_t mm = (__ballot_sync(0xffffffffu, look && kk == stored) >> gshift) & 0xffu;
+    const uint32_t em = (__ballot_sync(0xffffffffu, look && kk == KEY_EMPTY) >> gshift) & 0xffu;
+    const uint32_t lm = mm ? __ffs(mm) - 1 : 0;  // lane of the match
+    const uint32_t le = em ? __ffs(em) - 1 : 0;  // lane of the first free cell
+    // groups that must try to admit the sign into the first free cell of this bucket
+    const bool try_ins = !done && !mm && em && MODE != MODE_FIND && admit;
+    unsigned long long old = 0ULL;
+    if (try_ins && sub == le) old = atomicCAS(&t.cells[cell].key, KEY_EMPTY, stored);
+    old = __shfl_sync(0xffffffffu, old, gshift + le);
+    const bool won_cas = try_ins && old == KEY_EMPTY;  // lane `le` of this group admitted the sign
+    const uint32_t free_cell = special ? t.n_cells : bucket * BUCKET + le;
+    uint32_t row = 0;
+    if (won_cas && sub == le) {
+      row = atomicAdd(&t.counters[CTR_ROWS], 1u);
+      if (row >= t.capacity) {
+        row = ROW_NONE;
+        atomicAdd(&t.counters[CTR_FULL], 1u);
+      } else {
+        atomicAdd(&t.counters[CTR_ADMIT], 1u);
+      }
+      *reinterpret_cast<volatile uint32_t*>(&t.cells[free_cell].row) = row;
+    }
+    row = __shfl_sync(0xffffffffu, row, gshift + le);
+    if (MODE == MODE_TRAIN && won_cas && row != ROW_NONE) init_row(t, hy, op, sign, row, sub);  // all 8 lanes
+    if (!done) {
+      if (mm) {
+        result = special ? t.n_cells : bucket * BUCKET + lm;
+        done = true;
+      } else if (em) {
+        if (!try_ins) {
+          done = true;  // absent (and not admitted)
+        } else if (won_cas) {
+          result = (row == ROW_NONE) ? h_none : free_cell;
+          done = true;
+        } else if (old == stored) {  // a duplicate occurrence won the race for the same sign
+          result = free_cell;
+          done = true;
+        }
+        // else: another sign took the cell — look at the same bucket again
+      } else {
+        if (special) done = true;  // cannot happen: the reserved cell only ever holds this sign
+        bucket = (bucket + 1) & t.bucket_mask;  // full bucket without the sign: next line
+      }
+    }
+  }
+  if (valid && sub == 0) {
+    if (MODE != MODE_SET && result == h_none) atomicAdd(&t.counters[CTR_MISS], 1u);
+    occ_cell[i] = result;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A4 + A5: gather + pool.  A group of G lanes owns one output row (slot s, sample b); lanes stride over
+// VEC-float chunks of the embedding.  f32 accumulate in sample order, optional 1/sqrt(max(n,1)), RNE to
+// f16 (mod.rs:547-579, persia-common lib.rs:157-161).  OUT_F32 writes plain f32 rows (pb_lookup).
+// ------------------------------------------------------------------------------------------------
+template <int VEC, bool OUT_F32>
+__device__ __forceinline__ void store_out(void* out, size_t o, const float (&acc)[VEC], float scale) {
+  if (OUT_F32) {
+    float* dst = reinterpret_cast<float*>(out) + o;
+    if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[VEC > 1 ? 2 : 0], acc[VEC > 1 ? 3 : 0]);
+    else dst[0] = acc[0];
+  } else {
+    __half* dst = reinterpret_cast<__half*>(out) + o;
+    if (VEC == 4) {
+      __half2 a = __floats2half2_rn(__fmul_rn(acc[0], scale), __fmul_rn(acc[VEC > 1 ? 1 : 0], scale));
+      __half2 b = __floats2half2_rn(__fmul_rn(acc[VEC > 1 ? 2 : 0], scale), __fmul_rn(acc[VEC > 1 ? 3 : 0], scale));
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(dst) = pk;
+    } else {
+      dst[0] = __float2half_rn(__fmul_rn(acc[0], scale));
+    }
+  }
+}
+
+constexpr int GATHER_ROWS = 4;  // output rows per group in the one-id-per-sample layout (independent loads in flight)
+constexpr int ELECT_SLOTS = 512;  // per-block table for the leader election (>= 2 x rows a block can touch at once)
+
+// Leader election (training): the backward pass groups the occurrences of a batch by the position of the
+// first occurrence of their sign.  Every row keeps (batch number << 32 | ~position) in TableDev::row_lead and
+// occurrences race with atomicMax — but a hot sign (tiny-cardinality slots repeat an id thousands of times)
+// would serialise thousands of atomics on one address, so a block first reduces its own occurrences in
+// shared memory and only distinct rows go to global memory.  The high half doubles as the row's recency
+// (get_refresh, eviction_map.rs:48-60).
+struct Elector {
+  uint32_t* keys;  // row or 0xFFFFFFFF
+  uint32_t* best;  // min position
+  __device__ __forceinline__ void clear() {
+    for (uint32_t i = threadIdx.x; i < ELECT_SLOTS; i += blockDim.x) {
+      keys[i] = 0xFFFFFFFFu;
+      best[i] = 0xFFFFFFFFu;
+    }
+  }
+  __device__ __forceinline__ void offer(uint32_t row, uint32_t pos) {
+    uint32_t h = (row * 2654435761u) >> 23;  // 9 bits
+    for (;;) {
+      uint32_t k = atomicCAS(&keys[h], 0xFFFFFFFFu, row);
+      if (k == 0xFFFFFFFFu || k == row) {
+        atomicMin(&best[h], pos);
+        return;
+      }
+      h = (h + 1) & (ELECT_SLOTS - 1);
+    }
+  }
+  __device__ __forceinline__ void publish(unsigned long long* row_lead, unsigned long long lead_hi) {
+    for (uint32_t i = threadIdx.x; i < ELECT_SLOTS; i += blockDim.x) {
+      uint32_t row = keys[i];
+      if (row != 0xFFFFFFFFu) {
+        const unsigned long long mine = lead_hi | (uint32_t)~best[i];
+        if (__ldcg(&row_lead[row]) < mine) atomicMax(&row_lead[row], mine);
+      }
+    }
+  }
+};
+
+template <int VEC, int G, bool OUT_F32>
+__global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, const uint32_t* __restrict__ occ_cell,
+                                                     const uint32_t* __restrict__ row_off, uint32_t n_out,
+                                                     uint32_t batch, void* __restrict__ out,
+                                                     uint32_t* __restrict__ occ_row) {
+  __shared__ uint32_t el_keys[ELECT_SLOTS], el_best[ELECT_SLOTS];
+  Elector el{el_keys, el_best};
+  const bool elect = occ_row != nullptr;  // training forward
+  const unsigned long long lead_hi = elect ? ((unsigned long long)t.counters[CTR_TICK] << 32) : 0ULL;
+  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const uint32_t lane = threadIdx.x % G;
+  const uint32_t nvec = t.dim / VEC;
+  if (elect) {
+    el.clear();
+    __syncthreads();
+  }
+  if (!row_off) {
+    // one occurrence per output row: GATHER_ROWS rows per group, every stage issued for all rows before use
+    const uint32_t r0 = group * GATHER_ROWS;
+    uint32_t cell[GATHER_ROWS], row[GATHER_ROWS];
+#pragma unroll
+    for (int k = 0; k < GATHER_ROWS; ++k) cell[k] = (r0 + k < n_out) ? occ_cell[r0 + k] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < GATHER_ROWS; ++k) row[k] = (cell[k] <= t.n_cells) ? t.cells[cell[k]].row : ROW_NONE;
+    if (elect && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < GATHER_ROWS; ++k)
+        if (r0 + k < n_out) {
+          occ_row[r0 + k] = row[k] < t.capacity ? row[k] : ROW_NONE;
+          if (row[k] < t.capacity) {
+            if ((256 / G) * GATHER_ROWS > ELECT_SLOTS / 2) atomicMax(&t.row_lead[row[k]], lead_hi | (uint32_t)~(r0 + k));
+            else el.offer(row[k], r0 + k);
+          }
+        }
+    }
+    for (uint32_t c = lane; c < nvec; c += G) {
+      float v[GATHER_ROWS][VEC];
+#pragma unroll
+      for (int k = 0; k < GATHER_ROWS; ++k) {
+        if (row[k] < t.capacity) {
+          load_vec<VEC>(t.rows + (size_t)row[k] * t.stride + c * VEC, v[k]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) v[k][e] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < GATHER_ROWS; ++k)
+        if (r0 + k < n_out) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+            if (!OUT_F32) v[k][e] = __fadd_rn(0.0f, v[k][e]);  // the EW adds into a zeroed row (mod.rs:555-561)
+          store_out<VEC, OUT_F32>(out, (size_t)(r0 + k) * t.dim + c * VEC, v[k], 1.0f);  // 1/sqrt(max(1,1)) = 1
+        }
+    }
+  } else if (group < n_out) {
+    const uint32_t gid = group;
+    const uint32_t beg = row_off[gid], end = row_off[gid + 1];
+    float scale = 1.0f;
+    if (!OUT_F32 && batch && sl.sqrt_scaling[gid / batch]) {
+      uint32_t cnt = end - beg;
+      scale = __fdiv_rn(1.0f, __fsqrt_rn((float)(cnt > 1 ? cnt : 1)));
+    }
+    // a sample may hold more ids than the election table can absorb at once: spill straight to global
+    const bool direct = (end - beg) * (256 / G) > ELECT_SLOTS / 2;
+    for (uint32_t c = lane; c < nvec; c += G) {
+      float acc[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = 0.0f;
+      for (uint32_t j = beg; j < end; ++j) {
+        uint32_t h = occ_cell[j];
+        uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+        if (elect && c == 0) {  // lane 0, first chunk: once per occurrence
+          occ_row[j] = row < t.capacity ? row : ROW_NONE;
+          if (row < t.capacity) {
+            if (direct) atomicMax(&t.row_lead[row], lead_hi | (uint32_t)~j);
+            else el.offer(row, j);
+          }
+        }
+        if (row >= t.capacity) continue;
+        float v[VEC];
+        load_vec<VEC>(t.rows + (size_t)row * t.stride + c * VEC, v);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], v[k]);
+      }
+      store_out<VEC, OUT_F32>(out, (size_t)gid * t.dim + c * VEC, acc, scale);
+    }
+  }
+  if (elect) {
+    __syncthreads();
+    el.publish(t.row_lead, lead_hi);
+  }
+}
+
+// set_embedding / get_rows: whole entries (emb ++ state), one group per sign.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_copy_entries(TableDev t, const uint32_t* __restrict__ occ_cell, uint32_t n,
+                                                      float* __restrict__ entries, uint8_t* __restrict__ found) {
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  uint32_t h = occ_cell[warp];
+  uint32_t elen = t.dim + t.state_floats;
+  uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+  bool ok = row < t.capacity;
+  if (!WRITE && found && lane == 0) found[warp] = ok ? 1 : 0;
+  float* e = entries + (size_t)warp * elen;
+  if (WRITE) {
+    if (!ok) return;
+    float* dst = t.rows + (size_t)row * t.stride;
+    for (uint32_t i = lane; i < t.stride; i += 32) dst[i] = (i < elen) ? e[i] : 0.0f;
+  } else {
+    const float* src = t.rows + (size_t)row * t.stride;
+    for (uint32_t i = lane; i < elen; i += 32) e[i] = ok ? src[i] : 0.0f;
+  }
+}
+
+// CSR row offsets -> output row of every occurrence (multi-id slots)
+__global__ void __launch_bounds__(256) k_expand_rows(const uint32_t* __restrict__ row_off, uint32_t n_out,
+                                                     uint32_t* __restrict__ occ_outrow) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_out) return;
+  for (uint32_t j = row_off[r]; j < row_off[r + 1]; ++j) occ_outrow[j] = r;
+}
+
+__global__ void __launch_bounds__(256) k_add_prefix(SlotsDev sl, const uint64_t* __restrict__ ids, uint32_t n,
+                                                    uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t p = sl.prefix[slot_of_occ(sl, i)];
+  uint64_t v = ids[i];
+  out[i] = p ? mod_mersenne(v, sl.spacing_bits) + p : v;
+}
+
+__global__ void __launch_bounds__(256) k_shard_of(const uint64_t* __restrict__ signs, uint32_t n, uint32_t R,
+                                                  uint32_t* __restrict__ shard, uint64_t* __restrict__ hash) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t h = farmhash64_u64(signs[i]);
+  if (shard) shard[i] = (uint32_t)(h % R);
+  if (hash) hash[i] = h;
+}
+
+// Opens a training request on the device: bumps the batch number, empties the admitted-cell list and
+// records the batch number in the context (so the backward of this batch recognises its own NaN marks).
+__global__ void k_begin_batch(uint32_t* counters, uint32_t* ctx_tick) {
+  uint32_t t = counters[CTR_TICK] + 1;
+  counters[CTR_TICK] = t;
+  if (ctx_tick) *ctx_tick = t;
+}
+
+__global__ void k_fill_cells(Cell* cells, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  Cell e;
+  e.key = KEY_EMPTY;
+  e.row = ROW_PENDING;
+  e.aux = 0;
+  for (; i < n; i += stride) cells[i] = e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers (host)
+// ------------------------------------------------------------------------------------------------
+void launch_fill_cells(Cell* cells, uint64_t n, cudaStream_t st) { PB_LAUNCH(k_fill_cells, 148 * 8, 256, 0, st, cells, n); }
+
+void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, cudaStream_t st) {
+  PB_LAUNCH(k_begin_batch, 1, 1, 0, st, t.counters, ctx_tick);
+}
+
+void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const OptimDev& op, const SlotsDev& sl,
+                  const uint64_t* ids, uint32_t n, uint32_t* occ_cell, cudaStream_t st) {
+  if (!n) return;
+  uint32_t g = cdiv((uint64_t)n * BUCKET, 256);
+  if (mode == MODE_FIND) {
+    if (prefix) PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_FIND, true>), g, 256, 0, st, t, hy, op, sl, ids, n, occ_cell);
+    else PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_FIND, false>), g, 256, 0, st, t, hy, op, sl, ids, n, occ_cell);
+  } else if (mode == MODE_TRAIN) {
+    if (prefix) PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_TRAIN, true>), g, 256, 0, st, t, hy, op, sl, ids, n, occ_cell);
+    else PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_TRAIN, false>), g, 256, 0, st, t, hy, op, sl, ids, n, occ_cell);
+  } else {
+    PB_LAUNCH_F(FAM_PROBE, (k_probe<MODE_SET, false>), g, 256, 0, st, t, hy, op, sl, ids, n, occ_cell);
+  }
+}
+
+template <int VEC, bool F32>
+static void gather_dispatch(int G, const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell,
+                            const uint32_t* row_off, uint32_t n_out, uint32_t batch, void* out, uint32_t* occ_row,
+                            cudaStream_t st) {
+  uint32_t grid;
+#define PB_G(GG)                                                                                              \
+  case GG:                                                                                                    \
+    grid = cdiv((uint64_t)(row_off ? n_out : cdiv(n_out, GATHER_ROWS)) * GG, 256);                            \
+    PB_LAUNCH_F(FAM_GATHER, (k_gather_pool<VEC, GG, F32>), grid, 256, 0, st, t, sl, occ_cell, row_off, n_out, batch, out, occ_row);  \
+    break;
+  switch (G) {
+    PB_G(1) PB_G(2) PB_G(4) PB_G(8) PB_G(16) PB_G(32)
+  }
+#undef PB_G
+}
+
+void launch_gather(const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell, const uint32_t* row_off,
+                   uint32_t n_out, uint32_t batch, void* out, bool out_f32, uint32_t* occ_row, cudaStream_t st) {
+  if (!n_out) return;
+  int vec, G;
+  vec_group(t.dim, vec, G);
+  if (vec == 4) {
+    if (out_f32) gather_dispatch<4, true>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
+    else gather_dispatch<4, false>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
+  } else {
+    if (out_f32) gather_dispatch<1, true>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
+    else gather_dispatch<1, false>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
+  }
+}
+
+void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell, uint32_t n, float* entries,
+                         uint8_t* found, cudaStream_t st) {
+  if (!n) return;
+  uint32_t grid = cdiv((uint64_t)n * 32, 256);
+  if (write) PB_LAUNCH(k_copy_entries<true>, grid, 256, 0, st, t, occ_cell, n, entries, found);
+  else PB_LAUNCH(k_copy_entries<false>, grid, 256, 0, st, t, occ_cell, n, entries, found);
+}
+
+void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_outrow, cudaStream_t st) {
+  if (n_out) PB_LAUNCH(k_expand_rows, cdiv(n_out, 256), 256, 0, st, row_off, n_out, occ_outrow);
+}
+
+void launch_add_prefix(const SlotsDev& sl, const uint64_t* ids, uint32_t n, uint64_t* out, cudaStream_t st) {
+  if (n) PB_LAUNCH(k_add_prefix, cdiv(n, 256), 256, 0, st, sl, ids, n, out);
+}
+
+void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st) {
+  if (n) PB_LAUNCH(k_shard_of, cdiv(n, 256), 256, 0, st, signs, n, R, shard, hash);
+}
+
+}  // namespace pb

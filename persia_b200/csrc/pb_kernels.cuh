@@ -13,6 +13,7 @@ struct SlotsDev {
   uint8_t sqrt_scaling[PB_MAX_SLOTS];
   uint32_t n_slots;
   uint64_t spacing;  // 2^(64-prefix_bit) - 1
+  uint32_t spacing_bits;  // 64 - prefix_bit
 };
 
 // per-batch gradient table (GradientBatch, persia-core/src/backward.rs:74-106)
@@ -25,7 +26,8 @@ struct GradsDev {
 
 // arguments of the backward segment kernels (see pb_kernels.cu)
 struct SegArgs {
-  const uint32_t* skey;
+  const uint32_t* skey;        // first occurrence of the occurrence's sign (n = no storage), sorted
+  const uint32_t* occ_row;     // row number of every occurrence (ROW_NONE = no storage)
   const uint32_t* sval;        // occurrence position | slot << 24
   const uint32_t* occ_outrow;  // nullptr: one id per sample per slot (output row == occurrence)
   const uint32_t* row_off;
@@ -39,24 +41,28 @@ constexpr uint32_t PB_PIECE = 32;
 
 void launch_fill_cells(Cell* cells, uint64_t n, cudaStream_t st);
 void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, cudaStream_t st);
-void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const SlotsDev& sl, const uint64_t* ids,
-                  uint32_t n, uint32_t* occ_cell, cudaStream_t st);
-void launch_init_new(const TableDev& t, const HyperDev& hy, const OptimDev& op, uint32_t max_new, cudaStream_t st);
+void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const OptimDev& op, const SlotsDev& sl,
+                  const uint64_t* ids, uint32_t n, uint32_t* occ_cell, cudaStream_t st);
 void launch_gather(const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell, const uint32_t* row_off,
-                   uint32_t n_out, uint32_t batch, void* out, bool out_f32, cudaStream_t st);
+                   uint32_t n_out, uint32_t batch, void* out, bool out_f32, uint32_t* occ_row, cudaStream_t st);
 void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell, uint32_t n, float* entries,
                          uint8_t* found, cudaStream_t st);
 void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,
-                     uint32_t* nan_tick, int32_t* status, cudaStream_t st);
+                     uint32_t* nan_tick, int32_t* status, uint32_t* zero, uint32_t zero_words, cudaStream_t st);
 void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                          const GradsDev& gr, bool f16, const SegArgs& a, cudaStream_t st);
+                          const GradsDev& gr, bool f16, const SegArgs& a, uint2* heads, uint2* owners,
+                          uint32_t* counts, cudaStream_t st);
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
                           const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st);
 uint32_t radix_tile(uint32_t n);
-int launch_radix_sort_u32(const uint32_t* keys_in, uint32_t n, uint32_t bits, const SlotsDev& sl, uint32_t* keys_a,
-                          uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, cudaStream_t st);
+uint32_t radix_hist_words();
+int launch_radix_sort_leader(const TableDev& t, const uint32_t* occ_row, uint32_t n, const SlotsDev& sl, uint32_t* keys_a,
+                             uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* zero4,
+                             cudaStream_t st);
+void launch_zero_words(uint32_t* p, uint32_t n_words, cudaStream_t st);
+uint64_t partition_workspace_bytes(uint32_t n);
 void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* perm, uint32_t* counts,
-                               uint32_t* hist, cudaStream_t st);
+                               uint32_t* work, cudaStream_t st);
 void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_outrow, cudaStream_t st);
 void launch_add_prefix(const SlotsDev& sl, const uint64_t* ids, uint32_t n, uint64_t* out, cudaStream_t st);
 void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st);
