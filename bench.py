@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--rows", type=float, default=float(os.environ.get("PB_BENCH_ROWS", 1e8)),
                     help="resident rows per GPU (weak scaling: the table grows with N)")
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
-    ap.add_argument("--dim", type=int, default=None, help="default: 64 at N=1 (configs[1]), 128 at N>1 (configs[2..3])")
+    ap.add_argument("--dim", type=int, default=None, help="default 64 (configs[1]) at every N so that the scaling runs compare like with like; --dim 128 gives configs[2..3]")
     ap.add_argument("--slots", type=int, default=26)
     ap.add_argument("--alpha", type=float, default=1.05)
     ap.add_argument("--sets", type=int, default=16, help="rotating input/grad/output buffer sets (> L2 in total)")
@@ -162,7 +162,7 @@ def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    dim = args.dim or (64 if args.gpus == 1 else 128)
+    dim = args.dim or 64
     card = W.scaled_cardinalities(int(args.rows) * args.gpus, args.slots)
     arm = CpuArm(args, dim, card)
     per_step = 2 * arm.n_threads
@@ -192,8 +192,8 @@ def reference_main(args):
 
 def workload_config(args, dim, card, n_gpus):
     return {
-        "workload": f"configs[{1 if n_gpus == 1 else 2}]: {args.slots} Criteo-shaped slots, {int(args.rows) * n_gpus:.3g} "
-                    f"rows, dim {dim}, batch {args.batch}/GPU, Adagrad, training forward + backward",
+        "workload": f"configs[{1 if dim == 64 else 2}] shape x {n_gpus} GPU: {args.slots} Criteo-shaped slots, "
+                    f"{int(args.rows) * n_gpus:.3g} rows, dim {dim}, batch {args.batch}/GPU, Adagrad, training forward + backward",
         "global_batch": args.batch * n_gpus, "slots": args.slots, "dim": dim, "rows_total": int(args.rows) * n_gpus,
         "zipf_alpha": args.alpha, "optimizer": "adagrad(lr=0.01, init=0.01, eps=1e-10)",
         "parallelism": "single shard" if n_gpus == 1 else f"rows hash-sharded over {n_gpus} GPUs (farmhash64 % {n_gpus}), "
@@ -372,10 +372,15 @@ def single_gpu(args, torch, lib):
     ku = kern.get("reduce_update", {}).get("us_per_step")
     upd_bytes = n_occ * W.algorithmic_bytes_per_id(dim, state, "backward")
     achieved = upd_bytes / (ku * 1e-6) / 1e9 if ku else None
+    traffic = None
+    try:  # DRAM bytes per launch of the same kernel from the round's `ncu --set full` capture (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("k_reduce_update")
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": "k_reduce_update (A8+A9: gradient segment-reduce + Adagrad step + weight bound)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": upd_bytes,
         "whole_step": {"algorithmic_bytes": n_occ * bytes_per_id,
                        "achieved_gbs": n_occ * bytes_per_id / (ms_per_step * 1e-3) / 1e9,

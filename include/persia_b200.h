@@ -129,6 +129,17 @@ int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg);
  * embedding_worker_service/mod.rs:799-811, slower on tiny-cardinality slots. */
 int pb_ctx_set_strict_reduce(pb_ctx* c, int on);
 
+/* A context in owner mode serves the already-sharded requests of the multi-GPU exchange (the PS side of
+ * lookup_mixed / update_gradient_mixed): `batch` is then just the number of signs received and the u16
+ * sample-index limit of a PersiaBatch does not apply. */
+int pb_ctx_set_owner_mode(pb_ctx* c, int on);
+
+/* The EW's regrouping around the fan-out (embedding_worker_service/mod.rs:886-919): out[i] = src[perm[i]]. */
+int pb_permute_u64(const uint64_t* d_src, const uint32_t* d_perm, uint32_t n, uint64_t* d_out, void* stream);
+/* Rows of row_bytes (multiple of 16): scatter == 0: out[i] = src[perm[i]]; scatter != 0: out[perm[i]] = src[i]. */
+int pb_permute_rows(const void* d_src, const uint32_t* d_perm, uint32_t n, uint32_t row_bytes, int scatter, void* d_out,
+                    void* stream);
+
 /* EmbeddingWorker::forward_batched_direct for summation slots
  * (embedding_worker_service/mod.rs:1076-1107 -> :874-942 -> PS :162-262 -> :486-629).
  * d_ids: flat raw ids, slot-major then sample-major; d_row_off[n_slots*batch+1] CSR offsets, or NULL

@@ -104,6 +104,7 @@ struct pb_ctx {
   float* partials = nullptr;  // 2 rows per PIECE-block of the sorted occurrence list
   size_t partials_floats = 0;
   bool strict_reduce = false;
+  bool owner_mode = false;  // serves already-sharded requests: no u16 sample-index limit
   bool shared_groups = false;  // two slots carry the same non-zero prefix (one feature group)
 };
 
@@ -512,12 +513,34 @@ int pb_ctx_set_strict_reduce(pb_ctx* c, int on) {
   return PB_OK;
 }
 
+int pb_ctx_set_owner_mode(pb_ctx* c, int on) {
+  if (!c) return fail(PB_ERR_INVALID, "null argument");
+  c->owner_mode = on != 0;
+  return PB_OK;
+}
+
+int pb_permute_u64(const uint64_t* d_src, const uint32_t* d_perm, uint32_t n, uint64_t* d_out, void* stream) {
+  if (n && (!d_src || !d_perm || !d_out)) return fail(PB_ERR_INVALID, "null argument");
+  launch_permute_u64(d_src, d_perm, n, d_out, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_permute_rows(const void* d_src, const uint32_t* d_perm, uint32_t n, uint32_t row_bytes, int scatter, void* d_out,
+                    void* stream) {
+  if (n && (!d_src || !d_perm || !d_out)) return fail(PB_ERR_INVALID, "null argument");
+  if (row_bytes == 0 || row_bytes % 16) return fail(PB_ERR_INVALID, "row_bytes must be a multiple of 16");
+  launch_permute_rows(d_src, d_perm, n, row_bytes, scatter, d_out, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
 int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
                const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream) {
   if (!t || !c || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
   if (!c->has_slots) return fail(PB_ERR_STATE, "pb_ctx_set_slots not called");
   if (t->device != c->device) return fail(PB_ERR_INVALID, "table and context live on different devices");
-  if (batch > 65535) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
+  if (batch > 65535 && !c->owner_mode) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
   uint32_t S = c->slots.n_slots;
   uint64_t n_out = (uint64_t)S * batch;
   if (n_occ > c->max_occ || n_out > c->max_out) return fail(PB_ERR_CAPACITY, "batch exceeds the context's capacity");

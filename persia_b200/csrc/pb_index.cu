@@ -376,6 +376,26 @@ __global__ void k_fill_cells(Cell* cells, uint64_t n) {
   for (; i < n; i += stride) cells[i] = e;
 }
 
+// Row permutations around the shard exchange (the EW regroups signs per parameter server and puts the
+// returned rows back in batch order, mod.rs:886-919): out[i] = src[perm[i]] (gather) or out[perm[i]] = src[i]
+// (scatter), rows of `row_words` 16-byte words, one group of lanes per row.
+__global__ void __launch_bounds__(256) k_permute_rows(const uint4* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                      uint32_t n, uint32_t row_words, uint32_t lanes, int scatter,
+                                                      uint4* __restrict__ out) {
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / lanes;
+  const uint32_t l = threadIdx.x % lanes;
+  if (g >= n) return;
+  const uint32_t p = perm[g];
+  const size_t from = (size_t)(scatter ? g : p) * row_words, to = (size_t)(scatter ? p : g) * row_words;
+  for (uint32_t w = l; w < row_words; w += lanes) out[to + w] = src[from + w];
+}
+
+__global__ void __launch_bounds__(256) k_permute_u64(const uint64_t* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                     uint32_t n, uint64_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[perm[i]];
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers (host)
 // ------------------------------------------------------------------------------------------------
@@ -444,6 +464,19 @@ void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_o
 
 void launch_add_prefix(const SlotsDev& sl, const uint64_t* ids, uint32_t n, uint64_t* out, cudaStream_t st) {
   if (n) PB_LAUNCH(k_add_prefix, cdiv(n, 256), 256, 0, st, sl, ids, n, out);
+}
+
+void launch_permute_rows(const void* src, const uint32_t* perm, uint32_t n, uint32_t row_bytes, int scatter, void* out,
+                         cudaStream_t st) {
+  if (!n) return;
+  uint32_t words = row_bytes / 16, lanes = 1;
+  while (lanes < words && lanes < 32) lanes <<= 1;
+  PB_LAUNCH(k_permute_rows, cdiv((uint64_t)n * lanes, 256), 256, 0, st, (const uint4*)src, perm, n, words, lanes, scatter,
+            (uint4*)out);
+}
+
+void launch_permute_u64(const uint64_t* src, const uint32_t* perm, uint32_t n, uint64_t* out, cudaStream_t st) {
+  if (n) PB_LAUNCH(k_permute_u64, cdiv(n, 256), 256, 0, st, src, perm, n, out);
 }
 
 void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st) {

@@ -66,6 +66,9 @@ void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, ui
 void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_outrow, cudaStream_t st);
 void launch_add_prefix(const SlotsDev& sl, const uint64_t* ids, uint32_t n, uint64_t* out, cudaStream_t st);
 void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st);
+void launch_permute_rows(const void* src, const uint32_t* perm, uint32_t n, uint32_t row_bytes, int scatter, void* out,
+                         cudaStream_t st);
+void launch_permute_u64(const uint64_t* src, const uint32_t* perm, uint32_t n, uint64_t* out, cudaStream_t st);
 uint64_t launch_count();
 enum { FAM_PROBE = 0, FAM_INIT, FAM_GATHER, FAM_NAN, FAM_SORT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
 void profile_enable(bool on);

@@ -136,6 +136,10 @@ class BatchContext:
         """Sequential (reference-order) gradient reduction for any multiplicity; see persia_b200.h."""
         N.check(self.lib.pb_ctx_set_strict_reduce(self.h, int(on)))
 
+    def set_owner_mode(self, on=True):
+        """Serve already-sharded requests (no u16 sample-index limit); see persia_b200.h."""
+        N.check(self.lib.pb_ctx_set_owner_mode(self.h, int(on)))
+
     def forward(self, shard, ids, slot_occ_off, batch, row_off=None, training=True, out=None):
         """ids: flat device int64-bit ids (slot-major); slot_occ_off: host list, n_slots+1;
         row_off: device int32 CSR offsets [n_slots*batch+1] or None (one id per sample per slot).
@@ -221,3 +225,25 @@ def partition_by_shard(signs, R):
     work = torch.empty(wb, dtype=torch.uint8, device=signs.device)
     N.check(lib.pb_partition_by_shard(_ptr(signs), n, R, _ptr(perm), _ptr(counts), _ptr(work), wb, _stream(signs.device)))
     return perm, counts
+
+
+def permute_u64(src, perm, out=None):
+    """out[i] = src[perm[i]] for int64-bit ids."""
+    lib = N.load()
+    src = _as_i64_bits(src)
+    if out is None:
+        out = torch.empty(perm.numel(), dtype=torch.int64, device=src.device)
+    N.check(lib.pb_permute_u64(_ptr(src), _ptr(perm), perm.numel(), _ptr(out), _stream(src.device)))
+    return out
+
+
+def permute_rows(src, perm, scatter=False, out=None):
+    """Rows of a 2-D contiguous tensor: gather out[i] = src[perm[i]] or scatter out[perm[i]] = src[i]."""
+    lib = N.load()
+    assert src.is_contiguous() and src.dim() == 2
+    row_bytes = src.shape[1] * src.element_size()
+    if out is None:
+        out = torch.empty_like(src)
+    N.check(lib.pb_permute_rows(_ptr(src), _ptr(perm), perm.numel(), row_bytes, int(scatter), _ptr(out),
+                                _stream(src.device)))
+    return out
