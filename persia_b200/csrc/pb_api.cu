@@ -183,6 +183,9 @@ int make_slots(const pb_slots_cfg& cfg, const uint32_t* h_occ_off, SlotsDev& s) 
     s.occ_off[i] = h_occ_off[i];
   }
   s.occ_off[cfg.n_slots] = h_occ_off[cfg.n_slots];
+  s.uniform = cfg.n_slots ? (h_occ_off[cfg.n_slots] - h_occ_off[0]) / cfg.n_slots : 0;
+  for (uint32_t i = 0; i <= cfg.n_slots && s.uniform; ++i)
+    if (h_occ_off[i] != i * s.uniform) s.uniform = 0;
   return PB_OK;
 }
 
@@ -612,8 +615,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     gr.b2p[s] = t->b2p[s];
   }
   uint32_t elems = c->batch * t->d.dim;
-  const uint32_t sort_tiles = (c->n_occ + radix_tile(c->n_occ ? c->n_occ : 1) - 1) / radix_tile(c->n_occ ? c->n_occ : 1);
-  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, c->hist, sort_tiles * 512u, st);
+  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, c->hist, radix_hist_zero_words(c->n_occ), st);
   int which = launch_radix_sort_leader(t->d, c->occ_row, c->n_occ, sl, c->keys_a, c->vals_a, c->keys_b, c->vals_b, c->hist,
                                      c->seg_counts, st);
   const uint32_t* skey = which == 0 ? c->keys_a : c->keys_b;

@@ -5,6 +5,7 @@
 namespace pb {
 
 __device__ __forceinline__ uint32_t slot_of_occ(const SlotsDev& s, uint32_t occ) {
+  if (s.uniform) return occ / s.uniform;
   // slot boundaries are ascending; n_slots <= 128 -> <= 7 steps over kernel-parameter memory
   uint32_t lo = 0, hi = s.n_slots;
   while (hi - lo > 1) {

@@ -14,6 +14,7 @@ struct SlotsDev {
   uint32_t n_slots;
   uint64_t spacing;  // 2^(64-prefix_bit) - 1
   uint32_t spacing_bits;  // 64 - prefix_bit
+  uint32_t uniform;       // occurrences per slot when every slot holds the same number (one id per sample), else 0
 };
 
 // per-batch gradient table (GradientBatch, persia-core/src/backward.rs:74-106)
@@ -56,6 +57,7 @@ void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev&
                           const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st);
 uint32_t radix_tile(uint32_t n);
 uint32_t radix_hist_words();
+uint32_t radix_hist_zero_words(uint32_t n);
 int launch_radix_sort_leader(const TableDev& t, const uint32_t* occ_row, uint32_t n, const SlotsDev& sl, uint32_t* keys_a,
                              uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* zero4,
                              cudaStream_t st);

@@ -18,8 +18,13 @@ namespace pb {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 4;                    // keys per thread held in registers
-constexpr int RS_SUB = RS_THREADS * RS_ITEMS;  // 1024 keys per sub-tile: warp w owns keys [128 w, 128 w + 128)
+constexpr int RS_ITEMS = 2;                    // keys per thread held in registers
+constexpr int RS_SUB = RS_THREADS * RS_ITEMS;  // 512 keys per sub-tile: warp w owns keys [64 w, 64 w + 64)
+constexpr int RS_COARSE = 16;                  // tiles per coarse histogram row
+constexpr int RS_MAX_TILES = 256;
+constexpr int RS_COARSE_ROWS = RS_MAX_TILES / RS_COARSE;
+// One pass's histogram region: [RS_COARSE_ROWS coarse rows][RS_MAX_TILES fine rows] x RS_BINS words.  A scatter
+// block folds <= 16 coarse rows + <= 15 fine rows instead of every tile's row.
 constexpr int RS_BITS = 9;
 constexpr int RS_BINS = 1 << RS_BITS;          // 512: two bins per thread
 
@@ -52,6 +57,9 @@ struct ValOccSlot {
 // the row must be zero on entry.  Also writes the materialised keys, clears the later passes' rows and
 // (block 0) the segment-list counters of the backward pass.
 constexpr int RH_KEYS = 512;
+__device__ __forceinline__ uint32_t* fine_row(uint32_t* h, uint32_t tile_idx) { return h + (RS_COARSE_ROWS + tile_idx) * RS_BINS; }
+__device__ __forceinline__ const uint32_t* fine_row(const uint32_t* h, uint32_t tile_idx) { return h + (RS_COARSE_ROWS + tile_idx) * RS_BINS; }
+__device__ __forceinline__ uint32_t* coarse_row(uint32_t* h, uint32_t tile_idx) { return h + (tile_idx / RS_COARSE) * RS_BINS; }
 template <typename SRC>
 __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(SRC src, uint32_t n, uint32_t tile,
                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ hist,
@@ -81,15 +89,22 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(SRC src, uint32_t n, 
   }
   __syncthreads();
   const uint32_t row = beg / tile;  // RH_KEYS divides the tile size
+  const bool first_of_tile = beg % tile == 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     uint32_t bin = threadIdx.x + h * RS_THREADS;
-    uint32_t o = row * RS_BINS + bin;
-    if (cnt[bin]) atomicAdd(&hist[o], cnt[bin]);
-    if (beg % tile == 0) {
-      if (z1) z1[o] = 0;
-      if (z2) z2[o] = 0;
-      if (z3) z3[o] = 0;
+    if (cnt[bin]) {
+      atomicAdd(fine_row(hist, row) + bin, cnt[bin]);
+      atomicAdd(coarse_row(hist, row) + bin, cnt[bin]);
+    }
+    if (first_of_tile) {
+      uint32_t* z[3] = {z1, z2, z3};
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (z[k]) {
+          fine_row(z[k], row)[bin] = 0;
+          if (row % RS_COARSE == 0) coarse_row(z[k], row)[bin] = 0;
+        }
     }
   }
 }
@@ -114,22 +129,36 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __
   // thread d owns bins d and d + 256
   uint32_t below[2] = {0, 0}, total[2] = {0, 0};
   const uint32_t nb = gridDim.x;
-  for (uint32_t b0 = 0; b0 < nb; b0 += 16) {
-    uint32_t v[16][2];
+  const uint32_t ncoarse = (nb + RS_COARSE - 1) / RS_COARSE, cb = blockIdx.x / RS_COARSE;
+  {
+    uint32_t v[RS_COARSE_ROWS][2];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      bool in = b0 + u < nb;
-      v[u][0] = in ? hist[(b0 + u) * RS_BINS + d] : 0u;
-      v[u][1] = in ? hist[(b0 + u) * RS_BINS + d + RS_THREADS] : 0u;
+    for (int c = 0; c < RS_COARSE_ROWS; ++c) {
+      bool in = (uint32_t)c < ncoarse;
+      v[c][0] = in ? hist[c * RS_BINS + d] : 0u;
+      v[c][1] = in ? hist[c * RS_BINS + d + RS_THREADS] : 0u;
+    }
+    uint32_t f[RS_COARSE][2];
+#pragma unroll
+    for (int u = 0; u < RS_COARSE; ++u) {
+      uint32_t b = cb * RS_COARSE + u;
+      bool in = b < blockIdx.x;
+      f[u][0] = in ? fine_row(hist, b)[d] : 0u;
+      f[u][1] = in ? fine_row(hist, b)[d + RS_THREADS] : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      total[0] += v[u][0];
-      total[1] += v[u][1];
-      if (b0 + u < blockIdx.x) {
-        below[0] += v[u][0];
-        below[1] += v[u][1];
+    for (int c = 0; c < RS_COARSE_ROWS; ++c) {
+      total[0] += v[c][0];
+      total[1] += v[c][1];
+      if ((uint32_t)c < cb) {
+        below[0] += v[c][0];
+        below[1] += v[c][1];
       }
+    }
+#pragma unroll
+    for (int u = 0; u < RS_COARSE; ++u) {
+      below[0] += f[u][0];
+      below[1] += f[u][1];
     }
   }
   uint32_t x[2] = {total[0], total[1]};  // inclusive scans of the two halves over the 256 threads
@@ -218,7 +247,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __
       if (valid) {
         if (keys_out) keys_out[pos] = key[r];
         vals_out[pos] = val[r];
-        if (hist_next) atomicAdd(&hist_next[(pos / tile) * RS_BINS + ((key[r] >> next_shift) & (RS_BINS - 1))], 1u);
+        if (hist_next) {
+          const uint32_t nd = (key[r] >> next_shift) & (RS_BINS - 1), nt = pos / tile;
+          atomicAdd(fine_row(hist_next, nt) + nd, 1u);
+          atomicAdd(coarse_row(hist_next, nt) + nd, 1u);
+        }
       }
     }
     __syncthreads();
@@ -237,7 +270,7 @@ __global__ void k_counts_from_hist(const uint32_t* __restrict__ hist, uint32_t n
   uint32_t d = threadIdx.x;
   if (d >= R) return;
   uint32_t t = 0;
-  for (uint32_t b = 0; b < n_blocks; ++b) t += hist[b * RS_BINS + d];
+  for (uint32_t c = 0; c * RS_COARSE < n_blocks; ++c) t += hist[c * RS_BINS + d];  // coarse rows hold the column sums
   counts[d] = t;
 }
 
@@ -248,10 +281,13 @@ uint32_t radix_tile(uint32_t n) {
   // tiles are multiples of the 1024-key sub-tile; at most 256 of them so that folding the block-major
   // histogram inside every scatter block stays cheap
   uint32_t tile = RS_SUB;
-  while (cdiv(n, tile) > 256) tile += RS_SUB;
+  while (cdiv(n, tile) > RS_MAX_TILES) tile += RS_SUB;
   return tile;
 }
-uint32_t radix_hist_words() { return 256u * RS_BINS; }  // one pass: <= 256 tiles x 512 bins
+uint32_t radix_hist_words() { return (uint32_t)(RS_COARSE_ROWS + RS_MAX_TILES) * RS_BINS; }  // one pass's region
+uint32_t radix_hist_zero_words(uint32_t n) {  // what must be zero before the histogram pass of an n-key sort
+  return (uint32_t)(RS_COARSE_ROWS + cdiv(n ? n : 1, radix_tile(n ? n : 1))) * RS_BINS;
+}
 
 void launch_zero_words(uint32_t* p, uint32_t n_words, cudaStream_t st);
 
@@ -296,7 +332,7 @@ void launch_zero_words(uint32_t* p, uint32_t n_words, cudaStream_t st) {
   if (n_words) PB_LAUNCH(k_zero_words, cdiv(n_words, 1024) < 148 ? cdiv(n_words, 1024) : 148, 256, 0, st, p, n_words);
 }
 
-// d_work layout: [256 x 512 histogram words][n materialised shard ids]
+// d_work layout: [one pass's histogram region][n materialised shard ids]
 uint64_t partition_workspace_bytes(uint32_t n) { return ((uint64_t)radix_hist_words() + n) * sizeof(uint32_t); }
 
 void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* perm, uint32_t* counts,
@@ -305,7 +341,7 @@ void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, ui
   uint32_t* hist = work;
   uint32_t* keys = work + radix_hist_words();
   SrcShard src{signs, R};
-  launch_zero_words(hist, nb * RS_BINS, st);
+  launch_zero_words(hist, radix_hist_zero_words(n), st);
   if (n)
     PB_LAUNCH((k_radix_hist<SrcShard>), cdiv(n, RH_KEYS), RS_THREADS, 0, st, src, n, tile, keys, hist, (uint32_t*)nullptr,
               (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr);

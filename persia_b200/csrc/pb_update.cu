@@ -222,20 +222,29 @@ __device__ __forceinline__ void load_grad(float (&g)[VEC], const PieceCtx& pc, c
     const __half* gp = reinterpret_cast<const __half*>(pc.gbase) + off;
     if (VEC == 4) {
       uint2 raw = *reinterpret_cast<const uint2*>(gp);
-      float2 x = __half22float2(*reinterpret_cast<__half2*>(&raw.x));
-      float2 y = __half22float2(*reinterpret_cast<__half2*>(&raw.y));
+      // +-inf -> +-65504 (persia-common lib.rs:163-180), two halves per instruction; finite halves are inside already
+      const __half2 lim = __floats2half2_rn(65504.0f, 65504.0f);
+      __half2 h0 = __hmin2(__hmax2(*reinterpret_cast<__half2*>(&raw.x), __hneg2(lim)), lim);
+      __half2 h1 = __hmin2(__hmax2(*reinterpret_cast<__half2*>(&raw.y), __hneg2(lim)), lim);
+      float2 x = __half22float2(h0);
+      float2 y = __half22float2(h1);
       g[0] = x.x; g[VEC > 1 ? 1 : 0] = x.y; g[VEC > 1 ? 2 : 0] = y.x; g[VEC > 1 ? 3 : 0] = y.y;
     } else {
-      g[0] = __half2float(gp[0]);
+      g[0] = fminf(fmaxf(__half2float(gp[0]), -65504.0f), 65504.0f);
     }
   } else {
     load_vec<VEC>(reinterpret_cast<const float*>(pc.gbase) + off, g);
   }
 }
 
-template <int VEC, bool F16>
+template <int VEC, bool F16, bool PLAIN>
 __device__ __forceinline__ void add_grad(float (&acc)[VEC], const float (&g)[VEC], const PieceCtx& pc, const SegArgs& a,
                                          uint32_t orow) {
+  if (PLAIN) {  // no loss scale, no sqrt scaling: the gradient is summed as it is
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], g[k]);
+    return;
+  }
   float f = 1.0f;
   if (pc.sqrt_sc) {  // mirror of the forward scaling, without its max(.,1) (mod.rs:757-768)
     uint32_t cnt = a.row_off ? a.row_off[orow + 1] - a.row_off[orow] : 1u;
@@ -244,7 +253,6 @@ __device__ __forceinline__ void add_grad(float (&acc)[VEC], const float (&g)[VEC
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     float v = g[k];
-    if (F16) v = fminf(fmaxf(v, -65504.0f), 65504.0f);  // +-inf -> +-65504; finite halves are inside already
     if (pc.do_scale) v = __fmul_rn(v, pc.inv_scale);    // x 1/scale_factor
     if (pc.sqrt_sc) v = __fmul_rn(v, f);
     acc[k] = __fadd_rn(acc[k], v);
@@ -253,9 +261,9 @@ __device__ __forceinline__ void add_grad(float (&acc)[VEC], const float (&g)[VEC
 
 // sum of the (scaled) gradients of occurrences [j0, j1) of `slot`, chunk c, in position order.
 // Full batches of 8 and 4 occurrences have all their loads issued together; the adds stay sequential.
-template <int VEC, bool F16>
-__device__ __forceinline__ void reduce_piece(float (&acc)[VEC], const SegArgs& a, const TableDev& t, const SlotsDev& sl,
-                                             const GradsDev& gr, uint32_t slot, uint32_t j0, uint32_t j1, uint32_t c) {
+template <int VEC, bool F16, bool PLAIN>
+__device__ __forceinline__ void reduce_piece_t(float (&acc)[VEC], const SegArgs& a, const TableDev& t, const SlotsDev& sl,
+                                               const GradsDev& gr, uint32_t slot, uint32_t j0, uint32_t j1, uint32_t c) {
   PieceCtx pc;
   pc.gbase = gr.ptr[slot];
   pc.inv_scale = gr.inv_scale[slot];
@@ -270,37 +278,45 @@ __device__ __forceinline__ void reduce_piece(float (&acc)[VEC], const SegArgs& a
     float g[8][VEC];
 #pragma unroll
     for (int u = 0; u < 8; ++u) orow[u] = val_occ(a.sval[j + u]);
-    if (a.occ_outrow) {
+    if (!PLAIN && a.occ_outrow) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) orow[u] = a.occ_outrow[orow[u]];
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) load_grad<VEC, F16>(g[u], pc, a, t, orow[u], c);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) add_grad<VEC, F16>(acc, g[u], pc, a, orow[u]);
+    for (int u = 0; u < 8; ++u) add_grad<VEC, F16, PLAIN>(acc, g[u], pc, a, orow[u]);
   }
   if (j + 4 <= j1) {
     uint32_t orow[4];
     float g[4][VEC];
 #pragma unroll
     for (int u = 0; u < 4; ++u) orow[u] = val_occ(a.sval[j + u]);
-    if (a.occ_outrow) {
+    if (!PLAIN && a.occ_outrow) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) orow[u] = a.occ_outrow[orow[u]];
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) load_grad<VEC, F16>(g[u], pc, a, t, orow[u], c);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) add_grad<VEC, F16>(acc, g[u], pc, a, orow[u]);
+    for (int u = 0; u < 4; ++u) add_grad<VEC, F16, PLAIN>(acc, g[u], pc, a, orow[u]);
     j += 4;
   }
   for (; j < j1; ++j) {
     uint32_t orow = val_occ(a.sval[j]);
-    if (a.occ_outrow) orow = a.occ_outrow[orow];
+    if (!PLAIN && a.occ_outrow) orow = a.occ_outrow[orow];
     float g[VEC];
     load_grad<VEC, F16>(g, pc, a, t, orow, c);
-    add_grad<VEC, F16>(acc, g, pc, a, orow);
+    add_grad<VEC, F16, PLAIN>(acc, g, pc, a, orow);
   }
+}
+
+template <int VEC, bool F16>
+__device__ __forceinline__ void reduce_piece(float (&acc)[VEC], const SegArgs& a, const TableDev& t, const SlotsDev& sl,
+                                             const GradsDev& gr, uint32_t slot, uint32_t j0, uint32_t j1, uint32_t c) {
+  // the common case (one id per sample, loss scale 1, no sqrt scaling) gets a branch-free body
+  if (!a.occ_outrow && !gr.do_scale[slot] && !sl.sqrt_scaling[slot]) reduce_piece_t<VEC, F16, true>(acc, a, t, sl, gr, slot, j0, j1, c);
+  else reduce_piece_t<VEC, F16, false>(acc, a, t, sl, gr, slot, j0, j1, c);
 }
 
 // the optimizer step of one segment given per-lane reduced chunks produced by `reduce(c, acc)`
