@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--sets", type=int, default=16, help="rotating input/grad/output buffer sets (> L2 in total)")
     ap.add_argument("--cpu-seconds", type=float, default=float(os.environ.get("PB_BENCH_CPU_SECONDS", 12)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-grouping", action="store_true", help="run the backward's grouping inside pb_backward")
     ap.add_argument("--equal-card", action="store_true", help="diagnostic: every slot gets rows/slots ids (no tiny slots)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
@@ -247,6 +248,7 @@ def single_gpu(args, torch, lib):
     sh.set_optimizer(N.OPT_ADAGRAD, lr=0.01, initialization=0.01, eps=1e-10)
     sh.configure()
     ctx = SH.BatchContext(n_occ, n_occ, pf, device=dev)
+    ctx.set_async_grouping(not args.sync_grouping)
 
     # ---- make every row resident (the reference's "warm table"): admit all ids of every slot
     t_fill = time.time()
@@ -342,11 +344,28 @@ def single_gpu(args, torch, lib):
         ids_stage = torch.empty(n_occ, dtype=torch.int64, device=dev)
         out_e2e = outs[0]
 
-        def e2e_step(k):
+        def e2e_body(k):
             ids_stage.copy_(ids_pinned[k], non_blocking=True)
             ctx.forward(sh, ids_stage, slot_off, B, training=True, out=out_e2e)
             st = ctx.backward(sh, grads[k], want_status=True)
             status_host.copy_(st, non_blocking=True)
+
+        e2e_graphs = None
+        if use_graph:  # the whole call sequence incl. the H2D / D2H copies is one graph per pinned input buffer
+            e2e_body(0)
+            stream.synchronize()
+            e2e_graphs = []
+            for k in range(n_sets):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=stream):
+                    e2e_body(k)
+                e2e_graphs.append(gph)
+
+        def e2e_step(k):
+            if e2e_graphs is not None:
+                e2e_graphs[k].replay()
+            else:
+                e2e_body(k)
             stream.synchronize()  # the caller reads the status: one host sync per step, as persia's backward does
 
         for i in range(Wm):
@@ -399,7 +418,8 @@ def single_gpu(args, torch, lib):
                        table_fill_seconds=round(t_fill, 2),
                        l2="inputs larger than L2: %.1f GB table + %d rotating id/grad/output sets (%.0f MB)" % (
                            resident * 4.0 * (dim + state) / 1e9, n_sets, n_sets * 2 * n_occ * dim * 2 / 1e6),
-                       launch="CUDA graph replay, one graph per buffer set" if graphs is not None else "kernel by kernel"),
+                       launch=("CUDA graph replay, one graph per buffer set" if graphs is not None else "kernel by kernel") +
+                              ("" if args.sync_grouping else "; grouping forked onto the context's side stream in pb_forward")),
         "clocks": clocks,
         "e2e": {"value": B / (ms_e2e / K * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8,
                 "d2h_bytes_per_step": S * 4, "ms_per_step": ms_e2e / K,

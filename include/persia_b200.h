@@ -129,6 +129,13 @@ int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg);
  * embedding_worker_service/mod.rs:799-811, slower on tiny-cardinality slots. */
 int pb_ctx_set_strict_reduce(pb_ctx* c, int on);
 
+/* Where the gradient-independent half of the backward pass (leader election, radix grouping, piece heads) runs.
+ * 0 (default): inside pb_backward, on the caller's stream.  1: pb_forward(training) forks it onto the context's
+ * own stream right after the index probe, so it overlaps the row gather and everything the caller enqueues
+ * between forward and backward (the dense tower); pb_backward joins it.  When capturing into a CUDA graph the
+ * forward and the backward of a batch must then be part of the same capture. */
+int pb_ctx_set_async_grouping(pb_ctx* c, int on);
+
 /* A context in owner mode serves the already-sharded requests of the multi-GPU exchange (the PS side of
  * lookup_mixed / update_gradient_mixed): `batch` is then just the number of signs received and the u16
  * sample-index limit of a PersiaBatch does not apply. */

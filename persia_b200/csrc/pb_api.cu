@@ -105,6 +105,11 @@ struct pb_ctx {
   size_t partials_floats = 0;
   bool strict_reduce = false;
   bool owner_mode = false;  // serves already-sharded requests: no u16 sample-index limit
+  bool async_grouping = false;  // group occurrences on the side stream during the forward call
+  bool grouped = false;         // the pending batch's grouping has been enqueued
+  int sorted_in = 0;            // buffer pair holding the sorted list (0 = a, 1 = b)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool shared_groups = false;  // two slots carry the same non-zero prefix (one feature group)
 };
 
@@ -187,6 +192,36 @@ int make_slots(const pb_slots_cfg& cfg, const uint32_t* h_occ_off, SlotsDev& s) 
   for (uint32_t i = 0; i <= cfg.n_slots && s.uniform; ++i)
     if (h_occ_off[i] != i * s.uniform) s.uniform = 0;
   return PB_OK;
+}
+
+// SegArgs of the pending batch (sorted list in the pair `sorted_in`)
+SegArgs seg_args(pb_table* t, pb_ctx* c, float* vw) {
+  SegArgs a;
+  a.skey = c->sorted_in == 0 ? c->keys_a : c->keys_b;
+  a.sval = c->sorted_in == 0 ? c->vals_a : c->vals_b;
+  a.occ_row = c->occ_row;
+  a.occ_outrow = c->multi_id ? c->occ_outrow : nullptr;
+  a.row_off = c->multi_id ? c->row_off : nullptr;
+  a.tick_ptr = c->dev_tick;
+  a.nan_tick = c->nan_tick;
+  a.vw_stage = vw;
+  a.n = c->n_occ;
+  a.batch = c->batch;
+  a.piece = c->strict_reduce ? 0 : PB_PIECE;
+  a.shared_groups = c->shared_groups ? 1 : 0;
+  a.partials = c->partials;
+  return a;
+}
+
+// The gradient-independent half of the backward pass: elect per-sign leaders, sort the occurrences by
+// leader, mark piece heads.  Runs on `st` (the caller's stream, or the context's side stream).
+void group_occurrences(pb_table* t, pb_ctx* c, const SlotsDev& sl, cudaStream_t st) {
+  launch_elect(t->d, c->occ_cell, c->n_occ, c->occ_row, c->hist, radix_hist_zero_words(c->n_occ), st);
+  c->sorted_in = launch_radix_sort_leader(t->d, c->occ_row, c->n_occ, sl, c->keys_a, c->vals_a, c->keys_b, c->vals_b,
+                                          c->hist, c->seg_counts, st);
+  SegArgs a = seg_args(t, c, nullptr);
+  launch_find_heads(a, c->heads, c->owners, c->seg_counts, st);
+  c->grouped = true;
 }
 
 }  // namespace
@@ -342,7 +377,7 @@ int pb_lookup(pb_table* t, const uint64_t* d_signs, uint32_t n, int training, fl
   } else {
     launch_probe(MODE_FIND, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   }
-  launch_gather(t->d, sl, t->scratch, nullptr, n, 0, d_out, true, nullptr, st);
+  launch_gather(t->d, sl, t->scratch, nullptr, n, 0, d_out, true, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
 }
@@ -475,6 +510,9 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   A((void**)&c->dev_tick, 4);
   if (e == cudaSuccess) e = cudaMemset(c->nan_tick, 0, 4 * PB_MAX_SLOTS);
   if (e == cudaSuccess) e = cudaMemset(c->dev_tick, 0, 4);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     pb_ctx_destroy(c);
     return fail(PB_ERR_CUDA, std::string("pb_ctx_create: ") + cudaGetErrorString(e));
@@ -492,6 +530,9 @@ int pb_ctx_destroy(pb_ctx* c) {
                   c->heads,    c->owners,   c->seg_counts};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
   return PB_OK;
 }
@@ -513,6 +554,13 @@ int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg) {
 int pb_ctx_set_strict_reduce(pb_ctx* c, int on) {
   if (!c) return fail(PB_ERR_INVALID, "null argument");
   c->strict_reduce = on != 0;
+  return PB_OK;
+}
+
+int pb_ctx_set_async_grouping(pb_ctx* c, int on) {
+  if (!c) return fail(PB_ERR_INVALID, "null argument");
+  if (c->pending) return fail(PB_ERR_STATE, "a batch is pending in this context");
+  c->async_grouping = on != 0;
   return PB_OK;
 }
 
@@ -570,8 +618,19 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   } else {
     launch_probe(MODE_FIND, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
   }
-  launch_gather(t->d, sl, c->occ_cell, d_row_off, (uint32_t)n_out, batch, d_out_f16, false,
-                training ? c->occ_row : nullptr, st);
+  if (training) {
+    c->n_occ = n_occ;
+    c->batch = batch;
+    c->multi_id = d_row_off != nullptr;
+    c->grouped = false;
+    if (c->async_grouping && !d_row_off) {  // fork: the grouping overlaps the gather and whatever follows
+      PB_CUDA(cudaEventRecord(c->ev_fork, st));
+      PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+      group_occurrences(t, c, sl, c->side);
+      PB_CUDA(cudaEventRecord(c->ev_join, c->side));
+    }
+  }
+  launch_gather(t->d, sl, c->occ_cell, d_row_off, (uint32_t)n_out, batch, d_out_f16, false, st);
   if (training) {
     c->n_occ = n_occ;
     c->batch = batch;
@@ -615,11 +674,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     gr.b2p[s] = t->b2p[s];
   }
   uint32_t elems = c->batch * t->d.dim;
-  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, c->hist, radix_hist_zero_words(c->n_occ), st);
-  int which = launch_radix_sort_leader(t->d, c->occ_row, c->n_occ, sl, c->keys_a, c->vals_a, c->keys_b, c->vals_b, c->hist,
-                                     c->seg_counts, st);
-  const uint32_t* skey = which == 0 ? c->keys_a : c->keys_b;
-  const uint32_t* socc = which == 0 ? c->vals_a : c->vals_b;
+  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
   float* vw = nullptr;
   if (t->op.kind == PB_OPT_ADAGRAD_VW) {
     size_t need = (size_t)c->n_occ * t->d.dim;
@@ -633,34 +688,25 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     }
     vw = c->vw_stage;
   }
-  SegArgs a;
-  a.skey = skey;
-  a.sval = socc;
-  a.occ_row = c->occ_row;
-  a.occ_outrow = c->multi_id ? c->occ_outrow : nullptr;
-  a.row_off = c->multi_id ? c->row_off : nullptr;
-  a.tick_ptr = c->dev_tick;
-  a.nan_tick = c->nan_tick;
-  a.vw_stage = vw;
-  a.n = c->n_occ;
-  a.batch = c->batch;
-  a.piece = c->strict_reduce ? 0 : PB_PIECE;
-  a.shared_groups = c->shared_groups ? 1 : 0;
-  a.partials = nullptr;
-  if (a.piece) {
-    size_t need = 2 * (((size_t)c->n_occ + a.piece - 1) / a.piece) * t->d.dim;
+  if (!c->strict_reduce) {
+    size_t need = 2 * (((size_t)c->n_occ + PB_PIECE - 1) / PB_PIECE) * t->d.dim;
     if (need > c->partials_floats) {
       PB_CUDA(cudaStreamSynchronize(st));
       if (c->partials) cudaFree(c->partials);
       c->partials = nullptr;
       c->partials_floats = 0;
-      size_t cap = 2 * (((size_t)c->max_occ + a.piece - 1) / a.piece) * t->d.dim;
+      size_t cap = 2 * (((size_t)c->max_occ + PB_PIECE - 1) / PB_PIECE) * t->d.dim;
       if (cap < need) cap = need;
       PB_CUDA(cudaMalloc(&c->partials, sizeof(float) * cap));
       c->partials_floats = cap;
     }
-    a.partials = c->partials;
   }
+  if (c->grouped) {
+    PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));  // join the side stream's grouping
+  } else {
+    group_occurrences(t, c, sl, st);
+  }
+  SegArgs a = seg_args(t, c, vw);
   launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, c->heads, c->owners, c->seg_counts, st);
   c->pending = false;
   PB_CUDA(cudaGetLastError());

@@ -177,80 +177,23 @@ __device__ __forceinline__ void store_out(void* out, size_t o, const float (&acc
 }
 
 constexpr int GATHER_ROWS = 4;  // output rows per group in the one-id-per-sample layout (independent loads in flight)
-constexpr int ELECT_SLOTS = 512;  // per-block table for the leader election (>= 2 x rows a block can touch at once)
-
-// Leader election (training): the backward pass groups the occurrences of a batch by the position of the
-// first occurrence of their sign.  Every row keeps (batch number << 32 | ~position) in TableDev::row_lead and
-// occurrences race with atomicMax — but a hot sign (tiny-cardinality slots repeat an id thousands of times)
-// would serialise thousands of atomics on one address, so a block first reduces its own occurrences in
-// shared memory and only distinct rows go to global memory.  The high half doubles as the row's recency
-// (get_refresh, eviction_map.rs:48-60).
-struct Elector {
-  uint32_t* keys;  // row or 0xFFFFFFFF
-  uint32_t* best;  // min position
-  __device__ __forceinline__ void clear() {
-    for (uint32_t i = threadIdx.x; i < ELECT_SLOTS; i += blockDim.x) {
-      keys[i] = 0xFFFFFFFFu;
-      best[i] = 0xFFFFFFFFu;
-    }
-  }
-  __device__ __forceinline__ void offer(uint32_t row, uint32_t pos) {
-    uint32_t h = (row * 2654435761u) >> 23;  // 9 bits
-    for (;;) {
-      uint32_t k = atomicCAS(&keys[h], 0xFFFFFFFFu, row);
-      if (k == 0xFFFFFFFFu || k == row) {
-        atomicMin(&best[h], pos);
-        return;
-      }
-      h = (h + 1) & (ELECT_SLOTS - 1);
-    }
-  }
-  __device__ __forceinline__ void publish(unsigned long long* row_lead, unsigned long long lead_hi) {
-    for (uint32_t i = threadIdx.x; i < ELECT_SLOTS; i += blockDim.x) {
-      uint32_t row = keys[i];
-      if (row != 0xFFFFFFFFu) {
-        const unsigned long long mine = lead_hi | (uint32_t)~best[i];
-        if (__ldcg(&row_lead[row]) < mine) atomicMax(&row_lead[row], mine);
-      }
-    }
-  }
-};
 
 template <int VEC, int G, bool OUT_F32>
 __global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, const uint32_t* __restrict__ occ_cell,
                                                      const uint32_t* __restrict__ row_off, uint32_t n_out,
-                                                     uint32_t batch, void* __restrict__ out,
-                                                     uint32_t* __restrict__ occ_row) {
-  __shared__ uint32_t el_keys[ELECT_SLOTS], el_best[ELECT_SLOTS];
-  Elector el{el_keys, el_best};
-  const bool elect = occ_row != nullptr;  // training forward
-  const unsigned long long lead_hi = elect ? ((unsigned long long)t.counters[CTR_TICK] << 32) : 0ULL;
+                                                     uint32_t batch, void* __restrict__ out) {
   const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const uint32_t lane = threadIdx.x % G;
   const uint32_t nvec = t.dim / VEC;
-  if (elect) {
-    el.clear();
-    __syncthreads();
-  }
   if (!row_off) {
     // one occurrence per output row: GATHER_ROWS rows per group, every stage issued for all rows before use
     const uint32_t r0 = group * GATHER_ROWS;
+    if (r0 >= n_out) return;
     uint32_t cell[GATHER_ROWS], row[GATHER_ROWS];
 #pragma unroll
     for (int k = 0; k < GATHER_ROWS; ++k) cell[k] = (r0 + k < n_out) ? occ_cell[r0 + k] : 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < GATHER_ROWS; ++k) row[k] = (cell[k] <= t.n_cells) ? t.cells[cell[k]].row : ROW_NONE;
-    if (elect && lane == 0) {
-#pragma unroll
-      for (int k = 0; k < GATHER_ROWS; ++k)
-        if (r0 + k < n_out) {
-          occ_row[r0 + k] = row[k] < t.capacity ? row[k] : ROW_NONE;
-          if (row[k] < t.capacity) {
-            if ((256 / G) * GATHER_ROWS > ELECT_SLOTS / 2) atomicMax(&t.row_lead[row[k]], lead_hi | (uint32_t)~(r0 + k));
-            else el.offer(row[k], r0 + k);
-          }
-        }
-    }
     for (uint32_t c = lane; c < nvec; c += G) {
       float v[GATHER_ROWS][VEC];
 #pragma unroll
@@ -271,42 +214,79 @@ __global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, co
           store_out<VEC, OUT_F32>(out, (size_t)(r0 + k) * t.dim + c * VEC, v[k], 1.0f);  // 1/sqrt(max(1,1)) = 1
         }
     }
-  } else if (group < n_out) {
-    const uint32_t gid = group;
-    const uint32_t beg = row_off[gid], end = row_off[gid + 1];
-    float scale = 1.0f;
-    if (!OUT_F32 && batch && sl.sqrt_scaling[gid / batch]) {
-      uint32_t cnt = end - beg;
-      scale = __fdiv_rn(1.0f, __fsqrt_rn((float)(cnt > 1 ? cnt : 1)));
+    return;
+  }
+  const uint32_t gid = group;
+  if (gid >= n_out) return;
+  const uint32_t beg = row_off[gid], end = row_off[gid + 1];
+  float scale = 1.0f;
+  if (!OUT_F32 && batch && sl.sqrt_scaling[gid / batch]) {
+    uint32_t cnt = end - beg;
+    scale = __fdiv_rn(1.0f, __fsqrt_rn((float)(cnt > 1 ? cnt : 1)));
+  }
+  for (uint32_t c = lane; c < nvec; c += G) {
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.0f;
+    for (uint32_t j = beg; j < end; ++j) {
+      uint32_t h = occ_cell[j];
+      uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+      if (row >= t.capacity) continue;
+      float v[VEC];
+      load_vec<VEC>(t.rows + (size_t)row * t.stride + c * VEC, v);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], v[k]);
     }
-    // a sample may hold more ids than the election table can absorb at once: spill straight to global
-    const bool direct = (end - beg) * (256 / G) > ELECT_SLOTS / 2;
-    for (uint32_t c = lane; c < nvec; c += G) {
-      float acc[VEC];
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = 0.0f;
-      for (uint32_t j = beg; j < end; ++j) {
-        uint32_t h = occ_cell[j];
-        uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
-        if (elect && c == 0) {  // lane 0, first chunk: once per occurrence
-          occ_row[j] = row < t.capacity ? row : ROW_NONE;
-          if (row < t.capacity) {
-            if (direct) atomicMax(&t.row_lead[row], lead_hi | (uint32_t)~j);
-            else el.offer(row, j);
-          }
+    store_out<VEC, OUT_F32>(out, (size_t)gid * t.dim + c * VEC, acc, scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Leader election (training).  The backward pass groups the occurrences of a batch by the position of the
+// first occurrence of their sign — a key that does not depend on thread timing.  Every row keeps
+// (batch number << 32 | ~position) in TableDev::row_lead and occurrences race with atomicMax; a hot sign
+// (tiny-cardinality slots repeat an id thousands of times) would serialise thousands of atomics on one
+// address, so a block first reduces its 256 occurrences in shared memory and only distinct rows go to
+// global memory.  The high half doubles as the row's recency (get_refresh, eviction_map.rs:48-60).
+// Also records the row of every occurrence and clears the first radix histogram (side job).
+// ------------------------------------------------------------------------------------------------
+constexpr int ELECT_SLOTS = 512;
+__global__ void __launch_bounds__(256) k_elect_leaders(TableDev t, const uint32_t* __restrict__ occ_cell, uint32_t n,
+                                                       uint32_t* __restrict__ occ_row, uint32_t* __restrict__ zero,
+                                                       uint32_t zero_words) {
+  __shared__ uint32_t keys[ELECT_SLOTS], best[ELECT_SLOTS];
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < zero_words; w += gridDim.x * blockDim.x) zero[w] = 0;
+  for (uint32_t i = threadIdx.x; i < ELECT_SLOTS; i += blockDim.x) {
+    keys[i] = 0xFFFFFFFFu;
+    best[i] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  const unsigned long long lead_hi = (unsigned long long)t.counters[CTR_TICK] << 32;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t h = occ_cell[i];
+    uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+    if (row >= t.capacity) row = ROW_NONE;
+    occ_row[i] = row;
+    if (row != ROW_NONE) {
+      uint32_t s = (row * 2654435761u) >> 23;  // 9 bits
+      for (;;) {
+        uint32_t k = atomicCAS(&keys[s], 0xFFFFFFFFu, row);
+        if (k == 0xFFFFFFFFu || k == row) {
+          atomicMin(&best[s], i);
+          break;
         }
-        if (row >= t.capacity) continue;
-        float v[VEC];
-        load_vec<VEC>(t.rows + (size_t)row * t.stride + c * VEC, v);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], v[k]);
+        s = (s + 1) & (ELECT_SLOTS - 1);
       }
-      store_out<VEC, OUT_F32>(out, (size_t)gid * t.dim + c * VEC, acc, scale);
     }
   }
-  if (elect) {
-    __syncthreads();
-    el.publish(t.row_lead, lead_hi);
+  __syncthreads();
+  for (uint32_t s = threadIdx.x; s < ELECT_SLOTS; s += blockDim.x) {
+    uint32_t row = keys[s];
+    if (row != 0xFFFFFFFFu) {
+      const unsigned long long mine = lead_hi | (uint32_t)~best[s];
+      if (__ldcg(&t.row_lead[row]) < mine) atomicMax(&t.row_lead[row], mine);
+    }
   }
 }
 
@@ -422,13 +402,12 @@ void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, 
 
 template <int VEC, bool F32>
 static void gather_dispatch(int G, const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell,
-                            const uint32_t* row_off, uint32_t n_out, uint32_t batch, void* out, uint32_t* occ_row,
-                            cudaStream_t st) {
+                            const uint32_t* row_off, uint32_t n_out, uint32_t batch, void* out, cudaStream_t st) {
   uint32_t grid;
 #define PB_G(GG)                                                                                              \
   case GG:                                                                                                    \
     grid = cdiv((uint64_t)(row_off ? n_out : cdiv(n_out, GATHER_ROWS)) * GG, 256);                            \
-    PB_LAUNCH_F(FAM_GATHER, (k_gather_pool<VEC, GG, F32>), grid, 256, 0, st, t, sl, occ_cell, row_off, n_out, batch, out, occ_row);  \
+    PB_LAUNCH_F(FAM_GATHER, (k_gather_pool<VEC, GG, F32>), grid, 256, 0, st, t, sl, occ_cell, row_off, n_out, batch, out);  \
     break;
   switch (G) {
     PB_G(1) PB_G(2) PB_G(4) PB_G(8) PB_G(16) PB_G(32)
@@ -437,17 +416,22 @@ static void gather_dispatch(int G, const TableDev& t, const SlotsDev& sl, const 
 }
 
 void launch_gather(const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell, const uint32_t* row_off,
-                   uint32_t n_out, uint32_t batch, void* out, bool out_f32, uint32_t* occ_row, cudaStream_t st) {
+                   uint32_t n_out, uint32_t batch, void* out, bool out_f32, cudaStream_t st) {
   if (!n_out) return;
   int vec, G;
   vec_group(t.dim, vec, G);
   if (vec == 4) {
-    if (out_f32) gather_dispatch<4, true>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
-    else gather_dispatch<4, false>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
+    if (out_f32) gather_dispatch<4, true>(G, t, sl, occ_cell, row_off, n_out, batch, out, st);
+    else gather_dispatch<4, false>(G, t, sl, occ_cell, row_off, n_out, batch, out, st);
   } else {
-    if (out_f32) gather_dispatch<1, true>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
-    else gather_dispatch<1, false>(G, t, sl, occ_cell, row_off, n_out, batch, out, occ_row, st);
+    if (out_f32) gather_dispatch<1, true>(G, t, sl, occ_cell, row_off, n_out, batch, out, st);
+    else gather_dispatch<1, false>(G, t, sl, occ_cell, row_off, n_out, batch, out, st);
   }
+}
+
+void launch_elect(const TableDev& t, const uint32_t* occ_cell, uint32_t n, uint32_t* occ_row, uint32_t* zero,
+                  uint32_t zero_words, cudaStream_t st) {
+  if (n) PB_LAUNCH_F(FAM_SORT, k_elect_leaders, cdiv(n, 256), 256, 0, st, t, occ_cell, n, occ_row, zero, zero_words);
 }
 
 void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell, uint32_t n, float* entries,

@@ -138,12 +138,7 @@ __device__ float vw_dot(const float* g, uint32_t n) {
 template <bool F16>
 __global__ void __launch_bounds__(256) k_nan_scan(GradsDev gr, uint32_t elems_per_slot,
                                                   const uint32_t* __restrict__ tick_ptr,
-                                                  uint32_t* __restrict__ nan_tick, uint32_t* __restrict__ zero,
-                                                  uint32_t zero_words) {
-  // side job: clear the first radix pass's histogram rows (the kernels that follow accumulate into them)
-  for (uint32_t w = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; w < zero_words;
-       w += gridDim.x * gridDim.y * blockDim.x)
-    zero[w] = 0;
+                                                  uint32_t* __restrict__ nan_tick) {
   uint32_t s = blockIdx.y;
   const void* base = gr.ptr[s];
   if (!base) return;
@@ -634,13 +629,13 @@ __global__ void __launch_bounds__(256) k_update_direct(TableDev t, OptimDev op, 
 // launchers (host)
 // ------------------------------------------------------------------------------------------------
 void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,
-                     uint32_t* nan_tick, int32_t* status, uint32_t* zero, uint32_t zero_words, cudaStream_t st) {
+                     uint32_t* nan_tick, int32_t* status, cudaStream_t st) {
   uint32_t per = f16 ? elems_per_slot / 8 : elems_per_slot;
   uint32_t gx = cdiv(per ? per : 1, 256 * 4);
   if (gx > 148 * 4) gx = 148 * 4;
   dim3 grid(gx, n_slots);
-  if (f16) PB_LAUNCH_F(FAM_NAN, k_nan_scan<true>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick, zero, zero_words);
-  else PB_LAUNCH_F(FAM_NAN, k_nan_scan<false>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick, zero, zero_words);
+  if (f16) PB_LAUNCH_F(FAM_NAN, k_nan_scan<true>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick);
+  else PB_LAUNCH_F(FAM_NAN, k_nan_scan<false>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick);
   if (status) PB_LAUNCH(k_slot_status, 1, PB_MAX_SLOTS, 0, st, gr, n_slots, tick, nan_tick, status);
 }
 
@@ -672,7 +667,6 @@ void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev&
                           const GradsDev& gr, bool f16, const SegArgs& a, uint2* heads, uint2* owners,
                           uint32_t* counts, cudaStream_t st) {
   if (!a.n) return;
-  PB_LAUNCH_F(FAM_UPDATE, k_find_heads, cdiv((uint64_t)cdiv(a.n, 32) * 32, 256), 256, 0, st, a, heads, owners, counts);
   int vec, G;
   vec_group(t.dim, vec, G);
   if (vec == 4) {
@@ -682,6 +676,10 @@ void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev&
     if (f16) reduce_dispatch<1, true>(G, t, op, hy, sl, gr, a, heads, owners, counts, st);
     else reduce_dispatch<1, false>(G, t, op, hy, sl, gr, a, heads, owners, counts, st);
   }
+}
+
+void launch_find_heads(const SegArgs& a, uint2* heads, uint2* owners, uint32_t* counts, cudaStream_t st) {
+  if (a.n) PB_LAUNCH_F(FAM_SORT, k_find_heads, cdiv((uint64_t)cdiv(a.n, 32) * 32, 256), 256, 0, st, a, heads, owners, counts);
 }
 
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,

@@ -69,6 +69,7 @@ SYMBOLS = {
     "pb_ctx_set_slots": (_i32, [_vp, C.POINTER(SlotsCfg)]),
     "pb_ctx_set_strict_reduce": (_i32, [_vp, _i32]),
     "pb_ctx_set_owner_mode": (_i32, [_vp, _i32]),
+    "pb_ctx_set_async_grouping": (_i32, [_vp, _i32]),
     "pb_permute_u64": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "pb_permute_rows": (_i32, [_vp, _vp, _u32, _u32, _i32, _vp, _vp]),
     "pb_forward": (_i32, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp]),

@@ -136,6 +136,10 @@ class BatchContext:
         """Sequential (reference-order) gradient reduction for any multiplicity; see persia_b200.h."""
         N.check(self.lib.pb_ctx_set_strict_reduce(self.h, int(on)))
 
+    def set_async_grouping(self, on=True):
+        """Overlap the backward's grouping with the forward's gather / the dense tower; see persia_b200.h."""
+        N.check(self.lib.pb_ctx_set_async_grouping(self.h, int(on)))
+
     def set_owner_mode(self, on=True):
         """Serve already-sharded requests (no u16 sample-index limit); see persia_b200.h."""
         N.check(self.lib.pb_ctx_set_owner_mode(self.h, int(on)))

@@ -449,3 +449,50 @@ def test_piecewise_reduce_default_mode(torch_cuda, pb, oracle, dim, kind):
             assert a.tobytes() == b.tobytes()  # deterministic
     finally:
         oracle.set_rsqrt_exact(False)
+
+
+def test_async_grouping_same_result(torch_cuda, pb, oracle):
+    """pb_ctx_set_async_grouping: the grouping forked onto the context's stream in pb_forward gives bit-identical
+    rows (eager launches and a captured CUDA graph replayed several times)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(31)
+    S, B, dim, card = 6, 1024, 64, [3, 17, 900, 50000, 50000, 11]
+    s, ctx, w, pf = _pair(pb, oracle, S, dim, oracle.SGD, cap=1 << 17, optim_kw=dict(lr=0.05, wd=0.001))
+    ctx.set_async_grouping(True)
+    touched = _train_steps(torch, s, ctx, w, rng, S, B, dim, card, steps=4)
+    for t in touched:
+        _entries_equal(torch, s, w, t[:2000])
+    # the same step captured once and replayed: inputs are refreshed in place between replays
+    ids_np, _, slot_off = make_batch(rng, S, B, card)
+    ids_dev = to_dev_ids(ids_np, DEV)
+    g_dev = torch.zeros((S, B, dim), dtype=torch.float16, device=DEV)
+    out = torch.empty((S, B, dim), dtype=torch.float16, device=DEV)
+    grads = [g_dev[i] for i in range(S)]
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx.forward(s, ids_dev, slot_off, B, training=True, out=out)  # warm-up (allocations happen here)
+        ctx.backward(s, grads)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            ctx.forward(s, ids_dev, slot_off, B, training=True, out=out)
+            ctx.backward(s, grads)
+    # bring the oracle to the same state: one step with zero gradients happened above (plus the capture's none)
+    _, octx = w.forward(ids_np, full_row_off(S, B), B, training=True)
+    w.backward(octx, [np.zeros((B, dim), np.float16)] * S)
+    seen = [set() for _ in range(S)]
+    for it in range(3):
+        ids_np, _, _ = make_batch(rng, S, B, card)
+        g = (rng.standard_normal((S, B, dim)) * 1e-2).astype(np.float16)
+        ids_dev.copy_(to_dev_ids(ids_np, DEV))
+        g_dev.copy_(torch.from_numpy(g).to(DEV))
+        graph.replay()
+        torch.cuda.synchronize()
+        want, octx = w.forward(ids_np, full_row_off(S, B), B, training=True)
+        got = out.cpu().numpy()
+        for i in range(S):
+            np.testing.assert_array_equal(got[i].view(np.uint16), want[i].view(np.uint16))
+            seen[i].update(w.ctx_signs(octx, i).tolist())
+        w.backward(octx, [g[i] for i in range(S)])
+    for t in seen:
+        _entries_equal(torch, s, w, np.array(sorted(t), np.uint64)[:2000])
