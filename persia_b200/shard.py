@@ -179,6 +179,12 @@ class BatchContext:
         N.check(self.lib.pb_backward(shard.h, self.h, ptrs, int(bool(is_f16)), sc, _ptr(status), _stream(self.device)))
         return status
 
+    def backward_ptrs(self, shard, ptrs, is_f16, scales=None):
+        """GradientBatch form (persia-core/src/backward.rs:86-105): raw device pointers, None = skipped slot."""
+        arr = (C.c_void_p * self.n_slots)(*[(int(p) if p else None) for p in ptrs])
+        sc = (C.c_float * self.n_slots)(*[float(x) for x in scales]) if scales is not None else None
+        N.check(self.lib.pb_backward(shard.h, self.h, arr, int(bool(is_f16)), sc, None, _stream(self.device)))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.pb_ctx_destroy(self.h)

@@ -150,3 +150,12 @@ def test_init_row_properties(oracle):
     assert not np.array_equal(a, c)
     assert np.all(a >= -0.01) and np.all(a < 0.01)
     np.testing.assert_array_equal(a[:16], oracle.init_row(12345, 16, -0.01, 0.01))  # sequential prefix
+
+
+def test_farmhash_full_width_fixture(oracle):
+    import json
+    import os
+
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "farmhash64_kat.json")))
+    for k, v in fx["hash64"].items():
+        assert int(oracle.farmhash64(np.array([int(k)], np.uint64))[0]) == int(v, 16)
