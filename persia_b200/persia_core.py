@@ -316,6 +316,43 @@ class _Pending:
         self.parts = []
 
 
+def farmhash64_np(x):
+    """farmhash 1.1.5 hash64 of the 8 LE bytes of each u64 (FarmHash HashLen0to16, 8..16 branch), vectorised."""
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    k2 = np.uint64(0x9AE16A3B2F90404F)
+    mul = k2 + np.uint64(16)
+
+    def rotr(v, s):
+        return (v >> np.uint64(s)) | (v << np.uint64(64 - s))
+
+    with np.errstate(over="ignore"):
+        a = x + k2
+        c = rotr(x, 37) * mul + a
+        d = (rotr(a, 25) + x) * mul
+        h = (c ^ d) * mul
+        h ^= h >> np.uint64(47)
+        g = (d ^ h) * mul
+        g ^= g >> np.uint64(47)
+        return g * mul
+
+
+def _hashstack(feature, slot):
+    """indices_to_hashstack_indices (embedding_worker_service/mod.rs:347-400) as an id expansion: every id becomes
+    `rounds` keys, key_r = farmhash64^(r+1)(id) % embedding_size + r * embedding_size; sample_num_signs grows by the
+    same factor, which is what the sqrt scaling then counts."""
+    R, size = slot.hash_stack_rounds, np.uint64(slot.hash_stack_embedding_size)
+    rows = [np.array([v], np.uint64) for v in feature] if isinstance(feature, np.ndarray) else list(feature)
+    out = []
+    for ids in rows:
+        h = np.ascontiguousarray(ids, dtype=np.uint64)
+        keys = np.empty((h.size, R), np.uint64)
+        for r in range(R):
+            h = farmhash64_np(h)
+            keys[:, r] = h % size + np.uint64(r) * size
+        out.append(keys.reshape(-1))
+    return out
+
+
 def _flatten(feats, batch):
     """[(name, lil | single ids)] of one dim group -> flat ids, CSR offsets (None when one id per sample), slot offsets."""
     single = all(isinstance(x, np.ndarray) and x.ndim == 1 and x.dtype == np.uint64 for _, x in feats)
@@ -362,6 +399,7 @@ def _forward(batch, device_id, training):
             raise RuntimeError(f"slot: {name} not found")  # get_slot_by_feature_name expect()
         if not _S.by_name[name].embedding_summation:
             raise RuntimeError("raw (embedding_summation: false) slots are not built yet (SURVEY.md N3)")
+    feats = [(n, _hashstack(x, _S.by_name[n]) if _S.by_name[n].hash_stack_rounds > 0 else x) for n, x in feats]
     pending = _Pending()
     by_slot = {}
     for dim in sorted({_S.by_name[n].dim for n, _ in feats}):

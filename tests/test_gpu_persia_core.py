@@ -18,16 +18,19 @@ CFG = {
         "item": {"dim": 16, "sqrt_scaling": True},
         "tags": {"dim": 32},
         "shop": {"dim": 16},
+        "hs": {"dim": 16, "hash_stack_config": {"hash_stack_rounds": 2, "embedding_size": 1000}},
     },
 }
-CARD = {"user": 500, "item": 40, "tags": 3000, "shop": 7}
+CARD = {"user": 500, "item": 40, "tags": 3000, "shop": 7, "hs": 100000}
+KEYS = dict(CARD, hs=2000)  # resident key space per slot (hash stack: rounds x embedding_size)
 
 
 def _batch(pc, rng, B):
     lil = {"user": rng.integers(0, CARD["user"], size=B, dtype=np.uint64),
            "item": [rng.integers(0, CARD["item"], size=rng.integers(0, 5), dtype=np.uint64) for _ in range(B)],
            "tags": [rng.integers(0, CARD["tags"], size=rng.integers(1, 4), dtype=np.uint64) for _ in range(B)],
-           "shop": rng.integers(0, CARD["shop"], size=B, dtype=np.uint64)}
+           "shop": rng.integers(0, CARD["shop"], size=B, dtype=np.uint64),
+           "hs": rng.integers(0, CARD["hs"], size=B, dtype=np.uint64)}
     b = pc.data.PersiaBatch()
     for name, v in lil.items():
         if isinstance(v, np.ndarray):
@@ -47,7 +50,8 @@ def _oracle_worker(oracle, pc):
     ws = {}
     for dim in sorted({s.dim for s in slots}):
         part = [s for s in slots if s.dim == dim]
-        w = oracle.Worker([oracle.SlotCfg(dim, sqrt_scaling=s.sqrt_scaling, prefix=s.index_prefix) for s in part], n_ps=1)
+        w = oracle.Worker([oracle.SlotCfg(dim, sqrt_scaling=s.sqrt_scaling, prefix=s.index_prefix,
+                                          hs_rounds=s.hash_stack_rounds, hs_size=s.hash_stack_embedding_size) for s in part], n_ps=1)
         w.configure(-0.01, 0.01, 1.0, True, 10.0)
         w.set_optimizer(oracle.Optim(oracle.SGD, lr=0.05, wd=0.0))
         ws[dim] = (w, [s.name for s in part])
@@ -119,7 +123,7 @@ def test_surface_forward_backward_matches_oracle(oracle):
                 for n, wv in zip(names, want):
                     got = torch_embs[n].detach().cpu().numpy()
                     assert np.abs(got.astype(np.float32) - wv.astype(np.float32)).max() <= 2e-5  # <= 1 f16 ulp at |x|<=0.04
-                    if isinstance(lil[n], np.ndarray):
+                    if isinstance(lil[n], np.ndarray) and n != "hs":
                         np.testing.assert_array_equal(got.view(np.uint16), wv.view(np.uint16))
             # a loss and its gradients, then the GradientBatch protocol
             scale = 128.0
@@ -148,7 +152,7 @@ def test_surface_forward_backward_matches_oracle(oracle):
             sh = _S.groups[dim]["shard"]
             for n in names:
                 pf = _S.by_name[n].index_prefix
-                signs = oracle.add_prefix(np.arange(CARD[n], dtype=np.uint64), 8, pf)
+                signs = oracle.add_prefix(np.arange(KEYS[n], dtype=np.uint64), 8, pf)
                 ent, found = sh.get_entries(to_dev_ids(signs, "cuda:0"))
                 ent, found = ent.cpu().numpy(), found.cpu().numpy()
                 for k, s in enumerate(signs):

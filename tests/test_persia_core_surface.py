@@ -115,3 +115,16 @@ def test_reference_python_package_runs_on_the_surface(pc, monkeypatch):
     SGD(0.1).optimizer_base, Adagrad(0.1).optimizer_base, Adam(1e-3).optimizer_base  # noqa: B018
     cfg = EmbeddingConfig()
     assert cfg.weight_bound == 10 and cfg.admit_probability == 1.0
+
+
+def test_farmhash_numpy_matches_golden(pc):
+    import json
+
+    from persia_b200.persia_core import SlotConfig, _hashstack, farmhash64_np
+
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "farmhash64_kat.json")))
+    ids = np.array([int(k) for k in fx["hash64"]], np.uint64)
+    np.testing.assert_array_equal(farmhash64_np(ids), np.array([int(v, 16) for v in fx["hash64"].values()], np.uint64))
+    slot = SlotConfig("t", 32, hash_stack_rounds=2, hash_stack_embedding_size=10)
+    got = _hashstack(ids, slot)  # the reference's own test vector (mod.rs:1570-1613)
+    assert [g.tolist() for g in got] == [list(v) for v in fx["hashstack_rounds2_size10"].values()]
