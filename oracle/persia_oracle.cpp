@@ -488,6 +488,10 @@ struct ParamServer {
   int faithful_miss = 1;  // see update(): the reference does not advance the gradient cursor on a miss
   std::atomic<uint64_t> index_miss{0}, grad_miss{0};
   uint64_t admit_rng = 0x9E3779B97F4A7C15ULL;  // reference: unseeded thread_rng (unpinned); only used when admit_p < 1
+  // Adam: accumulated beta powers per feature group (optim.rs:99-131); key = sign & prefix mask
+  uint32_t prefix_bit = 8;
+  std::vector<std::pair<uint64_t, std::pair<float, float>>> accum_betas;
+  std::mutex adam_lock;
 
   ParamServer(size_t capacity, size_t n_internal) {
     if (n_internal == 0) n_internal = 1;
@@ -572,7 +576,38 @@ struct ParamServer {
     const float* cur = grads;
     const float* end = grads + n_grad_floats;
     uint64_t miss = 0;
-    // Adam batch-level state (optim.rs:155-197) is not restated: per-feature-group beta powers — N3.
+    // Adam batch-level state (optim.rs:155-197): the first sign of every feature group seen in this request
+    // advances that group's accumulated (beta1^t, beta2^t); every sign of the group then uses the advanced pair.
+    std::vector<float> b1p(n, 0.0f), b2p(n, 0.0f);
+    if (optim.kind == 3) {
+      std::lock_guard<std::mutex> g(adam_lock);
+      const uint64_t mask = ~((1ULL << (64 - prefix_bit)) - 1ULL);
+      std::vector<std::pair<uint64_t, std::pair<float, float>>> stepped;
+      for (size_t i = 0; i < n; ++i) {
+        uint64_t m = signs[i] & mask;
+        bool done = false;
+        for (auto& st : stepped)
+          if (st.first == m) {
+            b1p[i] = st.second.first;
+            b2p[i] = st.second.second;
+            done = true;
+            break;
+          }
+        if (done) continue;
+        std::pair<float, float>* acc = nullptr;
+        for (auto& a : accum_betas)
+          if (a.first == m) acc = &a.second;
+        if (!acc) {  // Adam::new seeds every feature group with (beta1, beta2) (optim.rs:104-131)
+          accum_betas.push_back({m, {optim.b1, optim.b2}});
+          acc = &accum_betas.back().second;
+        }
+        acc->first = acc->first * optim.b1;
+        acc->second = acc->second * optim.b2;
+        b1p[i] = acc->first;
+        b2p[i] = acc->second;
+        stepped.push_back({m, *acc});
+      }
+    }
     for (size_t i = 0; i < n; ++i) {
       uint64_t sign = signs[i];
       size_t si = shard_of(sign);
@@ -581,7 +616,7 @@ struct ParamServer {
       if (e) {
         size_t d = e->dim;
         if (cur + d > end) return -2;  // the reference would panic in split_at
-        optim_update(optim, e->inner.data(), e->inner.size(), cur, d, 0.0f, 0.0f);
+        optim_update(optim, e->inner.data(), e->inner.size(), cur, d, b1p[i], b2p[i]);
         if (hyper.enable_wb) weight_bound(e->inner.data(), d, hyper.wb);
         cur += d;
       } else {
@@ -971,7 +1006,10 @@ void* po_worker_new(uint32_t n_slots, uint32_t n_ps, uint64_t capacity_per_ps, u
   auto* w = new Worker();
   w->slots.resize(n_slots);
   w->prefix_bit = prefix_bit;
-  for (uint32_t r = 0; r < n_ps; ++r) w->ps.emplace_back(new ParamServer(capacity_per_ps, n_internal_shards));
+  for (uint32_t r = 0; r < n_ps; ++r) {
+    w->ps.emplace_back(new ParamServer(capacity_per_ps, n_internal_shards));
+    w->ps.back()->prefix_bit = prefix_bit;
+  }
   return w;
 }
 void po_worker_free(void* w) { delete (Worker*)w; }

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "pb_kernels.cuh"
 
@@ -74,7 +76,8 @@ struct pb_table {
   bool allocated = false;
   uint32_t* scratch = nullptr;  // index cells of a single-request call
   uint32_t scratch_cap = 0;
-  float b1p[PB_MAX_SLOTS], b2p[PB_MAX_SLOTS];  // Adam: accumulated beta powers per slot (optim.rs:155-197)
+  // Adam: accumulated (beta1^t, beta2^t) per feature group, keyed by index prefix (optim.rs:99-131, 155-197)
+  std::vector<std::pair<uint64_t, std::pair<float, float>>> adam_pow;
   float b1p_direct = 1.0f, b2p_direct = 1.0f;
 };
 
@@ -256,7 +259,6 @@ int pb_table_create(int device, const pb_table_cfg* cfg, pb_table** out) {
   pb_table* t = new pb_table();
   t->device = device;
   t->cfg = *cfg;
-  for (int i = 0; i < PB_MAX_SLOTS; ++i) t->b1p[i] = t->b2p[i] = 1.0f;
   *out = t;
   return PB_OK;
 }
@@ -290,10 +292,7 @@ int pb_table_set_optimizer(pb_table* t, const pb_optim_cfg* c) {
   t->op.b1 = c->beta1;
   t->op.b2 = c->beta2;
   if (!t->has_op) {
-    for (int i = 0; i < PB_MAX_SLOTS; ++i) {  // AdamPowerOfBetas starts at (beta1, beta2) (optim.rs:118-124)
-      t->b1p[i] = c->beta1;
-      t->b2p[i] = c->beta2;
-    }
+    t->adam_pow.clear();  // AdamPowerOfBetas starts at (beta1, beta2) for every feature group (optim.rs:118-124)
     t->b1p_direct = c->beta1;
     t->b2p_direct = c->beta2;
   }
@@ -666,12 +665,29 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     float inv = 1.0f / sc;
     if (gr.do_scale[s] && !std::isfinite(inv)) return fail(PB_ERR_INVALID, "scale on gradient must be finite");
     gr.inv_scale[s] = inv;
-    if (t->op.kind == PB_OPT_ADAM && h_grads[s]) {  // one power step per request and feature group
-      t->b1p[s] *= t->op.b1;
-      t->b2p[s] *= t->op.b2;
+  }
+  if (t->op.kind == PB_OPT_ADAM) {  // get_batch_level_state: one power step per request and feature group
+    std::vector<uint64_t> stepped;
+    for (uint32_t s = 0; s < S; ++s) {
+      if (!h_grads[s]) continue;
+      const uint64_t pfx = c->slots.prefix[s];
+      std::pair<float, float>* acc = nullptr;
+      for (auto& a : t->adam_pow)
+        if (a.first == pfx) acc = &a.second;
+      if (!acc) {
+        t->adam_pow.push_back({pfx, {t->op.b1, t->op.b2}});
+        acc = &t->adam_pow.back().second;
+      }
+      bool done = false;
+      for (uint64_t p : stepped) done |= p == pfx;
+      if (!done) {
+        acc->first *= t->op.b1;
+        acc->second *= t->op.b2;
+        stepped.push_back(pfx);
+      }
+      gr.b1p[s] = acc->first;
+      gr.b2p[s] = acc->second;
     }
-    gr.b1p[s] = t->b1p[s];
-    gr.b2p[s] = t->b2p[s];
   }
   uint32_t elems = c->batch * t->d.dim;
   launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);

@@ -496,3 +496,17 @@ def test_async_grouping_same_result(torch_cuda, pb, oracle):
         w.backward(octx, [g[i] for i in range(S)])
     for t in seen:
         _entries_equal(torch, s, w, np.array(sorted(t), np.uint64)[:2000])
+
+
+@pytest.mark.parametrize("dim", [12, 64])
+def test_adam_training_bit_exact(torch_cuda, pb, oracle, dim):
+    """Adam (persia-simd adam_avx2 + the per-feature-group beta powers of optim.rs:155-197), incl. two slots that
+    share one feature group (their power advances once per request)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(dim + 7)
+    S, B, card = 3, 200, [30, 30, 5000]
+    s, ctx, w, _ = _pair(pb, oracle, S, dim, oracle.ADAM, groups=[0, 0, 1],
+                         optim_kw=dict(lr=0.01, b1=0.9, b2=0.999, eps=1e-8))
+    touched = _train_steps(torch, s, ctx, w, rng, S, B, dim, card, steps=5, max_ids=2)
+    for t in touched:
+        _entries_equal(torch, s, w, t)
