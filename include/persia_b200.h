@@ -147,6 +147,16 @@ int pb_permute_u64(const uint64_t* d_src, const uint32_t* d_perm, uint32_t n, ui
 int pb_permute_rows(const void* d_src, const uint32_t* d_perm, uint32_t n, uint32_t row_bytes, int scatter, void* d_out,
                     void* stream);
 
+/* Fixed-capacity framing of the shard exchange (static shapes: no split sizes on the host, CUDA-graph capturable).
+ * Every (source, destination) pair owns `cap` slots: framed[r*cap + k] = signs[perm[off_r + k]] for k < counts[r],
+ * PB_NULL_SIGN (0xFFFFFFFFFFFFFFFE) otherwise; an owner-mode context skips those.  *d_overflow is set to 1 when a
+ * count exceeds cap (the caller checks it at its own pace and re-runs the batch with a larger cap). */
+int pb_frame_signs(const uint64_t* d_signs, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
+                   uint64_t* d_out, uint32_t* d_overflow, void* stream);
+/* pack != 0: framed rows from batch-order rows (zero rows in the padding); pack == 0: the inverse (framed -> batch order). */
+int pb_frame_rows(const void* d_src, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
+                  uint32_t row_bytes, int pack, void* d_out, void* stream);
+
 /* EmbeddingWorker::forward_batched_direct for summation slots
  * (embedding_worker_service/mod.rs:1076-1107 -> :874-942 -> PS :162-262 -> :486-629).
  * d_ids: flat raw ids, slot-major then sample-major; d_row_off[n_slots*batch+1] CSR offsets, or NULL

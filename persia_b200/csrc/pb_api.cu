@@ -212,6 +212,7 @@ SegArgs seg_args(pb_table* t, pb_ctx* c, float* vw) {
   a.batch = c->batch;
   a.piece = c->strict_reduce ? 0 : PB_PIECE;
   a.shared_groups = c->shared_groups ? 1 : 0;
+  a.quiet_miss = c->owner_mode ? 1 : 0;  // framed exchanges pad with null signs: not gradient-id misses
   a.partials = c->partials;
   return a;
 }
@@ -585,6 +586,23 @@ int pb_permute_rows(const void* d_src, const uint32_t* d_perm, uint32_t n, uint3
   return PB_OK;
 }
 
+int pb_frame_signs(const uint64_t* d_signs, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
+                   uint64_t* d_out, uint32_t* d_overflow, void* stream) {
+  if (!d_signs || !d_perm || !d_counts || !d_out || R == 0 || cap == 0) return fail(PB_ERR_INVALID, "bad argument");
+  launch_pack_signs(d_signs, d_perm, d_counts, R, cap, d_out, d_overflow, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_frame_rows(const void* d_src, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
+                  uint32_t row_bytes, int pack, void* d_out, void* stream) {
+  if (!d_src || !d_perm || !d_counts || !d_out || R == 0 || cap == 0) return fail(PB_ERR_INVALID, "bad argument");
+  if (row_bytes == 0 || row_bytes % 16) return fail(PB_ERR_INVALID, "row_bytes must be a multiple of 16");
+  launch_frame_rows(d_src, d_perm, d_counts, R, cap, row_bytes, pack, d_out, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
 int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
                const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream) {
   if (!t || !c || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
@@ -611,6 +629,7 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   if ((rc = ensure_alloc(t))) return rc;
   SlotsDev sl;
   if ((rc = make_slots(c->slots, h_slot_occ_off, sl))) return rc;
+  sl.null_sign = c->owner_mode ? 1 : 0;
   if (training) {
     launch_begin_batch(t->d, c->dev_tick, st);
     launch_probe(MODE_TRAIN, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);

@@ -12,6 +12,7 @@ constexpr uint64_t KEY_EMPTY = ~0ULL;          // hash-index cell holds no key
 constexpr uint32_t ROW_PENDING = 0xFFFFFFFFu;  // key claimed, row not yet published (never visible across kernels)
 constexpr uint32_t ROW_NONE = 0xFFFFFFFEu;     // key present but no storage (shard was full when it was admitted)
 constexpr uint32_t BUCKET = 8;                 // cells per bucket
+constexpr uint64_t PB_NULL_SIGN = 0xFFFFFFFFFFFFFFFEULL;  // padding of a framed shard exchange (owner-mode contexts only)
 
 // One cell of the index: 16 B.  Cells are grouped in buckets of BUCKET = 8 (one 128 B line): a sign's home
 // bucket is mix64(sign) & bucket_mask; a lookup reads whole buckets with 8 lanes, so the probe length is

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
   const uint32_t sub = threadIdx.x % BUCKET;
   const uint32_t gshift = (threadIdx.x & 31) & ~(BUCKET - 1);  // this group's bit offset in a warp ballot
   const uint32_t h_none = t.n_cells + 1;
-  const bool valid = i < n;
+  bool valid = i < n;
   // lane 0 of the group derives the sign (prefix arithmetic, hash); the other seven take it by shuffle
   uint64_t sign = 0ULL;
   uint32_t bucket = 0;
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
   }
   sign = __shfl_sync(0xffffffffu, sign, gshift);
   bucket = __shfl_sync(0xffffffffu, bucket, gshift);
+  const bool null_sign = sl.null_sign && sign == PB_NULL_SIGN;  // padding of a framed exchange: no lookup, reads as zeros
   const bool special = (sign == KEY_EMPTY);  // the one sign that collides with the empty marker has its own cell
   const unsigned long long stored = special ? 0ULL : sign;
   bool admit = true;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
     admit = u < hy.admit_p;
   }
   uint32_t result = h_none;
-  bool done = !valid;
+  bool done = !valid || null_sign;
   for (uint32_t step = 0; step <= t.bucket_mask + 1u; ++step) {
     if (!__any_sync(0xffffffffu, !done)) break;
     const bool look = !done && (!special || sub == 0);
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
     }
   }
   if (valid && sub == 0) {
-    if (MODE != MODE_SET && result == h_none) atomicAdd(&t.counters[CTR_MISS], 1u);
+    if (MODE != MODE_SET && result == h_none && !null_sign) atomicAdd(&t.counters[CTR_MISS], 1u);
     occ_cell[i] = result;
   }
 }
@@ -376,6 +377,48 @@ __global__ void __launch_bounds__(256) k_permute_u64(const uint64_t* __restrict_
   if (i < n) out[i] = src[perm[i]];
 }
 
+// Fixed-capacity framing of the shard exchange: every (source, destination) pair owns `cap` slots, so the
+// all-to-all has static shapes (no split sizes on the host, CUDA-graph capturable).  Unused slots carry
+// PB_NULL_SIGN (which the owner's probe ignores) / zero rows.  counts[r] > cap raises *overflow.
+__device__ __forceinline__ bool frame_slot(const uint32_t* __restrict__ counts, uint32_t R, uint32_t cap, uint32_t idx,
+                                           uint32_t& src_pos, uint32_t* overflow) {
+  const uint32_t r = idx / cap, k = idx % cap;
+  uint32_t off = 0;
+  for (uint32_t q = 0; q < r; ++q) off += counts[q];
+  const uint32_t c = counts[r];
+  if (k == 0 && c > cap && overflow) *overflow = 1;
+  src_pos = off + k;
+  return k < c;
+}
+
+__global__ void __launch_bounds__(256) k_pack_signs(const uint64_t* __restrict__ signs, const uint32_t* __restrict__ perm,
+                                                    const uint32_t* __restrict__ counts, uint32_t R, uint32_t cap,
+                                                    uint64_t* __restrict__ out, uint32_t* __restrict__ overflow) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * cap) return;
+  uint32_t pos;
+  out[idx] = frame_slot(counts, R, cap, idx, pos, overflow) ? signs[perm[pos]] : PB_NULL_SIGN;
+}
+
+// pack != 0: framed[r*cap + k] = rows[perm[off_r + k]] (zero rows in the padding); pack == 0: the inverse scatter
+__global__ void __launch_bounds__(256) k_frame_rows(const uint4* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                    const uint32_t* __restrict__ counts, uint32_t R, uint32_t cap,
+                                                    uint32_t row_words, uint32_t lanes, int pack, uint4* __restrict__ out) {
+  const uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) / lanes;
+  const uint32_t l = threadIdx.x % lanes;
+  if (idx >= R * cap) return;
+  uint32_t pos;
+  const bool valid = frame_slot(counts, R, cap, idx, pos, nullptr);
+  if (pack) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const size_t from = valid ? (size_t)perm[pos] * row_words : 0, to = (size_t)idx * row_words;
+    for (uint32_t w = l; w < row_words; w += lanes) out[to + w] = valid ? src[from + w] : z;
+  } else if (valid) {
+    const size_t from = (size_t)idx * row_words, to = (size_t)perm[pos] * row_words;
+    for (uint32_t w = l; w < row_words; w += lanes) out[to + w] = src[from + w];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers (host)
 // ------------------------------------------------------------------------------------------------
@@ -461,6 +504,19 @@ void launch_permute_rows(const void* src, const uint32_t* perm, uint32_t n, uint
 
 void launch_permute_u64(const uint64_t* src, const uint32_t* perm, uint32_t n, uint64_t* out, cudaStream_t st) {
   if (n) PB_LAUNCH(k_permute_u64, cdiv(n, 256), 256, 0, st, src, perm, n, out);
+}
+
+void launch_pack_signs(const uint64_t* signs, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
+                       uint64_t* out, uint32_t* overflow, cudaStream_t st) {
+  PB_LAUNCH(k_pack_signs, cdiv((uint64_t)R * cap, 256), 256, 0, st, signs, perm, counts, R, cap, out, overflow);
+}
+
+void launch_frame_rows(const void* src, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
+                       uint32_t row_bytes, int pack, void* out, cudaStream_t st) {
+  uint32_t words = row_bytes / 16, lanes = 1;
+  while (lanes < words && lanes < 32) lanes <<= 1;
+  PB_LAUNCH(k_frame_rows, cdiv((uint64_t)R * cap * lanes, 256), 256, 0, st, (const uint4*)src, perm, counts, R, cap, words,
+            lanes, pack, (uint4*)out);
 }
 
 void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st) {

@@ -14,6 +14,7 @@ struct SlotsDev {
   uint32_t n_slots;
   uint64_t spacing;  // 2^(64-prefix_bit) - 1
   uint32_t spacing_bits;  // 64 - prefix_bit
+  uint32_t null_sign;     // owner-mode contexts: PB_NULL_SIGN entries are padding, not lookups
   uint32_t uniform;       // occurrences per slot when every slot holds the same number (one id per sample), else 0
 };
 
@@ -36,7 +37,7 @@ struct SegArgs {
   const uint32_t* nan_tick;
   float* partials;  // 2 rows of dim floats per PIECE-block
   float* vw_stage;
-  uint32_t n, batch, piece, shared_groups;
+  uint32_t n, batch, piece, shared_groups, quiet_miss;
 };
 constexpr uint32_t PB_PIECE = 32;
 
@@ -74,6 +75,10 @@ void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* sh
 void launch_permute_rows(const void* src, const uint32_t* perm, uint32_t n, uint32_t row_bytes, int scatter, void* out,
                          cudaStream_t st);
 void launch_permute_u64(const uint64_t* src, const uint32_t* perm, uint32_t n, uint64_t* out, cudaStream_t st);
+void launch_pack_signs(const uint64_t* signs, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
+                       uint64_t* out, uint32_t* overflow, cudaStream_t st);
+void launch_frame_rows(const void* src, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
+                       uint32_t row_bytes, int pack, void* out, cudaStream_t st);
 uint64_t launch_count();
 enum { FAM_PROBE = 0, FAM_INIT, FAM_GATHER, FAM_NAN, FAM_SORT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
 void profile_enable(bool on);

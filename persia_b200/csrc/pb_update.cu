@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256, 3) k_reduce_update(TableDev t, OptimDev o
     if (!gr.ptr[slot] || a.nan_tick[slot] == tick) continue;  // skipped / NaN slot: nothing is applied
     if (whole) {
       if (row >= t.capacity) {
-        if (lane == 0) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
+        if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
         continue;
       }
       float* stage = a.vw_stage ? a.vw_stage + (size_t)j * t.dim : nullptr;
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256) k_combine_update(TableDev t, OptimDev op,
     }
     const uint32_t row = key < a.n ? a.occ_row[key] : ROW_NONE;
     if (row >= t.capacity) {
-      if (threadIdx.x == 0) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+      if (threadIdx.x == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
       continue;
     }
     const uint32_t q0 = (j0 < b) ? b : b + a.piece;   // first boundary after the first piece

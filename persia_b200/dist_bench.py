@@ -17,7 +17,17 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
     from .worker import CudaBackend, ShardedEmbeddingWorker
 
     dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
+    # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the one JSON line
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
     lib = N.load()
     dim = args.dim or 64
     S, B, K, Wm = args.slots, args.batch, args.steps, max(args.warmup, 3)
@@ -59,18 +69,65 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
     g.manual_seed(5 + rank)
     grads = (torch.randn((n_sets, S, B, dim), generator=g, device=dev) * 1e-2).half()
 
+    static = not args.dist_dynamic
+    if static:
+        wk.enable_static(B)
+
     def step(k):
-        wk.forward(ids_dev[k], B, training=True)
-        wk.backward(grads[k])
+        if static:
+            wk.forward_static(ids_dev[k], B, training=True)
+            wk.backward_static(grads[k])
+        else:
+            wk.forward(ids_dev[k], B, training=True)
+            wk.backward(grads[k])
+
+    graphs = None
+    graph_error = None
+    if static and args.dist_graph:  # static shapes: kernels + NCCL collectives of a step replay as one CUDA graph per buffer set
+        for i in range(3):
+            step(i % n_sets)
+        torch.cuda.synchronize()
+        dist.barrier()
+        try:
+            graphs = []
+            gstream = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(gstream):
+                for k in range(n_sets):
+                    gph = torch.cuda.CUDAGraph()
+                    # thread_local: the NCCL watchdog thread keeps polling its events while this thread captures
+                    with torch.cuda.graph(gph, stream=gstream, capture_error_mode="thread_local"):
+                        step(k)
+                    graphs.append(gph)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001 — fall back to eager static steps, say so in the output
+            graphs = None
+            graph_error = repr(e)[:200]
+    seg_steps = None
+    if static and graphs is None and not args.no_graph:
+        gstream = torch.cuda.Stream(device=dev)
+        seg_steps = [wk.make_graphed_step(ids_dev[k], grads[k], B, gstream)[0] for k in range(n_sets)]
+        torch.cuda.synchronize()
+        dist.barrier()
+    eager_step = step
+
+    def step(k):  # noqa: F811
+        if graphs is not None:
+            graphs[k].replay()
+        elif seg_steps is not None:
+            with torch.cuda.stream(gstream):
+                seg_steps[k]()
+        else:
+            eager_step(k)
 
     def timed(fn, n):
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        tstream = gstream if (seg_steps is not None and fn is step) else torch.cuda.current_stream()
+        e0.record(tstream)
         for i in range(n):
             fn(i % n_sets)
-        e1.record()
+        e1.record(tstream)
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
@@ -97,8 +154,12 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
 
     def e2e_step(k):
         ids_stage.copy_(ids_pinned[k], non_blocking=True)
-        out = wk.forward(ids_stage, B, training=True)
-        wk.backward(grads[k])
+        if static:
+            out = wk.forward_static(ids_stage, B, training=True)
+            wk.backward_static(grads[k])
+        else:
+            out = wk.forward(ids_stage, B, training=True)
+            wk.backward(grads[k])
         probe_host.copy_(out.view(-1)[:4], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -106,6 +167,8 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
         e2e_step(i % n_sets)
     ms_e2e = timed(e2e_step, K)
 
+    overflowed = wk.check_overflow() if static else False
+    assert not overflowed, "framed exchange overflowed its capacity: raise the slack"
     if rank == 0:
         ms_per_step = ms / K
         GB = B * world
@@ -126,8 +189,12 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
                            table_fill_seconds=round(t_fill, 2),
                            l2="inputs larger than L2: %.1f GB table per GPU + %d rotating id/grad sets" % (
                                resident * 4.0 * (dim + state) / 1e9, n_sets),
-                           launch="kernel by kernel (NCCL all_to_all_single via torch.distributed; one host sync per "
-                                  "step for the split sizes)"),
+                           launch=("fixed-capacity framed exchange (cap %d slots per GPU pair), step = one CUDA graph incl. the NCCL "
+                                   "all-to-alls" % wk.cap) if (static and graphs is not None) else
+                                  ("fixed-capacity framed exchange (cap %d slots per GPU pair); the compute segments between the 3 NCCL "
+                                   "all-to-alls replay as CUDA graphs" % wk.cap) if seg_steps is not None else
+                                  ("fixed-capacity framed exchange, kernel by kernel" if static else
+                                   "kernel by kernel (NCCL all_to_all_single with split sizes; one host sync per step)")),
             "clocks": clocks,
             "e2e": {"value": GB / (ms_e2e / K * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8 * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / K,
@@ -141,4 +208,9 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
         }
         print(json.dumps(line))
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    import sys
+
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)  # CUDA graphs + NCCL teardown order is fragile; everything has been reported

@@ -72,6 +72,8 @@ SYMBOLS = {
     "pb_ctx_set_async_grouping": (_i32, [_vp, _i32]),
     "pb_permute_u64": (_i32, [_vp, _vp, _u32, _vp, _vp]),
     "pb_permute_rows": (_i32, [_vp, _vp, _u32, _u32, _i32, _vp, _vp]),
+    "pb_frame_signs": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "pb_frame_rows": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _i32, _vp, _vp]),
     "pb_forward": (_i32, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp]),
     "pb_backward": (_i32, [_vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp]),
     "pb_launch_count": (_u64, []),

@@ -257,3 +257,21 @@ def permute_rows(src, perm, scatter=False, out=None):
     N.check(lib.pb_permute_rows(_ptr(src), _ptr(perm), perm.numel(), row_bytes, int(scatter), _ptr(out),
                                 _stream(src.device)))
     return out
+
+
+def frame_signs(signs, perm, counts, R, cap, overflow, out=None):
+    lib = N.load()
+    signs = _as_i64_bits(signs)
+    if out is None:
+        out = torch.empty(R * cap, dtype=torch.int64, device=signs.device)
+    N.check(lib.pb_frame_signs(_ptr(signs), _ptr(perm), _ptr(counts), R, cap, _ptr(out), _ptr(overflow), _stream(signs.device)))
+    return out
+
+
+def frame_rows(src, perm, counts, R, cap, pack, out):
+    """pack: batch-order rows [n, w] -> framed [R*cap, w]; unpack: framed -> batch order (out must be [n, w])."""
+    lib = N.load()
+    assert src.is_contiguous() and out.is_contiguous()
+    row_bytes = src.shape[1] * src.element_size()
+    N.check(lib.pb_frame_rows(_ptr(src), _ptr(perm), _ptr(counts), R, cap, row_bytes, int(pack), _ptr(out), _stream(src.device)))
+    return out

@@ -90,7 +90,23 @@ def test_worker_single_rank_matches_oracle():
     assert _check_shard(torch, be, w, pf, 1, 0, dev) > 1000
 
 
-def _rank_main(rank, R, port, q):
+def test_worker_single_rank_static_frames():
+    import torch
+
+    dev = torch.device("cuda", 0)
+    wk, be, pf = _make_worker(torch, dev)
+    wk.enable_static(B)
+    w, outs, _ = _reference(1)
+    for step, (ids, g) in enumerate(_batches(1)):
+        out = wk.forward_static(torch.from_numpy(ids[0].reshape(-1).view(np.int64)).to(dev), B, training=True).cpu().numpy()
+        for s in range(S):
+            np.testing.assert_array_equal(out[s].view(np.uint16), outs[step][s].view(np.uint16))
+        wk.backward_static(torch.from_numpy(g[0]).to(dev))
+    assert not wk.check_overflow()
+    assert _check_shard(torch, be, w, pf, 1, 0, dev) > 1000
+
+
+def _rank_main(rank, R, port, q, static=False):
     import torch
     import torch.distributed as dist
 
@@ -100,18 +116,24 @@ def _rank_main(rank, R, port, q):
     try:
         wk, be, pf = _make_worker(torch, dev)
         w, outs, _ = _reference(R)
+        if static:
+            wk.enable_static(B)
         for step, (ids, g) in enumerate(_batches(R)):
-            out = wk.forward(torch.from_numpy(ids[rank].reshape(-1).view(np.int64)).to(dev), B, training=True).cpu().numpy()
+            d_ids = torch.from_numpy(ids[rank].reshape(-1).view(np.int64)).to(dev)
+            out = (wk.forward_static if static else wk.forward)(d_ids, B, training=True).cpu().numpy()
             for s in range(S):
                 np.testing.assert_array_equal(out[s].view(np.uint16), outs[step][s][rank * B:(rank + 1) * B].view(np.uint16))
-            wk.backward(torch.from_numpy(g[rank]).to(dev))
+            (wk.backward_static if static else wk.backward)(torch.from_numpy(g[rank]).to(dev))
+        if static:
+            assert not wk.check_overflow()
         n = _check_shard(torch, be, w, pf, R, rank, dev)
         q.put((rank, n))
     finally:
         dist.destroy_process_group()
 
 
-def test_worker_two_ranks_nccl_matches_oracle():
+@pytest.mark.parametrize("static", [False, True])
+def test_worker_two_ranks_nccl_matches_oracle(static):
     import torch
     import torch.multiprocessing as mp
 
@@ -122,7 +144,7 @@ def test_worker_two_ranks_nccl_matches_oracle():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q, static)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=300) for _ in range(2))
