@@ -73,9 +73,16 @@ int pb_table_configure(pb_table* t, const pb_hyper_cfg* cfg);
 int pb_table_size(pb_table* t, uint64_t* h_out, void* stream);
 /* clear (persia-embedding-holder/src/lib.rs:95-97). */
 int pb_table_clear(pb_table* t, void* stream);
+/* Capacity policy.  The reference's EvictionMap drops the least recently used entry on every insert beyond capacity
+ * (persia-embedding-holder/src/eviction_map.rs:76-97).  Here recency is the batch number of a row's last training
+ * lookup and eviction is a sweep: every `check_every` training requests, if fewer than `low_water` rows are free,
+ * the oldest rows are released until `target_free` are (rows touched in the last `keep_batches` batches are never
+ * released: gradients may still be in flight for them).  check_every == 0 (default): no eviction, admissions beyond
+ * capacity are refused and counted. */
+int pb_table_set_eviction(pb_table* t, uint32_t check_every, uint64_t low_water, uint64_t target_free, uint32_t keep_batches);
 /* floats per resident row: dim + optimizer state (emb_entry.rs:17-25 `inner`). */
 int pb_table_entry_len(pb_table* t, uint32_t* h_out);
-/* counters since creation: [0] rows admitted, [1] lookups that missed (infer) or were not admitted,
+/* counters since creation / clear: [0] resident rows (admitted - evicted), [1] lookups that missed (infer) or were not admitted,
  * [2] gradient ids not found (gradient_id_miss_count), [3] admissions refused because the shard is full.
  * Synchronises `stream`. */
 int pb_table_counters(pb_table* t, uint64_t h_out[4], void* stream);

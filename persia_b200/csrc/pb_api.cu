@@ -79,6 +79,10 @@ struct pb_table {
   // Adam: accumulated (beta1^t, beta2^t) per feature group, keyed by index prefix (optim.rs:99-131, 155-197)
   std::vector<std::pair<uint64_t, std::pair<float, float>>> adam_pow;
   float b1p_direct = 1.0f, b2p_direct = 1.0f;
+  // capacity policy (pb_table_set_eviction): 0 = refuse admissions when full
+  uint32_t evict_every = 0, evict_low = 0, evict_target = 0, evict_keep = 2;
+  uint32_t train_calls = 0;
+  uint32_t* evict_ws = nullptr;
 };
 
 struct pb_ctx {
@@ -141,13 +145,14 @@ int ensure_alloc(pb_table* t) {
   d.n_cells = next_pow2(want);
   d.cell_mask = d.n_cells - 1;
   d.bucket_mask = d.n_cells / BUCKET - 1;
-  PB_CUDA(cudaMalloc(&d.cells, sizeof(Cell) * ((size_t)d.n_cells + 1)));
+  PB_CUDA(cudaMalloc(&d.cells, sizeof(Cell) * ((size_t)d.n_cells + N_SPECIAL)));
   PB_CUDA(cudaMalloc(&d.rows, sizeof(float) * (size_t)d.capacity * d.stride));
   PB_CUDA(cudaMalloc(&d.counters, sizeof(uint32_t) * CTR_COUNT));
   PB_CUDA(cudaMalloc(&d.row_lead, sizeof(unsigned long long) * (size_t)d.capacity));
   PB_CUDA(cudaMemset(d.row_lead, 0, sizeof(unsigned long long) * (size_t)d.capacity));
   PB_CUDA(cudaMemset(d.counters, 0, sizeof(uint32_t) * CTR_COUNT));
-  launch_fill_cells(d.cells, (uint64_t)d.n_cells + 1, 0);
+  launch_fill_cells(d.cells, (uint64_t)d.n_cells + N_SPECIAL, 0);
+  d.free_rows = nullptr;
   PB_CUDA(cudaDeviceSynchronize());
   t->allocated = true;
   return PB_OK;
@@ -161,6 +166,17 @@ int ensure_scratch(pb_table* t, uint32_t n) {
   uint32_t cap = next_pow2(n);
   PB_CUDA(cudaMalloc(&t->scratch, sizeof(uint32_t) * (size_t)cap));
   t->scratch_cap = cap;
+  return PB_OK;
+}
+
+// Between two training requests: release the least recently used rows when free storage runs low.
+int maybe_evict(pb_table* t, cudaStream_t st) {
+  if (!t->evict_every || (++t->train_calls % t->evict_every)) return PB_OK;
+  if (!t->d.free_rows) {
+    PB_CUDA(cudaMalloc(&t->d.free_rows, sizeof(uint32_t) * (size_t)t->d.capacity));
+    PB_CUDA(cudaMalloc(&t->evict_ws, sizeof(uint32_t) * (3 + 1024)));
+  }
+  launch_evict(t->d, t->evict_low, t->evict_target, t->evict_keep, t->evict_ws, st);
   return PB_OK;
 }
 
@@ -273,6 +289,8 @@ int pb_table_destroy(pb_table* t) {
     cudaFree(t->d.rows);
     cudaFree(t->d.counters);
     cudaFree(t->d.row_lead);
+    if (t->d.free_rows) cudaFree(t->d.free_rows);
+    if (t->evict_ws) cudaFree(t->evict_ws);
   }
   if (t->scratch) cudaFree(t->scratch);
   delete t;
@@ -312,6 +330,17 @@ int pb_table_configure(pb_table* t, const pb_hyper_cfg* c) {
   return PB_OK;
 }
 
+int pb_table_set_eviction(pb_table* t, uint32_t check_every, uint64_t low_water, uint64_t target_free, uint32_t keep_batches) {
+  if (!t) return fail(PB_ERR_INVALID, "null argument");
+  if (check_every && (target_free < low_water || target_free > t->cfg.capacity))
+    return fail(PB_ERR_INVALID, "need low_water <= target_free <= capacity");
+  t->evict_every = check_every;
+  t->evict_low = (uint32_t)low_water;
+  t->evict_target = (uint32_t)target_free;
+  t->evict_keep = keep_batches;
+  return PB_OK;
+}
+
 int pb_table_entry_len(pb_table* t, uint32_t* h_out) {
   if (!t || !h_out) return fail(PB_ERR_INVALID, "null argument");
   if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered");
@@ -328,7 +357,7 @@ int pb_table_counters(pb_table* t, uint64_t h_out[4], void* stream) {
   uint32_t c[CTR_COUNT];
   PB_CUDA(cudaMemcpyAsync(c, t->d.counters, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   PB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  h_out[0] = c[CTR_ADMIT];
+  h_out[0] = c[CTR_ADMIT] - c[CTR_EVICT];  // resident rows
   h_out[1] = c[CTR_MISS];
   h_out[2] = c[CTR_GRAD_MISS];
   h_out[3] = c[CTR_FULL];
@@ -349,7 +378,7 @@ int pb_table_clear(pb_table* t, void* stream) {
   if (!t->allocated) return PB_OK;
   DeviceGuard g(t->device);
   cudaStream_t st = (cudaStream_t)stream;
-  launch_fill_cells(t->d.cells, (uint64_t)t->d.n_cells + 1, st);
+  launch_fill_cells(t->d.cells, (uint64_t)t->d.n_cells + N_SPECIAL, st);
   PB_CUDA(cudaMemsetAsync(t->d.counters, 0, sizeof(uint32_t) * CTR_COUNT, st));
   PB_CUDA(cudaMemsetAsync(t->d.row_lead, 0, sizeof(unsigned long long) * (size_t)t->d.capacity, st));
   return PB_OK;
@@ -372,6 +401,7 @@ int pb_lookup(pb_table* t, const uint64_t* d_signs, uint32_t n, int training, fl
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
   if (training) {
+    if ((rc = maybe_evict(t, st))) return rc;
     launch_begin_batch(t->d, nullptr, st);
     launch_probe(MODE_TRAIN, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   } else {
@@ -631,6 +661,7 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   if ((rc = make_slots(c->slots, h_slot_occ_off, sl))) return rc;
   sl.null_sign = c->owner_mode ? 1 : 0;
   if (training) {
+    if ((rc = maybe_evict(t, st))) return rc;
     launch_begin_batch(t->d, c->dev_tick, st);
     launch_probe(MODE_TRAIN, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
   } else {

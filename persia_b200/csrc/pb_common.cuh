@@ -9,6 +9,8 @@
 namespace pb {
 
 constexpr uint64_t KEY_EMPTY = ~0ULL;          // hash-index cell holds no key
+constexpr uint64_t KEY_TOMB = ~0ULL - 2;       // cell whose sign was evicted: probing continues past it, admissions reuse it
+constexpr uint32_t N_SPECIAL = 3;              // signs >= KEY_TOMB collide with the markers: each has a reserved cell
 constexpr uint32_t ROW_PENDING = 0xFFFFFFFFu;  // key claimed, row not yet published (never visible across kernels)
 constexpr uint32_t ROW_NONE = 0xFFFFFFFEu;     // key present but no storage (shard was full when it was admitted)
 constexpr uint32_t BUCKET = 8;                 // cells per bucket
@@ -50,9 +52,10 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
 }
 
 struct TableDev {
-  Cell* cells;         // n_cells + 1 entries; the last one is reserved for sign == KEY_EMPTY
+  Cell* cells;         // n_cells + N_SPECIAL entries; the last ones are reserved for the signs that equal a marker
   float* rows;         // capacity * stride floats: emb(dim) ++ optimizer state ++ pad
   uint32_t* counters;  // see CTR_* below
+  uint32_t* free_rows;   // stack of rows released by eviction (CTR_FREE entries)
   unsigned long long* row_lead;  // per row: (batch number << 32) | ~(first occurrence of the sign in that batch)
   uint64_t cell_mask;    // n_cells - 1
   uint32_t bucket_mask;  // n_cells / BUCKET - 1
@@ -63,13 +66,14 @@ struct TableDev {
 
 enum {
   CTR_ROWS = 0,      // bump allocator of row storage
-  CTR_SPARE = 1,
+  CTR_FREE = 1,      // rows on the free stack
   CTR_TICK = 2,      // batch number: bumped on the device by every training request (CUDA-graph safe)
   CTR_MISS = 3,      // infer misses / refused admissions
   CTR_GRAD_MISS = 4, // gradient ids not found
   CTR_FULL = 5,      // admissions refused for lack of capacity
   CTR_ADMIT = 6,     // rows admitted
-  CTR_COUNT = 8
+  CTR_EVICT = 7,     // rows evicted
+  CTR_COUNT = 16
 };
 
 struct OptimDev {

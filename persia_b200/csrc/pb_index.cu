@@ -51,14 +51,15 @@ __device__ __noinline__ void init_row(const TableDev& t, const HyperDev& hy, con
 //   MODE_FIND   read-only probe (inference lookup, update, get_rows)
 //   MODE_TRAIN  find, refresh recency, admit on miss (training lookup)
 //   MODE_SET    find or force-admit without initialisation (set_embedding)
-// Output: the index cell of every occurrence (n_cells + 1 when the sign has no storage).  The row number
+// Output: the index cell of every occurrence (n_cells + N_SPECIAL when the sign has no storage).  The row number
 // is read from the cell by the kernels that follow, so nothing here ever waits on another thread.
 // The group that admits a sign also initialises its row (emb_entry.rs:28-68 + optim.rs:299-302).
 // Recency (get_refresh, eviction_map.rs:48-60) is not written here: thousands of occurrences of one hot
 // sign would all store to the same cell; the gather kernel records it per row after a block-level dedup.
-// Invariant that makes "an empty cell in the bucket => the sign is absent" true: a sign is always stored
-// in the first bucket of its probe sequence that had a free cell when it was admitted, and cells are
-// never freed in place.
+// Invariant that makes "an empty cell in the bucket => the sign is absent" true: a sign is stored no later
+// in its probe sequence than the first bucket that had an EMPTY cell when it was admitted, and a cell never
+// returns to EMPTY: eviction leaves a tombstone, which lookups walk past and admissions reuse (after having
+// seen an EMPTY cell further on, i.e. knowing the sign is absent).
 // ------------------------------------------------------------------------------------------------
 template <int MODE, bool PREFIX>
 __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev op, SlotsDev sl,
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
   const uint32_t i = (blockIdx.x * 256 + threadIdx.x) / BUCKET;
   const uint32_t sub = threadIdx.x % BUCKET;
   const uint32_t gshift = (threadIdx.x & 31) & ~(BUCKET - 1);  // this group's bit offset in a warp ballot
-  const uint32_t h_none = t.n_cells + 1;
+  const uint32_t h_none = t.n_cells + N_SPECIAL;
   bool valid = i < n;
   // lane 0 of the group derives the sign (prefix arithmetic, hash); the other seven take it by shuffle
   uint64_t sign = 0ULL;
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
   sign = __shfl_sync(0xffffffffu, sign, gshift);
   bucket = __shfl_sync(0xffffffffu, bucket, gshift);
   const bool null_sign = sl.null_sign && sign == PB_NULL_SIGN;  // padding of a framed exchange: no lookup, reads as zeros
-  const bool special = (sign == KEY_EMPTY);  // the one sign that collides with the empty marker has its own cell
+  const bool special = (sign >= KEY_TOMB);  // the three signs that collide with a marker have their own cells
+  const uint32_t special_cell = t.n_cells + (uint32_t)(KEY_EMPTY - sign);
   const unsigned long long stored = special ? 0ULL : sign;
   bool admit = true;
   if (MODE == MODE_TRAIN && hy.admit_p < 1.0f) {  // reference: unseeded thread_rng draw (unpinned)
@@ -93,32 +95,46 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
   }
   uint32_t result = h_none;
   bool done = !valid || null_sign;
-  for (uint32_t step = 0; step <= t.bucket_mask + 1u; ++step) {
+  const uint32_t home = bucket;
+  uint32_t tomb_cell = 0xFFFFFFFFu;  // first tombstone met on the probe path (admissions reuse it)
+  for (uint32_t step = 0; step <= 2u * (t.bucket_mask + 1u); ++step) {
     if (!__any_sync(0xffffffffu, !done)) break;
     const bool look = !done && (!special || sub == 0);
-    const uint32_t cell = special ? t.n_cells : bucket * BUCKET + sub;
-    uint4 c = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, ROW_PENDING, 0u);
+    const uint32_t cell = special ? special_cell : bucket * BUCKET + sub;
+    uint4 c = make_uint4(0xFFFFFFFEu, 0xFFFFFFFFu, ROW_PENDING, 0u);  // neither empty, tombstone nor any sign's low word pair
     if (look) c = __ldcg(reinterpret_cast<const uint4*>(t.cells + cell));
     const unsigned long long kk = (unsigned long long)c.x | ((unsigned long long)c.y << 32);
     const uint32_t mm = (__ballot_sync(0xffffffffu, look && kk == stored) >> gshift) & 0xffu;
     const uint32_t em = (__ballot_sync(0xffffffffu, look && kk == KEY_EMPTY) >> gshift) & 0xffu;
+    const uint32_t tm = (__ballot_sync(0xffffffffu, look && kk == KEY_TOMB && !special) >> gshift) & 0xffu;
     const uint32_t lm = mm ? __ffs(mm) - 1 : 0;  // lane of the match
-    const uint32_t le = em ? __ffs(em) - 1 : 0;  // lane of the first free cell
-    // groups that must try to admit the sign into the first free cell of this bucket
+    if (!done && !mm && tm && tomb_cell == 0xFFFFFFFFu) tomb_cell = bucket * BUCKET + (__ffs(tm) - 1);
+    // an EMPTY cell in this bucket (and no match so far) proves the sign absent: admit it into the first tombstone
+    // seen on the way, else into the first empty cell here
     const bool try_ins = !done && !mm && em && MODE != MODE_FIND && admit;
+    const bool use_tomb = try_ins && tomb_cell != 0xFFFFFFFFu;
+    const uint32_t le = em ? __ffs(em) - 1 : 0;  // lane of the first free cell
+    const uint32_t free_cell = special ? special_cell : (use_tomb ? tomb_cell : bucket * BUCKET + le);
     unsigned long long old = 0ULL;
-    if (try_ins && sub == le) old = atomicCAS(&t.cells[cell].key, KEY_EMPTY, stored);
+    if (try_ins && sub == le) old = atomicCAS(&t.cells[free_cell].key, use_tomb ? KEY_TOMB : KEY_EMPTY, stored);
     old = __shfl_sync(0xffffffffu, old, gshift + le);
-    const bool won_cas = try_ins && old == KEY_EMPTY;  // lane `le` of this group admitted the sign
-    const uint32_t free_cell = special ? t.n_cells : bucket * BUCKET + le;
+    const bool won_cas = try_ins && old == (use_tomb ? KEY_TOMB : KEY_EMPTY);  // lane `le` of this group admitted the sign
     uint32_t row = 0;
     if (won_cas && sub == le) {
-      row = atomicAdd(&t.counters[CTR_ROWS], 1u);
+      // storage: a row released by eviction if there is one, else the next never-used row
+      uint32_t f = atomicSub(&t.counters[CTR_FREE], 1u);
+      if (f > 0 && f <= t.capacity) {
+        row = t.free_rows[f - 1];
+      } else {
+        atomicAdd(&t.counters[CTR_FREE], 1u);
+        row = atomicAdd(&t.counters[CTR_ROWS], 1u);
+      }
       if (row >= t.capacity) {
         row = ROW_NONE;
         atomicAdd(&t.counters[CTR_FULL], 1u);
       } else {
         atomicAdd(&t.counters[CTR_ADMIT], 1u);
+        t.row_lead[row] = (unsigned long long)tick << 32;  // recency of a fresh row (training lookups raise it)
       }
       *reinterpret_cast<volatile uint32_t*>(&t.cells[free_cell].row) = row;
     }
@@ -126,7 +142,7 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
     if (MODE == MODE_TRAIN && won_cas && row != ROW_NONE) init_row(t, hy, op, sign, row, sub);  // all 8 lanes
     if (!done) {
       if (mm) {
-        result = special ? t.n_cells : bucket * BUCKET + lm;
+        result = special ? special_cell : bucket * BUCKET + lm;
         done = true;
       } else if (em) {
         if (!try_ins) {
@@ -134,14 +150,17 @@ __global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev
         } else if (won_cas) {
           result = (row == ROW_NONE) ? h_none : free_cell;
           done = true;
-        } else if (old == stored) {  // a duplicate occurrence won the race for the same sign
+        } else if (old == stored) {  // a duplicate occurrence won the race for the same cell
           result = free_cell;
           done = true;
+        } else {
+          // another sign took the cell (possibly this very sign took a different one): search again from home
+          bucket = home;
+          tomb_cell = 0xFFFFFFFFu;
         }
-        // else: another sign took the cell — look at the same bucket again
       } else {
-        if (special) done = true;  // cannot happen: the reserved cell only ever holds this sign
-        bucket = (bucket + 1) & t.bucket_mask;  // full bucket without the sign: next line
+        if (special) done = true;  // cannot happen: a reserved cell only ever holds its sign
+        bucket = (bucket + 1) & t.bucket_mask;  // no match and no empty cell: next line
       }
     }
   }
@@ -194,7 +213,7 @@ __global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, co
 #pragma unroll
     for (int k = 0; k < GATHER_ROWS; ++k) cell[k] = (r0 + k < n_out) ? occ_cell[r0 + k] : 0xFFFFFFFFu;
 #pragma unroll
-    for (int k = 0; k < GATHER_ROWS; ++k) row[k] = (cell[k] <= t.n_cells) ? t.cells[cell[k]].row : ROW_NONE;
+    for (int k = 0; k < GATHER_ROWS; ++k) row[k] = (cell[k] < t.n_cells + N_SPECIAL) ? t.cells[cell[k]].row : ROW_NONE;
     for (uint32_t c = lane; c < nvec; c += G) {
       float v[GATHER_ROWS][VEC];
 #pragma unroll
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, co
     for (int k = 0; k < VEC; ++k) acc[k] = 0.0f;
     for (uint32_t j = beg; j < end; ++j) {
       uint32_t h = occ_cell[j];
-      uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+      uint32_t row = (h < t.n_cells + N_SPECIAL) ? t.cells[h].row : ROW_NONE;
       if (row >= t.capacity) continue;
       float v[VEC];
       load_vec<VEC>(t.rows + (size_t)row * t.stride + c * VEC, v);
@@ -266,7 +285,7 @@ __global__ void __launch_bounds__(256) k_elect_leaders(TableDev t, const uint32_
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     uint32_t h = occ_cell[i];
-    uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+    uint32_t row = (h < t.n_cells + N_SPECIAL) ? t.cells[h].row : ROW_NONE;
     if (row >= t.capacity) row = ROW_NONE;
     occ_row[i] = row;
     if (row != ROW_NONE) {
@@ -299,7 +318,7 @@ __global__ void __launch_bounds__(256) k_copy_entries(TableDev t, const uint32_t
   if (warp >= n) return;
   uint32_t h = occ_cell[warp];
   uint32_t elen = t.dim + t.state_floats;
-  uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+  uint32_t row = (h < t.n_cells + N_SPECIAL) ? t.cells[h].row : ROW_NONE;
   bool ok = row < t.capacity;
   if (!WRITE && found && lane == 0) found[warp] = ok ? 1 : 0;
   float* e = entries + (size_t)warp * elen;
@@ -375,6 +394,71 @@ __global__ void __launch_bounds__(256) k_permute_u64(const uint64_t* __restrict_
                                                      uint32_t n, uint64_t* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = src[perm[i]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Capacity: the reference's EvictionMap drops the least recently used entry whenever an insert pushes it over
+// capacity (eviction_map.rs:76-97).  Here recency is the batch number kept in row_lead's high half and
+// eviction is a sweep run between batches when free storage is low: (1) histogram of row ages over the occupied
+// cells, (2) the age threshold that releases `want` rows (never rows touched in the last `keep` batches),
+// (3) tombstone those cells and push their rows on the free stack.  ev[0] = threshold age, ev[1] = want,
+// ev[2] = go flag, ev[3..] = age histogram (EV_BINS bins, last bin = older).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t EV_BINS = 1024;
+__global__ void k_evict_plan(TableDev t, uint32_t low_water, uint32_t target_free, uint32_t* __restrict__ ev) {
+  // one block: decide whether a sweep is needed and clear the histogram
+  uint32_t used = min(t.counters[CTR_ROWS], t.capacity);
+  uint32_t free_now = (t.capacity - used) + t.counters[CTR_FREE];
+  bool go = free_now < low_water;
+  for (uint32_t i = threadIdx.x; i < EV_BINS; i += blockDim.x) ev[3 + i] = 0;
+  if (threadIdx.x == 0) {
+    ev[2] = go ? 1u : 0u;
+    ev[1] = go ? (target_free > free_now ? target_free - free_now : 0u) : 0u;
+    ev[0] = 0xFFFFFFFFu;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_evict_hist(TableDev t, uint32_t* __restrict__ ev) {
+  if (!ev[2]) return;
+  const uint32_t tick = t.counters[CTR_TICK];
+  const uint64_t n = (uint64_t)t.n_cells + N_SPECIAL;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    Cell c = t.cells[i];
+    bool occupied = (i < t.n_cells) ? (c.key < KEY_TOMB) : (c.key == 0ULL);
+    if (!occupied || c.row >= t.capacity) continue;
+    uint32_t age = tick - (uint32_t)(t.row_lead[c.row] >> 32);
+    atomicAdd(&ev[3 + min(age, EV_BINS - 1)], 1u);
+  }
+}
+
+__global__ void k_evict_threshold(uint32_t keep, uint32_t* __restrict__ ev) {
+  if (threadIdx.x || !ev[2]) return;
+  uint32_t want = ev[1], got = 0, thr = 0xFFFFFFFFu;
+  for (uint32_t a = EV_BINS; a-- > 0 && a > keep;) {  // oldest first; ages <= keep are protected
+    got += ev[3 + a];
+    thr = a;
+    if (got >= want) break;
+  }
+  ev[0] = got ? thr : 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(256) k_evict_sweep(TableDev t, uint32_t* __restrict__ ev) {
+  if (!ev[2] || ev[0] == 0xFFFFFFFFu) return;
+  const uint32_t tick = t.counters[CTR_TICK], thr = ev[0];
+  const uint64_t n = (uint64_t)t.n_cells + N_SPECIAL;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    Cell c = t.cells[i];
+    bool occupied = (i < t.n_cells) ? (c.key < KEY_TOMB) : (c.key == 0ULL);
+    if (!occupied || c.row >= t.capacity) continue;
+    uint32_t age = tick - (uint32_t)(t.row_lead[c.row] >> 32);
+    if (age < thr) continue;
+    t.cells[i].key = (i < t.n_cells) ? KEY_TOMB : KEY_EMPTY;  // reserved cells have no probe chain behind them
+    t.cells[i].row = ROW_PENDING;
+    t.row_lead[c.row] = 0ULL;
+    uint32_t f = atomicAdd(&t.counters[CTR_FREE], 1u);
+    t.free_rows[f] = c.row;
+    atomicAdd(&t.counters[CTR_EVICT], 1u);
+  }
 }
 
 // Fixed-capacity framing of the shard exchange: every (source, destination) pair owns `cap` slots, so the
@@ -517,6 +601,13 @@ void launch_frame_rows(const void* src, const uint32_t* perm, const uint32_t* co
   while (lanes < words && lanes < 32) lanes <<= 1;
   PB_LAUNCH(k_frame_rows, cdiv((uint64_t)R * cap * lanes, 256), 256, 0, st, (const uint4*)src, perm, counts, R, cap, words,
             lanes, pack, (uint4*)out);
+}
+
+void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, uint32_t keep, uint32_t* ev, cudaStream_t st) {
+  PB_LAUNCH(k_evict_plan, 1, 256, 0, st, t, low_water, target_free, ev);
+  PB_LAUNCH(k_evict_hist, 148 * 8, 256, 0, st, t, ev);
+  PB_LAUNCH(k_evict_threshold, 1, 32, 0, st, keep, ev);
+  PB_LAUNCH(k_evict_sweep, 148 * 8, 256, 0, st, t, ev);
 }
 
 void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st) {

@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(256) k_update_direct(TableDev t, OptimDev op, 
   uint32_t lane = threadIdx.x % G;
   if (gid >= n) return;
   uint32_t h = occ_cell[gid];
-  uint32_t row = (h <= t.n_cells) ? t.cells[h].row : ROW_NONE;
+  uint32_t row = (h < t.n_cells + N_SPECIAL) ? t.cells[h].row : ROW_NONE;
   if (row >= t.capacity) {
     if (lane == 0) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
     return;

@@ -115,6 +115,7 @@ class _State:
 
             dev = self.device_id if self.device_id is not None else 0
             sh = SH.EmbeddingShard(dim, self.capacity, dev)
+            sh.set_eviction()  # the reference's holder is an LRU map bounded by `capacity` (eviction_map.rs:76-97)
             if self.optimizer is not None:
                 sh.set_optimizer(**self.optimizer)
             if self.hyper is not None:

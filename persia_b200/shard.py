@@ -53,6 +53,12 @@ class EmbeddingShard:
         cfg = N.HyperCfg(init_lower, init_upper, admit_probability, int(enable_weight_bound), weight_bound)
         N.check(self.lib.pb_table_configure(self.h, C.byref(cfg)))
 
+    def set_eviction(self, check_every=4, low_water=None, target_free=None, keep_batches=2):
+        """Recency-based capacity policy (EvictionMap semantics, batch-granular); see persia_b200.h."""
+        low = self.capacity // 16 if low_water is None else low_water
+        tgt = self.capacity // 8 if target_free is None else target_free
+        N.check(self.lib.pb_table_set_eviction(self.h, check_every, low, tgt, keep_batches))
+
     @property
     def entry_len(self):
         if self._entry_len is None:

@@ -510,3 +510,38 @@ def test_adam_training_bit_exact(torch_cuda, pb, oracle, dim):
     touched = _train_steps(torch, s, ctx, w, rng, S, B, dim, card, steps=5, max_ids=2)
     for t in touched:
         _entries_equal(torch, s, w, t)
+
+
+def test_capacity_eviction_keeps_recent_rows(torch_cuda, pb, oracle):
+    """EvictionMap semantics (eviction_map.rs:76-97), batch-granular: least recently used rows go first, rows used
+    in the recent batches and a hot set touched every batch survive, the shard never refuses an admission, and a
+    re-admitted sign starts again from its initial value."""
+    torch = torch_cuda
+    dim, cap = 8, 4096
+    s = _shard(pb, oracle, dim, cap, oracle.SGD)
+    s.set_eviction(check_every=1, low_water=600, target_free=1200, keep_batches=1)
+    hot = np.arange(10_000_000, 10_000_050, dtype=np.uint64)
+    batches = []
+    for k in range(60):
+        cold = np.arange(k * 300, (k + 1) * 300, dtype=np.uint64) + np.uint64(1)
+        q = np.concatenate([cold, hot])
+        batches.append(cold)
+        out = s.lookup(to_dev_ids(q, DEV), training=True).cpu().numpy()
+        assert np.abs(out).sum(axis=1).min() > 0  # every sign got storage (nothing refused, nothing read as zeros)
+        if k == 0:
+            first_val = out[:300].copy()
+    c = s.counters()
+    assert c["capacity_refused"] == 0
+    assert 0 < len(s) <= cap
+    _, found_hot = s.get_entries(to_dev_ids(hot, DEV))
+    assert found_hot.all()
+    for k in range(52, 60):  # the most recent batches are all resident
+        _, f = s.get_entries(to_dev_ids(batches[k], DEV))
+        assert f.all(), k
+    _, f0 = s.get_entries(to_dev_ids(batches[0], DEV))
+    assert not f0.any()  # the oldest batch is gone
+    np.testing.assert_array_equal(s.lookup(to_dev_ids(batches[0], DEV), training=False).cpu().numpy(), 0)
+    # dirty a few hot rows, then check an evicted sign comes back with its initial value (seeded by the sign)
+    again = s.lookup(to_dev_ids(batches[0], DEV), training=True).cpu().numpy()
+    np.testing.assert_array_equal(again, first_val)
+    np.testing.assert_array_equal(again, np.stack([oracle.init_row(int(x), dim, -0.01, 0.01) for x in batches[0]]))
