@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-grouping", action="store_true", help="run the backward's grouping inside pb_backward")
     ap.add_argument("--dist-graph", action="store_true", help="multi-GPU: capture the framed step incl. NCCL in CUDA graphs")
+    ap.add_argument("--dist-nccl", action="store_true", help="multi-GPU: NCCL all-to-all instead of the peer-memory exchange")
     ap.add_argument("--dist-dynamic", action="store_true", help="multi-GPU: split-size all-to-all (host sync per step)")
     ap.add_argument("--equal-card", action="store_true", help="diagnostic: every slot gets rows/slots ids (no tiny slots)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs")

@@ -164,6 +164,15 @@ int pb_frame_signs(const uint64_t* d_signs, const uint32_t* d_perm, const uint32
 int pb_frame_rows(const void* d_src, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
                   uint32_t row_bytes, int pack, void* d_out, void* stream);
 
+/* The same exchange over NVLink peer memory instead of NCCL (at most 16 GPUs of one box).  h_peer_ptrs[q] is the
+ * device address, mapped in this process, of rank q's receive buffer ([R*cap] rows); segment q of d_framed is stored
+ * into it at slot my_rank.  pb_p2p_barrier then orders the step across the ranks: h_flag_ptrs[q] addresses rank q's
+ * 16 flag words, *d_epoch counts barriers on the device (CUDA-graph safe); *d_err is raised instead of spinning
+ * forever when a peer does not arrive. */
+int pb_p2p_exchange(const void* d_framed, const uint64_t* h_peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
+                    uint32_t row_bytes, void* stream);
+int pb_p2p_barrier(const uint64_t* h_flag_ptrs, uint32_t* d_epoch, uint32_t R, uint32_t my_rank, uint32_t* d_err, void* stream);
+
 /* EmbeddingWorker::forward_batched_direct for summation slots
  * (embedding_worker_service/mod.rs:1076-1107 -> :874-942 -> PS :162-262 -> :486-629).
  * d_ids: flat raw ids, slot-major then sample-major; d_row_off[n_slots*batch+1] CSR offsets, or NULL

@@ -633,6 +633,22 @@ int pb_frame_rows(const void* d_src, const uint32_t* d_perm, const uint32_t* d_c
   return PB_OK;
 }
 
+int pb_p2p_exchange(const void* d_framed, const uint64_t* h_peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
+                    uint32_t row_bytes, void* stream) {
+  if (!d_framed || !h_peer_ptrs || R == 0 || R > 16 || my_rank >= R || cap == 0) return fail(PB_ERR_INVALID, "bad argument");
+  if (row_bytes == 0 || row_bytes % 16) return fail(PB_ERR_INVALID, "row_bytes must be a multiple of 16");
+  launch_p2p_exchange(d_framed, h_peer_ptrs, R, my_rank, cap, row_bytes, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_p2p_barrier(const uint64_t* h_flag_ptrs, uint32_t* d_epoch, uint32_t R, uint32_t my_rank, uint32_t* d_err, void* stream) {
+  if (!h_flag_ptrs || !d_epoch || R == 0 || R > 16 || my_rank >= R) return fail(PB_ERR_INVALID, "bad argument");
+  launch_p2p_barrier(h_flag_ptrs, d_epoch, R, my_rank, d_err, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
 int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
                const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream) {
   if (!t || !c || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");

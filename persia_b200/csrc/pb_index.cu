@@ -504,6 +504,54 @@ __global__ void __launch_bounds__(256) k_frame_rows(const uint4* __restrict__ sr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Shard exchange over NVLink peer memory (no NCCL, no host): the R segments of a framed buffer are stored
+// straight into the peers' receive buffers (peer q gets segment q at slot `my_rank`), then a barrier kernel
+// over peer-mapped flag words orders the step.  Buffers and flags live in symmetric memory mapped by the host
+// side (torch symmetric memory); everything here is plain stores / loads on peer pointers.
+// ------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+  uint64_t p[16];
+};
+
+__global__ void __launch_bounds__(256) k_p2p_exchange(const uint4* __restrict__ src, PeerPtrs peers, uint32_t R,
+                                                      uint32_t my_rank, uint32_t cap, uint32_t row_words, uint32_t lanes) {
+  const uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) / lanes;
+  const uint32_t l = threadIdx.x % lanes;
+  if (idx >= R * cap) return;
+  const uint32_t q = idx / cap, k = idx % cap;
+  uint4* dst = reinterpret_cast<uint4*>(peers.p[q]) + ((size_t)my_rank * cap + k) * row_words;
+  const uint4* from = src + (size_t)idx * row_words;
+  for (uint32_t w = l; w < row_words; w += lanes) dst[w] = from[w];
+}
+
+// flags: every rank owns an array of 16 u32; rank r's word [q] is written by rank q.  *epoch counts barriers.
+__global__ void k_p2p_barrier(PeerPtrs flags, uint32_t* __restrict__ epoch, uint32_t R, uint32_t my_rank,
+                              uint32_t* __restrict__ err) {
+  __shared__ uint32_t e_s;
+  if (threadIdx.x == 0) {
+    e_s = *epoch + 1;
+    *epoch = e_s;
+  }
+  __syncthreads();
+  const uint32_t e = e_s;
+  __threadfence_system();  // everything this GPU stored to its peers before the barrier is visible first
+  if (threadIdx.x < R) {
+    volatile uint32_t* theirs = reinterpret_cast<volatile uint32_t*>(flags.p[threadIdx.x]) + my_rank;
+    *theirs = e;
+    volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(flags.p[my_rank]) + threadIdx.x;
+    uint32_t spins = 0;
+    while ((int32_t)(*mine - e) < 0) {
+      if (++spins > (1u << 27)) {  // a peer is not coming: give up instead of hanging the GPU, and say so
+        if (err) *err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers (host)
 // ------------------------------------------------------------------------------------------------
 void launch_fill_cells(Cell* cells, uint64_t n, cudaStream_t st) { PB_LAUNCH(k_fill_cells, 148 * 8, 256, 0, st, cells, n); }
@@ -608,6 +656,21 @@ void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, u
   PB_LAUNCH(k_evict_hist, 148 * 8, 256, 0, st, t, ev);
   PB_LAUNCH(k_evict_threshold, 1, 32, 0, st, keep, ev);
   PB_LAUNCH(k_evict_sweep, 148 * 8, 256, 0, st, t, ev);
+}
+
+void launch_p2p_exchange(const void* src, const uint64_t* peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
+                         uint32_t row_bytes, cudaStream_t st) {
+  PeerPtrs pp;
+  for (uint32_t i = 0; i < 16; ++i) pp.p[i] = i < R ? peer_ptrs[i] : 0;
+  uint32_t words = row_bytes / 16, lanes = 1;
+  while (lanes < words && lanes < 32) lanes <<= 1;
+  PB_LAUNCH(k_p2p_exchange, cdiv((uint64_t)R * cap * lanes, 256), 256, 0, st, (const uint4*)src, pp, R, my_rank, cap, words, lanes);
+}
+
+void launch_p2p_barrier(const uint64_t* flag_ptrs, uint32_t* epoch, uint32_t R, uint32_t my_rank, uint32_t* err, cudaStream_t st) {
+  PeerPtrs pp;
+  for (uint32_t i = 0; i < 16; ++i) pp.p[i] = i < R ? flag_ptrs[i] : 0;
+  PB_LAUNCH(k_p2p_barrier, 1, 32, 0, st, pp, epoch, R, my_rank, err);
 }
 
 void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st) {

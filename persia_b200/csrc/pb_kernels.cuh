@@ -80,6 +80,9 @@ void launch_pack_signs(const uint64_t* signs, const uint32_t* perm, const uint32
 void launch_frame_rows(const void* src, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
                        uint32_t row_bytes, int pack, void* out, cudaStream_t st);
 void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, uint32_t keep, uint32_t* ev, cudaStream_t st);
+void launch_p2p_exchange(const void* src, const uint64_t* peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
+                         uint32_t row_bytes, cudaStream_t st);
+void launch_p2p_barrier(const uint64_t* flag_ptrs, uint32_t* epoch, uint32_t R, uint32_t my_rank, uint32_t* err, cudaStream_t st);
 uint64_t launch_count();
 enum { FAM_PROBE = 0, FAM_INIT, FAM_GATHER, FAM_NAN, FAM_SORT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
 void profile_enable(bool on);

@@ -70,60 +70,65 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
     grads = (torch.randn((n_sets, S, B, dim), generator=g, device=dev) * 1e-2).half()
 
     static = not args.dist_dynamic
+    mode = "dynamic"
+    gstream = torch.cuda.Stream(device=dev)
     if static:
         wk.enable_static(B)
+        mode = "nccl-framed"
+    if static and not args.dist_nccl:
+        try:
+            wk.enable_p2p(B)
+            mode = "p2p"
+            be.ctx.set_async_grouping(True)  # forward and backward of a step share one capture: the grouping may overlap
+        except Exception as e:  # noqa: BLE001 — no symmetric memory on this box: NCCL framed path
+            print(f"[bench] peer-memory exchange unavailable ({e!r}); using NCCL", file=__import__("sys").stderr)
 
-    def step(k):
-        if static:
+    def eager_step(k):
+        if mode == "p2p":
+            wk.forward_p2p(ids_dev[k], B, training=True)
+            wk.backward_p2p(grads[k])
+        elif mode == "nccl-framed":
             wk.forward_static(ids_dev[k], B, training=True)
             wk.backward_static(grads[k])
         else:
             wk.forward(ids_dev[k], B, training=True)
             wk.backward(grads[k])
 
-    graphs = None
-    graph_error = None
-    if static and args.dist_graph:  # static shapes: kernels + NCCL collectives of a step replay as one CUDA graph per buffer set
-        for i in range(3):
-            step(i % n_sets)
+    graphs, seg_steps = None, None
+    if mode == "p2p" and not args.no_graph:
+        # kernels + peer-memory exchanges + flag barriers of a whole step: one CUDA graph per buffer set, no NCCL inside
+        with torch.cuda.stream(gstream):
+            for i in range(3):
+                eager_step(i % n_sets)
+            gstream.synchronize()
+            dist.barrier()
+            graphs = []
+            for k in range(n_sets):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=gstream, capture_error_mode="thread_local"):
+                    eager_step(k)
+                graphs.append(gph)
         torch.cuda.synchronize()
         dist.barrier()
-        try:
-            graphs = []
-            gstream = torch.cuda.Stream(device=dev)
-            with torch.cuda.stream(gstream):
-                for k in range(n_sets):
-                    gph = torch.cuda.CUDAGraph()
-                    # thread_local: the NCCL watchdog thread keeps polling its events while this thread captures
-                    with torch.cuda.graph(gph, stream=gstream, capture_error_mode="thread_local"):
-                        step(k)
-                    graphs.append(gph)
-            torch.cuda.synchronize()
-        except Exception as e:  # noqa: BLE001 — fall back to eager static steps, say so in the output
-            graphs = None
-            graph_error = repr(e)[:200]
-    seg_steps = None
-    if static and graphs is None and not args.no_graph:
-        gstream = torch.cuda.Stream(device=dev)
+    elif mode == "nccl-framed" and not args.no_graph:
         seg_steps = [wk.make_graphed_step(ids_dev[k], grads[k], B, gstream)[0] for k in range(n_sets)]
         torch.cuda.synchronize()
         dist.barrier()
-    eager_step = step
 
-    def step(k):  # noqa: F811
-        if graphs is not None:
-            graphs[k].replay()
-        elif seg_steps is not None:
-            with torch.cuda.stream(gstream):
+    def step(k):
+        with torch.cuda.stream(gstream):
+            if graphs is not None:
+                graphs[k].replay()
+            elif seg_steps is not None:
                 seg_steps[k]()
-        else:
-            eager_step(k)
+            else:
+                eager_step(k)
 
     def timed(fn, n):
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tstream = gstream if (seg_steps is not None and fn is step) else torch.cuda.current_stream()
+        tstream = gstream if fn is step else torch.cuda.current_stream()
         e0.record(tstream)
         for i in range(n):
             fn(i % n_sets)
@@ -154,7 +159,10 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
 
     def e2e_step(k):
         ids_stage.copy_(ids_pinned[k], non_blocking=True)
-        if static:
+        if mode == "p2p":
+            out = wk.forward_p2p(ids_stage, B, training=True)
+            wk.backward_p2p(grads[k])
+        elif mode == "nccl-framed":
             out = wk.forward_static(ids_stage, B, training=True)
             wk.backward_static(grads[k])
         else:
@@ -167,8 +175,44 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
         e2e_step(i % n_sets)
     ms_e2e = timed(e2e_step, K)
 
+    breakdown = None
+    if mode == "nccl-framed" and os.environ.get("PB_DIST_BREAKDOWN"):
+        # eager framed step with CUDA events between its segments (diagnostic; rank 0's view)
+        names = ["prefix+partition+frame", "a2a signs", "owner forward", "a2a rows", "unframe", "frame grads", "a2a grads", "owner backward"]
+        acc = [0.0] * len(names)
+        S_, R_, cap_ = S, world, wk.cap
+        for it in range(20):
+            k = it % n_sets
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            slot_off = [s * B for s in range(S_ + 1)]
+            ev[0].record()
+            signs = be.add_prefix(ids_dev[k], slot_off, pf, 8)
+            perm, counts = be.partition(signs, R_)
+            send = be.frame_signs(signs, perm, counts, R_, cap_, wk.overflow)
+            ev[1].record()
+            recv = wk._a2a_equal(send)
+            ev[2].record()
+            rows = be.serve_lookup(recv, True)
+            ev[3].record()
+            back = wk._a2a_equal(rows)
+            ev[4].record()
+            out = be.frame_rows(back, perm, counts, R_, cap_, False, be.empty_rows(n_occ))
+            ev[5].record()
+            gs = be.frame_rows(grads[k].reshape(n_occ, dim), perm, counts, R_, cap_, True, be.empty_rows(R_ * cap_, grads.dtype))
+            ev[6].record()
+            gr = wk._a2a_equal(gs)
+            ev[7].record()
+            be.serve_update(gr, 1.0)
+            ev[8].record()
+            torch.cuda.synchronize()
+            if it >= 4:
+                for i in range(len(names)):
+                    acc[i] += ev[i].elapsed_time(ev[i + 1]) * 1e3 / 16
+        breakdown = {n: round(v, 1) for n, v in zip(names, acc)}
     overflowed = wk.check_overflow() if static else False
     assert not overflowed, "framed exchange overflowed its capacity: raise the slack"
+    if mode == "p2p":
+        assert not wk.check_p2p(), "a peer-memory barrier timed out"
     if rank == 0:
         ms_per_step = ms / K
         GB = B * world
@@ -189,12 +233,12 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
                            table_fill_seconds=round(t_fill, 2),
                            l2="inputs larger than L2: %.1f GB table per GPU + %d rotating id/grad sets" % (
                                resident * 4.0 * (dim + state) / 1e9, n_sets),
-                           launch=("fixed-capacity framed exchange (cap %d slots per GPU pair), step = one CUDA graph incl. the NCCL "
-                                   "all-to-alls" % wk.cap) if (static and graphs is not None) else
-                                  ("fixed-capacity framed exchange (cap %d slots per GPU pair); the compute segments between the 3 NCCL "
-                                   "all-to-alls replay as CUDA graphs" % wk.cap) if seg_steps is not None else
-                                  ("fixed-capacity framed exchange, kernel by kernel" if static else
-                                   "kernel by kernel (NCCL all_to_all_single with split sizes; one host sync per step)")),
+                           launch={"p2p": "framed exchange (cap %d slots per GPU pair) stored straight into the peers' buffers over NVLink by "
+                                          "libpersia_b200's own kernels + flag barriers; %s" % (
+                                              getattr(wk, "cap", 0), "whole step = one CUDA graph per rank" if graphs is not None else "kernel by kernel"),
+                                   "nccl-framed": "framed exchange (cap %d) over NCCL all_to_all_single; %s" % (
+                                       getattr(wk, "cap", 0), "compute segments replay as CUDA graphs" if seg_steps is not None else "kernel by kernel"),
+                                   "dynamic": "NCCL all_to_all_single with split sizes; one host sync per step"}[mode]),
             "clocks": clocks,
             "e2e": {"value": GB / (ms_e2e / K * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8 * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / K,
@@ -205,6 +249,7 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
                          "achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
             "cpu_baseline": None,
+            "segments_us": breakdown,
         }
         print(json.dumps(line))
     dist.barrier()

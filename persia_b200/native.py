@@ -75,6 +75,8 @@ SYMBOLS = {
     "pb_permute_rows": (_i32, [_vp, _vp, _u32, _u32, _i32, _vp, _vp]),
     "pb_frame_signs": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "pb_frame_rows": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _i32, _vp, _vp]),
+    "pb_p2p_exchange": (_i32, [_vp, C.POINTER(_u64), _u32, _u32, _u32, _u32, _vp]),
+    "pb_p2p_barrier": (_i32, [C.POINTER(_u64), _vp, _u32, _u32, _vp, _vp]),
     "pb_forward": (_i32, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp]),
     "pb_backward": (_i32, [_vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp]),
     "pb_launch_count": (_u64, []),

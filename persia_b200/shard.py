@@ -281,3 +281,23 @@ def frame_rows(src, perm, counts, R, cap, pack, out):
     row_bytes = src.shape[1] * src.element_size()
     N.check(lib.pb_frame_rows(_ptr(src), _ptr(perm), _ptr(counts), R, cap, row_bytes, int(pack), _ptr(out), _stream(src.device)))
     return out
+
+
+def p2p_exchange(framed, peer_ptrs, my_rank, cap):
+    """Store segment q of `framed` ([R*cap, w] or [R*cap]) into peer q's receive buffer at slot my_rank."""
+    lib = N.load()
+    R = len(peer_ptrs)
+    row_bytes = framed.element_size() * (framed.shape[1] if framed.dim() == 2 else 1)
+    ptrs = (C.c_uint64 * R)(*[int(p) for p in peer_ptrs])
+    if row_bytes % 16:  # 8-byte signs travel as pairs (cap is even)
+        assert row_bytes == 8 and cap % 2 == 0
+        N.check(lib.pb_p2p_exchange(_ptr(framed), ptrs, R, my_rank, cap // 2, 16, _stream(framed.device)))
+    else:
+        N.check(lib.pb_p2p_exchange(_ptr(framed), ptrs, R, my_rank, cap, row_bytes, _stream(framed.device)))
+
+
+def p2p_barrier(flag_ptrs, epoch, my_rank, err):
+    lib = N.load()
+    R = len(flag_ptrs)
+    ptrs = (C.c_uint64 * R)(*[int(p) for p in flag_ptrs])
+    N.check(lib.pb_p2p_barrier(ptrs, _ptr(epoch), R, my_rank, _ptr(err), _stream(epoch.device)))

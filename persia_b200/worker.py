@@ -168,6 +168,80 @@ class ShardedEmbeddingWorker:
         self.be.serve_update(recv, scale)
         return True
 
+    # ---- the framed exchange over NVLink peer memory (no NCCL on the data path) -----------------------------
+    def enable_p2p(self, batch):
+        """Receive buffers and barrier flags in symmetric memory (torch maps every peer's buffer into this process);
+        the exchange is then libpersia_b200's own store-to-peer kernel + flag barrier: stream-ordered, no host
+        involvement, capturable in one CUDA graph together with the compute."""
+        import torch.distributed._symmetric_memory as symm
+
+        if not hasattr(self, "cap"):
+            self.enable_static(batch)
+        R, cap, dev = self.R, self.cap, self.be.device
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self._symm = {}
+
+        def mapped(name, shape, dtype):
+            t = symm.empty(shape, dtype=dtype, device=dev)
+            t.zero_()
+            h = symm.rendezvous(t, grp)
+            self._symm[name] = (t, h, [int(p) for p in h.buffer_ptrs])
+            return t
+
+        if R > 1:
+            self.p2p_recv = mapped("recv", (R * cap,), torch.int64)
+            self.p2p_back = mapped("back", (R * cap, self.dim), torch.float16)
+            self.p2p_grecv = mapped("grecv", (R * cap, self.dim), torch.float16)
+            mapped("flags", (16,), torch.int32)
+        else:
+            self.p2p_recv = torch.zeros(cap, dtype=torch.int64, device=dev)
+            self.p2p_back = torch.zeros((cap, self.dim), dtype=torch.float16, device=dev)
+            self.p2p_grecv = torch.zeros((cap, self.dim), dtype=torch.float16, device=dev)
+            flags = torch.zeros(16, dtype=torch.int32, device=dev)
+            self._symm = {"recv": (self.p2p_recv, None, [self.p2p_recv.data_ptr()]),
+                          "back": (self.p2p_back, None, [self.p2p_back.data_ptr()]),
+                          "grecv": (self.p2p_grecv, None, [self.p2p_grecv.data_ptr()]),
+                          "flags": (flags, None, [flags.data_ptr()])}
+        self.p2p_epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.p2p_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        if R > 1:
+            dist.barrier(group=self.group)
+        return self
+
+    def _p2p_send(self, framed, name):
+        self.be.SH.p2p_exchange(framed, self._symm[name][2], self.rank, self.cap)
+        self.be.SH.p2p_barrier(self._symm["flags"][2], self.p2p_epoch, self.rank, self.p2p_err)
+
+    def forward_p2p(self, ids, batch, training=True):
+        S, B, R, cap = self.S, batch, self.R, self.cap
+        n = S * B
+        slot_off = [s * B for s in range(S + 1)]
+        signs = self.be.add_prefix(ids, slot_off, self.prefixes, self.prefix_bit)
+        perm, counts = self.be.partition(signs, R)
+        send = self.be.frame_signs(signs, perm, counts, R, cap, self.overflow)
+        self._p2p_send(send, "recv")
+        rows = self.be.serve_lookup(self.p2p_recv, training)
+        self._p2p_send(rows, "back")
+        out = self.be.frame_rows(self.p2p_back, perm, counts, R, cap, False, self.be.empty_rows(n))
+        if training:
+            self._pending = (perm, counts, None, n)
+        return out.view(S, B, self.dim)
+
+    def backward_p2p(self, grads, scale=1.0):
+        assert self._pending is not None, "no forward batch is pending"
+        perm, counts, _, n = self._pending
+        self._pending = None
+        g = grads.reshape(n, self.dim)
+        send = self.be.frame_rows(g, perm, counts, self.R, self.cap, True, self.be.empty_rows(self.R * self.cap, g.dtype))
+        self._p2p_send(send, "grecv")
+        self.be.serve_update(self.p2p_grecv, scale)
+        return True
+
+    def check_p2p(self):
+        """True if a barrier gave up waiting for a peer (host sync)."""
+        return bool(int(self.p2p_err))
+
     def make_graphed_step(self, ids, grads, batch, stream, scale=1.0):
         """The framed step on fixed buffers (`ids` int64 [S*B], `grads` f16 [S,B,dim]) with every compute segment
         between two collectives replayed as a CUDA graph: 5 graph launches + 3 NCCL calls per step instead of ~25

@@ -90,18 +90,21 @@ def test_worker_single_rank_matches_oracle():
     assert _check_shard(torch, be, w, pf, 1, 0, dev) > 1000
 
 
-def test_worker_single_rank_static_frames():
+@pytest.mark.parametrize("p2p", [False, True])
+def test_worker_single_rank_static_frames(p2p):
     import torch
 
     dev = torch.device("cuda", 0)
     wk, be, pf = _make_worker(torch, dev)
     wk.enable_static(B)
+    if p2p:
+        wk.enable_p2p(B)
     w, outs, _ = _reference(1)
     for step, (ids, g) in enumerate(_batches(1)):
-        out = wk.forward_static(torch.from_numpy(ids[0].reshape(-1).view(np.int64)).to(dev), B, training=True).cpu().numpy()
+        out = (wk.forward_p2p if p2p else wk.forward_static)(torch.from_numpy(ids[0].reshape(-1).view(np.int64)).to(dev), B, training=True).cpu().numpy()
         for s in range(S):
             np.testing.assert_array_equal(out[s].view(np.uint16), outs[step][s].view(np.uint16))
-        wk.backward_static(torch.from_numpy(g[0]).to(dev))
+        (wk.backward_p2p if p2p else wk.backward_static)(torch.from_numpy(g[0]).to(dev))
     assert not wk.check_overflow()
     assert _check_shard(torch, be, w, pf, 1, 0, dev) > 1000
 
@@ -118,21 +121,27 @@ def _rank_main(rank, R, port, q, static=False):
         w, outs, _ = _reference(R)
         if static:
             wk.enable_static(B)
+        if static == "p2p":
+            wk.enable_p2p(B)
+        fwd = {False: wk.forward, True: wk.forward_static, "p2p": wk.forward_p2p}[static]
+        bwd = {False: wk.backward, True: wk.backward_static, "p2p": wk.backward_p2p}[static]
         for step, (ids, g) in enumerate(_batches(R)):
             d_ids = torch.from_numpy(ids[rank].reshape(-1).view(np.int64)).to(dev)
-            out = (wk.forward_static if static else wk.forward)(d_ids, B, training=True).cpu().numpy()
+            out = fwd(d_ids, B, training=True).cpu().numpy()
             for s in range(S):
                 np.testing.assert_array_equal(out[s].view(np.uint16), outs[step][s][rank * B:(rank + 1) * B].view(np.uint16))
-            (wk.backward_static if static else wk.backward)(torch.from_numpy(g[rank]).to(dev))
+            bwd(torch.from_numpy(g[rank]).to(dev))
         if static:
             assert not wk.check_overflow()
+        if static == "p2p":
+            assert not wk.check_p2p()
         n = _check_shard(torch, be, w, pf, R, rank, dev)
         q.put((rank, n))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("static", [False, True])
+@pytest.mark.parametrize("static", [False, True, "p2p"])
 def test_worker_two_ranks_nccl_matches_oracle(static):
     import torch
     import torch.multiprocessing as mp
