@@ -192,11 +192,12 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
 
 /* Number of kernels the library has launched on behalf of the caller since load (bench bookkeeping). */
 uint64_t pb_launch_count(void);
-/* Bench instrumentation: when enabled every kernel launch is bracketed by CUDA events on its stream.
- * pb_profile_read synchronises the device and returns summed milliseconds and launch counts per kernel
- * family: 0 probe/admit, 1 row init, 2 gather+pool, 3 NaN scan, 4 radix grouping, 5 reduce+update, 6 other. */
+/* Bench instrumentation: launches of the kernel families selected by the bit mask are bracketed by CUDA events on
+ * their stream (0 = off).  pb_profile_read synchronises the device and returns summed milliseconds and launch
+ * counts per family: 0 probe/admit, 1 combine (cut segments), 2 gather+pool, 3 NaN scan, 4 grouping (election,
+ * radix passes, piece heads), 5 reduce+update, 6 other. */
 #define PB_PROFILE_FAMILIES 7
-int pb_profile_enable(int on);
+int pb_profile_enable(int family_mask);
 int pb_profile_read(double* h_ms, uint64_t* h_count, int n_families);
 
 #ifdef __cplusplus

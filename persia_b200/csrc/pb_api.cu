@@ -251,8 +251,8 @@ extern "C" {
 const char* pb_last_error(void) { return g_err.c_str(); }
 int pb_version(void) { return 100; }
 uint64_t pb_launch_count(void) { return launch_count(); }
-int pb_profile_enable(int on) {
-  profile_enable(on != 0);
+int pb_profile_enable(int family_mask) {
+  profile_enable((uint32_t)family_mask);
   return PB_OK;
 }
 int pb_profile_read(double* h_ms, uint64_t* h_count, int n) {

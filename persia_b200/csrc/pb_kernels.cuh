@@ -84,8 +84,8 @@ void launch_p2p_exchange(const void* src, const uint64_t* peer_ptrs, uint32_t R,
                          uint32_t row_bytes, cudaStream_t st);
 void launch_p2p_barrier(const uint64_t* flag_ptrs, uint32_t* epoch, uint32_t R, uint32_t my_rank, uint32_t* err, cudaStream_t st);
 uint64_t launch_count();
-enum { FAM_PROBE = 0, FAM_INIT, FAM_GATHER, FAM_NAN, FAM_SORT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
-void profile_enable(bool on);
+enum { FAM_PROBE = 0, FAM_COMBINE, FAM_GATHER, FAM_NAN, FAM_SORT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
+void profile_enable(uint32_t family_mask);
 void profile_read(double* ms, uint64_t* count, int n_families);
 
 enum { MODE_FIND = 0, MODE_TRAIN = 1, MODE_SET = 2 };

@@ -10,18 +10,23 @@ std::atomic<uint64_t> g_launches{0};
 // Optional per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline leg).
 // Off by default: the hot path then pays one relaxed atomic increment per launch and nothing else.
 struct Profiler {
-  bool on = false;
+  uint32_t mask = 0;  // families being timed
   static constexpr int MAX_EV = 1 << 15;
   std::vector<cudaEvent_t> ev;  // pairs
   std::vector<int> fam;
   int used = 0;
+  int cur = -1;  // family of the launch being bracketed, -1 = not timed
 };
 Profiler g_prof;
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void prof_begin(int family, cudaStream_t st) {
-  if (!g_prof.on) return;
+  if (!((g_prof.mask >> family) & 1u)) {
+    g_prof.cur = -1;
+    return;
+  }
+  g_prof.cur = family;
   if ((int)g_prof.ev.size() < 2 * (g_prof.used + 1)) {
     if (g_prof.used >= Profiler::MAX_EV) return;
     cudaEvent_t a, b;
@@ -35,13 +40,14 @@ void prof_begin(int family, cudaStream_t st) {
   cudaEventRecord(g_prof.ev[2 * g_prof.used], st);
 }
 void prof_end(cudaStream_t st) {
-  if (!g_prof.on || g_prof.used >= Profiler::MAX_EV || (int)g_prof.ev.size() < 2 * (g_prof.used + 1)) return;
+  if (g_prof.cur < 0 || g_prof.used >= Profiler::MAX_EV || (int)g_prof.ev.size() < 2 * (g_prof.used + 1)) return;
   cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st);
   g_prof.used++;
 }
-void profile_enable(bool on) {
-  g_prof.on = on;
+void profile_enable(uint32_t family_mask) {
+  g_prof.mask = family_mask;
   g_prof.used = 0;
+  g_prof.cur = -1;
 }
 // sums elapsed ms and launch counts per family; call after synchronising the stream(s)
 void profile_read(double* ms, uint64_t* count, int n_families) {

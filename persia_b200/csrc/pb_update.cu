@@ -654,7 +654,7 @@ static void reduce_dispatch(int G, const TableDev& t, const OptimDev& op, const 
 #define PB_G(GG)                                                                                                    \
   case GG:                                                                                                          \
     PB_LAUNCH_F(FAM_UPDATE, (k_reduce_update<VEC, GG, F16>), grid, 256, 0, st, t, op, hy, sl, gr, a, heads, counts); \
-    if (n_bound > 1) PB_LAUNCH_F(FAM_UPDATE, (k_combine_update<VEC, GG>), gridc, 256, smemc, st, t, op, hy, gr, a, owners, counts, ng); \
+    if (n_bound > 1) PB_LAUNCH_F(FAM_COMBINE, (k_combine_update<VEC, GG>), gridc, 256, smemc, st, t, op, hy, gr, a, owners, counts, ng); \
     if (a.shared_groups) PB_LAUNCH_F(FAM_UPDATE, (k_update_shared<VEC, GG, F16>), full, 256, 0, st, t, op, hy, sl, gr, a);  \
     break;
   switch (G) {
