@@ -190,6 +190,26 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
 int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, const float* h_scale,
                 int32_t* d_slot_status, void* stream);
 
+/* Raw (embedding_summation: false) slot of one batch — FeatureRawEmbeddingBatch,
+ * embedding_worker_service/mod.rs:498-512, :540-545, :593-623 and the index list of persia-core forward.rs:336-347.
+ * The context serves ONE slot (pb_ctx_set_slots with n_slots == 1; its prefix applies).  d_ids: the slot's flat
+ * ids, sample-major; d_row_off[batch+1] CSR offsets or NULL when every sample holds one id.  Outputs (device):
+ *   d_table_f16   [(U+1), dim] f16, row 0 zeros, row u+1 = embedding of distinct sign u; capacity n_occ+1 rows
+ *   d_index       [batch * sample_fixed_size] i64, 0 = padding, else u+1
+ *   d_non_empty   ascending positions of d_index that hold an id; capacity batch * sample_fixed_size
+ *   d_sample_id_num [batch] = min(ids of the sample, sample_fixed_size)
+ *   d_counts      [2] = {U, number of entries of d_non_empty}
+ * Distinct signs are numbered by first occurrence (the reference: hashbrown iteration order, unpinned).  A raw slot
+ * with hash-stack (mod.rs:503-507, :581-590) is not supported. */
+int pb_forward_raw(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
+                   uint32_t batch, uint32_t sample_fixed_size, int training, void* d_table_f16, int64_t* d_index,
+                   int64_t* d_non_empty, uint32_t* d_sample_id_num, uint32_t* d_counts, void* stream);
+/* Raw arm of update_all_batched_gradients (mod.rs:731-755, :790-798) + update_gradient_mixed: d_grad is the
+ * [U, dim] gradient of the distinct-sign table without its row 0 (persia/ctx.py:970-980 passes f32), NULL =
+ * add_skipped_gradient.  *d_status: 0 applied, 1 skipped, 2 dropped for NaN. */
+int pb_backward_raw(pb_table* t, pb_ctx* c, const void* d_grad, int is_f16, float scale, int32_t* d_status,
+                    void* stream);
+
 /* Number of kernels the library has launched on behalf of the caller since load (bench bookkeeping). */
 uint64_t pb_launch_count(void);
 /* Bench instrumentation: launches of the kernel families selected by the bit mask are bracketed by CUDA events on

@@ -76,6 +76,8 @@ def lib():
         "po_ctx_signs": (None, [vp, u32, vp]),
         "po_worker_forward": (i32, [vp, vp, vp, u32, i32, vp, vp]),
         "po_worker_backward": (i32, [vp, vp, vp, i32, vp, vp, vp]),
+        "po_worker_forward_raw": (i32, [vp, u32, vp, vp, u32, i32, vp, vp, vp, vp, vp]),
+        "po_worker_backward_raw": (i32, [vp, u32, vp, vp, i32, f32, i32, vp]),
         "po_worker_bench": (C.c_double, [vp, vp, vp, u32, u64, u32, vp, u32]),
     }
     for name, (res, args) in sig.items():
@@ -311,6 +313,37 @@ class Worker:
         if rc != 0:
             raise RuntimeError(f"oracle backward failed rc={rc}")
         return status.tolist()
+
+    def forward_raw(self, slot, ids, row_off, B, training=True, keep_ctx=True):
+        """One raw slot.  ids: the slot's flat u64 ids; row_off: u32[B+1].
+        Returns (table f16 [U+1, dim], index i64 [B*fixed], non_empty i64, sample_id_num u32 [B], ctx)."""
+        ids, row_off = _c(ids, np.uint64), _c(row_off, np.uint32)
+        s = self.slots[slot]
+        table = np.zeros((ids.size + 1) * s.dim, np.uint16)
+        index = np.zeros(B * s.sample_fixed_size, np.int64)
+        num = np.zeros(max(B, 1), np.uint32)
+        U = np.zeros(1, np.uint32)
+        ctx = lib().po_ctx_new() if keep_ctx else None
+        rc = lib().po_worker_forward_raw(self.h, slot, _p(ids), _p(row_off), B, int(training), _p(table), _p(index),
+                                         _p(num), _p(U), ctx)
+        if rc != 0:
+            raise RuntimeError(f"oracle raw forward failed rc={rc}")
+        U = int(U[0])
+        non_empty = np.nonzero(index)[0].astype(np.int64)  # persia-core forward.rs:336-347
+        return table[:(U + 1) * s.dim].view(np.float16).reshape(U + 1, s.dim), index, non_empty, num[:B], ctx
+
+    def backward_raw(self, slot, ctx, grad, scale=1.0, skip=False, free_ctx=True):
+        """grad: [U, dim] f32 or f16 (None with skip=True).  Returns the slot status (0 applied, 1 skipped, 2 NaN)."""
+        is_f16 = grad is not None and grad.dtype == np.float16
+        g = _c(grad, np.float16 if is_f16 else np.float32) if grad is not None else None
+        status = np.zeros(1, np.int32)
+        rc = lib().po_worker_backward_raw(self.h, slot, ctx, _p(g), int(is_f16), float(scale), int(skip or g is None),
+                                          _p(status))
+        if free_ctx:
+            lib().po_ctx_free(ctx)
+        if rc != 0:
+            raise RuntimeError(f"oracle raw backward failed rc={rc}")
+        return int(status[0])
 
     def bench(self, ids_batches, row_off, B, grads_f16, n_threads):
         """ids_batches: [n_batches, ids_per_batch] u64.  Returns wall seconds for fwd+bwd of all batches."""

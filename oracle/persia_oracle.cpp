@@ -772,7 +772,7 @@ struct Worker {
     std::vector<FeatureBatch> fbs;
   };
 
-  // mod.rs:448-484 + 874-942 + 486-629 (summation slots; raw slots are N3)
+  // mod.rs:448-484 + 874-942 + 486-629 (summation slots; raw slots: forward_raw below)
   // ids: flat, slot-major; row_off: S*B+1 offsets; out: per slot [B,dim] f16, concatenated.
   int forward(const uint64_t* ids, const uint32_t* row_off, uint32_t B, int training, uint16_t* out, Ctx* keep) {
     size_t S = slots.size(), R = ps.size();
@@ -899,6 +899,108 @@ struct Worker {
         sh_dims[r].push_back(dim);
         sh_grads[r].insert(sh_grads[r].end(), sg.begin() + u * dim, sg.begin() + (u + 1) * dim);
       }
+    }
+    for (size_t r = 0; r < R; ++r)
+      if (ps[r]->update(sh_signs[r].data(), sh_dims[r].data(), sh_signs[r].size(), sh_grads[r].data(),
+                        sh_grads[r].size()) != 0)
+        return -2;
+    return 0;
+  }
+
+  // ---- raw (embedding_summation = false) slot, one slot per request -------------------------------
+  // mod.rs:498-512 (table of distinct signs + zero row 0), :540-545 (row idx+1 = embedding), :593-623
+  // (index / sample_id_num).  Hash-stack on a raw slot (:503-507, :581-590) is not restated.
+  // table: (U+1)*dim f16 (caller sizes it for n_occ+1 rows); index: B*fixed; returns U via *n_distinct.
+  int forward_raw(uint32_t slot, const uint64_t* ids, const uint32_t* row_off, uint32_t B, int training,
+                  uint16_t* table, int64_t* index, uint32_t* sample_id_num, uint32_t* n_distinct, Ctx* keep) {
+    const Slot& sc = slots[slot];
+    if (sc.hs_rounds) return -3;
+    size_t R = ps.size();
+    FeatureBatch fb;
+    if (feature_batch_new(ids, row_off, B, fb) != 0) return -1;
+    add_prefix(fb, sc, prefix_bit);
+    const uint32_t dim = sc.dim, fixed = sc.sample_fixed_size;
+    size_t U = fb.signs.size();
+    std::vector<float> res((U + 1) * dim, 0.0f);
+    std::vector<std::vector<uint32_t>> sharded(R);
+    for (size_t u = 0; u < U; ++u) sharded[farmhash64_u64(fb.signs[u]) % R].push_back((uint32_t)u);
+    std::vector<uint64_t> sg;
+    std::vector<uint32_t> dm;
+    std::vector<float> rows;
+    for (size_t r = 0; r < R; ++r) {
+      size_t n = sharded[r].size();
+      sg.resize(n);
+      dm.assign(n, dim);
+      for (size_t i = 0; i < n; ++i) sg[i] = fb.signs[sharded[r][i]];
+      rows.resize(n * dim);
+      if (ps[r]->lookup(sg.data(), dm.data(), n, training, rows.data()) != 0) return -2;
+      for (size_t i = 0; i < n; ++i)  // sign2idx[sign] + 1 (mod.rs:540-545); sign2idx = index_batch position
+        std::memcpy(res.data() + ((size_t)sharded[r][i] + 1) * dim, rows.data() + i * dim, dim * 4);
+    }
+    for (size_t i = 0; i < (U + 1) * dim; ++i) table[i] = f32_to_f16(res[i]);
+    std::fill(index, index + (size_t)B * fixed, (int64_t)0);
+    std::fill(sample_id_num, sample_id_num + B, 0u);
+    for (size_t u = 0; u < U; ++u)  // mod.rs:601-616
+      for (uint32_t j = fb.seg_off[u]; j < fb.seg_off[u + 1]; ++j) {
+        uint32_t b = fb.occ_sample[j], col = fb.occ_col[j];
+        if (sample_id_num[b] < fixed && col < fixed) {
+          index[(size_t)b * fixed + col] = (int64_t)u + 1;
+          sample_id_num[b] += 1;
+        }
+      }
+    *n_distinct = (uint32_t)U;
+    if (keep) {
+      keep->fbs.clear();
+      keep->fbs.push_back(std::move(fb));
+    }
+    return 0;
+  }
+
+  // raw arm of update_all_batched_gradients (mod.rs:731-755, :790-798): grads [U, dim]
+  int backward_raw(uint32_t slot, const Ctx& ctx, const void* grads, int is_f16, float scale, int skip, int* status) {
+    size_t R = ps.size();
+    const FeatureBatch& fb = ctx.fbs[0];
+    const uint32_t dim = slots[slot].dim;
+    size_t U = fb.signs.size(), n = U * dim;
+    if (status) *status = 0;
+    if (skip) {
+      if (status) *status = 1;
+      return 0;
+    }
+    std::vector<float> g32(n);
+    bool nan = false;
+    if (is_f16) {
+      const uint16_t* h = (const uint16_t*)grads;
+      for (size_t i = 0; i < n; ++i)
+        if ((h[i] & 0x7c00) == 0x7c00 && (h[i] & 0x03ff)) { nan = true; break; }
+      if (!nan)
+        for (size_t i = 0; i < n; ++i) {
+          float v = f16_to_f32(h[i]);
+          if (v == INFINITY) v = 65504.0f; else if (v == -INFINITY) v = -65504.0f;
+          g32[i] = v;
+        }
+    } else {
+      const float* f = (const float*)grads;
+      for (size_t i = 0; i < n; ++i) if (std::isnan(f[i])) { nan = true; break; }
+      if (!nan) std::memcpy(g32.data(), f, n * 4);
+    }
+    if (nan) {
+      if (status) *status = 2;
+      return 0;
+    }
+    if (std::fabs(scale - 1.0f) > 1.1920929e-07f) {
+      float r = 1.0f / scale;
+      for (size_t i = 0; i < n; ++i) g32[i] *= r;
+    }
+    // sqrt_scaling only scales a raw slot's gradient when hash-stack is on (mod.rs:769-776)
+    std::vector<std::vector<uint64_t>> sh_signs(R);
+    std::vector<std::vector<uint32_t>> sh_dims(R);
+    std::vector<std::vector<float>> sh_grads(R);
+    for (size_t u = 0; u < U; ++u) {  // hashed2index_batch_idx[sign] == u (mod.rs:790-798), then :813-821
+      size_t r = farmhash64_u64(fb.signs[u]) % R;
+      sh_signs[r].push_back(fb.signs[u]);
+      sh_dims[r].push_back(dim);
+      sh_grads[r].insert(sh_grads[r].end(), g32.begin() + u * dim, g32.begin() + (u + 1) * dim);
     }
     for (size_t r = 0; r < R; ++r)
       if (ps[r]->update(sh_signs[r].data(), sh_dims[r].data(), sh_signs[r].size(), sh_grads[r].data(),
@@ -1084,6 +1186,15 @@ int po_worker_forward(void* w, const uint64_t* ids, const uint32_t* row_off, uin
 int po_worker_backward(void* w, void* ctx, const void* grads, int is_f16, const float* scale, const int* skip,
                        int* slot_status) {
   return ((Worker*)w)->backward(*(Worker::Ctx*)ctx, grads, is_f16, scale, skip, slot_status);
+}
+int po_worker_forward_raw(void* w, uint32_t slot, const uint64_t* ids, const uint32_t* row_off, uint32_t B, int training,
+                          uint16_t* table, int64_t* index, uint32_t* sample_id_num, uint32_t* n_distinct, void* ctx) {
+  return ((Worker*)w)->forward_raw(slot, ids, row_off, B, training, table, index, sample_id_num, n_distinct,
+                                   (Worker::Ctx*)ctx);
+}
+int po_worker_backward_raw(void* w, uint32_t slot, void* ctx, const void* grads, int is_f16, float scale, int skip,
+                           int* status) {
+  return ((Worker*)w)->backward_raw(slot, *(Worker::Ctx*)ctx, grads, is_f16, scale, skip, status);
 }
 
 // ---- timed CPU baseline ----

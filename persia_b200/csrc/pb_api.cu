@@ -118,6 +118,11 @@ struct pb_ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool shared_groups = false;  // two slots carry the same non-zero prefix (one feature group)
+  // raw slot (pb_forward_raw / pb_backward_raw): allocated on first use
+  RawWork raw{};
+  bool raw_ready = false, raw_pending = false;
+  float* raw_stage = nullptr;
+  size_t raw_stage_floats = 0;
 };
 
 namespace {
@@ -557,7 +562,8 @@ int pb_ctx_destroy(pb_ctx* c) {
   cudaDeviceSynchronize();
   void* ptrs[] = {c->occ_cell, c->occ_row, c->occ_outrow, c->row_off, c->keys_a, c->vals_a,
                   c->keys_b,   c->vals_b,   c->hist,       c->nan_tick, c->vw_stage, c->dev_tick, c->partials,
-                  c->heads,    c->owners,   c->seg_counts};
+                  c->heads,    c->owners,   c->seg_counts, c->raw.set,  c->raw.occ_set, c->raw.flag, c->raw.rank,
+                  c->raw.tiles, c->raw.distinct_cell, c->raw.counts, c->raw_stage};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->side) cudaStreamDestroy(c->side);
@@ -791,6 +797,135 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
   SegArgs a = seg_args(t, c, vw);
   launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, c->heads, c->owners, c->seg_counts, st);
   c->pending = false;
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+// ---- raw slots ------------------------------------------------------------------------------------
+static int ensure_raw(pb_ctx* c) {
+  if (c->raw_ready) return PB_OK;
+  RawWork& w = c->raw;
+  size_t n = c->max_occ;
+  size_t m = n > c->max_out ? n : c->max_out;
+  uint32_t cells = next_pow2(2 * (uint64_t)n < 1024 ? 1024 : 2 * (uint64_t)n);
+  w.set_mask = cells - 1;
+  PB_CUDA(cudaMalloc(&w.set, sizeof(RawCell) * ((size_t)cells + 1)));
+  PB_CUDA(cudaMalloc(&w.occ_set, 4 * n));
+  PB_CUDA(cudaMalloc(&w.flag, 4 * m));
+  PB_CUDA(cudaMalloc(&w.rank, 4 * m));
+  PB_CUDA(cudaMalloc(&w.tiles, 4 * (size_t)raw_scan_tiles((uint32_t)m)));
+  PB_CUDA(cudaMalloc(&w.distinct_cell, 4 * n));
+  PB_CUDA(cudaMalloc(&w.counts, 8));
+  PB_CUDA(cudaMemset(w.counts, 0, 8));
+  c->raw_ready = true;
+  return PB_OK;
+}
+
+int pb_forward_raw(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
+                   uint32_t batch, uint32_t sample_fixed_size, int training, void* d_table_f16, int64_t* d_index,
+                   int64_t* d_non_empty, uint32_t* d_sample_id_num, uint32_t* d_counts, void* stream) {
+  if (!t || !c || !d_table_f16 || !d_index || !d_non_empty || !d_sample_id_num || !d_counts || (n_occ && !d_ids))
+    return fail(PB_ERR_INVALID, "null argument");
+  if (!c->has_slots || c->slots.n_slots != 1) return fail(PB_ERR_STATE, "a raw context serves exactly one slot (pb_ctx_set_slots)");
+  if (t->device != c->device) return fail(PB_ERR_INVALID, "table and context live on different devices");
+  if (batch > 65535) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
+  if (sample_fixed_size == 0) return fail(PB_ERR_INVALID, "sample_fixed_size must be positive");
+  if (n_occ > c->max_occ || batch > c->max_out || (uint64_t)batch * sample_fixed_size > (1ull << 31))
+    return fail(PB_ERR_CAPACITY, "batch exceeds the context's capacity");
+  if (!d_row_off && n_occ != batch) return fail(PB_ERR_INVALID, "row offsets are required unless every sample has one id");
+  int rc;
+  if (training) {
+    if ((rc = ready_for_training(t))) return rc;
+  } else if (!t->has_op) {
+    return fail(PB_ERR_STATE, "optimizer not registered (OptimizerNotFoundError)");
+  }
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_alloc(t))) return rc;
+  if ((rc = ensure_raw(c))) return rc;
+  const uint32_t occ_off[2] = {0, n_occ};
+  SlotsDev sl;
+  if ((rc = make_slots(c->slots, occ_off, sl))) return rc;
+  sl.uniform = 0;
+  if (training) {
+    if ((rc = maybe_evict(t, st))) return rc;
+    launch_begin_batch(t->d, c->dev_tick, st);
+    launch_probe(MODE_TRAIN, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
+  } else {
+    launch_probe(MODE_FIND, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
+  }
+  const uint32_t* occ_sample = nullptr;
+  if (d_row_off) {
+    PB_CUDA(cudaMemcpyAsync(c->row_off, d_row_off, 4 * ((size_t)batch + 1), cudaMemcpyDeviceToDevice, st));
+    launch_expand_rows(c->row_off, batch, c->occ_outrow, st);
+    occ_sample = c->occ_outrow;
+  }
+  launch_raw_forward(t->d, sl, d_ids, n_occ, d_row_off ? c->row_off : nullptr, occ_sample, batch, sample_fixed_size,
+                     c->occ_cell, c->raw, d_table_f16, (long long*)d_index, (long long*)d_non_empty, d_sample_id_num, st);
+  PB_CUDA(cudaMemcpyAsync(d_counts, c->raw.counts, 8, cudaMemcpyDeviceToDevice, st));
+  if (training) {
+    c->n_occ = n_occ;
+    c->batch = batch;
+    c->raw_pending = true;
+  }
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_backward_raw(pb_table* t, pb_ctx* c, const void* d_grad, int is_f16, float scale, int32_t* d_status,
+                    void* stream) {
+  if (!t || !c) return fail(PB_ERR_INVALID, "null argument");
+  if (!c->raw_pending) return fail(PB_ERR_STATE, "no raw forward batch is pending in this context (backward_ref_id not found)");
+  int rc = ready_for_training(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  c->raw_pending = false;
+  GradsDev gr;
+  std::memset(&gr, 0, sizeof(gr));
+  gr.ptr[0] = d_grad;
+  if (!d_grad) {  // add_skipped_gradient
+    if (d_status) launch_slot_status(gr, 1, c->dev_tick, c->nan_tick, d_status, st);
+    return PB_OK;
+  }
+  const bool do_scale = std::fabs(scale - 1.0f) > 1.1920929e-07f;
+  const float inv = 1.0f / scale;
+  if (do_scale && !std::isfinite(inv)) return fail(PB_ERR_INVALID, "scale on gradient must be finite");
+  float b1p = 0.0f, b2p = 0.0f;
+  if (t->op.kind == PB_OPT_ADAM) {  // one power step per request and feature group (optim.rs:155-197)
+    const uint64_t pfx = c->slots.prefix[0];
+    std::pair<float, float>* acc = nullptr;
+    for (auto& a : t->adam_pow)
+      if (a.first == pfx) acc = &a.second;
+    if (!acc) {
+      t->adam_pow.push_back({pfx, {t->op.b1, t->op.b2}});
+      acc = &t->adam_pow.back().second;
+    }
+    acc->first *= t->op.b1;
+    acc->second *= t->op.b2;
+    b1p = acc->first;
+    b2p = acc->second;
+  }
+  const uint32_t dim = t->d.dim;
+  launch_raw_nan(d_grad, is_f16 != 0, c->raw.counts, dim, c->dev_tick, c->nan_tick, st);
+  if (d_status) launch_slot_status(gr, 1, c->dev_tick, c->nan_tick, d_status, st);
+  const float* g32 = (const float*)d_grad;
+  if (is_f16 || do_scale) {
+    size_t need = (size_t)c->n_occ * dim;
+    if (need > c->raw_stage_floats) {
+      PB_CUDA(cudaStreamSynchronize(st));
+      if (c->raw_stage) cudaFree(c->raw_stage);
+      c->raw_stage = nullptr;
+      c->raw_stage_floats = 0;
+      size_t cap = (size_t)c->max_occ * dim;
+      PB_CUDA(cudaMalloc(&c->raw_stage, sizeof(float) * cap));
+      c->raw_stage_floats = cap;
+    }
+    launch_raw_stage(d_grad, is_f16 != 0, c->raw.counts, dim, inv, do_scale, c->raw_stage, st);
+    g32 = c->raw_stage;
+  }
+  launch_update_direct(t->d, t->op, t->hy, c->raw.distinct_cell, g32, c->n_occ, b1p, b2p, st, c->raw.counts,
+                       c->dev_tick, c->nan_tick);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
 }

@@ -41,6 +41,23 @@ struct SegArgs {
 };
 constexpr uint32_t PB_PIECE = 32;
 
+// raw slots (pb_raw.cu): per-batch scratch set of distinct signs and its workspace
+struct RawCell {
+  uint64_t key;
+  uint32_t first;  // first occurrence of the sign in the flat id array
+  uint32_t rank;   // number of the sign among the batch's distinct signs (first-occurrence order)
+};
+struct RawWork {
+  RawCell* set;      // set_mask + 2 cells
+  uint32_t set_mask;
+  uint32_t* occ_set;        // set cell of every occurrence
+  uint32_t* flag;           // scan input / second scan output
+  uint32_t* rank;           // scan output
+  uint32_t* tiles;          // scan spine
+  uint32_t* distinct_cell;  // index cell of every distinct sign (forward -> backward)
+  uint32_t* counts;         // [0] distinct signs, [1] ids placed in `index`
+};
+
 void launch_fill_cells(Cell* cells, uint64_t n, cudaStream_t st);
 void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, cudaStream_t st);
 void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const OptimDev& op, const SlotsDev& sl,
@@ -57,8 +74,22 @@ void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_sl
 void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
                           const GradsDev& gr, bool f16, const SegArgs& a, uint2* heads, uint2* owners,
                           uint32_t* counts, cudaStream_t st);
+// n_ptr (optional): the live count on the device (<= n); tick/nan_tick (optional): skip everything when equal
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
-                          const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st);
+                          const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st,
+                          const uint32_t* n_ptr = nullptr, const uint32_t* tick = nullptr,
+                          const uint32_t* nan_tick = nullptr);
+uint32_t raw_scan_tiles(uint32_t n);
+void launch_raw_forward(const TableDev& t, const SlotsDev& sl, const uint64_t* ids, uint32_t n,
+                        const uint32_t* row_off, const uint32_t* occ_sample, uint32_t batch, uint32_t fixed,
+                        const uint32_t* occ_cell, const RawWork& w, void* table_f16, long long* index,
+                        long long* non_empty, uint32_t* sample_id_num, cudaStream_t st);
+void launch_raw_nan(const void* grad, bool f16, const uint32_t* n_distinct, uint32_t dim, const uint32_t* tick,
+                    uint32_t* nan_tick, cudaStream_t st);
+void launch_raw_stage(const void* grad, bool f16, const uint32_t* n_distinct, uint32_t dim, float inv_scale,
+                      bool do_scale, float* out, cudaStream_t st);
+void launch_slot_status(const GradsDev& gr, uint32_t n_slots, const uint32_t* tick, const uint32_t* nan_tick,
+                        int32_t* status, cudaStream_t st);
 uint32_t radix_tile(uint32_t n);
 uint32_t radix_hist_words();
 uint32_t radix_hist_zero_words(uint32_t n);

@@ -595,10 +595,14 @@ template <int VEC, int G>
 __global__ void __launch_bounds__(256) k_update_direct(TableDev t, OptimDev op, HyperDev hy,
                                                        const uint32_t* __restrict__ occ_cell,
                                                        const float* __restrict__ grads, uint32_t n, float b1p,
-                                                       float b2p, float* __restrict__ vw_stage) {
+                                                       float b2p, const uint32_t* __restrict__ n_ptr,
+                                                       const uint32_t* __restrict__ tick_ptr,
+                                                       const uint32_t* __restrict__ nan_tick) {
   uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   uint32_t lane = threadIdx.x % G;
+  if (n_ptr) n = *n_ptr;
   if (gid >= n) return;
+  if (nan_tick && nan_tick[0] == *tick_ptr) return;  // NaN rule: the whole gradient is dropped
   uint32_t h = occ_cell[gid];
   uint32_t row = (h < t.n_cells + N_SPECIAL) ? t.cells[h].row : ROW_NONE;
   if (row >= t.capacity) {
@@ -637,6 +641,11 @@ void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_sl
   if (f16) PB_LAUNCH_F(FAM_NAN, k_nan_scan<true>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick);
   else PB_LAUNCH_F(FAM_NAN, k_nan_scan<false>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick);
   if (status) PB_LAUNCH(k_slot_status, 1, PB_MAX_SLOTS, 0, st, gr, n_slots, tick, nan_tick, status);
+}
+
+void launch_slot_status(const GradsDev& gr, uint32_t n_slots, const uint32_t* tick, const uint32_t* nan_tick,
+                        int32_t* status, cudaStream_t st) {
+  PB_LAUNCH(k_slot_status, 1, PB_MAX_SLOTS, 0, st, gr, n_slots, tick, nan_tick, status);
 }
 
 template <int VEC, bool F16>
@@ -683,14 +692,16 @@ void launch_find_heads(const SegArgs& a, uint2* heads, uint2* owners, uint32_t* 
 }
 
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
-                          const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st) {
+                          const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st,
+                          const uint32_t* n_ptr, const uint32_t* tick, const uint32_t* nan_tick) {
   if (!n) return;
   int vec, G;
   vec_group(t.dim, vec, G);
   uint32_t grid = cdiv((uint64_t)n * G, 256);
 #define PB_U(V, GG)                                                                                          \
   if (vec == V && G == GG)                                                                                   \
-    PB_LAUNCH_F(FAM_UPDATE, (k_update_direct<V, GG>), grid, 256, 0, st, t, op, hy, occ_cell, grads, n, b1p, b2p, nullptr);
+    PB_LAUNCH_F(FAM_UPDATE, (k_update_direct<V, GG>), grid, 256, 0, st, t, op, hy, occ_cell, grads, n, b1p, b2p, n_ptr, \
+                tick, nan_tick);
   PB_U(4, 1) PB_U(4, 2) PB_U(4, 4) PB_U(4, 8) PB_U(4, 16) PB_U(4, 32)
   PB_U(1, 1) PB_U(1, 2) PB_U(1, 4) PB_U(1, 8) PB_U(1, 16) PB_U(1, 32)
 #undef PB_U

@@ -7,7 +7,7 @@ process's GPU, `get_embedding_from_data` / `Forward.get_batch` run pb_forward, `
 the raw device pointers `GradientBatch.add_gradient` receives.  `install()` registers it (and its submodules)
 in `sys.modules` as `persia_core`, after which the reference's own `persia` package runs unchanged on top.
 
-Scope of round 1: summation slots (raw slots: N3), one process / one GPU (`replica_size == 1`; the sharded
+Scope of round 1: summation and raw slots (no hash-stack on raw slots), one process / one GPU (`replica_size == 1`; the sharded
 multi-GPU worker is persia_b200.worker), synchronous engines (the pipelining / staleness of
 forward.rs:470-780 is N1), `to_bytes()` is a private encoding (the speedy wire format is N4), `dump`/`load`
 of embedding checkpoints are N2 and raise.
@@ -215,20 +215,30 @@ class Tensor:
 
 
 class Embedding:  # forward.rs:57-99
-    def __init__(self, tensor):
-        self._inner = tensor
+    def __init__(self, tensor, raw=None):
+        self._inner = tensor   # sum: Tensor; raw: (Tensor table, Tensor index, Tensor non_empty_index, [sample_id_num])
+        self._raw = raw is not None
+        if self._raw:
+            self._inner = raw
 
     def is_raw_embedding(self):
-        return False
+        return self._raw
 
     def get_sum_embedding(self):
+        if self._raw:
+            raise RuntimeError("AttrError: raw embedding can not convert to sum embedding")
         if self._inner is None:
             raise RuntimeError("embedding already taken")  # Option::take().unwrap() panics in the reference
         t, self._inner = self._inner, None
         return t
 
     def get_raw_embedding(self):
-        raise RuntimeError("AttrError: sum embedding can not convert to raw embedding")
+        if not self._raw:
+            raise RuntimeError("AttrError: sum embedding can not convert to raw embedding")
+        if self._inner is None:
+            raise RuntimeError("embedding already taken")
+        t, self._inner = self._inner, None
+        return t
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -309,10 +319,10 @@ class _Pending:
     """What the EW keeps under backward_ref_id (mod.rs:1087-1098): per dim group, the device context."""
 
     def __init__(self):
-        self.parts = []  # (group, ctx, [slot names in order])
+        self.parts = []  # (group, ctx, [slot names in order], is_raw)
 
     def release(self):
-        for g, ctx, _ in self.parts:
+        for g, ctx, _, _ in self.parts:
             g["ctx"].setdefault(ctx._pool_key, []).append(ctx)
         self.parts = []
 
@@ -398,13 +408,40 @@ def _forward(batch, device_id, training):
     for name, _ in feats:
         if name not in _S.by_name:
             raise RuntimeError(f"slot: {name} not found")  # get_slot_by_feature_name expect()
-        if not _S.by_name[name].embedding_summation:
-            raise RuntimeError("raw (embedding_summation: false) slots are not built yet (SURVEY.md N3)")
+        sc = _S.by_name[name]
+        if not sc.embedding_summation and sc.hash_stack_rounds > 0:
+            raise RuntimeError(f"slot {name}: a raw (embedding_summation: false) slot with hash_stack is not supported")
     feats = [(n, _hashstack(x, _S.by_name[n]) if _S.by_name[n].hash_stack_rounds > 0 else x) for n, x in feats]
     pending = _Pending()
     by_slot = {}
-    for dim in sorted({_S.by_name[n].dim for n, _ in feats}):
-        part = [(n, x) for n, x in feats if _S.by_name[n].dim == dim]
+    raw_out = {}
+    for n, x in feats:  # raw slots: one request each (FeatureRawEmbeddingBatch, mod.rs:586-623)
+        sc = _S.by_name[n]
+        if sc.embedding_summation:
+            continue
+        g = _S.group(sc.dim)
+        key = ("raw", n)
+        pool = g["ctx"].setdefault(key, [])
+        ids, row_off, _ = _flatten([(n, x)], B)
+        if pool and pool[-1]._cap >= max(len(ids), B):
+            ctx = pool.pop()
+        else:
+            cap = max(2 * len(ids), 2 * B, 1024)
+            ctx = SH.BatchContext(cap, cap, [sc.index_prefix], None, _S.prefix_bit, dev)
+            ctx._pool_key, ctx._cap = key, cap
+        d_ids = torch.from_numpy(ids.view(np.int64)).to(dev, non_blocking=True)
+        d_off = torch.from_numpy(row_off.view(np.int32)).to(dev, non_blocking=True) if row_off is not None else None
+        table, index, non_empty, num, counts = ctx.forward_raw(g["shard"], d_ids, B, sc.sample_fixed_size, row_off=d_off,
+                                                               training=training)
+        U, ne = counts.tolist()  # the distinct-sign table is sized on the host, like the reference's CPU tensors
+        raw_out[n] = (Tensor(table[:U + 1], n), Tensor(index, f"{n}_index"),
+                      Tensor(non_empty[:ne], f"{n}_non_empty_index"), num.tolist())
+        if training:
+            pending.parts.append((g, ctx, [n], True))
+        else:
+            pool.append(ctx)
+    for dim in sorted({_S.by_name[n].dim for n, _ in feats if _S.by_name[n].embedding_summation}):
+        part = [(n, x) for n, x in feats if _S.by_name[n].dim == dim and _S.by_name[n].embedding_summation]
         names = [n for n, _ in part]
         g = _S.group(dim)
         key = tuple(names)
@@ -424,10 +461,10 @@ def _forward(batch, device_id, training):
         for i, n in enumerate(names):
             by_slot[n] = out[i]
         if training:
-            pending.parts.append((g, ctx, names))
+            pending.parts.append((g, ctx, names, False))
         else:
             pool.append(ctx)
-    emb = [Embedding(Tensor(by_slot[n], n)) for n, _ in feats]
+    emb = [Embedding(None, raw=raw_out[n]) if n in raw_out else Embedding(Tensor(by_slot[n], n)) for n, _ in feats]
     to_dev = lambda items: [Tensor(torch.from_numpy(a).to(dev), n) for n, a in items]  # noqa: E731
     return PersiaTrainingBatch(to_dev(batch.non_id_type_features), emb, to_dev(batch.labels), batch.meta_data,
                                pending if training else None)
@@ -490,7 +527,15 @@ class Backward:  # backward.rs:357-405
         if p is None:
             raise RuntimeError("cannot find gradient batch")
         try:
-            for g, ctx, names in p.parts:
+            for g, ctx, names, is_raw in p.parts:
+                if is_raw:  # [U, dim] gradient of the distinct-sign table (persia/ctx.py:970-980)
+                    item = gradients._grads.get(names[0])
+                    if item is None:
+                        ctx.backward_raw(g["shard"], None)
+                    else:
+                        ptr, shape, is16, sc = item
+                        ctx.backward_raw(g["shard"], ptr, scale=sc, is_f16=is16)
+                    continue
                 ptrs, scales, f16 = [], [], None
                 for n in names:
                     item = gradients._grads.get(n)

@@ -191,6 +191,46 @@ class BatchContext:
         sc = (C.c_float * self.n_slots)(*[float(x) for x in scales]) if scales is not None else None
         N.check(self.lib.pb_backward(shard.h, self.h, arr, int(bool(is_f16)), sc, None, _stream(self.device)))
 
+    def forward_raw(self, shard, ids, batch, sample_fixed_size, row_off=None, training=True):
+        """Raw (embedding_summation: false) slot; the context must have been built with ONE prefix.
+        Returns (table f16 [n_occ+1, dim] of which rows [0, U] are valid, index i64 [batch*fixed],
+        non_empty i64 [batch*fixed] of which counts[1] entries are valid, sample_id_num i32 [batch],
+        counts i32 [2] = (U, non-empty entries)), all on the device (mod.rs:586-623, forward.rs:336-347)."""
+        assert self.n_slots == 1, "a raw context serves one slot"
+        ids = _as_i64_bits(ids)
+        n, fixed = ids.numel(), int(sample_fixed_size)
+        table = torch.empty((n + 1, shard.dim), dtype=torch.float16, device=self.device)
+        index = torch.empty(batch * fixed, dtype=torch.int64, device=self.device)
+        non_empty = torch.empty(max(batch * fixed, 1), dtype=torch.int64, device=self.device)
+        sample_id_num = torch.empty(max(batch, 1), dtype=torch.int32, device=self.device)
+        counts = torch.empty(2, dtype=torch.int32, device=self.device)
+        if row_off is not None:
+            assert row_off.dtype == torch.int32 and row_off.is_contiguous() and row_off.numel() == batch + 1
+        N.check(self.lib.pb_forward_raw(shard.h, self.h, _ptr(ids), n, _ptr(row_off), int(batch), fixed, int(training),
+                                        _ptr(table), _ptr(index), _ptr(non_empty), _ptr(sample_id_num), _ptr(counts),
+                                        _stream(self.device)))
+        return table, index, non_empty, sample_id_num[:batch], counts
+
+    def backward_raw(self, shard, grad, scale=1.0, want_status=False, is_f16=None):
+        """grad: device tensor [U, dim] (f32 as persia/ctx.py:970-980 builds it, or f16), a raw device pointer
+        (then pass is_f16), or None (add_skipped_gradient)."""
+        ptr = None
+        if grad is not None and not isinstance(grad, int):
+            assert grad.is_contiguous() and grad.dtype in (torch.float16, torch.float32)
+            is_f16 = grad.dtype == torch.float16
+            ptr = grad.data_ptr() if grad.numel() else self._raw_dummy().data_ptr()
+        elif grad is not None:
+            ptr = grad
+        status = torch.empty(1, dtype=torch.int32, device=self.device) if want_status else None
+        N.check(self.lib.pb_backward_raw(shard.h, self.h, ptr, int(bool(is_f16)), float(scale), _ptr(status),
+                                         _stream(self.device)))
+        return status
+
+    def _raw_dummy(self):
+        if not hasattr(self, "_dummy"):
+            self._dummy = torch.zeros(4, dtype=torch.float32, device=self.device)
+        return self._dummy
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.pb_ctx_destroy(self.h)

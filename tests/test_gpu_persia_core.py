@@ -164,3 +164,100 @@ def test_surface_forward_backward_matches_oracle(oracle):
         assert ctx.get_embedding_size() == [0, 0]
     finally:
         impl.reset()
+
+
+RAW_CFG = {
+    "feature_index_prefix_bit": 8,
+    "slots_config": {
+        "seq": {"dim": 16, "embedding_summation": False, "sample_fixed_size": 4},
+        "user": {"dim": 16},
+    },
+}
+
+
+def test_surface_raw_slot_matches_oracle(oracle):
+    """A raw (embedding_summation: false) slot through the surface, consumed the way persia/ctx.py:121-165 builds
+    the [B, fixed, dim+1] tensor and :966-981 builds the [U, dim] f32 gradient."""
+    import torch
+    import torch.utils.dlpack as dl
+
+    from persia_b200 import persia_core as impl
+    from persia_b200.persia_core import parse_embedding_config
+
+    impl.reset()
+    pc = impl.install()
+    try:
+        pc.set_embedding_config(RAW_CFG)
+        ctx = pc.PersiaCommonContext(10, 0, 1, 0)
+        opt = pc.optim.OptimizerBase()
+        opt.init_sgd(0.05, 0.0)
+        opt.apply()
+        ctx.configure_embedding_parameter_servers(-0.01, 0.01, 1.0, True, 10.0)
+        bwd = pc.backward.Backward(8)
+        _, slots = parse_embedding_config(RAW_CFG)
+        by = {s.name: s for s in slots}
+        # the oracle serves the two slots as two one-slot requests against the same parameter server
+        w = oracle.Worker([oracle.SlotCfg(16, summation=False, sample_fixed_size=4, prefix=by["seq"].index_prefix),
+                           oracle.SlotCfg(16, prefix=by["user"].index_prefix)], n_ps=1)
+        w.configure(-0.01, 0.01, 1.0, True, 10.0)
+        w.set_optimizer(oracle.Optim(oracle.SGD, lr=0.05, wd=0.0))
+        rng = np.random.default_rng(21)
+        B, fixed, dim = 64, 4, 16
+        seen = set()
+        for step in range(3):
+            seq = [rng.integers(0, 50, size=rng.integers(0, 7), dtype=np.uint64) for _ in range(B)]
+            b = pc.data.PersiaBatch()
+            b.add_id_type_feature(seq, "seq")
+            b.add_label(np.zeros((B, 1), np.float32), np.dtype(np.float32), "y")
+            b.converted_id_type_features2embedding_tensor(True)
+            tb = ctx.get_embedding_from_data(b, 0)
+            (e,) = tb.consume_all_id_type_feature_embedding_tensors()
+            assert e.is_raw_embedding()
+            with pytest.raises(RuntimeError):
+                e.get_sum_embedding()
+            raw, index, non_empty, sample_id_num = e.get_raw_embedding()
+            distinct = dl.from_dlpack(raw.dlpack)
+            index_t = dl.from_dlpack(index.dlpack)
+            non_empty_t = dl.from_dlpack(non_empty.dlpack)
+            ids = np.concatenate(seq) if sum(map(len, seq)) else np.zeros(0, np.uint64)
+            off = np.zeros(B + 1, np.uint32)
+            off[1:] = np.cumsum([len(r) for r in seq])
+            wt, wi, wne, wnum, octx = w.forward_raw(0, ids, off, B, training=True)
+            assert distinct.cpu().numpy().tobytes() == wt.tobytes()
+            np.testing.assert_array_equal(index_t.cpu().numpy(), wi)
+            np.testing.assert_array_equal(non_empty_t.cpu().numpy(), wne)
+            assert sample_id_num == wnum.tolist()
+            seen.update(oracle.add_prefix(ids, 8, by["seq"].index_prefix).tolist())
+            # persia/ctx.py:131-165
+            assert index_t.max() < distinct.shape[0]
+            sel = distinct.index_select(0, index_t.view(-1))
+            sel.requires_grad = True
+            x = sel.view(-1, fixed, dim)
+            mask = (index_t.view(B, fixed, 1) != 0).half()
+            out = torch.cat([x, mask], dim=2)
+            scale = 64.0
+            (out.float() * torch.arange(1, dim + 2, device=out.device)).sum().mul(scale * 1e-3).backward()
+            # persia/ctx.py:966-981
+            gb = tb.create_gradient_batch()
+            U = distinct.shape[0] - 1
+            if distinct.shape[0] > 1:
+                grad = torch.zeros_like(distinct, dtype=torch.float32)
+                nz = sel.grad.index_select(0, non_empty_t.view(-1)).float()
+                grad.index_add_(0, index_t.view(-1)[non_empty_t.view(-1)], nz)
+                grad = grad[1:, :].contiguous()
+                gb.add_gradient("seq", grad.data_ptr(), list(grad.shape), False, scale)
+            torch.cuda.synchronize()
+            bwd.update_id_type_feature_gradient_batched(gb)
+            if U:
+                assert w.backward_raw(0, octx, grad.cpu().numpy(), scale=scale) == 0
+        from persia_b200.persia_core import _S
+        from util import to_dev_ids
+
+        signs = np.array(sorted(seen), np.uint64)
+        ent, found = _S.groups[16]["shard"].get_entries(to_dev_ids(signs, "cuda:0"))
+        assert found.all()
+        ent = ent.cpu().numpy()
+        for k, s in enumerate(signs):
+            assert ent[k].tobytes() == w.get_entry(int(s)).tobytes()
+    finally:
+        impl.reset()
