@@ -105,7 +105,7 @@ struct pb_ctx {
   uint32_t* nan_tick = nullptr;
   float* vw_stage = nullptr;
   size_t vw_stage_floats = 0;
-  uint2* heads = nullptr;       // compacted piece heads of the sorted occurrence list
+  uint4* heads = nullptr;       // compacted piece heads of the sorted occurrence list
   uint2* owners = nullptr;      // (first boundary, segment start) of cut segments
   uint32_t* seg_counts = nullptr;
   float* partials = nullptr;  // 2 rows per PIECE-block of the sorted occurrence list
@@ -539,7 +539,7 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   A((void**)&c->vals_b, 4 * n);
   A((void**)&c->hist, 4 * hist_elems);
   A((void**)&c->nan_tick, 4 * PB_MAX_SLOTS);
-  A((void**)&c->heads, 8 * n);
+  A((void**)&c->heads, 16 * n);
   A((void**)&c->owners, 8 * (n / PB_PIECE + 2));
   A((void**)&c->seg_counts, 16);
   A((void**)&c->dev_tick, 4);

@@ -66,13 +66,13 @@ void launch_gather(const TableDev& t, const SlotsDev& sl, const uint32_t* occ_ce
                    uint32_t n_out, uint32_t batch, void* out, bool out_f32, cudaStream_t st);
 void launch_elect(const TableDev& t, const uint32_t* occ_cell, uint32_t n, uint32_t* occ_row, uint32_t* zero,
                   uint32_t zero_words, cudaStream_t st);
-void launch_find_heads(const SegArgs& a, uint2* heads, uint2* owners, uint32_t* counts, cudaStream_t st);
+void launch_find_heads(const SegArgs& a, uint4* heads, uint2* owners, uint32_t* counts, cudaStream_t st);
 void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell, uint32_t n, float* entries,
                          uint8_t* found, cudaStream_t st);
 void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,
                      uint32_t* nan_tick, int32_t* status, cudaStream_t st);
 void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                          const GradsDev& gr, bool f16, const SegArgs& a, uint2* heads, uint2* owners,
+                          const GradsDev& gr, bool f16, const SegArgs& a, uint4* heads, uint2* owners,
                           uint32_t* counts, cudaStream_t st);
 // n_ptr (optional): the live count on the device (<= n); tick/nan_tick (optional): skip everything when equal
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,

@@ -1,5 +1,7 @@
 // pb_update.cu — backward of the sparse path: NaN rule, in-order gradient segment reduce (A8) fused with the
 // optimizer step and weight bound on the resident rows (A9).  SURVEY.md §8a.
+#include <cstdlib>
+
 #include "pb_device.cuh"
 
 namespace pb {
@@ -193,6 +195,7 @@ __global__ void k_slot_status(GradsDev gr, uint32_t n_slots, const uint32_t* __r
 // k_update_shared — only when two slots of one feature group can hold the same sign: such a sign gets
 //   one step per slot, sequentially in slot order (mod.rs:720-822); one group walks the whole run.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t PB_SHORT_PIECE = 4;  // a piece of more occurrences than this is listed as long
 __device__ __forceinline__ uint32_t val_occ(uint32_t v) { return v & 0x00FFFFFFu; }
 __device__ __forceinline__ uint32_t val_slot(uint32_t v) { return v >> 24; }
 
@@ -306,11 +309,24 @@ __device__ __forceinline__ void reduce_piece_t(float (&acc)[VEC], const SegArgs&
   }
 }
 
+// sv0 = a.sval[j0], carried by the head record: a piece of one occurrence (the majority) loads no index at all
 template <int VEC, bool F16>
 __device__ __forceinline__ void reduce_piece(float (&acc)[VEC], const SegArgs& a, const TableDev& t, const SlotsDev& sl,
-                                             const GradsDev& gr, uint32_t slot, uint32_t j0, uint32_t j1, uint32_t c) {
+                                             const GradsDev& gr, uint32_t slot, uint32_t j0, uint32_t j1, uint32_t c,
+                                             uint32_t sv0) {
   // the common case (one id per sample, loss scale 1, no sqrt scaling) gets a branch-free body
-  if (!a.occ_outrow && !gr.do_scale[slot] && !sl.sqrt_scaling[slot]) reduce_piece_t<VEC, F16, true>(acc, a, t, sl, gr, slot, j0, j1, c);
+  const bool plain = !a.occ_outrow && !gr.do_scale[slot] && !sl.sqrt_scaling[slot];
+  if (plain && j1 - j0 == 1) {
+    PieceCtx pc;
+    pc.gbase = gr.ptr[slot];
+    pc.slot_row0 = slot * a.batch;
+    float g[VEC];
+    load_grad<VEC, F16>(g, pc, a, t, val_occ(sv0), c);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(0.0f, g[k]);  // the reference adds into a zeroed row (-0 -> +0)
+    return;
+  }
+  if (plain) reduce_piece_t<VEC, F16, true>(acc, a, t, sl, gr, slot, j0, j1, c);
   else reduce_piece_t<VEC, F16, false>(acc, a, t, sl, gr, slot, j0, j1, c);
 }
 
@@ -355,16 +371,17 @@ __device__ __forceinline__ float* partial_slot(const SegArgs& a, const TableDev&
 // independent piece of work).  One warp looks at one PIECE-block (PIECE == 32 == warp width): segment
 // starts of the previous, own and next block become three ballot masks, from which every lane derives
 // its piece end without walking the list.
-//   heads[k]  = (first position, end position | whole << 31)
+//   heads[k]  = (first position, end position | whole << 31, row of the sign, sorted value at the first position)
 //   owners[k] = (first boundary of a cut segment, start of that segment)
-// counts[0] / counts[1] are the list lengths (cleared by the histogram pass).
+// counts[0] = long pieces (heads[0..)), counts[2] = short pieces (heads[n-1] downwards), counts[1] = owners,
+// counts[3] = the reducing kernel's work counter; all four are cleared by the histogram pass.
 __device__ __forceinline__ bool seg_start_at(const SegArgs& a, uint32_t p) {
   if (p >= a.n) return true;  // past the end: terminates any segment
   if (p == 0) return true;
   return a.skey[p] != a.skey[p - 1] || val_slot(a.sval[p]) != val_slot(a.sval[p - 1]);
 }
 
-__global__ void __launch_bounds__(256) k_find_heads(SegArgs a, uint2* __restrict__ heads, uint2* __restrict__ owners,
+__global__ void __launch_bounds__(256) k_find_heads(SegArgs a, uint4* __restrict__ heads, uint2* __restrict__ owners,
                                                     uint32_t* __restrict__ counts) {
   static_assert(PB_PIECE == 32, "one warp per PIECE-block");
   const uint32_t lane = threadIdx.x & 31;
@@ -419,54 +436,76 @@ __global__ void __launch_bounds__(256) k_find_heads(SegArgs a, uint2* __restrict
         is_head = false;
     }
   }
-  uint32_t hm = __ballot_sync(0xffffffffu, is_head);
-  uint32_t om = __ballot_sync(0xffffffffu, is_owner);
-  uint32_t hb = 0, ob = 0;
+  // long pieces (the expensive ones) are listed from the front, short ones from the back: the reducing kernel
+  // hands out the list front to back, so the tail of the launch is made of cheap pieces
+  const bool is_long = is_head && (e - j) > PB_SHORT_PIECE;
+  const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
+  const uint32_t sm = __ballot_sync(0xffffffffu, is_head && !is_long);
+  const uint32_t om = __ballot_sync(0xffffffffu, is_owner);
+  uint32_t lb = 0, sb = 0, ob = 0;
   if (lane == 0) {
-    if (hm) hb = atomicAdd(&counts[0], __popc(hm));
+    if (lm) lb = atomicAdd(&counts[0], __popc(lm));
+    if (sm) sb = atomicAdd(&counts[2], __popc(sm));
     if (om) ob = atomicAdd(&counts[1], __popc(om));
   }
-  hb = __shfl_sync(0xffffffffu, hb, 0);
+  lb = __shfl_sync(0xffffffffu, lb, 0);
+  sb = __shfl_sync(0xffffffffu, sb, 0);
   ob = __shfl_sync(0xffffffffu, ob, 0);
-  if (is_head) heads[hb + __popc(hm & ((1u << lane) - 1u))] = make_uint2(j, e | (whole << 31));
+  if (is_head) {  // the record carries what the reducing group would otherwise chase through three dependent loads
+    const uint32_t lead = a.skey[j];  // the sort key is the sign's first occurrence (n = no storage)
+    const uint32_t row = lead < a.n ? a.occ_row[lead] : ROW_NONE;
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t at = is_long ? lb + __popc(lm & below) : a.n - 1u - (sb + __popc(sm & below));
+    heads[at] = make_uint4(j, e | (whole << 31), row, a.sval[j]);
+  }
   if (is_owner) owners[ob + __popc(om & ((1u << lane) - 1u))] = make_uint2(j, j0);
 }
 
-// One group of G lanes per piece, striding over the compacted head list.
+#ifndef PB_REDUCE_BLOCKS
+#define PB_REDUCE_BLOCKS 3  // resident blocks per SM k_reduce_update is compiled for
+#endif
+// One group of G lanes per piece.  Every group starts on the piece of its own number and then takes pieces
+// off a device-side counter (requested before the current piece is worked on, consumed after it), so long
+// pieces, which come first in the list, never pile up on one group.
 template <int VEC, int G, bool F16>
-__global__ void __launch_bounds__(256, 3) k_reduce_update(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
-                                                          SegArgs a, const uint2* __restrict__ heads,
-                                                       const uint32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(256, PB_REDUCE_BLOCKS) k_reduce_update(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                          SegArgs a, const uint4* __restrict__ heads,
+                                                          uint32_t* __restrict__ counts) {
   const uint32_t lane = threadIdx.x % G;
   const uint32_t n_groups = gridDim.x * (blockDim.x / G);
-  const uint32_t n_heads = counts[0];
+  const uint32_t n_long = counts[0], n_work = n_long + counts[2];
   const uint32_t tick = *a.tick_ptr;
-  for (uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) / G; idx < n_heads; idx += n_groups) {
-    const uint2 hd = heads[idx];
+  const uint32_t wl = threadIdx.x & 31;
+  const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  while (w < n_work) {
+    uint32_t next = 0;
+    if (lane == 0) next = n_groups + atomicAdd(&counts[3], 1u);
+    const uint4 hd = heads[w < n_long ? w : a.n - 1u - (w - n_long)];
     const uint32_t j = hd.x, e = hd.y & 0x7FFFFFFFu;
     const bool whole = hd.y >> 31;
-    const uint32_t lead = a.skey[j];  // the sort key is the sign's first occurrence (n = no storage)
-    const uint32_t row = lead < a.n ? a.occ_row[lead] : ROW_NONE;
-    const uint32_t slot = val_slot(a.sval[j]);
-    if (!gr.ptr[slot] || a.nan_tick[slot] == tick) continue;  // skipped / NaN slot: nothing is applied
-    if (whole) {
+    const uint32_t row = hd.z;
+    const uint32_t slot = val_slot(hd.w);
+    const bool live = gr.ptr[slot] && a.nan_tick[slot] != tick;  // skipped / NaN slot: nothing is applied
+    if (live && whole) {
       if (row >= t.capacity) {
         if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
-        continue;
+      } else {
+        float* stage = a.vw_stage ? a.vw_stage + (size_t)j * t.dim : nullptr;
+        step_segment<VEC, G>(t, op, hy, gr, slot, row, lane, stage, [&](uint32_t c, float (&acc)[VEC]) {
+          reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j, e, c, hd.w);
+        });
       }
-      float* stage = a.vw_stage ? a.vw_stage + (size_t)j * t.dim : nullptr;
-      step_segment<VEC, G>(t, op, hy, gr, slot, row, lane, stage,
-                           [&](uint32_t c, float (&acc)[VEC]) { reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j, e, c); });
-    } else {
-      if (row >= t.capacity) continue;  // counted once by k_combine_update
+    } else if (live && row < t.capacity) {  // a miss is counted once by k_combine_update
       float* dst = partial_slot(a, t, j);
       const uint32_t nvec = t.dim / VEC;
       for (uint32_t c = lane; c < nvec; c += G) {
         float acc[VEC];
-        reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j, e, c);
+        reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j, e, c, hd.w);
         store_vec<VEC>(dst + c * VEC, acc);
       }
     }
+    w = __shfl_sync(gmask, next, wl / G * G);
   }
 }
 
@@ -584,7 +623,7 @@ __global__ void __launch_bounds__(256) k_update_shared(TableDev t, OptimDev op, 
     if (active) {
       float* stage = a.vw_stage ? a.vw_stage + (size_t)j0 * t.dim : nullptr;
       step_segment<VEC, G>(t, op, hy, gr, slot, row, lane, stage,
-                           [&](uint32_t c, float (&acc)[VEC]) { reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j0, j1, c); });
+                           [&](uint32_t c, float (&acc)[VEC]) { reduce_piece<VEC, F16>(acc, a, t, sl, gr, slot, j0, j1, c, a.sval[j0]); });
     }
     j0 = j1;
   }
@@ -650,11 +689,12 @@ void launch_slot_status(const GradsDev& gr, uint32_t n_slots, const uint32_t* ti
 
 template <int VEC, bool F16>
 static void reduce_dispatch(int G, const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                            const GradsDev& gr, const SegArgs& a, const uint2* heads, const uint2* owners,
-                            const uint32_t* counts, cudaStream_t st) {
+                            const GradsDev& gr, const SegArgs& a, const uint4* heads, const uint2* owners,
+                            uint32_t* counts, cudaStream_t st) {
   // persistent-style grids: the list lengths live on the device
   const uint32_t full = cdiv((uint64_t)a.n * G, 256);
-  const uint32_t grid = full < 148u * 4u ? full : 148u * 4u;
+  static const uint32_t tune_grid = getenv("PB_REDUCE_GRID") ? (uint32_t)atoi(getenv("PB_REDUCE_GRID")) : 148u * PB_REDUCE_BLOCKS;
+  const uint32_t grid = full < tune_grid ? full : tune_grid;
   const uint32_t n_bound = a.piece ? cdiv(a.n, a.piece) : 0;
   const uint32_t gridc = n_bound < 148u * 2u ? (n_bound ? n_bound : 1) : 148u * 2u;  // one block per cut segment
   uint32_t ng = 256u / (uint32_t)G;
@@ -673,7 +713,7 @@ static void reduce_dispatch(int G, const TableDev& t, const OptimDev& op, const 
 }
 
 void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                          const GradsDev& gr, bool f16, const SegArgs& a, uint2* heads, uint2* owners,
+                          const GradsDev& gr, bool f16, const SegArgs& a, uint4* heads, uint2* owners,
                           uint32_t* counts, cudaStream_t st) {
   if (!a.n) return;
   int vec, G;
@@ -687,7 +727,7 @@ void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev&
   }
 }
 
-void launch_find_heads(const SegArgs& a, uint2* heads, uint2* owners, uint32_t* counts, cudaStream_t st) {
+void launch_find_heads(const SegArgs& a, uint4* heads, uint2* owners, uint32_t* counts, cudaStream_t st) {
   if (a.n) PB_LAUNCH_F(FAM_SORT, k_find_heads, cdiv((uint64_t)cdiv(a.n, 32) * 32, 256), 256, 0, st, a, heads, owners, counts);
 }
 
