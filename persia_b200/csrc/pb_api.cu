@@ -77,8 +77,9 @@ struct pb_table {
   uint32_t* scratch = nullptr;  // index cells of a single-request call
   uint32_t scratch_cap = 0;
   // Adam: accumulated (beta1^t, beta2^t) per feature group, keyed by index prefix (optim.rs:99-131, 155-197)
-  std::vector<std::pair<uint64_t, std::pair<float, float>>> adam_pow;
-  float b1p_direct = 1.0f, b2p_direct = 1.0f;
+  // (the pairs live on the device: a captured backward advances them on every replay)
+  std::vector<uint64_t> adam_keys;  // position = pair number; pair PB_ADAM_KEYS-1 serves pb_update
+  float* adam_dev = nullptr;
   // capacity policy (pb_table_set_eviction): 0 = refuse admissions when full
   uint32_t evict_every = 0, evict_low = 0, evict_target = 0, evict_keep = 2;
   uint32_t train_calls = 0;
@@ -97,7 +98,7 @@ struct pb_ctx {
   uint32_t* row_off = nullptr;
   bool multi_id = false;
   uint32_t n_occ = 0, batch = 0;
-  uint32_t* dev_tick = nullptr;  // batch number of the pending forward
+  uint32_t* dev_tick = nullptr;  // request number of the pending forward (device side, CUDA-graph safe)
   uint32_t occ_off[PB_MAX_SLOTS + 1];
   bool pending = false;
   // backward workspace
@@ -189,6 +190,15 @@ int ready_for_training(pb_table* t) {
   if (!t->has_op) return fail(PB_ERR_STATE, "optimizer not registered (OptimizerNotFoundError)");
   if (!t->has_hy) return fail(PB_ERR_STATE, "embedding server not configured (NotConfiguredError)");
   return PB_OK;
+}
+
+// pair number of a feature group (keyed by its index prefix); -1 when the table is out of pairs
+int adam_index(pb_table* t, uint64_t prefix) {
+  for (size_t i = 0; i < t->adam_keys.size(); ++i)
+    if (t->adam_keys[i] == prefix) return (int)i;
+  if (t->adam_keys.size() + 1 >= PB_ADAM_KEYS) return -1;
+  t->adam_keys.push_back(prefix);
+  return (int)t->adam_keys.size() - 1;
 }
 
 SlotsDev no_slots() {
@@ -298,6 +308,7 @@ int pb_table_destroy(pb_table* t) {
     if (t->evict_ws) cudaFree(t->evict_ws);
   }
   if (t->scratch) cudaFree(t->scratch);
+  if (t->adam_dev) cudaFree(t->adam_dev);
   delete t;
   return PB_OK;
 }
@@ -315,10 +326,12 @@ int pb_table_set_optimizer(pb_table* t, const pb_optim_cfg* c) {
   t->op.eps = c->eps;
   t->op.b1 = c->beta1;
   t->op.b2 = c->beta2;
-  if (!t->has_op) {
-    t->adam_pow.clear();  // AdamPowerOfBetas starts at (beta1, beta2) for every feature group (optim.rs:118-124)
-    t->b1p_direct = c->beta1;
-    t->b2p_direct = c->beta2;
+  if (!t->has_op && c->kind == PB_OPT_ADAM) {  // AdamPowerOfBetas starts at (beta1, beta2) for every feature group (optim.rs:118-124)
+    DeviceGuard g(t->device);
+    t->adam_keys.clear();
+    if (!t->adam_dev) PB_CUDA(cudaMalloc(&t->adam_dev, sizeof(float) * 2 * PB_ADAM_KEYS));
+    launch_adam_fill(t->adam_dev, c->beta1, c->beta2, 0);
+    PB_CUDA(cudaDeviceSynchronize());
   }
   t->has_op = true;
   return PB_OK;
@@ -427,11 +440,15 @@ int pb_update(pb_table* t, const uint64_t* d_signs, const float* d_grads, uint32
   if ((rc = ensure_scratch(t, n))) return rc;
   SlotsDev sl = no_slots();
   launch_probe(MODE_FIND, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
+  const float* pair = nullptr;
   if (t->op.kind == PB_OPT_ADAM) {  // get_batch_level_state: one power step per request (optim.rs:155-197)
-    t->b1p_direct *= t->op.b1;
-    t->b2p_direct *= t->op.b2;
+    AdamKeys k{};
+    k.idx[0] = (uint8_t)(PB_ADAM_KEYS - 1);
+    k.n = 1;
+    launch_adam_advance(t->adam_dev, k, t->op.b1, t->op.b2, st);
+    pair = t->adam_dev + 2 * (PB_ADAM_KEYS - 1);
   }
-  launch_update_direct(t->d, t->op, t->hy, t->scratch, d_grads, n, t->b1p_direct, t->b2p_direct, st);
+  launch_update_direct(t->d, t->op, t->hy, t->scratch, d_grads, n, pair, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
 }
@@ -739,27 +756,18 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     gr.inv_scale[s] = inv;
   }
   if (t->op.kind == PB_OPT_ADAM) {  // get_batch_level_state: one power step per request and feature group
-    std::vector<uint64_t> stepped;
+    AdamKeys keys{};
     for (uint32_t s = 0; s < S; ++s) {
       if (!h_grads[s]) continue;
-      const uint64_t pfx = c->slots.prefix[s];
-      std::pair<float, float>* acc = nullptr;
-      for (auto& a : t->adam_pow)
-        if (a.first == pfx) acc = &a.second;
-      if (!acc) {
-        t->adam_pow.push_back({pfx, {t->op.b1, t->op.b2}});
-        acc = &t->adam_pow.back().second;
-      }
+      const int k = adam_index(t, c->slots.prefix[s]);
+      if (k < 0) return fail(PB_ERR_CAPACITY, "more feature groups than Adam beta-power pairs");
+      gr.pow_idx[s] = (uint8_t)k;
       bool done = false;
-      for (uint64_t p : stepped) done |= p == pfx;
-      if (!done) {
-        acc->first *= t->op.b1;
-        acc->second *= t->op.b2;
-        stepped.push_back(pfx);
-      }
-      gr.b1p[s] = acc->first;
-      gr.b2p[s] = acc->second;
+      for (uint32_t i = 0; i < keys.n; ++i) done |= keys.idx[i] == (uint8_t)k;
+      if (!done) keys.idx[keys.n++] = (uint8_t)k;
     }
+    gr.adam_pow = t->adam_dev;
+    launch_adam_advance(t->adam_dev, keys, t->op.b1, t->op.b2, st);
   }
   uint32_t elems = c->batch * t->d.dim;
   launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
@@ -891,20 +899,15 @@ int pb_backward_raw(pb_table* t, pb_ctx* c, const void* d_grad, int is_f16, floa
   const bool do_scale = std::fabs(scale - 1.0f) > 1.1920929e-07f;
   const float inv = 1.0f / scale;
   if (do_scale && !std::isfinite(inv)) return fail(PB_ERR_INVALID, "scale on gradient must be finite");
-  float b1p = 0.0f, b2p = 0.0f;
+  const float* pair = nullptr;
   if (t->op.kind == PB_OPT_ADAM) {  // one power step per request and feature group (optim.rs:155-197)
-    const uint64_t pfx = c->slots.prefix[0];
-    std::pair<float, float>* acc = nullptr;
-    for (auto& a : t->adam_pow)
-      if (a.first == pfx) acc = &a.second;
-    if (!acc) {
-      t->adam_pow.push_back({pfx, {t->op.b1, t->op.b2}});
-      acc = &t->adam_pow.back().second;
-    }
-    acc->first *= t->op.b1;
-    acc->second *= t->op.b2;
-    b1p = acc->first;
-    b2p = acc->second;
+    const int k = adam_index(t, c->slots.prefix[0]);
+    if (k < 0) return fail(PB_ERR_CAPACITY, "more feature groups than Adam beta-power pairs");
+    AdamKeys keys{};
+    keys.idx[0] = (uint8_t)k;
+    keys.n = 1;
+    launch_adam_advance(t->adam_dev, keys, t->op.b1, t->op.b2, st);
+    pair = t->adam_dev + 2 * k;
   }
   const uint32_t dim = t->d.dim;
   launch_raw_nan(d_grad, is_f16 != 0, c->raw.counts, dim, c->dev_tick, c->nan_tick, st);
@@ -924,7 +927,7 @@ int pb_backward_raw(pb_table* t, pb_ctx* c, const void* d_grad, int is_f16, floa
     launch_raw_stage(d_grad, is_f16 != 0, c->raw.counts, dim, inv, do_scale, c->raw_stage, st);
     g32 = c->raw_stage;
   }
-  launch_update_direct(t->d, t->op, t->hy, c->raw.distinct_cell, g32, c->n_occ, b1p, b2p, st, c->raw.counts,
+  launch_update_direct(t->d, t->op, t->hy, c->raw.distinct_cell, g32, c->n_occ, pair, st, c->raw.counts,
                        c->dev_tick, c->nan_tick);
   PB_CUDA(cudaGetLastError());
   return PB_OK;

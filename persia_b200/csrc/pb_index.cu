@@ -358,12 +358,12 @@ __global__ void __launch_bounds__(256) k_shard_of(const uint64_t* __restrict__ s
   if (hash) hash[i] = h;
 }
 
-// Opens a training request on the device: bumps the batch number, empties the admitted-cell list and
-// records the batch number in the context (so the backward of this batch recognises its own NaN marks).
+// Opens a training request on the device: bumps the table's batch number (recency, leader election) and the
+// context's own request number, by which the backward of this batch recognises its NaN marks.  The latter never
+// repeats within a context, whatever tables it serves and whenever they are cleared.
 __global__ void k_begin_batch(uint32_t* counters, uint32_t* ctx_tick) {
-  uint32_t t = counters[CTR_TICK] + 1;
-  counters[CTR_TICK] = t;
-  if (ctx_tick) *ctx_tick = t;
+  counters[CTR_TICK] = counters[CTR_TICK] + 1;
+  if (ctx_tick) *ctx_tick = *ctx_tick + 1;
 }
 
 __global__ void k_fill_cells(Cell* cells, uint64_t n) {

@@ -23,7 +23,8 @@ struct GradsDev {
   const void* ptr[PB_MAX_SLOTS];  // nullptr = skipped slot
   float inv_scale[PB_MAX_SLOTS];  // 1/scale_factor
   uint8_t do_scale[PB_MAX_SLOTS]; // |scale-1| > f32::EPSILON (mod.rs:751)
-  float b1p[PB_MAX_SLOTS], b2p[PB_MAX_SLOTS];  // Adam accumulated beta powers of the slot's feature group
+  const float* adam_pow;          // Adam: accumulated (beta1^t, beta2^t) pairs on the device, one per feature group
+  uint8_t pow_idx[PB_MAX_SLOTS];  // the slot's pair
 };
 
 // arguments of the backward segment kernels (see pb_kernels.cu)
@@ -76,9 +77,16 @@ void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev&
                           uint32_t* counts, cudaStream_t st);
 // n_ptr (optional): the live count on the device (<= n); tick/nan_tick (optional): skip everything when equal
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
-                          const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st,
+                          const float* grads, uint32_t n, const float* adam_pair, cudaStream_t st,
                           const uint32_t* n_ptr = nullptr, const uint32_t* tick = nullptr,
                           const uint32_t* nan_tick = nullptr);
+constexpr uint32_t PB_ADAM_KEYS = 256;  // beta-power pairs per table; the last one serves pb_update
+struct AdamKeys {
+  uint8_t idx[PB_MAX_SLOTS];
+  uint32_t n;
+};
+void launch_adam_fill(float* pow, float b1, float b2, cudaStream_t st);
+void launch_adam_advance(float* pow, const AdamKeys& keys, float b1, float b2, cudaStream_t st);
 uint32_t raw_scan_tiles(uint32_t n);
 void launch_raw_forward(const TableDev& t, const SlotsDev& sl, const uint64_t* ids, uint32_t n,
                         const uint32_t* row_off, const uint32_t* occ_sample, uint32_t batch, uint32_t fixed,

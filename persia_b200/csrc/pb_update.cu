@@ -339,8 +339,9 @@ __device__ __forceinline__ void step_segment(const TableDev& t, const OptimDev& 
   float vw_state = 0.0f, r1 = 0.0f, r2 = 0.0f;
   if (op.kind == PB_OPT_ADAGRAD_VW) vw_state = prow[t.dim];
   if (op.kind == PB_OPT_ADAM) {
-    r1 = __fdiv_rn(1.0f, __fsub_rn(1.0f, gr.b1p[slot]));
-    r2 = __fdiv_rn(1.0f, __fsub_rn(1.0f, gr.b2p[slot]));
+    const float* pw = gr.adam_pow + 2u * gr.pow_idx[slot];
+    r1 = __fdiv_rn(1.0f, __fsub_rn(1.0f, pw[0]));
+    r2 = __fdiv_rn(1.0f, __fsub_rn(1.0f, pw[1]));
   }
   for (uint32_t c = lane; c < nvec; c += G) {
     RowChunk<VEC> rc;
@@ -477,6 +478,13 @@ __global__ void __launch_bounds__(256, PB_REDUCE_BLOCKS) k_reduce_update(TableDe
   const uint32_t tick = *a.tick_ptr;
   const uint32_t wl = threadIdx.x & 31;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
+  // slots whose gradient is skipped or holds a NaN, as a bit mask per block (instead of a dependent load per piece)
+  __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
+  if (threadIdx.x < PB_MAX_SLOTS / 32) dead[threadIdx.x] = 0u;
+  __syncthreads();
+  if (threadIdx.x < PB_MAX_SLOTS && (!gr.ptr[threadIdx.x] || a.nan_tick[threadIdx.x] == tick))
+    atomicOr(&dead[threadIdx.x >> 5], 1u << (threadIdx.x & 31));
+  __syncthreads();
   uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   while (w < n_work) {
     uint32_t next = 0;
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(256, PB_REDUCE_BLOCKS) k_reduce_update(TableDe
     const bool whole = hd.y >> 31;
     const uint32_t row = hd.z;
     const uint32_t slot = val_slot(hd.w);
-    const bool live = gr.ptr[slot] && a.nan_tick[slot] != tick;  // skipped / NaN slot: nothing is applied
+    const bool live = !((dead[slot >> 5] >> (slot & 31)) & 1u);  // skipped / NaN slot: nothing is applied
     if (live && whole) {
       if (row >= t.capacity) {
         if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
@@ -633,8 +641,9 @@ __global__ void __launch_bounds__(256) k_update_shared(TableDev t, OptimDev op, 
 template <int VEC, int G>
 __global__ void __launch_bounds__(256) k_update_direct(TableDev t, OptimDev op, HyperDev hy,
                                                        const uint32_t* __restrict__ occ_cell,
-                                                       const float* __restrict__ grads, uint32_t n, float b1p,
-                                                       float b2p, const uint32_t* __restrict__ n_ptr,
+                                                       const float* __restrict__ grads, uint32_t n,
+                                                       const float* __restrict__ adam_pair,
+                                                       const uint32_t* __restrict__ n_ptr,
                                                        const uint32_t* __restrict__ tick_ptr,
                                                        const uint32_t* __restrict__ nan_tick) {
   uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -653,8 +662,8 @@ __global__ void __launch_bounds__(256) k_update_direct(TableDev t, OptimDev op, 
   float vw_state = (op.kind == PB_OPT_ADAGRAD_VW) ? prow[t.dim] : 0.0f;
   float r1 = 0.0f, r2 = 0.0f;
   if (op.kind == PB_OPT_ADAM) {
-    r1 = __fdiv_rn(1.0f, __fsub_rn(1.0f, b1p));
-    r2 = __fdiv_rn(1.0f, __fsub_rn(1.0f, b2p));
+    r1 = __fdiv_rn(1.0f, __fsub_rn(1.0f, adam_pair[0]));
+    r2 = __fdiv_rn(1.0f, __fsub_rn(1.0f, adam_pair[1]));
   }
   const float* g0 = grads + (size_t)gid * t.dim;
   for (uint32_t c = lane; c < nvec; c += G) {
@@ -680,6 +689,28 @@ void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_sl
   if (f16) PB_LAUNCH_F(FAM_NAN, k_nan_scan<true>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick);
   else PB_LAUNCH_F(FAM_NAN, k_nan_scan<false>, grid, 256, 0, st, gr, elems_per_slot, tick, nan_tick);
   if (status) PB_LAUNCH(k_slot_status, 1, PB_MAX_SLOTS, 0, st, gr, n_slots, tick, nan_tick, status);
+}
+
+// Adam's batch-level state (optim.rs:99-131, 155-197): one (beta1^t, beta2^t) pair per feature group, kept on the
+// device so that a captured backward advances it on every replay.
+__global__ void k_adam_fill(float* pow, float b1, float b2) {
+  uint32_t i = threadIdx.x;
+  if (i < PB_ADAM_KEYS) {
+    pow[2 * i] = b1;
+    pow[2 * i + 1] = b2;
+  }
+}
+__global__ void k_adam_advance(float* pow, AdamKeys keys, float b1, float b2) {
+  uint32_t i = threadIdx.x;
+  if (i < keys.n) {
+    float* p = pow + 2u * keys.idx[i];
+    p[0] = __fmul_rn(p[0], b1);
+    p[1] = __fmul_rn(p[1], b2);
+  }
+}
+void launch_adam_fill(float* pow, float b1, float b2, cudaStream_t st) { PB_LAUNCH(k_adam_fill, 1, PB_ADAM_KEYS, 0, st, pow, b1, b2); }
+void launch_adam_advance(float* pow, const AdamKeys& keys, float b1, float b2, cudaStream_t st) {
+  if (keys.n) PB_LAUNCH(k_adam_advance, 1, PB_MAX_SLOTS, 0, st, pow, keys, b1, b2);
 }
 
 void launch_slot_status(const GradsDev& gr, uint32_t n_slots, const uint32_t* tick, const uint32_t* nan_tick,
@@ -732,7 +763,7 @@ void launch_find_heads(const SegArgs& a, uint4* heads, uint2* owners, uint32_t* 
 }
 
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
-                          const float* grads, uint32_t n, float b1p, float b2p, cudaStream_t st,
+                          const float* grads, uint32_t n, const float* adam_pair, cudaStream_t st,
                           const uint32_t* n_ptr, const uint32_t* tick, const uint32_t* nan_tick) {
   if (!n) return;
   int vec, G;
@@ -740,7 +771,7 @@ void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev&
   uint32_t grid = cdiv((uint64_t)n * G, 256);
 #define PB_U(V, GG)                                                                                          \
   if (vec == V && G == GG)                                                                                   \
-    PB_LAUNCH_F(FAM_UPDATE, (k_update_direct<V, GG>), grid, 256, 0, st, t, op, hy, occ_cell, grads, n, b1p, b2p, n_ptr, \
+    PB_LAUNCH_F(FAM_UPDATE, (k_update_direct<V, GG>), grid, 256, 0, st, t, op, hy, occ_cell, grads, n, adam_pair, n_ptr, \
                 tick, nan_tick);
   PB_U(4, 1) PB_U(4, 2) PB_U(4, 4) PB_U(4, 8) PB_U(4, 16) PB_U(4, 32)
   PB_U(1, 1) PB_U(1, 2) PB_U(1, 4) PB_U(1, 8) PB_U(1, 16) PB_U(1, 32)

@@ -3,7 +3,4 @@ run() { echo "== $1"; shift; env "$@" timeout 200 python bench.py --no-cpu-basel
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print(d['ms_per_step']*1000, d['roofline']['kernel_timed_alone_us'], {k:round(v['us_per_step'],1) for k,v in d['roofline']['kernels_us_per_step'].items()})"; }
-run rb3_444 A=1
-run rb3_592 PB_REDUCE_GRID=592
-run rb2_296 PERSIA_B200_LIB=/root/repo/persia_b200/libpersia_b200_rb2.so
-run rb4_592 PERSIA_B200_LIB=/root/repo/persia_b200/libpersia_b200_rb4.so
+run dead_mask A=1

@@ -512,6 +512,47 @@ def test_adam_training_bit_exact(torch_cuda, pb, oracle, dim):
         _entries_equal(torch, s, w, t)
 
 
+def test_adam_graph_replay_advances_beta_powers(torch_cuda, pb, oracle):
+    """The beta powers live on the device: a captured forward+backward replayed k times equals k oracle steps."""
+    torch = torch_cuda
+    rng = np.random.default_rng(77)
+    S, B, dim, card = 2, 256, 32, [40, 3000]
+    s, ctx, w, _ = _pair(pb, oracle, S, dim, oracle.ADAM, optim_kw=dict(lr=0.01, b1=0.9, b2=0.999, eps=1e-8))
+    ids_np, _, slot_off = make_batch(rng, S, B, card)
+    ids_dev = to_dev_ids(ids_np, DEV)
+    g_dev = torch.zeros((S, B, dim), dtype=torch.float16, device=DEV)
+    out = torch.empty((S, B, dim), dtype=torch.float16, device=DEV)
+    grads = [g_dev[i] for i in range(S)]
+
+    def oracle_step(ids, g):
+        _, octx = w.forward(ids, full_row_off(S, B), B, training=True)
+        w.backward(octx, [g[i] for i in range(S)])
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx.forward(s, ids_dev, slot_off, B, training=True, out=out)  # eager step (allocations happen here)
+        ctx.backward(s, grads)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):  # capture launches nothing
+            ctx.forward(s, ids_dev, slot_off, B, training=True, out=out)
+            ctx.backward(s, grads)
+    oracle_step(ids_np, np.zeros((S, B, dim), np.float16))
+    seen = [set() for _ in range(S)]
+    for it in range(4):
+        ids_np, _, _ = make_batch(rng, S, B, card)
+        g = (rng.standard_normal((S, B, dim)) * 1e-2).astype(np.float16)
+        ids_dev.copy_(to_dev_ids(ids_np, DEV))
+        g_dev.copy_(torch.from_numpy(g).to(DEV))
+        graph.replay()
+        torch.cuda.synchronize()
+        oracle_step(ids_np, g)
+        for i in range(S):
+            seen[i].update(oracle.add_prefix(ids_np[i * B:(i + 1) * B], 8, oracle.index_prefix(i)).tolist())
+    for t in seen:
+        _entries_equal(torch, s, w, np.array(sorted(t), np.uint64))
+
+
 def test_capacity_eviction_keeps_recent_rows(torch_cuda, pb, oracle):
     """EvictionMap semantics (eviction_map.rs:76-97), batch-granular: least recently used rows go first, rows used
     in the recent batches and a hot set touched every batch survive, the shard never refuses an admission, and a
