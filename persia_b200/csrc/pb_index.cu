@@ -61,8 +61,11 @@ __device__ __noinline__ void init_row(const TableDev& t, const HyperDev& hy, con
 // returns to EMPTY: eviction leaves a tombstone, which lookups walk past and admissions reuse (after having
 // seen an EMPTY cell further on, i.e. knowing the sign is absent).
 // ------------------------------------------------------------------------------------------------
+#ifndef PB_PROBE_BLOCKS
+#define PB_PROBE_BLOCKS 5  // resident blocks per SM the probe is compiled for (48 registers; 6 and 8 measured no faster)
+#endif
 template <int MODE, bool PREFIX>
-__global__ void __launch_bounds__(256) k_probe(TableDev t, HyperDev hy, OptimDev op, SlotsDev sl,
+__global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_probe(TableDev t, HyperDev hy, OptimDev op, SlotsDev sl,
                                                const uint64_t* __restrict__ ids, uint32_t n,
                                                uint32_t* __restrict__ occ_cell) {
   const uint32_t tick = t.counters[CTR_TICK];
