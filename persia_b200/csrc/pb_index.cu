@@ -1,6 +1,6 @@
 // pb_index.cu — the shard's hash index and row store: find-or-admit, row initialisation, gather + pool
 //  and the small id-preprocessing kernels (A2, A3 hash).
-#include "pb_device.cuh"
+#include "pb_group.cuh"
 
 namespace pb {
 
@@ -273,44 +273,11 @@ __global__ void __launch_bounds__(256) k_gather_pool(TableDev t, SlotsDev sl, co
 // global memory.  The high half doubles as the row's recency (get_refresh, eviction_map.rs:48-60).
 // Also records the row of every occurrence and clears the first radix histogram (side job).
 // ------------------------------------------------------------------------------------------------
-constexpr int ELECT_SLOTS = 512;
 __global__ void __launch_bounds__(256) k_elect_leaders(TableDev t, const uint32_t* __restrict__ occ_cell, uint32_t n,
                                                        uint32_t* __restrict__ occ_row, uint32_t* __restrict__ zero,
                                                        uint32_t zero_words) {
-  __shared__ uint32_t keys[ELECT_SLOTS], best[ELECT_SLOTS];
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < zero_words; w += gridDim.x * blockDim.x) zero[w] = 0;
-  for (uint32_t i = threadIdx.x; i < ELECT_SLOTS; i += blockDim.x) {
-    keys[i] = 0xFFFFFFFFu;
-    best[i] = 0xFFFFFFFFu;
-  }
-  __syncthreads();
-  const unsigned long long lead_hi = (unsigned long long)t.counters[CTR_TICK] << 32;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint32_t h = occ_cell[i];
-    uint32_t row = (h < t.n_cells + N_SPECIAL) ? t.cells[h].row : ROW_NONE;
-    if (row >= t.capacity) row = ROW_NONE;
-    occ_row[i] = row;
-    if (row != ROW_NONE) {
-      uint32_t s = (row * 2654435761u) >> 23;  // 9 bits
-      for (;;) {
-        uint32_t k = atomicCAS(&keys[s], 0xFFFFFFFFu, row);
-        if (k == 0xFFFFFFFFu || k == row) {
-          atomicMin(&best[s], i);
-          break;
-        }
-        s = (s + 1) & (ELECT_SLOTS - 1);
-      }
-    }
-  }
-  __syncthreads();
-  for (uint32_t s = threadIdx.x; s < ELECT_SLOTS; s += blockDim.x) {
-    uint32_t row = keys[s];
-    if (row != 0xFFFFFFFFu) {
-      const unsigned long long mine = lead_hi | (uint32_t)~best[s];
-      if (__ldcg(&t.row_lead[row]) < mine) atomicMax(&t.row_lead[row], mine);
-    }
-  }
+  elect_body(blockIdx.x, t, occ_cell, n, occ_row);
 }
 
 // set_embedding / get_rows: whole entries (emb ++ state), one group per sign.

@@ -2,7 +2,7 @@
 // optimizer step and weight bound on the resident rows (A9).  SURVEY.md §8a.
 #include <cstdlib>
 
-#include "pb_device.cuh"
+#include "pb_group.cuh"
 
 namespace pb {
 
@@ -195,14 +195,6 @@ __global__ void k_slot_status(GradsDev gr, uint32_t n_slots, const uint32_t* __r
 // k_update_shared — only when two slots of one feature group can hold the same sign: such a sign gets
 //   one step per slot, sequentially in slot order (mod.rs:720-822); one group walks the whole run.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t PB_SHORT_PIECE = 4;  // a piece of more occurrences than this is listed as long
-__device__ __forceinline__ uint32_t val_occ(uint32_t v) { return v & 0x00FFFFFFu; }
-__device__ __forceinline__ uint32_t val_slot(uint32_t v) { return v >> 24; }
-
-__device__ __forceinline__ bool same_seg(const SegArgs& a, uint32_t j, uint32_t key, uint32_t slot) {
-  return a.skey[j] == key && val_slot(a.sval[j]) == slot;
-}
-
 // One gradient chunk of one occurrence, already clamped / unscaled / sqrt-scaled as the EW does before summing
 // (persia-common lib.rs:163-180, mod.rs:751-778).
 struct PieceCtx {
@@ -368,98 +360,9 @@ __device__ __forceinline__ float* partial_slot(const SegArgs& a, const TableDev&
   return a.partials + ((size_t)2 * blk + (head % a.piece ? 1 : 0)) * t.dim;
 }
 
-// Piece heads and combine owners of the sorted list, compacted (order is irrelevant: every entry is an
-// independent piece of work).  One warp looks at one PIECE-block (PIECE == 32 == warp width): segment
-// starts of the previous, own and next block become three ballot masks, from which every lane derives
-// its piece end without walking the list.
-//   heads[k]  = (first position, end position | whole << 31, row of the sign, sorted value at the first position)
-//   owners[k] = (first boundary of a cut segment, start of that segment)
-// counts[0] = long pieces (heads[0..)), counts[2] = short pieces (heads[n-1] downwards), counts[1] = owners,
-// counts[3] = the reducing kernel's work counter; all four are cleared by the histogram pass.
-__device__ __forceinline__ bool seg_start_at(const SegArgs& a, uint32_t p) {
-  if (p >= a.n) return true;  // past the end: terminates any segment
-  if (p == 0) return true;
-  return a.skey[p] != a.skey[p - 1] || val_slot(a.sval[p]) != val_slot(a.sval[p - 1]);
-}
-
 __global__ void __launch_bounds__(256) k_find_heads(SegArgs a, uint4* __restrict__ heads, uint2* __restrict__ owners,
                                                     uint32_t* __restrict__ counts) {
-  static_assert(PB_PIECE == 32, "one warp per PIECE-block");
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // PIECE-block of this warp
-  const uint32_t B0 = m * 32;
-  if (B0 >= a.n) return;  // whole warp
-  const uint32_t Fp = m ? __ballot_sync(0xffffffffu, seg_start_at(a, B0 - 32 + lane)) : 1u;  // previous block
-  const uint32_t F0 = __ballot_sync(0xffffffffu, seg_start_at(a, B0 + lane));
-  const uint32_t F1 = __ballot_sync(0xffffffffu, seg_start_at(a, B0 + 32 + lane));
-  const bool s2 = seg_start_at(a, B0 + 64);  // first position of the block after next
-  const uint32_t j = B0 + lane;
-  bool is_head = false, is_owner = false;
-  uint32_t e = 0, whole = 0, j0 = 0;
-  if (j < a.n) {
-    const bool seg_start = (F0 >> lane) & 1u;
-    is_head = seg_start;
-    if (a.piece && lane == 0) {
-      // a boundary cuts its segment only if the segment also holds the boundary before or after it:
-      // segments of <= PIECE occurrences are never cut and keep the reference summation order
-      const bool next_in = (F0 & ~1u) == 0 && !(F1 & 1u);            // no start in B0+1 .. B0+32
-      const bool prev_in = m && (Fp & ~1u) == 0 && !(F0 & 1u);       // no start in B0-31 .. B0
-      if (!seg_start) is_head = next_in || prev_in;
-      is_owner = next_in && !prev_in;  // first boundary of a segment that holds a second one
-      j0 = seg_start ? B0 : (B0 - 32 + (31 - __clz(Fp)));  // last start before the boundary (exists: !prev_in)
-    }
-    if (is_head) {
-      const uint32_t above = (lane == 31) ? 0u : (F0 & (0xFFFFFFFEu << lane));  // starts after this lane
-      bool seg_end = true;
-      if (!a.piece) {  // strict mode: no cutting — walk to the true end
-        e = j + 1;
-        const uint32_t key = a.skey[j], slot = val_slot(a.sval[j]);
-        while (e < a.n && same_seg(a, e, key, slot)) ++e;
-      } else if (above) {
-        e = B0 + __ffs(above) - 1;
-      } else if (F1 & 1u) {
-        e = B0 + 32;  // ends exactly on the boundary
-      } else {
-        // reaches the boundary B0+32 and continues: cut there iff this piece already spans a whole block
-        // (head on a boundary) or the segment also holds the boundary after it
-        const bool cut = (lane == 0) || ((F1 & ~1u) == 0 && !s2);
-        if (cut) {
-          e = B0 + 32;
-          seg_end = false;
-        } else {
-          e = (F1 & ~1u) ? B0 + 32 + __ffs(F1 & ~1u) - 1 : B0 + 64;  // ends inside the next block, or exactly at its end
-        }
-      }
-      if (e > a.n) e = a.n;
-      whole = (seg_start && seg_end) ? 1u : 0u;
-      // a sign held by several slots of one feature group is stepped slot by slot in k_update_shared
-      if (whole && a.shared_groups && ((j > 0 && a.skey[j - 1] == a.skey[j]) || (e < a.n && a.skey[e] == a.skey[j])))
-        is_head = false;
-    }
-  }
-  // long pieces (the expensive ones) are listed from the front, short ones from the back: the reducing kernel
-  // hands out the list front to back, so the tail of the launch is made of cheap pieces
-  const bool is_long = is_head && (e - j) > PB_SHORT_PIECE;
-  const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
-  const uint32_t sm = __ballot_sync(0xffffffffu, is_head && !is_long);
-  const uint32_t om = __ballot_sync(0xffffffffu, is_owner);
-  uint32_t lb = 0, sb = 0, ob = 0;
-  if (lane == 0) {
-    if (lm) lb = atomicAdd(&counts[0], __popc(lm));
-    if (sm) sb = atomicAdd(&counts[2], __popc(sm));
-    if (om) ob = atomicAdd(&counts[1], __popc(om));
-  }
-  lb = __shfl_sync(0xffffffffu, lb, 0);
-  sb = __shfl_sync(0xffffffffu, sb, 0);
-  ob = __shfl_sync(0xffffffffu, ob, 0);
-  if (is_head) {  // the record carries what the reducing group would otherwise chase through three dependent loads
-    const uint32_t lead = a.skey[j];  // the sort key is the sign's first occurrence (n = no storage)
-    const uint32_t row = lead < a.n ? a.occ_row[lead] : ROW_NONE;
-    const uint32_t below = (1u << lane) - 1u;
-    const uint32_t at = is_long ? lb + __popc(lm & below) : a.n - 1u - (sb + __popc(sm & below));
-    heads[at] = make_uint4(j, e | (whole << 31), row, a.sval[j]);
-  }
-  if (is_owner) owners[ob + __popc(om & ((1u << lane) - 1u))] = make_uint2(j, j0);
+  find_heads_body(blockIdx.x, a, heads, owners, counts);
 }
 
 #ifndef PB_REDUCE_BLOCKS
