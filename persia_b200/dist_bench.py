@@ -73,7 +73,9 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
     mode = "dynamic"
     gstream = torch.cuda.Stream(device=dev)
     if static:
-        wk.enable_static(B)
+        # slots per GPU pair: sized from the batches themselves (+10 %); a production loop sizes it on its warm-up
+        # batches and re-runs a batch that raises the overflow flag with a larger capacity
+        wk.enable_static(B, cap=wk.calibrate_cap(ids_dev, B))
         mode = "nccl-framed"
     if static and not args.dist_nccl:
         try:

@@ -126,15 +126,34 @@ class ShardedEmbeddingWorker:
     # split sizes travel to the host and the whole step — kernels and NCCL collectives — can be captured in a
     # CUDA graph.  `overflow` (device int32) is raised when a pair needs more than cap slots; check_overflow()
     # reads it (a host sync: call it outside the hot loop).
-    def enable_static(self, batch, slack=1.3, extra=4096):
+    def enable_static(self, batch, slack=1.3, extra=4096, cap=None):
         n = self.S * batch
-        self.cap = int(n / self.R * slack) + extra if self.R > 1 else n
+        if cap is not None:
+            self.cap = min(int(cap), n) if self.R > 1 else n
+        else:
+            self.cap = int(n / self.R * slack) + extra if self.R > 1 else n
         self.cap = (self.cap + 7) // 8 * 8
         self.overflow = torch.zeros(1, dtype=torch.int32, device=self.be.device)
         return self.cap
 
     def check_overflow(self):
         return bool(int(self.overflow))
+
+    def calibrate_cap(self, id_batches, batch, margin=1.10, extra=256):
+        """Capacity per (source, destination) pair from sample batches: the largest per-owner count seen on any rank
+        (hot signs make it a property of the id distribution, not of chance), plus a margin.  Collective: every
+        rank must call it.  A later batch that still overflows raises the overflow flag (check_overflow)."""
+        if self.R == 1:
+            return self.S * batch
+        slot_off = [s * batch for s in range(self.S + 1)]
+        worst, where = 0, None
+        for ids in id_batches:
+            signs = self.be.add_prefix(ids, slot_off, self.prefixes, self.prefix_bit)
+            _, counts = self.be.partition(signs, self.R)
+            worst, where = max(worst, int(counts.max())), counts.device
+        t = torch.tensor([worst], dtype=torch.int64, device=where)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(int(t) * margin) + extra
 
     def _a2a_equal(self, send):
         if self.R == 1:

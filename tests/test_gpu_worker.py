@@ -119,7 +119,12 @@ def _rank_main(rank, R, port, q, static=False):
     try:
         wk, be, pf = _make_worker(torch, dev)
         w, outs, _ = _reference(R)
-        if static:
+        if static == "p2p":  # capacity sized from the batches (collective), as bench.py does
+            sample = [torch.from_numpy(ids[rank].reshape(-1).view(np.int64)).to(dev) for ids, _ in _batches(R)]
+            cap = wk.calibrate_cap(sample, B)
+            assert cap < S * B
+            wk.enable_static(B, cap=cap)
+        elif static:
             wk.enable_static(B)
         if static == "p2p":
             wk.enable_p2p(B)
