@@ -159,3 +159,40 @@ def test_farmhash_full_width_fixture(oracle):
     fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "farmhash64_kat.json")))
     for k, v in fx["hash64"].items():
         assert int(oracle.farmhash64(np.array([int(k)], np.uint64))[0]) == int(v, 16)
+
+
+def test_raw_slot_known_answer(oracle):
+    """FeatureRawEmbeddingBatch by hand (embedding_worker_service/mod.rs:498-512, 540-545, 593-623 and the raw arm of
+    :790-798): a 5-sample LIL with repeats inside and across samples, an empty sample and one longer than
+    sample_fixed_size.  Distinct signs are numbered by first occurrence (the reference: hashbrown order)."""
+    dim, fixed = 4, 3
+    pf = oracle.index_prefix(0, 8)
+    w = oracle.Worker([oracle.SlotCfg(dim, summation=False, sample_fixed_size=fixed, prefix=pf)], n_ps=2)
+    w.configure()
+    w.set_optimizer(oracle.Optim(oracle.SGD, lr=0.5, wd=0.0))
+    ids = np.array([5, 7, 5, 9, 7, 7, 7, 7, 1], np.uint64)
+    row_off = np.array([0, 3, 4, 4, 8, 9], np.uint32)
+    signs = oracle.add_prefix(np.array([5, 7, 9, 1], np.uint64), 8, pf)  # first-occurrence order
+    rows = np.arange(16, dtype=np.float32).reshape(4, dim) / 8  # exactly representable in f16
+    w.set_embedding(signs, rows, dim)
+    table, index, non_empty, num, ctx = w.forward_raw(0, ids, row_off, 5, training=True)
+    assert table.shape == (5, dim)
+    np.testing.assert_array_equal(table[0], np.zeros(dim, np.float16))              # row 0: the padding target
+    np.testing.assert_array_equal(table[1:].astype(np.float32), rows)               # row u+1 = embedding of sign u
+    assert index.reshape(5, fixed).tolist() == [[1, 2, 1], [3, 0, 0], [0, 0, 0], [2, 2, 2], [4, 0, 0]]
+    assert num.tolist() == [3, 1, 0, 3, 1]                                          # min(len, sample_fixed_size)
+    assert non_empty.tolist() == [0, 1, 2, 3, 9, 10, 11, 12]                        # forward.rs:336-347
+    # the gradient of distinct sign u is row u of the [U, dim] tensor: one SGD step each, no reduction
+    g = np.arange(16, dtype=np.float32).reshape(4, dim)[::-1].copy()
+    assert w.backward_raw(0, ctx, g, scale=2.0) == 0                                # x 1/scale_factor
+    for u, s in enumerate(signs):
+        np.testing.assert_array_equal(w.get_entry(int(s)), rows[u] - np.float32(0.5) * (g[u] * np.float32(0.5)))
+    # NaN anywhere drops the whole gradient (mod.rs:731-746); a skipped gradient is reported as such
+    _, _, _, _, ctx = w.forward_raw(0, ids, row_off, 5, training=True)
+    g[2, 1] = np.nan
+    before = [w.get_entry(int(s)).copy() for s in signs]
+    assert w.backward_raw(0, ctx, g) == 2
+    _, _, _, _, ctx = w.forward_raw(0, ids, row_off, 5, training=True)
+    assert w.backward_raw(0, ctx, None, skip=True) == 1
+    for b, s in zip(before, signs):
+        np.testing.assert_array_equal(w.get_entry(int(s)), b)

@@ -23,6 +23,9 @@ STEPS = 3
 class OracleBackend:
     """Test double of worker.CudaBackend: numpy for the id plumbing, the oracle's parameter server for rows."""
 
+    NULL = np.uint64(0xFFFFFFFFFFFFFFFE)  # PB_NULL_SIGN: padding of a framed exchange
+    device = torch.device("cpu")
+
     def __init__(self, oracle, dim, optim, rank):
         self.o, self.dim = oracle, dim
         self.w = oracle.Worker([oracle.SlotCfg(dim)], n_ps=1)  # this rank's PS, addressed directly
@@ -55,8 +58,40 @@ class OracleBackend:
     def serve_lookup(self, signs, training):
         s = signs.numpy().view(np.uint64)
         self.last = s
-        rows = self.w.ps_lookup(0, s, np.full(s.size, self.dim, np.uint32), training).reshape(-1, self.dim)
-        return torch.from_numpy(self.o.f32_to_f16(rows).reshape(-1, self.dim))
+        real = s != self.NULL  # an owner-mode context skips the padding: no lookup, zero rows
+        rows = np.zeros((s.size, self.dim), np.float32)
+        rows[real] = self.w.ps_lookup(0, s[real], np.full(int(real.sum()), self.dim, np.uint32), training).reshape(-1, self.dim)
+        return torch.from_numpy(self.o.f32_to_f16(rows).view(np.float16).reshape(-1, self.dim))
+
+    # fixed-capacity framing (pb_frame_signs / pb_frame_rows restated in numpy)
+    def empty_rows(self, n, dtype=torch.float16):
+        return torch.zeros((n, self.dim), dtype=dtype)
+
+    def frame_signs(self, signs, perm, counts, Rn, cap, overflow):
+        x, pm, ct = signs.numpy().view(np.uint64), perm.numpy(), counts.numpy()
+        out = np.full(Rn * cap, self.NULL, np.uint64)
+        off = 0
+        for r in range(Rn):
+            k = min(int(ct[r]), cap)
+            out[r * cap:r * cap + k] = x[pm[off:off + k]]
+            if ct[r] > cap:
+                overflow[0] = 1
+            off += int(ct[r])
+        return torch.from_numpy(out.view(np.int64))
+
+    def frame_rows(self, src, perm, counts, Rn, cap, pack, out):
+        pm, ct = perm.numpy().astype(np.int64), counts.numpy()
+        off = 0
+        out.zero_()
+        for r in range(Rn):
+            k = min(int(ct[r]), cap)
+            idx = torch.from_numpy(pm[off:off + k])
+            if pack:
+                out[r * cap:r * cap + k] = src[idx]
+            else:
+                out[idx] = src[r * cap:r * cap + k]
+            off += int(ct[r])
+        return out
 
     def serve_update(self, grads, scale):
         # what the owner-side context does: one segment per sign, gradients summed in arrival order
@@ -65,6 +100,8 @@ class OracleBackend:
             g = g * np.float32(1.0 / scale)
         uniq, first = {}, []
         for k, s in enumerate(self.last.tolist()):
+            if s == int(self.NULL):
+                continue
             if s not in uniq:
                 uniq[s] = np.zeros(self.dim, np.float32)
                 first.append(s)
@@ -89,7 +126,7 @@ def _batches():
     return out
 
 
-def _run(rank, port, q):
+def _run(rank, port, q, static=False):
     import oracle
     from persia_b200.worker import ShardedEmbeddingWorker
 
@@ -98,11 +135,19 @@ def _run(rank, port, q):
         pf = [oracle.index_prefix(i) for i in range(S)]
         be = OracleBackend(oracle, DIM, oracle.Optim(oracle.SGD, lr=0.1, wd=0.0), rank)
         wk = ShardedEmbeddingWorker(S, DIM, pf, be)
+        if static:  # fixed-capacity frames, capacity calibrated on the batches (a collective)
+            sample = [torch.from_numpy(ids[rank].reshape(-1).view(np.int64)) for ids, _ in _batches()]
+            cap = wk.calibrate_cap(sample, B, margin=1.05, extra=2)
+            assert cap < S * B
+            wk.enable_static(B, cap=cap)
+        fwd, bwd = (wk.forward_static, wk.backward_static) if static else (wk.forward, wk.backward)
         outs = []
         for ids, g in _batches():
-            out = wk.forward(torch.from_numpy(ids[rank].reshape(-1).view(np.int64)), B, training=True)
+            out = fwd(torch.from_numpy(ids[rank].reshape(-1).view(np.int64)), B, training=True)
             outs.append(out.numpy().copy())
-            assert wk.backward(torch.from_numpy(g[rank]), scale=1.0)
+            assert bwd(torch.from_numpy(g[rank]), scale=1.0)
+        if static:
+            assert not wk.check_overflow()
         # dump this rank's shard
         probe = np.concatenate([oracle.add_prefix(np.arange(min(c, 400), dtype=np.uint64), 8, pf[i]) for i, c in enumerate(CARD)])
         mine = probe[oracle.shard_of(probe, R) == rank]
@@ -112,13 +157,14 @@ def _run(rank, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_worker_equals_global_batch_oracle():
+@pytest.mark.parametrize("static", [False, True])
+def test_sharded_worker_equals_global_batch_oracle(static):
     import oracle
 
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, port, q)) for r in range(R)]
+    procs = [ctx.Process(target=_run, args=(r, port, q, static)) for r in range(R)]
     for p in procs:
         p.start()
     res = {}
