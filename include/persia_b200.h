@@ -102,6 +102,14 @@ int pb_set_rows(pb_table* t, const uint64_t* d_signs, const float* d_entries, ui
 /* debug read-back of full entries (zeros + found=0 when absent); does not touch recency. */
 int pb_get_rows(pb_table* t, const uint64_t* d_signs, uint32_t n, float* d_entries, uint8_t* d_found, void* stream);
 
+/* Checkpoint support (persia-model-manager/src/lib.rs:242-257 dumps every internal shard's LRU list): the signs
+ * resident in the table and, per sign, the training-request number it was last used in (ascending = the
+ * reference's list order, oldest first, up to ties inside a request).  At most max_n pairs are written, in no
+ * particular order; *d_count receives the number of resident signs (call with max_n = 0 to size the buffers).
+ * Entries are then read with pb_get_rows and restored with pb_set_rows. */
+int pb_table_export_signs(pb_table* t, uint64_t* d_signs, uint32_t* d_recency, uint32_t max_n, uint32_t* d_count,
+                          void* stream);
+
 /* ---- id preprocessing (the EW's lookup_batched_all_slots_preprocess) --------------------------- */
 /* indices_add_prefix (embedding_worker_service/mod.rs:402-429): out[i] = ids[i] % spacing + prefix of
  * the slot owning occurrence i; h_slot_occ_off[n_slots+1] are the slot boundaries in the flat id array. */

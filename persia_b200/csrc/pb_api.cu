@@ -483,6 +483,20 @@ int pb_get_rows(pb_table* t, const uint64_t* d_signs, uint32_t n, float* d_entri
   return PB_OK;
 }
 
+int pb_table_export_signs(pb_table* t, uint64_t* d_signs, uint32_t* d_recency, uint32_t max_n, uint32_t* d_count,
+                          void* stream) {
+  if (!t || !d_count || (max_n && (!d_signs || !d_recency))) return fail(PB_ERR_INVALID, "null argument");
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!t->allocated) {
+    PB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), st));
+    return PB_OK;
+  }
+  launch_export_signs(t->d, d_signs, d_recency, max_n, d_count, st);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
 int pb_add_prefix(const uint64_t* d_ids, uint32_t n, const uint32_t* h_slot_occ_off, const uint64_t* h_prefix,
                   uint32_t n_slots, uint32_t prefix_bit, uint64_t* d_out, void* stream) {
   if (n && (!d_ids || !d_out)) return fail(PB_ERR_INVALID, "null argument");

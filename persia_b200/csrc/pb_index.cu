@@ -621,6 +621,31 @@ void launch_frame_rows(const void* src, const uint32_t* perm, const uint32_t* co
             lanes, pack, (uint4*)out);
 }
 
+// Checkpointing (persia-model-manager dump_internal_shard_embeddings, lib.rs:242-257): the resident signs and the
+// batch number each was last used in (the reference walks its LRU list; this is the same order up to ties inside
+// a batch).  Writes at most `max_n` pairs in index order; *count receives the number of resident signs.
+__global__ void __launch_bounds__(256) k_export_signs(TableDev t, uint64_t* __restrict__ signs,
+                                                      uint32_t* __restrict__ recency, uint32_t max_n,
+                                                      uint32_t* __restrict__ count) {
+  const uint64_t n = (uint64_t)t.n_cells + N_SPECIAL;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    Cell c = t.cells[i];
+    const bool occupied = (i < t.n_cells) ? (c.key < KEY_TOMB) : (c.key == 0ULL);
+    if (!occupied || c.row >= t.capacity) continue;
+    const uint32_t k = atomicAdd(count, 1u);
+    if (k < max_n) {
+      signs[k] = (i < t.n_cells) ? c.key : KEY_EMPTY - (i - t.n_cells);  // the three marker-valued signs
+      recency[k] = (uint32_t)(t.row_lead[c.row] >> 32);
+    }
+  }
+}
+
+void launch_export_signs(const TableDev& t, uint64_t* signs, uint32_t* recency, uint32_t max_n, uint32_t* count,
+                         cudaStream_t st) {
+  cudaMemsetAsync(count, 0, sizeof(uint32_t), st);
+  PB_LAUNCH(k_export_signs, 148 * 8, 256, 0, st, t, signs, recency, max_n, count);
+}
+
 void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, uint32_t keep, uint32_t* ev, cudaStream_t st) {
   PB_LAUNCH(k_evict_plan, 1, 256, 0, st, t, low_water, target_free, ev);
   PB_LAUNCH(k_evict_hist, 148 * 8, 256, 0, st, t, ev);

@@ -118,6 +118,8 @@ void launch_pack_signs(const uint64_t* signs, const uint32_t* perm, const uint32
                        uint64_t* out, uint32_t* overflow, cudaStream_t st);
 void launch_frame_rows(const void* src, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
                        uint32_t row_bytes, int pack, void* out, cudaStream_t st);
+void launch_export_signs(const TableDev& t, uint64_t* signs, uint32_t* recency, uint32_t max_n, uint32_t* count,
+                         cudaStream_t st);
 void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, uint32_t keep, uint32_t* ev, cudaStream_t st);
 void launch_p2p_exchange(const void* src, const uint64_t* peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
                          uint32_t row_bytes, cudaStream_t st);

@@ -60,6 +60,7 @@ SYMBOLS = {
     "pb_update": (_i32, [_vp, _vp, _vp, _u32, _vp]),
     "pb_set_rows": (_i32, [_vp, _vp, _vp, _u32, _vp]),
     "pb_get_rows": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp]),
+    "pb_table_export_signs": (_i32, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "pb_add_prefix": (_i32, [_vp, _u32, C.POINTER(_u32), C.POINTER(_u64), _u32, _u32, _vp, _vp]),
     "pb_shard_of": (_i32, [_vp, _u32, _u32, _vp, _vp]),
     "pb_farmhash64": (_i32, [_vp, _u32, _vp, _vp]),

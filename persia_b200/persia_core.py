@@ -9,8 +9,8 @@ in `sys.modules` as `persia_core`, after which the reference's own `persia` pack
 
 Scope of round 1: summation and raw slots (no hash-stack on raw slots), one process / one GPU (`replica_size == 1`; the sharded
 multi-GPU worker is persia_b200.worker), synchronous engines (the pipelining / staleness of
-forward.rs:470-780 is N1), `to_bytes()` is a private encoding (the speedy wire format is N4), `dump`/`load`
-of embedding checkpoints are N2 and raise.
+forward.rs:470-780 is N1), `to_bytes()` is a private encoding (the speedy wire format is N4); `dump`/`load`
+write and read the reference's `.emb` checkpoint files (persia_b200/checkpoint.py).
 """
 import os
 import pickle
@@ -713,11 +713,20 @@ class PersiaCommonContext:
         for g in _S.all_groups():
             g["shard"].clear()
 
-    def dump(self, dst_dir):
-        raise RuntimeError("embedding checkpoint dump is not built yet (SURVEY.md N2)")
+    def dump(self, dst_dir):  # lib.rs:356-366 -> PS dump (mod.rs:453-458): the reference's .emb files
+        from . import checkpoint as CK
 
-    def load(self, src_dir):
-        raise RuntimeError("embedding checkpoint load is not built yet (SURVEY.md N2)")
+        _S.ensure_config()
+        CK.dump_shards(dst_dir, [g["shard"] for g in _S.all_groups()])
+
+    def load(self, src_dir):  # lib.rs:368-378 -> PS load (mod.rs:460-466)
+        from . import checkpoint as CK
+
+        _S.ensure_config()
+        if _S.optimizer is None:
+            raise RuntimeError("optimizer not registered: the entry layout (embedding ++ state) is unknown")
+        dims = sorted({s.dim for s in _S.slots})
+        CK.load_shards(src_dir, {d: _S.group(d)["shard"] for d in dims})
 
     def wait_for_serving(self):
         return None

@@ -109,6 +109,22 @@ class EmbeddingShard:
         N.check(self.lib.pb_get_rows(self.h, _ptr(signs), n, _ptr(ent), _ptr(found), _stream(self.device)))
         return ent, found.bool()
 
+    def export_signs(self):
+        """Resident signs (int64 bit patterns) and the training-request number each was last used in, on the device,
+        sorted oldest first (ties by sign): the order the reference's LRU list is dumped in."""
+        count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        N.check(self.lib.pb_table_export_signs(self.h, None, None, 0, _ptr(count), _stream(self.device)))
+        n = int(count)
+        signs = torch.empty(n, dtype=torch.int64, device=self.device)
+        rec = torch.empty(n, dtype=torch.int32, device=self.device)
+        if n:
+            N.check(self.lib.pb_table_export_signs(self.h, _ptr(signs), _ptr(rec), n, _ptr(count), _stream(self.device)))
+            assert int(count) == n, "the table changed during the export"
+            order = torch.argsort(signs, stable=True)           # deterministic file: by sign ...
+            order = order[torch.argsort(rec[order].to(torch.int64) & 0xFFFFFFFF, stable=True)]  # ... inside a request
+            signs, rec = signs[order], rec[order]
+        return signs, rec
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.pb_table_destroy(self.h)
