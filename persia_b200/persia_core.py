@@ -8,8 +8,8 @@ the raw device pointers `GradientBatch.add_gradient` receives.  `install()` regi
 in `sys.modules` as `persia_core`, after which the reference's own `persia` package runs unchanged on top.
 
 Scope of round 1: summation and raw slots (no hash-stack on raw slots), one process / one GPU (`replica_size == 1`; the sharded
-multi-GPU worker is persia_b200.worker), synchronous engines (the pipelining / staleness of
-forward.rs:470-780 is N1), `to_bytes()` is a private encoding (the speedy wire format is N4); `dump`/`load`
+multi-GPU worker is persia_b200.worker); `Forward` prefetches on worker threads with the reference's ordering and
+staleness rules (persia_b200/engine.py), `Backward` applies updates in the caller's thread; `to_bytes()` is a private encoding (the speedy wire format is N4); `dump`/`load`
 write and read the reference's `.emb` checkpoint files (persia_b200/checkpoint.py).
 """
 import os
@@ -382,7 +382,15 @@ def _flatten(feats, batch):
     return ids, row_off, slot_off
 
 
+_GPU_LOCK = threading.RLock()  # the C library keeps per-table host state: one caller at a time
+
+
 def _forward(batch, device_id, training):
+    with _GPU_LOCK:
+        return _forward_locked(batch, device_id, training)
+
+
+def _forward_locked(batch, device_id, training):
     import torch
 
     from . import shard as SH
@@ -473,6 +481,12 @@ def _forward(batch, device_id, training):
 class PersiaTrainingBatch:  # forward.rs:256-306, #[pyclass(dict)]: python attaches attributes to it
     def __init__(self, non_id, emb, labels, meta, pending):
         self._non_id, self._emb, self._labels, self._meta, self._pending = non_id, emb, labels, meta, pending
+        self._permit = None  # embedding staleness permit (forward.rs:316): moves into the gradient batch
+
+    def __del__(self):  # a batch dropped without an update gives its permit back, like the Rust Drop
+        permit = getattr(self, "_permit", None)
+        if permit is not None:
+            permit.release()
 
     def embedding_worker_addr(self):
         return "local"
@@ -494,7 +508,9 @@ class PersiaTrainingBatch:  # forward.rs:256-306, #[pyclass(dict)]: python attac
 
     def create_gradient_batch(self):
         p, self._pending = self._pending, None
-        return GradientBatch(p)
+        gb = GradientBatch(p)
+        gb._permit, self._permit = self._permit, None  # forward.rs:299-305
+        return gb
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -504,6 +520,7 @@ class GradientBatch:  # backward.rs:60-106
     def __init__(self, pending):
         self._pending = pending
         self._grads = {}
+        self._permit = None
 
     def add_skipped_gradient(self, slot_name):
         self._grads[slot_name] = None
@@ -524,8 +541,12 @@ class Backward:  # backward.rs:357-405
 
     def update_id_type_feature_gradient_batched(self, gradients):
         p, gradients._pending = gradients._pending, None
+        permit, gradients._permit = gradients._permit, None
         if p is None:
+            if permit is not None:
+                permit.release()
             raise RuntimeError("cannot find gradient batch")
+        _GPU_LOCK.acquire()
         try:
             for g, ctx, names, is_raw in p.parts:
                 if is_raw:  # [U, dim] gradient of the distinct-sign table (persia/ctx.py:970-980)
@@ -552,6 +573,9 @@ class Backward:  # backward.rs:357-405
                 ctx.backward_ptrs(g["shard"], ptrs, bool(f16), scales)
         finally:
             p.release()
+            _GPU_LOCK.release()
+            if permit is not None:  # the update is enqueued: the batch no longer counts as in flight (backward.rs:341-343)
+                permit.release()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -644,33 +668,32 @@ class PersiaMessageQueueClient:
 # ---------------------------------------------------------------------------------------------------------
 # forward.Forward (forward.rs:833-907): input channel -> lookup -> training batch
 # ---------------------------------------------------------------------------------------------------------
-class Forward:
+class Forward:  # forward.rs:833-907 over persia_b200.engine.ForwardEngine (reorder, prefetch, staleness permits)
     def __init__(self, forward_buffer_size, reproducible, embedding_staleness=None):
+        from .engine import ForwardEngine
+
         self.forward_buffer_size, self.reproducible, self.embedding_staleness = forward_buffer_size, reproducible, embedding_staleness
-        self._input = None
-        self._launched = False
+
+        def lookup(batch, permit):
+            tb = _forward(batch, _S.device_id, training=True)
+            tb._permit = permit
+            return tb
+
+        self._engine = ForwardEngine(lookup, forward_buffer_size, reproducible, embedding_staleness,
+                                     world_size=max(1, _S.replica_size or 1), rank=_S.replica_index or 0)
+        self._engine.is_remote_ref = lambda b: b.embedding_tensor is not None and b.embedding_tensor[0] == "ref"
 
     def set_input_channel(self, receiver):
-        if self._input is not None:
-            raise RuntimeError("do not set input channel again")
-        self._input = receiver._q
+        self._engine.set_input(receiver._q)
 
     def launch(self, num_workers):
-        if self._input is None:
-            raise RuntimeError("please set input channel before launch")
-        self._launched = True
+        self._engine.launch(num_workers)
 
     def shutdown(self):
-        self._launched = False
+        self._engine.shutdown()
 
     def get_batch(self, timeout_ms):
-        if not self._launched:
-            raise RuntimeError("forward engine is not launched")
-        try:
-            batch = self._input.get(timeout=max(timeout_ms, 1) / 1000.0)
-        except queue.Empty:
-            raise TimeoutError("get train batch timed out")
-        return _forward(batch, _S.device_id, training=True)
+        return self._engine.get_batch(timeout_ms)
 
 
 # ---------------------------------------------------------------------------------------------------------
