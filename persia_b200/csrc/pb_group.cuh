@@ -102,8 +102,8 @@ __device__ __forceinline__ void radix_hist_body(uint32_t vb, SRC src, uint32_t n
   }
 }
 
-// One scatter pass.  A block owns one tile; inside a 1024-key sub-tile warp w owns 128 consecutive keys
-// (4 rounds of 32, kept in registers).  Phase 1: every warp counts its own digits (warp-private shared
+// One scatter pass.  A block owns one tile; inside a 512-key sub-tile warp w owns 64 consecutive keys
+// (2 rounds of 32, kept in registers).  Phase 1: every warp counts its own digits (warp-private shared
 // counters, __match_any_sync per round).  Phase 2: one sweep turns the counters into each warp's first
 // output slot per bin.  Phase 3: every warp walks its keys again in order and writes them out, bumping
 // its private cursors.  Two block barriers per sub-tile.

@@ -55,7 +55,7 @@ __device__ __noinline__ void init_row(const TableDev& t, const HyperDev& hy, con
 // is read from the cell by the kernels that follow, so nothing here ever waits on another thread.
 // The group that admits a sign also initialises its row (emb_entry.rs:28-68 + optim.rs:299-302).
 // Recency (get_refresh, eviction_map.rs:48-60) is not written here: thousands of occurrences of one hot
-// sign would all store to the same cell; the gather kernel records it per row after a block-level dedup.
+// sign would all store to the same cell; k_elect_leaders records it per row after a block-level dedup.
 // Invariant that makes "an empty cell in the bucket => the sign is absent" true: a sign is stored no later
 // in its probe sequence than the first bucket that had an EMPTY cell when it was admitted, and a cell never
 // returns to EMPTY: eviction leaves a tombstone, which lookups walk past and admissions reuse (after having

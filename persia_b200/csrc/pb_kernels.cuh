@@ -27,7 +27,7 @@ struct GradsDev {
   uint8_t pow_idx[PB_MAX_SLOTS];  // the slot's pair
 };
 
-// arguments of the backward segment kernels (see pb_kernels.cu)
+// arguments of the backward segment kernels (see pb_update.cu)
 struct SegArgs {
   const uint32_t* skey;        // first occurrence of the occurrence's sign (n = no storage), sorted
   const uint32_t* occ_row;     // row number of every occurrence (ROW_NONE = no storage)

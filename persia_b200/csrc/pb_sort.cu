@@ -47,7 +47,7 @@ __global__ void k_counts_from_hist(const uint32_t* __restrict__ hist, uint32_t n
 // launchers (host)
 // ------------------------------------------------------------------------------------------------
 uint32_t radix_tile(uint32_t n) {
-  // tiles are multiples of the 1024-key sub-tile; at most 256 of them so that folding the block-major
+  // tiles are multiples of the 512-key sub-tile; at most 256 of them so that folding the block-major
   // histogram inside every scatter block stays cheap
   uint32_t tile = RS_SUB;
   while (cdiv(n, tile) > RS_MAX_TILES) tile += RS_SUB;

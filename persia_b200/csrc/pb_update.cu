@@ -188,9 +188,9 @@ __global__ void k_slot_status(GradsDev gr, uint32_t n_slots, const uint32_t* __r
 //   in one piece (the vast majority) is summed in reference order and the optimizer step + weight bound
 //   are applied with the reduced gradient still in registers: bit-exact w.r.t. the reference order.
 //   Other pieces store their partial sum (<= 2 per PIECE-block).
-// k_combine_update — one group per PIECE boundary; the group on the first boundary of a multi-piece
-//   segment adds the partials in position order and performs the step.  Deterministic, but the f32
-//   association differs from the reference's strictly sequential sum (documented tolerance); piece == 0
+// k_combine_update — one block per cut segment (owner record): its lane groups add contiguous ranges of the
+//   segment's partial sums in position order, group 0 adds the range sums and performs the step.  Deterministic, but
+//   the f32 association differs from the reference's strictly sequential sum (documented tolerance); piece == 0
 //   ("strict") disables cutting and restores the sequential order for any length.
 // k_update_shared — only when two slots of one feature group can hold the same sign: such a sign gets
 //   one step per slot, sequentially in slot order (mod.rs:720-822); one group walks the whole run.
