@@ -81,3 +81,103 @@ def test_done_marker_yaml():
     info = yaml.safe_load(CK.done_yaml(2, 128, now=1700000000.25))
     assert info == {"num_shards": 2, "num_internal_shards": 128,
                     "datetime": {"secs_since_epoch": 1700000000, "nanos_since_epoch": 250000000}}
+
+
+class _ListModel:
+    """ArrayLinkedList as the reference implements it (array_linked_list.rs:215-330, 422-520): 1-based node indices,
+    0 = none, a free list threaded through `next_index` of unused nodes."""
+
+    def __init__(self, capacity):
+        self.count, self.first, self.last, self.free, self.end = 0, 0, 0, 0, 0
+        self.nodes = []  # [next, prev, data]
+        if capacity:  # fill_elements
+            for i in range(1, capacity):
+                self.nodes.append([i + 1, 0, None])
+            self.nodes.append([0, 0, None])
+            self.free, self.end = 1, capacity
+
+    def _take(self, node):
+        if self.free == 0:
+            self.nodes.append(node)
+            return len(self.nodes)
+        idx = self.free
+        self.free = self.nodes[idx - 1][0]
+        self.nodes[idx - 1] = node
+        return idx
+
+    def push_back(self, data):
+        idx = self._take([0, self.last, data])
+        if self.last:
+            self.nodes[self.last - 1][0] = idx
+        else:
+            self.first = idx
+        self.last = idx
+        self.count += 1
+        return idx
+
+    def push_front(self, data):
+        idx = self._take([self.first, 0, data])
+        if self.first:
+            self.nodes[self.first - 1][1] = idx
+        else:
+            self.last = idx
+        self.first = idx
+        self.count += 1
+        return idx
+
+    def remove(self, idx):
+        nxt, prv, data = self.nodes[idx - 1]
+        if prv:
+            self.nodes[prv - 1][0] = nxt
+        else:
+            self.first = nxt
+        if nxt:
+            self.nodes[nxt - 1][1] = prv
+        else:
+            self.last = prv
+        self.nodes[idx - 1] = [self.free, 0, None]  # back on the free list
+        self.free = idx
+        self.count -= 1
+        return data
+
+    def order(self):
+        out, cur = [], self.first
+        while cur:
+            out.append(self.nodes[cur - 1][2])
+            cur = self.nodes[cur - 1][0]
+        return out
+
+    def to_bytes(self):
+        buf = struct.pack("<QIIII", self.count, self.first, self.last, self.free, self.end) + struct.pack("<I", len(self.nodes))
+        for nxt, prv, data in self.nodes:
+            buf += struct.pack("<IIB", nxt, prv, 1 if data is not None else 0)
+            if data is not None:
+                buf += _entry(*data)
+        return buf
+
+
+@pytest.mark.parametrize("seed,capacity", [(0, 0), (1, 8), (2, 50), (3, 200)])
+def test_decoder_follows_any_list_the_reference_can_produce(seed, capacity):
+    """An LRU holder's life — inserts at the back, refreshes (remove + push_back), evictions from the front, the odd
+    push_front — replayed on a model of the reference's list, serialised node by node, decoded, compared."""
+    rng = np.random.default_rng(seed)
+    m, where, next_sign = _ListModel(capacity), {}, 1
+    for _ in range(600):
+        r = rng.random()
+        if r < 0.45 or not where:
+            inner = rng.standard_normal(int(rng.integers(1, 6))).astype(np.float32).tolist()
+            data = (inner, int(rng.integers(1, 4)), next_sign)
+            where[next_sign] = m.push_back(data) if rng.random() < 0.9 else m.push_front(data)
+            next_sign += 1
+        elif r < 0.8:  # get_refresh: move to the back (eviction_map.rs:48-60)
+            sign = int(rng.choice(list(where)))
+            where[sign] = m.push_back(m.remove(where[sign]))
+        else:  # evict the least recently used (eviction_map.rs:76-97)
+            data = m.remove(m.first)
+            del where[data[2]]
+    want = m.order()
+    signs, dims, entries = CK.decode_list(m.to_bytes())
+    assert signs.tolist() == [d[2] for d in want]
+    assert dims.tolist() == [d[1] for d in want]
+    for e, d in zip(entries, want):
+        assert e.tolist() == d[0]
