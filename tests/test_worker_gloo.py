@@ -116,7 +116,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _batches():
+def _batches(R=R):
     rng = np.random.default_rng(77)
     out = []
     for _ in range(STEPS):
@@ -126,7 +126,7 @@ def _batches():
     return out
 
 
-def _run(rank, port, q, static=False):
+def _run(rank, port, q, static=False, R=R):
     import oracle
     from persia_b200.worker import ShardedEmbeddingWorker
 
@@ -136,13 +136,13 @@ def _run(rank, port, q, static=False):
         be = OracleBackend(oracle, DIM, oracle.Optim(oracle.SGD, lr=0.1, wd=0.0), rank)
         wk = ShardedEmbeddingWorker(S, DIM, pf, be)
         if static:  # fixed-capacity frames, capacity calibrated on the batches (a collective)
-            sample = [torch.from_numpy(ids[rank].reshape(-1).view(np.int64)) for ids, _ in _batches()]
+            sample = [torch.from_numpy(ids[rank].reshape(-1).view(np.int64)) for ids, _ in _batches(R)]
             cap = wk.calibrate_cap(sample, B, margin=1.05, extra=2)
             assert cap < S * B
             wk.enable_static(B, cap=cap)
         fwd, bwd = (wk.forward_static, wk.backward_static) if static else (wk.forward, wk.backward)
         outs = []
-        for ids, g in _batches():
+        for ids, g in _batches(R):
             out = fwd(torch.from_numpy(ids[rank].reshape(-1).view(np.int64)), B, training=True)
             outs.append(out.numpy().copy())
             assert bwd(torch.from_numpy(g[rank]), scale=1.0)
@@ -157,14 +157,14 @@ def _run(rank, port, q, static=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("static", [False, True])
-def test_sharded_worker_equals_global_batch_oracle(static):
+@pytest.mark.parametrize("static,R", [(False, 2), (True, 2), (True, 3)])
+def test_sharded_worker_equals_global_batch_oracle(static, R):
     import oracle
 
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, port, q, static)) for r in range(R)]
+    procs = [ctx.Process(target=_run, args=(r, port, q, static, R)) for r in range(R)]
     for p in procs:
         p.start()
     res = {}
@@ -181,7 +181,7 @@ def test_sharded_worker_equals_global_batch_oracle(static):
     w.configure()
     w.set_optimizer(oracle.Optim(oracle.SGD, lr=0.1, wd=0.0))
     GB = R * B
-    for step, (ids, g) in enumerate(_batches()):
+    for step, (ids, g) in enumerate(_batches(R)):
         gid = np.concatenate([ids[:, s, :].reshape(-1) for s in range(S)])  # slot-major, rank-major samples
         want, octx = w.forward(gid, np.arange(S * GB + 1, dtype=np.uint32), GB, training=True)
         for r in range(R):
