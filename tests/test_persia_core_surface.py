@@ -128,3 +128,30 @@ def test_farmhash_numpy_matches_golden(pc):
     slot = SlotConfig("t", 32, hash_stack_rounds=2, hash_stack_embedding_size=10)
     got = _hashstack(ids, slot)  # the reference's own test vector (mod.rs:1570-1613)
     assert [g.tolist() for g in got] == [list(v) for v in fx["hashstack_rounds2_size10"].values()]
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "test", "embedding", "test_data.py")),
+                    reason="reference checkout not present")
+def test_reference_own_test_file_passes_unmodified(tmp_path):
+    """The reference's test/embedding/test_data.py, run by pytest as it stands in /root/reference, with this repo's
+    persia_core registered in place of the Rust extension (a subprocess: clean module state, cwd outside both trees)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prelude = (
+        "import sys, types, logging\n"
+        "try:\n"
+        "    import colorlog\n"
+        "except ImportError:\n"  # the reference's logger wants colorlog; give it a plain formatter
+        "    m = types.ModuleType('colorlog')\n"
+        "    m.ColoredFormatter = lambda fmt=None, *a, **k: logging.Formatter('%(levelname)s %(message)s')\n"
+        "    sys.modules['colorlog'] = m\n"
+        "from persia_b200 import persia_core\n"
+        "persia_core.install()\n"
+        "import pytest\n"
+        f"sys.exit(pytest.main(['-q', '-p', 'no:cacheprovider', {os.path.join(REF, 'test', 'embedding', 'test_data.py')!r}]))\n"
+    )
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, REF]), PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-c", prelude], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "5 passed" in r.stdout
