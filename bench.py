@@ -251,7 +251,6 @@ def single_gpu(args, torch, lib):
     sh.set_optimizer(N.OPT_ADAGRAD, lr=0.01, initialization=0.01, eps=1e-10)
     sh.configure()
     ctx = SH.BatchContext(n_occ, n_occ, pf, device=dev)
-    ctx.set_async_grouping(not args.sync_grouping)
 
     # ---- make every row resident (the reference's "warm table"): admit all ids of every slot
     t_fill = time.time()
@@ -330,7 +329,7 @@ def single_gpu(args, torch, lib):
         clocks = sampler.stop(t0, t1)
 
         # ---- per-kernel durations (CUDA events on the launching stream), separate instrumented pass
-        fam_names = ["probe_admit", "combine_update", "gather_pool", "nan_scan", "grouping", "reduce_update", "other"]
+        fam_names = ["probe_items", "dedup", "gather_pool", "nan_scan", "reduce_hot", "reduce_items", "other"]
         n_prof = min(K, 50)
 
         def profiled(mask):
@@ -398,7 +397,7 @@ def single_gpu(args, torch, lib):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    ku = kern_alone.get("reduce_update", {}).get("us_per_step")
+    ku = kern_alone.get("reduce_items", {}).get("us_per_step")
     upd_bytes = n_occ * W.algorithmic_bytes_per_id(dim, state, "backward")
     achieved = upd_bytes / (ku * 1e-6) / 1e9 if ku else None
     traffic = None

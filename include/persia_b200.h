@@ -82,10 +82,11 @@ int pb_table_clear(pb_table* t, void* stream);
 int pb_table_set_eviction(pb_table* t, uint32_t check_every, uint64_t low_water, uint64_t target_free, uint32_t keep_batches);
 /* floats per resident row: dim + optimizer state (emb_entry.rs:17-25 `inner`). */
 int pb_table_entry_len(pb_table* t, uint32_t* h_out);
-/* counters since creation / clear: [0] resident rows (admitted - evicted), [1] lookups that missed (infer) or were not admitted,
- * [2] gradient ids not found (gradient_id_miss_count), [3] admissions refused because the shard is full.
- * Synchronises `stream`. */
-int pb_table_counters(pb_table* t, uint64_t h_out[4], void* stream);
+/* counters since creation / clear: [0] resident rows (admitted - evicted), [1] distinct signs of a request that missed
+ * (infer) or were not admitted (index_miss_count), [2] gradient ids not found (gradient_id_miss_count), [3] admissions
+ * refused because the shard is full, [4] in-kernel waits that gave up (must stay 0: a non-zero value voids the batch
+ * that raised it).  Synchronises `stream`. */
+int pb_table_counters(pb_table* t, uint64_t h_out[5], void* stream);
 
 /* ---- single-request entry points (the PS RPCs) ------------------------------------------------- */
 /* lookup_mixed -> batched_lookup (embedding_parameter_service/mod.rs:162-262, 344-357).
@@ -138,55 +139,14 @@ typedef struct {
 int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, pb_ctx** out);
 int pb_ctx_destroy(pb_ctx* c);
 int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg);
-/* Gradient reduction order of pb_backward.  Default (0): a sign repeated more than 32 times in one slot of a
- * batch is reduced piecewise (deterministic, f32 association differs from the reference's sequential sum);
- * on (1): strictly sequential in occurrence order for any multiplicity, bit-identical to
- * embedding_worker_service/mod.rs:799-811, slower on tiny-cardinality slots. */
-int pb_ctx_set_strict_reduce(pb_ctx* c, int on);
-
-/* Where the gradient-independent half of the backward pass (leader election, radix grouping, piece heads) runs.
- * 0 (default): inside pb_backward, on the caller's stream.  1: pb_forward(training) forks it onto the context's
- * own stream right after the index probe, so it overlaps the row gather and everything the caller enqueues
- * between forward and backward (the dense tower); pb_backward joins it.  When capturing into a CUDA graph the
- * forward and the backward of a batch must then be part of the same capture. */
-int pb_ctx_set_async_grouping(pb_ctx* c, int on);
-
-/* A context in owner mode serves the already-sharded requests of the multi-GPU exchange (the PS side of
- * lookup_mixed / update_gradient_mixed): `batch` is then just the number of signs received and the u16
- * sample-index limit of a PersiaBatch does not apply. */
-int pb_ctx_set_owner_mode(pb_ctx* c, int on);
-
-/* The EW's regrouping around the fan-out (embedding_worker_service/mod.rs:886-919): out[i] = src[perm[i]]. */
-int pb_permute_u64(const uint64_t* d_src, const uint32_t* d_perm, uint32_t n, uint64_t* d_out, void* stream);
-/* Rows of row_bytes (multiple of 16): scatter == 0: out[i] = src[perm[i]]; scatter != 0: out[perm[i]] = src[i]. */
-int pb_permute_rows(const void* d_src, const uint32_t* d_perm, uint32_t n, uint32_t row_bytes, int scatter, void* d_out,
-                    void* stream);
-
-/* Fixed-capacity framing of the shard exchange (static shapes: no split sizes on the host, CUDA-graph capturable).
- * Every (source, destination) pair owns `cap` slots: framed[r*cap + k] = signs[perm[off_r + k]] for k < counts[r],
- * PB_NULL_SIGN (0xFFFFFFFFFFFFFFFE) otherwise; an owner-mode context skips those.  *d_overflow is set to 1 when a
- * count exceeds cap (the caller checks it at its own pace and re-runs the batch with a larger cap). */
-int pb_frame_signs(const uint64_t* d_signs, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
-                   uint64_t* d_out, uint32_t* d_overflow, void* stream);
-/* pack != 0: framed rows from batch-order rows (zero rows in the padding); pack == 0: the inverse (framed -> batch order). */
-int pb_frame_rows(const void* d_src, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
-                  uint32_t row_bytes, int pack, void* d_out, void* stream);
-
-/* The same exchange over NVLink peer memory instead of NCCL (at most 16 GPUs of one box).  h_peer_ptrs[q] is the
- * device address, mapped in this process, of rank q's receive buffer ([R*cap] rows); segment q of d_framed is stored
- * into it at slot my_rank.  pb_p2p_barrier then orders the step across the ranks: h_flag_ptrs[q] addresses rank q's
- * 16 flag words, *d_epoch counts barriers on the device (CUDA-graph safe); *d_err is raised instead of spinning
- * forever when a peer does not arrive. */
-int pb_p2p_exchange(const void* d_framed, const uint64_t* h_peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
-                    uint32_t row_bytes, void* stream);
-int pb_p2p_barrier(const uint64_t* h_flag_ptrs, uint32_t* d_epoch, uint32_t R, uint32_t my_rank, uint32_t* d_err, void* stream);
-
 /* EmbeddingWorker::forward_batched_direct for summation slots
  * (embedding_worker_service/mod.rs:1076-1107 -> :874-942 -> PS :162-262 -> :486-629).
  * d_ids: flat raw ids, slot-major then sample-major; d_row_off[n_slots*batch+1] CSR offsets, or NULL
  * when every sample holds exactly one id per slot (then n_occ == n_slots*batch).
  * h_slot_occ_off[n_slots+1]: slot boundaries in d_ids.  d_out: n_slots*batch rows of `dim` f16
- * (slot s, sample b at row s*batch+b).  training!=0 keeps the deduplicated ids in `c` for pb_backward. */
+ * (slot s, sample b at row s*batch+b).  training!=0 keeps the deduplicated ids in `c` for pb_backward.
+ * Inside: FeatureBatch::new (persia-common/src/lib.rs:45-82) as a device-side per-slot dedup, then the lookup over the
+ * distinct signs only, then pooling.  Capturable in a CUDA graph on its own. */
 int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
                const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream);
 
@@ -194,7 +154,10 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
  * PS :359-427).  h_grads[s]: device pointer to slot s's [batch, dim] gradient (GradientBatch::add_gradient,
  * persia-core/src/backward.rs:86-105), NULL = add_skipped_gradient; is_f16 as there; h_scale[s] the loss
  * scale.  A slot whose gradient holds a NaN is skipped whole (:731-746); d_slot_status[n_slots] (optional)
- * receives 0 applied / 1 skipped / 2 NaN. */
+ * receives 0 applied / 1 skipped / 2 NaN.  The gradients of a sign are summed in the reference's order (ascending
+ * sample) whatever its multiplicity, so updated rows are bit-identical to the reference's f32 arithmetic.  Part of the
+ * work runs on a stream owned by the context and is joined before the call returns control of `stream`'s order
+ * (capturable in a CUDA graph on its own). */
 int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, const float* h_scale,
                 int32_t* d_slot_status, void* stream);
 
@@ -222,8 +185,8 @@ int pb_backward_raw(pb_table* t, pb_ctx* c, const void* d_grad, int is_f16, floa
 uint64_t pb_launch_count(void);
 /* Bench instrumentation: launches of the kernel families selected by the bit mask are bracketed by CUDA events on
  * their stream (0 = off).  pb_profile_read synchronises the device and returns summed milliseconds and launch
- * counts per family: 0 probe/admit, 1 combine (cut segments), 2 gather+pool, 3 NaN scan, 4 grouping (election,
- * radix passes, piece heads), 5 reduce+update, 6 other. */
+ * counts per family: 0 probe/admit, 1 dedup, 2 gather+pool, 3 NaN scan, 4 reduce+update of hot signs (bulk-copy ring),
+ * 5 reduce+update of the other signs, 6 other. */
 #define PB_PROFILE_FAMILIES 7
 int pb_profile_enable(int family_mask);
 int pb_profile_read(double* h_ms, uint64_t* h_count, int n_families);

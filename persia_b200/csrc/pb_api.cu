@@ -84,6 +84,7 @@ struct pb_table {
   uint32_t evict_every = 0, evict_low = 0, evict_target = 0, evict_keep = 2;
   uint32_t train_calls = 0;
   uint32_t* evict_ws = nullptr;
+  uint32_t pending_batches = 0;  // training forwards whose backward has not been enqueued yet
 };
 
 struct pb_ctx {
@@ -91,9 +92,11 @@ struct pb_ctx {
   uint32_t max_occ = 0, max_out = 0;
   pb_slots_cfg slots{};
   bool has_slots = false;
-  // forward -> backward state (the EW's post_forward_buffer entry, mod.rs:1087-1098)
-  uint32_t* occ_cell = nullptr;
-  uint32_t* occ_row = nullptr;
+  // forward -> backward state (the EW's post_forward_buffer entry, mod.rs:1087-1098): the batch's distinct signs,
+  // where each lives, the occurrence lists and the work lists of the backward (pb_kernels.cuh BatchDev)
+  BatchDev b{};
+  size_t set_cells = 0;
+  bool set_dirty = false;  // the scratch set still holds the last batch's cells
   uint32_t* occ_outrow = nullptr;
   uint32_t* row_off = nullptr;
   bool multi_id = false;
@@ -101,25 +104,18 @@ struct pb_ctx {
   uint32_t* dev_tick = nullptr;  // request number of the pending forward (device side, CUDA-graph safe)
   uint32_t occ_off[PB_MAX_SLOTS + 1];
   bool pending = false;
+  pb_table* pending_table = nullptr;  // the table whose rows the pending batch refers to (eviction spares them)
+  // slots of one feature group take turns in the backward (mod.rs:720-822): round of every slot
+  uint32_t n_rounds = 1;
+  uint8_t round_of[PB_MAX_SLOTS];
   // backward workspace
-  uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *hist = nullptr;
   uint32_t* nan_tick = nullptr;
   float* vw_stage = nullptr;
   size_t vw_stage_floats = 0;
-  uint4* heads = nullptr;       // compacted piece heads of the sorted occurrence list
-  uint2* owners = nullptr;      // (first boundary, segment start) of cut segments
-  uint32_t* seg_counts = nullptr;
-  float* partials = nullptr;  // 2 rows per PIECE-block of the sorted occurrence list
-  size_t partials_floats = 0;
-  bool strict_reduce = false;
-  bool owner_mode = false;  // serves already-sharded requests: no u16 sample-index limit
-  bool async_grouping = false;  // group occurrences on the side stream during the forward call
-  bool grouped = false;         // the pending batch's grouping has been enqueued
-  int sorted_in = 0;            // buffer pair holding the sorted list (0 = a, 1 = b)
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool shared_groups = false;  // two slots carry the same non-zero prefix (one feature group)
+  cudaStream_t side = nullptr;  // hot items + scratch-set clearing run beside the main stream during pb_backward
+  cudaEvent_t ev_fork = nullptr, ev_nan = nullptr, ev_join = nullptr;
   // raw slot (pb_forward_raw / pb_backward_raw): allocated on first use
+  uint32_t* occ_cell = nullptr;
   RawWork raw{};
   bool raw_ready = false, raw_pending = false;
   float* raw_stage = nullptr;
@@ -154,8 +150,8 @@ int ensure_alloc(pb_table* t) {
   PB_CUDA(cudaMalloc(&d.cells, sizeof(Cell) * ((size_t)d.n_cells + N_SPECIAL)));
   PB_CUDA(cudaMalloc(&d.rows, sizeof(float) * (size_t)d.capacity * d.stride));
   PB_CUDA(cudaMalloc(&d.counters, sizeof(uint32_t) * CTR_COUNT));
-  PB_CUDA(cudaMalloc(&d.row_lead, sizeof(unsigned long long) * (size_t)d.capacity));
-  PB_CUDA(cudaMemset(d.row_lead, 0, sizeof(unsigned long long) * (size_t)d.capacity));
+  PB_CUDA(cudaMalloc(&d.row_tick, sizeof(uint32_t) * (size_t)d.capacity));
+  PB_CUDA(cudaMemset(d.row_tick, 0, sizeof(uint32_t) * (size_t)d.capacity));
   PB_CUDA(cudaMemset(d.counters, 0, sizeof(uint32_t) * CTR_COUNT));
   launch_fill_cells(d.cells, (uint64_t)d.n_cells + N_SPECIAL, 0);
   d.free_rows = nullptr;
@@ -182,7 +178,10 @@ int maybe_evict(pb_table* t, cudaStream_t st) {
     PB_CUDA(cudaMalloc(&t->d.free_rows, sizeof(uint32_t) * (size_t)t->d.capacity));
     PB_CUDA(cudaMalloc(&t->evict_ws, sizeof(uint32_t) * (3 + 1024)));
   }
-  launch_evict(t->d, t->evict_low, t->evict_target, t->evict_keep, t->evict_ws, st);
+  // rows of batches whose gradients are still to come are never released: a row used by a pending batch was
+  // refreshed by its forward, i.e. at most `pending_batches` requests ago
+  const uint32_t keep = t->evict_keep > t->pending_batches + 1 ? t->evict_keep : t->pending_batches + 1;
+  launch_evict(t->d, t->evict_low, t->evict_target, keep, t->evict_ws, st);
   return PB_OK;
 }
 
@@ -228,35 +227,10 @@ int make_slots(const pb_slots_cfg& cfg, const uint32_t* h_occ_off, SlotsDev& s) 
   return PB_OK;
 }
 
-// SegArgs of the pending batch (sorted list in the pair `sorted_in`)
-SegArgs seg_args(pb_table* t, pb_ctx* c, float* vw) {
-  SegArgs a;
-  a.skey = c->sorted_in == 0 ? c->keys_a : c->keys_b;
-  a.sval = c->sorted_in == 0 ? c->vals_a : c->vals_b;
-  a.occ_row = c->occ_row;
-  a.occ_outrow = c->multi_id ? c->occ_outrow : nullptr;
-  a.row_off = c->multi_id ? c->row_off : nullptr;
-  a.tick_ptr = c->dev_tick;
-  a.nan_tick = c->nan_tick;
-  a.vw_stage = vw;
-  a.n = c->n_occ;
-  a.batch = c->batch;
-  a.piece = c->strict_reduce ? 0 : PB_PIECE;
-  a.shared_groups = c->shared_groups ? 1 : 0;
-  a.quiet_miss = c->owner_mode ? 1 : 0;  // framed exchanges pad with null signs: not gradient-id misses
-  a.partials = c->partials;
-  return a;
-}
-
-// The gradient-independent half of the backward pass: elect per-sign leaders, sort the occurrences by
-// leader, mark piece heads.  Runs on `st` (the caller's stream, or the context's side stream).
-void group_occurrences(pb_table* t, pb_ctx* c, const SlotsDev& sl, cudaStream_t st) {
-  launch_elect(t->d, c->occ_cell, c->n_occ, c->occ_row, c->hist, radix_hist_zero_words(c->n_occ), st);
-  c->sorted_in = launch_radix_sort_leader(t->d, c->occ_row, c->n_occ, sl, c->keys_a, c->vals_a, c->keys_b, c->vals_b,
-                                          c->hist, c->seg_counts, st);
-  SegArgs a = seg_args(t, c, nullptr);
-  launch_find_heads(a, c->heads, c->owners, c->seg_counts, st);
-  c->grouped = true;
+void drop_pending(pb_ctx* c) {
+  if (c->pending && c->pending_table && c->pending_table->pending_batches) c->pending_table->pending_batches--;
+  c->pending = false;
+  c->pending_table = nullptr;
 }
 
 }  // namespace
@@ -303,7 +277,7 @@ int pb_table_destroy(pb_table* t) {
     cudaFree(t->d.cells);
     cudaFree(t->d.rows);
     cudaFree(t->d.counters);
-    cudaFree(t->d.row_lead);
+    cudaFree(t->d.row_tick);
     if (t->d.free_rows) cudaFree(t->d.free_rows);
     if (t->evict_ws) cudaFree(t->evict_ws);
   }
@@ -367,9 +341,9 @@ int pb_table_entry_len(pb_table* t, uint32_t* h_out) {
   return PB_OK;
 }
 
-int pb_table_counters(pb_table* t, uint64_t h_out[4], void* stream) {
+int pb_table_counters(pb_table* t, uint64_t h_out[5], void* stream) {
   if (!t || !h_out) return fail(PB_ERR_INVALID, "null argument");
-  h_out[0] = h_out[1] = h_out[2] = h_out[3] = 0;
+  h_out[0] = h_out[1] = h_out[2] = h_out[3] = h_out[4] = 0;
   if (!t->allocated) return PB_OK;
   DeviceGuard g(t->device);
   uint32_t c[CTR_COUNT];
@@ -379,12 +353,13 @@ int pb_table_counters(pb_table* t, uint64_t h_out[4], void* stream) {
   h_out[1] = c[CTR_MISS];
   h_out[2] = c[CTR_GRAD_MISS];
   h_out[3] = c[CTR_FULL];
+  h_out[4] = c[CTR_ERR];
   return PB_OK;
 }
 
 int pb_table_size(pb_table* t, uint64_t* h_out, void* stream) {
   if (!t || !h_out) return fail(PB_ERR_INVALID, "null argument");
-  uint64_t c[4];
+  uint64_t c[5];
   int rc = pb_table_counters(t, c, stream);
   if (rc) return rc;
   *h_out = c[0];
@@ -398,7 +373,7 @@ int pb_table_clear(pb_table* t, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   launch_fill_cells(t->d.cells, (uint64_t)t->d.n_cells + N_SPECIAL, st);
   PB_CUDA(cudaMemsetAsync(t->d.counters, 0, sizeof(uint32_t) * CTR_COUNT, st));
-  PB_CUDA(cudaMemsetAsync(t->d.row_lead, 0, sizeof(unsigned long long) * (size_t)t->d.capacity, st));
+  PB_CUDA(cudaMemsetAsync(t->d.row_tick, 0, sizeof(uint32_t) * (size_t)t->d.capacity, st));
   return PB_OK;
 }
 
@@ -420,12 +395,12 @@ int pb_lookup(pb_table* t, const uint64_t* d_signs, uint32_t n, int training, fl
   SlotsDev sl = no_slots();
   if (training) {
     if ((rc = maybe_evict(t, st))) return rc;
-    launch_begin_batch(t->d, nullptr, st);
+    launch_begin_batch(t->d, nullptr, nullptr, st);
     launch_probe(MODE_TRAIN, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   } else {
     launch_probe(MODE_FIND, false, t->d, t->hy, t->op, sl, d_signs, n, t->scratch, st);
   }
-  launch_gather(t->d, sl, t->scratch, nullptr, n, 0, d_out, true, st);
+  launch_gather(t->d, t->scratch, n, d_out, st);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
 }
@@ -550,34 +525,36 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   c->device = device;
   c->max_occ = max_occurrences;
   c->max_out = max_out_rows;
-  size_t n = max_occurrences;
-  uint32_t tile = radix_tile(max_occurrences);
-  size_t nb = (n + tile - 1) / tile;
-  // smaller batches pick smaller tiles: size the histogram for the worst case (n/2048 tiles, capped at 128)
-  size_t hist_elems = 4 * (size_t)radix_hist_words();  // four passes x (<= 256 tiles x 512 bins)
-  (void)nb;
+  std::memset(c->round_of, 0, sizeof(c->round_of));
+  const size_t n = max_occurrences;
+  c->set_cells = 2 * n + 2 * PB_MAX_SLOTS;  // region of slot s: 2*n_s + 1 cells and the reserved one
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
+  A((void**)&c->b.set, sizeof(DCell) * c->set_cells);
+  A((void**)&c->b.occ_set, 4 * n);
+  A((void**)&c->b.item_cell, 4 * n);
+  A((void**)&c->b.seg_occ, 4 * n);
+  A((void**)&c->b.cold, 8 * n);
+  A((void**)&c->b.warm, 16 * (n / 2 + 1));
+  A((void**)&c->b.hot, 16 * (n / (PB_WARM_MAX + 1) + 1));
+  A((void**)&c->b.cnt, 4 * BC_COUNT);
   A((void**)&c->occ_cell, 4 * n);
-  A((void**)&c->occ_row, 4 * n);
   A((void**)&c->occ_outrow, 4 * n);
   A((void**)&c->row_off, 4 * ((size_t)max_out_rows + 1));
-  A((void**)&c->keys_a, 4 * n);
-  A((void**)&c->vals_a, 4 * n);
-  A((void**)&c->keys_b, 4 * n);
-  A((void**)&c->vals_b, 4 * n);
-  A((void**)&c->hist, 4 * hist_elems);
   A((void**)&c->nan_tick, 4 * PB_MAX_SLOTS);
-  A((void**)&c->heads, 16 * n);
-  A((void**)&c->owners, 8 * (n / PB_PIECE + 2));
-  A((void**)&c->seg_counts, 16);
   A((void**)&c->dev_tick, 4);
   if (e == cudaSuccess) e = cudaMemset(c->nan_tick, 0, 4 * PB_MAX_SLOTS);
   if (e == cudaSuccess) e = cudaMemset(c->dev_tick, 0, 4);
+  if (e == cudaSuccess) e = cudaMemset(c->b.cnt, 0, 4 * BC_COUNT);
+  if (e == cudaSuccess) {
+    launch_fill_set(c->b.set, c->set_cells, 0);
+    e = cudaDeviceSynchronize();
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_nan, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     pb_ctx_destroy(c);
@@ -591,14 +568,15 @@ int pb_ctx_destroy(pb_ctx* c) {
   if (!c) return PB_OK;
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {c->occ_cell, c->occ_row, c->occ_outrow, c->row_off, c->keys_a, c->vals_a,
-                  c->keys_b,   c->vals_b,   c->hist,       c->nan_tick, c->vw_stage, c->dev_tick, c->partials,
-                  c->heads,    c->owners,   c->seg_counts, c->raw.set,  c->raw.occ_set, c->raw.flag, c->raw.rank,
-                  c->raw.tiles, c->raw.distinct_cell, c->raw.counts, c->raw_stage};
+  drop_pending(c);
+  void* ptrs[] = {c->b.set,   c->b.occ_set, c->b.item_cell, c->b.seg_occ, c->b.cold, c->b.warm, c->b.hot, c->b.cnt,
+                  c->occ_cell, c->occ_outrow, c->row_off, c->nan_tick, c->vw_stage, c->dev_tick, c->raw.set,
+                  c->raw.occ_set, c->raw.flag, c->raw.rank, c->raw.tiles, c->raw.distinct_cell, c->raw.counts, c->raw_stage};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_nan) cudaEventDestroy(c->ev_nan);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
   return PB_OK;
@@ -611,78 +589,16 @@ int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg) {
     return fail(PB_ERR_INVALID, "feature_index_prefix_bit must be in 1..63");
   c->slots = *cfg;
   c->has_slots = true;
-  c->shared_groups = false;
-  for (uint32_t i = 0; i < cfg->n_slots; ++i)
-    for (uint32_t k = i + 1; k < cfg->n_slots; ++k)
-      if (cfg->prefix[i] == cfg->prefix[k]) c->shared_groups = true;  // same key space: a sign may sit in both
-  return PB_OK;
-}
-
-int pb_ctx_set_strict_reduce(pb_ctx* c, int on) {
-  if (!c) return fail(PB_ERR_INVALID, "null argument");
-  c->strict_reduce = on != 0;
-  return PB_OK;
-}
-
-int pb_ctx_set_async_grouping(pb_ctx* c, int on) {
-  if (!c) return fail(PB_ERR_INVALID, "null argument");
-  if (c->pending) return fail(PB_ERR_STATE, "a batch is pending in this context");
-  c->async_grouping = on != 0;
-  return PB_OK;
-}
-
-int pb_ctx_set_owner_mode(pb_ctx* c, int on) {
-  if (!c) return fail(PB_ERR_INVALID, "null argument");
-  c->owner_mode = on != 0;
-  return PB_OK;
-}
-
-int pb_permute_u64(const uint64_t* d_src, const uint32_t* d_perm, uint32_t n, uint64_t* d_out, void* stream) {
-  if (n && (!d_src || !d_perm || !d_out)) return fail(PB_ERR_INVALID, "null argument");
-  launch_permute_u64(d_src, d_perm, n, d_out, (cudaStream_t)stream);
-  PB_CUDA(cudaGetLastError());
-  return PB_OK;
-}
-
-int pb_permute_rows(const void* d_src, const uint32_t* d_perm, uint32_t n, uint32_t row_bytes, int scatter, void* d_out,
-                    void* stream) {
-  if (n && (!d_src || !d_perm || !d_out)) return fail(PB_ERR_INVALID, "null argument");
-  if (row_bytes == 0 || row_bytes % 16) return fail(PB_ERR_INVALID, "row_bytes must be a multiple of 16");
-  launch_permute_rows(d_src, d_perm, n, row_bytes, scatter, d_out, (cudaStream_t)stream);
-  PB_CUDA(cudaGetLastError());
-  return PB_OK;
-}
-
-int pb_frame_signs(const uint64_t* d_signs, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
-                   uint64_t* d_out, uint32_t* d_overflow, void* stream) {
-  if (!d_signs || !d_perm || !d_counts || !d_out || R == 0 || cap == 0) return fail(PB_ERR_INVALID, "bad argument");
-  launch_pack_signs(d_signs, d_perm, d_counts, R, cap, d_out, d_overflow, (cudaStream_t)stream);
-  PB_CUDA(cudaGetLastError());
-  return PB_OK;
-}
-
-int pb_frame_rows(const void* d_src, const uint32_t* d_perm, const uint32_t* d_counts, uint32_t R, uint32_t cap,
-                  uint32_t row_bytes, int pack, void* d_out, void* stream) {
-  if (!d_src || !d_perm || !d_counts || !d_out || R == 0 || cap == 0) return fail(PB_ERR_INVALID, "bad argument");
-  if (row_bytes == 0 || row_bytes % 16) return fail(PB_ERR_INVALID, "row_bytes must be a multiple of 16");
-  launch_frame_rows(d_src, d_perm, d_counts, R, cap, row_bytes, pack, d_out, (cudaStream_t)stream);
-  PB_CUDA(cudaGetLastError());
-  return PB_OK;
-}
-
-int pb_p2p_exchange(const void* d_framed, const uint64_t* h_peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
-                    uint32_t row_bytes, void* stream) {
-  if (!d_framed || !h_peer_ptrs || R == 0 || R > 16 || my_rank >= R || cap == 0) return fail(PB_ERR_INVALID, "bad argument");
-  if (row_bytes == 0 || row_bytes % 16) return fail(PB_ERR_INVALID, "row_bytes must be a multiple of 16");
-  launch_p2p_exchange(d_framed, h_peer_ptrs, R, my_rank, cap, row_bytes, (cudaStream_t)stream);
-  PB_CUDA(cudaGetLastError());
-  return PB_OK;
-}
-
-int pb_p2p_barrier(const uint64_t* h_flag_ptrs, uint32_t* d_epoch, uint32_t R, uint32_t my_rank, uint32_t* d_err, void* stream) {
-  if (!h_flag_ptrs || !d_epoch || R == 0 || R > 16 || my_rank >= R) return fail(PB_ERR_INVALID, "bad argument");
-  launch_p2p_barrier(h_flag_ptrs, d_epoch, R, my_rank, d_err, (cudaStream_t)stream);
-  PB_CUDA(cudaGetLastError());
+  // two slots with the same prefix share a key space (one feature group): a sign may sit in both, and the reference
+  // steps it once per slot, in slot order (mod.rs:720-822).  Slot s runs in round = number of earlier slots of its group.
+  c->n_rounds = 1;
+  for (uint32_t i = 0; i < cfg->n_slots; ++i) {
+    uint32_t r = 0;
+    for (uint32_t k = 0; k < i; ++k)
+      if (cfg->prefix[i] == cfg->prefix[k]) ++r;
+    c->round_of[i] = (uint8_t)r;
+    if (r + 1 > c->n_rounds) c->n_rounds = r + 1;
+  }
   return PB_OK;
 }
 
@@ -691,7 +607,7 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   if (!t || !c || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
   if (!c->has_slots) return fail(PB_ERR_STATE, "pb_ctx_set_slots not called");
   if (t->device != c->device) return fail(PB_ERR_INVALID, "table and context live on different devices");
-  if (batch > 65535 && !c->owner_mode) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
+  if (batch > 65535) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
   uint32_t S = c->slots.n_slots;
   uint64_t n_out = (uint64_t)S * batch;
   if (n_occ > c->max_occ || n_out > c->max_out) return fail(PB_ERR_CAPACITY, "batch exceeds the context's capacity");
@@ -712,27 +628,20 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   if ((rc = ensure_alloc(t))) return rc;
   SlotsDev sl;
   if ((rc = make_slots(c->slots, h_slot_occ_off, sl))) return rc;
-  sl.null_sign = c->owner_mode ? 1 : 0;
+  // a batch whose gradients never came (or an inference request) leaves its cells in the scratch set: empty it first
+  if (c->set_dirty) {
+    launch_clear_items(c->b, st);
+    c->set_dirty = false;
+  }
+  drop_pending(c);  // like an expired post_forward_buffer entry (mod.rs:991-1029)
   if (training) {
     if ((rc = maybe_evict(t, st))) return rc;
-    launch_begin_batch(t->d, c->dev_tick, st);
-    launch_probe(MODE_TRAIN, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
-  } else {
-    launch_probe(MODE_FIND, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
   }
-  if (training) {
-    c->n_occ = n_occ;
-    c->batch = batch;
-    c->multi_id = d_row_off != nullptr;
-    c->grouped = false;
-    if (c->async_grouping && !d_row_off) {  // fork: the grouping overlaps the gather and whatever follows
-      PB_CUDA(cudaEventRecord(c->ev_fork, st));
-      PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-      group_occurrences(t, c, sl, c->side);
-      PB_CUDA(cudaEventRecord(c->ev_join, c->side));
-    }
-  }
-  launch_gather(t->d, sl, c->occ_cell, d_row_off, (uint32_t)n_out, batch, d_out_f16, false, st);
+  launch_begin_batch(t->d, training ? c->dev_tick : nullptr, c->b.cnt, st, training != 0);
+  c->b.n = n_occ;
+  launch_dedup(sl, c->b, d_ids, st);
+  launch_probe_items(training != 0, t->d, t->hy, t->op, c->b, st);
+  launch_gather_items(t->d, sl, c->b, d_row_off, (uint32_t)n_out, batch, training != 0, d_out_f16, st);
   if (training) {
     c->n_occ = n_occ;
     c->batch = batch;
@@ -743,6 +652,11 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
       launch_expand_rows(c->row_off, (uint32_t)n_out, c->occ_outrow, st);
     }
     c->pending = true;
+    c->pending_table = t;
+    t->pending_batches++;
+    c->set_dirty = true;  // emptied beside the backward (or by the next forward)
+  } else {
+    launch_clear_items(c->b, st);
   }
   PB_CUDA(cudaGetLastError());
   return PB_OK;
@@ -752,6 +666,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
                 int32_t* d_slot_status, void* stream) {
   if (!t || !c || !h_grads) return fail(PB_ERR_INVALID, "null argument");
   if (!c->pending) return fail(PB_ERR_STATE, "no forward batch is pending in this context (backward_ref_id not found)");
+  if (c->pending_table != t) return fail(PB_ERR_INVALID, "the pending batch was looked up in another table");
   int rc = ready_for_training(t);
   if (rc) return rc;
   DeviceGuard g(t->device);
@@ -783,8 +698,6 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     gr.adam_pow = t->adam_dev;
     launch_adam_advance(t->adam_dev, keys, t->op.b1, t->op.b2, st);
   }
-  uint32_t elems = c->batch * t->d.dim;
-  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
   float* vw = nullptr;
   if (t->op.kind == PB_OPT_ADAGRAD_VW) {
     size_t need = (size_t)c->n_occ * t->d.dim;
@@ -798,27 +711,39 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     }
     vw = c->vw_stage;
   }
-  if (!c->strict_reduce) {
-    size_t need = 2 * (((size_t)c->n_occ + PB_PIECE - 1) / PB_PIECE) * t->d.dim;
-    if (need > c->partials_floats) {
-      PB_CUDA(cudaStreamSynchronize(st));
-      if (c->partials) cudaFree(c->partials);
-      c->partials = nullptr;
-      c->partials_floats = 0;
-      size_t cap = 2 * (((size_t)c->max_occ + PB_PIECE - 1) / PB_PIECE) * t->d.dim;
-      if (cap < need) cap = need;
-      PB_CUDA(cudaMalloc(&c->partials, sizeof(float) * cap));
-      c->partials_floats = cap;
-    }
+  // beside the main stream: the scratch set is emptied and, once the NaN marks are known, the hot items are reduced
+  PB_CUDA(cudaEventRecord(c->ev_fork, st));
+  PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  if (c->set_dirty) {
+    launch_clear_items(c->b, c->side);
+    c->set_dirty = false;
   }
-  if (c->grouped) {
-    PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));  // join the side stream's grouping
-  } else {
-    group_occurrences(t, c, sl, st);
+  uint32_t elems = c->batch * t->d.dim;
+  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
+  PB_CUDA(cudaEventRecord(c->ev_nan, st));
+  PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_nan, 0));
+  ReduceArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.b = c->b;
+  a.b.n = c->n_occ;
+  a.occ_outrow = c->multi_id ? c->occ_outrow : nullptr;
+  a.row_off = c->multi_id ? c->row_off : nullptr;
+  a.tick_ptr = c->dev_tick;
+  a.nan_tick = c->nan_tick;
+  a.vw_stage = vw;
+  a.batch = c->batch;
+  a.quiet_miss = 0;
+  for (uint32_t r = 0; r < c->n_rounds; ++r) {
+    a.round = r;
+    std::memset(a.round_mask, 0, sizeof(a.round_mask));
+    for (uint32_t s = 0; s < S; ++s)
+      if (c->round_of[s] == r) a.round_mask[s >> 5] |= 1u << (s & 31);
+    // one round (no shared feature groups, the usual case): hot items run beside the others; several: one after another
+    launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, c->n_rounds == 1 ? c->side : st);
   }
-  SegArgs a = seg_args(t, c, vw);
-  launch_reduce_update(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, c->heads, c->owners, c->seg_counts, st);
-  c->pending = false;
+  PB_CUDA(cudaEventRecord(c->ev_join, c->side));
+  PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+  drop_pending(c);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
 }
@@ -871,7 +796,7 @@ int pb_forward_raw(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ
   sl.uniform = 0;
   if (training) {
     if ((rc = maybe_evict(t, st))) return rc;
-    launch_begin_batch(t->d, c->dev_tick, st);
+    launch_begin_batch(t->d, c->dev_tick, nullptr, st);
     launch_probe(MODE_TRAIN, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);
   } else {
     launch_probe(MODE_FIND, true, t->d, t->hy, t->op, sl, d_ids, n_occ, c->occ_cell, st);

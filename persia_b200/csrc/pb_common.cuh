@@ -22,7 +22,20 @@ constexpr uint64_t PB_NULL_SIGN = 0xFFFFFFFFFFFFFFFEULL;  // padding of a framed
 struct __align__(16) Cell {
   unsigned long long key;
   uint32_t row;
-  uint32_t aux;   // reserved (recency lives in TableDev::row_lead)
+  uint32_t aux;   // reserved (recency lives in TableDev::row_tick)
+};
+
+// One cell of a batch's scratch set (pb_dedup.cu): the device-side FeatureBatch::new (persia-common/src/lib.rs:45-82).
+// The set is split into one region per slot (the reference builds one hashmap per slot), so a sign carried by two
+// slots of one feature group is two entries, as there.  32 B = one sector per access.
+struct __align__(32) DCell {
+  unsigned long long key;  // the (prefixed) sign; KEY_EMPTY = free
+  uint32_t count;          // occurrences of the sign in this slot of this batch
+  uint32_t cursor;         // next free entry of the sign's occurrence list (count > 1)
+  uint32_t target;         // where the sign lives: table row (single GPU) or owner slot (sharded); ROW_NONE = nowhere
+  uint32_t base;           // first entry of the occurrence list in BatchDev::seg_occ (count > 1)
+  uint32_t first;          // the occurrence that inserted the sign: its only one when count == 1
+  uint32_t item;           // number of the distinct sign in this batch (insertion order)
 };
 
 // farmhash 1.1.5 hash64 of an 8-byte LE value (FarmHash HashLen0to16, 8..16 branch).
@@ -56,7 +69,7 @@ struct TableDev {
   float* rows;         // capacity * stride floats: emb(dim) ++ optimizer state ++ pad
   uint32_t* counters;  // see CTR_* below
   uint32_t* free_rows;   // stack of rows released by eviction (CTR_FREE entries)
-  unsigned long long* row_lead;  // per row: (batch number << 32) | ~(first occurrence of the sign in that batch)
+  uint32_t* row_tick;    // per row: batch number of its last training lookup (get_refresh, eviction_map.rs:48-60)
   uint64_t cell_mask;    // n_cells - 1
   uint32_t bucket_mask;  // n_cells / BUCKET - 1
   uint32_t n_cells;
@@ -73,6 +86,7 @@ enum {
   CTR_FULL = 5,      // admissions refused for lack of capacity
   CTR_ADMIT = 6,     // rows admitted
   CTR_EVICT = 7,     // rows evicted
+  CTR_ERR = 8,       // an in-kernel wait gave up (mbarrier / peer flag): results of that batch are void
   CTR_COUNT = 16
 };
 

@@ -1,7 +1,5 @@
-// pb_group.cuh — device bodies of the backward's grouping steps (leader election, radix histogram, radix
-// scatter, piece heads), written against a virtual block number (internal).  Their kernels are thin wrappers;
-// a single cooperative launch looping over the bodies with grid barriers in between was measured slower than
-// the five launches (92 vs 86 us per step; branch exp/fused-grouping).
+// pb_group.cuh — device bodies of the stable radix partition (histogram pass, scatter pass), written against a
+// virtual block number (internal).  Used by pb_partition_by_shard (pb_sort.cu).
 #pragma once
 #include "pb_device.cuh"
 
@@ -21,15 +19,6 @@ constexpr int RS_BITS = 9;
 constexpr int RS_BINS = 1 << RS_BITS;          // 512: two bins per thread
 
 // key sources of the histogram pass -----------------------------------------------------------------
-struct SrcLeader {  // occurrence -> row -> first occurrence of the sign in this batch; no storage sorts last
-  const uint32_t* occ_row;
-  const unsigned long long* row_lead;
-  uint32_t n;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
-    uint32_t row = occ_row[i];
-    return row == ROW_NONE ? n : ~(uint32_t)row_lead[row];
-  }
-};
 struct SrcShard {  // sign_to_shard_modulo (mod.rs:341-345)
   const uint64_t* signs;
   uint32_t R;
@@ -38,10 +27,6 @@ struct SrcShard {  // sign_to_shard_modulo (mod.rs:341-345)
 
 struct ValIdentity {
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i; }
-};
-struct ValOccSlot {
-  SlotsDev sl;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i | (slot_of_occ(sl, i) << 24); }
 };
 
 // Pass-0 histogram, block-major hist[tile][bin].  Blocks cover 512 keys each (more blocks than tiles, so
@@ -253,150 +238,6 @@ __device__ __forceinline__ void radix_scatter_body(uint32_t vb, uint32_t nb, con
     }
     __syncthreads();
   }
-}
-
-
-// ---- leader election (see pb_index.cu) -------------------------------------------------------------------------
-constexpr int ELECT_SLOTS = 512;
-__device__ __forceinline__ void elect_body(uint32_t vb, const TableDev& t, const uint32_t* __restrict__ occ_cell, uint32_t n,
-                                           uint32_t* __restrict__ occ_row) {
-  __shared__ uint32_t keys[ELECT_SLOTS], best[ELECT_SLOTS];
-  for (uint32_t i = threadIdx.x; i < ELECT_SLOTS; i += blockDim.x) {
-    keys[i] = 0xFFFFFFFFu;
-    best[i] = 0xFFFFFFFFu;
-  }
-  __syncthreads();
-  const unsigned long long lead_hi = (unsigned long long)t.counters[CTR_TICK] << 32;
-  const uint32_t i = vb * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint32_t h = occ_cell[i];
-    uint32_t row = (h < t.n_cells + N_SPECIAL) ? t.cells[h].row : ROW_NONE;
-    if (row >= t.capacity) row = ROW_NONE;
-    occ_row[i] = row;
-    if (row != ROW_NONE) {
-      uint32_t s = (row * 2654435761u) >> 23;  // 9 bits
-      for (;;) {
-        uint32_t k = atomicCAS(&keys[s], 0xFFFFFFFFu, row);
-        if (k == 0xFFFFFFFFu || k == row) {
-          atomicMin(&best[s], i);
-          break;
-        }
-        s = (s + 1) & (ELECT_SLOTS - 1);
-      }
-    }
-  }
-  __syncthreads();
-  for (uint32_t s = threadIdx.x; s < ELECT_SLOTS; s += blockDim.x) {
-    uint32_t row = keys[s];
-    if (row != 0xFFFFFFFFu) {
-      const unsigned long long mine = lead_hi | (uint32_t)~best[s];
-      if (__ldcg(&t.row_lead[row]) < mine) atomicMax(&t.row_lead[row], mine);
-    }
-  }
-}
-
-
-// ---- piece heads (see pb_update.cu) ----------------------------------------------------------------------------
-constexpr uint32_t PB_SHORT_PIECE = 4;  // a piece of more occurrences than this is listed as long
-__device__ __forceinline__ uint32_t val_occ(uint32_t v) { return v & 0x00FFFFFFu; }
-__device__ __forceinline__ uint32_t val_slot(uint32_t v) { return v >> 24; }
-
-__device__ __forceinline__ bool same_seg(const SegArgs& a, uint32_t j, uint32_t key, uint32_t slot) {
-  return a.skey[j] == key && val_slot(a.sval[j]) == slot;
-}
-
-// Piece heads and combine owners of the sorted list, compacted (order is irrelevant: every entry is an
-// independent piece of work).  One warp looks at one PIECE-block (PIECE == 32 == warp width): segment
-// starts of the previous, own and next block become three ballot masks, from which every lane derives
-// its piece end without walking the list.
-//   heads[k]  = (first position, end position | whole << 31, row of the sign, sorted value at the first position)
-//   owners[k] = (first boundary of a cut segment, start of that segment)
-// counts[0] = long pieces (heads[0..)), counts[2] = short pieces (heads[n-1] downwards), counts[1] = owners,
-// counts[3] = the reducing kernel's work counter; all four are cleared by the histogram pass.
-__device__ __forceinline__ bool seg_start_at(const SegArgs& a, uint32_t p) {
-  if (p >= a.n) return true;  // past the end: terminates any segment
-  if (p == 0) return true;
-  return a.skey[p] != a.skey[p - 1] || val_slot(a.sval[p]) != val_slot(a.sval[p - 1]);
-}
-
-__device__ __forceinline__ void find_heads_body(uint32_t vb, const SegArgs& a, uint4* __restrict__ heads,
-                                                uint2* __restrict__ owners, uint32_t* __restrict__ counts) {
-  static_assert(PB_PIECE == 32, "one warp per PIECE-block");
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t m = (vb * blockDim.x + threadIdx.x) >> 5;  // PIECE-block of this warp
-  const uint32_t B0 = m * 32;
-  if (B0 >= a.n) return;  // whole warp
-  const uint32_t Fp = m ? __ballot_sync(0xffffffffu, seg_start_at(a, B0 - 32 + lane)) : 1u;  // previous block
-  const uint32_t F0 = __ballot_sync(0xffffffffu, seg_start_at(a, B0 + lane));
-  const uint32_t F1 = __ballot_sync(0xffffffffu, seg_start_at(a, B0 + 32 + lane));
-  const bool s2 = seg_start_at(a, B0 + 64);  // first position of the block after next
-  const uint32_t j = B0 + lane;
-  bool is_head = false, is_owner = false;
-  uint32_t e = 0, whole = 0, j0 = 0;
-  if (j < a.n) {
-    const bool seg_start = (F0 >> lane) & 1u;
-    is_head = seg_start;
-    if (a.piece && lane == 0) {
-      // a boundary cuts its segment only if the segment also holds the boundary before or after it:
-      // segments of <= PIECE occurrences are never cut and keep the reference summation order
-      const bool next_in = (F0 & ~1u) == 0 && !(F1 & 1u);            // no start in B0+1 .. B0+32
-      const bool prev_in = m && (Fp & ~1u) == 0 && !(F0 & 1u);       // no start in B0-31 .. B0
-      if (!seg_start) is_head = next_in || prev_in;
-      is_owner = next_in && !prev_in;  // first boundary of a segment that holds a second one
-      j0 = seg_start ? B0 : (B0 - 32 + (31 - __clz(Fp)));  // last start before the boundary (exists: !prev_in)
-    }
-    if (is_head) {
-      const uint32_t above = (lane == 31) ? 0u : (F0 & (0xFFFFFFFEu << lane));  // starts after this lane
-      bool seg_end = true;
-      if (!a.piece) {  // strict mode: no cutting — walk to the true end
-        e = j + 1;
-        const uint32_t key = a.skey[j], slot = val_slot(a.sval[j]);
-        while (e < a.n && same_seg(a, e, key, slot)) ++e;
-      } else if (above) {
-        e = B0 + __ffs(above) - 1;
-      } else if (F1 & 1u) {
-        e = B0 + 32;  // ends exactly on the boundary
-      } else {
-        // reaches the boundary B0+32 and continues: cut there iff this piece already spans a whole block
-        // (head on a boundary) or the segment also holds the boundary after it
-        const bool cut = (lane == 0) || ((F1 & ~1u) == 0 && !s2);
-        if (cut) {
-          e = B0 + 32;
-          seg_end = false;
-        } else {
-          e = (F1 & ~1u) ? B0 + 32 + __ffs(F1 & ~1u) - 1 : B0 + 64;  // ends inside the next block, or exactly at its end
-        }
-      }
-      if (e > a.n) e = a.n;
-      whole = (seg_start && seg_end) ? 1u : 0u;
-      // a sign held by several slots of one feature group is stepped slot by slot in k_update_shared
-      if (whole && a.shared_groups && ((j > 0 && a.skey[j - 1] == a.skey[j]) || (e < a.n && a.skey[e] == a.skey[j])))
-        is_head = false;
-    }
-  }
-  // long pieces (the expensive ones) are listed from the front, short ones from the back: the reducing kernel
-  // hands out the list front to back, so the tail of the launch is made of cheap pieces
-  const bool is_long = is_head && (e - j) > PB_SHORT_PIECE;
-  const uint32_t lm = __ballot_sync(0xffffffffu, is_long);
-  const uint32_t sm = __ballot_sync(0xffffffffu, is_head && !is_long);
-  const uint32_t om = __ballot_sync(0xffffffffu, is_owner);
-  uint32_t lb = 0, sb = 0, ob = 0;
-  if (lane == 0) {
-    if (lm) lb = atomicAdd(&counts[0], __popc(lm));
-    if (sm) sb = atomicAdd(&counts[2], __popc(sm));
-    if (om) ob = atomicAdd(&counts[1], __popc(om));
-  }
-  lb = __shfl_sync(0xffffffffu, lb, 0);
-  sb = __shfl_sync(0xffffffffu, sb, 0);
-  ob = __shfl_sync(0xffffffffu, ob, 0);
-  if (is_head) {  // the record carries what the reducing group would otherwise chase through three dependent loads
-    const uint32_t lead = a.skey[j];  // the sort key is the sign's first occurrence (n = no storage)
-    const uint32_t row = lead < a.n ? a.occ_row[lead] : ROW_NONE;
-    const uint32_t below = (1u << lane) - 1u;
-    const uint32_t at = is_long ? lb + __popc(lm & below) : a.n - 1u - (sb + __popc(sm & below));
-    heads[at] = make_uint4(j, e | (whole << 31), row, a.sval[j]);
-  }
-  if (is_owner) owners[ob + __popc(om & ((1u << lane) - 1u))] = make_uint2(j, j0);
 }
 
 

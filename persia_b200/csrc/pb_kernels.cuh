@@ -14,7 +14,6 @@ struct SlotsDev {
   uint32_t n_slots;
   uint64_t spacing;  // 2^(64-prefix_bit) - 1
   uint32_t spacing_bits;  // 64 - prefix_bit
-  uint32_t null_sign;     // owner-mode contexts: PB_NULL_SIGN entries are padding, not lookups
   uint32_t uniform;       // occurrences per slot when every slot holds the same number (one id per sample), else 0
 };
 
@@ -27,20 +26,45 @@ struct GradsDev {
   uint8_t pow_idx[PB_MAX_SLOTS];  // the slot's pair
 };
 
-// arguments of the backward segment kernels (see pb_update.cu)
-struct SegArgs {
-  const uint32_t* skey;        // first occurrence of the occurrence's sign (n = no storage), sorted
-  const uint32_t* occ_row;     // row number of every occurrence (ROW_NONE = no storage)
-  const uint32_t* sval;        // occurrence position | slot << 24
+// ---- the batch context on the device (what the EW keeps in post_forward_buffer, mod.rs:1087-1098) ------------------
+// Filled by the forward (dedup -> probe -> gather), consumed by the backward.  A distinct (sign, slot) pair of the
+// batch is an "item"; the occurrences of an item with count > 1 are listed in seg_occ[base, base + count) in
+// arbitrary order (the reducing kernels put them in ascending order, the reference's summation order).
+constexpr uint32_t PB_WARM_MAX = 32;  // items of 2..PB_WARM_MAX occurrences are reduced by a lane group, larger ones by a CTA
+enum {
+  BC_ITEMS = 0,  // distinct items of the batch
+  BC_COLD,       // items of one occurrence
+  BC_WARM,       // items of 2..PB_WARM_MAX occurrences
+  BC_HOT,        // items of more
+  BC_SEG,        // entries of seg_occ handed out
+  BC_SENT,       // sharded: per-owner send counts follow at BC_PEER (16 words)
+  BC_PEER = 8,
+  BC_NEXT = 24,  // work cursors of the reducing kernels: [round] warm, [PB_MAX_SLOTS + round] hot
+  BC_COUNT = BC_NEXT + 2 * PB_MAX_SLOTS
+};
+struct BatchDev {
+  DCell* set;           // scratch set: region of slot s = [2*occ_off[s] + 2*s, +2*n_s + 1), then its reserved cell
+  uint32_t* occ_set;    // [n] set cell of every occurrence
+  uint32_t* item_cell;  // [n] set cell of every item
+  uint32_t* seg_occ;    // [n] occurrence lists
+  uint2* cold;          // [n]   (target, occurrence)
+  uint4* warm;          // [n/2] (target, base, count, -)
+  uint4* hot;           // [n/PB_WARM_MAX] (target, base, count, -)
+  uint32_t* cnt;        // BC_* words
+  uint32_t n;           // id occurrences of the batch
+};
+
+// arguments of the backward kernels (pb_reduce.cu)
+struct ReduceArgs {
+  BatchDev b;
   const uint32_t* occ_outrow;  // nullptr: one id per sample per slot (output row == occurrence)
   const uint32_t* row_off;
   const uint32_t* tick_ptr;
   const uint32_t* nan_tick;
-  float* partials;  // 2 rows of dim floats per PIECE-block
-  float* vw_stage;
-  uint32_t n, batch, piece, shared_groups, quiet_miss;
+  float* vw_stage;             // Adagrad vectorwise: one reduced gradient per item
+  uint32_t batch, round, quiet_miss;
+  uint32_t round_mask[PB_MAX_SLOTS / 32];  // slots stepped by this launch (slots of one feature group take turns)
 };
-constexpr uint32_t PB_PIECE = 32;
 
 // raw slots (pb_raw.cu): per-batch scratch set of distinct signs and its workspace
 struct RawCell {
@@ -60,21 +84,26 @@ struct RawWork {
 };
 
 void launch_fill_cells(Cell* cells, uint64_t n, cudaStream_t st);
-void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, cudaStream_t st);
+void launch_fill_set(DCell* set, uint64_t n, cudaStream_t st);
+// bump: a training request (advances the table's batch number and the context's request number)
+void launch_begin_batch(const TableDev& t, uint32_t* ctx_tick, uint32_t* batch_cnt, cudaStream_t st, bool bump = true);
 void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, const OptimDev& op, const SlotsDev& sl,
                   const uint64_t* ids, uint32_t n, uint32_t* occ_cell, cudaStream_t st);
-void launch_gather(const TableDev& t, const SlotsDev& sl, const uint32_t* occ_cell, const uint32_t* row_off,
-                   uint32_t n_out, uint32_t batch, void* out, bool out_f32, cudaStream_t st);
-void launch_elect(const TableDev& t, const uint32_t* occ_cell, uint32_t n, uint32_t* occ_row, uint32_t* zero,
-                  uint32_t zero_words, cudaStream_t st);
-void launch_find_heads(const SegArgs& a, uint4* heads, uint2* owners, uint32_t* counts, cudaStream_t st);
+void launch_gather(const TableDev& t, const uint32_t* occ_cell, uint32_t n_out, float* out, cudaStream_t st);
+// batched path (pb_dedup.cu)
+void launch_dedup(const SlotsDev& sl, const BatchDev& b, const uint64_t* ids, cudaStream_t st);
+void launch_probe_items(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const BatchDev& b,
+                        cudaStream_t st);
+void launch_gather_items(const TableDev& t, const SlotsDev& sl, const BatchDev& b, const uint32_t* row_off,
+                         uint32_t n_out, uint32_t batch, bool training, void* out_f16, cudaStream_t st);
+void launch_clear_items(const BatchDev& b, cudaStream_t st);
 void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell, uint32_t n, float* entries,
                          uint8_t* found, cudaStream_t st);
 void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,
                      uint32_t* nan_tick, int32_t* status, cudaStream_t st);
-void launch_reduce_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                          const GradsDev& gr, bool f16, const SegArgs& a, uint4* heads, uint2* owners,
-                          uint32_t* counts, cudaStream_t st);
+// pb_reduce.cu: cold + warm items on `st`, hot items on `st_hot` (may equal st)
+void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
+                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot);
 // n_ptr (optional): the live count on the device (<= n); tick/nan_tick (optional): skip everything when equal
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
                           const float* grads, uint32_t n, const float* adam_pair, cudaStream_t st,
@@ -101,9 +130,6 @@ void launch_slot_status(const GradsDev& gr, uint32_t n_slots, const uint32_t* ti
 uint32_t radix_tile(uint32_t n);
 uint32_t radix_hist_words();
 uint32_t radix_hist_zero_words(uint32_t n);
-int launch_radix_sort_leader(const TableDev& t, const uint32_t* occ_row, uint32_t n, const SlotsDev& sl, uint32_t* keys_a,
-                             uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* zero4,
-                             cudaStream_t st);
 void launch_zero_words(uint32_t* p, uint32_t n_words, cudaStream_t st);
 uint64_t partition_workspace_bytes(uint32_t n);
 void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* perm, uint32_t* counts,
@@ -111,21 +137,11 @@ void launch_partition_by_shard(const uint64_t* signs, uint32_t n, uint32_t R, ui
 void launch_expand_rows(const uint32_t* row_off, uint32_t n_out, uint32_t* occ_outrow, cudaStream_t st);
 void launch_add_prefix(const SlotsDev& sl, const uint64_t* ids, uint32_t n, uint64_t* out, cudaStream_t st);
 void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* shard, uint64_t* hash, cudaStream_t st);
-void launch_permute_rows(const void* src, const uint32_t* perm, uint32_t n, uint32_t row_bytes, int scatter, void* out,
-                         cudaStream_t st);
-void launch_permute_u64(const uint64_t* src, const uint32_t* perm, uint32_t n, uint64_t* out, cudaStream_t st);
-void launch_pack_signs(const uint64_t* signs, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
-                       uint64_t* out, uint32_t* overflow, cudaStream_t st);
-void launch_frame_rows(const void* src, const uint32_t* perm, const uint32_t* counts, uint32_t R, uint32_t cap,
-                       uint32_t row_bytes, int pack, void* out, cudaStream_t st);
 void launch_export_signs(const TableDev& t, uint64_t* signs, uint32_t* recency, uint32_t max_n, uint32_t* count,
                          cudaStream_t st);
 void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, uint32_t keep, uint32_t* ev, cudaStream_t st);
-void launch_p2p_exchange(const void* src, const uint64_t* peer_ptrs, uint32_t R, uint32_t my_rank, uint32_t cap,
-                         uint32_t row_bytes, cudaStream_t st);
-void launch_p2p_barrier(const uint64_t* flag_ptrs, uint32_t* epoch, uint32_t R, uint32_t my_rank, uint32_t* err, cudaStream_t st);
 uint64_t launch_count();
-enum { FAM_PROBE = 0, FAM_COMBINE, FAM_GATHER, FAM_NAN, FAM_SORT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
+enum { FAM_PROBE = 0, FAM_DEDUP, FAM_GATHER, FAM_NAN, FAM_HOT, FAM_UPDATE, FAM_OTHER, FAM_COUNT };
 void profile_enable(uint32_t family_mask);
 void profile_read(double* ms, uint64_t* count, int n_families);
 

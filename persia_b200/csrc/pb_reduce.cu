@@ -1,0 +1,640 @@
+// pb_reduce.cu — backward of the batched path: per distinct sign, the in-order gradient segment reduce (A8) fused with
+// the optimizer step and weight bound on the resident row (A9).  SURVEY.md §8a.
+//
+// Reference: update_all_batched_gradients (embedding_worker_service/mod.rs:703-872) reduces, per slot and distinct
+// sign, the gradients of the samples holding the sign — sequentially, in the order FeatureBatch::new listed them
+// (ascending sample) — and update_gradient_mixed (embedding_parameter_service/mod.rs:359-427) performs one optimizer
+// step per (slot, sign) with the sum.  f32 addition is not associative, so the order is kept exactly, for any
+// multiplicity: results are bit-identical to the reference's whatever a sign's popularity.
+//
+// The forward left three work lists (pb_dedup.cu): cold items (one occurrence — nothing to reduce), warm items
+// (2..PB_WARM_MAX occurrences, list unsorted) and hot items (more: the head of the Zipf curve and every sign of a
+// tiny-cardinality slot, thousands of occurrences each).
+//   k_reduce_items  persistent; a lane group per item.  Cold: four items per group in flight (all row and gradient
+//                   loads issued before the first use).  Warm: the group sorts the item's <= 32 occurrences in shared
+//                   memory (rank by counting), then adds them in order.
+//   k_reduce_hot    persistent; a two-warp CTA per item.  The occurrences are put in order by setting one bit per
+//                   occurrence in a shared-memory bitmap over the slot's sample range (a counting sort that costs
+//                   B/32 words).  Warp 0 streams the gradient rows, 32 per stage, into a shared-memory ring with
+//                   cp.async.bulk (one bulk copy per row, completion on the stage's mbarrier); warp 1 waits on the
+//                   stage and adds its rows in order — a dependent FADD chain fed from shared memory, which is the
+//                   floor for a strictly sequential sum — then performs the optimizer step.
+#include <cstdlib>
+
+#include "pb_optim.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------------------------------------
+// shared pieces
+// ------------------------------------------------------------------------------------------------
+struct ItemSrc {  // where an item's gradients come from
+  const void* gbase;    // the slot's gradient tensor [batch, dim]
+  uint32_t slot_row0;   // slot * batch
+  float inv_scale;
+  bool do_scale, do_sqrt, plain;
+};
+
+__device__ __forceinline__ ItemSrc item_src(const SlotsDev& sl, const GradsDev& gr, const ReduceArgs& a, uint32_t slot) {
+  ItemSrc s;
+  s.gbase = gr.ptr[slot];
+  s.slot_row0 = slot * a.batch;
+  s.inv_scale = gr.inv_scale[slot];
+  s.do_scale = gr.do_scale[slot];
+  s.do_sqrt = sl.sqrt_scaling[slot];
+  s.plain = !a.occ_outrow && !s.do_scale && !s.do_sqrt;
+  return s;
+}
+
+// output row (= gradient row) of an occurrence and its sample's sqrt factor (mirror of the forward scaling without
+// its max(.,1), mod.rs:757-768)
+__device__ __forceinline__ uint32_t occ_out_row(const ReduceArgs& a, uint32_t occ) {
+  return a.occ_outrow ? a.occ_outrow[occ] : occ;
+}
+__device__ __forceinline__ GradPrep grad_prep(const ItemSrc& s, const ReduceArgs& a, uint32_t orow) {
+  GradPrep p;
+  p.inv_scale = s.inv_scale;
+  p.do_scale = s.do_scale;
+  p.do_sqrt = s.do_sqrt;
+  p.sqrt_f = 1.0f;
+  if (s.do_sqrt) {
+    uint32_t cnt = a.row_off ? a.row_off[orow + 1] - a.row_off[orow] : 1u;
+    p.sqrt_f = __fdiv_rn(1.0f, __fsqrt_rn((float)cnt));
+  }
+  return p;
+}
+
+// N consecutive gradient elements of one output row starting at element e0, converted to f32 and clamped
+template <int N, bool F16>
+__device__ __forceinline__ void load_grad_elems(float (&g)[N], const void* gbase, size_t row_elem0, uint32_t e0) {
+  if (F16) {
+    const __half* gp = reinterpret_cast<const __half*>(gbase) + row_elem0 + e0;
+    if (N % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) {
+        uint2 raw = *reinterpret_cast<const uint2*>(gp + 4 * q);
+        // +-inf -> +-65504 (persia-common lib.rs:163-180), two halves per instruction; finite halves are inside already
+        const __half2 lim = __floats2half2_rn(65504.0f, 65504.0f);
+        __half2 h0 = __hmin2(__hmax2(*reinterpret_cast<__half2*>(&raw.x), __hneg2(lim)), lim);
+        __half2 h1 = __hmin2(__hmax2(*reinterpret_cast<__half2*>(&raw.y), __hneg2(lim)), lim);
+        float2 x = __half22float2(h0), y = __half22float2(h1);
+        g[4 * q] = x.x; g[4 * q + 1] = x.y; g[4 * q + 2] = y.x; g[4 * q + 3] = y.y;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < N; ++q) g[q] = clamp_f16(__half2float(gp[q]));
+    }
+  } else {
+    const float* gp = reinterpret_cast<const float*>(gbase) + row_elem0 + e0;
+    if (N % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) {
+        float4 x = *reinterpret_cast<const float4*>(gp + 4 * q);
+        g[4 * q] = x.x; g[4 * q + 1] = x.y; g[4 * q + 2] = x.z; g[4 * q + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < N; ++q) g[q] = gp[q];
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void add_prepared(float (&acc)[N], const float (&g)[N], const GradPrep& p, bool plain) {
+  if (plain) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) acc[q] = __fadd_rn(acc[q], g[q]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) acc[q] = __fadd_rn(acc[q], p(g[q]));
+  }
+}
+
+// sum of the gradients of occurrences pos(0..cnt-1) (already in ascending order), elements [e0, e0+N).
+// Batches of 8 / 4 occurrences have all their loads issued together; the adds stay sequential.
+template <int N, bool F16, typename POS>
+__device__ __forceinline__ void reduce_sorted(float (&acc)[N], const ItemSrc& s, const ReduceArgs& a, const TableDev& t,
+                                              uint32_t cnt, uint32_t e0, POS pos) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) acc[q] = 0.0f;
+  uint32_t k = 0;
+  for (; k + 8 <= cnt; k += 8) {
+    uint32_t orow[8];
+    float g[8][N];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) orow[u] = occ_out_row(a, pos(k + u));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) load_grad_elems<N, F16>(g[u], s.gbase, (size_t)(orow[u] - s.slot_row0) * t.dim, e0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) add_prepared<N>(acc, g[u], grad_prep(s, a, orow[u]), s.plain);
+  }
+  if (k + 4 <= cnt) {
+    uint32_t orow[4];
+    float g[4][N];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) orow[u] = occ_out_row(a, pos(k + u));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_grad_elems<N, F16>(g[u], s.gbase, (size_t)(orow[u] - s.slot_row0) * t.dim, e0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add_prepared<N>(acc, g[u], grad_prep(s, a, orow[u]), s.plain);
+    k += 4;
+  }
+  for (; k < cnt; ++k) {
+    const uint32_t orow = occ_out_row(a, pos(k));
+    float g[N];
+    load_grad_elems<N, F16>(g, s.gbase, (size_t)(orow - s.slot_row0) * t.dim, e0);
+    add_prepared<N>(acc, g, grad_prep(s, a, orow), s.plain);
+  }
+}
+
+// slots whose gradient is skipped or holds a NaN (mod.rs:731-746), or that this launch does not step, as a bit mask
+__device__ __forceinline__ void build_dead_mask(uint32_t* dead, const GradsDev& gr, const ReduceArgs& a, uint32_t n_slots) {
+  if (threadIdx.x < PB_MAX_SLOTS / 32) dead[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t tick = *a.tick_ptr;
+  for (uint32_t s = threadIdx.x; s < PB_MAX_SLOTS; s += blockDim.x) {
+    const bool off = s >= n_slots || !gr.ptr[s] || a.nan_tick[s] == tick || !((a.round_mask[s >> 5] >> (s & 31)) & 1u);
+    if (off) atomicOr(&dead[s >> 5], 1u << (s & 31));
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ bool slot_dead(const uint32_t* dead, uint32_t slot) { return (dead[slot >> 5] >> (slot & 31)) & 1u; }
+
+// ------------------------------------------------------------------------------------------------
+// cold + warm items
+// ------------------------------------------------------------------------------------------------
+#ifndef PB_REDUCE_BLOCKS
+#define PB_REDUCE_BLOCKS 2  // resident blocks per SM k_reduce_items is compiled for (128 registers: four items per lane group in flight)
+#endif
+constexpr int COLD_ITEMS = 4;
+
+// one item through the generic path: sorted occurrence list pos(0..cnt-1)
+template <int VEC, bool F16, int KIND, typename POS>
+__device__ __forceinline__ void step_item(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
+                                          const GradsDev& gr, const ReduceArgs& a, uint32_t row, uint32_t slot,
+                                          uint32_t cnt, uint32_t lane, uint32_t G, uint32_t gmask, float* stage, POS pos) {
+  float* prow = t.rows + (size_t)row * t.stride;
+  const uint32_t nvec = t.dim / VEC;
+  const ItemSrc src = item_src(sl, gr, a, slot);
+  const StepCtx sc = step_ctx(prow, t, op, gr, slot);
+  for (uint32_t c = lane; c < nvec; c += G) {
+    RowElems<KIND, VEC> rc;
+    rc.load(prow, c * VEC, t, op);  // in flight while the gradients are fetched and summed
+    float acc[VEC];
+    reduce_sorted<VEC, F16>(acc, src, a, t, cnt, c * VEC, pos);
+    if (KIND == PB_OPT_ADAGRAD_VW) store_vec<VEC>(stage + c * VEC, acc);
+    rc.step(c * VEC, acc, t, op, hy, sc);
+    rc.store(prow, c * VEC, t, op);
+  }
+  if (KIND == PB_OPT_ADAGRAD_VW) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
+    __syncwarp(gmask);              // the staged gradient of every lane of the group is visible to lane 0
+    if (lane == 0) {
+      float gs = __fdiv_rn(vw_dot(stage, t.dim), (float)t.dim);
+      prow[t.dim] = __fadd_rn(__fmul_rn(sc.vw_state, op.mom), gs);
+    }
+    __syncwarp(gmask);
+  }
+}
+
+template <int VEC, bool F16, int KIND>
+__global__ void __launch_bounds__(256, PB_REDUCE_BLOCKS) k_reduce_items(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl,
+                                                                       GradsDev gr, ReduceArgs a, uint32_t G) {
+  __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
+  __shared__ uint32_t sortbuf[64][2 * PB_WARM_MAX];  // per lane group (G >= 4): unsorted | sorted occurrences
+  build_dead_mask(dead, gr, a, sl.n_slots);
+  const uint32_t lane = threadIdx.x % G;
+  const uint32_t grp = threadIdx.x / G;
+  const uint32_t wl = threadIdx.x & 31;
+  const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
+  const uint32_t n_groups = gridDim.x * (blockDim.x / G);
+  const uint32_t g_global = blockIdx.x * (blockDim.x / G) + grp;
+  const uint32_t n_cold = a.b.cnt[BC_COLD], n_warm = a.b.cnt[BC_WARM];
+  const uint32_t nvec = t.dim / VEC;
+
+  // ---- warm items first (the longer ones), handed out one at a time
+  {
+    uint32_t* next = a.b.cnt + BC_NEXT + a.round;
+    uint32_t* raw = sortbuf[grp];
+    uint32_t* srt = raw + PB_WARM_MAX;
+    for (;;) {
+      uint32_t w = 0;
+      if (lane == 0) w = atomicAdd(next, 1u);
+      w = __shfl_sync(gmask, w, wl / G * G);
+      if (w >= n_warm) break;
+      const uint4 d = a.b.warm[w];
+      const uint32_t row = d.x, base = d.y, cnt = d.z;
+      for (uint32_t l = lane; l < cnt; l += G) raw[l] = a.b.seg_occ[base + l];
+      __syncwarp(gmask);
+      for (uint32_t l = lane; l < cnt; l += G) {  // rank by counting: occurrences are distinct numbers
+        const uint32_t p = raw[l];
+        uint32_t r = 0;
+        for (uint32_t m = 0; m < cnt; ++m) r += raw[m] < p;
+        srt[r] = p;
+      }
+      __syncwarp(gmask);
+      const uint32_t slot = slot_of_occ(sl, srt[0]);
+      if (!slot_dead(dead, slot)) {
+        if (row >= t.capacity) {
+          if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
+        } else {
+          float* stage = a.vw_stage ? a.vw_stage + (size_t)(n_cold + w) * t.dim : nullptr;
+          step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, row, slot, cnt, lane, G, gmask, stage,
+                                    [&](uint32_t k) { return srt[k]; });
+        }
+      }
+      __syncwarp(gmask);  // the buffers are reused by the next item
+    }
+  }
+
+  // ---- cold items: COLD_ITEMS per group and iteration, every load issued before the first use
+  for (uint32_t w0 = g_global * COLD_ITEMS; w0 < n_cold; w0 += n_groups * COLD_ITEMS) {
+    if (KIND == PB_OPT_ADAGRAD_VW) {  // needs the whole reduced gradient staged: one item at a time
+      for (uint32_t w = w0; w < min(n_cold, w0 + COLD_ITEMS); ++w) {
+        const uint2 d = a.b.cold[w];
+        const uint32_t slot = slot_of_occ(sl, d.y);
+        if (slot_dead(dead, slot)) continue;
+        if (d.x >= t.capacity) {
+          if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+          continue;
+        }
+        const uint32_t occ = d.y;
+        step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, d.x, slot, 1u, lane, G, gmask, a.vw_stage + (size_t)w * t.dim,
+                                  [&](uint32_t) { return occ; });
+      }
+      continue;
+    }
+    float* prow[COLD_ITEMS];
+    ItemSrc src[COLD_ITEMS];
+    GradPrep prep[COLD_ITEMS];
+    StepCtx sc[COLD_ITEMS];
+    size_t gelem[COLD_ITEMS];
+    bool act[COLD_ITEMS];
+#pragma unroll
+    for (int k = 0; k < COLD_ITEMS; ++k) {
+      act[k] = w0 + k < n_cold;
+      uint2 d = make_uint2(ROW_NONE, 0u);
+      if (act[k]) d = a.b.cold[w0 + k];
+      uint32_t slot = 0;
+      if (act[k]) {
+        slot = slot_of_occ(sl, d.y);
+        act[k] = !slot_dead(dead, slot);
+      }
+      if (act[k] && d.x >= t.capacity) {
+        if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+        act[k] = false;
+      }
+      prow[k] = t.rows + (size_t)(act[k] ? d.x : 0u) * t.stride;
+      src[k] = item_src(sl, gr, a, slot);
+      const uint32_t orow = act[k] ? occ_out_row(a, d.y) : src[k].slot_row0;
+      prep[k] = grad_prep(src[k], a, orow);
+      gelem[k] = (size_t)(orow - src[k].slot_row0) * t.dim;
+      sc[k].vw_state = 0.0f;
+      sc[k].r1 = sc[k].r2 = 0.0f;
+      if (KIND == PB_OPT_ADAM && act[k]) sc[k] = step_ctx(prow[k], t, op, gr, slot);
+    }
+    for (uint32_t c = lane; c < nvec; c += G) {
+      RowElems<KIND, VEC> rc[COLD_ITEMS];
+      float g[COLD_ITEMS][VEC];
+#pragma unroll
+      for (int k = 0; k < COLD_ITEMS; ++k)
+        if (act[k]) rc[k].load(prow[k], c * VEC, t, op);
+#pragma unroll
+      for (int k = 0; k < COLD_ITEMS; ++k)
+        if (act[k]) load_grad_elems<VEC, F16>(g[k], src[k].gbase, gelem[k], c * VEC);
+#pragma unroll
+      for (int k = 0; k < COLD_ITEMS; ++k)
+        if (act[k]) {
+          float acc[VEC];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;  // the reference adds into a zeroed row (-0 -> +0)
+          add_prepared<VEC>(acc, g[k], prep[k], src[k].plain);
+          rc[k].step(c * VEC, acc, t, op, hy, sc[k]);
+          rc[k].store(prow[k], c * VEC, t, op);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hot items: bitmap order + cp.async.bulk / mbarrier ring
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t HOT_BITS = 65536;  // samples covered by one bitmap window (a PersiaBatch holds <= 65535 samples)
+constexpr uint32_t HOT_WORDS = HOT_BITS / 32;
+constexpr uint32_t HOT_ROWS = 32;     // gradient rows per ring stage (one bitmap word)
+constexpr uint32_t HOT_THREADS = 64;
+constexpr uint32_t WAIT_SPINS = 1u << 22;  // bounded waits: a lost completion voids the batch (CTR_ERR) instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; spins < WAIT_SPINS; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+// one row: global -> shared, completion counted in bytes on the stage's mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// EPL consecutive gradient elements of a staged (shared memory) or resident (global) row -> f32, clamped
+template <int EPL, bool F16>
+__device__ __forceinline__ void read_elems(float (&g)[EPL], const unsigned char* rowp, uint32_t e0) {
+  if constexpr (F16) {
+    const __half* p = reinterpret_cast<const __half*>(rowp) + e0;
+    if constexpr (EPL == 8) {
+      uint4 raw = *reinterpret_cast<const uint4*>(p);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 x = __half22float2(h[q]);
+        g[2 * q] = clamp_f16(x.x);
+        g[2 * q + 1] = clamp_f16(x.y);
+      }
+    } else if constexpr (EPL == 4) {
+      uint2 raw = *reinterpret_cast<const uint2*>(p);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float2 x = __half22float2(h[q]);
+        g[2 * q] = clamp_f16(x.x);
+        g[2 * q + 1] = clamp_f16(x.y);
+      }
+    } else if constexpr (EPL == 2) {
+      float2 x = __half22float2(*reinterpret_cast<const __half2*>(p));
+      g[0] = clamp_f16(x.x);
+      g[1] = clamp_f16(x.y);
+    } else {
+      g[0] = clamp_f16(__half2float(p[0]));
+    }
+  } else {
+    const float* p = reinterpret_cast<const float*>(rowp) + e0;
+    if constexpr (EPL % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < EPL / 4; ++q) {
+        float4 x = *reinterpret_cast<const float4*>(p + 4 * q);
+        g[4 * q] = x.x; g[4 * q + 1] = x.y; g[4 * q + 2] = x.z; g[4 * q + 3] = x.w;
+      }
+    } else if constexpr (EPL == 2) {
+      float2 x = *reinterpret_cast<const float2*>(p);
+      g[0] = x.x;
+      g[1] = x.y;
+    } else {
+      g[0] = p[0];
+    }
+  }
+}
+
+struct HotSmem {  // carved out of dynamic shared memory
+  unsigned char* ring;
+  uint32_t* bitmap;
+  float* vstage;
+  uint64_t* bars;  // [stages] full, [stages] empty
+};
+
+template <int EPL, bool F16>
+__global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                           ReduceArgs a, uint32_t stages, uint32_t bulk, uint32_t ring_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
+  __shared__ uint32_t s_item;
+  const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
+  HotSmem sm;
+  sm.ring = smem_raw;
+  sm.bitmap = reinterpret_cast<uint32_t*>(smem_raw + ring_bytes);
+  sm.vstage = reinterpret_cast<float*>(sm.bitmap + HOT_WORDS);
+  sm.bars = reinterpret_cast<uint64_t*>(sm.vstage + ((t.dim + 1u) & ~1u));
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (uint32_t s = 0; s < 2 * stages; ++s) mbar_init(smem_u32(sm.bars + s), 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  build_dead_mask(dead, gr, a, sl.n_slots);  // ends with __syncthreads
+  const uint32_t n_hot = a.b.cnt[BC_HOT];
+  uint32_t* next = a.b.cnt + BC_NEXT + PB_MAX_SLOTS + a.round;
+  const uint32_t n_pass = (t.dim + 32u * EPL - 1u) / (32u * EPL);
+  uint32_t it = 0;  // ring stages used so far: both warps count the same non-empty bitmap words
+  bool failed = false;
+  for (;;) {
+    __syncthreads();  // s_item and the bitmap are free again
+    if (tid == 0) s_item = atomicAdd(next, 1u);
+    __syncthreads();
+    const uint32_t h = s_item;
+    if (h >= n_hot) break;
+    const uint4 d = a.b.hot[h];
+    const uint32_t row = d.x, base = d.y, cnt = d.z;
+    const uint32_t slot = slot_of_occ(sl, a.b.seg_occ[base]);
+    if (slot_dead(dead, slot)) continue;
+    if (row >= t.capacity) {
+      if (tid == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+      continue;
+    }
+    const uint32_t lo = sl.occ_off[slot], hi = sl.occ_off[slot + 1];
+    const ItemSrc src = item_src(sl, gr, a, slot);
+    float* prow = t.rows + (size_t)row * t.stride;
+    const StepCtx sc = step_ctx(prow, t, op, gr, slot);
+    for (uint32_t pass = 0; pass < n_pass; ++pass) {
+      const uint32_t e0 = (pass * 32u + lane) * EPL;
+      const bool own = e0 < t.dim;  // lanes past the row's end idle
+      float acc[EPL];
+#pragma unroll
+      for (int q = 0; q < EPL; ++q) acc[q] = 0.0f;
+      for (uint32_t wbase = lo; wbase < hi; wbase += HOT_BITS) {
+        const uint32_t wend = min(hi, wbase + HOT_BITS);
+        const uint32_t n_words = (wend - wbase + 31u) / 32u;
+        for (uint32_t w = tid; w < n_words; w += HOT_THREADS) sm.bitmap[w] = 0u;
+        __syncthreads();
+        for (uint32_t k = tid; k < cnt; k += HOT_THREADS) {  // counting sort: one bit per occurrence
+          const uint32_t p = a.b.seg_occ[base + k];
+          if (p >= wbase && p < wend) atomicOr(&sm.bitmap[(p - wbase) >> 5], 1u << ((p - wbase) & 31u));
+        }
+        __syncthreads();
+        if (warp == 0) {
+          // ---- producer: one stage per non-empty word, one bulk copy per set bit
+          if (bulk) {
+            for (uint32_t w = 0; w < n_words; ++w) {
+              const uint32_t m = sm.bitmap[w];
+              if (!m) continue;
+              const uint32_t p = __popc(m), stage = it % stages, par = (it / stages) & 1u;
+              if (!failed && !mbar_wait(smem_u32(sm.bars + stages + stage), par ^ 1u)) failed = true;
+              const uint32_t full = smem_u32(sm.bars + stage);
+              if (lane == 0) mbar_expect_tx(full, p * rowbytes);
+              __syncwarp();
+              if (lane < p) {
+                const uint32_t occ = wbase + w * 32u + __fns(m, 0u, (int)lane + 1);
+                const uint32_t orow = occ_out_row(a, occ);
+                const unsigned char* g = reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow - src.slot_row0) * rowbytes;
+                bulk_g2s(smem_u32(sm.ring + ((size_t)stage * HOT_ROWS + lane) * rowbytes), g, rowbytes, full);
+              }
+              ++it;
+            }
+          }
+        } else {
+          // ---- consumer: the rows of a word in ascending order, a dependent add per row
+          for (uint32_t w = 0; w < n_words; ++w) {
+            const uint32_t m = sm.bitmap[w];
+            if (!m) continue;
+            const uint32_t p = __popc(m), stage = it % stages, par = (it / stages) & 1u;
+            if (bulk) {
+              if (!failed && !mbar_wait(smem_u32(sm.bars + stage), par)) failed = true;
+              const unsigned char* rows = sm.ring + (size_t)stage * HOT_ROWS * rowbytes;
+              for (uint32_t k = 0; k < p; k += 4) {
+                float g[4][EPL];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (own && k + u < p) read_elems<EPL, F16>(g[u], rows + (size_t)(k + u) * rowbytes, e0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (own && k + u < p) {
+                    GradPrep gp;
+                    gp.do_scale = gp.do_sqrt = false;
+                    if (!src.plain) gp = grad_prep(src, a, occ_out_row(a, wbase + w * 32u + __fns(m, 0u, (int)(k + u) + 1)));
+                    add_prepared<EPL>(acc, g[u], gp, src.plain);
+                  }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(sm.bars + stages + stage));  // the stage may be refilled
+            } else {
+              for (uint32_t k = 0; k < p; k += 8) {
+                float g[8][EPL];
+                uint32_t orow[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (k + u < p) orow[u] = occ_out_row(a, wbase + w * 32u + __fns(m, 0u, (int)(k + u) + 1));
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (own && k + u < p)
+                    read_elems<EPL, F16>(g[u], reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow[u] - src.slot_row0) * rowbytes, e0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (own && k + u < p) add_prepared<EPL>(acc, g[u], grad_prep(src, a, orow[u]), src.plain);
+              }
+            }
+            ++it;
+          }
+        }
+        __syncthreads();  // the bitmap is rebuilt for the next window / pass / item
+      }
+      // ---- the optimizer step on this pass's elements (consumer warp)
+      if (warp == 1 && own) {
+        RowElems<-1, EPL> rc;
+        rc.load(prow, e0, t, op);
+        if (op.kind == PB_OPT_ADAGRAD_VW) {
+#pragma unroll
+          for (int q = 0; q < EPL; ++q) sm.vstage[e0 + q] = acc[q];
+        }
+        rc.step(e0, acc, t, op, hy, sc);
+        rc.store(prow, e0, t, op);
+      }
+    }
+    if (op.kind == PB_OPT_ADAGRAD_VW && warp == 1) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
+      __syncwarp();
+      if (lane == 0) {
+        float gs = __fdiv_rn(vw_dot(sm.vstage, t.dim), (float)t.dim);
+        prow[t.dim] = __fadd_rn(__fmul_rn(sc.vw_state, op.mom), gs);
+      }
+    }
+  }
+  if (failed && lane == 0) atomicAdd(&t.counters[CTR_ERR], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers (host)
+// ------------------------------------------------------------------------------------------------
+template <int VEC, bool F16>
+static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
+                           const ReduceArgs& a, uint32_t G, cudaStream_t st) {
+  static const uint32_t tune_grid = getenv("PB_REDUCE_GRID") ? (uint32_t)atoi(getenv("PB_REDUCE_GRID")) : 148u * PB_REDUCE_BLOCKS;
+  const uint32_t full = cdiv((uint64_t)a.b.n * G, 256);
+  const uint32_t grid = full < tune_grid ? full : tune_grid;
+#define PB_K(KK)                                                                                                   \
+  case KK:                                                                                                         \
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_items<VEC, F16, KK>), grid, 256, 0, st, t, op, hy, sl, gr, a, G);          \
+    break;
+  switch (op.kind) { PB_K(PB_OPT_SGD) PB_K(PB_OPT_ADAGRAD) PB_K(PB_OPT_ADAGRAD_VW) PB_K(PB_OPT_ADAM) }
+#undef PB_K
+}
+
+template <int EPL, bool F16>
+static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
+                       const ReduceArgs& a, uint32_t bulk, cudaStream_t st) {
+  const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
+  uint32_t stages = 8;
+  while (stages > 2 && (size_t)stages * HOT_ROWS * rowbytes > 64u * 1024u) stages >>= 1;
+  if (bulk && (size_t)stages * HOT_ROWS * rowbytes > 160u * 1024u) bulk = 0;  // rows too long for a ring: plain loads
+  if (!bulk) stages = 1;
+  const size_t ring = bulk ? (size_t)stages * HOT_ROWS * rowbytes : 0;
+  const size_t smem = ring + HOT_WORDS * 4u + (((size_t)t.dim + 1u) & ~(size_t)1u) * 4u + 2u * stages * 8u;
+  auto kern = k_reduce_hot<EPL, F16>;
+  static size_t configured[64] = {0};  // per instantiation and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured[dev] = smem;
+  }
+  uint32_t per_sm = (uint32_t)(200u * 1024u / (smem + 1024u));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t cap_blocks = cdiv(a.b.n, PB_WARM_MAX + 1);  // at most this many hot items exist
+  uint32_t grid = 148u * per_sm;
+  if (grid > cap_blocks) grid = cap_blocks ? cap_blocks : 1;
+  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, stages, bulk, (uint32_t)ring);
+}
+
+void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
+                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot) {
+  if (!a.b.n) return;
+  int vec, Gi;
+  vec_group(t.dim, vec, Gi);
+  uint32_t G = (uint32_t)Gi < 4u ? 4u : (uint32_t)Gi;
+  // hot items first in time when they have their own stream: they are the long poles
+  {
+    const uint32_t dim = t.dim;
+    int epl;
+    if (dim % 2 == 0 && dim <= 64) epl = 2;
+    else if (dim % 4 == 0 && dim <= 128) epl = 4;
+    else if (dim % 8 == 0) epl = 8;
+    else if (dim % 2 == 0 && dim > 64) epl = 2;  // several passes
+    else epl = 1;
+    const uint32_t rowbytes = dim * (f16 ? 2u : 4u);
+    uint32_t bulk = rowbytes % 16u == 0 ? 1u : 0u;
+    for (uint32_t s = 0; s < sl.n_slots && bulk; ++s)
+      if (gr.ptr[s] && (reinterpret_cast<uintptr_t>(gr.ptr[s]) & 15u)) bulk = 0;  // cp.async.bulk needs 16 B alignment
+    if (getenv("PB_HOT_NO_BULK")) bulk = 0;
+#define PB_H(E)                                                                         \
+  case E:                                                                               \
+    if (f16) hot_launch<E, true>(t, op, hy, sl, gr, a, bulk, st_hot);                   \
+    else hot_launch<E, false>(t, op, hy, sl, gr, a, bulk, st_hot);                      \
+    break;
+    switch (epl) { PB_H(1) PB_H(2) PB_H(4) PB_H(8) }
+#undef PB_H
+  }
+  if (vec == 4) {
+    if (f16) items_dispatch<4, true>(t, op, hy, sl, gr, a, G, st);
+    else items_dispatch<4, false>(t, op, hy, sl, gr, a, G, st);
+  } else {
+    if (f16) items_dispatch<1, true>(t, op, hy, sl, gr, a, G, st);
+    else items_dispatch<1, false>(t, op, hy, sl, gr, a, G, st);
+  }
+}
+
+}  // namespace pb

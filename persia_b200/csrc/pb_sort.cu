@@ -1,17 +1,12 @@
-// pb_sort.cu — stable LSD radix partition of a batch's id occurrences (SURVEY.md §8a rows A3, A8 grouping).
+// pb_sort.cu — stable LSD radix partition of a batch's signs by shard.
 //
 // "Warp-radix partition": ranks inside a warp come from __match_any_sync, across warps from per-warp digit
 // counters in shared memory, across blocks from a block-major digit histogram that every scatter block folds
 // itself (no separate scan kernel).  A scatter pass also builds the histogram of the next pass with global
 // REDs on each element's destination tile, so a k-pass sort is 1 + k launches.  Digits are 9 bits.
 //
-// Two uses:
-//  * backward grouping: key = position of the first occurrence of the occurrence's sign in the batch (elected
-//    per row by the forward pass, materialised by the histogram pass), payload = position | slot << 24.
-//    After the sort the occurrences of one sign are adjacent, ordered by slot and then by ascending position —
-//    the order FeatureBatch::new pushed them (persia-common/src/lib.rs:45-82) — and signs follow each other in
-//    first-seen order; the key does not depend on thread timing, so neither does anything derived from it.
-//  * pb_partition_by_shard: key = farmhash64(sign) % R, one pass (indices_to_sharded_indices, mod.rs:454-479).
+// Use: pb_partition_by_shard: key = farmhash64(sign) % R, one pass (indices_to_sharded_indices, mod.rs:454-479).
+// (Round 1 also grouped the backward's occurrences with it; the batched path now dedups first, pb_dedup.cu.)
 #include "pb_group.cuh"
 
 namespace pb {
@@ -59,40 +54,6 @@ uint32_t radix_hist_zero_words(uint32_t n) {  // what must be zero before the hi
 }
 
 void launch_zero_words(uint32_t* p, uint32_t n_words, cudaStream_t st);
-
-// Sorts the occurrences of a batch by the first occurrence of their sign (stable), i.e. groups them per
-// sign in first-seen order.  keys_a receives the materialised keys; the result alternates between the
-// (keys_b, vals_b) and (keys_a, vals_a) pairs; returns 0 if it ends in the a pair, 1 if in the b pair.
-// hist: 4 x radix_hist_words() u32, the first pass's rows zero on entry.
-int launch_radix_sort_leader(const TableDev& t, const uint32_t* occ_row, uint32_t n, const SlotsDev& sl, uint32_t* keys_a,
-                             uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist, uint32_t* zero4,
-                             cudaStream_t st) {
-  if (!n) return 0;
-  uint32_t bits = 1;
-  while ((1ull << bits) <= (uint64_t)n) ++bits;  // keys are in [0, n]
-  uint32_t passes = (bits + RS_BITS - 1) / RS_BITS;
-  uint32_t tile = radix_tile(n), nb = cdiv(n, tile);
-  const uint32_t W = radix_hist_words();
-  uint32_t* h[4] = {hist, hist + W, hist + 2 * W, hist + 3 * W};
-  SrcLeader src{occ_row, t.row_lead, n};
-  PB_LAUNCH_F(FAM_SORT, (k_radix_hist<SrcLeader>), cdiv(n, RH_KEYS), RS_THREADS, 0, st, src, n, tile, keys_a, h[0],
-              passes > 1 ? h[1] : nullptr, passes > 2 ? h[2] : nullptr, passes > 3 ? h[3] : nullptr, zero4);
-  const uint32_t* kin = keys_a;
-  const uint32_t* vin = nullptr;
-  ValOccSlot vop{sl};
-  int cur = 0;  // pair holding the current input keys (a after the histogram pass)
-  for (uint32_t p = 0; p < passes; ++p) {
-    cur ^= 1;
-    uint32_t* kout = cur == 0 ? keys_a : keys_b;
-    uint32_t* vout = cur == 0 ? vals_a : vals_b;
-    uint32_t* hn = (p + 1 < passes) ? h[p + 1] : nullptr;
-    PB_LAUNCH_F(FAM_SORT, (k_radix_scatter<ValOccSlot>), nb, RS_THREADS, 0, st, kin, vin, kout, vout, n, p * RS_BITS, tile,
-                vop, h[p], hn);
-    kin = kout;
-    vin = vout;
-  }
-  return cur;
-}
 
 __global__ void k_zero_words(uint32_t* p, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;

@@ -55,7 +55,7 @@ SYMBOLS = {
     "pb_table_clear": (_i32, [_vp, _vp]),
     "pb_table_entry_len": (_i32, [_vp, C.POINTER(_u32)]),
     "pb_table_set_eviction": (_i32, [_vp, _u32, _u64, _u64, _u32]),
-    "pb_table_counters": (_i32, [_vp, C.POINTER(_u64 * 4), _vp]),
+    "pb_table_counters": (_i32, [_vp, C.POINTER(_u64 * 5), _vp]),
     "pb_lookup": (_i32, [_vp, _vp, _u32, _i32, _vp, _vp]),
     "pb_update": (_i32, [_vp, _vp, _vp, _u32, _vp]),
     "pb_set_rows": (_i32, [_vp, _vp, _vp, _u32, _vp]),
@@ -69,15 +69,6 @@ SYMBOLS = {
     "pb_ctx_create": (_i32, [_i32, _u32, _u32, C.POINTER(_vp)]),
     "pb_ctx_destroy": (_i32, [_vp]),
     "pb_ctx_set_slots": (_i32, [_vp, C.POINTER(SlotsCfg)]),
-    "pb_ctx_set_strict_reduce": (_i32, [_vp, _i32]),
-    "pb_ctx_set_owner_mode": (_i32, [_vp, _i32]),
-    "pb_ctx_set_async_grouping": (_i32, [_vp, _i32]),
-    "pb_permute_u64": (_i32, [_vp, _vp, _u32, _vp, _vp]),
-    "pb_permute_rows": (_i32, [_vp, _vp, _u32, _u32, _i32, _vp, _vp]),
-    "pb_frame_signs": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
-    "pb_frame_rows": (_i32, [_vp, _vp, _vp, _u32, _u32, _u32, _i32, _vp, _vp]),
-    "pb_p2p_exchange": (_i32, [_vp, C.POINTER(_u64), _u32, _u32, _u32, _u32, _vp]),
-    "pb_p2p_barrier": (_i32, [C.POINTER(_u64), _vp, _u32, _u32, _vp, _vp]),
     "pb_forward": (_i32, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp]),
     "pb_backward": (_i32, [_vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp]),
     "pb_forward_raw": (_i32, [_vp, _vp, _vp, _u32, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

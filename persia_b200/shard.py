@@ -68,9 +68,10 @@ class EmbeddingShard:
         return self._entry_len
 
     def counters(self):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 5)()
         N.check(self.lib.pb_table_counters(self.h, C.byref(out), _stream(self.device)))
-        return {"admitted": out[0], "lookup_miss": out[1], "gradient_id_miss": out[2], "capacity_refused": out[3]}
+        return {"admitted": out[0], "lookup_miss": out[1], "gradient_id_miss": out[2], "capacity_refused": out[3],
+                "wait_errors": out[4]}
 
     def __len__(self):
         return int(self.counters()["admitted"])
@@ -153,18 +154,6 @@ class BatchContext:
             cfg.prefix[i] = int(p)
             cfg.sqrt_scaling[i] = int(bool(sqrt_scaling[i])) if sqrt_scaling is not None else 0
         N.check(self.lib.pb_ctx_set_slots(self.h, C.byref(cfg)))
-
-    def set_strict_reduce(self, on=True):
-        """Sequential (reference-order) gradient reduction for any multiplicity; see persia_b200.h."""
-        N.check(self.lib.pb_ctx_set_strict_reduce(self.h, int(on)))
-
-    def set_async_grouping(self, on=True):
-        """Overlap the backward's grouping with the forward's gather / the dense tower; see persia_b200.h."""
-        N.check(self.lib.pb_ctx_set_async_grouping(self.h, int(on)))
-
-    def set_owner_mode(self, on=True):
-        """Serve already-sharded requests (no u16 sample-index limit); see persia_b200.h."""
-        N.check(self.lib.pb_ctx_set_owner_mode(self.h, int(on)))
 
     def forward(self, shard, ids, slot_occ_off, batch, row_off=None, training=True, out=None):
         """ids: flat device int64-bit ids (slot-major); slot_occ_off: host list, n_slots+1;
@@ -297,63 +286,3 @@ def partition_by_shard(signs, R):
     work = torch.empty(wb, dtype=torch.uint8, device=signs.device)
     N.check(lib.pb_partition_by_shard(_ptr(signs), n, R, _ptr(perm), _ptr(counts), _ptr(work), wb, _stream(signs.device)))
     return perm, counts
-
-
-def permute_u64(src, perm, out=None):
-    """out[i] = src[perm[i]] for int64-bit ids."""
-    lib = N.load()
-    src = _as_i64_bits(src)
-    if out is None:
-        out = torch.empty(perm.numel(), dtype=torch.int64, device=src.device)
-    N.check(lib.pb_permute_u64(_ptr(src), _ptr(perm), perm.numel(), _ptr(out), _stream(src.device)))
-    return out
-
-
-def permute_rows(src, perm, scatter=False, out=None):
-    """Rows of a 2-D contiguous tensor: gather out[i] = src[perm[i]] or scatter out[perm[i]] = src[i]."""
-    lib = N.load()
-    assert src.is_contiguous() and src.dim() == 2
-    row_bytes = src.shape[1] * src.element_size()
-    if out is None:
-        out = torch.empty_like(src)
-    N.check(lib.pb_permute_rows(_ptr(src), _ptr(perm), perm.numel(), row_bytes, int(scatter), _ptr(out),
-                                _stream(src.device)))
-    return out
-
-
-def frame_signs(signs, perm, counts, R, cap, overflow, out=None):
-    lib = N.load()
-    signs = _as_i64_bits(signs)
-    if out is None:
-        out = torch.empty(R * cap, dtype=torch.int64, device=signs.device)
-    N.check(lib.pb_frame_signs(_ptr(signs), _ptr(perm), _ptr(counts), R, cap, _ptr(out), _ptr(overflow), _stream(signs.device)))
-    return out
-
-
-def frame_rows(src, perm, counts, R, cap, pack, out):
-    """pack: batch-order rows [n, w] -> framed [R*cap, w]; unpack: framed -> batch order (out must be [n, w])."""
-    lib = N.load()
-    assert src.is_contiguous() and out.is_contiguous()
-    row_bytes = src.shape[1] * src.element_size()
-    N.check(lib.pb_frame_rows(_ptr(src), _ptr(perm), _ptr(counts), R, cap, row_bytes, int(pack), _ptr(out), _stream(src.device)))
-    return out
-
-
-def p2p_exchange(framed, peer_ptrs, my_rank, cap):
-    """Store segment q of `framed` ([R*cap, w] or [R*cap]) into peer q's receive buffer at slot my_rank."""
-    lib = N.load()
-    R = len(peer_ptrs)
-    row_bytes = framed.element_size() * (framed.shape[1] if framed.dim() == 2 else 1)
-    ptrs = (C.c_uint64 * R)(*[int(p) for p in peer_ptrs])
-    if row_bytes % 16:  # 8-byte signs travel as pairs (cap is even)
-        assert row_bytes == 8 and cap % 2 == 0
-        N.check(lib.pb_p2p_exchange(_ptr(framed), ptrs, R, my_rank, cap // 2, 16, _stream(framed.device)))
-    else:
-        N.check(lib.pb_p2p_exchange(_ptr(framed), ptrs, R, my_rank, cap, row_bytes, _stream(framed.device)))
-
-
-def p2p_barrier(flag_ptrs, epoch, my_rank, err):
-    lib = N.load()
-    R = len(flag_ptrs)
-    ptrs = (C.c_uint64 * R)(*[int(p) for p in flag_ptrs])
-    N.check(lib.pb_p2p_barrier(ptrs, _ptr(epoch), R, my_rank, _ptr(err), _stream(epoch.device)))

@@ -3,7 +3,7 @@ HBM), batch 4096, Zipf(1.05) ids.  The oracle cannot hold 1e8 rows, so parity is
 
 * a real training step is replayed on the oracle for exactly the rows the batch touches (the oracle's rows are
   seeded from the GPU's with set_embedding — the reference's own debug loader, lib.rs:433-449), then every touched
-  row is compared bit for bit (strict reduction order) / within the piecewise tolerance (default order);
+  row is compared bit for bit (the gradient sums keep the reference order for every multiplicity);
 * size-independent properties: a repeated forward is idempotent and admits nothing, the batched forward equals the
   f16 rounding of the direct lookup, zero gradients leave Adagrad rows untouched (momentum 1), and a batch whose
   samples are permuted produces the same rows when the gradient sums are exact in f32.
@@ -59,15 +59,14 @@ def _signs(oracle, ids, pf):
     return np.concatenate([oracle.add_prefix(ids[i * B:(i + 1) * B], 8, pf[i]) for i in range(S)])
 
 
-@pytest.mark.parametrize("strict", [True, False])
-def test_full_size_step_matches_oracle(torch_cuda, full, oracle, strict):
+@pytest.mark.parametrize("which", [0, 1])
+def test_full_size_step_matches_oracle(torch_cuda, full, oracle, which):
     torch = torch_cuda
     s, ctx, ids, slot_off, pf, _ = full
-    ctx.set_strict_reduce(strict)
     oracle.set_rsqrt_exact(True)
     try:
-        rng = np.random.default_rng(17 + strict)
-        b = ids[0 if strict else 1]
+        rng = np.random.default_rng(17 + which)
+        b = ids[which]
         d_ids = to_dev_ids(b, DEV)
         out = ctx.forward(s, d_ids, slot_off, B, training=True)  # admits what is new
         signs = np.unique(_signs(oracle, b, pf))
@@ -84,18 +83,11 @@ def test_full_size_step_matches_oracle(torch_cuda, full, oracle, strict):
         assert st.tolist() == w.backward(octx, [g[i] for i in range(S)])
         ent2 = s.get_entries(to_dev_ids(signs, DEV))[0].cpu().numpy()
         ref = np.stack([w.get_entry(int(x)) for x in signs])
-        if strict:
-            assert ent2.tobytes() == ref.tobytes()
-        else:  # signs repeated > 32 times in a slot are reduced piecewise: same values, other f32 association
-            np.testing.assert_allclose(ent2, ref, rtol=2e-4, atol=1e-7)
-            few = np.ones(signs.size, bool)
-            for i in range(S):
-                sg, cnt = np.unique(oracle.add_prefix(b[i * B:(i + 1) * B], 8, pf[i]), return_counts=True)
-                few[np.searchsorted(signs, sg[cnt > 32])] = False
-            assert ent2[few].tobytes() == ref[few].tobytes()
+        # every sign, whatever its multiplicity (tiny slots repeat one id thousands of times): reference order
+        assert ent2.tobytes() == ref.tobytes()
+        assert s.counters()["wait_errors"] == 0
     finally:
         oracle.set_rsqrt_exact(False)
-        ctx.set_strict_reduce(False)
 
 
 def test_full_size_properties(torch_cuda, full, oracle):
