@@ -181,6 +181,38 @@ int pb_forward_raw(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ
 int pb_backward_raw(pb_table* t, pb_ctx* c, const void* d_grad, int is_f16, float scale, int32_t* d_status,
                     void* stream);
 
+/* ---- the same two calls over the R GPUs of one box ------------------------------------------------------------------
+ * Every rank is the embedding worker of its own batches and parameter server `rank` (rows with
+ * farmhash64(sign) % R == rank, sign_to_shard_modulo, embedding_worker_service/mod.rs:341-345).  The EW's fan-out
+ * (one lookup_mixed / update_gradient_mixed per server, mod.rs:886-919, :835-859) is done by the kernels themselves:
+ * the distinct signs of the batch (mod.rs:454-479 shards the deduplicated signs), the returned rows and the reduced
+ * gradients are stored straight into the receiver's area over NVLink peer mappings, ordered by flag words in that
+ * area.  No NCCL and no host on the data path; a step is capturable in a CUDA graph.
+ *
+ * A rank's batch is one request per owner, as with R data-parallel NN workers in the reference; an owner serves the
+ * forward requests of a step together and applies the R gradient requests one after another in rank order (the
+ * reference applies them in arrival order).  Both calls are collective: every rank of the box calls them once per
+ * step.  A rank's receive area is pb_xchg_bytes() bytes of zero-initialised device memory that all ranks can store
+ * to (CUDA peer access / symmetric memory); h_peer_base[q] is rank q's area as mapped in this process, 256-byte
+ * aligned; cap = slots per (source, owner) pair, i.e. the most distinct signs one rank may request of one owner in one
+ * batch; rows_f32 != 0 returns f32 rows (needed for ragged layouts, which pool on the requester; f16 otherwise). */
+typedef struct pb_xchg pb_xchg;
+uint64_t pb_xchg_bytes(uint32_t R, uint32_t cap, uint32_t dim, int rows_f32);
+int pb_xchg_create(int device, uint32_t R, uint32_t rank, uint32_t cap, uint32_t dim, int rows_f32,
+                   const uint64_t* h_peer_base, pb_xchg** out);
+int pb_xchg_destroy(pb_xchg* x);
+/* h_out[0] != 0: a batch needed more than cap slots for one pair (its excess signs read as zeros and took no
+ * gradient: re-run it with a larger cap); h_out[1] != 0: a wait for a peer gave up.  Synchronises `stream`. */
+int pb_xchg_status(pb_xchg* x, uint32_t h_out[2], void* stream);
+/* forward_batched_direct over R shards: arguments as pb_forward.  Not supported here yet: Adam, slots sharing a
+ * feature group, raw slots. */
+int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
+                       const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream);
+/* update_gradient_batched over R shards: arguments as pb_backward.  The NaN rule is applied per slot on the requesting
+ * rank, before anything is sent (mod.rs:731-746). */
+int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h_grads, int is_f16, const float* h_scale,
+                        int32_t* d_slot_status, void* stream);
+
 /* Number of kernels the library has launched on behalf of the caller since load (bench bookkeeping). */
 uint64_t pb_launch_count(void);
 /* Bench instrumentation: launches of the kernel families selected by the bit mask are bracketed by CUDA events on

@@ -748,6 +748,209 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
   return PB_OK;
 }
 
+// ---- the sharded path: R GPUs of one box -------------------------------------------------------------
+struct pb_xchg {
+  int device = 0;
+  uint32_t dim = 0;
+  XchgDev d{};
+  uint32_t* mem = nullptr;  // epoch | waited | own_cnt | err | own_row
+};
+
+namespace {
+uint64_t round256(uint64_t v) { return (v + 255u) & ~(uint64_t)255u; }
+void xchg_layout(uint32_t R, uint32_t cap, uint32_t dim, int rows_f32, uint64_t off[5]) {
+  off[0] = round256((uint64_t)XC_WORDS * PB_MAX_RANKS * 4);                        // sign
+  off[1] = off[0] + round256((uint64_t)R * cap * 8);                               // row
+  off[2] = off[1] + round256((uint64_t)R * cap * dim * (rows_f32 ? 4 : 2));        // grad
+  off[3] = off[2] + round256((uint64_t)R * cap * dim * 4);                         // gok
+  off[4] = off[3] + round256((uint64_t)R * cap * 4);                               // end
+}
+}  // namespace
+
+uint64_t pb_xchg_bytes(uint32_t R, uint32_t cap, uint32_t dim, int rows_f32) {
+  if (R == 0 || R > PB_MAX_RANKS || cap == 0 || dim == 0) return 0;
+  uint64_t off[5];
+  xchg_layout(R, cap, dim, rows_f32, off);
+  return off[4];
+}
+
+int pb_xchg_create(int device, uint32_t R, uint32_t rank, uint32_t cap, uint32_t dim, int rows_f32,
+                   const uint64_t* h_peer_base, pb_xchg** out) {
+  if (!out || !h_peer_base || R == 0 || R > PB_MAX_RANKS || rank >= R || cap == 0 || dim == 0)
+    return fail(PB_ERR_INVALID, "bad argument");
+  if ((uint64_t)R * cap >= 0xFFFFFFF0ull) return fail(PB_ERR_INVALID, "R * cap must stay below 2^32 - 16");
+  for (uint32_t q = 0; q < R; ++q)
+    if (!h_peer_base[q] || (h_peer_base[q] & 255u)) return fail(PB_ERR_INVALID, "receive areas must be mapped and 256-byte aligned");
+  DeviceGuard g(device);
+  pb_xchg* x = new pb_xchg();
+  x->device = device;
+  x->dim = dim;
+  uint64_t off[5];
+  xchg_layout(R, cap, dim, rows_f32, off);
+  XchgDev& d = x->d;
+  std::memset(&d, 0, sizeof(d));
+  for (uint32_t q = 0; q < R; ++q) d.base[q] = h_peer_base[q];
+  d.off_sign = off[0];
+  d.off_row = off[1];
+  d.off_grad = off[2];
+  d.off_gok = off[3];
+  d.R = R;
+  d.rank = rank;
+  d.cap = cap;
+  d.row_f32 = rows_f32 ? 1 : 0;
+  const size_t words = XC_WORDS + (size_t)XC_WORDS * PB_MAX_RANKS + PB_MAX_RANKS + 4 + (size_t)R * cap;
+  cudaError_t e = cudaMalloc(&x->mem, 4 * words);
+  if (e == cudaSuccess) e = cudaMemset(x->mem, 0, 4 * words);
+  if (e != cudaSuccess) {
+    delete x;
+    return fail(PB_ERR_CUDA, std::string("pb_xchg_create: ") + cudaGetErrorString(e));
+  }
+  d.epoch = x->mem;
+  d.waited = d.epoch + XC_WORDS;
+  d.own_cnt = d.waited + (size_t)XC_WORDS * PB_MAX_RANKS;
+  d.err = d.own_cnt + PB_MAX_RANKS;
+  d.own_row = d.err + 4;
+  *out = x;
+  return PB_OK;
+}
+
+int pb_xchg_destroy(pb_xchg* x) {
+  if (!x) return PB_OK;
+  DeviceGuard g(x->device);
+  cudaDeviceSynchronize();
+  if (x->mem) cudaFree(x->mem);
+  delete x;
+  return PB_OK;
+}
+
+int pb_xchg_status(pb_xchg* x, uint32_t h_out[2], void* stream) {
+  if (!x || !h_out) return fail(PB_ERR_INVALID, "null argument");
+  DeviceGuard g(x->device);
+  PB_CUDA(cudaMemcpyAsync(h_out, x->d.err, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return PB_OK;
+}
+
+int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
+                       const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream) {
+  if (!t || !c || !x || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
+  if (!c->has_slots) return fail(PB_ERR_STATE, "pb_ctx_set_slots not called");
+  if (t->device != c->device || t->device != x->device) return fail(PB_ERR_INVALID, "table, context and exchange live on different devices");
+  if (x->dim != t->cfg.dim) return fail(PB_ERR_INVALID, "the exchange was sized for another embedding dim");
+  if (batch > 65535) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
+  if (c->n_rounds != 1) return fail(PB_ERR_INVALID, "slots sharing a feature group are not supported on the sharded path");
+  if (t->has_op && t->op.kind == PB_OPT_ADAM) return fail(PB_ERR_INVALID, "Adam is not supported on the sharded path yet");
+  if (d_row_off && !x->d.row_f32) return fail(PB_ERR_INVALID, "ragged layouts need an exchange created with f32 rows");
+  uint32_t S = c->slots.n_slots;
+  uint64_t n_out = (uint64_t)S * batch;
+  if (n_occ > c->max_occ || n_out > c->max_out) return fail(PB_ERR_CAPACITY, "batch exceeds the context's capacity");
+  if (!d_row_off && n_occ != n_out) return fail(PB_ERR_INVALID, "row offsets are required unless every sample has one id per slot");
+  if (h_slot_occ_off[0] != 0 || h_slot_occ_off[S] != n_occ) return fail(PB_ERR_INVALID, "slot offsets do not span the id array");
+  for (uint32_t s = 0; s < S; ++s)
+    if (h_slot_occ_off[s] > h_slot_occ_off[s + 1]) return fail(PB_ERR_INVALID, "slot offsets must ascend");
+  int rc;
+  // every rank serves lookups whether or not its own batch trains: the shard must be usable (a collective call)
+  if ((rc = ready_for_training(t))) return rc;
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_alloc(t))) return rc;
+  SlotsDev sl;
+  if ((rc = make_slots(c->slots, h_slot_occ_off, sl))) return rc;
+  if (c->set_dirty) {
+    launch_clear_items(c->b, st);
+    c->set_dirty = false;
+  }
+  drop_pending(c);
+  if (training) {
+    if ((rc = maybe_evict(t, st))) return rc;
+  }
+  launch_begin_batch(t->d, training ? c->dev_tick : nullptr, c->b.cnt, st, training != 0);
+  c->b.n = n_occ;
+  launch_dedup(sl, c->b, d_ids, st);
+  launch_route_items(training != 0, sl, c->b, x->d, st);                 // requester: signs -> owners' areas
+  launch_signal(x->d, XC_FLAG_SIGN, c->b.cnt + BC_PEER, st);
+  launch_wait(x->d, XC_FLAG_SIGN, -1, st);
+  launch_owner_lookup(training != 0, t->d, t->hy, t->op, x->d, st);      // owner: rows -> requesters' areas
+  launch_signal(x->d, XC_FLAG_ROW, nullptr, st);
+  launch_wait(x->d, XC_FLAG_ROW, -1, st);
+  launch_expand_items(t->d, sl, c->b, x->d, d_row_off, (uint32_t)n_out, batch, training != 0, d_out_f16, st);
+  if (training) {
+    c->n_occ = n_occ;
+    c->batch = batch;
+    c->multi_id = d_row_off != nullptr;
+    std::memcpy(c->occ_off, h_slot_occ_off, sizeof(uint32_t) * (S + 1));
+    if (d_row_off) {
+      PB_CUDA(cudaMemcpyAsync(c->row_off, d_row_off, 4 * (n_out + 1), cudaMemcpyDeviceToDevice, st));
+      launch_expand_rows(c->row_off, (uint32_t)n_out, c->occ_outrow, st);
+    }
+    c->pending = true;
+    c->pending_table = t;
+    t->pending_batches++;
+    c->set_dirty = true;
+  } else {
+    launch_clear_items(c->b, st);
+  }
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
+int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h_grads, int is_f16, const float* h_scale,
+                        int32_t* d_slot_status, void* stream) {
+  if (!t || !c || !x || !h_grads) return fail(PB_ERR_INVALID, "null argument");
+  if (!c->pending) return fail(PB_ERR_STATE, "no forward batch is pending in this context (backward_ref_id not found)");
+  if (c->pending_table != t) return fail(PB_ERR_INVALID, "the pending batch was looked up in another table");
+  int rc = ready_for_training(t);
+  if (rc) return rc;
+  DeviceGuard g(t->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t S = c->slots.n_slots;
+  SlotsDev sl;
+  if ((rc = make_slots(c->slots, c->occ_off, sl))) return rc;
+  GradsDev gr;
+  std::memset(&gr, 0, sizeof(gr));
+  for (uint32_t s = 0; s < S; ++s) {
+    gr.ptr[s] = h_grads[s];
+    float sc = h_scale ? h_scale[s] : 1.0f;
+    gr.do_scale[s] = std::fabs(sc - 1.0f) > 1.1920929e-07f;
+    float inv = 1.0f / sc;
+    if (gr.do_scale[s] && !std::isfinite(inv)) return fail(PB_ERR_INVALID, "scale on gradient must be finite");
+    gr.inv_scale[s] = inv;
+  }
+  PB_CUDA(cudaEventRecord(c->ev_fork, st));
+  PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  if (c->set_dirty) {
+    launch_clear_items(c->b, c->side);
+    c->set_dirty = false;
+  }
+  uint32_t elems = c->batch * t->d.dim;
+  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);  // per slot, on the requester (mod.rs:731-746)
+  PB_CUDA(cudaEventRecord(c->ev_nan, st));
+  PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_nan, 0));
+  ReduceArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.b = c->b;
+  a.b.n = c->n_occ;
+  a.occ_outrow = c->multi_id ? c->occ_outrow : nullptr;
+  a.row_off = c->multi_id ? c->row_off : nullptr;
+  a.tick_ptr = c->dev_tick;
+  a.nan_tick = c->nan_tick;
+  a.batch = c->batch;
+  a.round = 0;
+  for (uint32_t s = 0; s < S; ++s) a.round_mask[s >> 5] |= 1u << (s & 31);
+  a.x = x->d;
+  launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, c->side, true);  // requester: gradients -> owners' areas
+  PB_CUDA(cudaEventRecord(c->ev_join, c->side));
+  PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+  launch_signal(x->d, XC_FLAG_GRAD, nullptr, st);
+  for (uint32_t src = 0; src < x->d.R; ++src) {  // owner: the R requests, one after another in rank order
+    launch_wait(x->d, XC_FLAG_GRAD, (int)src, st);
+    launch_owner_update(t->d, t->op, t->hy, x->d, src, st);
+  }
+  drop_pending(c);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
 // ---- raw slots ------------------------------------------------------------------------------------
 static int ensure_raw(pb_ctx* c) {
   if (c->raw_ready) return PB_OK;

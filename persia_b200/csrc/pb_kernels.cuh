@@ -54,6 +54,27 @@ struct BatchDev {
   uint32_t n;           // id occurrences of the batch
 };
 
+// ---- the shard exchange (pb_shard.cu): one endpoint per rank, buffers in peer-mapped memory -----------------------
+// Every rank is an embedding worker for its own batches (requester) and parameter server `rank` (owner).  Rank r owns
+// one receive area, written by its peers over NVLink with plain stores; `base[q]` is rank q's area as mapped here.
+//   ctrl   [XC_WORDS][16] u32   flags (one word per phase and source, written by that source) and sign counts
+//   sign   [R][cap] u64         signs requested of this rank, by source
+//   row    [R][cap][dim]        rows returned to this rank, by owner (f16, or f32 for ragged layouts)
+//   grad   [R][cap][dim] f32    reduced gradients sent to this rank, by source
+//   gok    [R][cap] u32         1 = apply the gradient, 0 = the slot was skipped / held a NaN
+enum { XC_FLAG_SIGN = 0, XC_FLAG_ROW, XC_FLAG_GRAD, XC_COUNT, XC_WORDS };
+constexpr uint32_t PB_MAX_RANKS = 16;
+struct XchgDev {
+  uint64_t base[PB_MAX_RANKS];
+  uint64_t off_sign, off_row, off_grad, off_gok;  // byte offsets inside an area (ctrl at 0)
+  uint32_t R, rank, cap, row_f32;
+  uint32_t* epoch;     // [XC_WORDS] phases signalled so far (device side: CUDA-graph safe)
+  uint32_t* waited;    // [XC_WORDS][PB_MAX_RANKS] phases waited for so far, per source
+  uint32_t* own_row;   // [R][cap] row of every received sign (forward -> backward)
+  uint32_t* own_cnt;   // [R] signs received per source (copied out of ctrl: the next request may overwrite it early)
+  uint32_t* err;       // [0] a pair needed more than cap slots, [1] a wait gave up
+};
+
 // arguments of the backward kernels (pb_reduce.cu)
 struct ReduceArgs {
   BatchDev b;
@@ -64,6 +85,7 @@ struct ReduceArgs {
   float* vw_stage;             // Adagrad vectorwise: one reduced gradient per item
   uint32_t batch, round, quiet_miss;
   uint32_t round_mask[PB_MAX_SLOTS / 32];  // slots stepped by this launch (slots of one feature group take turns)
+  XchgDev x;                   // sharded: the reduced gradient is stored into the owner's receive area instead
 };
 
 // raw slots (pb_raw.cu): per-batch scratch set of distinct signs and its workspace
@@ -102,8 +124,21 @@ void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell
 void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,
                      uint32_t* nan_tick, int32_t* status, cudaStream_t st);
 // pb_reduce.cu: cold + warm items on `st`, hot items on `st_hot` (may equal st)
+// send: sharded requester — a.x names the owners' receive areas, no row is touched here
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot);
+                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot,
+                         bool send = false);
+// pb_shard.cu
+void launch_route_items(bool training, const SlotsDev& sl, const BatchDev& b, const XchgDev& x, cudaStream_t st);
+void launch_signal(const XchgDev& x, int phase, const uint32_t* counts, cudaStream_t st);
+void launch_wait(const XchgDev& x, int phase, int src /* -1: every source */, cudaStream_t st);
+void launch_owner_lookup(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const XchgDev& x,
+                         cudaStream_t st);
+void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& b, const XchgDev& x,
+                         const uint32_t* row_off, uint32_t n_out, uint32_t batch, bool training, void* out_f16,
+                         cudaStream_t st);
+void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,
+                         cudaStream_t st);
 // n_ptr (optional): the live count on the device (<= n); tick/nan_tick (optional): skip everything when equal
 void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev& hy, const uint32_t* occ_cell,
                           const float* grads, uint32_t n, const float* adam_pair, cudaStream_t st,

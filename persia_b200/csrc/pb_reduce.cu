@@ -147,6 +147,17 @@ __device__ __forceinline__ void reduce_sorted(float (&acc)[N], const ItemSrc& s,
   }
 }
 
+// sharded requester: where the reduced gradient of the item with target = owner * cap + k goes (the owner's receive
+// area, slot [this rank][k]) and its apply / skip word
+__device__ __forceinline__ float* send_grad_ptr(const XchgDev& x, uint32_t target, uint32_t dim) {
+  const uint32_t q = target / x.cap, k = target % x.cap;
+  return reinterpret_cast<float*>(x.base[q] + x.off_grad) + ((size_t)x.rank * x.cap + k) * dim;
+}
+__device__ __forceinline__ uint32_t* send_gok_ptr(const XchgDev& x, uint32_t target) {
+  const uint32_t q = target / x.cap, k = target % x.cap;
+  return reinterpret_cast<uint32_t*>(x.base[q] + x.off_gok) + ((size_t)x.rank * x.cap + k);
+}
+
 // slots whose gradient is skipped or holds a NaN (mod.rs:731-746), or that this launch does not step, as a bit mask
 __device__ __forceinline__ void build_dead_mask(uint32_t* dead, const GradsDev& gr, const ReduceArgs& a, uint32_t n_slots) {
   if (threadIdx.x < PB_MAX_SLOTS / 32) dead[threadIdx.x] = 0u;
@@ -164,11 +175,28 @@ __device__ __forceinline__ bool slot_dead(const uint32_t* dead, uint32_t slot) {
 // cold + warm items
 // ------------------------------------------------------------------------------------------------
 #ifndef PB_REDUCE_BLOCKS
-#define PB_REDUCE_BLOCKS 2  // resident blocks per SM k_reduce_items is compiled for (128 registers: four items per lane group in flight)
-#endif
-constexpr int COLD_ITEMS = 4;
+#define PB_REDUCE_BLOCKS 3  // blocks per SM k_reduce_items is launched with (compiled for 4): the rest of the register
+#endif                      // file is left to the hot kernel, which runs beside it
+constexpr int ITEMS_THREADS = 128;
+constexpr int COLD_ITEMS = 3;
 
 // one item through the generic path: sorted occurrence list pos(0..cnt-1)
+// sharded requester: the reduced gradient of one item goes to its owner (update_all_batched_gradients ends with one
+// (signs, gradients) request per parameter server, mod.rs:813-857)
+template <int VEC, bool F16, typename POS>
+__device__ __forceinline__ void send_item(const TableDev& t, const SlotsDev& sl, const GradsDev& gr, const ReduceArgs& a,
+                                          uint32_t target, uint32_t slot, uint32_t cnt, uint32_t lane, uint32_t G, POS pos) {
+  float* dst = send_grad_ptr(a.x, target, t.dim);
+  const uint32_t nvec = t.dim / VEC;
+  const ItemSrc src = item_src(sl, gr, a, slot);
+  for (uint32_t c = lane; c < nvec; c += G) {
+    float acc[VEC];
+    reduce_sorted<VEC, F16>(acc, src, a, t, cnt, c * VEC, pos);
+    store_vec<VEC>(dst + c * VEC, acc);
+  }
+  if (lane == 0) *send_gok_ptr(a.x, target) = 1u;
+}
+
 template <int VEC, bool F16, int KIND, typename POS>
 __device__ __forceinline__ void step_item(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
                                           const GradsDev& gr, const ReduceArgs& a, uint32_t row, uint32_t slot,
@@ -196,11 +224,11 @@ __device__ __forceinline__ void step_item(const TableDev& t, const OptimDev& op,
   }
 }
 
-template <int VEC, bool F16, int KIND>
-__global__ void __launch_bounds__(256, PB_REDUCE_BLOCKS) k_reduce_items(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl,
+template <int VEC, bool F16, int KIND, bool SEND>
+__global__ void __launch_bounds__(ITEMS_THREADS, 4) k_reduce_items(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl,
                                                                        GradsDev gr, ReduceArgs a, uint32_t G) {
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
-  __shared__ uint32_t sortbuf[64][2 * PB_WARM_MAX];  // per lane group (G >= 4): unsorted | sorted occurrences
+  __shared__ uint32_t sortbuf[ITEMS_THREADS / 4][2 * PB_WARM_MAX];  // per lane group (G >= 4): unsorted | sorted occurrences
   build_dead_mask(dead, gr, a, sl.n_slots);
   const uint32_t lane = threadIdx.x % G;
   const uint32_t grp = threadIdx.x / G;
@@ -233,7 +261,15 @@ __global__ void __launch_bounds__(256, PB_REDUCE_BLOCKS) k_reduce_items(TableDev
       }
       __syncwarp(gmask);
       const uint32_t slot = slot_of_occ(sl, srt[0]);
-      if (!slot_dead(dead, slot)) {
+      if (SEND) {
+        if (row != ROW_NONE) {  // ROW_NONE: the item found no room in its owner's segment (flagged in k_route_items)
+          if (slot_dead(dead, slot)) {
+            if (lane == 0) *send_gok_ptr(a.x, row) = 0u;
+          } else {
+            send_item<VEC, F16>(t, sl, gr, a, row, slot, cnt, lane, G, [&](uint32_t k) { return srt[k]; });
+          }
+        }
+      } else if (!slot_dead(dead, slot)) {
         if (row >= t.capacity) {
           if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
         } else {
@@ -248,6 +284,51 @@ __global__ void __launch_bounds__(256, PB_REDUCE_BLOCKS) k_reduce_items(TableDev
 
   // ---- cold items: COLD_ITEMS per group and iteration, every load issued before the first use
   for (uint32_t w0 = g_global * COLD_ITEMS; w0 < n_cold; w0 += n_groups * COLD_ITEMS) {
+    if (SEND) {
+      float* dst[COLD_ITEMS];
+      ItemSrc src[COLD_ITEMS];
+      GradPrep prep[COLD_ITEMS];
+      size_t gelem[COLD_ITEMS];
+      bool act[COLD_ITEMS];
+#pragma unroll
+      for (int k = 0; k < COLD_ITEMS; ++k) {
+        act[k] = w0 + k < n_cold;
+        uint2 d = make_uint2(ROW_NONE, 0u);
+        if (act[k]) d = a.b.cold[w0 + k];
+        act[k] = act[k] && d.x != ROW_NONE;
+        uint32_t slot = 0;
+        if (act[k]) {
+          slot = slot_of_occ(sl, d.y);
+          if (slot_dead(dead, slot)) {
+            if (lane == 0) *send_gok_ptr(a.x, d.x) = 0u;
+            act[k] = false;
+          } else if (lane == 0) {
+            *send_gok_ptr(a.x, d.x) = 1u;
+          }
+        }
+        dst[k] = act[k] ? send_grad_ptr(a.x, d.x, t.dim) : nullptr;
+        src[k] = item_src(sl, gr, a, slot);
+        const uint32_t orow = act[k] ? occ_out_row(a, d.y) : src[k].slot_row0;
+        prep[k] = grad_prep(src[k], a, orow);
+        gelem[k] = (size_t)(orow - src[k].slot_row0) * t.dim;
+      }
+      for (uint32_t c = lane; c < nvec; c += G) {
+        float g[COLD_ITEMS][VEC];
+#pragma unroll
+        for (int k = 0; k < COLD_ITEMS; ++k)
+          if (act[k]) load_grad_elems<VEC, F16>(g[k], src[k].gbase, gelem[k], c * VEC);
+#pragma unroll
+        for (int k = 0; k < COLD_ITEMS; ++k)
+          if (act[k]) {
+            float acc[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;
+            add_prepared<VEC>(acc, g[k], prep[k], src[k].plain);
+            store_vec<VEC>(dst[k] + c * VEC, acc);
+          }
+      }
+      continue;
+    }
     if (KIND == PB_OPT_ADAGRAD_VW) {  // needs the whole reduced gradient staged: one item at a time
       for (uint32_t w = w0; w < min(n_cold, w0 + COLD_ITEMS); ++w) {
         const uint2 d = a.b.cold[w];
@@ -322,6 +403,7 @@ constexpr uint32_t HOT_BITS = 65536;  // samples covered by one bitmap window (a
 constexpr uint32_t HOT_WORDS = HOT_BITS / 32;
 constexpr uint32_t HOT_ROWS = 32;     // gradient rows per ring stage (one bitmap word)
 constexpr uint32_t HOT_THREADS = 64;
+constexpr uint32_t HOT_DENSE = 6;    // a bitmap word with at least this many rows is staged as one window copy
 constexpr uint32_t WAIT_SPINS = 1u << 22;  // bounded waits: a lost completion voids the batch (CTR_ERR) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -355,6 +437,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// +-inf -> +-65504 (persia-common lib.rs:163-180), two halves per instruction; finite halves are inside already
+__device__ __forceinline__ __half2 clamp_h2(__half2 v) {
+  const __half2 lim = __floats2half2_rn(65504.0f, 65504.0f);
+  return __hmin2(__hmax2(v, __hneg2(lim)), lim);
+}
+
 // EPL consecutive gradient elements of a staged (shared memory) or resident (global) row -> f32, clamped
 template <int EPL, bool F16>
 __device__ __forceinline__ void read_elems(float (&g)[EPL], const unsigned char* rowp, uint32_t e0) {
@@ -365,23 +453,23 @@ __device__ __forceinline__ void read_elems(float (&g)[EPL], const unsigned char*
       const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float2 x = __half22float2(h[q]);
-        g[2 * q] = clamp_f16(x.x);
-        g[2 * q + 1] = clamp_f16(x.y);
+        float2 x = __half22float2(clamp_h2(h[q]));
+        g[2 * q] = x.x;
+        g[2 * q + 1] = x.y;
       }
     } else if constexpr (EPL == 4) {
       uint2 raw = *reinterpret_cast<const uint2*>(p);
       const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        float2 x = __half22float2(h[q]);
-        g[2 * q] = clamp_f16(x.x);
-        g[2 * q + 1] = clamp_f16(x.y);
+        float2 x = __half22float2(clamp_h2(h[q]));
+        g[2 * q] = x.x;
+        g[2 * q + 1] = x.y;
       }
     } else if constexpr (EPL == 2) {
-      float2 x = __half22float2(*reinterpret_cast<const __half2*>(p));
-      g[0] = clamp_f16(x.x);
-      g[1] = clamp_f16(x.y);
+      float2 x = __half22float2(clamp_h2(*reinterpret_cast<const __half2*>(p)));
+      g[0] = x.x;
+      g[1] = x.y;
     } else {
       g[0] = clamp_f16(__half2float(p[0]));
     }
@@ -410,8 +498,8 @@ struct HotSmem {  // carved out of dynamic shared memory
   uint64_t* bars;  // [stages] full, [stages] empty
 };
 
-template <int EPL, bool F16>
-__global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+template <int EPL, bool F16, bool SEND>
+__global__ void __launch_bounds__(HOT_THREADS, 6) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
                                                            ReduceArgs a, uint32_t stages, uint32_t bulk, uint32_t ring_bytes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
@@ -442,15 +530,24 @@ __global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev
     const uint4 d = a.b.hot[h];
     const uint32_t row = d.x, base = d.y, cnt = d.z;
     const uint32_t slot = slot_of_occ(sl, a.b.seg_occ[base]);
-    if (slot_dead(dead, slot)) continue;
-    if (row >= t.capacity) {
-      if (tid == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
-      continue;
+    if (SEND) {
+      if (row == ROW_NONE) continue;
+      if (tid == 0) *send_gok_ptr(a.x, row) = slot_dead(dead, slot) ? 0u : 1u;
+      if (slot_dead(dead, slot)) continue;
+    } else {
+      if (slot_dead(dead, slot)) continue;
+      if (row >= t.capacity) {
+        if (tid == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+        continue;
+      }
     }
     const uint32_t lo = sl.occ_off[slot], hi = sl.occ_off[slot + 1];
     const ItemSrc src = item_src(sl, gr, a, slot);
-    float* prow = t.rows + (size_t)row * t.stride;
-    const StepCtx sc = step_ctx(prow, t, op, gr, slot);
+    const bool contiguous = !a.occ_outrow;  // one id per sample: the gradient row of occurrence lo + b is row b
+    float* prow = SEND ? send_grad_ptr(a.x, row, t.dim) : t.rows + (size_t)row * t.stride;
+    StepCtx sc;
+    sc.vw_state = sc.r1 = sc.r2 = 0.0f;
+    if (!SEND) sc = step_ctx(prow, t, op, gr, slot);
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const uint32_t e0 = (pass * 32u + lane) * EPL;
       const bool own = e0 < t.dim;  // lanes past the row's end idle
@@ -468,7 +565,9 @@ __global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev
         }
         __syncthreads();
         if (warp == 0) {
-          // ---- producer: one stage per non-empty word, one bulk copy per set bit
+          // ---- producer: one stage per non-empty word.  A dense word (the rule, for the signs of a tiny slot) is
+          // staged as ONE bulk copy of its whole 32-row window — gradient rows of consecutive samples are adjacent —
+          // a sparse one as one bulk copy per set bit: the copy engine is bound by operations, not bytes, at this size
           if (bulk) {
             for (uint32_t w = 0; w < n_words; ++w) {
               const uint32_t m = sm.bitmap[w];
@@ -476,13 +575,23 @@ __global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev
               const uint32_t p = __popc(m), stage = it % stages, par = (it / stages) & 1u;
               if (!failed && !mbar_wait(smem_u32(sm.bars + stages + stage), par ^ 1u)) failed = true;
               const uint32_t full = smem_u32(sm.bars + stage);
-              if (lane == 0) mbar_expect_tx(full, p * rowbytes);
-              __syncwarp();
-              if (lane < p) {
-                const uint32_t occ = wbase + w * 32u + __fns(m, 0u, (int)lane + 1);
-                const uint32_t orow = occ_out_row(a, occ);
-                const unsigned char* g = reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow - src.slot_row0) * rowbytes;
-                bulk_g2s(smem_u32(sm.ring + ((size_t)stage * HOT_ROWS + lane) * rowbytes), g, rowbytes, full);
+              const bool dense = contiguous && p >= HOT_DENSE;
+              if (dense) {
+                if (lane == 0) {
+                  const uint32_t first = (wbase - lo) + w * 32u, rows_here = min(32u, (wend - wbase) - w * 32u);
+                  mbar_expect_tx(full, rows_here * rowbytes);
+                  bulk_g2s(smem_u32(sm.ring + (size_t)stage * HOT_ROWS * rowbytes),
+                           reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)first * rowbytes, rows_here * rowbytes, full);
+                }
+              } else {
+                if (lane == 0) mbar_expect_tx(full, p * rowbytes);
+                __syncwarp();
+                if (lane < p) {
+                  const uint32_t occ = wbase + w * 32u + __fns(m, 0u, (int)lane + 1);
+                  const uint32_t orow = occ_out_row(a, occ);
+                  const unsigned char* g = reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow - src.slot_row0) * rowbytes;
+                  bulk_g2s(smem_u32(sm.ring + ((size_t)stage * HOT_ROWS + lane) * rowbytes), g, rowbytes, full);
+                }
               }
               ++it;
             }
@@ -493,40 +602,40 @@ __global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev
             const uint32_t m = sm.bitmap[w];
             if (!m) continue;
             const uint32_t p = __popc(m), stage = it % stages, par = (it / stages) & 1u;
-            if (bulk) {
-              if (!failed && !mbar_wait(smem_u32(sm.bars + stage), par)) failed = true;
-              const unsigned char* rows = sm.ring + (size_t)stage * HOT_ROWS * rowbytes;
-              for (uint32_t k = 0; k < p; k += 4) {
-                float g[4][EPL];
+            const bool dense = bulk && contiguous && p >= HOT_DENSE;
+            if (bulk && !failed && !mbar_wait(smem_u32(sm.bars + stage), par)) failed = true;
+            const unsigned char* rows = sm.ring + (size_t)stage * HOT_ROWS * rowbytes;
+            uint32_t mm = m, idx = 0;
+            while (mm) {  // four rows per round: loads first, then the dependent adds
+              uint32_t bit[4];
+              int nb = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (own && k + u < p) read_elems<EPL, F16>(g[u], rows + (size_t)(k + u) * rowbytes, e0);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (own && k + u < p) {
-                    GradPrep gp;
-                    gp.do_scale = gp.do_sqrt = false;
-                    if (!src.plain) gp = grad_prep(src, a, occ_out_row(a, wbase + w * 32u + __fns(m, 0u, (int)(k + u) + 1)));
-                    add_prepared<EPL>(acc, g[u], gp, src.plain);
-                  }
+              for (int u = 0; u < 4; ++u) {
+                bit[u] = 0;
+                if (mm) {
+                  bit[u] = __ffs(mm) - 1;
+                  mm &= mm - 1;
+                  nb = u + 1;
+                }
               }
+              float g[4][EPL];
+              uint32_t orow[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (u < nb) {
+                  orow[u] = occ_out_row(a, wbase + w * 32u + bit[u]);
+                  const unsigned char* rp = bulk ? rows + (size_t)(dense ? bit[u] : idx + u) * rowbytes
+                                                 : reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow[u] - src.slot_row0) * rowbytes;
+                  if (own) read_elems<EPL, F16>(g[u], rp, e0);
+                }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (u < nb && own) add_prepared<EPL>(acc, g[u], grad_prep(src, a, orow[u]), src.plain);
+              idx += nb;
+            }
+            if (bulk) {
               __syncwarp();
               if (lane == 0) mbar_arrive(smem_u32(sm.bars + stages + stage));  // the stage may be refilled
-            } else {
-              for (uint32_t k = 0; k < p; k += 8) {
-                float g[8][EPL];
-                uint32_t orow[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (k + u < p) orow[u] = occ_out_row(a, wbase + w * 32u + __fns(m, 0u, (int)(k + u) + 1));
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (own && k + u < p)
-                    read_elems<EPL, F16>(g[u], reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow[u] - src.slot_row0) * rowbytes, e0);
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (own && k + u < p) add_prepared<EPL>(acc, g[u], grad_prep(src, a, orow[u]), src.plain);
-              }
             }
             ++it;
           }
@@ -534,7 +643,9 @@ __global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev
         __syncthreads();  // the bitmap is rebuilt for the next window / pass / item
       }
       // ---- the optimizer step on this pass's elements (consumer warp)
-      if (warp == 1 && own) {
+      if (SEND) {
+        if (warp == 1 && own) RowElems<-1, EPL>::template st<EPL>(prow + e0, acc);
+      } else if (warp == 1 && own) {
         RowElems<-1, EPL> rc;
         rc.load(prow, e0, t, op);
         if (op.kind == PB_OPT_ADAGRAD_VW) {
@@ -545,7 +656,7 @@ __global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev
         rc.store(prow, e0, t, op);
       }
     }
-    if (op.kind == PB_OPT_ADAGRAD_VW && warp == 1) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
+    if (!SEND && op.kind == PB_OPT_ADAGRAD_VW && warp == 1) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
       __syncwarp();
       if (lane == 0) {
         float gs = __fdiv_rn(vw_dot(sm.vstage, t.dim), (float)t.dim);
@@ -561,19 +672,23 @@ __global__ void __launch_bounds__(HOT_THREADS) k_reduce_hot(TableDev t, OptimDev
 // ------------------------------------------------------------------------------------------------
 template <int VEC, bool F16>
 static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
-                           const ReduceArgs& a, uint32_t G, cudaStream_t st) {
+                           const ReduceArgs& a, uint32_t G, cudaStream_t st, bool send) {
   static const uint32_t tune_grid = getenv("PB_REDUCE_GRID") ? (uint32_t)atoi(getenv("PB_REDUCE_GRID")) : 148u * PB_REDUCE_BLOCKS;
-  const uint32_t full = cdiv((uint64_t)a.b.n * G, 256);
+  const uint32_t full = cdiv((uint64_t)a.b.n * G, ITEMS_THREADS);
   const uint32_t grid = full < tune_grid ? full : tune_grid;
+  if (send) {
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_items<VEC, F16, PB_OPT_SGD, true>), grid, ITEMS_THREADS, 0, st, t, op, hy, sl, gr, a, G);
+    return;
+  }
 #define PB_K(KK)                                                                                                   \
   case KK:                                                                                                         \
-    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_items<VEC, F16, KK>), grid, 256, 0, st, t, op, hy, sl, gr, a, G);          \
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_items<VEC, F16, KK, false>), grid, ITEMS_THREADS, 0, st, t, op, hy, sl, gr, a, G); \
     break;
   switch (op.kind) { PB_K(PB_OPT_SGD) PB_K(PB_OPT_ADAGRAD) PB_K(PB_OPT_ADAGRAD_VW) PB_K(PB_OPT_ADAM) }
 #undef PB_K
 }
 
-template <int EPL, bool F16>
+template <int EPL, bool F16, bool SEND>
 static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
                        const ReduceArgs& a, uint32_t bulk, cudaStream_t st) {
   const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
@@ -583,7 +698,7 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
   if (!bulk) stages = 1;
   const size_t ring = bulk ? (size_t)stages * HOT_ROWS * rowbytes : 0;
   const size_t smem = ring + HOT_WORDS * 4u + (((size_t)t.dim + 1u) & ~(size_t)1u) * 4u + 2u * stages * 8u;
-  auto kern = k_reduce_hot<EPL, F16>;
+  auto kern = k_reduce_hot<EPL, F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -601,7 +716,8 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
 }
 
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot) {
+                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot,
+                         bool send) {
   if (!a.b.n) return;
   int vec, Gi;
   vec_group(t.dim, vec, Gi);
@@ -622,18 +738,23 @@ void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& 
     if (getenv("PB_HOT_NO_BULK")) bulk = 0;
 #define PB_H(E)                                                                         \
   case E:                                                                               \
-    if (f16) hot_launch<E, true>(t, op, hy, sl, gr, a, bulk, st_hot);                   \
-    else hot_launch<E, false>(t, op, hy, sl, gr, a, bulk, st_hot);                      \
+    if (send) {                                                                         \
+      if (f16) hot_launch<E, true, true>(t, op, hy, sl, gr, a, bulk, st_hot);           \
+      else hot_launch<E, false, true>(t, op, hy, sl, gr, a, bulk, st_hot);              \
+    } else {                                                                            \
+      if (f16) hot_launch<E, true, false>(t, op, hy, sl, gr, a, bulk, st_hot);          \
+      else hot_launch<E, false, false>(t, op, hy, sl, gr, a, bulk, st_hot);             \
+    }                                                                                   \
     break;
     switch (epl) { PB_H(1) PB_H(2) PB_H(4) PB_H(8) }
 #undef PB_H
   }
   if (vec == 4) {
-    if (f16) items_dispatch<4, true>(t, op, hy, sl, gr, a, G, st);
-    else items_dispatch<4, false>(t, op, hy, sl, gr, a, G, st);
+    if (f16) items_dispatch<4, true>(t, op, hy, sl, gr, a, G, st, send);
+    else items_dispatch<4, false>(t, op, hy, sl, gr, a, G, st, send);
   } else {
-    if (f16) items_dispatch<1, true>(t, op, hy, sl, gr, a, G, st);
-    else items_dispatch<1, false>(t, op, hy, sl, gr, a, G, st);
+    if (f16) items_dispatch<1, true>(t, op, hy, sl, gr, a, G, st, send);
+    else items_dispatch<1, false>(t, op, hy, sl, gr, a, G, st, send);
   }
 }
 

@@ -1,0 +1,391 @@
+// pb_shard.cu — the embedding worker's fan-out over the R GPUs of one box, fused with the compute
+// on both sides of it.
+//
+// Reference: the EW shards a batch's DISTINCT signs by farmhash64(sign) % R (indices_to_sharded_indices,
+// embedding_worker_service/mod.rs:454-479), issues one lookup_mixed per parameter server (:886-919), puts the rows
+// back in batch order (:486-629); in backward it reduces the gradients per distinct sign and issues one
+// update_gradient_mixed per server (:786-857), which applies them (embedding_parameter_service/mod.rs:359-427).
+// Here every rank is the EW of its own batches and PS `rank`; a "request" is what one rank sends one owner.  The
+// requests of the R data-parallel trainers reach an owner as R separate requests — exactly the reference's picture
+// with R NN workers — and are served in rank order, so a sign looked up by several ranks takes one optimizer step
+// per requesting rank, as it does there (deterministically ordered here).
+//
+// There is no separate exchange step: the kernel that produces data writes it where its consumer lives.
+//   k_route_items    (requester) owner of every distinct sign, sign stored straight into the owner's receive area
+//   k_owner_lookup   (owner) find / admit / initialise, row gathered, converted and stored straight into the
+//                    requester's receive area
+//   k_expand_items   (requester) received rows -> output rows in batch order (+ pooling for ragged layouts)
+//   k_reduce_items / k_reduce_hot <SEND>  (requester, pb_reduce.cu) reduced gradient stored into the owner's area
+//   k_owner_update   (owner) one request at a time, in rank order: optimizer step on the resident rows
+// Ordering between ranks is by flag words in the receiver's area (one per phase and source, written after a
+// system-scope fence); k_wait spins on them in ONE block so that the box — or, in tests, the other virtual ranks
+// sharing a GPU — keeps running.  Phase counters live on the device: a whole step is CUDA-graph capturable.
+#include "pb_optim.cuh"
+#include "pb_probe.cuh"
+
+namespace pb {
+
+__device__ __forceinline__ uint32_t* x_ctrl(const XchgDev& x, uint32_t q) { return reinterpret_cast<uint32_t*>(x.base[q]); }
+__device__ __forceinline__ uint64_t* x_sign(const XchgDev& x, uint32_t q) {
+  return reinterpret_cast<uint64_t*>(x.base[q] + x.off_sign);
+}
+__device__ __forceinline__ unsigned char* x_row(const XchgDev& x, uint32_t q) {
+  return reinterpret_cast<unsigned char*>(x.base[q] + x.off_row);
+}
+
+// ------------------------------------------------------------------------------------------------
+// requester, forward: A3 over the distinct signs.  One thread per item; segment slots are handed out per owner
+// with one atomic per warp and owner (__match_any_sync).  Mirrors k_probe_items' bookkeeping: the item's target
+// (owner * cap + slot) replaces the row, and the backward's work lists are filled by multiplicity.
+// ------------------------------------------------------------------------------------------------
+template <bool TRAIN>
+__global__ void __launch_bounds__(256) k_route_items(SlotsDev sl, BatchDev b, XchgDev x) {
+  const uint32_t n_items = b.cnt[BC_ITEMS];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t first_u = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
+  for (uint32_t u0 = first_u; u0 < n_items; u0 += gridDim.x * blockDim.x) {  // uniform per warp
+    const uint32_t u = u0 + lane;
+    const bool valid = u < n_items;
+    uint32_t cell = 0, cnt = 0, first = 0, owner = 0xFFFFFFFFu;
+    uint64_t sign = 0;
+    if (valid) {
+      cell = b.item_cell[u];
+      const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);
+      const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);
+      sign = (hi.w >> 31) ? KEY_EMPTY : ((uint64_t)lo.x | ((uint64_t)lo.y << 32));
+      cnt = TRAIN ? lo.z : 0u;
+      first = hi.z;
+      owner = (uint32_t)(farmhash64_u64(sign) % x.R);  // sign_to_shard_modulo, mod.rs:341-345
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, owner);
+    uint32_t k = 0;
+    const uint32_t leader = __ffs(peers) - 1;
+    if (valid && lane == leader) k = atomicAdd(&b.cnt[BC_PEER + owner], (uint32_t)__popc(peers));
+    k = __shfl_sync(0xffffffffu, k, leader) + __popc(peers & ((1u << lane) - 1u));
+    uint32_t target = ROW_NONE, base = 0;
+    if (valid) {
+      if (k < x.cap) {
+        target = owner * x.cap + k;
+        x_sign(x, owner)[(size_t)x.rank * x.cap + k] = sign;  // over NVLink when owner != rank
+      } else {
+        x.err[0] = 1u;  // the pair needs more than cap slots: the caller re-runs the batch with a larger cap
+      }
+      if (cnt > 1) base = atomicAdd(&b.cnt[BC_SEG], cnt);
+      b.set[cell].target = target;
+      b.set[cell].base = base;
+    }
+    const uint32_t cm = __ballot_sync(0xffffffffu, valid && cnt == 1);
+    const uint32_t wm = __ballot_sync(0xffffffffu, valid && cnt > 1 && cnt <= PB_WARM_MAX);
+    const uint32_t hm = __ballot_sync(0xffffffffu, valid && cnt > PB_WARM_MAX);
+    uint32_t cb = 0, wb = 0, hb = 0;
+    if (lane == 0) {
+      if (cm) cb = atomicAdd(&b.cnt[BC_COLD], (uint32_t)__popc(cm));
+      if (wm) wb = atomicAdd(&b.cnt[BC_WARM], (uint32_t)__popc(wm));
+      if (hm) hb = atomicAdd(&b.cnt[BC_HOT], (uint32_t)__popc(hm));
+    }
+    cb = __shfl_sync(0xffffffffu, cb, 0);
+    wb = __shfl_sync(0xffffffffu, wb, 0);
+    hb = __shfl_sync(0xffffffffu, hb, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (valid && cnt == 1) b.cold[cb + __popc(cm & below)] = make_uint2(target, first);
+    else if (valid && cnt > 1 && cnt <= PB_WARM_MAX) b.warm[wb + __popc(wm & below)] = make_uint4(target, base, cnt, 0u);
+    else if (valid && cnt > PB_WARM_MAX) b.hot[hb + __popc(hm & below)] = make_uint4(target, base, cnt, 0u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flags.  signal: this rank finished writing phase `phase` into every peer's area -> bump the device-side phase
+// counter, publish (optionally) the per-owner counts, fence, write the flag word [phase][rank] of every peer.
+// wait: spin (bounded) until source `src` (or every source) has signalled the phase this rank is about to consume.
+// ------------------------------------------------------------------------------------------------
+#ifndef PB_WAIT_SPINS
+#define PB_WAIT_SPINS (1u << 25)
+#endif
+__global__ void k_signal(XchgDev x, int phase, const uint32_t* __restrict__ counts) {
+  __shared__ uint32_t e_s;
+  if (threadIdx.x == 0) {
+    e_s = x.epoch[phase] + 1;
+    x.epoch[phase] = e_s;
+  }
+  __syncthreads();
+  const uint32_t q = threadIdx.x;
+  if (q < x.R) {
+    uint32_t* ctrl = x_ctrl(x, q);
+    if (counts) ctrl[XC_COUNT * PB_MAX_RANKS + x.rank] = counts[q] < x.cap ? counts[q] : x.cap;
+    __threadfence_system();  // everything this GPU stored into the peer's area before is visible before the flag
+    *reinterpret_cast<volatile uint32_t*>(&ctrl[phase * PB_MAX_RANKS + x.rank]) = e_s;
+  }
+}
+
+__global__ void k_wait(XchgDev x, int phase, int src) {
+  const uint32_t q = threadIdx.x;
+  if (q >= x.R || (src >= 0 && q != (uint32_t)src)) return;
+  uint32_t* w = &x.waited[phase * PB_MAX_RANKS + q];
+  const uint32_t e = *w + 1;
+  *w = e;
+  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(&x_ctrl(x, x.rank)[phase * PB_MAX_RANKS + q]);
+  uint32_t spins = 0;
+  while ((int32_t)(*flag - e) < 0) {
+    if (++spins > PB_WAIT_SPINS) {  // a peer is not coming: give up instead of hanging the GPU, and say so
+      x.err[1] = 1u;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------
+// owner, forward: lookup_mixed of R requests at once (PS mod.rs:162-262, 344-357).  Eight lanes per received sign
+// probe the index (pb_probe.cuh: find / refresh / admit + initialise), then the same eight lanes read the row and
+// store it, converted, into the requester's area.  f16 rows serve one-id-per-sample layouts (the EW's result is
+// f16(0 + row) there, bit for bit); f32 rows serve ragged layouts, which pool on the requester.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool ROW_F32>
+__global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev t, HyperDev hy, OptimDev op, XchgDev x) {
+  const uint32_t tick = t.counters[CTR_TICK];
+  const uint32_t sub = threadIdx.x % BUCKET;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gshift = lane & ~(BUCKET - 1);
+  const uint32_t groups = gridDim.x * (blockDim.x / BUCKET);
+  const uint32_t total = x.R * x.cap;
+  const uint32_t* ctrl = x_ctrl(x, x.rank);
+  const uint32_t warp_first = ((blockIdx.x * blockDim.x + threadIdx.x) / 32) * (32 / BUCKET);
+  if (blockIdx.x == 0 && threadIdx.x < x.R) x.own_cnt[threadIdx.x] = ctrl[XC_COUNT * PB_MAX_RANKS + threadIdx.x];
+  for (uint32_t j0 = warp_first; j0 < total; j0 += groups) {  // uniform per warp
+    const uint32_t j = j0 + lane / BUCKET;
+    const uint32_t src = j / x.cap, k = j % x.cap;
+    const bool valid = j < total && k < ctrl[XC_COUNT * PB_MAX_RANKS + src];
+    if (!__any_sync(0xffffffffu, valid)) continue;
+    uint64_t sign = 0;
+    if (valid && sub == 0) sign = x_sign(x, x.rank)[j];
+    sign = __shfl_sync(0xffffffffu, sign, gshift);
+    const ProbeOut r = probe_group<MODE>(t, hy, op, sign, valid, tick, sub, gshift);
+    if (!valid) continue;
+    if (sub == 0) {
+      x.own_row[j] = r.row;
+      if (r.row == ROW_NONE) atomicAdd(&t.counters[CTR_MISS], 1u);
+    }
+    const float* row = t.rows + (size_t)(r.row < t.capacity ? r.row : 0u) * t.stride;
+    const bool have = r.row < t.capacity;
+    const size_t slot = (size_t)x.rank * x.cap + k;  // this owner's segment in the requester's area
+    if (ROW_F32) {
+      float* dst = reinterpret_cast<float*>(x_row(x, src)) + slot * t.dim;
+      if (t.dim % 4 == 0) {
+        for (uint32_t e = sub * 4; e < t.dim; e += BUCKET * 4) {
+          float4 v = have ? *reinterpret_cast<const float4*>(row + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dst + e) = v;
+        }
+      } else {
+        for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = have ? row[e] : 0.0f;
+      }
+    } else {
+      __half* dst = reinterpret_cast<__half*>(x_row(x, src)) + slot * t.dim;
+      if (t.dim % 4 == 0) {
+        for (uint32_t e = sub * 4; e < t.dim; e += BUCKET * 4) {
+          float4 v = have ? *reinterpret_cast<const float4*>(row + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // the EW adds the row into a zeroed f32 row, then converts (mod.rs:555-561, persia-common lib.rs:157-161)
+          __half2 a = __floats2half2_rn(__fadd_rn(0.0f, v.x), __fadd_rn(0.0f, v.y));
+          __half2 c = __floats2half2_rn(__fadd_rn(0.0f, v.z), __fadd_rn(0.0f, v.w));
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&a);
+          pk.y = *reinterpret_cast<uint32_t*>(&c);
+          *reinterpret_cast<uint2*>(dst + e) = pk;
+        }
+      } else {
+        for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = __float2half_rn(__fadd_rn(0.0f, have ? row[e] : 0.0f));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// requester, forward: received rows -> batch order (lookup_batched_all_slots_postprocess, mod.rs:486-629).
+// One-id layouts: a pure copy of the f16 row.  Ragged layouts: f32 rows summed in sample order, sqrt scaling, RNE.
+// TRAIN: files every occurrence of a repeated sign into the sign's list, like k_gather_items.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void file_occ(const BatchDev& b, uint32_t cell, uint32_t count, uint32_t base, uint32_t occ) {
+  if (count > 1) b.seg_occ[base + atomicAdd(&b.set[cell].cursor, 1u)] = occ;
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256) k_expand_copy(uint32_t dim, BatchDev b, XchgDev x, uint32_t n_out,
+                                                     __half* __restrict__ out, uint32_t lanes) {
+  // `lanes` lanes per output row, 16 bytes per lane and step
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / lanes;
+  const uint32_t l = threadIdx.x % lanes;
+  if (g >= n_out) return;
+  const uint32_t cell = b.occ_set[g];
+  const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);
+  const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);
+  const uint32_t target = hi.x;
+  if (TRAIN && l == 0) file_occ(b, cell, lo.z, hi.y, g);
+  const uint32_t words = dim / 8;  // 16-byte words per f16 row (dim % 8 == 0 on this path)
+  const uint4* src = reinterpret_cast<const uint4*>(x_row(x, x.rank)) + (size_t)(target == ROW_NONE ? 0u : target) * words;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)g * words;
+  for (uint32_t w = l; w < words; w += lanes) dst[w] = target == ROW_NONE ? make_uint4(0u, 0u, 0u, 0u) : src[w];
+}
+
+template <bool TRAIN, bool ROW_F32>
+__global__ void __launch_bounds__(256) k_expand_pool(uint32_t dim, SlotsDev sl, BatchDev b, XchgDev x,
+                                                     const uint32_t* __restrict__ row_off, uint32_t n_out, uint32_t batch,
+                                                     __half* __restrict__ out, uint32_t G) {
+  const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const uint32_t lane = threadIdx.x % G;
+  if (gid >= n_out) return;
+  const uint32_t beg = row_off ? row_off[gid] : gid, end = row_off ? row_off[gid + 1] : gid + 1;
+  float scale = 1.0f;
+  if (row_off && batch && sl.sqrt_scaling[gid / batch]) {
+    uint32_t cnt = end - beg;
+    scale = __fdiv_rn(1.0f, __fsqrt_rn((float)(cnt > 1 ? cnt : 1)));
+  }
+  if (TRAIN && lane == 0) {
+    for (uint32_t j = beg; j < end; ++j) {
+      const uint32_t cell = b.occ_set[j];
+      file_occ(b, cell, b.set[cell].count, b.set[cell].base, j);
+    }
+  }
+  for (uint32_t e = lane; e < dim; e += G) {
+    float acc = 0.0f;
+    for (uint32_t j = beg; j < end; ++j) {
+      const uint32_t target = b.set[b.occ_set[j]].target;
+      if (target == ROW_NONE) continue;
+      float v;
+      if (ROW_F32) v = reinterpret_cast<const float*>(x_row(x, x.rank))[(size_t)target * dim + e];
+      else v = __half2float(reinterpret_cast<const __half*>(x_row(x, x.rank))[(size_t)target * dim + e]);
+      acc = __fadd_rn(acc, v);
+    }
+    out[(size_t)gid * dim + e] = __float2half_rn(__fmul_rn(acc, scale));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// owner, backward: update_gradient_mixed of ONE request (PS mod.rs:359-427): one optimizer step per received
+// (sign, gradient) whose apply word is set; signs without storage are counted (gradient_id_miss_count).  The
+// requests of a step are served one launch after another, in rank order.
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_owner_update(TableDev t, OptimDev op, HyperDev hy, XchgDev x, uint32_t src,
+                                                      uint32_t G) {
+  const uint32_t lane = threadIdx.x % G;
+  const uint32_t n = x.own_cnt[src];
+  const uint32_t nvec = t.dim / VEC;
+  const uint32_t n_groups = gridDim.x * (blockDim.x / G);
+  const float* grads = reinterpret_cast<const float*>(x.base[x.rank] + x.off_grad) + (size_t)src * x.cap * t.dim;
+  const uint32_t* gok = reinterpret_cast<const uint32_t*>(x.base[x.rank] + x.off_gok) + (size_t)src * x.cap;
+  const uint32_t* own_row = x.own_row + (size_t)src * x.cap;
+  for (uint32_t k0 = (blockIdx.x * (blockDim.x / G) + threadIdx.x / G) * 2; k0 < n; k0 += n_groups * 2) {
+    // two requests' worth of loads in flight per lane group
+    float* prow[2];
+    const float* g0[2];
+    bool act[2];
+    StepCtx sc[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t k = k0 + u;
+      act[u] = k < n && gok[k < n ? k : 0] != 0u;
+      uint32_t row = act[u] ? own_row[k] : ROW_NONE;
+      if (act[u] && row >= t.capacity) {
+        if (lane == 0) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+        act[u] = false;
+      }
+      prow[u] = t.rows + (size_t)(act[u] ? row : 0u) * t.stride;
+      g0[u] = grads + (size_t)(act[u] ? k : 0u) * t.dim;
+      sc[u].vw_state = (act[u] && op.kind == PB_OPT_ADAGRAD_VW) ? prow[u][t.dim] : 0.0f;
+      sc[u].r1 = sc[u].r2 = 0.0f;
+    }
+    for (uint32_t c = lane; c < nvec; c += G) {
+      RowElems<-1, VEC> rc[2];
+      float g[2][VEC];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (act[u]) {
+          rc[u].load(prow[u], c * VEC, t, op);
+          load_vec<VEC>(g0[u] + c * VEC, g[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (act[u]) {
+          rc[u].step(c * VEC, g[u], t, op, hy, sc[u]);
+          rc[u].store(prow[u], c * VEC, t, op);
+        }
+    }
+    if (op.kind == PB_OPT_ADAGRAD_VW && lane == 0) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (act[u]) {
+          float gs = __fdiv_rn(vw_dot(g0[u], t.dim), (float)t.dim);
+          prow[u][t.dim] = __fadd_rn(__fmul_rn(sc[u].vw_state, op.mom), gs);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers (host)
+// ------------------------------------------------------------------------------------------------
+void launch_route_items(bool training, const SlotsDev& sl, const BatchDev& b, const XchgDev& x, cudaStream_t st) {
+  if (!b.n) return;
+  const uint32_t full = cdiv(b.n, 256);
+  const uint32_t grid = full < 148u * 4u ? full : 148u * 4u;
+  if (training) PB_LAUNCH_F(FAM_PROBE, (k_route_items<true>), grid, 256, 0, st, sl, b, x);
+  else PB_LAUNCH_F(FAM_PROBE, (k_route_items<false>), grid, 256, 0, st, sl, b, x);
+}
+
+void launch_signal(const XchgDev& x, int phase, const uint32_t* counts, cudaStream_t st) {
+  PB_LAUNCH(k_signal, 1, 32, 0, st, x, phase, counts);
+}
+
+void launch_wait(const XchgDev& x, int phase, int src, cudaStream_t st) { PB_LAUNCH(k_wait, 1, 32, 0, st, x, phase, src); }
+
+void launch_owner_lookup(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const XchgDev& x,
+                         cudaStream_t st) {
+  const uint32_t full = cdiv((uint64_t)x.R * x.cap * BUCKET, 256);
+  const uint32_t grid = full < 148u * PB_PROBE_BLOCKS ? full : 148u * PB_PROBE_BLOCKS;
+  if (training) {
+    if (x.row_f32) PB_LAUNCH_F(FAM_PROBE, (k_owner_lookup<MODE_TRAIN, true>), grid, 256, 0, st, t, hy, op, x);
+    else PB_LAUNCH_F(FAM_PROBE, (k_owner_lookup<MODE_TRAIN, false>), grid, 256, 0, st, t, hy, op, x);
+  } else {
+    if (x.row_f32) PB_LAUNCH_F(FAM_PROBE, (k_owner_lookup<MODE_FIND, true>), grid, 256, 0, st, t, hy, op, x);
+    else PB_LAUNCH_F(FAM_PROBE, (k_owner_lookup<MODE_FIND, false>), grid, 256, 0, st, t, hy, op, x);
+  }
+}
+
+void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& b, const XchgDev& x,
+                         const uint32_t* row_off, uint32_t n_out, uint32_t batch, bool training, void* out_f16,
+                         cudaStream_t st) {
+  if (!n_out) return;
+  __half* out = reinterpret_cast<__half*>(out_f16);
+  if (!row_off && !x.row_f32 && t.dim % 8 == 0) {
+    uint32_t words = t.dim / 8, lanes = 1;
+    while (lanes < words && lanes < 32) lanes <<= 1;
+    const uint32_t grid = cdiv((uint64_t)n_out * lanes, 256);
+    if (training) PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<true>), grid, 256, 0, st, t.dim, b, x, n_out, out, lanes);
+    else PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<false>), grid, 256, 0, st, t.dim, b, x, n_out, out, lanes);
+    return;
+  }
+  uint32_t G = 1;
+  while (G < t.dim && G < 32) G <<= 1;
+  const uint32_t grid = cdiv((uint64_t)n_out * G, 256);
+#define PB_E(TR, F32) PB_LAUNCH_F(FAM_GATHER, (k_expand_pool<TR, F32>), grid, 256, 0, st, t.dim, sl, b, x, row_off, n_out, batch, out, G)
+  if (training) {
+    if (x.row_f32) PB_E(true, true);
+    else PB_E(true, false);
+  } else {
+    if (x.row_f32) PB_E(false, true);
+    else PB_E(false, false);
+  }
+#undef PB_E
+}
+
+void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,
+                         cudaStream_t st) {
+  int vec, Gi;
+  vec_group(t.dim, vec, Gi);
+  const uint32_t G = (uint32_t)Gi;
+  const uint32_t full = cdiv((uint64_t)cdiv(x.cap, 2) * G, 256);
+  const uint32_t grid = full < 148u * 6u ? full : 148u * 6u;
+  if (vec == 4) PB_LAUNCH_F(FAM_UPDATE, (k_owner_update<4>), grid, 256, 0, st, t, op, hy, x, src, G);
+  else PB_LAUNCH_F(FAM_UPDATE, (k_owner_update<1>), grid, 256, 0, st, t, op, hy, x, src, G);
+}
+
+}  // namespace pb

@@ -73,6 +73,12 @@ SYMBOLS = {
     "pb_backward": (_i32, [_vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp]),
     "pb_forward_raw": (_i32, [_vp, _vp, _vp, _u32, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pb_backward_raw": (_i32, [_vp, _vp, _vp, _i32, C.c_float, _vp, _vp]),
+    "pb_xchg_bytes": (_u64, [_u32, _u32, _u32, _i32]),
+    "pb_xchg_create": (_i32, [_i32, _u32, _u32, _u32, _u32, _i32, C.POINTER(_u64), C.POINTER(_vp)]),
+    "pb_xchg_destroy": (_i32, [_vp]),
+    "pb_xchg_status": (_i32, [_vp, C.POINTER(_u32 * 2), _vp]),
+    "pb_forward_sharded": (_i32, [_vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp]),
+    "pb_backward_sharded": (_i32, [_vp, _vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp]),
     "pb_launch_count": (_u64, []),
     "pb_profile_enable": (_i32, [_i32]),
     "pb_profile_read": (_i32, [C.POINTER(C.c_double), C.POINTER(_u64), _i32]),

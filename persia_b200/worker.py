@@ -1,336 +1,188 @@
-"""ShardedEmbeddingWorker — the embedding worker's fan-out over R GPUs of one box.
+"""ShardedEmbeddingWorker — the embedding worker's fan-out over the R GPUs of one box.
 
-Reference: rust/persia-embedding-server/src/embedding_worker_service/mod.rs.  There the EW shards a batch's
-signs by farmhash64(sign) % R and issues one HTTP `lookup_mixed` / `update_gradient_mixed` per parameter
-server (:886-919, :835-859).  Here every rank is at once a data-parallel trainer (its own slice of the batch),
-an embedding worker (prefix, partition, exchange) and parameter server r (its pb_table); the R requests become
-one all-to-all of signs, one of rows back, and in backward one of gradients — torch.distributed (NCCL over
-NVLink) carries them, the CUDA library does everything else.
+Reference: rust/persia-embedding-server/src/embedding_worker_service/mod.rs.  There the EW shards a batch's distinct
+signs by farmhash64(sign) % R and issues one HTTP `lookup_mixed` / `update_gradient_mixed` per parameter server
+(:886-919, :835-859).  Here every rank is at once a data-parallel trainer (its own batches), the embedding worker of
+those batches and parameter server `rank` (its pb_table).  The fan-out is inside libpersia_b200's kernels
+(pb_forward_sharded / pb_backward_sharded, csrc/pb_shard.cu): signs, rows and reduced gradients are stored straight
+into the receiver's area over NVLink peer mappings.  What is left on the host is set-up: sizing the areas, mapping
+them (torch symmetric memory) and choosing `cap`, the slots per (source, owner) pair.
 
-Semantics (documented in DESIGN.md §Multi-GPU): a step is synchronous over the GLOBAL batch — every shard
-sees all ranks' occurrences of its signs at once, exactly what the reference computes when one embedding
-worker is handed the concatenated batch; duplicates across ranks are reduced in (rank, sample) order.
+Semantics: a rank's batch is one request per owner — the reference's picture with R NN
+workers.  An owner serves a step's R lookup requests together and applies its R gradient requests one after another
+in rank order.  Both calls are collective.
 
-`backend` isolates what touches a device so that the exchange bookkeeping (partition order, split sizes,
-permutations) can be exercised on CPU with gloo (tests/test_worker_gloo.py supplies an oracle-backed one).
+Two ways to build the ranks of a box:
+  * `ShardedEmbeddingWorker.distributed(...)`: one process per GPU (torchrun), areas in symmetric memory.
+  * `ShardedEmbeddingWorker.local_group(R, ...)`: R virtual ranks on ONE GPU in one process, each with its own table,
+    context and stream, areas in plain device memory.  Same kernels, same protocol; lets a single-GPU box run the
+    R > 1 parity tests.  Needs CUDA_DEVICE_MAX_CONNECTIONS >= 2R so that no two ranks' streams share a hardware queue
+    (a rank spinning on a flag must not sit in front of the kernel that will raise it).
 """
+import ctypes as C
+import os
+
+import numpy as np
 import torch
-import torch.distributed as dist
+
+from . import native as N
+from . import shard as SH
 
 
-class CudaBackend:
-    """The product backend: libpersia_b200.so on the current CUDA device."""
+def distinct_per_owner(ids, batch, prefixes, R, prefix_bit=8):
+    """Host-side (numpy) count of the distinct signs one batch requests of every owner: what `cap` must cover.
+    ids: uint64 [n_slots * batch] slot-major.  Mirrors indices_add_prefix + FeatureBatch::new + sign_to_shard_modulo."""
+    from .persia_core import farmhash64_np
 
-    def __init__(self, dim, capacity, device, optimizer, hyper, max_occurrences):
-        from . import native as N
-        from . import shard as SH
-
-        self.SH, self.N = SH, N
-        self.device = device
-        self.dim = dim
-        self.shard = SH.EmbeddingShard(dim, capacity, device)
-        self.shard.set_optimizer(**optimizer)
-        self.shard.configure(**hyper)
-        # owner-side context: one logical slot of already prefixed signs
-        self.ctx = SH.BatchContext(max_occurrences, max_occurrences, [0], device=device)
-        self.ctx.set_owner_mode(True)
-
-    def add_prefix(self, ids, slot_occ_off, prefixes, prefix_bit):
-        return self.SH.add_prefix(ids, slot_occ_off, prefixes, prefix_bit)
-
-    def partition(self, signs, R):
-        return self.SH.partition_by_shard(signs, R)
-
-    def take(self, src, perm):
-        return self.SH.permute_u64(src, perm)
-
-    def take_rows(self, src, perm):
-        return self.SH.permute_rows(src, perm, scatter=False)
-
-    def put_rows(self, src, perm):
-        return self.SH.permute_rows(src, perm, scatter=True)
-
-    def serve_lookup(self, signs, training):
-        m = signs.numel()
-        if m == 0:
-            return torch.empty((0, self.dim), dtype=torch.float16, device=self.device)
-        return self.ctx.forward(self.shard, signs, [0, m], m, training=training).view(m, self.dim)
-
-    def serve_update(self, grads, scale):
-        if grads.shape[0]:
-            self.ctx.backward(self.shard, [grads], scales=[scale])
-
-    def empty_rows(self, n, dtype=torch.float16):
-        return torch.empty((n, self.dim), dtype=dtype, device=self.device)
-
-    # framed (fixed-capacity) exchange helpers
-    def frame_signs(self, signs, perm, counts, R, cap, overflow):
-        return self.SH.frame_signs(signs, perm, counts, R, cap, overflow)
-
-    def frame_rows(self, src, perm, counts, R, cap, pack, out):
-        return self.SH.frame_rows(src, perm, counts, R, cap, pack, out)
+    S = len(prefixes)
+    ids = np.ascontiguousarray(ids, dtype=np.uint64).reshape(S, batch)
+    spacing = np.uint64((1 << (64 - prefix_bit)) - 1)
+    counts = np.zeros(R, np.int64)
+    for s in range(S):
+        signs = ids[s] % spacing + np.uint64(prefixes[s]) if prefixes[s] else ids[s]
+        u = np.unique(signs)
+        counts += np.bincount((farmhash64_np(u) % np.uint64(R)).astype(np.int64), minlength=R)
+    return counts
 
 
 class ShardedEmbeddingWorker:
-    def __init__(self, n_slots, dim, prefixes, backend, group=None, prefix_bit=8):
-        self.S, self.dim, self.prefixes, self.prefix_bit = n_slots, dim, list(prefixes), prefix_bit
-        self.be = backend
-        self.group = group
-        self.R = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self._pending = None
+    def __init__(self, n_slots, dim, prefixes, capacity, device, rank, world, cap, area, peer_bases, optimizer,
+                 hyper=None, max_batch=4096, sqrt_scaling=None, rows_f32=False, prefix_bit=8, stream=None,
+                 max_ids_per_sample=1):
+        self.S, self.dim, self.rank, self.R, self.cap = n_slots, dim, rank, world, int(cap)
+        self.device = device if isinstance(device, torch.device) else torch.device("cuda", device)
+        self.lib = N.load()
+        self.stream = stream
+        self.area = area  # keeps the receive area alive
+        self.shard = SH.EmbeddingShard(dim, capacity, self.device)
+        self.shard.set_optimizer(**optimizer)
+        self.shard.configure(**(hyper or {}))
+        n = n_slots * max_batch * max_ids_per_sample
+        self.ctx = SH.BatchContext(n, n_slots * max_batch, prefixes, sqrt_scaling, prefix_bit, self.device)
+        bases = (C.c_uint64 * world)(*[int(p) for p in peer_bases])
+        h = C.c_void_p()
+        N.check(self.lib.pb_xchg_create(self.device.index or 0, world, rank, self.cap, dim, int(rows_f32), bases, C.byref(h)))
+        self.h = h
 
-    # ---- exchange primitives -------------------------------------------------------------------------
-    def _exchange_counts(self, counts):
-        """counts: int32[R] on device -> (send list, recv list).  One host sync: torch's all_to_all_single needs
-        the split sizes on the host (NCCL's API does)."""
-        if self.R == 1:
-            c = int(counts[0])
-            return [c], [c]
-        recv = torch.empty_like(counts)
-        dist.all_to_all_single(recv, counts, group=self.group)
-        both = torch.stack([counts, recv]).tolist()
-        return both[0], both[1]
+    # ---- set-up helpers --------------------------------------------------------------------------------------------
+    @staticmethod
+    def area_bytes(world, cap, dim, rows_f32=False):
+        b = int(N.load().pb_xchg_bytes(world, int(cap), dim, int(rows_f32)))
+        assert b > 0, "bad exchange geometry"
+        return b
 
-    def _a2a(self, send, send_splits, recv_splits, out=None):
-        if self.R == 1:
-            return send
-        shape = (sum(recv_splits),) + tuple(send.shape[1:])
-        if out is None:
-            out = torch.empty(shape, dtype=send.dtype, device=send.device)
-        dist.all_to_all_single(out, send, output_split_sizes=recv_splits, input_split_sizes=send_splits, group=self.group)
-        return out
+    @classmethod
+    def local_group(cls, world, n_slots, dim, prefixes, capacity, cap, optimizer, device=0, **kw):
+        """R virtual ranks on one GPU (tests; also a way to exercise the protocol without a multi-GPU box)."""
+        dev = torch.device("cuda", device)
+        need = 2 * world
+        have = int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8"))
+        assert have >= min(need, 32), f"set CUDA_DEVICE_MAX_CONNECTIONS >= {min(need, 32)} before CUDA starts (is {have})"
+        nbytes = cls.area_bytes(world, cap, dim, kw.get("rows_f32", False))
+        areas = [torch.zeros(nbytes + 256, dtype=torch.uint8, device=dev) for _ in range(world)]
+        bases = [(a.data_ptr() + 255) // 256 * 256 for a in areas]
+        torch.cuda.synchronize(dev)
+        return [cls(n_slots, dim, prefixes, capacity, dev, r, world, cap, areas[r], bases, optimizer,
+                    stream=torch.cuda.Stream(device=dev), **kw) for r in range(world)]
 
-    # ---- forward_batched_direct (mod.rs:1076-1107 -> :874-942) -----------------------------------------
-    def forward(self, ids, batch, training=True):
-        """ids: int64-bit raw ids [n_slots * batch] (slot-major, one id per sample per slot) on the device.
-        Returns f16 [n_slots, batch, dim]."""
-        S, B = self.S, batch
-        n = S * B
-        assert ids.numel() == n, "the multi-GPU path takes one id per sample per slot (Criteo layout)"
-        slot_off = [s * B for s in range(S + 1)]
-        signs = self.be.add_prefix(ids, slot_off, self.prefixes, self.prefix_bit)
-        perm, counts = self.be.partition(signs, self.R)  # stable: (slot, sample) order kept inside a shard
-        send_signs = self.be.take(signs, perm)
-        send_splits, recv_splits = self._exchange_counts(counts)
-        recv_signs = self._a2a(send_signs, send_splits, recv_splits)
-        rows = self.be.serve_lookup(recv_signs, training)                      # [m, dim] f16, this shard's rows
-        back = self._a2a(rows, recv_splits, send_splits)                       # [n, dim] in partition order
-        out = self.be.put_rows(back, perm)                                     # batch order: row s*B+b
-        if training:
-            self._pending = (perm, send_splits, recv_splits, n)
-        return out.view(S, B, self.dim)
-
-    # ---- the same two calls with static shapes --------------------------------------------------------
-    # Every (source, destination) pair exchanges exactly `cap` slots (padding = PB_NULL_SIGN / zero rows), so no
-    # split sizes travel to the host and the whole step — kernels and NCCL collectives — can be captured in a
-    # CUDA graph.  `overflow` (device int32) is raised when a pair needs more than cap slots; check_overflow()
-    # reads it (a host sync: call it outside the hot loop).
-    def enable_static(self, batch, slack=1.3, extra=4096, cap=None):
-        n = self.S * batch
-        if cap is not None:
-            self.cap = min(int(cap), n) if self.R > 1 else n
-        else:
-            self.cap = int(n / self.R * slack) + extra if self.R > 1 else n
-        self.cap = (self.cap + 7) // 8 * 8
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=self.be.device)
-        return self.cap
-
-    def check_overflow(self):
-        return bool(int(self.overflow))
-
-    def calibrate_cap(self, id_batches, batch, margin=1.10, extra=256):
-        """Capacity per (source, destination) pair from sample batches: the largest per-owner count seen on any rank
-        (hot signs make it a property of the id distribution, not of chance), plus a margin.  Collective: every
-        rank must call it.  A later batch that still overflows raises the overflow flag (check_overflow)."""
-        if self.R == 1:
-            return self.S * batch
-        slot_off = [s * batch for s in range(self.S + 1)]
-        worst, where = 0, None
-        for ids in id_batches:
-            signs = self.be.add_prefix(ids, slot_off, self.prefixes, self.prefix_bit)
-            _, counts = self.be.partition(signs, self.R)
-            worst, where = max(worst, int(counts.max())), counts.device
-        t = torch.tensor([worst], dtype=torch.int64, device=where)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        return int(int(t) * margin) + extra
-
-    def _a2a_equal(self, send):
-        if self.R == 1:
-            return send
-        out = torch.empty_like(send)
-        dist.all_to_all_single(out, send, group=self.group)
-        return out
-
-    def forward_static(self, ids, batch, training=True):
-        S, B, R, cap = self.S, batch, self.R, self.cap
-        n = S * B
-        slot_off = [s * B for s in range(S + 1)]
-        signs = self.be.add_prefix(ids, slot_off, self.prefixes, self.prefix_bit)
-        perm, counts = self.be.partition(signs, R)
-        send = self.be.frame_signs(signs, perm, counts, R, cap, self.overflow)       # [R*cap]
-        recv = self._a2a_equal(send)
-        rows = self.be.serve_lookup(recv, training)                                   # [R*cap, dim] f16
-        back = self._a2a_equal(rows)
-        out = self.be.frame_rows(back, perm, counts, R, cap, False, self.be.empty_rows(n))
-        if training:
-            self._pending = (perm, counts, None, n)
-        return out.view(S, B, self.dim)
-
-    def backward_static(self, grads, scale=1.0):
-        assert self._pending is not None, "no forward batch is pending"
-        perm, counts, _, n = self._pending
-        self._pending = None
-        g = grads.reshape(n, self.dim)
-        send = self.be.frame_rows(g, perm, counts, self.R, self.cap, True, self.be.empty_rows(self.R * self.cap, g.dtype))
-        recv = self._a2a_equal(send)
-        self.be.serve_update(recv, scale)
-        return True
-
-    # ---- the framed exchange over NVLink peer memory (no NCCL on the data path) -----------------------------
-    def enable_p2p(self, batch):
-        """Receive buffers and barrier flags in symmetric memory (torch maps every peer's buffer into this process);
-        the exchange is then libpersia_b200's own store-to-peer kernel + flag barrier: stream-ordered, no host
-        involvement, capturable in one CUDA graph together with the compute."""
+    @classmethod
+    def distributed(cls, n_slots, dim, prefixes, capacity, cap, optimizer, device, group=None, **kw):
+        """One process per GPU: the receive areas live in torch symmetric memory (every peer's area mapped here)."""
+        import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
-        if not hasattr(self, "cap"):
-            self.enable_static(batch)
-        R, cap, dev = self.R, self.cap, self.be.device
-        grp = self.group if self.group is not None else dist.group.WORLD
-        self._symm = {}
+        grp = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+        dev = device if isinstance(device, torch.device) else torch.device("cuda", device)
+        nbytes = cls.area_bytes(world, cap, dim, kw.get("rows_f32", False))
+        if world == 1:
+            area = torch.zeros(nbytes + 256, dtype=torch.uint8, device=dev)
+            bases = [(area.data_ptr() + 255) // 256 * 256]
+            return cls(n_slots, dim, prefixes, capacity, dev, 0, 1, cap, area, bases, optimizer, **kw)
+        area = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        area.zero_()
+        hdl = symm.rendezvous(area, grp)
+        bases = [int(p) for p in hdl.buffer_ptrs]
+        assert all(b % 256 == 0 for b in bases)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=grp)
+        w = cls(n_slots, dim, prefixes, capacity, dev, rank, world, cap, (area, hdl), bases, optimizer, **kw)
+        w.group = grp
+        return w
 
-        def mapped(name, shape, dtype):
-            t = symm.empty(shape, dtype=dtype, device=dev)
-            t.zero_()
-            h = symm.rendezvous(t, grp)
-            self._symm[name] = (t, h, [int(p) for p in h.buffer_ptrs])
-            return t
+    @staticmethod
+    def calibrate_cap(id_batches, batch, prefixes, world, margin=1.15, extra=64, group=None):
+        """Slots per (source, owner) pair from sample batches (host ids, uint64 [n_slots * batch] each): the largest
+        number of distinct signs any batch requests of one owner, plus a margin.  With a process group: the maximum
+        over its ranks (collective).  A later batch that still overflows raises the status flag; the caller then
+        re-runs it on a worker built with a larger cap."""
+        worst = 0
+        for ids in id_batches:
+            worst = max(worst, int(distinct_per_owner(ids, batch, prefixes, world).max()))
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            import torch.distributed as dist
 
-        if R > 1:
-            self.p2p_recv = mapped("recv", (R * cap,), torch.int64)
-            self.p2p_back = mapped("back", (R * cap, self.dim), torch.float16)
-            self.p2p_grecv = mapped("grecv", (R * cap, self.dim), torch.float16)
-            mapped("flags", (16,), torch.int32)
-        else:
-            self.p2p_recv = torch.zeros(cap, dtype=torch.int64, device=dev)
-            self.p2p_back = torch.zeros((cap, self.dim), dtype=torch.float16, device=dev)
-            self.p2p_grecv = torch.zeros((cap, self.dim), dtype=torch.float16, device=dev)
-            flags = torch.zeros(16, dtype=torch.int32, device=dev)
-            self._symm = {"recv": (self.p2p_recv, None, [self.p2p_recv.data_ptr()]),
-                          "back": (self.p2p_back, None, [self.p2p_back.data_ptr()]),
-                          "grecv": (self.p2p_grecv, None, [self.p2p_grecv.data_ptr()]),
-                          "flags": (flags, None, [flags.data_ptr()])}
-        self.p2p_epoch = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.p2p_err = torch.zeros(1, dtype=torch.int32, device=dev)
-        torch.cuda.synchronize()
-        if R > 1:
-            dist.barrier(group=self.group)
-        return self
+            t = torch.tensor([worst], dtype=torch.int64)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            worst = int(t)
+        return (int(worst * margin) + extra + 7) // 8 * 8
 
-    def _p2p_send(self, framed, name):
-        self.be.SH.p2p_exchange(framed, self._symm[name][2], self.rank, self.cap)
-        self.be.SH.p2p_barrier(self._symm["flags"][2], self.p2p_epoch, self.rank, self.p2p_err)
+    # ---- forward_batched_direct / update_gradient_batched ------------------------------------------------------------
+    def _st(self):
+        s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
 
-    def forward_p2p(self, ids, batch, training=True):
-        S, B, R, cap = self.S, batch, self.R, self.cap
-        n = S * B
-        slot_off = [s * B for s in range(S + 1)]
-        signs = self.be.add_prefix(ids, slot_off, self.prefixes, self.prefix_bit)
-        perm, counts = self.be.partition(signs, R)
-        send = self.be.frame_signs(signs, perm, counts, R, cap, self.overflow)
-        self._p2p_send(send, "recv")
-        rows = self.be.serve_lookup(self.p2p_recv, training)
-        self._p2p_send(rows, "back")
-        out = self.be.frame_rows(self.p2p_back, perm, counts, R, cap, False, self.be.empty_rows(n))
-        if training:
-            self._pending = (perm, counts, None, n)
-        return out.view(S, B, self.dim)
+    def forward(self, ids, batch, training=True, row_off=None, slot_occ_off=None, out=None):
+        """ids: device int64-bit ids, slot-major; one id per sample per slot unless row_off (device int32 CSR offsets,
+        [n_slots*batch+1]) and slot_occ_off (host list) are given.  Returns f16 [n_slots, batch, dim]."""
+        ids = SH._as_i64_bits(ids)
+        if slot_occ_off is None:
+            slot_occ_off = [s * batch for s in range(self.S + 1)]
+        if out is None:
+            out = torch.empty((self.S, batch, self.dim), dtype=torch.float16, device=self.device)
+        off = (C.c_uint32 * (self.S + 1))(*[int(v) for v in slot_occ_off])
+        N.check(self.lib.pb_forward_sharded(self.shard.h, self.ctx.h, self.h, SH._ptr(ids), ids.numel(), SH._ptr(row_off), off,
+                                            int(batch), int(training), SH._ptr(out), self._st()))
+        return out
 
-    def backward_p2p(self, grads, scale=1.0):
-        assert self._pending is not None, "no forward batch is pending"
-        perm, counts, _, n = self._pending
-        self._pending = None
-        g = grads.reshape(n, self.dim)
-        send = self.be.frame_rows(g, perm, counts, self.R, self.cap, True, self.be.empty_rows(self.R * self.cap, g.dtype))
-        self._p2p_send(send, "grecv")
-        self.be.serve_update(self.p2p_grecv, scale)
-        return True
+    def backward(self, grads, scales=None, want_status=False):
+        """grads: f16/f32 tensor [n_slots, batch, dim] or a list of per-slot tensors (None = skipped slot)."""
+        if torch.is_tensor(grads):
+            grads = [grads[i] for i in range(self.S)]
+        ptrs = (C.c_void_p * self.S)()
+        is_f16 = None
+        for i, g in enumerate(grads):
+            if g is None:
+                ptrs[i] = None
+                continue
+            assert g.is_contiguous() and g.dtype in (torch.float16, torch.float32)
+            f16 = g.dtype == torch.float16
+            assert is_f16 is None or is_f16 == f16, "all slot gradients of one request share a dtype"
+            is_f16 = f16
+            ptrs[i] = g.data_ptr()
+        sc = (C.c_float * self.S)(*[float(v) for v in scales]) if scales is not None else None
+        status = torch.empty(self.S, dtype=torch.int32, device=self.device) if want_status else None
+        N.check(self.lib.pb_backward_sharded(self.shard.h, self.ctx.h, self.h, ptrs, int(bool(is_f16)), sc, SH._ptr(status),
+                                             self._st()))
+        return status
 
-    def check_p2p(self):
-        """True if a barrier gave up waiting for a peer (host sync)."""
-        return bool(int(self.p2p_err))
+    def status(self):
+        """(overflowed, wait_gave_up) — host sync."""
+        out = (C.c_uint32 * 2)()
+        N.check(self.lib.pb_xchg_status(self.h, C.byref(out), self._st()))
+        return bool(out[0]), bool(out[1])
 
-    def make_graphed_step(self, ids, grads, batch, stream, scale=1.0):
-        """The framed step on fixed buffers (`ids` int64 [S*B], `grads` f16 [S,B,dim]) with every compute segment
-        between two collectives replayed as a CUDA graph: 5 graph launches + 3 NCCL calls per step instead of ~25
-        kernel launches.  The collectives themselves stay outside the graphs.  Returns (step_fn, out) where out is
-        the f16 [S,B,dim] forward result buffer; refresh `ids` / `grads` in place between calls."""
-        S, B, R, cap, n = self.S, batch, self.R, self.cap, self.S * batch
-        slot_off = [s * B for s in range(S + 1)]
-        st = {}
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pb_xchg_destroy(self.h)
+            self.h = None
+        self.ctx.close()
+        self.shard.close()
 
-        def seg_a():
-            signs = self.be.add_prefix(ids, slot_off, self.prefixes, self.prefix_bit)
-            st["perm"], st["counts"] = self.be.partition(signs, R)
-            st["send"] = self.be.frame_signs(signs, st["perm"], st["counts"], R, cap, self.overflow)
-
-        def seg_b():
-            st["rows"] = self.be.serve_lookup(st["recv"], True)
-
-        def seg_c():
-            st["out"] = self.be.frame_rows(st["back"], st["perm"], st["counts"], R, cap, False, self.be.empty_rows(n))
-
-        def seg_d():
-            st["gsend"] = self.be.frame_rows(grads.reshape(n, self.dim), st["perm"], st["counts"], R, cap, True,
-                                             self.be.empty_rows(R * cap, grads.dtype))
-
-        def seg_e():
-            self.be.serve_update(st["grecv"], scale)
-
-        def a2a(key_in, key_out):
-            if key_out not in st:
-                st[key_out] = torch.empty_like(st[key_in])
-            if R == 1:
-                st[key_out].copy_(st[key_in])
-            else:
-                dist.all_to_all_single(st[key_out], st[key_in], group=self.group)
-
-        graphs = {}
-        with torch.cuda.stream(stream):
-            for _ in range(2):  # warm-up: allocations, NCCL channels
-                seg_a(); a2a("send", "recv"); seg_b(); a2a("rows", "back"); seg_c(); seg_d(); a2a("gsend", "grecv"); seg_e()  # noqa: E702
-            stream.synchronize()
-            for name, fn, nxt in (("a", seg_a, ("send", "recv")), ("b", seg_b, ("rows", "back")), ("c", seg_c, None),
-                                  ("d", seg_d, ("gsend", "grecv")), ("e", seg_e, None)):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
-                    fn()
-                graphs[name] = g
-                if nxt:  # run the collective once so that the next segment captures against a live buffer
-                    a2a(*nxt)
-            stream.synchronize()
-
-        def step():
-            graphs["a"].replay(); a2a("send", "recv")    # noqa: E702
-            graphs["b"].replay(); a2a("rows", "back")    # noqa: E702
-            graphs["c"].replay()
-            graphs["d"].replay(); a2a("gsend", "grecv")  # noqa: E702
-            graphs["e"].replay()
-
-        return step, st["out"].view(S, B, self.dim)
-
-    # ---- update_gradient_batched (mod.rs:1109-1129 -> :703-872) ------------------------------------------
-    def backward(self, grads, scale=1.0):
-        """grads: f16 [n_slots, batch, dim] (the loss-scaled gradient of forward()'s output)."""
-        assert self._pending is not None, "no forward batch is pending"
-        perm, send_splits, recv_splits, n = self._pending
-        self._pending = None
-        g = grads.reshape(n, self.dim)
-        # NaN rule: the reference skips a slot whose gradient holds a NaN (mod.rs:731-746).  Here the scan runs on
-        # the owner over what it received (device side, no host sync): a shard that is handed any NaN skips this
-        # step's update of its rows; see DESIGN.md §Multi-GPU for the difference.
-        send = self.be.take_rows(g, perm)
-        recv = self._a2a(send, send_splits, recv_splits)
-        self.be.serve_update(recv, scale)
-        return True
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,6 +1,15 @@
-"""GPU: ShardedEmbeddingWorker with the CUDA backend.  R = 1 in process (every GPU box), R = 2 over NCCL when
-two GPUs are visible (gpurun --gpus 2): results equal the oracle's embedding worker with R parameter servers
-fed the concatenated batch, bit for bit (SGD; strict reduce order on the owners)."""
+"""GPU: the sharded path (pb_forward_sharded / pb_backward_sharded through ShardedEmbeddingWorker) against the oracle's
+embedding worker with R parameter servers.
+
+R virtual ranks share cuda:0 (own table, context, stream and receive area each; the kernels and the flag protocol are
+the ones a multi-GPU box runs, "peer" stores just land in the same GPU), so the R > 1 parity runs on every box,
+including the driver's 1-GPU lease.  With >= 2 GPUs the same comparison also runs with one process per GPU over
+symmetric memory (torch.multiprocessing spawn).
+
+Semantics checked: a rank's batch is one request per owner; an owner applies the R gradient requests of a step in
+rank order (the reference with R NN workers applies them in arrival order).  The oracle therefore runs R forward
+requests, then R backward requests in rank order.  Everything bit for bit (Adagrad against the oracle's exact-rsqrt
+mode), incl. the per-slot NaN / skipped-slot rule on the requesting rank (mod.rs:731-746)."""
 import os
 import socket
 import sys
@@ -12,157 +21,300 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+from util import f16_ulp_diff, full_row_off, make_batch, to_dev_i32, to_dev_ids  # noqa: E402
+
 pytestmark = pytest.mark.gpu
-
-S, B, DIM = 4, 512, 64
-CARD = [3, 50, 3000, 200000]
-STEPS = 3
+DEV = "cuda:0"
 
 
-def _batches(R):
-    rng = np.random.default_rng(5)
-    out = []
-    for _ in range(STEPS):
-        ids = np.stack([np.stack([rng.integers(0, CARD[s], size=B, dtype=np.uint64) for s in range(S)]) for _ in range(R)])
-        g = (rng.standard_normal((R, S, B, DIM)) * 1e-2).astype(np.float16)
-        out.append((ids, g))
-    return out
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
 
 
-def _reference(R):
-    import oracle
-
-    pf = [oracle.index_prefix(i) for i in range(S)]
-    w = oracle.Worker([oracle.SlotCfg(DIM, prefix=p) for p in pf], n_ps=R)
-    w.configure()
-    w.set_optimizer(oracle.Optim(oracle.SGD, lr=0.05, wd=0.001))
-    GB = R * B
-    outs = []
-    for ids, g in _batches(R):
-        gid = np.concatenate([ids[:, s, :].reshape(-1) for s in range(S)])
-        want, octx = w.forward(gid, np.arange(S * GB + 1, dtype=np.uint32), GB, training=True)
-        outs.append(want)
-        w.backward(octx, [np.concatenate([g[r, s] for r in range(R)]) for s in range(S)])
-    return w, outs, pf
+def _optim(N, oracle, kind):
+    if kind == oracle.SGD:
+        return dict(kind=N.OPT_SGD, lr=0.05, wd=0.001), oracle.Optim(oracle.SGD, lr=0.05, wd=0.001)
+    if kind == oracle.ADAGRAD:
+        return (dict(kind=N.OPT_ADAGRAD, lr=0.02, initialization=0.01, eps=1e-10),
+                oracle.Optim(oracle.ADAGRAD, lr=0.02, init_acc=0.01, eps=1e-10))
+    return (dict(kind=N.OPT_ADAGRAD_VW, lr=0.02, initialization=0.01, eps=1e-10),
+            oracle.Optim(oracle.ADAGRAD_VW, lr=0.02, init_acc=0.01, eps=1e-10))
 
 
-def _make_worker(torch, rank_dev):
-    import oracle
+def _group(torch, oracle, R, S, dim, kind, B, sqrt=None, rows_f32=False, max_ids=1):
     from persia_b200 import native as N
-    from persia_b200.worker import CudaBackend, ShardedEmbeddingWorker
+    from persia_b200.worker import ShardedEmbeddingWorker
 
     pf = [oracle.index_prefix(i) for i in range(S)]
-    be = CudaBackend(DIM, 1 << 18, rank_dev, dict(kind=N.OPT_SGD, lr=0.05, wd=0.001), {}, max_occurrences=1 << 16)
-    be.ctx.set_strict_reduce(True)
-    return ShardedEmbeddingWorker(S, DIM, pf, be), be, pf
+    gpu_opt, cpu_opt = _optim(N, oracle, kind)
+    ws = ShardedEmbeddingWorker.local_group(R, S, dim, pf, 1 << 16, cap=S * B * max_ids, optimizer=gpu_opt, max_batch=B,
+                                            sqrt_scaling=sqrt, rows_f32=rows_f32, max_ids_per_sample=max_ids)
+    w = oracle.Worker([oracle.SlotCfg(dim, sqrt_scaling=bool(sqrt[i]) if sqrt else False, prefix=pf[i]) for i in range(S)], n_ps=R)
+    w.configure()
+    w.set_optimizer(cpu_opt)
+    for x in ws:  # table storage is allocated on first use, with a device-wide sync: not while a peer spins on a flag
+        x.shard.get_entries(torch.zeros(1, dtype=torch.int64, device=DEV))
+    torch.cuda.synchronize()
+    return ws, w, pf
 
 
-def _check_shard(torch, be, w, pf, R, rank, dev):
-    import oracle
-    from util import to_dev_ids
-
-    probe = np.concatenate([oracle.add_prefix(np.arange(min(c, 3000), dtype=np.uint64), 8, pf[i]) for i, c in enumerate(CARD)])
-    mine = probe[oracle.shard_of(probe, R) == rank]
-    ent, found = be.shard.get_entries(to_dev_ids(mine, dev))
-    ent, found = ent.cpu().numpy(), found.cpu().numpy()
-    n = 0
-    for k, s in enumerate(mine):
-        ref = w.get_entry(int(s))
-        assert (ref is not None) == bool(found[k])
-        if ref is not None:
-            assert ent[k].tobytes() == ref.tobytes()
-            n += 1
-    return n
-
-
-def test_worker_single_rank_matches_oracle():
-    import torch
-
-    assert torch.cuda.is_available()
-    dev = torch.device("cuda", 0)
-    wk, be, pf = _make_worker(torch, dev)
-    w, outs, _ = _reference(1)
-    for step, (ids, g) in enumerate(_batches(1)):
-        out = wk.forward(torch.from_numpy(ids[0].reshape(-1).view(np.int64)).to(dev), B, training=True).cpu().numpy()
-        for s in range(S):
-            np.testing.assert_array_equal(out[s].view(np.uint16), outs[step][s].view(np.uint16))
-        wk.backward(torch.from_numpy(g[0]).to(dev))
-    assert _check_shard(torch, be, w, pf, 1, 0, dev) > 1000
+def _check_rows(torch, oracle, ws, w, signs, R):
+    signs = np.array(sorted(signs), np.uint64)
+    owner = oracle.shard_of(signs, R)
+    for r in range(R):
+        mine = signs[owner == r]
+        if not mine.size:
+            continue
+        ent, found = ws[r].shard.get_entries(to_dev_ids(mine, DEV))
+        ent = ent.cpu().numpy()
+        assert found.all()
+        for k, sign in enumerate(mine):
+            ref = w.get_entry(int(sign))
+            assert ref is not None and ent[k].tobytes() == ref.tobytes(), (r, k, sign)
+        assert len(ws[r].shard) == w.ps_len(r)
+    for x in ws:
+        assert x.status() == (False, False)
+        assert x.shard.counters()["wait_errors"] == 0
 
 
-@pytest.mark.parametrize("p2p", [False, True])
-def test_worker_single_rank_static_frames(p2p):
-    import torch
+@pytest.mark.parametrize("R,dim,kind,f32", [(2, 64, 0, False), (2, 128, 1, False), (4, 128, 1, False), (8, 128, 1, False),
+                                            (3, 16, 2, True), (2, 12, 0, False), (1, 64, 1, False)])
+def test_virtual_ranks_match_oracle(torch_cuda, oracle, R, dim, kind, f32):
+    torch = torch_cuda
+    oracle.set_rsqrt_exact(True)
+    try:
+        rng = np.random.default_rng(100 * R + dim)
+        S, B, card = 5, 600, [3, 50, 2000, 100000, 11]
+        ws, w, pf = _group(torch, oracle, R, S, dim, kind, B)
+        outs = [torch.empty((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
+        seen = set()
+        for step in range(4):
+            ids = [make_batch(rng, S, B, card)[0] for _ in range(R)]
+            d_ids = [to_dev_ids(ids[r], DEV) for r in range(R)]
+            torch.cuda.synchronize()
+            for r in range(R):
+                ws[r].forward(d_ids[r], B, training=True, out=outs[r])
+            torch.cuda.synchronize()
+            octx = []
+            for r in range(R):
+                want, c = w.forward(ids[r], full_row_off(S, B), B, training=True)
+                octx.append(c)
+                got = outs[r].cpu().numpy()
+                for i in range(S):
+                    np.testing.assert_array_equal(got[i].view(np.uint16), want[i].view(np.uint16))
+                    seen.update(w.ctx_signs(c, i).tolist())
+            g = (rng.standard_normal((R, S, B, dim)) * 1e-2).astype(np.float32 if f32 else np.float16)
+            skip = [None] * R
+            if step == 1:
+                g[0, 2, B // 2, dim - 1] = np.nan          # rank 0 drops slot 2 of ITS request; the other ranks' stand
+            dg = [[torch.from_numpy(g[r, i]).to(DEV) for i in range(S)] for r in range(R)]
+            if step == 2 and R > 1:
+                dg[R - 1][0] = None                          # add_skipped_gradient on the last rank
+                skip[R - 1] = [1] + [0] * (S - 1)
+            torch.cuda.synchronize()
+            sts = [ws[r].backward(dg[r], want_status=True) for r in range(R)]
+            torch.cuda.synchronize()
+            for r in range(R):
+                ost = w.backward(octx[r], [g[r, i] for i in range(S)], skip=skip[r])
+                assert sts[r].cpu().numpy().tolist() == ost, (step, r)
+        _check_rows(torch, oracle, ws, w, seen, R)
+    finally:
+        oracle.set_rsqrt_exact(False)
 
-    dev = torch.device("cuda", 0)
-    wk, be, pf = _make_worker(torch, dev)
-    wk.enable_static(B)
-    if p2p:
-        wk.enable_p2p(B)
-    w, outs, _ = _reference(1)
-    for step, (ids, g) in enumerate(_batches(1)):
-        out = (wk.forward_p2p if p2p else wk.forward_static)(torch.from_numpy(ids[0].reshape(-1).view(np.int64)).to(dev), B, training=True).cpu().numpy()
-        for s in range(S):
-            np.testing.assert_array_equal(out[s].view(np.uint16), outs[step][s].view(np.uint16))
-        (wk.backward_p2p if p2p else wk.backward_static)(torch.from_numpy(g[0]).to(dev))
-    assert not wk.check_overflow()
-    assert _check_shard(torch, be, w, pf, 1, 0, dev) > 1000
+
+def test_virtual_ranks_ragged_sqrt_scale(torch_cuda, oracle):
+    """Ragged LIL (several ids per sample, empty samples), sqrt scaling and a loss scale: f32 rows travel, pooling and
+    the gradient's sample factors are applied on the requester."""
+    torch = torch_cuda
+    rng = np.random.default_rng(7)
+    R, S, B, dim, card = 3, 4, 300, 32, [5, 300, 40000, 17]
+    sqrt = [True, False, True, False]
+    ws, w, pf = _group(torch, oracle, R, S, dim, oracle.SGD, B, sqrt=sqrt, rows_f32=True, max_ids=5)
+    seen = set()
+    for step in range(3):
+        batches = [make_batch(rng, S, B, card, max_ids=5, allow_empty=True) for _ in range(R)]
+        outs = []
+        torch.cuda.synchronize()
+        dev_in = [(to_dev_ids(b[0], DEV), to_dev_i32(b[1], DEV)) for b in batches]
+        pre = [torch.empty((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
+        torch.cuda.synchronize()
+        for r in range(R):
+            outs.append(ws[r].forward(dev_in[r][0], B, training=True, row_off=dev_in[r][1], slot_occ_off=batches[r][2], out=pre[r]))
+        torch.cuda.synchronize()
+        octx = []
+        for r in range(R):
+            want, c = w.forward(batches[r][0], batches[r][1], B, training=True)
+            octx.append(c)
+            got = outs[r].cpu().numpy()
+            for i in range(S):
+                assert f16_ulp_diff(got[i], want[i]) <= 1  # f32 sum order of a sample's ids differs (shard order there)
+                seen.update(w.ctx_signs(c, i).tolist())
+        g = (rng.integers(-64, 65, size=(R, S, B, dim)) / 4.0).astype(np.float16)  # x 1/128 stays exact in f32
+        scale = [128.0, 1.0, 128.0, 1.0]
+        dg = [[torch.from_numpy(g[r, i]).to(DEV) for i in range(S)] for r in range(R)]
+        torch.cuda.synchronize()
+        for r in range(R):
+            ws[r].backward(dg[r], scales=scale)
+        torch.cuda.synchronize()
+        for r in range(R):
+            w.backward(octx[r], [g[r, i] for i in range(S)], scale=scale)
+    _check_rows(torch, oracle, ws, w, seen, R)
 
 
-def _rank_main(rank, R, port, q, static=False):
+def test_virtual_ranks_graph_replay(torch_cuda, oracle):
+    """The whole sharded step of a rank — kernels, peer stores, flag waits — captured in ONE CUDA graph per rank and
+    replayed: the mode bench.py --gpus N times.  Phase counters live on the device, so replays stay in step."""
+    torch = torch_cuda
+    oracle.set_rsqrt_exact(True)
+    try:
+        rng = np.random.default_rng(11)
+        R, S, B, dim, card = 4, 6, 512, 128, [3, 17, 900, 50000, 50000, 11]
+        ws, w, pf = _group(torch, oracle, R, S, dim, oracle.ADAGRAD, B)
+        ids_dev = [torch.zeros(S * B, dtype=torch.int64, device=DEV) for _ in range(R)]
+        g_dev = [torch.zeros((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
+        outs = [torch.empty((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
+
+        def enqueue(r):
+            ws[r].forward(ids_dev[r], B, training=True, out=outs[r])
+            ws[r].backward(g_dev[r])
+
+        def oracle_step(ids, g):
+            octx = [w.forward(ids[r], full_row_off(S, B), B, training=True) for r in range(R)]
+            for r in range(R):
+                w.backward(octx[r][1], [g[r, i] for i in range(S)])
+            return [o[0] for o in octx]
+
+        zero_ids = [np.zeros(S * B, np.uint64) for _ in range(R)]
+        zero_g = np.zeros((R, S, B, dim), np.float16)
+        torch.cuda.synchronize()
+        for r in range(R):  # eager warm-up step (id 0 in every slot, zero gradients)
+            enqueue(r)
+        torch.cuda.synchronize()
+        oracle_step(zero_ids, zero_g)
+        graphs = []
+        for r in range(R):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=ws[r].stream, capture_error_mode="thread_local"):
+                enqueue(r)
+            graphs.append(gph)
+        seen = {int(oracle.add_prefix(np.zeros(1, np.uint64), 8, p)[0]) for p in pf}
+        for it in range(3):
+            ids = [make_batch(rng, S, B, card)[0] for _ in range(R)]
+            g = (rng.standard_normal((R, S, B, dim)) * 1e-2).astype(np.float16)
+            for r in range(R):
+                ids_dev[r].copy_(to_dev_ids(ids[r], DEV))
+                g_dev[r].copy_(torch.from_numpy(g[r]).to(DEV))
+            torch.cuda.synchronize()
+            for r in range(R):
+                with torch.cuda.stream(ws[r].stream):
+                    graphs[r].replay()
+            torch.cuda.synchronize()
+            want = oracle_step(ids, g)
+            for r in range(R):
+                got = outs[r].cpu().numpy()
+                for i in range(S):
+                    np.testing.assert_array_equal(got[i].view(np.uint16), want[r][i].view(np.uint16))
+                    seen.update(oracle.add_prefix(ids[r][i * B:(i + 1) * B], 8, pf[i]).tolist())
+        _check_rows(torch, oracle, ws, w, seen, R)
+    finally:
+        oracle.set_rsqrt_exact(False)
+
+
+def test_overflow_is_flagged(torch_cuda, oracle):
+    """A pair that needs more than cap slots raises the status flag (the excess signs read as zeros)."""
+    torch = torch_cuda
+    from persia_b200 import native as N
+    from persia_b200.worker import ShardedEmbeddingWorker
+
+    S, B, dim, R = 2, 256, 16, 2
+    pf = [oracle.index_prefix(i) for i in range(S)]
+    ws = ShardedEmbeddingWorker.local_group(R, S, dim, pf, 1 << 12, cap=16, optimizer=dict(kind=N.OPT_SGD, lr=0.1), max_batch=B)
+    for x in ws:
+        x.shard.get_entries(torch.zeros(1, dtype=torch.int64, device=DEV))
+    ids = [to_dev_ids(np.arange(S * B, dtype=np.uint64) + 1000 * r, DEV) for r in range(R)]
+    outs = [torch.empty((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
+    torch.cuda.synchronize()
+    for r in range(R):
+        ws[r].forward(ids[r], B, training=False, out=outs[r])
+    torch.cuda.synchronize()
+    assert all(x.status()[0] for x in ws) and not any(x.status()[1] for x in ws)
+
+
+# ---- one process per GPU over symmetric memory (needs >= 2 GPUs) --------------------------------------------------------
+def _rank_main(rank, world, port, result_dir):
     import torch
     import torch.distributed as dist
 
+    import oracle
+    from persia_b200 import native as N
+    from persia_b200.worker import ShardedEmbeddingWorker
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=R, device_id=dev)
-    try:
-        wk, be, pf = _make_worker(torch, dev)
-        w, outs, _ = _reference(R)
-        if static == "p2p":  # capacity sized from the batches (collective), as bench.py does
-            sample = [torch.from_numpy(ids[rank].reshape(-1).view(np.int64)).to(dev) for ids, _ in _batches(R)]
-            cap = wk.calibrate_cap(sample, B)
-            assert cap < S * B
-            wk.enable_static(B, cap=cap)
-        elif static:
-            wk.enable_static(B)
-        if static == "p2p":
-            wk.enable_p2p(B)
-        fwd = {False: wk.forward, True: wk.forward_static, "p2p": wk.forward_p2p}[static]
-        bwd = {False: wk.backward, True: wk.backward_static, "p2p": wk.backward_p2p}[static]
-        for step, (ids, g) in enumerate(_batches(R)):
-            d_ids = torch.from_numpy(ids[rank].reshape(-1).view(np.int64)).to(dev)
-            out = fwd(d_ids, B, training=True).cpu().numpy()
-            for s in range(S):
-                np.testing.assert_array_equal(out[s].view(np.uint16), outs[step][s][rank * B:(rank + 1) * B].view(np.uint16))
-            bwd(torch.from_numpy(g[rank]).to(dev))
-        if static:
-            assert not wk.check_overflow()
-        if static == "p2p":
-            assert not wk.check_p2p()
-        n = _check_shard(torch, be, w, pf, R, rank, dev)
-        q.put((rank, n))
-    finally:
-        dist.destroy_process_group()
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    S, B, dim, card = 5, 600, 128, [3, 50, 2000, 100000, 11]
+    pf = [oracle.index_prefix(i) for i in range(S)]
+    wk = ShardedEmbeddingWorker.distributed(S, dim, pf, 1 << 16, cap=S * B, device=dev, max_batch=B,
+                                            optimizer=dict(kind=N.OPT_ADAGRAD, lr=0.02, initialization=0.01, eps=1e-10))
+    rng = np.random.default_rng(42)
+    outs, seen = [], set()
+    for step in range(3):
+        ids = [make_batch(rng, S, B, card)[0] for _ in range(world)]  # every rank draws all, keeps its own
+        g = (rng.standard_normal((world, S, B, dim)) * 1e-2).astype(np.float16)
+        out = wk.forward(torch.from_numpy(ids[rank].view(np.int64)).to(dev), B, training=True)
+        wk.backward(torch.from_numpy(g[rank]).to(dev))
+        torch.cuda.synchronize()
+        dist.barrier()
+        outs.append(out.cpu().numpy())
+        for r in range(world):
+            for i in range(S):
+                seen.update(oracle.add_prefix(ids[r][i * B:(i + 1) * B], 8, pf[i]).tolist())
+    signs = np.array(sorted(seen), np.uint64)
+    mine = signs[oracle.shard_of(signs, world) == rank]
+    ent, found = wk.shard.get_entries(torch.from_numpy(mine.view(np.int64)).to(dev))
+    assert found.all() and wk.status() == (False, False)
+    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), outs=np.stack(outs), signs=mine, ent=ent.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("static", [False, True, "p2p"])
-def test_worker_two_ranks_nccl_matches_oracle(static):
-    import torch
+def test_two_processes_symmetric_memory(torch_cuda, oracle, tmp_path):
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2); the virtual-rank tests above cover R > 1 on one GPU")
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world = 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q, static)) for r in range(2)]
-    for p in procs:
-        p.start()
-    got = dict(q.get(timeout=300) for _ in range(2))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    assert sum(got.values()) > 1000
+    mp.spawn(_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    oracle.set_rsqrt_exact(True)
+    try:
+        S, B, dim, card = 5, 600, 128, [3, 50, 2000, 100000, 11]
+        pf = [oracle.index_prefix(i) for i in range(S)]
+        w = oracle.Worker([oracle.SlotCfg(dim, prefix=p) for p in pf], n_ps=world)
+        w.configure()
+        w.set_optimizer(oracle.Optim(oracle.ADAGRAD, lr=0.02, init_acc=0.01, eps=1e-10))
+        rng = np.random.default_rng(42)
+        res = [np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(world)]
+        for step in range(3):
+            ids = [make_batch(rng, S, B, card)[0] for _ in range(world)]
+            g = (rng.standard_normal((world, S, B, dim)) * 1e-2).astype(np.float16)
+            octx = [w.forward(ids[r], full_row_off(S, B), B, training=True) for r in range(world)]
+            for r in range(world):
+                for i in range(S):
+                    np.testing.assert_array_equal(res[r]["outs"][step][i].view(np.uint16), octx[r][0][i].view(np.uint16))
+            for r in range(world):
+                w.backward(octx[r][1], [g[r, i] for i in range(S)])
+        for r in range(world):
+            for k, sign in enumerate(res[r]["signs"]):
+                assert res[r]["ent"][k].tobytes() == w.get_entry(int(sign)).tobytes()
+    finally:
+        oracle.set_rsqrt_exact(False)
