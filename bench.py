@@ -2,8 +2,16 @@
 """bench.py — samples/s of PERSIA's sparse-embedding hot path on B200 (BASELINE.json metric).
 
 A "step" is one pass of the hot path over one batch of synthetic Criteo-shaped ids: training forward
-(prefix -> find-or-admit -> gather+pool -> f16) and backward (NaN scan -> group -> reduce -> Adagrad update).
-N=1 workload = BASELINE configs[1]: 26 slots, 1e8 resident rows, dim 64, batch 4096, Adagrad.
+(prefix -> per-slot dedup -> find-or-admit over the distinct signs -> gather+pool -> f16) and backward (NaN rule ->
+in-order gradient reduce per sign -> Adagrad update).
+
+BASELINE.json names two things, measured by two legs:
+  * metric leg — "samples/sec (26 slots, dim128) at 1/2/4/8 B200": dim 128, 8192 samples per GPU (configs[3]'s
+    65536 / 8), 1e8 resident rows per GPU, Adagrad.  This is `value` / `e2e` at every N (weak scaling: per-GPU work is
+    fixed).  At N >= 2 the rows are hash-sharded over the GPUs and the exchange runs inside the kernels (configs[2]); at
+    N = 8 the ids are drawn from a 1e10 key space over a capacity-bounded table with eviction on (configs[3]).
+  * roofline leg — configs[1], "1xB200: 26 slots, 1e8 rows, dim-64, batch 4096, GPU hash lookup + sparse Adagrad,
+    HBM GB/s vs roofline": run at N = 1 only; `roofline` comes from it.
 
   python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA, through the C ABI)
   python bench.py --impl reference [...]                     the reference's CPU path (oracle port) on host cores
@@ -26,7 +34,7 @@ if ROOT not in sys.path:
 
 from persia_b200 import workload as W  # noqa: E402
 
-METRIC = "samples/sec (Criteo-1TB-shape DLRM sparse path, 26 slots)"
+METRIC = "samples/sec (Criteo-1TB-shape DLRM sparse path, 26 slots, dim128)"
 UNIT = "samples/s"
 
 
@@ -38,20 +46,43 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=float, default=float(os.environ.get("PB_BENCH_ROWS", 1e8)),
                     help="resident rows per GPU (weak scaling: the table grows with N)")
-    ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
-    ap.add_argument("--dim", type=int, default=None, help="default 64 (configs[1]) at every N so that the scaling runs compare like with like; --dim 128 gives configs[2..3]")
+    ap.add_argument("--batch", type=int, default=8192, help="samples per GPU per step (metric leg)")
+    ap.add_argument("--dim", type=int, default=128, help="embedding dim of the metric leg")
     ap.add_argument("--slots", type=int, default=26)
     ap.add_argument("--alpha", type=float, default=1.05)
-    ap.add_argument("--sets", type=int, default=16, help="rotating input/grad/output buffer sets (> L2 in total)")
+    ap.add_argument("--keyspace", type=float, default=None,
+                    help="key space per GPU the ids are drawn from; default = --rows (everything resident) except at "
+                         "N = 8: 1.25e9 per GPU = configs[3]'s 1e10, over a table bounded at --rows with eviction on")
+    ap.add_argument("--sets", type=int, default=8, help="rotating input/grad/output buffer sets (> L2 in total)")
     ap.add_argument("--cpu-seconds", type=float, default=float(os.environ.get("PB_BENCH_CPU_SECONDS", 12)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sync-grouping", action="store_true", help="run the backward's grouping inside pb_backward")
-    ap.add_argument("--dist-graph", action="store_true", help="multi-GPU: capture the framed step incl. NCCL in CUDA graphs")
-    ap.add_argument("--dist-nccl", action="store_true", help="multi-GPU: NCCL all-to-all instead of the peer-memory exchange")
-    ap.add_argument("--dist-dynamic", action="store_true", help="multi-GPU: split-size all-to-all (host sync per step)")
-    ap.add_argument("--equal-card", action="store_true", help="diagnostic: every slot gets rows/slots ids (no tiny slots)")
+    ap.add_argument("--no-roofline-leg", action="store_true", help="N = 1: skip the configs[1] (dim 64) leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the replay of captured steps against the oracle")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
+
+
+def keyspace_per_gpu(args):
+    if args.keyspace is not None:
+        return float(args.keyspace)
+    return 1.25e9 if args.gpus == 8 else float(args.rows)
+
+
+def workload_config(args):
+    """The same dict in both arms (the driver compares them)."""
+    n, ks = args.gpus, keyspace_per_gpu(args)
+    bounded = ks > args.rows
+    which = "configs[3]" if (n == 8 and bounded) else ("configs[2]" if n >= 2 else "configs[2] shape on one GPU")
+    return {
+        "workload": f"{which}: {args.slots} Criteo-shaped slots, dim {args.dim}, batch {args.batch}/GPU x {n} GPU, "
+                    f"{int(args.rows):.3g} resident rows/GPU, key space {ks * n:.3g}"
+                    f"{' (capacity-bounded table, eviction on)' if bounded else ''}, Adagrad, training forward + backward",
+        "global_batch": args.batch * n, "slots": args.slots, "dim": args.dim, "rows_per_gpu": int(args.rows),
+        "key_space_total": int(ks * n), "zipf_alpha": args.alpha, "optimizer": "adagrad(lr=0.01, init=0.01, eps=1e-10)",
+        "parallelism": "single shard" if n == 1 else f"rows hash-sharded over {n} GPUs (farmhash64 % {n}), data-parallel "
+                                                      f"batches, distinct signs / rows / reduced gradients stored into the "
+                                                      f"peer's memory over NVLink by the compute kernels",
+    }
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -111,24 +142,47 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # the reference's CPU path (oracle port): timed on the host cores
 # ------------------------------------------------------------------------------------------------------
+def host_cores():
+    """Cores this process may really use: the affinity mask, capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(quota)))
+    return n, quota
+
+
 class CpuArm:
     """The reference's CPU path (oracle port of its EW + PS, in process) on the same workload: a pool of distinct
     batches, admitted once untimed (steady state is a warm table; the GPU arm is timed on a resident table too)."""
 
-    def __init__(self, args, dim, card, n_threads=None):
+    def __init__(self, args, n_threads=None):
         import oracle
 
-        self.S, self.B, self.dim = args.slots, args.batch, dim
-        self.n_threads = n_threads or os.cpu_count() or 1
+        self.S, self.B, self.dim = args.slots, args.batch, args.dim
+        self.cores, self.quota = host_cores()
+        self.n_threads = n_threads or self.cores
+        card = W.scaled_cardinalities(int(keyspace_per_gpu(args) * args.gpus), self.S)
         pf = W.index_prefixes(self.S)
-        self.w = oracle.Worker([oracle.SlotCfg(dim, prefix=p) for p in pf], n_ps=1, capacity_per_ps=1 << 40,
+        self.w = oracle.Worker([oracle.SlotCfg(self.dim, prefix=p) for p in pf], n_ps=1, capacity_per_ps=1 << 40,
                                n_internal_shards=max(64, 8 * self.n_threads))
         self.w.configure()
         self.w.set_optimizer(oracle.Optim(oracle.ADAGRAD, lr=0.01, init_acc=0.01, eps=1e-10))
         self.row_off = np.arange(self.S * self.B + 1, dtype=np.uint32)
         rng = np.random.default_rng(123)
-        self.g = [(rng.standard_normal((self.B, dim)) * 1e-2).astype(np.float16) for _ in range(self.S)]
-        self.n_pool = int(min(256, max(4 * self.n_threads, 16)))
+        self.g = [(rng.standard_normal((self.B, self.dim)) * 1e-2).astype(np.float16) for _ in range(self.S)]
+        self.n_pool = int(min(128, max(2 * self.n_threads, 8)))
         self.ids = W.make_batches(1001, card, self.B, self.n_pool, args.alpha)
         self.warm_seconds = self.run(self.ids)
         self.cursor = 0
@@ -142,68 +196,57 @@ class CpuArm:
         self.cursor = (self.cursor + n_batches) % self.n_pool
         return self.run(np.ascontiguousarray(self.ids[idx]))
 
-    def describe(self, n_batches):
-        return (f"{n_batches} batches ({self.n_pool} distinct, table warmed by one untimed pass) x {self.B} samples x "
-                f"{self.S} slots dim {self.dim}, Adagrad, fwd+bwd, {self.n_threads} threads each owning whole batches "
-                f"(in-process EW+PS, no RPC/codec/H2D)")
+    def describe(self, n_batches, reps):
+        return (f"median of {reps} repetitions of {n_batches} batches ({self.n_pool} distinct, table warmed by one untimed "
+                f"pass) x {self.B} samples x {self.S} slots dim {self.dim}, Adagrad, fwd+bwd, {self.n_threads} threads each "
+                f"owning whole batches (in-process EW+PS, no RPC/codec/H2D); affinity+cgroup give {self.cores} cores"
+                f"{'' if not self.quota else ' (cpu.max quota %.1f)' % self.quota}")
 
 
-def cpu_arm(args, dim, seconds, card, n_threads=None):
-    arm = CpuArm(args, dim, card, n_threads)
+def cpu_arm(args, seconds):
+    arm = CpuArm(args)
     t = arm.step(arm.n_pool)
-    reps = int(max(1, min(64, seconds / max(t, 1e-3))))
-    n_batches, tot = 0, 0.0
-    for _ in range(reps):
-        tot += arm.step(arm.n_pool)
-        n_batches += arm.n_pool
-    return {"value": n_batches * arm.B / tot, "unit": UNIT, "cores": arm.n_threads, "kind": "port",
-            "sample": arm.describe(n_batches), "seconds": tot}
+    per_rep = int(max(arm.n_threads, min(arm.n_pool, arm.n_pool * (seconds / 3.0) / max(t, 1e-3))))
+    vals = []
+    for _ in range(3):
+        tt = arm.step(per_rep)
+        vals.append(per_rep * arm.B / tt)
+    return {"value": float(np.median(vals)), "unit": UNIT, "cores": arm.n_threads, "kind": "port",
+            "sample": arm.describe(per_rep, 3), "spread": [float(min(vals)), float(max(vals))]}
 
 
 def reference_main(args):
     """--impl reference: the reference's own CPU implementation of the path (no Rust toolchain here, so the
-    oracle port) with all host threads.  A step = two batches per host thread, fwd+bwd."""
+    oracle port) with all the host threads this process may use.  A step = two batches per host thread, fwd+bwd."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    dim = args.dim or 64
-    card = W.scaled_cardinalities(int(args.rows) * args.gpus, args.slots)
-    arm = CpuArm(args, dim, card)
-    per_step = 2 * arm.n_threads
+    arm = CpuArm(args)
+    per_step = min(arm.n_pool, 2 * arm.n_threads)
     for _ in range(max(args.warmup, 1)):
         arm.step(per_step)
+        if arm.warm_seconds > 20:
+            break
     K = max(1, args.steps)
     t0 = time.time()
-    tot = 0.0
-    done = 0
+    times = []
     for _ in range(K):
-        tot += arm.step(per_step)
-        done += 1
+        times.append(arm.step(per_step))
         if time.time() - t0 > 150:  # keep the whole run within a few minutes
             break
-    v = done * per_step * arm.B / tot
+    done = len(times)
+    v = done * per_step * arm.B / sum(times)
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * sum(times) / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": workload_config(args, dim, card, args.gpus),
+        "config": workload_config(args),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.n_threads, "kind": "port",
-                         "sample": arm.describe(done * per_step)},
+                         "sample": arm.describe(per_step, done),
+                         "median_step_value": float(per_step * arm.B / np.median(times))},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def workload_config(args, dim, card, n_gpus):
-    return {
-        "workload": f"configs[{1 if dim == 64 else 2}] shape x {n_gpus} GPU: {args.slots} Criteo-shaped slots, "
-                    f"{int(args.rows) * n_gpus:.3g} rows, dim {dim}, batch {args.batch}/GPU, Adagrad, training forward + backward",
-        "global_batch": args.batch * n_gpus, "slots": args.slots, "dim": dim, "rows_total": int(args.rows) * n_gpus,
-        "zipf_alpha": args.alpha, "optimizer": "adagrad(lr=0.01, init=0.01, eps=1e-10)",
-        "parallelism": "single shard" if n_gpus == 1 else f"rows hash-sharded over {n_gpus} GPUs (farmhash64 % {n_gpus}), "
-                                                          f"data-parallel batches, all-to-all over NCCL",
-        "cardinalities": [int(c) for c in card],
-    }
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -221,51 +264,89 @@ def b200_main(args):
     if world != args.gpus:
         assert world == 1 and args.gpus == 1, f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})"
     torch.cuda.set_device(local_rank)
-    lib = N.load()
+    N.load()
     if world > 1:
         from persia_b200 import dist_bench
 
-        return dist_bench.run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampler, cpu_arm)
-    return single_gpu(args, torch, lib)
+        return dist_bench.run(args, rank, local_rank, world, sys.modules[__name__])
+    return single_gpu(args, torch)
 
 
-def single_gpu(args, torch, lib):
+def peak_hbm():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+def fill_table(torch, SH, sh, card, pf, dev, dim, owner=None):
+    """Make the rows of ids [0, card[s]) of every slot resident (the reference's "warm table")."""
+    chunk = 1 << 21
+    buf = torch.empty((chunk, dim), dtype=torch.float32, device=dev)
+    for s in range(len(card)):
+        for lo in range(0, int(card[s]), chunk):
+            hi = min(int(card[s]), lo + chunk)
+            ids = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+            signs = SH.add_prefix(ids, [0, hi - lo], [pf[s]])
+            if owner is not None:
+                signs = signs[SH.shard_of(signs, owner[1]) == owner[0]].contiguous()
+            if signs.numel():
+                sh.lookup(signs, training=True, out=buf[: signs.numel()])
+    torch.cuda.synchronize()
+    del buf
+
+
+def kernel_bytes(stats, dim, state):
+    """Algorithmic bytes per launch from the batch's MEASURED multiplicities (with U as observed):
+    N id occurrences, U distinct (slot, sign) pairs of which `cold` occur once and `hot` more than 32 times."""
+    n, u = stats["occurrences"], stats["items"]
+    cold, warm, hot, rep = stats["cold"], stats["warm"], stats["hot"], stats["repeated_occurrences"]
+    row = 4 * (dim + state)
+    # `rep` = occurrences of the repeated signs; its split between warm (2..32 each) and hot (> 32 each) items is not
+    # recorded: take the smallest hot share consistent with the counts, which makes the k_reduce_items figure the
+    # LARGEST consistent one for its time — never flatter the hot kernel, never the dominant one by more than the
+    # bound allows (both are printed).
+    hot_occ = max(33 * hot, rep - 32 * warm) if hot else 0
+    hot_occ = min(hot_occ, max(0, rep - 2 * warm))
+    warm_occ = rep - hot_occ
+    return {
+        "k_dedup": n * (8 + 4) + u * 8,                          # ids in, set cell out, distinct list
+        "k_probe_items": u * 16,                                 # one index cell per distinct sign
+        "k_gather_items": u * 4 * dim + n * 2 * dim,             # each distinct row once + f16 outputs
+        "k_nan_scan": n * 2 * dim,
+        "k_reduce_items": (cold + warm) * (16 + 2 * row) + (cold + warm_occ) * 2 * dim,
+        "k_reduce_hot": hot * (16 + 2 * row) + hot_occ * 2 * dim,
+        "worst_case_backward": n * (2 * dim + 16 + 2 * row),
+        "whole_step": n * (20 + 2 * dim + 2 * dim) + u * (16 + 4 * dim + 16 + 2 * row),
+        "whole_step_worst_case": n * W.algorithmic_bytes_per_id(dim, state, "total"),
+    }
+
+
+def run_leg(args, torch, dim, B, rows, name, want_kernels, want_parity):
+    """One single-GPU leg: table of `rows` resident rows of `dim`, batches of B samples."""
     import ctypes as C
 
     from persia_b200 import native as N
     from persia_b200 import shard as SH
 
+    lib = N.load()
     dev = torch.device("cuda", torch.cuda.current_device())
-    dim = args.dim or 64
-    S, B, K, Wm = args.slots, args.batch, args.steps, max(args.warmup, 3)
-    rows = int(args.rows)
+    S, K, Wm = args.slots, args.steps, max(args.warmup, 3)
     card = W.scaled_cardinalities(rows, S)
-    if args.equal_card:
-        card = np.full(S, rows // S, np.int64)
-        card[0] += rows - int(card.sum())
     pf = W.index_prefixes(S)
     slot_off = [s * B for s in range(S + 1)]
     n_occ = S * B
-
     sh = SH.EmbeddingShard(dim, rows + 1024, dev)
     sh.set_optimizer(N.OPT_ADAGRAD, lr=0.01, initialization=0.01, eps=1e-10)
     sh.configure()
     ctx = SH.BatchContext(n_occ, n_occ, pf, device=dev)
-
-    # ---- make every row resident (the reference's "warm table"): admit all ids of every slot
     t_fill = time.time()
-    chunk = 1 << 21
-    buf = torch.empty((chunk, dim), dtype=torch.float32, device=dev)
-    for s in range(S):
-        for lo in range(0, int(card[s]), chunk):
-            hi = min(int(card[s]), lo + chunk)
-            ids = torch.arange(lo, hi, dtype=torch.int64, device=dev)
-            signs = SH.add_prefix(ids, [0, hi - lo], [pf[s]])
-            sh.lookup(signs, training=True, out=buf[: hi - lo])
-    torch.cuda.synchronize()
+    fill_table(torch, SH, sh, card, pf, dev, dim)
     resident = len(sh)
     t_fill = time.time() - t_fill
-    del buf
     assert resident == rows, (resident, rows)
 
     # ---- rotating buffer sets: ids, gradients, outputs (together > L2) ; pinned host ids for e2e
@@ -278,13 +359,12 @@ def single_gpu(args, torch, lib):
     grads_all = (torch.randn((n_sets, S, B, dim), generator=g, device=dev) * 1e-2).half()
     grads = [[grads_all[k, s] for s in range(S)] for k in range(n_sets)]
     outs = [torch.empty((S, B, dim), dtype=torch.float16, device=dev) for _ in range(n_sets)]
-    uniq = float(np.mean([np.unique(ids_host[k].reshape(S, B) + (np.arange(S, dtype=np.uint64) << np.uint64(56))[:, None]).size
-                          for k in range(min(4, n_sets))])) / n_occ
 
     def step(k):
         ctx.forward(sh, ids_dev[k], slot_off, B, training=True, out=outs[k])
         ctx.backward(sh, grads[k])
 
+    res = {"name": name, "dim": dim, "batch": B}
     stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
     with torch.cuda.stream(stream):
@@ -295,6 +375,7 @@ def single_gpu(args, torch, lib):
         step(0)
         launches_per_step = int(lib.pb_launch_count() - l0)
         stream.synchronize()
+        stats = ctx.batch_stats()
         graphs = None
         if use_graph:
             graphs = []
@@ -327,26 +408,32 @@ def single_gpu(args, torch, lib):
         t1 = time.time()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop(t0, t1)
+        reps = []
+        for _ in range(3):  # run-to-run spread of the same K steps
+            e0.record(stream)
+            for i in range(K):
+                run(i)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            reps.append(e0.elapsed_time(e1) / K)
 
-        # ---- per-kernel durations (CUDA events on the launching stream), separate instrumented pass
-        fam_names = ["probe_items", "dedup", "gather_pool", "nan_scan", "reduce_hot", "reduce_items", "other"]
-        n_prof = min(K, 50)
-
-        def profiled(mask):
-            lib.pb_profile_enable(mask)
-            for i in range(n_prof):
-                step(i % n_sets)
-            fam_ms = (C.c_double * 7)()
-            fam_cnt = (C.c_uint64 * 7)()
-            N.check(lib.pb_profile_read(fam_ms, fam_cnt, 7))
-            lib.pb_profile_enable(0)
-            return {fam_names[i]: {"us_per_step": 1e3 * fam_ms[i] / n_prof, "launches_per_step": fam_cnt[i] / n_prof}
-                    for i in range(7) if fam_cnt[i]}
-
-        # every launch bracketed: the host (two event records per launch) is slower than most of these kernels, so
-        # small kernels read high — a table for orientation; the roofline kernel is then timed alone
-        kern = profiled(0x7F)
-        kern_alone = profiled(1 << 5)
+        kern = None
+        if want_kernels:
+            # per-kernel durations: CUDA events around every launch of ONE family at a time on its launching stream
+            # (bracketing all launches at once makes the host the bottleneck and small kernels read high)
+            fam_names = ["k_probe_items", "k_dedup", "k_gather_items", "k_nan_scan", "k_reduce_hot", "k_reduce_items", "other"]
+            n_prof = min(K, 40)
+            kern = {}
+            for f in range(6):
+                lib.pb_profile_enable(1 << f)
+                for i in range(n_prof):
+                    step(i % n_sets)
+                fam_ms = (C.c_double * 7)()
+                fam_cnt = (C.c_uint64 * 7)()
+                N.check(lib.pb_profile_read(fam_ms, fam_cnt, 7))
+                lib.pb_profile_enable(0)
+                if fam_cnt[f]:
+                    kern[fam_names[f]] = {"us": 1e3 * fam_ms[f] / fam_cnt[f], "launches_per_step": fam_cnt[f] / n_prof}
 
         # ---- e2e: host ids (pinned) -> H2D -> forward -> backward -> D2H of the per-slot status, every step
         status_host = torch.empty(S, dtype=torch.int32).pin_memory()
@@ -386,54 +473,141 @@ def single_gpu(args, torch, lib):
         torch.cuda.synchronize()
         ms_e2e = e0.elapsed_time(e1)
 
-    ms_per_step = ms / K
-    value = B / (ms_per_step * 1e-3)
-    state = dim  # Adagrad, elementwise
-    bytes_per_id = W.algorithmic_bytes_per_id(dim, state, "total")
-    peaks = {}
+        parity = None
+        if want_parity:
+            parity = parity_single(torch, sh, run, outs, ids_host, grads_all, pf, S, B, dim, dev, stream)
+    wait_errors = sh.counters()["wait_errors"]
+    assert wait_errors == 0, "an in-kernel wait gave up: the run is void"
+    res.update(ms_per_step=ms / K, ms_per_step_reps=reps, ms_e2e=ms_e2e / K, launches_per_step=launches_per_step,
+               stats=stats, kernels=kern, clocks=clocks, resident=resident, t_fill=round(t_fill, 2), parity=parity,
+               n_sets=n_sets, graph=graphs is not None,
+               l2="inputs larger than L2: %.1f GB table + %d rotating id/grad/output sets (%.0f MB)" % (
+                   resident * 4.0 * 2 * dim / 1e9, n_sets, n_sets * 2 * n_occ * dim * 2 / 1e6))
+    del graphs, e2e_graphs
+    ctx.close()
+    sh.close()
+    del grads_all, grads, outs, ids_dev
+    torch.cuda.empty_cache()
+    return res
+
+
+def parity_single(torch, sh, run, outs, ids_host, grads_all, pf, S, B, dim, dev, stream):
+    """Replays two of the timed (graph-captured) steps from the table's current state and checks outputs and every
+    touched row against the oracle, bit for bit (Adagrad in the oracle's exact-rsqrt mode).  The oracle is the checker
+    here, never the thing measured."""
+    import oracle
+
+    sets = (0, 1)
+    signs = np.unique(np.concatenate([oracle.add_prefix(ids_host[k][i * B:(i + 1) * B], 8, pf[i]) for k in sets for i in range(S)]))
+    d_signs = torch.from_numpy(signs.view(np.int64)).to(dev)
+    ent, found = sh.get_entries(d_signs)
+    assert bool(found.all())
+    w = oracle.Worker([oracle.SlotCfg(dim, prefix=p) for p in pf], n_ps=1, capacity_per_ps=1 << 40)
+    w.configure()
+    w.set_optimizer(oracle.Optim(oracle.ADAGRAD, lr=0.01, init_acc=0.01, eps=1e-10))
+    w.set_embedding(signs, ent.cpu().numpy(), dim)
+    oracle.set_rsqrt_exact(True)
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    ku = kern_alone.get("reduce_items", {}).get("us_per_step")
-    upd_bytes = n_occ * W.algorithmic_bytes_per_id(dim, state, "backward")
-    achieved = upd_bytes / (ku * 1e-6) / 1e9 if ku else None
-    traffic = None
-    try:  # DRAM bytes per launch of the same kernel from the round's `ncu --set full` capture (profiles/)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("k_reduce_update")
-    except Exception:
-        pass
-    roofline = {
-        "bound": "hbm", "kernel": "k_reduce_update (A8+A9: gradient segment-reduce + Adagrad step + weight bound)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": upd_bytes,
-        "whole_step": {"algorithmic_bytes": n_occ * bytes_per_id,
-                       "achieved_gbs": n_occ * bytes_per_id / (ms_per_step * 1e-3) / 1e9,
-                       "frac": n_occ * bytes_per_id / (ms_per_step * 1e-3) / 1e9 / peak},
-        "kernels_us_per_step": kern, "kernel_timed_alone_us": ku,
+        row_off = np.arange(S * B + 1, dtype=np.uint32)
+        for k in sets:
+            run(k)
+            stream.synchronize()
+            want, octx = w.forward(ids_host[k], row_off, B, training=True)
+            got = outs[k].cpu().numpy()
+            for i in range(S):
+                if got[i].tobytes() != want[i].tobytes():
+                    raise AssertionError(f"parity: forward output of slot {i} differs from the oracle")
+            gk = grads_all[k].cpu().numpy()
+            w.backward(octx, [gk[i] for i in range(S)])
+        ent2 = sh.get_entries(d_signs)[0].cpu().numpy()
+        bad = sum(ent2[j].tobytes() != w.get_entry(int(s)).tobytes() for j, s in enumerate(signs))
+        if bad:
+            raise AssertionError(f"parity: {bad} of {signs.size} updated rows differ from the oracle")
+    finally:
+        oracle.set_rsqrt_exact(False)
+    return {"checked": True, "steps_replayed": len(sets), "rows_compared": int(signs.size),
+            "what": "graph-captured steps replayed from the live table; outputs and rows bit-identical to the oracle"}
+
+
+def roofline_from(leg, peak, peak_src, label):
+    dim, B = leg["dim"], leg["batch"]
+    st = leg["stats"]
+    by = kernel_bytes(st, dim, dim)
+    kern = leg["kernels"] or {}
+    table = {}
+    for k, v in kern.items():
+        if k in by:
+            gbs = by[k] / (v["us"] * 1e-6) / 1e9
+            table[k] = {"us": round(v["us"], 2), "algorithmic_bytes": int(by[k]), "achieved_gbs": round(gbs, 1),
+                        "frac": round(gbs / peak, 4)}
+    dom = "k_reduce_items"
+    ach = table.get(dom, {}).get("achieved_gbs")
+    us = kern.get(dom, {}).get("us")
+    worst = by["worst_case_backward"] / (us * 1e-6) / 1e9 if us else None
+    step_s = leg["ms_per_step"] * 1e-3
+    return {
+        "bound": "hbm", "kernel": "k_reduce_items (A8+A9 of the signs occurring <= 32 times: in-order gradient reduce + Adagrad "
+                                  "step + weight bound) on " + label,
+        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+        "frac_worst_case": (worst / peak) if worst else None,
+        "traffic": None,
+        "traffic_note": "not measured by this run: see profiles/ for the ncu --set full capture of this command "
+                        "(dram__bytes_read.sum + dram__bytes_write.sum of the same kernel) and its command line",
+        "peak_source": peak_src,
+        "bytes_model": "measured multiplicities of the batch: N occurrences, U distinct (slot, sign) pairs; "
+                       "k_reduce_items = (cold+warm items) x (16 + 8(D+S)) + their occurrences x 2D; frac_worst_case "
+                       "divides the U = N backward bytes N x (2D + 16 + 8(D+S)) by the same time",
+        "unique_fraction": st["items"] / max(1, st["occurrences"]), "batch_stats": st,
+        "kernels": table,
+        "whole_step": {"ms": leg["ms_per_step"], "samples_per_s": B / step_s,
+                       "algorithmic_bytes": int(by["whole_step"]), "achieved_gbs": by["whole_step"] / step_s / 1e9,
+                       "frac": by["whole_step"] / step_s / 1e9 / peak,
+                       "frac_worst_case": by["whole_step_worst_case"] / step_s / 1e9 / peak},
     }
+
+
+def single_gpu(args, torch):
+    peak, peak_src = peak_hbm()
+    rows = int(args.rows)
+    roof_leg = None
+    if not args.no_roofline_leg:
+        roof_leg = run_leg(args, torch, 64, 4096, rows, "roofline leg (configs[1])", True, not args.no_parity)
+    leg = run_leg(args, torch, args.dim, args.batch, rows, "metric leg", True, not args.no_parity)
+    B, K = args.batch, args.steps
+    S = args.slots
+    n_occ = S * B
+    value = B / (leg["ms_per_step"] * 1e-3)
+    metric_roof = roofline_from(leg, peak, peak_src, f"the metric leg: dim {args.dim}, batch {B}, {rows:.3g} rows")
+    if roof_leg:
+        roofline = roofline_from(roof_leg, peak, peak_src, "configs[1]: dim 64, batch 4096, 1e8 rows")
+        roofline["metric_leg"] = {k: metric_roof[k] for k in ("achieved", "frac", "frac_worst_case", "kernels", "whole_step",
+                                                              "unique_fraction", "batch_stats")}
+    else:
+        roofline = metric_roof
     cpu = None
     if not args.no_cpu_baseline:
-        c = cpu_arm(args, dim, args.cpu_seconds, card)
-        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        c = cpu_arm(args, args.cpu_seconds)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "spread")}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": Wm,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, dim, card, 1), unique_id_fraction=uniq, resident_rows=resident,
-                       table_fill_seconds=round(t_fill, 2),
-                       l2="inputs larger than L2: %.1f GB table + %d rotating id/grad/output sets (%.0f MB)" % (
-                           resident * 4.0 * (dim + state) / 1e9, n_sets, n_sets * 2 * n_occ * dim * 2 / 1e6),
-                       launch=("CUDA graph replay, one graph per buffer set" if graphs is not None else "kernel by kernel") +
-                              ("" if args.sync_grouping else "; grouping forked onto the context's side stream in pb_forward")),
-        "clocks": clocks,
-        "e2e": {"value": B / (ms_e2e / K * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8,
-                "d2h_bytes_per_step": S * 4, "ms_per_step": ms_e2e / K,
+        "config": workload_config(args),
+        "run": {"ms_per_step_repetitions": leg["ms_per_step_reps"], "resident_rows": leg["resident"],
+                "table_fill_seconds": leg["t_fill"], "l2": leg["l2"],
+                "launch": ("CUDA graph replay, one graph per buffer set" if leg["graph"] else "kernel by kernel") +
+                          "; pb_backward forks the hot-sign reduce onto the context's own stream",
+                "reduce_order": "reference order for every multiplicity (bit-exact vs the oracle)",
+                "roofline_leg": None if not roof_leg else {
+                    "workload": "configs[1]: 26 slots, 1e8 rows, dim 64, batch 4096, Adagrad", "ms_per_step": roof_leg["ms_per_step"],
+                    "samples_per_s": 4096 / (roof_leg["ms_per_step"] * 1e-3), "ms_per_step_repetitions": roof_leg["ms_per_step_reps"],
+                    "e2e_samples_per_s": 4096 / (roof_leg["ms_e2e"] * 1e-3), "parity": roof_leg["parity"]}},
+        "clocks": leg["clocks"],
+        "e2e": {"value": B / (leg["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8,
+                "d2h_bytes_per_step": S * 4, "ms_per_step": leg["ms_e2e"],
                 "path": "pinned host ids -> H2D -> pb_forward -> pb_backward -> D2H slot status, host sync every step"},
-        "gpu_launches": launches_per_step * K,
+        "gpu_launches": leg["launches_per_step"] * K,
+        "parity_checked": bool(leg["parity"] and leg["parity"]["checked"]), "parity": leg["parity"],
         "roofline": roofline,
         "cpu_baseline": cpu,
     }

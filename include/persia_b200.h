@@ -139,6 +139,11 @@ typedef struct {
 int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, pb_ctx** out);
 int pb_ctx_destroy(pb_ctx* c);
 int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg);
+/* The last training batch seen by the context, as the reference's batch_unique_indices_rate gauge reports it
+ * (embedding_worker_service/mod.rs:664-673): [0] distinct (slot, sign) pairs, of which [1] occur once, [2] 2..32 times,
+ * [3] more often; [4] occurrences held by the repeated ones; [5] id occurrences.  Synchronises `stream`. */
+int pb_ctx_batch_stats(pb_ctx* c, uint32_t h_out[6], void* stream);
+
 /* EmbeddingWorker::forward_batched_direct for summation slots
  * (embedding_worker_service/mod.rs:1076-1107 -> :874-942 -> PS :162-262 -> :486-629).
  * d_ids: flat raw ids, slot-major then sample-major; d_row_off[n_slots*batch+1] CSR offsets, or NULL
@@ -204,14 +209,23 @@ int pb_xchg_destroy(pb_xchg* x);
 /* h_out[0] != 0: a batch needed more than cap slots for one pair (its excess signs read as zeros and took no
  * gradient: re-run it with a larger cap); h_out[1] != 0: a wait for a peer gave up.  Synchronises `stream`. */
 int pb_xchg_status(pb_xchg* x, uint32_t h_out[2], void* stream);
+/* `phases`: the call enqueues these parts of the exchange (0 = PB_PHASE_ALL, the normal call).  One process per GPU
+ * always passes 0.  Splitting exists for hosts that drive several ranks of one GPU from one thread (tests: R virtual
+ * ranks sharing a device): enqueue SEND for every rank, then SERVE for every rank, then FINISH for every rank, with
+ * the same arguments each time — no rank then waits on a flag whose raising has not been enqueued yet. */
+#define PB_PHASE_SEND 1   /* requester: forward dedup + signs out; backward NaN rule + reduce + gradients out */
+#define PB_PHASE_SERVE 2  /* owner: forward lookups + rows out; backward optimizer steps */
+#define PB_PHASE_FINISH 4 /* requester, forward only: rows in -> output */
+#define PB_PHASE_ALL 7
 /* forward_batched_direct over R shards: arguments as pb_forward.  Not supported here yet: Adam, slots sharing a
  * feature group, raw slots. */
 int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
-                       const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream);
+                       const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream,
+                       int phases);
 /* update_gradient_batched over R shards: arguments as pb_backward.  The NaN rule is applied per slot on the requesting
  * rank, before anything is sent (mod.rs:731-746). */
 int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h_grads, int is_f16, const float* h_scale,
-                        int32_t* d_slot_status, void* stream);
+                        int32_t* d_slot_status, void* stream, int phases);
 
 /* Number of kernels the library has launched on behalf of the caller since load (bench bookkeeping). */
 uint64_t pb_launch_count(void);

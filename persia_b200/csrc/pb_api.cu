@@ -602,6 +602,21 @@ int pb_ctx_set_slots(pb_ctx* c, const pb_slots_cfg* cfg) {
   return PB_OK;
 }
 
+int pb_ctx_batch_stats(pb_ctx* c, uint32_t h_out[6], void* stream) {
+  if (!c || !h_out) return fail(PB_ERR_INVALID, "null argument");
+  DeviceGuard g(c->device);
+  uint32_t w[BC_PEER];
+  PB_CUDA(cudaMemcpyAsync(w, c->b.cnt, sizeof(w), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  h_out[0] = w[BC_ITEMS];
+  h_out[1] = w[BC_COLD];
+  h_out[2] = w[BC_WARM];
+  h_out[3] = w[BC_HOT];
+  h_out[4] = w[BC_SEG];
+  h_out[5] = c->n_occ;
+  return PB_OK;
+}
+
 int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
                const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream) {
   if (!t || !c || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
@@ -832,7 +847,9 @@ int pb_xchg_status(pb_xchg* x, uint32_t h_out[2], void* stream) {
 }
 
 int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids, uint32_t n_occ, const uint32_t* d_row_off,
-                       const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream) {
+                       const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream,
+                       int phases) {
+  if (phases == 0) phases = PB_PHASE_ALL;
   if (!t || !c || !x || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
   if (!c->has_slots) return fail(PB_ERR_STATE, "pb_ctx_set_slots not called");
   if (t->device != c->device || t->device != x->device) return fail(PB_ERR_INVALID, "table, context and exchange live on different devices");
@@ -856,22 +873,30 @@ int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids
   if ((rc = ensure_alloc(t))) return rc;
   SlotsDev sl;
   if ((rc = make_slots(c->slots, h_slot_occ_off, sl))) return rc;
-  if (c->set_dirty) {
-    launch_clear_items(c->b, st);
-    c->set_dirty = false;
+  if (phases & PB_PHASE_SEND) {
+    if (c->set_dirty) {
+      launch_clear_items(c->b, st);
+      c->set_dirty = false;
+    }
+    drop_pending(c);
+    if (training) {
+      if ((rc = maybe_evict(t, st))) return rc;
+    }
+    launch_begin_batch(t->d, training ? c->dev_tick : nullptr, c->b.cnt, st, training != 0);
+    c->b.n = n_occ;
+    launch_dedup(sl, c->b, d_ids, st);
+    launch_route_items(training != 0, sl, c->b, x->d, st);               // requester: signs -> owners' areas
+    launch_signal(x->d, XC_FLAG_SIGN, c->b.cnt + BC_PEER, st);
   }
-  drop_pending(c);
-  if (training) {
-    if ((rc = maybe_evict(t, st))) return rc;
+  if (phases & PB_PHASE_SERVE) {
+    launch_wait(x->d, XC_FLAG_SIGN, -1, st);
+    launch_owner_lookup(training != 0, t->d, t->hy, t->op, x->d, st);    // owner: rows -> requesters' areas
+    launch_signal(x->d, XC_FLAG_ROW, nullptr, st);
   }
-  launch_begin_batch(t->d, training ? c->dev_tick : nullptr, c->b.cnt, st, training != 0);
-  c->b.n = n_occ;
-  launch_dedup(sl, c->b, d_ids, st);
-  launch_route_items(training != 0, sl, c->b, x->d, st);                 // requester: signs -> owners' areas
-  launch_signal(x->d, XC_FLAG_SIGN, c->b.cnt + BC_PEER, st);
-  launch_wait(x->d, XC_FLAG_SIGN, -1, st);
-  launch_owner_lookup(training != 0, t->d, t->hy, t->op, x->d, st);      // owner: rows -> requesters' areas
-  launch_signal(x->d, XC_FLAG_ROW, nullptr, st);
+  if (!(phases & PB_PHASE_FINISH)) {
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+  }
   launch_wait(x->d, XC_FLAG_ROW, -1, st);
   launch_expand_items(t->d, sl, c->b, x->d, d_row_off, (uint32_t)n_out, batch, training != 0, d_out_f16, st);
   if (training) {
@@ -895,7 +920,8 @@ int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids
 }
 
 int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h_grads, int is_f16, const float* h_scale,
-                        int32_t* d_slot_status, void* stream) {
+                        int32_t* d_slot_status, void* stream, int phases) {
+  if (phases == 0) phases = PB_PHASE_ALL;
   if (!t || !c || !x || !h_grads) return fail(PB_ERR_INVALID, "null argument");
   if (!c->pending) return fail(PB_ERR_STATE, "no forward batch is pending in this context (backward_ref_id not found)");
   if (c->pending_table != t) return fail(PB_ERR_INVALID, "the pending batch was looked up in another table");
@@ -916,14 +942,14 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
     if (gr.do_scale[s] && !std::isfinite(inv)) return fail(PB_ERR_INVALID, "scale on gradient must be finite");
     gr.inv_scale[s] = inv;
   }
+  if (phases & PB_PHASE_SEND) {
   PB_CUDA(cudaEventRecord(c->ev_fork, st));
   PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
   if (c->set_dirty) {
     launch_clear_items(c->b, c->side);
     c->set_dirty = false;
   }
-  uint32_t elems = c->batch * t->d.dim;
-  launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);  // per slot, on the requester (mod.rs:731-746)
+  launch_nan_scan(gr, S, c->batch * t->d.dim, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);  // per slot, on the requester (mod.rs:731-746)
   PB_CUDA(cudaEventRecord(c->ev_nan, st));
   PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_nan, 0));
   ReduceArgs a;
@@ -942,6 +968,11 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
   PB_CUDA(cudaEventRecord(c->ev_join, c->side));
   PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   launch_signal(x->d, XC_FLAG_GRAD, nullptr, st);
+  }
+  if (!(phases & PB_PHASE_SERVE)) {
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+  }
   for (uint32_t src = 0; src < x->d.R; ++src) {  // owner: the R requests, one after another in rank order
     launch_wait(x->d, XC_FLAG_GRAD, (int)src, st);
     launch_owner_update(t->d, t->op, t->hy, x->d, src, st);

@@ -397,13 +397,25 @@ __global__ void __launch_bounds__(ITEMS_THREADS, 4) k_reduce_items(TableDev t, O
 }
 
 // ------------------------------------------------------------------------------------------------
-// hot items: bitmap order + cp.async.bulk / mbarrier ring
+// hot items: counting-sort order + cp.async.bulk / mbarrier rings, three roles per CTA
+//
+//   all threads   per window of HOT_WIN samples of the item's slot: one bit per occurrence in a shared bitmap
+//                 (atomicOr: order-free), word prefix sums, then the set bits written out in ascending order — a
+//                 counting sort of the occurrence list that costs HOT_WIN/32 words.
+//   loader        (warp 0) streams the gradient rows of 32 consecutive occurrences per stage into the f16 ring with
+//                 cp.async.bulk, completion in bytes on the stage's mbarrier.  Runs of adjacent samples (the rule for
+//                 the signs of a tiny slot) go as ONE copy: the copy engine is bound by operations, not bytes, here.
+//   converters    (warps 1..3) turn a landed stage into prepared f32 rows (clamp, 1/scale, sqrt factor — everything
+//                 the EW does to a gradient value before it is summed, mod.rs:751-778) in the f32 ring.  All of this
+//                 is order-independent, so it is done by 96 lanes in parallel, off the summation's critical path.
+//   chain         (warp 4) adds the prepared rows in order: per row one shared-memory load and one dependent FADD per
+//                 element — the floor for a strictly sequential f32 sum — then performs the optimizer step.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t HOT_BITS = 65536;  // samples covered by one bitmap window (a PersiaBatch holds <= 65535 samples)
-constexpr uint32_t HOT_WORDS = HOT_BITS / 32;
-constexpr uint32_t HOT_ROWS = 32;     // gradient rows per ring stage (one bitmap word)
-constexpr uint32_t HOT_THREADS = 64;
-constexpr uint32_t HOT_DENSE = 6;    // a bitmap word with at least this many rows is staged as one window copy
+constexpr uint32_t HOT_WIN = 8192;   // samples per bitmap window
+constexpr uint32_t HOT_WORDS = HOT_WIN / 32;
+constexpr uint32_t HOT_ROWS = 32;    // rows per ring stage
+constexpr uint32_t HOT_CONV_WARPS = 3;
+constexpr uint32_t HOT_THREADS = 32 * (2 + HOT_CONV_WARPS);
 constexpr uint32_t WAIT_SPINS = 1u << 22;  // bounded waits: a lost completion voids the batch (CTR_ERR) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -430,12 +442,13 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
-// one row: global -> shared, completion counted in bytes on the stage's mbarrier (SASS: UBLKCP)
+// rows: global -> shared, completion counted in bytes on the stage's mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void conv_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * HOT_CONV_WARPS) : "memory"); }
 
 // +-inf -> +-65504 (persia-common lib.rs:163-180), two halves per instruction; finite halves are inside already
 __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
@@ -443,86 +456,48 @@ __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
   return __hmin2(__hmax2(v, __hneg2(lim)), lim);
 }
 
-// EPL consecutive gradient elements of a staged (shared memory) or resident (global) row -> f32, clamped
-template <int EPL, bool F16>
-__device__ __forceinline__ void read_elems(float (&g)[EPL], const unsigned char* rowp, uint32_t e0) {
-  if constexpr (F16) {
-    const __half* p = reinterpret_cast<const __half*>(rowp) + e0;
-    if constexpr (EPL == 8) {
-      uint4 raw = *reinterpret_cast<const uint4*>(p);
-      const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 x = __half22float2(clamp_h2(h[q]));
-        g[2 * q] = x.x;
-        g[2 * q + 1] = x.y;
-      }
-    } else if constexpr (EPL == 4) {
-      uint2 raw = *reinterpret_cast<const uint2*>(p);
-      const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float2 x = __half22float2(clamp_h2(h[q]));
-        g[2 * q] = x.x;
-        g[2 * q + 1] = x.y;
-      }
-    } else if constexpr (EPL == 2) {
-      float2 x = __half22float2(clamp_h2(*reinterpret_cast<const __half2*>(p)));
-      g[0] = x.x;
-      g[1] = x.y;
-    } else {
-      g[0] = clamp_f16(__half2float(p[0]));
-    }
-  } else {
-    const float* p = reinterpret_cast<const float*>(rowp) + e0;
-    if constexpr (EPL % 4 == 0) {
-#pragma unroll
-      for (int q = 0; q < EPL / 4; ++q) {
-        float4 x = *reinterpret_cast<const float4*>(p + 4 * q);
-        g[4 * q] = x.x; g[4 * q + 1] = x.y; g[4 * q + 2] = x.z; g[4 * q + 3] = x.w;
-      }
-    } else if constexpr (EPL == 2) {
-      float2 x = *reinterpret_cast<const float2*>(p);
-      g[0] = x.x;
-      g[1] = x.y;
-    } else {
-      g[0] = p[0];
-    }
-  }
-}
-
-struct HotSmem {  // carved out of dynamic shared memory
-  unsigned char* ring;
-  uint32_t* bitmap;
-  float* vstage;
-  uint64_t* bars;  // [stages] full, [stages] empty
+struct HotRing {  // a ring of `n` stages and its two mbarrier arrays, with the running phase of one role
+  uint32_t n, it;
+  uint32_t full0, empty0;  // shared addresses of the first full / empty barrier
+  __device__ __forceinline__ uint32_t stage() const { return it % n; }
+  __device__ __forceinline__ uint32_t par() const { return (it / n) & 1u; }
+  __device__ __forceinline__ uint32_t full() const { return full0 + 8u * stage(); }
+  __device__ __forceinline__ uint32_t empty() const { return empty0 + 8u * stage(); }
 };
 
 template <int EPL, bool F16, bool SEND>
-__global__ void __launch_bounds__(HOT_THREADS, 6) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
-                                                           ReduceArgs a, uint32_t stages, uint32_t bulk, uint32_t ring_bytes) {
+__global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                              ReduceArgs a, uint32_t rs, uint32_t cs, uint32_t bulk, uint32_t hr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
-  __shared__ uint32_t s_item;
+  __shared__ uint32_t s_item, s_nwin;
+  __shared__ uint32_t bitmap[HOT_WORDS], wpre[HOT_WORDS];
+  __shared__ uint16_t sorted[HOT_WIN];
+  __shared__ __align__(8) uint64_t bars[4 * 8];  // f16 ring full/empty (<= 8 stages), f32 ring full/empty (<= 8)
+  __shared__ float s_fac[8][HOT_ROWS];           // per f32 stage: the sample's sqrt factor of every row
   const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
-  HotSmem sm;
-  sm.ring = smem_raw;
-  sm.bitmap = reinterpret_cast<uint32_t*>(smem_raw + ring_bytes);
-  sm.vstage = reinterpret_cast<float*>(sm.bitmap + HOT_WORDS);
-  sm.bars = reinterpret_cast<uint64_t*>(sm.vstage + ((t.dim + 1u) & ~1u));
+  const uint32_t ring16 = bulk ? rs * hr * rowbytes : 0u;  // hr = rows per stage (32 unless the rows are very long)
+  unsigned char* ring = smem_raw;                                       // [rs][32][rowbytes]   landed gradient rows
+  float* cring = reinterpret_cast<float*>(smem_raw + ring16);          // [cs][32][dim]        prepared f32 rows
+  float* vstage = cring + (size_t)cs * hr * t.dim;               // [dim]                Adagrad-vectorwise dot
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_loader = warp == 0, is_chain = warp == 1 + HOT_CONV_WARPS, is_conv = !is_loader && !is_chain;
+  const uint32_t ctid = tid - 32u;  // converter thread number
   if (tid == 0) {
-    for (uint32_t s = 0; s < 2 * stages; ++s) mbar_init(smem_u32(sm.bars + s), 1u);
+    for (uint32_t s = 0; s < 32; ++s) mbar_init(smem_u32(bars + s), 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   build_dead_mask(dead, gr, a, sl.n_slots);  // ends with __syncthreads
+  HotRing r16, r32;  // every role keeps its own copy and advances it once per chunk: the chunk sequence is the same for all
+  r16.n = rs; r16.it = 0; r16.full0 = smem_u32(bars); r16.empty0 = smem_u32(bars + 8);
+  r32.n = cs; r32.it = 0; r32.full0 = smem_u32(bars + 16); r32.empty0 = smem_u32(bars + 24);
   const uint32_t n_hot = a.b.cnt[BC_HOT];
   uint32_t* next = a.b.cnt + BC_NEXT + PB_MAX_SLOTS + a.round;
   const uint32_t n_pass = (t.dim + 32u * EPL - 1u) / (32u * EPL);
-  uint32_t it = 0;  // ring stages used so far: both warps count the same non-empty bitmap words
+  const uint32_t half_dim = t.dim / 2;  // converters work on element pairs when the dim is even
   bool failed = false;
   for (;;) {
-    __syncthreads();  // s_item and the bitmap are free again
+    __syncthreads();  // s_item, bitmap and sorted are free again
     if (tid == 0) s_item = atomicAdd(next, 1u);
     __syncthreads();
     const uint32_t h = s_item;
@@ -544,122 +519,182 @@ __global__ void __launch_bounds__(HOT_THREADS, 6) k_reduce_hot(TableDev t, Optim
     const uint32_t lo = sl.occ_off[slot], hi = sl.occ_off[slot + 1];
     const ItemSrc src = item_src(sl, gr, a, slot);
     const bool contiguous = !a.occ_outrow;  // one id per sample: the gradient row of occurrence lo + b is row b
+    const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
     float* prow = SEND ? send_grad_ptr(a.x, row, t.dim) : t.rows + (size_t)row * t.stride;
     StepCtx sc;
     sc.vw_state = sc.r1 = sc.r2 = 0.0f;
     if (!SEND) sc = step_ctx(prow, t, op, gr, slot);
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const uint32_t e0 = (pass * 32u + lane) * EPL;
-      const bool own = e0 < t.dim;  // lanes past the row's end idle
+      const bool own = e0 < t.dim;  // chain lanes past the row's end idle
       float acc[EPL];
 #pragma unroll
       for (int q = 0; q < EPL; ++q) acc[q] = 0.0f;
-      for (uint32_t wbase = lo; wbase < hi; wbase += HOT_BITS) {
-        const uint32_t wend = min(hi, wbase + HOT_BITS);
-        const uint32_t n_words = (wend - wbase + 31u) / 32u;
-        for (uint32_t w = tid; w < n_words; w += HOT_THREADS) sm.bitmap[w] = 0u;
+      for (uint32_t wbase = lo; wbase < hi; wbase += HOT_WIN) {
+        const uint32_t wend = min(hi, wbase + HOT_WIN);
+        // ---- counting sort of the item's occurrences inside this window
+        for (uint32_t w = tid; w < HOT_WORDS; w += HOT_THREADS) bitmap[w] = 0u;
         __syncthreads();
-        for (uint32_t k = tid; k < cnt; k += HOT_THREADS) {  // counting sort: one bit per occurrence
+        for (uint32_t k = tid; k < cnt; k += HOT_THREADS) {
           const uint32_t p = a.b.seg_occ[base + k];
-          if (p >= wbase && p < wend) atomicOr(&sm.bitmap[(p - wbase) >> 5], 1u << ((p - wbase) & 31u));
+          if (p >= wbase && p < wend) atomicOr(&bitmap[(p - wbase) >> 5], 1u << ((p - wbase) & 31u));
         }
         __syncthreads();
-        if (warp == 0) {
-          // ---- producer: one stage per non-empty word.  A dense word (the rule, for the signs of a tiny slot) is
-          // staged as ONE bulk copy of its whole 32-row window — gradient rows of consecutive samples are adjacent —
-          // a sparse one as one bulk copy per set bit: the copy engine is bound by operations, not bytes, at this size
+        if (warp == 0) {  // exclusive prefix of the word popcounts: HOT_WORDS / 32 words per lane
+          uint32_t c[HOT_WORDS / 32], sum = 0;
+#pragma unroll
+          for (uint32_t j = 0; j < HOT_WORDS / 32; ++j) {
+            c[j] = sum;
+            sum += __popc(bitmap[lane * (HOT_WORDS / 32) + j]);
+          }
+          uint32_t inc = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+          }
+#pragma unroll
+          for (uint32_t j = 0; j < HOT_WORDS / 32; ++j) wpre[lane * (HOT_WORDS / 32) + j] = inc - sum + c[j];
+          if (lane == 31) s_nwin = inc;
+        }
+        __syncthreads();
+        for (uint32_t w = tid; w < HOT_WORDS; w += HOT_THREADS) {
+          uint32_t m = bitmap[w], at = wpre[w];
+          while (m) {
+            sorted[at++] = (uint16_t)(w * 32u + __ffs(m) - 1u);
+            m &= m - 1u;
+          }
+        }
+        __syncthreads();
+        const uint32_t nwin = s_nwin;
+        const uint32_t n_chunks = (nwin + hr - 1u) / hr;
+        // ---- the pipeline over chunks of 32 consecutive occurrences
+        if (is_loader) {
           if (bulk) {
-            for (uint32_t w = 0; w < n_words; ++w) {
-              const uint32_t m = sm.bitmap[w];
-              if (!m) continue;
-              const uint32_t p = __popc(m), stage = it % stages, par = (it / stages) & 1u;
-              if (!failed && !mbar_wait(smem_u32(sm.bars + stages + stage), par ^ 1u)) failed = true;
-              const uint32_t full = smem_u32(sm.bars + stage);
-              const bool dense = contiguous && p >= HOT_DENSE;
-              if (dense) {
-                if (lane == 0) {
-                  const uint32_t first = (wbase - lo) + w * 32u, rows_here = min(32u, (wend - wbase) - w * 32u);
-                  mbar_expect_tx(full, rows_here * rowbytes);
-                  bulk_g2s(smem_u32(sm.ring + (size_t)stage * HOT_ROWS * rowbytes),
-                           reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)first * rowbytes, rows_here * rowbytes, full);
-                }
-              } else {
-                if (lane == 0) mbar_expect_tx(full, p * rowbytes);
-                __syncwarp();
-                if (lane < p) {
-                  const uint32_t occ = wbase + w * 32u + __fns(m, 0u, (int)lane + 1);
-                  const uint32_t orow = occ_out_row(a, occ);
-                  const unsigned char* g = reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow - src.slot_row0) * rowbytes;
-                  bulk_g2s(smem_u32(sm.ring + ((size_t)stage * HOT_ROWS + lane) * rowbytes), g, rowbytes, full);
-                }
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+              const uint32_t nv = min(hr, nwin - c * hr);
+              if (!failed && !mbar_wait(r16.empty(), r16.par() ^ 1u)) failed = true;
+              const bool valid = lane < nv;
+              const uint32_t occ = wbase + (valid ? sorted[c * hr + lane] : 0u);
+              const uint32_t orow = valid ? occ_out_row(a, occ) : 0u;
+              const uint32_t prev = __shfl_up_sync(0xffffffffu, orow, 1);
+              const bool head = valid && (lane == 0 || !contiguous || orow != prev + 1u);
+              const uint32_t hm = __ballot_sync(0xffffffffu, head);
+              if (lane == 0) mbar_expect_tx(r16.full(), nv * rowbytes);
+              __syncwarp();
+              if (head) {
+                const uint32_t later = (lane == 31) ? 0u : (hm >> (lane + 1));
+                const uint32_t len = later ? (uint32_t)__ffs(later) : nv - lane;  // rows up to the next run's head
+                bulk_g2s(smem_u32(ring + ((size_t)r16.stage() * hr + lane) * rowbytes),
+                         gbytes + (size_t)(orow - src.slot_row0) * rowbytes, len * rowbytes, r16.full());
               }
-              ++it;
+              ++r16.it;
             }
+          } else {
+            r16.it += n_chunks;
+          }
+        } else if (is_conv) {
+          for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t nv = min(hr, nwin - c * hr);
+            if (!failed && !mbar_wait(r32.empty(), r32.par() ^ 1u)) failed = true;
+            if (bulk && !failed && !mbar_wait(r16.full(), r16.par())) failed = true;
+            float* fac = s_fac[r32.stage()];
+            if (src.do_sqrt) {  // the sample's 1/sqrt(n ids), one lane per row
+              if (ctid < nv) fac[ctid] = grad_prep(src, a, occ_out_row(a, wbase + sorted[c * hr + ctid])).sqrt_f;
+              conv_barrier();
+            }
+            float* dst = cring + (size_t)r32.stage() * hr * t.dim;
+            const unsigned char* srows = ring + (size_t)r16.stage() * hr * rowbytes;
+            if (t.dim % 2 == 0) {
+              const uint32_t total = nv * half_dim;
+              for (uint32_t i = ctid; i < total; i += 32 * HOT_CONV_WARPS) {
+                const uint32_t k = i / half_dim, col = i - k * half_dim;
+                const unsigned char* rp = bulk ? srows + (size_t)k * rowbytes
+                                               : gbytes + (size_t)(occ_out_row(a, wbase + sorted[c * hr + k]) - src.slot_row0) * rowbytes;
+                float2 v;
+                if (F16) v = __half22float2(clamp_h2(reinterpret_cast<const __half2*>(rp)[col]));
+                else v = reinterpret_cast<const float2*>(rp)[col];
+                if (src.do_scale) {
+                  v.x = __fmul_rn(v.x, src.inv_scale);
+                  v.y = __fmul_rn(v.y, src.inv_scale);
+                }
+                if (src.do_sqrt) {
+                  v.x = __fmul_rn(v.x, fac[k]);
+                  v.y = __fmul_rn(v.y, fac[k]);
+                }
+                reinterpret_cast<float2*>(dst + (size_t)k * t.dim)[col] = v;
+              }
+            } else {
+              const uint32_t total = nv * t.dim;
+              for (uint32_t i = ctid; i < total; i += 32 * HOT_CONV_WARPS) {
+                const uint32_t k = i / t.dim, col = i - k * t.dim;
+                const unsigned char* rp = bulk ? srows + (size_t)k * rowbytes
+                                               : gbytes + (size_t)(occ_out_row(a, wbase + sorted[c * hr + k]) - src.slot_row0) * rowbytes;
+                float v = F16 ? clamp_f16(__half2float(reinterpret_cast<const __half*>(rp)[col])) : reinterpret_cast<const float*>(rp)[col];
+                if (src.do_scale) v = __fmul_rn(v, src.inv_scale);
+                if (src.do_sqrt) v = __fmul_rn(v, fac[k]);
+                dst[(size_t)k * t.dim + col] = v;
+              }
+            }
+            conv_barrier();  // every converter is done with both stages
+            if (ctid == 0) {
+              mbar_arrive(r32.full());             // the chain may add this stage
+              if (bulk) mbar_arrive(r16.empty());  // the loader may refill the f16 stage
+            }
+            ++r16.it;
+            ++r32.it;
           }
         } else {
-          // ---- consumer: the rows of a word in ascending order, a dependent add per row
-          for (uint32_t w = 0; w < n_words; ++w) {
-            const uint32_t m = sm.bitmap[w];
-            if (!m) continue;
-            const uint32_t p = __popc(m), stage = it % stages, par = (it / stages) & 1u;
-            const bool dense = bulk && contiguous && p >= HOT_DENSE;
-            if (bulk && !failed && !mbar_wait(smem_u32(sm.bars + stage), par)) failed = true;
-            const unsigned char* rows = sm.ring + (size_t)stage * HOT_ROWS * rowbytes;
-            uint32_t mm = m, idx = 0;
-            while (mm) {  // four rows per round: loads first, then the dependent adds
-              uint32_t bit[4];
-              int nb = 0;
+          // ---- chain: the prepared rows in ascending order, one dependent add per row and element
+          for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t nv = min(hr, nwin - c * hr);
+            if (!failed && !mbar_wait(r32.full(), r32.par())) failed = true;
+            const float* rows = cring + (size_t)r32.stage() * hr * t.dim + e0;
+            if (own) {
+              uint32_t k = 0;
+              for (; k + 8 <= nv; k += 8) {
+                float g[8][EPL];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                bit[u] = 0;
-                if (mm) {
-                  bit[u] = __ffs(mm) - 1;
-                  mm &= mm - 1;
-                  nb = u + 1;
-                }
+                for (int u = 0; u < 8; ++u) RowElems<-1, EPL>::template ld<EPL>(rows + (size_t)(k + u) * t.dim, g[u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                  for (int q = 0; q < EPL; ++q) acc[q] = __fadd_rn(acc[q], g[u][q]);
               }
-              float g[4][EPL];
-              uint32_t orow[4];
+              for (; k < nv; ++k) {
+                float g[EPL];
+                RowElems<-1, EPL>::template ld<EPL>(rows + (size_t)k * t.dim, g);
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (u < nb) {
-                  orow[u] = occ_out_row(a, wbase + w * 32u + bit[u]);
-                  const unsigned char* rp = bulk ? rows + (size_t)(dense ? bit[u] : idx + u) * rowbytes
-                                                 : reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)(orow[u] - src.slot_row0) * rowbytes;
-                  if (own) read_elems<EPL, F16>(g[u], rp, e0);
-                }
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (u < nb && own) add_prepared<EPL>(acc, g[u], grad_prep(src, a, orow[u]), src.plain);
-              idx += nb;
+                for (int q = 0; q < EPL; ++q) acc[q] = __fadd_rn(acc[q], g[q]);
+              }
             }
-            if (bulk) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(sm.bars + stages + stage));  // the stage may be refilled
-            }
-            ++it;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(r32.empty());  // the stage may be refilled
+            ++r16.it;
+            ++r32.it;
           }
         }
-        __syncthreads();  // the bitmap is rebuilt for the next window / pass / item
+        // roles that skipped the loops above keep their ring counters in step
+        if (is_loader) r32.it += n_chunks;
       }
-      // ---- the optimizer step on this pass's elements (consumer warp)
+      // ---- the optimizer step on this pass's elements (chain warp)
       if (SEND) {
-        if (warp == 1 && own) RowElems<-1, EPL>::template st<EPL>(prow + e0, acc);
-      } else if (warp == 1 && own) {
+        if (is_chain && own) RowElems<-1, EPL>::template st<EPL>(prow + e0, acc);
+      } else if (is_chain && own) {
         RowElems<-1, EPL> rc;
         rc.load(prow, e0, t, op);
         if (op.kind == PB_OPT_ADAGRAD_VW) {
 #pragma unroll
-          for (int q = 0; q < EPL; ++q) sm.vstage[e0 + q] = acc[q];
+          for (int q = 0; q < EPL; ++q) vstage[e0 + q] = acc[q];
         }
         rc.step(e0, acc, t, op, hy, sc);
         rc.store(prow, e0, t, op);
       }
     }
-    if (!SEND && op.kind == PB_OPT_ADAGRAD_VW && warp == 1) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
+    if (!SEND && op.kind == PB_OPT_ADAGRAD_VW && is_chain) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
       __syncwarp();
       if (lane == 0) {
-        float gs = __fdiv_rn(vw_dot(sm.vstage, t.dim), (float)t.dim);
+        float gs = __fdiv_rn(vw_dot(vstage, t.dim), (float)t.dim);
         prow[t.dim] = __fadd_rn(__fmul_rn(sc.vw_state, op.mom), gs);
       }
     }
@@ -692,12 +727,14 @@ template <int EPL, bool F16, bool SEND>
 static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
                        const ReduceArgs& a, uint32_t bulk, cudaStream_t st) {
   const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
-  uint32_t stages = 8;
-  while (stages > 2 && (size_t)stages * HOT_ROWS * rowbytes > 64u * 1024u) stages >>= 1;
-  if (bulk && (size_t)stages * HOT_ROWS * rowbytes > 160u * 1024u) bulk = 0;  // rows too long for a ring: plain loads
-  if (!bulk) stages = 1;
-  const size_t ring = bulk ? (size_t)stages * HOT_ROWS * rowbytes : 0;
-  const size_t smem = ring + HOT_WORDS * 4u + (((size_t)t.dim + 1u) & ~(size_t)1u) * 4u + 2u * stages * 8u;
+  uint32_t hr = HOT_ROWS;  // rows per stage: fewer when a row is very long
+  while (hr > 1 && (size_t)hr * t.dim * 4u > 16u * 1024u) hr >>= 1;
+  const size_t stage16 = (size_t)hr * rowbytes, stage32 = (size_t)hr * t.dim * 4u;
+  uint32_t rs = 8, cs = 4;
+  while (rs > 2 && rs * stage16 > 32u * 1024u) rs >>= 1;
+  while (cs > 2 && cs * stage32 > 32u * 1024u) cs >>= 1;
+  if (!bulk) rs = 1;
+  const size_t smem = (bulk ? rs * stage16 : 0) + cs * stage32 + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
   auto kern = k_reduce_hot<EPL, F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
@@ -706,13 +743,13 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured[dev] = smem;
   }
-  uint32_t per_sm = (uint32_t)(200u * 1024u / (smem + 1024u));
-  if (per_sm > 8) per_sm = 8;
+  uint32_t per_sm = (uint32_t)(200u * 1024u / (smem + 24u * 1024u));  // + the kernel's static shared memory
+  if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   const uint32_t cap_blocks = cdiv(a.b.n, PB_WARM_MAX + 1);  // at most this many hot items exist
   uint32_t grid = 148u * per_sm;
   if (grid > cap_blocks) grid = cap_blocks ? cap_blocks : 1;
-  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, stages, bulk, (uint32_t)ring);
+  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, rs, cs, bulk, hr);
 }
 
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,

@@ -12,6 +12,7 @@ SO_PATH = os.environ.get("PERSIA_B200_LIB") or os.path.join(_HERE, "libpersia_b2
 PB_MAX_SLOTS = 128
 OPT_SGD, OPT_ADAGRAD, OPT_ADAGRAD_VW, OPT_ADAM = 0, 1, 2, 3
 
+PHASE_SEND, PHASE_SERVE, PHASE_FINISH, PHASE_ALL = 1, 2, 4, 7
 PB_OK, PB_ERR_INVALID, PB_ERR_CUDA, PB_ERR_STATE, PB_ERR_CAPACITY, PB_ERR_BATCH = 0, -1, -2, -3, -4, -5
 
 
@@ -69,6 +70,7 @@ SYMBOLS = {
     "pb_ctx_create": (_i32, [_i32, _u32, _u32, C.POINTER(_vp)]),
     "pb_ctx_destroy": (_i32, [_vp]),
     "pb_ctx_set_slots": (_i32, [_vp, C.POINTER(SlotsCfg)]),
+    "pb_ctx_batch_stats": (_i32, [_vp, C.POINTER(_u32 * 6), _vp]),
     "pb_forward": (_i32, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp]),
     "pb_backward": (_i32, [_vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp]),
     "pb_forward_raw": (_i32, [_vp, _vp, _vp, _u32, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -77,8 +79,8 @@ SYMBOLS = {
     "pb_xchg_create": (_i32, [_i32, _u32, _u32, _u32, _u32, _i32, C.POINTER(_u64), C.POINTER(_vp)]),
     "pb_xchg_destroy": (_i32, [_vp]),
     "pb_xchg_status": (_i32, [_vp, C.POINTER(_u32 * 2), _vp]),
-    "pb_forward_sharded": (_i32, [_vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp]),
-    "pb_backward_sharded": (_i32, [_vp, _vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp]),
+    "pb_forward_sharded": (_i32, [_vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(_u32), _u32, _i32, _vp, _vp, _i32]),
+    "pb_backward_sharded": (_i32, [_vp, _vp, _vp, C.POINTER(_vp), _i32, C.POINTER(C.c_float), _vp, _vp, _i32]),
     "pb_launch_count": (_u64, []),
     "pb_profile_enable": (_i32, [_i32]),
     "pb_profile_read": (_i32, [C.POINTER(C.c_double), C.POINTER(_u64), _i32]),

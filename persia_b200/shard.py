@@ -155,6 +155,13 @@ class BatchContext:
             cfg.sqrt_scaling[i] = int(bool(sqrt_scaling[i])) if sqrt_scaling is not None else 0
         N.check(self.lib.pb_ctx_set_slots(self.h, C.byref(cfg)))
 
+    def batch_stats(self):
+        """Dedup statistics of the last training batch (host sync): distinct items and their multiplicity classes."""
+        out = (C.c_uint32 * 6)()
+        N.check(self.lib.pb_ctx_batch_stats(self.h, C.byref(out), _stream(self.device)))
+        return {"items": out[0], "cold": out[1], "warm": out[2], "hot": out[3], "repeated_occurrences": out[4],
+                "occurrences": out[5]}
+
     def forward(self, shard, ids, slot_occ_off, batch, row_off=None, training=True, out=None):
         """ids: flat device int64-bit ids (slot-major); slot_occ_off: host list, n_slots+1;
         row_off: device int32 CSR offsets [n_slots*batch+1] or None (one id per sample per slot).

@@ -16,8 +16,8 @@ Two ways to build the ranks of a box:
   * `ShardedEmbeddingWorker.distributed(...)`: one process per GPU (torchrun), areas in symmetric memory.
   * `ShardedEmbeddingWorker.local_group(R, ...)`: R virtual ranks on ONE GPU in one process, each with its own table,
     context and stream, areas in plain device memory.  Same kernels, same protocol; lets a single-GPU box run the
-    R > 1 parity tests.  Needs CUDA_DEVICE_MAX_CONNECTIONS >= 2R so that no two ranks' streams share a hardware queue
-    (a rank spinning on a flag must not sit in front of the kernel that will raise it).
+    R > 1 parity tests.  One host thread drives them phase by phase (group_forward / group_backward: all ranks send,
+    then all serve, then all finish), so a rank never spins on a flag whose raising has not been enqueued yet.
 """
 import ctypes as C
 import os
@@ -75,9 +75,6 @@ class ShardedEmbeddingWorker:
     def local_group(cls, world, n_slots, dim, prefixes, capacity, cap, optimizer, device=0, **kw):
         """R virtual ranks on one GPU (tests; also a way to exercise the protocol without a multi-GPU box)."""
         dev = torch.device("cuda", device)
-        need = 2 * world
-        have = int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8"))
-        assert have >= min(need, 32), f"set CUDA_DEVICE_MAX_CONNECTIONS >= {min(need, 32)} before CUDA starts (is {have})"
         nbytes = cls.area_bytes(world, cap, dim, kw.get("rows_f32", False))
         areas = [torch.zeros(nbytes + 256, dtype=torch.uint8, device=dev) for _ in range(world)]
         bases = [(a.data_ptr() + 255) // 256 * 256 for a in areas]
@@ -134,9 +131,10 @@ class ShardedEmbeddingWorker:
         s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
         return C.c_void_p(s.cuda_stream)
 
-    def forward(self, ids, batch, training=True, row_off=None, slot_occ_off=None, out=None):
+    def forward(self, ids, batch, training=True, row_off=None, slot_occ_off=None, out=None, phases=0):
         """ids: device int64-bit ids, slot-major; one id per sample per slot unless row_off (device int32 CSR offsets,
-        [n_slots*batch+1]) and slot_occ_off (host list) are given.  Returns f16 [n_slots, batch, dim]."""
+        [n_slots*batch+1]) and slot_occ_off (host list) are given.  Returns f16 [n_slots, batch, dim].
+        phases: see PB_PHASE_* in persia_b200.h (0 = the whole call; virtual ranks are driven phase by phase)."""
         ids = SH._as_i64_bits(ids)
         if slot_occ_off is None:
             slot_occ_off = [s * batch for s in range(self.S + 1)]
@@ -144,10 +142,10 @@ class ShardedEmbeddingWorker:
             out = torch.empty((self.S, batch, self.dim), dtype=torch.float16, device=self.device)
         off = (C.c_uint32 * (self.S + 1))(*[int(v) for v in slot_occ_off])
         N.check(self.lib.pb_forward_sharded(self.shard.h, self.ctx.h, self.h, SH._ptr(ids), ids.numel(), SH._ptr(row_off), off,
-                                            int(batch), int(training), SH._ptr(out), self._st()))
+                                            int(batch), int(training), SH._ptr(out), self._st(), int(phases)))
         return out
 
-    def backward(self, grads, scales=None, want_status=False):
+    def backward(self, grads, scales=None, want_status=False, phases=0, status=None):
         """grads: f16/f32 tensor [n_slots, batch, dim] or a list of per-slot tensors (None = skipped slot)."""
         if torch.is_tensor(grads):
             grads = [grads[i] for i in range(self.S)]
@@ -163,10 +161,31 @@ class ShardedEmbeddingWorker:
             is_f16 = f16
             ptrs[i] = g.data_ptr()
         sc = (C.c_float * self.S)(*[float(v) for v in scales]) if scales is not None else None
-        status = torch.empty(self.S, dtype=torch.int32, device=self.device) if want_status else None
+        if status is None and want_status:
+            status = torch.empty(self.S, dtype=torch.int32, device=self.device)
         N.check(self.lib.pb_backward_sharded(self.shard.h, self.ctx.h, self.h, ptrs, int(bool(is_f16)), sc, SH._ptr(status),
-                                             self._st()))
+                                             self._st(), int(phases)))
         return status
+
+    @staticmethod
+    def group_forward(workers, ids, batch, training=True, row_offs=None, slot_occ_offs=None, outs=None):
+        """Virtual ranks of one GPU, driven by one host thread: every phase is enqueued for all ranks before the next."""
+        R = len(workers)
+        outs = outs if outs is not None else [None] * R
+        for ph in (N.PHASE_SEND, N.PHASE_SERVE, N.PHASE_FINISH):
+            for r, w in enumerate(workers):
+                outs[r] = w.forward(ids[r], batch, training, row_offs[r] if row_offs else None,
+                                    slot_occ_offs[r] if slot_occ_offs else None, outs[r], phases=ph)
+        return outs
+
+    @staticmethod
+    def group_backward(workers, grads, scales=None, want_status=False):
+        R = len(workers)
+        sts = [torch.empty(w.S, dtype=torch.int32, device=w.device) if want_status else None for w in workers]
+        for ph in (N.PHASE_SEND, N.PHASE_SERVE):
+            for r, w in enumerate(workers):
+                w.backward(grads[r], scales, want_status, phases=ph, status=sts[r])
+        return sts
 
     def status(self):
         """(overflowed, wait_gave_up) — host sync."""

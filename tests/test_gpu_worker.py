@@ -2,7 +2,7 @@
 embedding worker with R parameter servers.
 
 R virtual ranks share cuda:0 (own table, context, stream and receive area each; the kernels and the flag protocol are
-the ones a multi-GPU box runs, "peer" stores just land in the same GPU), so the R > 1 parity runs on every box,
+the ones a multi-GPU box runs, "peer" stores just land in the same GPU; one host thread enqueues them phase by phase), so the R > 1 parity runs on every box,
 including the driver's 1-GPU lease.  With >= 2 GPUs the same comparison also runs with one process per GPU over
 symmetric memory (torch.multiprocessing spawn).
 
@@ -85,6 +85,8 @@ def _check_rows(torch, oracle, ws, w, signs, R):
 @pytest.mark.parametrize("R,dim,kind,f32", [(2, 64, 0, False), (2, 128, 1, False), (4, 128, 1, False), (8, 128, 1, False),
                                             (3, 16, 2, True), (2, 12, 0, False), (1, 64, 1, False)])
 def test_virtual_ranks_match_oracle(torch_cuda, oracle, R, dim, kind, f32):
+    from persia_b200.worker import ShardedEmbeddingWorker as W
+
     torch = torch_cuda
     oracle.set_rsqrt_exact(True)
     try:
@@ -97,8 +99,7 @@ def test_virtual_ranks_match_oracle(torch_cuda, oracle, R, dim, kind, f32):
             ids = [make_batch(rng, S, B, card)[0] for _ in range(R)]
             d_ids = [to_dev_ids(ids[r], DEV) for r in range(R)]
             torch.cuda.synchronize()
-            for r in range(R):
-                ws[r].forward(d_ids[r], B, training=True, out=outs[r])
+            W.group_forward(ws, d_ids, B, training=True, outs=outs)
             torch.cuda.synchronize()
             octx = []
             for r in range(R):
@@ -117,7 +118,7 @@ def test_virtual_ranks_match_oracle(torch_cuda, oracle, R, dim, kind, f32):
                 dg[R - 1][0] = None                          # add_skipped_gradient on the last rank
                 skip[R - 1] = [1] + [0] * (S - 1)
             torch.cuda.synchronize()
-            sts = [ws[r].backward(dg[r], want_status=True) for r in range(R)]
+            sts = W.group_backward(ws, dg, want_status=True)
             torch.cuda.synchronize()
             for r in range(R):
                 ost = w.backward(octx[r], [g[r, i] for i in range(S)], skip=skip[r])
@@ -130,6 +131,8 @@ def test_virtual_ranks_match_oracle(torch_cuda, oracle, R, dim, kind, f32):
 def test_virtual_ranks_ragged_sqrt_scale(torch_cuda, oracle):
     """Ragged LIL (several ids per sample, empty samples), sqrt scaling and a loss scale: f32 rows travel, pooling and
     the gradient's sample factors are applied on the requester."""
+    from persia_b200.worker import ShardedEmbeddingWorker as W
+
     torch = torch_cuda
     rng = np.random.default_rng(7)
     R, S, B, dim, card = 3, 4, 300, 32, [5, 300, 40000, 17]
@@ -143,8 +146,8 @@ def test_virtual_ranks_ragged_sqrt_scale(torch_cuda, oracle):
         dev_in = [(to_dev_ids(b[0], DEV), to_dev_i32(b[1], DEV)) for b in batches]
         pre = [torch.empty((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
         torch.cuda.synchronize()
-        for r in range(R):
-            outs.append(ws[r].forward(dev_in[r][0], B, training=True, row_off=dev_in[r][1], slot_occ_off=batches[r][2], out=pre[r]))
+        outs = W.group_forward(ws, [d[0] for d in dev_in], B, training=True, row_offs=[d[1] for d in dev_in],
+                               slot_occ_offs=[b[2] for b in batches], outs=pre)
         torch.cuda.synchronize()
         octx = []
         for r in range(R):
@@ -158,8 +161,7 @@ def test_virtual_ranks_ragged_sqrt_scale(torch_cuda, oracle):
         scale = [128.0, 1.0, 128.0, 1.0]
         dg = [[torch.from_numpy(g[r, i]).to(DEV) for i in range(S)] for r in range(R)]
         torch.cuda.synchronize()
-        for r in range(R):
-            ws[r].backward(dg[r], scales=scale)
+        W.group_backward(ws, dg, scales=scale)
         torch.cuda.synchronize()
         for r in range(R):
             w.backward(octx[r], [g[r, i] for i in range(S)], scale=scale)
@@ -167,8 +169,11 @@ def test_virtual_ranks_ragged_sqrt_scale(torch_cuda, oracle):
 
 
 def test_virtual_ranks_graph_replay(torch_cuda, oracle):
-    """The whole sharded step of a rank — kernels, peer stores, flag waits — captured in ONE CUDA graph per rank and
-    replayed: the mode bench.py --gpus N times.  Phase counters live on the device, so replays stay in step."""
+    """The sharded step of every rank — kernels, peer stores, flag waits — captured in CUDA graphs (one per rank and
+    phase, since one host thread drives the virtual ranks phase by phase; a process per GPU captures the whole step in
+    one graph, bench.py --gpus N) and replayed.  Phase counters live on the device, so replays stay in step."""
+    from persia_b200 import native as N
+
     torch = torch_cuda
     oracle.set_rsqrt_exact(True)
     try:
@@ -178,10 +183,13 @@ def test_virtual_ranks_graph_replay(torch_cuda, oracle):
         ids_dev = [torch.zeros(S * B, dtype=torch.int64, device=DEV) for _ in range(R)]
         g_dev = [torch.zeros((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
         outs = [torch.empty((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
+        plan = [("f", N.PHASE_SEND), ("f", N.PHASE_SERVE), ("f", N.PHASE_FINISH), ("b", N.PHASE_SEND), ("b", N.PHASE_SERVE)]
 
-        def enqueue(r):
-            ws[r].forward(ids_dev[r], B, training=True, out=outs[r])
-            ws[r].backward(g_dev[r])
+        def enqueue(r, kind, ph):
+            if kind == "f":
+                ws[r].forward(ids_dev[r], B, training=True, out=outs[r], phases=ph)
+            else:
+                ws[r].backward(g_dev[r], phases=ph)
 
         def oracle_step(ids, g):
             octx = [w.forward(ids[r], full_row_off(S, B), B, training=True) for r in range(R)]
@@ -192,16 +200,18 @@ def test_virtual_ranks_graph_replay(torch_cuda, oracle):
         zero_ids = [np.zeros(S * B, np.uint64) for _ in range(R)]
         zero_g = np.zeros((R, S, B, dim), np.float16)
         torch.cuda.synchronize()
-        for r in range(R):  # eager warm-up step (id 0 in every slot, zero gradients)
-            enqueue(r)
+        for kind, ph in plan:  # eager warm-up step (id 0 in every slot, zero gradients)
+            for r in range(R):
+                enqueue(r, kind, ph)
         torch.cuda.synchronize()
         oracle_step(zero_ids, zero_g)
-        graphs = []
+        graphs = {}
         for r in range(R):
-            gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph, stream=ws[r].stream, capture_error_mode="thread_local"):
-                enqueue(r)
-            graphs.append(gph)
+            for kind, ph in plan:
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=ws[r].stream, capture_error_mode="thread_local"):
+                    enqueue(r, kind, ph)
+                graphs[(r, kind, ph)] = gph
         seen = {int(oracle.add_prefix(np.zeros(1, np.uint64), 8, p)[0]) for p in pf}
         for it in range(3):
             ids = [make_batch(rng, S, B, card)[0] for _ in range(R)]
@@ -210,9 +220,10 @@ def test_virtual_ranks_graph_replay(torch_cuda, oracle):
                 ids_dev[r].copy_(to_dev_ids(ids[r], DEV))
                 g_dev[r].copy_(torch.from_numpy(g[r]).to(DEV))
             torch.cuda.synchronize()
-            for r in range(R):
-                with torch.cuda.stream(ws[r].stream):
-                    graphs[r].replay()
+            for kind, ph in plan:
+                for r in range(R):
+                    with torch.cuda.stream(ws[r].stream):
+                        graphs[(r, kind, ph)].replay()
             torch.cuda.synchronize()
             want = oracle_step(ids, g)
             for r in range(R):
@@ -239,8 +250,7 @@ def test_overflow_is_flagged(torch_cuda, oracle):
     ids = [to_dev_ids(np.arange(S * B, dtype=np.uint64) + 1000 * r, DEV) for r in range(R)]
     outs = [torch.empty((S, B, dim), dtype=torch.float16, device=DEV) for _ in range(R)]
     torch.cuda.synchronize()
-    for r in range(R):
-        ws[r].forward(ids[r], B, training=False, out=outs[r])
+    ShardedEmbeddingWorker.group_forward(ws, ids, B, training=False, outs=outs)
     torch.cuda.synchronize()
     assert all(x.status()[0] for x in ws) and not any(x.status()[1] for x in ws)
 
