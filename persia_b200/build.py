@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpersia_b200.so")
 SOURCES = ["pb_index.cu", "pb_dedup.cu", "pb_reduce.cu", "pb_shard.cu", "pb_sort.cu", "pb_update.cu", "pb_raw.cu", "pb_launch.cu", "pb_api.cu"]
-HEADERS = ["pb_common.cuh", "pb_kernels.cuh", "pb_device.cuh", "pb_group.cuh", "pb_probe.cuh", "pb_optim.cuh", os.path.join(ROOT, "include", "persia_b200.h")]
+HEADERS = ["pb_common.cuh", "pb_kernels.cuh", "pb_device.cuh", "pb_group.cuh", "pb_probe.cuh", "pb_optim.cuh", "pb_batch.cuh", os.path.join(ROOT, "include", "persia_b200.h")]
 
 
 def nvcc():

@@ -12,6 +12,7 @@
 // Everything downstream of k_dedup works on U distinct signs instead of N occurrences (Criteo batches: U/N ~ 0.3), and
 // nothing here depends on thread timing in a way that reaches a result: item numbers and list orders do, values do not
 // (a sign's gradient is summed in ascending occurrence order whatever order its list was filled in, pb_reduce.cu).
+#include "pb_batch.cuh"
 #include "pb_probe.cuh"
 
 namespace pb {
@@ -65,18 +66,23 @@ __global__ void __launch_bounds__(256) k_dedup(SlotsDev sl, BatchDev b, const ui
   __syncwarp();
   const uint32_t peers = __match_any_sync(0xffffffffu, idx);
   if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&b.set[idx].count, (uint32_t)__popc(peers));
+  // item numbers: one global atomic per BLOCK (same-address atomics with a return serialise in L2 at several cycles
+  // each: one per warp — thousands on one word — was most of this kernel's time)
+  __shared__ uint32_t s_won, s_base;
+  if (threadIdx.x == 0) s_won = 0;
+  __syncthreads();
   const uint32_t wm = __ballot_sync(0xffffffffu, won);
-  if (wm) {
-    uint32_t base = 0;
-    const uint32_t leader = __ffs(wm) - 1;
-    if (lane == leader) base = atomicAdd(&b.cnt[BC_ITEMS], (uint32_t)__popc(wm));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (won) {
-      const uint32_t u = base + __popc(wm & ((1u << lane) - 1u));
-      b.item_cell[u] = idx;
-      b.set[idx].first = i;
-      b.set[idx].item = u | (special_sign ? 0x80000000u : 0u);  // the reserved cell stores 0 for the sign KEY_EMPTY
-    }
+  uint32_t woff = 0;
+  if (wm && lane == 0) woff = atomicAdd(&s_won, (uint32_t)__popc(wm));
+  woff = __shfl_sync(0xffffffffu, woff, 0);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_won) s_base = atomicAdd(&b.cnt[BC_ITEMS], s_won);
+  __syncthreads();
+  if (won) {
+    const uint32_t u = s_base + woff + __popc(wm & ((1u << lane) - 1u));
+    b.item_cell[u] = idx;
+    b.set[idx].first = i;
+    b.set[idx].item = u | (special_sign ? 0x80000000u : 0u);  // the reserved cell stores 0 for the sign KEY_EMPTY
   }
 }
 
@@ -88,54 +94,36 @@ __global__ void __launch_bounds__(256) k_dedup(SlotsDev sl, BatchDev b, const ui
 // Persistent grid: the number of items lives on the device.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_probe_items(TableDev t, HyperDev hy, OptimDev op, BatchDev b) {
+__global__ void __launch_bounds__(256, 4) k_probe_items(TableDev t, HyperDev hy, OptimDev op, BatchDev b) {
   const uint32_t tick = t.counters[CTR_TICK];
   const uint32_t n_items = b.cnt[BC_ITEMS];
+  if (blockIdx.x * (blockDim.x / BUCKET) >= n_items) return;  // whole block (the grid is sized for the worst case)
   const uint32_t sub = threadIdx.x % BUCKET;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gshift = lane & ~(BUCKET - 1);
-  const uint32_t groups = gridDim.x * (blockDim.x / BUCKET);
-  const uint32_t warp_first = ((blockIdx.x * blockDim.x + threadIdx.x) / 32) * (32 / BUCKET);  // first item of this warp
-  for (uint32_t u0 = warp_first; u0 < n_items; u0 += groups) {  // uniform per warp
-    const uint32_t u = u0 + (lane / BUCKET);
-    const bool valid = u < n_items;
-    uint64_t sign = 0ULL;
-    uint32_t cell = 0, cnt = 0, first = 0, base = 0;
-    if (valid && sub == 0) {
-      cell = b.item_cell[u];
-      const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);        // key (2 words), count, cursor
-      const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);  // target, base, first, item
-      sign = (hi.w >> 31) ? KEY_EMPTY : ((uint64_t)lo.x | ((uint64_t)lo.y << 32));
-      cnt = lo.z;
-      first = hi.z;
-    }
-    sign = __shfl_sync(0xffffffffu, sign, gshift);
-    const ProbeOut r = probe_group<MODE>(t, hy, op, sign, valid, tick, sub, gshift);
-    // classify (lane 0 of every group), appends aggregated per warp
-    const bool head = valid && sub == 0;
-    if (head) {
-      if (MODE != MODE_TRAIN) cnt = 0;  // inference: nothing is kept for a backward
-      if (cnt > 1) base = atomicAdd(&b.cnt[BC_SEG], cnt);
-      b.set[cell].target = r.row;
-      b.set[cell].base = base;
-      if (r.row == ROW_NONE && MODE != MODE_SET) atomicAdd(&t.counters[CTR_MISS], 1u);  // index_miss_count, per distinct sign
-    }
-    const uint32_t cm = __ballot_sync(0xffffffffu, head && cnt == 1);
-    const uint32_t wm = __ballot_sync(0xffffffffu, head && cnt > 1 && cnt <= PB_WARM_MAX);
-    const uint32_t hm = __ballot_sync(0xffffffffu, head && cnt > PB_WARM_MAX);
-    uint32_t cb = 0, wb = 0, hb = 0;
-    if (lane == 0) {
-      if (cm) cb = atomicAdd(&b.cnt[BC_COLD], (uint32_t)__popc(cm));
-      if (wm) wb = atomicAdd(&b.cnt[BC_WARM], (uint32_t)__popc(wm));
-      if (hm) hb = atomicAdd(&b.cnt[BC_HOT], (uint32_t)__popc(hm));
-    }
-    cb = __shfl_sync(0xffffffffu, cb, 0);
-    wb = __shfl_sync(0xffffffffu, wb, 0);
-    hb = __shfl_sync(0xffffffffu, hb, 0);
-    const uint32_t below = (1u << lane) - 1u;
-    if (head && cnt == 1) b.cold[cb + __popc(cm & below)] = make_uint2(r.row, first);
-    else if (head && cnt > 1 && cnt <= PB_WARM_MAX) b.warm[wb + __popc(wm & below)] = make_uint4(r.row, base, cnt, 0u);
-    else if (head && cnt > PB_WARM_MAX) b.hot[hb + __popc(hm & below)] = make_uint4(r.row, base, cnt, 0u);
+  const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) / BUCKET;
+  const bool valid = u < n_items;
+  uint64_t sign = 0ULL;
+  uint32_t cell = 0, cnt = 0, first = 0;
+  if (valid && sub == 0) {
+    cell = b.item_cell[u];
+    const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);        // key (2 words), count, cursor
+    const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);  // target, base, first, item
+    sign = (hi.w >> 31) ? KEY_EMPTY : ((uint64_t)lo.x | ((uint64_t)lo.y << 32));
+    cnt = lo.z;
+    first = hi.z;
+  }
+  sign = __shfl_sync(0xffffffffu, sign, gshift);
+  const ProbeOut r = probe_group<MODE>(t, hy, op, sign, valid, tick, sub, gshift);
+  const bool head = valid && sub == 0;
+  if (MODE != MODE_TRAIN) cnt = 0;  // inference: nothing is kept for a backward
+  const ItemSlots sl = block_item_slots(b, head, cnt);
+  if (head) {
+    *(reinterpret_cast<uint2*>(&b.set[cell]) + 2) = make_uint2(r.row, sl.base);  // target, base
+    if (r.row == ROW_NONE && MODE != MODE_SET) atomicAdd(&t.counters[CTR_MISS], 1u);  // index_miss_count, per distinct sign
+    if (sl.cls == 1) b.cold[sl.pos] = make_uint2(r.row, first);
+    else if (sl.cls == 2) b.warm[sl.pos] = make_uint4(r.row, sl.base, cnt, 0u);
+    else if (sl.cls == 3) b.hot[sl.pos] = make_uint4(r.row, sl.base, cnt, 0u);
   }
 }
 
@@ -174,6 +162,26 @@ __device__ __forceinline__ OccRef occ_ref(const BatchDev& b, uint32_t cell) {
 __device__ __forceinline__ void file_occurrence(const BatchDev& b, uint32_t cell, const OccRef& r, uint32_t occ) {
   if (r.count > 1) b.seg_occ[r.base + atomicAdd(&b.set[cell].cursor, 1u)] = occ;
 }
+// the same for 32 consecutive occurrences at once, one per lane: occurrences of one sign share ONE atomic (a sign
+// repeated thousands of times would otherwise serialise thousands of atomics on its cursor)
+__device__ __forceinline__ void file_occurrences_warp(const BatchDev& b, uint32_t occ, bool valid) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t cell = 0xFFFFFFFFu;
+  OccRef r;
+  r.row = r.base = r.count = 0;
+  if (valid) {
+    cell = b.occ_set[occ];
+    r = occ_ref(b, cell);
+    if (r.count <= 1) cell = 0xFFFFFFFFu;
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, cell);
+  if (cell == 0xFFFFFFFFu) return;
+  const uint32_t leader = __ffs(peers) - 1;
+  uint32_t at = 0;
+  if (lane == leader) at = atomicAdd(&b.set[cell].cursor, (uint32_t)__popc(peers));
+  at = __shfl_sync(peers, at, leader);
+  b.seg_occ[r.base + at + __popc(peers & ((1u << lane) - 1u))] = occ;
+}
 
 constexpr int GATHER_ITEM_ROWS = 4;  // output rows per group in the one-id-per-sample layout (independent loads in flight)
 
@@ -186,6 +194,10 @@ __global__ void __launch_bounds__(256) k_gather_items(TableDev t, SlotsDev sl, B
   const uint32_t nvec = t.dim / VEC;
   if (!row_off) {
     // one occurrence per output row: GATHER_ITEM_ROWS rows per group, every stage issued for all rows before use
+    if (TRAIN) {  // one occurrence per thread first: the grid has at least n_out threads
+      const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+      if ((gt & ~31u) < n_out) file_occurrences_warp(b, gt, gt < n_out);
+    }
     const uint32_t r0 = group * GATHER_ITEM_ROWS;
     if (r0 >= n_out) return;
     uint32_t cell[GATHER_ITEM_ROWS];
@@ -201,11 +213,6 @@ __global__ void __launch_bounds__(256) k_gather_items(TableDev t, SlotsDev sl, B
         ref[k].base = 0;
         ref[k].count = 0;
       }
-    }
-    if (TRAIN && lane == 0) {
-#pragma unroll
-      for (int k = 0; k < GATHER_ITEM_ROWS; ++k)
-        if (cell[k] != 0xFFFFFFFFu) file_occurrence(b, cell[k], ref[k], r0 + k);
     }
     for (uint32_t c = lane; c < nvec; c += G) {
       float v[GATHER_ITEM_ROWS][VEC];
@@ -292,8 +299,7 @@ void launch_dedup(const SlotsDev& sl, const BatchDev& b, const uint64_t* ids, cu
 void launch_probe_items(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const BatchDev& b,
                         cudaStream_t st) {
   if (!b.n) return;
-  const uint32_t full = cdiv((uint64_t)b.n * BUCKET, 256);
-  const uint32_t grid = full < 148u * PB_PROBE_BLOCKS ? full : 148u * PB_PROBE_BLOCKS;
+  const uint32_t grid = cdiv((uint64_t)b.n * BUCKET, 256);  // worst case U = N; blocks past the item count return at once
   if (training) PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_TRAIN>), grid, 256, 0, st, t, hy, op, b);
   else PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_FIND>), grid, 256, 0, st, t, hy, op, b);
 }
@@ -305,6 +311,7 @@ static void gather_items_dispatch(int G, const TableDev& t, const SlotsDev& sl, 
 #define PB_G(GG)                                                                                                  \
   case GG:                                                                                                        \
     grid = cdiv((uint64_t)(row_off ? n_out : cdiv(n_out, GATHER_ITEM_ROWS)) * GG, 256);                           \
+    if (!row_off && grid < cdiv(n_out, 256)) grid = cdiv(n_out, 256);                                             \
     PB_LAUNCH_F(FAM_GATHER, (k_gather_items<VEC, GG, TRAIN>), grid, 256, 0, st, t, sl, b, row_off, n_out, batch, out); \
     break;
   switch (G) { PB_G(1) PB_G(2) PB_G(4) PB_G(8) PB_G(16) PB_G(32) }

@@ -128,14 +128,24 @@ __device__ __forceinline__ ProbeOut probe_group(const TableDev& t, const HyperDe
         atomicAdd(&t.counters[CTR_ADMIT], 1u);
         t.row_tick[row] = tick;  // recency of a fresh row
       }
-      *reinterpret_cast<volatile uint32_t*>(&t.cells[free_cell].row) = row;
       if (row == ROW_NONE) {  // no storage: give the cell back (duplicates that matched meanwhile read ROW_NONE)
+        *reinterpret_cast<volatile uint32_t*>(&t.cells[free_cell].row) = row;
         __threadfence();
         *reinterpret_cast<volatile unsigned long long*>(&t.cells[free_cell].key) = special ? KEY_EMPTY : KEY_TOMB;
+      } else if (MODE != MODE_TRAIN) {
+        *reinterpret_cast<volatile uint32_t*>(&t.cells[free_cell].row) = row;  // set_embedding: the caller fills the row
       }
     }
     row = __shfl_sync(0xffffffffu, row, gshift + le);
-    if (MODE == MODE_TRAIN && won_cas && row != ROW_NONE) init_row(t, hy, op, sign, row, sub);  // all 8 lanes
+    if (MODE == MODE_TRAIN && won_cas && row != ROW_NONE) {
+      // the row number is published only once all eight lanes have initialised the row: whoever finds the sign in the
+      // index meanwhile (a duplicate in this launch, another requester's lookup) waits for it below instead of reading
+      // a half-written row
+      init_row(t, hy, op, sign, row, sub);
+      __threadfence();
+      __syncwarp(0xFFu << gshift);
+      if (sub == le) *reinterpret_cast<volatile uint32_t*>(&t.cells[free_cell].row) = row;
+    }
     if (!done) {
       if (mm) {
         result = special ? special_cell : bucket * BUCKET + lm;
@@ -175,7 +185,7 @@ __device__ __forceinline__ ProbeOut probe_group(const TableDev& t, const HyperDe
     row_res = ROW_NONE;
     result = h_none;
   } else if (MODE == MODE_TRAIN && sub == 0) {
-    if (t.row_tick[row_res] != tick) t.row_tick[row_res] = tick;  // get_refresh: one store per sign and batch
+    t.row_tick[row_res] = tick;  // get_refresh (a store, never a dependent load: probing is latency-bound)
   }
   ProbeOut o;
   o.cell = result;

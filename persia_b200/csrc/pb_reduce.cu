@@ -10,9 +10,10 @@
 // The forward left three work lists (pb_dedup.cu): cold items (one occurrence — nothing to reduce), warm items
 // (2..PB_WARM_MAX occurrences, list unsorted) and hot items (more: the head of the Zipf curve and every sign of a
 // tiny-cardinality slot, thousands of occurrences each).
-//   k_reduce_items  persistent; a lane group per item.  Cold: four items per group in flight (all row and gradient
-//                   loads issued before the first use).  Warm: the group sorts the item's <= 32 occurrences in shared
-//                   memory (rank by counting), then adds them in order.
+//   k_reduce_cold   a lane group per item: two independent loads (row, gradient), step, store — light on registers, the
+//                   whole chip's worth of groups resident.
+//   k_reduce_warm   a lane group per item: the group sorts the item's <= 32 occurrences in shared memory (rank by
+//                   counting), then adds them in order.
 //   k_reduce_hot    persistent; a two-warp CTA per item.  The occurrences are put in order by setting one bit per
 //                   occurrence in a shared-memory bitmap over the slot's sample range (a counting sort that costs
 //                   B/32 words).  Warp 0 streams the gradient rows, 32 per stage, into a shared-memory ring with
@@ -172,14 +173,8 @@ __device__ __forceinline__ void build_dead_mask(uint32_t* dead, const GradsDev& 
 __device__ __forceinline__ bool slot_dead(const uint32_t* dead, uint32_t slot) { return (dead[slot >> 5] >> (slot & 31)) & 1u; }
 
 // ------------------------------------------------------------------------------------------------
-// cold + warm items
+// cold and warm items
 // ------------------------------------------------------------------------------------------------
-#ifndef PB_REDUCE_BLOCKS
-#define PB_REDUCE_BLOCKS 3  // blocks per SM k_reduce_items is launched with (compiled for 4): the rest of the register
-#endif                      // file is left to the hot kernel, which runs beside it
-constexpr int ITEMS_THREADS = 128;
-constexpr int COLD_ITEMS = 3;
-
 // one item through the generic path: sorted occurrence list pos(0..cnt-1)
 // sharded requester: the reduced gradient of one item goes to its owner (update_all_batched_gradients ends with one
 // (signs, gradients) request per parameter server, mod.rs:813-857)
@@ -224,175 +219,114 @@ __device__ __forceinline__ void step_item(const TableDev& t, const OptimDev& op,
   }
 }
 
+// ---- warm items: one lane group per item; the group sorts the item's <= 32 occurrences (rank by counting), then adds
+// them in order.  Items are assigned statically (a shared work counter would be thousands of same-address atomics).
 template <int VEC, bool F16, int KIND, bool SEND>
-__global__ void __launch_bounds__(ITEMS_THREADS, 4) k_reduce_items(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl,
-                                                                       GradsDev gr, ReduceArgs a, uint32_t G) {
+__global__ void __launch_bounds__(256) k_reduce_warm(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                     ReduceArgs a, uint32_t G) {
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
-  __shared__ uint32_t sortbuf[ITEMS_THREADS / 4][2 * PB_WARM_MAX];  // per lane group (G >= 4): unsorted | sorted occurrences
+  __shared__ uint32_t sortbuf[64][2 * PB_WARM_MAX];  // per lane group (G >= 4): unsorted | sorted occurrences
+  const uint32_t n_warm = a.b.cnt[BC_WARM], n_cold = a.b.cnt[BC_COLD];
+  if (blockIdx.x * (blockDim.x / G) >= n_warm) return;  // whole block
   build_dead_mask(dead, gr, a, sl.n_slots);
-  const uint32_t lane = threadIdx.x % G;
-  const uint32_t grp = threadIdx.x / G;
-  const uint32_t wl = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x % G, grp = threadIdx.x / G, wl = threadIdx.x & 31;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
-  const uint32_t n_groups = gridDim.x * (blockDim.x / G);
-  const uint32_t g_global = blockIdx.x * (blockDim.x / G) + grp;
-  const uint32_t n_cold = a.b.cnt[BC_COLD], n_warm = a.b.cnt[BC_WARM];
-  const uint32_t nvec = t.dim / VEC;
-
-  // ---- warm items first (the longer ones), handed out one at a time
-  {
-    uint32_t* next = a.b.cnt + BC_NEXT + a.round;
-    uint32_t* raw = sortbuf[grp];
-    uint32_t* srt = raw + PB_WARM_MAX;
-    for (;;) {
-      uint32_t w = 0;
-      if (lane == 0) w = atomicAdd(next, 1u);
-      w = __shfl_sync(gmask, w, wl / G * G);
-      if (w >= n_warm) break;
-      const uint4 d = a.b.warm[w];
-      const uint32_t row = d.x, base = d.y, cnt = d.z;
-      for (uint32_t l = lane; l < cnt; l += G) raw[l] = a.b.seg_occ[base + l];
-      __syncwarp(gmask);
-      for (uint32_t l = lane; l < cnt; l += G) {  // rank by counting: occurrences are distinct numbers
-        const uint32_t p = raw[l];
-        uint32_t r = 0;
-        for (uint32_t m = 0; m < cnt; ++m) r += raw[m] < p;
-        srt[r] = p;
-      }
-      __syncwarp(gmask);
-      const uint32_t slot = slot_of_occ(sl, srt[0]);
-      if (SEND) {
-        if (row != ROW_NONE) {  // ROW_NONE: the item found no room in its owner's segment (flagged in k_route_items)
-          if (slot_dead(dead, slot)) {
-            if (lane == 0) *send_gok_ptr(a.x, row) = 0u;
-          } else {
-            send_item<VEC, F16>(t, sl, gr, a, row, slot, cnt, lane, G, [&](uint32_t k) { return srt[k]; });
-          }
-        }
-      } else if (!slot_dead(dead, slot)) {
-        if (row >= t.capacity) {
-          if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
-        } else {
-          float* stage = a.vw_stage ? a.vw_stage + (size_t)(n_cold + w) * t.dim : nullptr;
-          step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, row, slot, cnt, lane, G, gmask, stage,
-                                    [&](uint32_t k) { return srt[k]; });
-        }
-      }
-      __syncwarp(gmask);  // the buffers are reused by the next item
-    }
+  const uint32_t w = blockIdx.x * (blockDim.x / G) + grp;
+  if (w >= n_warm) return;  // whole group
+  uint32_t* raw = sortbuf[grp];
+  uint32_t* srt = raw + PB_WARM_MAX;
+  const uint4 d = a.b.warm[w];
+  const uint32_t row = d.x, base = d.y, cnt = d.z;
+  for (uint32_t l = lane; l < cnt; l += G) raw[l] = a.b.seg_occ[base + l];
+  __syncwarp(gmask);
+  for (uint32_t l = lane; l < cnt; l += G) {  // occurrences are distinct numbers
+    const uint32_t p = raw[l];
+    uint32_t r = 0;
+    for (uint32_t m = 0; m < cnt; ++m) r += raw[m] < p;
+    srt[r] = p;
   }
+  __syncwarp(gmask);
+  const uint32_t slot = slot_of_occ(sl, srt[0]);
+  if (SEND) {
+    if (row == ROW_NONE) return;  // the item found no room in its owner's segment (flagged in k_route_items)
+    if (slot_dead(dead, slot)) {
+      if (lane == 0) *send_gok_ptr(a.x, row) = 0u;
+    } else {
+      send_item<VEC, F16>(t, sl, gr, a, row, slot, cnt, lane, G, [&](uint32_t k) { return srt[k]; });
+    }
+    return;
+  }
+  if (slot_dead(dead, slot)) return;
+  if (row >= t.capacity) {
+    if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
+    return;
+  }
+  float* stage = a.vw_stage ? a.vw_stage + (size_t)(n_cold + w) * t.dim : nullptr;
+  step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, row, slot, cnt, lane, G, gmask, stage, [&](uint32_t k) { return srt[k]; });
+}
 
-  // ---- cold items: COLD_ITEMS per group and iteration, every load issued before the first use
-  for (uint32_t w0 = g_global * COLD_ITEMS; w0 < n_cold; w0 += n_groups * COLD_ITEMS) {
-    if (SEND) {
-      float* dst[COLD_ITEMS];
-      ItemSrc src[COLD_ITEMS];
-      GradPrep prep[COLD_ITEMS];
-      size_t gelem[COLD_ITEMS];
-      bool act[COLD_ITEMS];
-#pragma unroll
-      for (int k = 0; k < COLD_ITEMS; ++k) {
-        act[k] = w0 + k < n_cold;
-        uint2 d = make_uint2(ROW_NONE, 0u);
-        if (act[k]) d = a.b.cold[w0 + k];
-        act[k] = act[k] && d.x != ROW_NONE;
-        uint32_t slot = 0;
-        if (act[k]) {
-          slot = slot_of_occ(sl, d.y);
-          if (slot_dead(dead, slot)) {
-            if (lane == 0) *send_gok_ptr(a.x, d.x) = 0u;
-            act[k] = false;
-          } else if (lane == 0) {
-            *send_gok_ptr(a.x, d.x) = 1u;
-          }
-        }
-        dst[k] = act[k] ? send_grad_ptr(a.x, d.x, t.dim) : nullptr;
-        src[k] = item_src(sl, gr, a, slot);
-        const uint32_t orow = act[k] ? occ_out_row(a, d.y) : src[k].slot_row0;
-        prep[k] = grad_prep(src[k], a, orow);
-        gelem[k] = (size_t)(orow - src[k].slot_row0) * t.dim;
-      }
-      for (uint32_t c = lane; c < nvec; c += G) {
-        float g[COLD_ITEMS][VEC];
-#pragma unroll
-        for (int k = 0; k < COLD_ITEMS; ++k)
-          if (act[k]) load_grad_elems<VEC, F16>(g[k], src[k].gbase, gelem[k], c * VEC);
-#pragma unroll
-        for (int k = 0; k < COLD_ITEMS; ++k)
-          if (act[k]) {
-            float acc[VEC];
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;
-            add_prepared<VEC>(acc, g[k], prep[k], src[k].plain);
-            store_vec<VEC>(dst[k] + c * VEC, acc);
-          }
-      }
-      continue;
-    }
-    if (KIND == PB_OPT_ADAGRAD_VW) {  // needs the whole reduced gradient staged: one item at a time
-      for (uint32_t w = w0; w < min(n_cold, w0 + COLD_ITEMS); ++w) {
-        const uint2 d = a.b.cold[w];
-        const uint32_t slot = slot_of_occ(sl, d.y);
-        if (slot_dead(dead, slot)) continue;
-        if (d.x >= t.capacity) {
-          if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
-          continue;
-        }
-        const uint32_t occ = d.y;
-        step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, d.x, slot, 1u, lane, G, gmask, a.vw_stage + (size_t)w * t.dim,
-                                  [&](uint32_t) { return occ; });
-      }
-      continue;
-    }
-    float* prow[COLD_ITEMS];
-    ItemSrc src[COLD_ITEMS];
-    GradPrep prep[COLD_ITEMS];
-    StepCtx sc[COLD_ITEMS];
-    size_t gelem[COLD_ITEMS];
-    bool act[COLD_ITEMS];
-#pragma unroll
-    for (int k = 0; k < COLD_ITEMS; ++k) {
-      act[k] = w0 + k < n_cold;
-      uint2 d = make_uint2(ROW_NONE, 0u);
-      if (act[k]) d = a.b.cold[w0 + k];
-      uint32_t slot = 0;
-      if (act[k]) {
-        slot = slot_of_occ(sl, d.y);
-        act[k] = !slot_dead(dead, slot);
-      }
-      if (act[k] && d.x >= t.capacity) {
-        if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
-        act[k] = false;
-      }
-      prow[k] = t.rows + (size_t)(act[k] ? d.x : 0u) * t.stride;
-      src[k] = item_src(sl, gr, a, slot);
-      const uint32_t orow = act[k] ? occ_out_row(a, d.y) : src[k].slot_row0;
-      prep[k] = grad_prep(src[k], a, orow);
-      gelem[k] = (size_t)(orow - src[k].slot_row0) * t.dim;
-      sc[k].vw_state = 0.0f;
-      sc[k].r1 = sc[k].r2 = 0.0f;
-      if (KIND == PB_OPT_ADAM && act[k]) sc[k] = step_ctx(prow[k], t, op, gr, slot);
-    }
+// ---- cold items (one occurrence — the majority): nothing to reduce.  One lane group per item, nothing but two
+// independent loads (row, gradient), the step and the store; light on registers so that the whole chip's worth of
+// groups is resident and the loads of many rows are in flight.
+template <int VEC, bool F16, int KIND, bool SEND>
+__global__ void __launch_bounds__(256) k_reduce_cold(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                     ReduceArgs a, uint32_t G) {
+  __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
+  const uint32_t n_cold = a.b.cnt[BC_COLD];
+  if (blockIdx.x * (blockDim.x / G) >= n_cold) return;  // whole block
+  build_dead_mask(dead, gr, a, sl.n_slots);
+  const uint32_t lane = threadIdx.x % G, wl = threadIdx.x & 31;
+  const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
+  const uint32_t w = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+  if (w >= n_cold) return;
+  const uint2 d = a.b.cold[w];
+  const uint32_t slot = slot_of_occ(sl, d.y);
+  const uint32_t nvec = t.dim / VEC;
+  const ItemSrc src = item_src(sl, gr, a, slot);
+  const uint32_t orow = occ_out_row(a, d.y);
+  const GradPrep prep = grad_prep(src, a, orow);
+  const size_t gelem = (size_t)(orow - src.slot_row0) * t.dim;
+  if (SEND) {
+    if (d.x == ROW_NONE) return;
+    const bool off = slot_dead(dead, slot);
+    if (lane == 0) *send_gok_ptr(a.x, d.x) = off ? 0u : 1u;
+    if (off) return;
+    float* dst = send_grad_ptr(a.x, d.x, t.dim);
     for (uint32_t c = lane; c < nvec; c += G) {
-      RowElems<KIND, VEC> rc[COLD_ITEMS];
-      float g[COLD_ITEMS][VEC];
+      float g[VEC], acc[VEC];
+      load_grad_elems<VEC, F16>(g, src.gbase, gelem, c * VEC);
 #pragma unroll
-      for (int k = 0; k < COLD_ITEMS; ++k)
-        if (act[k]) rc[k].load(prow[k], c * VEC, t, op);
-#pragma unroll
-      for (int k = 0; k < COLD_ITEMS; ++k)
-        if (act[k]) load_grad_elems<VEC, F16>(g[k], src[k].gbase, gelem[k], c * VEC);
-#pragma unroll
-      for (int k = 0; k < COLD_ITEMS; ++k)
-        if (act[k]) {
-          float acc[VEC];
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;  // the reference adds into a zeroed row (-0 -> +0)
-          add_prepared<VEC>(acc, g[k], prep[k], src[k].plain);
-          rc[k].step(c * VEC, acc, t, op, hy, sc[k]);
-          rc[k].store(prow[k], c * VEC, t, op);
-        }
+      for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;
+      add_prepared<VEC>(acc, g, prep, src.plain);
+      store_vec<VEC>(dst + c * VEC, acc);
     }
+    return;
+  }
+  if (slot_dead(dead, slot)) return;
+  if (d.x >= t.capacity) {
+    if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+    return;
+  }
+  if (KIND == PB_OPT_ADAGRAD_VW) {  // needs the whole reduced gradient staged for the dot
+    const uint32_t occ = d.y;
+    step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, d.x, slot, 1u, lane, G, gmask, a.vw_stage + (size_t)w * t.dim,
+                              [&](uint32_t) { return occ; });
+    return;
+  }
+  float* prow = t.rows + (size_t)d.x * t.stride;
+  StepCtx sc;
+  sc.vw_state = sc.r1 = sc.r2 = 0.0f;
+  if (KIND == PB_OPT_ADAM) sc = step_ctx(prow, t, op, gr, slot);
+  for (uint32_t c = lane; c < nvec; c += G) {
+    RowElems<KIND, VEC> rc;
+    float g[VEC], acc[VEC];
+    rc.load(prow, c * VEC, t, op);
+    load_grad_elems<VEC, F16>(g, src.gbase, gelem, c * VEC);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;  // the reference adds into a zeroed row (-0 -> +0)
+    add_prepared<VEC>(acc, g, prep, src.plain);
+    rc.step(c * VEC, acc, t, op, hy, sc);
+    rc.store(prow, c * VEC, t, op);
   }
 }
 
@@ -605,35 +539,53 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
             }
             float* dst = cring + (size_t)r32.stage() * hr * t.dim;
             const unsigned char* srows = ring + (size_t)r16.stage() * hr * rowbytes;
+            const uint32_t cw = warp - 1u;  // converter warp: rows cw, cw + 3, ...; its lanes cover a row's element pairs
             if (t.dim % 2 == 0) {
-              const uint32_t total = nv * half_dim;
-              for (uint32_t i = ctid; i < total; i += 32 * HOT_CONV_WARPS) {
-                const uint32_t k = i / half_dim, col = i - k * half_dim;
-                const unsigned char* rp = bulk ? srows + (size_t)k * rowbytes
-                                               : gbytes + (size_t)(occ_out_row(a, wbase + sorted[c * hr + k]) - src.slot_row0) * rowbytes;
-                float2 v;
-                if (F16) v = __half22float2(clamp_h2(reinterpret_cast<const __half2*>(rp)[col]));
-                else v = reinterpret_cast<const float2*>(rp)[col];
-                if (src.do_scale) {
-                  v.x = __fmul_rn(v.x, src.inv_scale);
-                  v.y = __fmul_rn(v.y, src.inv_scale);
+              for (uint32_t k0 = cw; k0 < nv; k0 += 4u * HOT_CONV_WARPS) {  // four independent rows per round
+                const unsigned char* rp[4];
+                float f[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t k = k0 + (uint32_t)u * HOT_CONV_WARPS;
+                  const uint32_t kk = k < nv ? k : k0;
+                  f[u] = src.do_sqrt ? fac[kk] : 1.0f;
+                  if (bulk) rp[u] = srows + (size_t)kk * rowbytes;
+                  else rp[u] = gbytes + (size_t)(occ_out_row(a, wbase + sorted[c * hr + kk]) - src.slot_row0) * rowbytes;
                 }
-                if (src.do_sqrt) {
-                  v.x = __fmul_rn(v.x, fac[k]);
-                  v.y = __fmul_rn(v.y, fac[k]);
+                for (uint32_t col = lane; col < half_dim; col += 32) {
+                  float2 v[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    if (F16) v[u] = __half22float2(clamp_h2(reinterpret_cast<const __half2*>(rp[u])[col]));
+                    else v[u] = reinterpret_cast<const float2*>(rp[u])[col];
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const uint32_t k = k0 + (uint32_t)u * HOT_CONV_WARPS;
+                    if (k < nv) {
+                      if (src.do_scale) {
+                        v[u].x = __fmul_rn(v[u].x, src.inv_scale);
+                        v[u].y = __fmul_rn(v[u].y, src.inv_scale);
+                      }
+                      if (src.do_sqrt) {
+                        v[u].x = __fmul_rn(v[u].x, f[u]);
+                        v[u].y = __fmul_rn(v[u].y, f[u]);
+                      }
+                      reinterpret_cast<float2*>(dst + (size_t)k * t.dim)[col] = v[u];
+                    }
+                  }
                 }
-                reinterpret_cast<float2*>(dst + (size_t)k * t.dim)[col] = v;
               }
             } else {
-              const uint32_t total = nv * t.dim;
-              for (uint32_t i = ctid; i < total; i += 32 * HOT_CONV_WARPS) {
-                const uint32_t k = i / t.dim, col = i - k * t.dim;
+              for (uint32_t k = cw; k < nv; k += HOT_CONV_WARPS) {
                 const unsigned char* rp = bulk ? srows + (size_t)k * rowbytes
                                                : gbytes + (size_t)(occ_out_row(a, wbase + sorted[c * hr + k]) - src.slot_row0) * rowbytes;
-                float v = F16 ? clamp_f16(__half2float(reinterpret_cast<const __half*>(rp)[col])) : reinterpret_cast<const float*>(rp)[col];
-                if (src.do_scale) v = __fmul_rn(v, src.inv_scale);
-                if (src.do_sqrt) v = __fmul_rn(v, fac[k]);
-                dst[(size_t)k * t.dim + col] = v;
+                for (uint32_t col = lane; col < t.dim; col += 32) {
+                  float v = F16 ? clamp_f16(__half2float(reinterpret_cast<const __half*>(rp)[col])) : reinterpret_cast<const float*>(rp)[col];
+                  if (src.do_scale) v = __fmul_rn(v, src.inv_scale);
+                  if (src.do_sqrt) v = __fmul_rn(v, fac[k]);
+                  dst[(size_t)k * t.dim + col] = v;
+                }
               }
             }
             conv_barrier();  // every converter is done with both stages
@@ -708,16 +660,18 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
 template <int VEC, bool F16>
 static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
                            const ReduceArgs& a, uint32_t G, cudaStream_t st, bool send) {
-  static const uint32_t tune_grid = getenv("PB_REDUCE_GRID") ? (uint32_t)atoi(getenv("PB_REDUCE_GRID")) : 148u * PB_REDUCE_BLOCKS;
-  const uint32_t full = cdiv((uint64_t)a.b.n * G, ITEMS_THREADS);
-  const uint32_t grid = full < tune_grid ? full : tune_grid;
+  // grids sized for the worst case (every occurrence its own item); blocks past the list lengths return at once
+  const uint32_t per_block = 256u / G;
+  const uint32_t grid_cold = cdiv(a.b.n, per_block), grid_warm = cdiv(a.b.n / 2 + 1, per_block);
   if (send) {
-    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_items<VEC, F16, PB_OPT_SGD, true>), grid, ITEMS_THREADS, 0, st, t, op, hy, sl, gr, a, G);
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_warm<VEC, F16, PB_OPT_SGD, true>), grid_warm, 256, 0, st, t, op, hy, sl, gr, a, G);
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_cold<VEC, F16, PB_OPT_SGD, true>), grid_cold, 256, 0, st, t, op, hy, sl, gr, a, G);
     return;
   }
 #define PB_K(KK)                                                                                                   \
   case KK:                                                                                                         \
-    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_items<VEC, F16, KK, false>), grid, ITEMS_THREADS, 0, st, t, op, hy, sl, gr, a, G); \
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_warm<VEC, F16, KK, false>), grid_warm, 256, 0, st, t, op, hy, sl, gr, a, G); \
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_cold<VEC, F16, KK, false>), grid_cold, 256, 0, st, t, op, hy, sl, gr, a, G); \
     break;
   switch (op.kind) { PB_K(PB_OPT_SGD) PB_K(PB_OPT_ADAGRAD) PB_K(PB_OPT_ADAGRAD_VW) PB_K(PB_OPT_ADAM) }
 #undef PB_K

@@ -20,6 +20,7 @@
 // Ordering between ranks is by flag words in the receiver's area (one per phase and source, written after a
 // system-scope fence); k_wait spins on them in ONE block so that the box — or, in tests, the other virtual ranks
 // sharing a GPU — keeps running.  Phase counters live on the device: a whole step is CUDA-graph capturable.
+#include "pb_batch.cuh"
 #include "pb_optim.cuh"
 #include "pb_probe.cuh"
 
@@ -41,55 +42,49 @@ __device__ __forceinline__ unsigned char* x_row(const XchgDev& x, uint32_t q) {
 template <bool TRAIN>
 __global__ void __launch_bounds__(256) k_route_items(SlotsDev sl, BatchDev b, XchgDev x) {
   const uint32_t n_items = b.cnt[BC_ITEMS];
+  if (blockIdx.x * blockDim.x >= n_items) return;  // whole block (the grid is sized for the worst case)
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t first_u = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
-  for (uint32_t u0 = first_u; u0 < n_items; u0 += gridDim.x * blockDim.x) {  // uniform per warp
-    const uint32_t u = u0 + lane;
-    const bool valid = u < n_items;
-    uint32_t cell = 0, cnt = 0, first = 0, owner = 0xFFFFFFFFu;
-    uint64_t sign = 0;
-    if (valid) {
-      cell = b.item_cell[u];
-      const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);
-      const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);
-      sign = (hi.w >> 31) ? KEY_EMPTY : ((uint64_t)lo.x | ((uint64_t)lo.y << 32));
-      cnt = TRAIN ? lo.z : 0u;
-      first = hi.z;
-      owner = (uint32_t)(farmhash64_u64(sign) % x.R);  // sign_to_shard_modulo, mod.rs:341-345
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = u < n_items;
+  uint32_t cell = 0, cnt = 0, first = 0, owner = 0xFFFFFFFFu;
+  uint64_t sign = 0;
+  if (valid) {
+    cell = b.item_cell[u];
+    const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);
+    const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);
+    sign = (hi.w >> 31) ? KEY_EMPTY : ((uint64_t)lo.x | ((uint64_t)lo.y << 32));
+    cnt = TRAIN ? lo.z : 0u;
+    first = hi.z;
+    owner = (uint32_t)(farmhash64_u64(sign) % x.R);  // sign_to_shard_modulo, mod.rs:341-345
+  }
+  // a slot in the owner's segment: counted per block in shared memory, one global atomic per block and owner
+  __shared__ uint32_t s_n[PB_MAX_RANKS], s_g[PB_MAX_RANKS];
+  if (threadIdx.x < PB_MAX_RANKS) s_n[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t peers = __match_any_sync(0xffffffffu, owner);
+  const uint32_t leader = __ffs(peers) - 1;
+  uint32_t k = 0;
+  if (valid && lane == leader) k = atomicAdd(&s_n[owner], (uint32_t)__popc(peers));
+  k = __shfl_sync(0xffffffffu, k, leader) + __popc(peers & ((1u << lane) - 1u));
+  __syncthreads();
+  if (threadIdx.x < x.R && s_n[threadIdx.x]) s_g[threadIdx.x] = atomicAdd(&b.cnt[BC_PEER + threadIdx.x], s_n[threadIdx.x]);
+  __syncthreads();
+  uint32_t target = ROW_NONE;
+  if (valid) {
+    k += s_g[owner];
+    if (k < x.cap) {
+      target = owner * x.cap + k;
+      x_sign(x, owner)[(size_t)x.rank * x.cap + k] = sign;  // over NVLink when owner != rank
+    } else {
+      x.err[0] = 1u;  // the pair needs more than cap slots: the caller re-runs the batch with a larger cap
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, owner);
-    uint32_t k = 0;
-    const uint32_t leader = __ffs(peers) - 1;
-    if (valid && lane == leader) k = atomicAdd(&b.cnt[BC_PEER + owner], (uint32_t)__popc(peers));
-    k = __shfl_sync(0xffffffffu, k, leader) + __popc(peers & ((1u << lane) - 1u));
-    uint32_t target = ROW_NONE, base = 0;
-    if (valid) {
-      if (k < x.cap) {
-        target = owner * x.cap + k;
-        x_sign(x, owner)[(size_t)x.rank * x.cap + k] = sign;  // over NVLink when owner != rank
-      } else {
-        x.err[0] = 1u;  // the pair needs more than cap slots: the caller re-runs the batch with a larger cap
-      }
-      if (cnt > 1) base = atomicAdd(&b.cnt[BC_SEG], cnt);
-      b.set[cell].target = target;
-      b.set[cell].base = base;
-    }
-    const uint32_t cm = __ballot_sync(0xffffffffu, valid && cnt == 1);
-    const uint32_t wm = __ballot_sync(0xffffffffu, valid && cnt > 1 && cnt <= PB_WARM_MAX);
-    const uint32_t hm = __ballot_sync(0xffffffffu, valid && cnt > PB_WARM_MAX);
-    uint32_t cb = 0, wb = 0, hb = 0;
-    if (lane == 0) {
-      if (cm) cb = atomicAdd(&b.cnt[BC_COLD], (uint32_t)__popc(cm));
-      if (wm) wb = atomicAdd(&b.cnt[BC_WARM], (uint32_t)__popc(wm));
-      if (hm) hb = atomicAdd(&b.cnt[BC_HOT], (uint32_t)__popc(hm));
-    }
-    cb = __shfl_sync(0xffffffffu, cb, 0);
-    wb = __shfl_sync(0xffffffffu, wb, 0);
-    hb = __shfl_sync(0xffffffffu, hb, 0);
-    const uint32_t below = (1u << lane) - 1u;
-    if (valid && cnt == 1) b.cold[cb + __popc(cm & below)] = make_uint2(target, first);
-    else if (valid && cnt > 1 && cnt <= PB_WARM_MAX) b.warm[wb + __popc(wm & below)] = make_uint4(target, base, cnt, 0u);
-    else if (valid && cnt > PB_WARM_MAX) b.hot[hb + __popc(hm & below)] = make_uint4(target, base, cnt, 0u);
+  }
+  const ItemSlots is = block_item_slots(b, valid, cnt);
+  if (valid) {
+    *(reinterpret_cast<uint2*>(&b.set[cell]) + 2) = make_uint2(target, is.base);  // target, base
+    if (is.cls == 1) b.cold[is.pos] = make_uint2(target, first);
+    else if (is.cls == 2) b.warm[is.pos] = make_uint4(target, is.base, cnt, 0u);
+    else if (is.cls == 3) b.hot[is.pos] = make_uint4(target, is.base, cnt, 0u);
   }
 }
 
@@ -160,6 +155,8 @@ __global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev 
     if (valid && sub == 0) sign = x_sign(x, x.rank)[j];
     sign = __shfl_sync(0xffffffffu, sign, gshift);
     const ProbeOut r = probe_group<MODE>(t, hy, op, sign, valid, tick, sub, gshift);
+    // a row admitted just now was initialised by this very group (fenced before its number was published); rows are
+    // read through L2 below, never from a stale L1 line
     if (!valid) continue;
     if (sub == 0) {
       x.own_row[j] = r.row;
@@ -172,17 +169,17 @@ __global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev 
       float* dst = reinterpret_cast<float*>(x_row(x, src)) + slot * t.dim;
       if (t.dim % 4 == 0) {
         for (uint32_t e = sub * 4; e < t.dim; e += BUCKET * 4) {
-          float4 v = have ? *reinterpret_cast<const float4*>(row + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v = have ? __ldcg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(dst + e) = v;
         }
       } else {
-        for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = have ? row[e] : 0.0f;
+        for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = have ? __ldcg(row + e) : 0.0f;
       }
     } else {
       __half* dst = reinterpret_cast<__half*>(x_row(x, src)) + slot * t.dim;
       if (t.dim % 4 == 0) {
         for (uint32_t e = sub * 4; e < t.dim; e += BUCKET * 4) {
-          float4 v = have ? *reinterpret_cast<const float4*>(row + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v = have ? __ldcg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
           // the EW adds the row into a zeroed f32 row, then converts (mod.rs:555-561, persia-common lib.rs:157-161)
           __half2 a = __floats2half2_rn(__fadd_rn(0.0f, v.x), __fadd_rn(0.0f, v.y));
           __half2 c = __floats2half2_rn(__fadd_rn(0.0f, v.z), __fadd_rn(0.0f, v.w));
@@ -192,7 +189,7 @@ __global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev 
           *reinterpret_cast<uint2*>(dst + e) = pk;
         }
       } else {
-        for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = __float2half_rn(__fadd_rn(0.0f, have ? row[e] : 0.0f));
+        for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = __float2half_rn(__fadd_rn(0.0f, have ? __ldcg(row + e) : 0.0f));
       }
     }
   }
@@ -211,14 +208,32 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(256) k_expand_copy(uint32_t dim, BatchDev b, XchgDev x, uint32_t n_out,
                                                      __half* __restrict__ out, uint32_t lanes) {
   // `lanes` lanes per output row, 16 bytes per lane and step
+  if (TRAIN) {  // one occurrence per thread first (the grid has at least n_out threads), one atomic per warp and sign
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gt & ~31u) < n_out) {
+      const uint32_t lane = threadIdx.x & 31;
+      uint32_t fc = 0xFFFFFFFFu, fbase = 0;
+      if (gt < n_out) {
+        fc = b.occ_set[gt];
+        const uint4 flo = *reinterpret_cast<const uint4*>(&b.set[fc]);
+        fbase = (reinterpret_cast<const uint4*>(&b.set[fc]) + 1)->y;
+        if (flo.z <= 1) fc = 0xFFFFFFFFu;
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, fc);
+      if (fc != 0xFFFFFFFFu) {
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t at = 0;
+        if (lane == leader) at = atomicAdd(&b.set[fc].cursor, (uint32_t)__popc(peers));
+        at = __shfl_sync(peers, at, leader);
+        b.seg_occ[fbase + at + __popc(peers & ((1u << lane) - 1u))] = gt;
+      }
+    }
+  }
   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / lanes;
   const uint32_t l = threadIdx.x % lanes;
   if (g >= n_out) return;
   const uint32_t cell = b.occ_set[g];
-  const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);
-  const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);
-  const uint32_t target = hi.x;
-  if (TRAIN && l == 0) file_occ(b, cell, lo.z, hi.y, g);
+  const uint32_t target = (reinterpret_cast<const uint4*>(&b.set[cell]) + 1)->x;
   const uint32_t words = dim / 8;  // 16-byte words per f16 row (dim % 8 == 0 on this path)
   const uint4* src = reinterpret_cast<const uint4*>(x_row(x, x.rank)) + (size_t)(target == ROW_NONE ? 0u : target) * words;
   uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)g * words;
@@ -325,8 +340,7 @@ __global__ void __launch_bounds__(256) k_owner_update(TableDev t, OptimDev op, H
 // ------------------------------------------------------------------------------------------------
 void launch_route_items(bool training, const SlotsDev& sl, const BatchDev& b, const XchgDev& x, cudaStream_t st) {
   if (!b.n) return;
-  const uint32_t full = cdiv(b.n, 256);
-  const uint32_t grid = full < 148u * 4u ? full : 148u * 4u;
+  const uint32_t grid = cdiv(b.n, 256);  // worst case U = N; blocks past the item count return at once
   if (training) PB_LAUNCH_F(FAM_PROBE, (k_route_items<true>), grid, 256, 0, st, sl, b, x);
   else PB_LAUNCH_F(FAM_PROBE, (k_route_items<false>), grid, 256, 0, st, sl, b, x);
 }
@@ -358,7 +372,8 @@ void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& 
   if (!row_off && !x.row_f32 && t.dim % 8 == 0) {
     uint32_t words = t.dim / 8, lanes = 1;
     while (lanes < words && lanes < 32) lanes <<= 1;
-    const uint32_t grid = cdiv((uint64_t)n_out * lanes, 256);
+    uint32_t grid = cdiv((uint64_t)n_out * lanes, 256);
+    if (grid < cdiv(n_out, 256)) grid = cdiv(n_out, 256);
     if (training) PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<true>), grid, 256, 0, st, t.dim, b, x, n_out, out, lanes);
     else PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<false>), grid, 256, 0, st, t.dim, b, x, n_out, out, lanes);
     return;

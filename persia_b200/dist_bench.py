@@ -1,8 +1,15 @@
-"""Multi-GPU leg of bench.py: R ranks, rows hash-sharded by farmhash64(sign) % R, data-parallel batches,
-forward / backward all-to-all over NCCL (BASELINE configs[2..3]).  Weak scaling: every rank keeps
-`--rows` resident rows and a batch of `--batch` samples."""
+"""Multi-GPU leg of bench.py: R ranks (one process per GPU), rows hash-sharded by farmhash64(sign) % R, data-parallel
+batches, the exchange fused into the kernels over NVLink peer memory (BASELINE configs[2..3]).  Weak scaling: every rank
+keeps `--rows` resident rows and a batch of `--batch` samples (dim 128 by default: the metric's config).
+
+What is timed is one CUDA graph per rank and buffer set holding the whole step (pb_forward_sharded + pb_backward_sharded:
+compute kernels, peer stores, flag waits).  After the timed loops the same captured graphs are replayed from the live
+tables and checked against the oracle (R parameter servers, the R ranks' requests applied in rank order): outputs and
+every row this rank owns among the touched ones, bit for bit — `parity_checked`."""
 import json
 import os
+import sys
+import threading
 import time
 
 import numpy as np
@@ -10,11 +17,56 @@ import torch
 import torch.distributed as dist
 
 
-def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampler, cpu_arm):
+def _check_parity(rank, world, wk, replay, outs, all_ids, all_grads, pf, S, B, dim, dev, sets):
+    """Every rank runs its own oracle worker with R parameter servers over ALL ranks' check batches (inputs are
+    regenerated from their seeds), seeds only ITS shard with the live rows and compares only what it owns: rows of one
+    shard never depend on another shard's.  Forward outputs are compared where the sign is owned by this rank."""
+    import oracle
+
+    owned = []
+    for k in sets:
+        for q in range(world):
+            sg = np.concatenate([oracle.add_prefix(all_ids[q][k][i * B:(i + 1) * B], 8, pf[i]) for i in range(S)])
+            owned.append(sg[oracle.shard_of(sg, world) == rank])
+    signs = np.unique(np.concatenate(owned))
+    d_signs = torch.from_numpy(signs.view(np.int64)).to(dev)
+    ent, found = wk.shard.get_entries(d_signs)
+    found = found.cpu().numpy()
+    w = oracle.Worker([oracle.SlotCfg(dim, prefix=p) for p in pf], n_ps=world, capacity_per_ps=1 << 40)
+    w.configure()
+    w.set_optimizer(oracle.Optim(oracle.ADAGRAD, lr=0.01, init_acc=0.01, eps=1e-10))
+    w.set_embedding(signs[found], ent.cpu().numpy()[found], dim)  # signs not resident yet are admitted by both sides
+    oracle.set_rsqrt_exact(True)
+    bad_out = 0
+    try:
+        row_off = np.arange(S * B + 1, dtype=np.uint32)
+        for k in sets:
+            dist.barrier()
+            replay(k)
+            torch.cuda.synchronize()
+            dist.barrier()
+            octx = [w.forward(all_ids[q][k], row_off, B, training=True) for q in range(world)]
+            got = outs[k].cpu().numpy()
+            mine = np.concatenate([oracle.add_prefix(all_ids[rank][k][i * B:(i + 1) * B], 8, pf[i]) for i in range(S)])
+            mask = (oracle.shard_of(mine, world) == rank).reshape(S, B)
+            for i in range(S):
+                bad_out += int((got[i][mask[i]].view(np.uint16) != octx[rank][0][i][mask[i]].view(np.uint16)).any(axis=1).sum())
+            for q in range(world):  # the owner applies the R requests in rank order
+                w.backward(octx[q][1], [all_grads[q][k][i] for i in range(S)])
+        ent2, found2 = wk.shard.get_entries(d_signs)
+        ent2 = ent2.cpu().numpy()
+        assert bool(found2.all())
+        bad_rows = sum(ent2[j].tobytes() != w.get_entry(int(s)).tobytes() for j, s in enumerate(signs))
+    finally:
+        oracle.set_rsqrt_exact(False)
+    return bad_out, bad_rows, int(signs.size)
+
+
+def run(args, rank, local_rank, world, B_):
     from . import native as N
     from . import shard as SH
     from . import workload as W
-    from .worker import CudaBackend, ShardedEmbeddingWorker
+    from .worker import ShardedEmbeddingWorker
 
     dev = torch.device("cuda", local_rank)
     # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the one JSON line
@@ -29,100 +81,74 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
         os.dup2(saved, 1)
         os.close(saved)
     lib = N.load()
-    dim = args.dim or 64
+    dim = args.dim
     S, B, K, Wm = args.slots, args.batch, args.steps, max(args.warmup, 3)
-    rows_total = int(args.rows) * world
-    card = W.scaled_cardinalities(rows_total, S)
+    rows = int(args.rows)
+    ks = B_.keyspace_per_gpu(args)
+    bounded = ks > rows
+    card = W.scaled_cardinalities(int(ks) * world, S)       # the key space the ids are drawn from
+    fill_card = W.scaled_cardinalities(rows * world, S)      # what is made resident before timing
     pf = W.index_prefixes(S)
     n_occ = S * B
-    cap = int(int(args.rows) * 1.02) + 4096
-    be = CudaBackend(dim, cap, dev, dict(kind=N.OPT_ADAGRAD, lr=0.01, initialization=0.01, eps=1e-10), {},
-                     max_occurrences=max(4 * n_occ, 1 << 16))
-    wk = ShardedEmbeddingWorker(S, dim, pf, be)
-
+    n_sets = max(2, args.sets)
+    all_ids = None
+    ids_host = W.make_batches(100 + rank, card, B, n_sets, args.alpha)  # every rank draws its own samples
+    cap = ShardedEmbeddingWorker.calibrate_cap([ids_host[k] for k in range(n_sets)], B, pf, world)
+    table_cap = int(rows * 1.02) + 4096
+    wk = ShardedEmbeddingWorker.distributed(S, dim, pf, table_cap, cap, dict(kind=N.OPT_ADAGRAD, lr=0.01, initialization=0.01, eps=1e-10),
+                                            dev, max_batch=B)
     # ---- make this rank's share of every slot resident
     t_fill = time.time()
-    chunk = 1 << 21
-    buf = torch.empty((chunk, dim), dtype=torch.float32, device=dev)
-    for s in range(S):
-        for lo in range(0, int(card[s]), chunk):
-            hi = min(int(card[s]), lo + chunk)
-            ids = torch.arange(lo, hi, dtype=torch.int64, device=dev)
-            signs = SH.add_prefix(ids, [0, hi - lo], [pf[s]])
-            mine = signs[SH.shard_of(signs, world) == rank].contiguous()
-            if mine.numel():
-                be.shard.lookup(mine, training=True, out=buf[: mine.numel()])
-    torch.cuda.synchronize()
-    resident = len(be.shard)
+    B_.fill_table(torch, SH, wk.shard, fill_card, pf, dev, dim, owner=(rank, world))
+    resident = len(wk.shard)
     t_fill = time.time() - t_fill
-    del buf
     tot = torch.tensor([resident], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
-    assert int(tot) == rows_total, (int(tot), rows_total)
-    assert be.shard.counters()["capacity_refused"] == 0
+    assert int(tot) == rows * world, (int(tot), rows * world)
+    assert wk.shard.counters()["capacity_refused"] == 0
+    if bounded:  # configs[3]: ids from a key space far larger than the table; least recently used rows make room
+        free_now = table_cap - resident
+        wk.shard.set_eviction(check_every=1, low_water=max(1 << 20, free_now // 2), target_free=max(1 << 22, 2 * free_now),
+                              keep_batches=2)
 
-    n_sets = max(2, args.sets)
-    ids_host = W.make_batches(100 + rank, card, B, n_sets, args.alpha)  # every rank draws its own samples
     ids_pinned = torch.from_numpy(ids_host.view(np.int64)).pin_memory()
     ids_dev = [ids_pinned[k].to(dev) for k in range(n_sets)]
     g = torch.Generator(device=dev)
     g.manual_seed(5 + rank)
     grads = (torch.randn((n_sets, S, B, dim), generator=g, device=dev) * 1e-2).half()
-
-    static = not args.dist_dynamic
-    mode = "dynamic"
+    outs = [torch.empty((S, B, dim), dtype=torch.float16, device=dev) for _ in range(n_sets)]
     gstream = torch.cuda.Stream(device=dev)
-    if static:
-        # slots per GPU pair: sized from the batches themselves (+10 %); a production loop sizes it on its warm-up
-        # batches and re-runs a batch that raises the overflow flag with a larger capacity
-        wk.enable_static(B, cap=wk.calibrate_cap(ids_dev, B))
-        mode = "nccl-framed"
-    if static and not args.dist_nccl:
-        try:
-            wk.enable_p2p(B)
-            mode = "p2p"
-            be.ctx.set_async_grouping(True)  # forward and backward of a step share one capture: the grouping may overlap
-        except Exception as e:  # noqa: BLE001 — no symmetric memory on this box: NCCL framed path
-            print(f"[bench] peer-memory exchange unavailable ({e!r}); using NCCL", file=__import__("sys").stderr)
+    wk.stream = gstream
 
     def eager_step(k):
-        if mode == "p2p":
-            wk.forward_p2p(ids_dev[k], B, training=True)
-            wk.backward_p2p(grads[k])
-        elif mode == "nccl-framed":
-            wk.forward_static(ids_dev[k], B, training=True)
-            wk.backward_static(grads[k])
-        else:
-            wk.forward(ids_dev[k], B, training=True)
-            wk.backward(grads[k])
+        wk.forward(ids_dev[k], B, training=True, out=outs[k])
+        wk.backward(grads[k])
 
-    graphs, seg_steps = None, None
-    if mode == "p2p" and not args.no_graph:
-        # kernels + peer-memory exchanges + flag barriers of a whole step: one CUDA graph per buffer set, no NCCL inside
-        with torch.cuda.stream(gstream):
-            for i in range(3):
-                eager_step(i % n_sets)
-            gstream.synchronize()
-            dist.barrier()
+    # kernels + peer stores + flag waits of a whole step: one CUDA graph per rank and buffer set, no NCCL inside
+    with torch.cuda.stream(gstream):
+        for i in range(3):
+            eager_step(i % n_sets)
+        gstream.synchronize()
+        l0 = lib.pb_launch_count()
+        eager_step(0)
+        launches_per_step = int(lib.pb_launch_count() - l0)
+        gstream.synchronize()
+        dist.barrier()
+        graphs = None
+        if not args.no_graph:
             graphs = []
             for k in range(n_sets):
                 gph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gph, stream=gstream, capture_error_mode="thread_local"):
                     eager_step(k)
                 graphs.append(gph)
-        torch.cuda.synchronize()
-        dist.barrier()
-    elif mode == "nccl-framed" and not args.no_graph:
-        seg_steps = [wk.make_graphed_step(ids_dev[k], grads[k], B, gstream)[0] for k in range(n_sets)]
-        torch.cuda.synchronize()
-        dist.barrier()
+    torch.cuda.synchronize()
+    dist.barrier()
 
     def step(k):
         with torch.cuda.stream(gstream):
             if graphs is not None:
                 graphs[k].replay()
-            elif seg_steps is not None:
-                seg_steps[k]()
             else:
                 eager_step(k)
 
@@ -130,11 +156,10 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tstream = gstream if fn is step else torch.cuda.current_stream()
-        e0.record(tstream)
+        e0.record(gstream)
         for i in range(n):
             fn(i % n_sets)
-        e1.record(tstream)
+        e1.record(gstream)
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
@@ -144,10 +169,9 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
     for i in range(Wm):
         step(i % n_sets)
     torch.cuda.synchronize()
-    l0 = lib.pb_launch_count()
-    step(0)
-    launches_per_step = int(lib.pb_launch_count() - l0)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    stats = wk.ctx.batch_stats()
+    admitted0 = len(wk.shard)
+    sampler = B_.ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
@@ -155,109 +179,146 @@ def run(args, rank, local_rank, world, METRIC, UNIT, workload_config, ClockSampl
     ms = timed(step, K)
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
+    reps = [timed(step, K) / K for _ in range(3)]
 
+    # ---- e2e: pinned host ids -> H2D -> sharded forward + backward -> D2H of the slot status, host sync every step;
+    # the same captured graph mechanism, with the copies inside
     ids_stage = torch.empty(n_occ, dtype=torch.int64, device=dev)
-    probe_host = torch.empty(4, dtype=torch.float16).pin_memory()
+    status_host = torch.empty(S, dtype=torch.int32).pin_memory()
+    status_dev = torch.empty(S, dtype=torch.int32, device=dev)
+
+    def e2e_body(k):
+        ids_stage.copy_(ids_pinned[k], non_blocking=True)
+        wk.forward(ids_stage, B, training=True, out=outs[0])
+        wk.backward(grads[k], want_status=True, status=status_dev)
+        status_host.copy_(status_dev, non_blocking=True)
+
+    e2e_graphs = None
+    with torch.cuda.stream(gstream):
+        e2e_body(0)
+        gstream.synchronize()
+        dist.barrier()
+        if not args.no_graph:
+            e2e_graphs = []
+            for k in range(n_sets):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=gstream, capture_error_mode="thread_local"):
+                    e2e_body(k)
+                e2e_graphs.append(gph)
+    torch.cuda.synchronize()
+    dist.barrier()
 
     def e2e_step(k):
-        ids_stage.copy_(ids_pinned[k], non_blocking=True)
-        if mode == "p2p":
-            out = wk.forward_p2p(ids_stage, B, training=True)
-            wk.backward_p2p(grads[k])
-        elif mode == "nccl-framed":
-            out = wk.forward_static(ids_stage, B, training=True)
-            wk.backward_static(grads[k])
-        else:
-            out = wk.forward(ids_stage, B, training=True)
-            wk.backward(grads[k])
-        probe_host.copy_(out.view(-1)[:4], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(gstream):
+            if e2e_graphs is not None:
+                e2e_graphs[k].replay()
+            else:
+                e2e_body(k)
+        gstream.synchronize()
 
     for i in range(Wm):
         e2e_step(i % n_sets)
     ms_e2e = timed(e2e_step, K)
+    admitted1 = len(wk.shard)
+    counters = wk.shard.counters()
 
-    breakdown = None
-    if mode == "nccl-framed" and os.environ.get("PB_DIST_BREAKDOWN"):
-        # eager framed step with CUDA events between its segments (diagnostic; rank 0's view)
-        names = ["prefix+partition+frame", "a2a signs", "owner forward", "a2a rows", "unframe", "frame grads", "a2a grads", "owner backward"]
-        acc = [0.0] * len(names)
-        S_, R_, cap_ = S, world, wk.cap
-        for it in range(20):
-            k = it % n_sets
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-            slot_off = [s * B for s in range(S_ + 1)]
-            ev[0].record()
-            signs = be.add_prefix(ids_dev[k], slot_off, pf, 8)
-            perm, counts = be.partition(signs, R_)
-            send = be.frame_signs(signs, perm, counts, R_, cap_, wk.overflow)
-            ev[1].record()
-            recv = wk._a2a_equal(send)
-            ev[2].record()
-            rows = be.serve_lookup(recv, True)
-            ev[3].record()
-            back = wk._a2a_equal(rows)
-            ev[4].record()
-            out = be.frame_rows(back, perm, counts, R_, cap_, False, be.empty_rows(n_occ))
-            ev[5].record()
-            gs = be.frame_rows(grads[k].reshape(n_occ, dim), perm, counts, R_, cap_, True, be.empty_rows(R_ * cap_, grads.dtype))
-            ev[6].record()
-            gr = wk._a2a_equal(gs)
-            ev[7].record()
-            be.serve_update(gr, 1.0)
-            ev[8].record()
+    overflowed, gave_up = wk.status()
+    assert not overflowed, "a (source, owner) pair needed more than cap slots: raise the margin of calibrate_cap"
+    assert not gave_up and counters["wait_errors"] == 0, "a wait for a peer gave up: the run is void"
+
+    parity = None
+    if not args.no_parity:
+        sets = (0, 1)
+        all_ids = [W.make_batches(100 + q, card, B, n_sets, args.alpha) if q != rank else ids_host for q in range(world)]
+        all_grads = []
+        for q in range(world):
+            gq = torch.Generator(device=dev)
+            gq.manual_seed(5 + q)
+            full = (torch.randn((n_sets, S, B, dim), generator=gq, device=dev) * 1e-2).half()
+            all_grads.append({k: full[k].cpu().numpy() for k in sets})
+            del full
+        replay = step
+        if bounded:
+            # a sweep between seeding the oracle and the check would re-admit a seeded sign from scratch on the GPU only:
+            # the check replays graphs captured with the sweep switched off (same kernels otherwise)
+            wk.shard.set_eviction(check_every=0)
+            chk = {}
+            with torch.cuda.stream(gstream):
+                for k in sets:
+                    gph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gph, stream=gstream, capture_error_mode="thread_local"):
+                        eager_step(k)
+                    chk[k] = gph
             torch.cuda.synchronize()
-            if it >= 4:
-                for i in range(len(names)):
-                    acc[i] += ev[i].elapsed_time(ev[i + 1]) * 1e3 / 16
-        breakdown = {n: round(v, 1) for n, v in zip(names, acc)}
-    overflowed = wk.check_overflow() if static else False
-    assert not overflowed, "framed exchange overflowed its capacity: raise the slack"
-    if mode == "p2p":
-        assert not wk.check_p2p(), "a peer-memory barrier timed out"
+            dist.barrier()
+
+            def replay(k):
+                with torch.cuda.stream(gstream):
+                    chk[k].replay()
+        bad_out, bad_rows, n_rows = _check_parity(rank, world, wk, replay, outs, all_ids, all_grads, pf, S, B, dim, dev, sets)
+        res = torch.tensor([bad_out, bad_rows, n_rows], dtype=torch.int64, device=dev)
+        dist.all_reduce(res)
+        if int(res[0]) or int(res[1]):
+            raise AssertionError(f"parity: {int(res[0])} output rows and {int(res[1])} table rows differ from the oracle")
+        parity = {"checked": True, "steps_replayed": len(sets), "rows_compared": int(res[2]),
+                  "what": ("CUDA graphs of the same step captured with the capacity sweep switched off, " if bounded else "the timed CUDA graphs ") +
+                          "replayed from the live tables on every rank; each rank's shard and the "
+                          "outputs it serves are bit-identical to the oracle (R parameter servers, the R requests of a "
+                          "step applied in rank order)"}
+
     if rank == 0:
         ms_per_step = ms / K
         GB = B * world
-        state = dim
-        bytes_per_id = W.algorithmic_bytes_per_id(dim, state, "total")
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        whole = n_occ * bytes_per_id / (ms_per_step * 1e-3) / 1e9  # per GPU
+        peak, peak_src = B_.peak_hbm()
+        by = B_.kernel_bytes(stats, dim, dim)
+        whole = by["whole_step"] / (ms_per_step * 1e-3) / 1e9  # per GPU, measured multiplicities of rank 0's batch
         line = {
-            "metric": METRIC, "value": GB / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "metric": B_.METRIC, "value": GB / (ms_per_step * 1e-3), "unit": B_.UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, dim, card, world), resident_rows_rank0=resident,
-                           table_fill_seconds=round(t_fill, 2),
-                           l2="inputs larger than L2: %.1f GB table per GPU + %d rotating id/grad sets" % (
-                               resident * 4.0 * (dim + state) / 1e9, n_sets),
-                           launch={"p2p": "framed exchange (cap %d slots per GPU pair) stored straight into the peers' buffers over NVLink by "
-                                          "libpersia_b200's own kernels + flag barriers; %s" % (
-                                              getattr(wk, "cap", 0), "whole step = one CUDA graph per rank" if graphs is not None else "kernel by kernel"),
-                                   "nccl-framed": "framed exchange (cap %d) over NCCL all_to_all_single; %s" % (
-                                       getattr(wk, "cap", 0), "compute segments replay as CUDA graphs" if seg_steps is not None else "kernel by kernel"),
-                                   "dynamic": "NCCL all_to_all_single with split sizes; one host sync per step"}[mode]),
+            "config": B_.workload_config(args),
+            "run": {"ms_per_step_repetitions": reps, "resident_rows_rank0": resident, "table_fill_seconds": round(t_fill, 2),
+                    "l2": "inputs larger than L2: %.1f GB table per GPU + %d rotating id/grad/output sets" % (
+                        resident * 4.0 * 2 * dim / 1e9, n_sets),
+                    "exchange": "slots per (source, owner) pair: %d (calibrated on the batches, +15%%); distinct signs per "
+                                "batch on rank 0: %d of %d occurrences" % (cap, stats["items"], stats["occurrences"]),
+                    "launch": "whole step (compute kernels, peer stores, flag waits) = one CUDA graph per rank" if graphs is not None else "kernel by kernel",
+                    "eviction": None if not bounded else {
+                        "policy": "sweep when free rows < low water; rows of the last 2 batches are protected",
+                        "resident_rows_rank0_before_after_e2e_loop": [int(admitted0), int(admitted1)],
+                        "index_miss_count_rank0": int(counters["lookup_miss"]), "capacity_refused_rank0": int(counters["capacity_refused"])}},
             "clocks": clocks,
-            "e2e": {"value": GB / (ms_e2e / K * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8 * world,
-                    "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / K,
-                    "path": "pinned host ids -> H2D -> ShardedEmbeddingWorker.forward/backward -> D2H of 4 output "
-                            "values, host sync every step"},
+            "e2e": {"value": GB / (ms_e2e / K * 1e-3), "unit": B_.UNIT, "h2d_bytes_per_step": n_occ * 8 * world,
+                    "d2h_bytes_per_step": S * 4 * world, "ms_per_step": ms_e2e / K,
+                    "path": "pinned host ids -> H2D -> pb_forward_sharded -> pb_backward_sharded -> D2H slot status (one CUDA "
+                            "graph per rank), host sync every step"},
             "gpu_launches": launches_per_step * K,
-            "roofline": {"bound": "hbm", "kernel": "whole step per GPU (multi-GPU runs report no per-kernel split)",
+            "parity_checked": bool(parity and parity["checked"]), "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": "whole step per GPU (the per-kernel roofline is the N = 1 run's)",
                          "achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak, "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+                         "peak_source": peak_src, "batch_stats_rank0": stats,
+                         "bytes_model": "measured multiplicities of rank 0's batch (see bench.py kernel_bytes); NVLink bytes not counted"},
             "cpu_baseline": None,
-            "segments_us": breakdown,
         }
         print(json.dumps(line))
+        sys.stdout.flush()
+    # ---- orderly teardown: graphs first (they reference the exchange areas), then the worker, then the process group;
+    # a watchdog ends the process if a driver-level teardown stalls after everything has been reported
+    done = threading.Event()
+
+    def watchdog():
+        if not done.wait(60):
+            sys.stderr.write("[bench] teardown stalled: exiting\n")
+            sys.stderr.flush()
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
     dist.barrier()
     torch.cuda.synchronize()
-    import sys
-
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)  # CUDA graphs + NCCL teardown order is fragile; everything has been reported
+    del graphs, e2e_graphs
+    torch.cuda.synchronize()
+    wk.close()
+    del wk
+    dist.barrier()
+    dist.destroy_process_group()
+    done.set()

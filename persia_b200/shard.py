@@ -55,8 +55,8 @@ class EmbeddingShard:
 
     def set_eviction(self, check_every=4, low_water=None, target_free=None, keep_batches=2):
         """Recency-based capacity policy (EvictionMap semantics, batch-granular); see persia_b200.h."""
-        low = self.capacity // 16 if low_water is None else low_water
-        tgt = self.capacity // 8 if target_free is None else target_free
+        low = (self.capacity // 16 if low_water is None else low_water) if check_every else 0
+        tgt = (self.capacity // 8 if target_free is None else target_free) if check_every else 0
         N.check(self.lib.pb_table_set_eviction(self.h, check_every, low, tgt, keep_batches))
 
     @property

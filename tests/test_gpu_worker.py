@@ -155,7 +155,9 @@ def test_virtual_ranks_ragged_sqrt_scale(torch_cuda, oracle):
             octx.append(c)
             got = outs[r].cpu().numpy()
             for i in range(S):
-                assert f16_ulp_diff(got[i], want[i]) <= 1  # f32 sum order of a sample's ids differs (shard order there)
+                # the f32 sum order of a sample's ids differs (sample order here, shard order there): one f16 step of the
+                # largest summand (trained rows reach +-8 in this test and cancel inside a sample)
+                np.testing.assert_allclose(got[i].astype(np.float32), want[i].astype(np.float32), rtol=2e-3, atol=8e-3)
                 seen.update(w.ctx_signs(c, i).tolist())
         g = (rng.integers(-64, 65, size=(R, S, B, dim)) / 4.0).astype(np.float16)  # x 1/128 stays exact in f32
         scale = [128.0, 1.0, 128.0, 1.0]
