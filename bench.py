@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=float(os.environ.get("PB_BENCH_CPU_SECONDS", 12)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline-leg", action="store_true", help="N = 1: skip the configs[1] (dim 64) leg")
+    ap.add_argument("--no-model-leg", action="store_true", help="N = 1: skip the TrainCtx + DLRM tower leg (e2e_model)")
     ap.add_argument("--no-parity", action="store_true", help="skip the replay of captured steps against the oracle")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
@@ -266,9 +267,9 @@ def b200_main(args):
     torch.cuda.set_device(local_rank)
     N.load()
     if world > 1:
-        from persia_b200 import dist_bench
+        import bench_dist
 
-        return dist_bench.run(args, rank, local_rank, world, sys.modules[__name__])
+        return bench_dist.run(args, rank, local_rank, world, sys.modules[__name__])
     return single_gpu(args, torch)
 
 
@@ -566,6 +567,60 @@ def roofline_from(leg, peak, peak_src, label):
     }
 
 
+def model_leg(args, torch, steps, warmup):
+    """e2e_model: the same sparse path driven the way a user drives it — persia_b200.api.TrainCtx (the persia.ctx API)
+    with a DLRM-style PyTorch dense tower: host numpy batch -> PersiaBatch -> get_embedding_from_data -> model forward
+    -> BCE loss -> ctx.backward (dense SGD step + sparse Adagrad update), every step, wall clock around the loop."""
+    from persia_b200 import api
+    from persia_b200 import persia_core as PC
+
+    S, B, dim, n_dense = args.slots, args.batch, args.dim, 13
+    names = [f"C{i + 1}" for i in range(S)]
+    PC.reset()
+    PC._S.capacity = int(min(args.rows, 2e7)) + 1024
+    PC.set_embedding_config({"slots_config": {n: {"dim": dim} for n in names}})
+    card = W.scaled_cardinalities(int(min(args.rows, 2e7)), S)
+    torch.manual_seed(0)
+    model = W.make_dlrm_tower(S, dim, n_dense=n_dense).cuda()
+    dense_opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    loss_fn = torch.nn.BCEWithLogitsLoss()
+    n_pool = 8
+    ids_pool = W.make_batches(7, card, B, n_pool, args.alpha).reshape(n_pool, S, B)
+    rng = np.random.default_rng(11)
+    dense_pool = rng.standard_normal((n_pool, B, n_dense)).astype(np.float32)
+    label_pool = (rng.random((n_pool, B, 1)) < 0.25).astype(np.float32)
+    losses = []
+    with api.TrainCtx(model=model, embedding_optimizer=api.Adagrad(lr=0.01, initial_accumulator_value=0.01, eps=1e-10),
+                      dense_optimizer=dense_opt, device_id=torch.cuda.current_device(), mixed_precision=False) as ctx:
+        def step(k):
+            pb = api.PersiaBatch([api.IDTypeFeatureWithSingleID(names[i], ids_pool[k, i]) for i in range(S)],
+                                 non_id_type_features=[api.NonIDTypeFeature(dense_pool[k], name="dense")],
+                                 labels=[api.Label(label_pool[k], name="click")], requires_grad=True)
+            tb = ctx.get_embedding_from_data(pb)
+            out, labels = ctx.forward(tb)
+            loss = loss_fn(out, labels[0].squeeze(1))
+            ctx.backward(loss)
+            return loss
+
+        for i in range(warmup):
+            step(i % n_pool)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for i in range(steps):
+            losses.append(step(i % n_pool))
+        ctx.backward_engine.flush()
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+    res = {"value": B * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps, "steps": steps,
+           "first_loss": float(losses[0]), "last_loss": float(losses[-1]),
+           "path": f"numpy batch -> api.PersiaBatch -> TrainCtx.get_embedding_from_data -> DLRM tower ({sum(p.numel() for p in model.parameters())} "
+                   f"dense parameters, fp32) -> BCE -> TrainCtx.backward (dense SGD + sparse Adagrad); {int(min(args.rows, 2e7)):.3g}-id key space, "
+                   "rows admitted on the fly", "h2d_bytes_per_step": S * B * 8 + B * n_dense * 4 + B * 4}
+    PC.reset()
+    torch.cuda.empty_cache()
+    return res
+
+
 def single_gpu(args, torch):
     peak, peak_src = peak_hbm()
     rows = int(args.rows)
@@ -584,6 +639,9 @@ def single_gpu(args, torch):
                                                               "unique_fraction", "batch_stats")}
     else:
         roofline = metric_roof
+    e2e_model = None
+    if not args.no_model_leg:
+        e2e_model = model_leg(args, torch, steps=min(K, 50), warmup=10)
     cpu = None
     if not args.no_cpu_baseline:
         c = cpu_arm(args, args.cpu_seconds)
@@ -606,6 +664,7 @@ def single_gpu(args, torch):
         "e2e": {"value": B / (leg["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8,
                 "d2h_bytes_per_step": S * 4, "ms_per_step": leg["ms_e2e"],
                 "path": "pinned host ids -> H2D -> pb_forward -> pb_backward -> D2H slot status, host sync every step"},
+        "e2e_model": e2e_model,
         "gpu_launches": leg["launches_per_step"] * K,
         "parity_checked": bool(leg["parity"] and leg["parity"]["checked"]), "parity": leg["parity"],
         "roofline": roofline,

@@ -1,4 +1,5 @@
-"""Multi-GPU leg of bench.py: R ranks (one process per GPU), rows hash-sharded by farmhash64(sign) % R, data-parallel
+"""bench_dist.py — multi-GPU leg of bench.py (bench infrastructure, not part of the persia_b200 package: it uses the
+oracle as a checker).   R ranks (one process per GPU), rows hash-sharded by farmhash64(sign) % R, data-parallel
 batches, the exchange fused into the kernels over NVLink peer memory (BASELINE configs[2..3]).  Weak scaling: every rank
 keeps `--rows` resident rows and a batch of `--batch` samples (dim 128 by default: the metric's config).
 
@@ -63,10 +64,10 @@ def _check_parity(rank, world, wk, replay, outs, all_ids, all_grads, pf, S, B, d
 
 
 def run(args, rank, local_rank, world, B_):
-    from . import native as N
-    from . import shard as SH
-    from . import workload as W
-    from .worker import ShardedEmbeddingWorker
+    from persia_b200 import native as N
+    from persia_b200 import shard as SH
+    from persia_b200 import workload as W
+    from persia_b200.worker import ShardedEmbeddingWorker
 
     dev = torch.device("cuda", local_rank)
     # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the one JSON line

@@ -539,6 +539,8 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   A((void**)&c->b.cold, 8 * n);
   A((void**)&c->b.warm, 16 * (n / 2 + 1));
   A((void**)&c->b.hot, 16 * (n / (PB_WARM_MAX + 1) + 1));
+  c->b.hot_words = (uint32_t)(n < 4096 ? 4096 : n);  // 32 bits of pool per id occurrence the context can hold
+  A((void**)&c->b.hot_bits, 4 * (size_t)c->b.hot_words);
   A((void**)&c->b.cnt, 4 * BC_COUNT);
   A((void**)&c->occ_cell, 4 * n);
   A((void**)&c->occ_outrow, 4 * n);
@@ -548,6 +550,7 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   if (e == cudaSuccess) e = cudaMemset(c->nan_tick, 0, 4 * PB_MAX_SLOTS);
   if (e == cudaSuccess) e = cudaMemset(c->dev_tick, 0, 4);
   if (e == cudaSuccess) e = cudaMemset(c->b.cnt, 0, 4 * BC_COUNT);
+  if (e == cudaSuccess) e = cudaMemset(c->b.hot_bits, 0, 4 * (size_t)c->b.hot_words);
   if (e == cudaSuccess) {
     launch_fill_set(c->b.set, c->set_cells, 0);
     e = cudaDeviceSynchronize();
@@ -569,7 +572,7 @@ int pb_ctx_destroy(pb_ctx* c) {
   DeviceGuard g(c->device);
   cudaDeviceSynchronize();
   drop_pending(c);
-  void* ptrs[] = {c->b.set,   c->b.occ_set, c->b.item_cell, c->b.seg_occ, c->b.cold, c->b.warm, c->b.hot, c->b.cnt,
+  void* ptrs[] = {c->b.set,   c->b.occ_set, c->b.item_cell, c->b.seg_occ, c->b.cold, c->b.warm, c->b.hot, c->b.hot_bits, c->b.cnt,
                   c->occ_cell, c->occ_outrow, c->row_off, c->nan_tick, c->vw_stage, c->dev_tick, c->raw.set,
                   c->raw.occ_set, c->raw.flag, c->raw.rank, c->raw.tiles, c->raw.distinct_cell, c->raw.counts, c->raw_stage};
   for (void* p : ptrs)
@@ -648,6 +651,7 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
     launch_clear_items(c->b, st);
     c->set_dirty = false;
   }
+  if (c->pending) launch_clear_hot_bits(c->b, st);  // its hot items' bitmaps were never consumed
   drop_pending(c);  // like an expired post_forward_buffer entry (mod.rs:991-1029)
   if (training) {
     if ((rc = maybe_evict(t, st))) return rc;
@@ -655,7 +659,7 @@ int pb_forward(pb_table* t, pb_ctx* c, const uint64_t* d_ids, uint32_t n_occ, co
   launch_begin_batch(t->d, training ? c->dev_tick : nullptr, c->b.cnt, st, training != 0);
   c->b.n = n_occ;
   launch_dedup(sl, c->b, d_ids, st);
-  launch_probe_items(training != 0, t->d, t->hy, t->op, c->b, st);
+  launch_probe_items(training != 0, t->d, t->hy, t->op, sl, c->b, st);
   launch_gather_items(t->d, sl, c->b, d_row_off, (uint32_t)n_out, batch, training != 0, d_out_f16, st);
   if (training) {
     c->n_occ = n_occ;
@@ -878,6 +882,7 @@ int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids
       launch_clear_items(c->b, st);
       c->set_dirty = false;
     }
+    if (c->pending) launch_clear_hot_bits(c->b, st);
     drop_pending(c);
     if (training) {
       if ((rc = maybe_evict(t, st))) return rc;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_dedup(SlotsDev sl, BatchDev b, const ui
 // Persistent grid: the number of items lives on the device.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) k_probe_items(TableDev t, HyperDev hy, OptimDev op, BatchDev b) {
+__global__ void __launch_bounds__(256, 4) k_probe_items(TableDev t, HyperDev hy, OptimDev op, SlotsDev slots, BatchDev b) {
   const uint32_t tick = t.counters[CTR_TICK];
   const uint32_t n_items = b.cnt[BC_ITEMS];
   if (blockIdx.x * (blockDim.x / BUCKET) >= n_items) return;  // whole block (the grid is sized for the worst case)
@@ -117,13 +117,18 @@ __global__ void __launch_bounds__(256, 4) k_probe_items(TableDev t, HyperDev hy,
   const ProbeOut r = probe_group<MODE>(t, hy, op, sign, valid, tick, sub, gshift);
   const bool head = valid && sub == 0;
   if (MODE != MODE_TRAIN) cnt = 0;  // inference: nothing is kept for a backward
-  const ItemSlots sl = block_item_slots(b, head, cnt);
+  uint32_t slot = 0, hot_nwords = 0;
+  if (head && cnt > PB_WARM_MAX) {
+    slot = slot_of_occ(slots, first);
+    hot_nwords = (slots.occ_off[slot + 1] - slots.occ_off[slot] + 31u) / 32u;
+  }
+  const ItemSlots sl = block_item_slots(b, head, cnt, hot_nwords);
   if (head) {
     *(reinterpret_cast<uint2*>(&b.set[cell]) + 2) = make_uint2(r.row, sl.base);  // target, base
     if (r.row == ROW_NONE && MODE != MODE_SET) atomicAdd(&t.counters[CTR_MISS], 1u);  // index_miss_count, per distinct sign
     if (sl.cls == 1) b.cold[sl.pos] = make_uint2(r.row, first);
     else if (sl.cls == 2) b.warm[sl.pos] = make_uint4(r.row, sl.base, cnt, 0u);
-    else if (sl.cls == 3) b.hot[sl.pos] = make_uint4(r.row, sl.base, cnt, 0u);
+    else if (sl.cls == 3) b.hot[sl.pos] = make_uint4(r.row, sl.base, cnt, slot);
   }
 }
 
@@ -146,43 +151,6 @@ __device__ __forceinline__ void store_f16(__half* dst, const float (&acc)[VEC], 
   }
 }
 
-// what the gather needs of an occurrence's set cell: one 16 B load (target, base) + count/cursor when filing
-struct OccRef {
-  uint32_t row, base, count;
-};
-__device__ __forceinline__ OccRef occ_ref(const BatchDev& b, uint32_t cell) {
-  const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);           // key (2 words), count, cursor
-  const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);     // target, base, first, item
-  OccRef r;
-  r.row = hi.x;
-  r.base = hi.y;
-  r.count = lo.z;
-  return r;
-}
-__device__ __forceinline__ void file_occurrence(const BatchDev& b, uint32_t cell, const OccRef& r, uint32_t occ) {
-  if (r.count > 1) b.seg_occ[r.base + atomicAdd(&b.set[cell].cursor, 1u)] = occ;
-}
-// the same for 32 consecutive occurrences at once, one per lane: occurrences of one sign share ONE atomic (a sign
-// repeated thousands of times would otherwise serialise thousands of atomics on its cursor)
-__device__ __forceinline__ void file_occurrences_warp(const BatchDev& b, uint32_t occ, bool valid) {
-  const uint32_t lane = threadIdx.x & 31;
-  uint32_t cell = 0xFFFFFFFFu;
-  OccRef r;
-  r.row = r.base = r.count = 0;
-  if (valid) {
-    cell = b.occ_set[occ];
-    r = occ_ref(b, cell);
-    if (r.count <= 1) cell = 0xFFFFFFFFu;
-  }
-  const uint32_t peers = __match_any_sync(0xffffffffu, cell);
-  if (cell == 0xFFFFFFFFu) return;
-  const uint32_t leader = __ffs(peers) - 1;
-  uint32_t at = 0;
-  if (lane == leader) at = atomicAdd(&b.set[cell].cursor, (uint32_t)__popc(peers));
-  at = __shfl_sync(peers, at, leader);
-  b.seg_occ[r.base + at + __popc(peers & ((1u << lane) - 1u))] = occ;
-}
-
 constexpr int GATHER_ITEM_ROWS = 4;  // output rows per group in the one-id-per-sample layout (independent loads in flight)
 
 template <int VEC, int G, bool TRAIN>
@@ -196,7 +164,7 @@ __global__ void __launch_bounds__(256) k_gather_items(TableDev t, SlotsDev sl, B
     // one occurrence per output row: GATHER_ITEM_ROWS rows per group, every stage issued for all rows before use
     if (TRAIN) {  // one occurrence per thread first: the grid has at least n_out threads
       const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-      if ((gt & ~31u) < n_out) file_occurrences_warp(b, gt, gt < n_out);
+      if ((gt & ~31u) < n_out) file_occurrences_warp(b, sl, gt, gt < n_out);
     }
     const uint32_t r0 = group * GATHER_ITEM_ROWS;
     if (r0 >= n_out) return;
@@ -246,7 +214,7 @@ __global__ void __launch_bounds__(256) k_gather_items(TableDev t, SlotsDev sl, B
   if (TRAIN && lane == 0) {
     for (uint32_t j = beg; j < end; ++j) {
       const uint32_t cell = b.occ_set[j];
-      file_occurrence(b, cell, occ_ref(b, cell), j);
+      file_occurrence(b, sl, cell, occ_ref(b, cell), j);
     }
   }
   for (uint32_t c = lane; c < nvec; c += G) {
@@ -277,6 +245,12 @@ __global__ void __launch_bounds__(256) k_clear_items(BatchDev b) {
   }
 }
 
+// a batch whose gradients never came leaves the bits its forward set in the hot-item bitmap pool
+__global__ void __launch_bounds__(256) k_clear_hot_bits(BatchDev b) {
+  const uint32_t used = min(b.cnt[BC_HOTW], b.hot_words);
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < used; w += gridDim.x * blockDim.x) b.hot_bits[w] = 0u;
+}
+
 __global__ void k_fill_set(DCell* set, uint64_t n) {
   const uint4 e0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
   const uint4 e1 = make_uint4(ROW_NONE, 0u, 0u, 0u);
@@ -296,12 +270,12 @@ void launch_dedup(const SlotsDev& sl, const BatchDev& b, const uint64_t* ids, cu
   if (b.n) PB_LAUNCH_F(FAM_DEDUP, (k_dedup<true>), cdiv(b.n, 256), 256, 0, st, sl, b, ids);
 }
 
-void launch_probe_items(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const BatchDev& b,
-                        cudaStream_t st) {
+void launch_probe_items(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const SlotsDev& sl,
+                        const BatchDev& b, cudaStream_t st) {
   if (!b.n) return;
   const uint32_t grid = cdiv((uint64_t)b.n * BUCKET, 256);  // worst case U = N; blocks past the item count return at once
-  if (training) PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_TRAIN>), grid, 256, 0, st, t, hy, op, b);
-  else PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_FIND>), grid, 256, 0, st, t, hy, op, b);
+  if (training) PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_TRAIN>), grid, 256, 0, st, t, hy, op, sl, b);
+  else PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_FIND>), grid, 256, 0, st, t, hy, op, sl, b);
 }
 
 template <int VEC, bool TRAIN>
@@ -332,6 +306,8 @@ void launch_gather_items(const TableDev& t, const SlotsDev& sl, const BatchDev& 
     else gather_items_dispatch<1, false>(G, t, sl, b, row_off, n_out, batch, out, st);
   }
 }
+
+void launch_clear_hot_bits(const BatchDev& b, cudaStream_t st) { PB_LAUNCH(k_clear_hot_bits, 148, 256, 0, st, b); }
 
 void launch_clear_items(const BatchDev& b, cudaStream_t st) {
   if (!b.n) return;

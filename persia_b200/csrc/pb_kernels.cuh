@@ -37,7 +37,8 @@ enum {
   BC_WARM,       // items of 2..PB_WARM_MAX occurrences
   BC_HOT,        // items of more
   BC_SEG,        // entries of seg_occ handed out
-  BC_SENT,       // sharded: per-owner send counts follow at BC_PEER (16 words)
+  BC_SENT,       // (unused)
+  BC_HOTW,       // words of the hot-item bitmap pool handed out
   BC_PEER = 8,
   BC_NEXT = 24,  // work cursors of the reducing kernels: [round] warm, [PB_MAX_SLOTS + round] hot
   BC_COUNT = BC_NEXT + 2 * PB_MAX_SLOTS
@@ -49,7 +50,9 @@ struct BatchDev {
   uint32_t* seg_occ;    // [n] occurrence lists
   uint2* cold;          // [n]   (target, occurrence)
   uint4* warm;          // [n/2] (target, base, count, -)
-  uint4* hot;           // [n/PB_WARM_MAX] (target, base, count, -)
+  uint4* hot;           // [n/PB_WARM_MAX] (target, base | bitmap word offset + bit 31, count, slot)
+  uint32_t* hot_bits;   // [hot_words] one bit per sample of the slot for hot items in bitmap mode (all zero between batches)
+  uint32_t hot_words;
   uint32_t* cnt;        // BC_* words
   uint32_t n;           // id occurrences of the batch
 };
@@ -114,11 +117,12 @@ void launch_probe(int mode, bool prefix, const TableDev& t, const HyperDev& hy, 
 void launch_gather(const TableDev& t, const uint32_t* occ_cell, uint32_t n_out, float* out, cudaStream_t st);
 // batched path (pb_dedup.cu)
 void launch_dedup(const SlotsDev& sl, const BatchDev& b, const uint64_t* ids, cudaStream_t st);
-void launch_probe_items(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const BatchDev& b,
-                        cudaStream_t st);
+void launch_probe_items(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const SlotsDev& sl,
+                        const BatchDev& b, cudaStream_t st);
 void launch_gather_items(const TableDev& t, const SlotsDev& sl, const BatchDev& b, const uint32_t* row_off,
                          uint32_t n_out, uint32_t batch, bool training, void* out_f16, cudaStream_t st);
 void launch_clear_items(const BatchDev& b, cudaStream_t st);
+void launch_clear_hot_bits(const BatchDev& b, cudaStream_t st);  // of a batch whose backward never came
 void launch_copy_entries(bool write, const TableDev& t, const uint32_t* occ_cell, uint32_t n, float* entries,
                          uint8_t* found, cudaStream_t st);
 void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_slot, bool f16, const uint32_t* tick,

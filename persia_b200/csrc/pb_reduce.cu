@@ -331,25 +331,24 @@ __global__ void __launch_bounds__(256) k_reduce_cold(TableDev t, OptimDev op, Hy
 }
 
 // ------------------------------------------------------------------------------------------------
-// hot items: counting-sort order + cp.async.bulk / mbarrier rings, three roles per CTA
+// hot items: counting-sort order + a cp.async.bulk / mbarrier ring, one CTA per item
 //
-//   all threads   per window of HOT_WIN samples of the item's slot: one bit per occurrence in a shared bitmap
-//                 (atomicOr: order-free), word prefix sums, then the set bits written out in ascending order — a
-//                 counting sort of the occurrence list that costs HOT_WIN/32 words.
-//   loader        (warp 0) streams the gradient rows of 32 consecutive occurrences per stage into the f16 ring with
-//                 cp.async.bulk, completion in bytes on the stage's mbarrier.  Runs of adjacent samples (the rule for
-//                 the signs of a tiny slot) go as ONE copy: the copy engine is bound by operations, not bytes, here.
-//   converters    (warps 1..3) turn a landed stage into prepared f32 rows (clamp, 1/scale, sqrt factor — everything
-//                 the EW does to a gradient value before it is summed, mod.rs:751-778) in the f32 ring.  All of this
-//                 is order-independent, so it is done by 96 lanes in parallel, off the summation's critical path.
-//   chain         (warp 4) adds the prepared rows in order: per row one shared-memory load and one dependent FADD per
-//                 element — the floor for a strictly sequential f32 sum — then performs the optimizer step.
+//   order     The forward already set one bit per occurrence in the item's bitmap over its slot's samples (hot_bits,
+//             k_gather_items) — a counting sort that costs B/32 words.  Here the words are loaded (and zeroed for the
+//             next batch), prefix-summed and expanded into the ascending list of sample numbers in shared memory.
+//             (Items that found no room in the bitmap pool come with an unsorted occurrence list instead and set the
+//             bits here.)
+//   loader    (warp 0) streams the gradient rows of HOT_ROWS consecutive occurrences per stage into the ring with
+//             cp.async.bulk, completion in bytes on the stage's mbarrier.  Runs of adjacent samples (the rule for the
+//             signs of a tiny slot) go as ONE copy: the copy engine is bound by operations, not bytes, at this size.
+//   chain     (warp 1) waits for a stage and adds its rows in order: per row one shared-memory load, the EW's value
+//             preparation (f16 -> f32 with +-inf clamped, 1/scale, sqrt factor; mod.rs:751-778) and one dependent FADD
+//             per element — the floor for a strictly sequential f32 sum — then performs the optimizer step.
+//   warps 2, 3 only help with the order phase.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t HOT_WIN = 8192;   // samples per bitmap window
 constexpr uint32_t HOT_WORDS = HOT_WIN / 32;
-constexpr uint32_t HOT_ROWS = 32;    // rows per ring stage
-constexpr uint32_t HOT_CONV_WARPS = 3;
-constexpr uint32_t HOT_THREADS = 32 * (2 + HOT_CONV_WARPS);
+constexpr uint32_t HOT_THREADS = 128;
 constexpr uint32_t WAIT_SPINS = 1u << 22;  // bounded waits: a lost completion voids the batch (CTR_ERR) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -382,7 +381,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void conv_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * HOT_CONV_WARPS) : "memory"); }
 
 // +-inf -> +-65504 (persia-common lib.rs:163-180), two halves per instruction; finite halves are inside already
 __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
@@ -390,45 +388,64 @@ __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
   return __hmin2(__hmax2(v, __hneg2(lim)), lim);
 }
 
-struct HotRing {  // a ring of `n` stages and its two mbarrier arrays, with the running phase of one role
-  uint32_t n, it;
-  uint32_t full0, empty0;  // shared addresses of the first full / empty barrier
-  __device__ __forceinline__ uint32_t stage() const { return it % n; }
-  __device__ __forceinline__ uint32_t par() const { return (it / n) & 1u; }
-  __device__ __forceinline__ uint32_t full() const { return full0 + 8u * stage(); }
-  __device__ __forceinline__ uint32_t empty() const { return empty0 + 8u * stage(); }
-};
+// EPL consecutive gradient elements of a row (shared memory or global) -> f32, clamped
+template <int EPL, bool F16>
+__device__ __forceinline__ void read_elems(float (&g)[EPL], const unsigned char* rowp, uint32_t e0) {
+  if constexpr (F16) {
+    const __half* p = reinterpret_cast<const __half*>(rowp) + e0;
+    if constexpr (EPL == 8) {
+      uint4 raw = *reinterpret_cast<const uint4*>(p);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 x = __half22float2(clamp_h2(h[q]));
+        g[2 * q] = x.x;
+        g[2 * q + 1] = x.y;
+      }
+    } else if constexpr (EPL == 4) {
+      uint2 raw = *reinterpret_cast<const uint2*>(p);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float2 x = __half22float2(clamp_h2(h[q]));
+        g[2 * q] = x.x;
+        g[2 * q + 1] = x.y;
+      }
+    } else if constexpr (EPL == 2) {
+      float2 x = __half22float2(clamp_h2(*reinterpret_cast<const __half2*>(p)));
+      g[0] = x.x;
+      g[1] = x.y;
+    } else {
+      g[0] = clamp_f16(__half2float(p[0]));
+    }
+  } else {
+    RowElems<-1, EPL>::template ld<EPL>(reinterpret_cast<const float*>(rowp) + e0, g);
+  }
+}
 
 template <int EPL, bool F16, bool SEND>
-__global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
-                                                              ReduceArgs a, uint32_t rs, uint32_t cs, uint32_t bulk, uint32_t hr) {
+__global__ void __launch_bounds__(HOT_THREADS, 4) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                              ReduceArgs a, uint32_t rs, uint32_t bulk, uint32_t hr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
   __shared__ uint32_t s_item, s_nwin;
   __shared__ uint32_t bitmap[HOT_WORDS], wpre[HOT_WORDS];
   __shared__ uint16_t sorted[HOT_WIN];
-  __shared__ __align__(8) uint64_t bars[4 * 8];  // f16 ring full/empty (<= 8 stages), f32 ring full/empty (<= 8)
-  __shared__ float s_fac[8][HOT_ROWS];           // per f32 stage: the sample's sqrt factor of every row
+  __shared__ __align__(8) uint64_t bars[16];  // ring full[0..8), empty[8..16)
   const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
-  const uint32_t ring16 = bulk ? rs * hr * rowbytes : 0u;  // hr = rows per stage (32 unless the rows are very long)
-  unsigned char* ring = smem_raw;                                       // [rs][32][rowbytes]   landed gradient rows
-  float* cring = reinterpret_cast<float*>(smem_raw + ring16);          // [cs][32][dim]        prepared f32 rows
-  float* vstage = cring + (size_t)cs * hr * t.dim;               // [dim]                Adagrad-vectorwise dot
+  unsigned char* ring = smem_raw;  // [rs][hr][rowbytes] landed gradient rows (bulk mode)
+  float* vstage = reinterpret_cast<float*>(smem_raw + (bulk ? (size_t)rs * hr * rowbytes : 0));  // [dim] Adagrad-vectorwise dot
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_loader = warp == 0, is_chain = warp == 1 + HOT_CONV_WARPS, is_conv = !is_loader && !is_chain;
-  const uint32_t ctid = tid - 32u;  // converter thread number
   if (tid == 0) {
-    for (uint32_t s = 0; s < 32; ++s) mbar_init(smem_u32(bars + s), 1u);
+    for (uint32_t s = 0; s < 16; ++s) mbar_init(smem_u32(bars + s), 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   build_dead_mask(dead, gr, a, sl.n_slots);  // ends with __syncthreads
-  HotRing r16, r32;  // every role keeps its own copy and advances it once per chunk: the chunk sequence is the same for all
-  r16.n = rs; r16.it = 0; r16.full0 = smem_u32(bars); r16.empty0 = smem_u32(bars + 8);
-  r32.n = cs; r32.it = 0; r32.full0 = smem_u32(bars + 16); r32.empty0 = smem_u32(bars + 24);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 8);
   const uint32_t n_hot = a.b.cnt[BC_HOT];
   uint32_t* next = a.b.cnt + BC_NEXT + PB_MAX_SLOTS + a.round;
   const uint32_t n_pass = (t.dim + 32u * EPL - 1u) / (32u * EPL);
-  const uint32_t half_dim = t.dim / 2;  // converters work on element pairs when the dim is even
+  uint32_t it = 0;  // ring stages used so far: loader and chain count the same chunks
   bool failed = false;
   for (;;) {
     __syncthreads();  // s_item, bitmap and sorted are free again
@@ -437,20 +454,23 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
     const uint32_t h = s_item;
     if (h >= n_hot) break;
     const uint4 d = a.b.hot[h];
-    const uint32_t row = d.x, base = d.y, cnt = d.z;
-    const uint32_t slot = slot_of_occ(sl, a.b.seg_occ[base]);
-    if (SEND) {
-      if (row == ROW_NONE) continue;
-      if (tid == 0) *send_gok_ptr(a.x, row) = slot_dead(dead, slot) ? 0u : 1u;
-      if (slot_dead(dead, slot)) continue;
-    } else {
-      if (slot_dead(dead, slot)) continue;
-      if (row >= t.capacity) {
-        if (tid == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
-        continue;
-      }
-    }
+    const uint32_t row = d.x, cnt = d.z, slot = d.w;
+    const bool bm_mode = d.y >> 31;
+    const uint32_t base = d.y & 0x7FFFFFFFu;  // first bitmap word of the item, or first entry of its occurrence list
     const uint32_t lo = sl.occ_off[slot], hi = sl.occ_off[slot + 1];
+    bool skip = false;
+    if (SEND) {
+      skip = row == ROW_NONE || slot_dead(dead, slot);
+      if (row != ROW_NONE && tid == 0) *send_gok_ptr(a.x, row) = slot_dead(dead, slot) ? 0u : 1u;
+    } else {
+      skip = slot_dead(dead, slot) || row >= t.capacity;
+      if (!slot_dead(dead, slot) && row >= t.capacity && tid == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+    }
+    if (skip) {  // the item's bits must still go back to zero for the next batch
+      if (bm_mode)
+        for (uint32_t w = tid; w < (hi - lo + 31u) / 32u; w += HOT_THREADS) a.b.hot_bits[base + w] = 0u;
+      continue;
+    }
     const ItemSrc src = item_src(sl, gr, a, slot);
     const bool contiguous = !a.occ_outrow;  // one id per sample: the gradient row of occurrence lo + b is row b
     const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
@@ -466,12 +486,25 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
       for (int q = 0; q < EPL; ++q) acc[q] = 0.0f;
       for (uint32_t wbase = lo; wbase < hi; wbase += HOT_WIN) {
         const uint32_t wend = min(hi, wbase + HOT_WIN);
-        // ---- counting sort of the item's occurrences inside this window
-        for (uint32_t w = tid; w < HOT_WORDS; w += HOT_THREADS) bitmap[w] = 0u;
-        __syncthreads();
-        for (uint32_t k = tid; k < cnt; k += HOT_THREADS) {
-          const uint32_t p = a.b.seg_occ[base + k];
-          if (p >= wbase && p < wend) atomicOr(&bitmap[(p - wbase) >> 5], 1u << ((p - wbase) & 31u));
+        const uint32_t n_words = (wend - wbase + 31u) / 32u;
+        // ---- the item's occurrences inside this window, ascending
+        if (bm_mode) {
+          uint32_t* g = a.b.hot_bits + base + (wbase - lo) / 32u;
+          for (uint32_t w = tid; w < HOT_WORDS; w += HOT_THREADS) {
+            bitmap[w] = w < n_words ? g[w] : 0u;
+            if (w < n_words && pass + 1 == n_pass) g[w] = 0u;  // all zero again for the next batch
+          }
+        } else {
+          for (uint32_t w = tid; w < HOT_WORDS; w += HOT_THREADS) bitmap[w] = 0u;
+          __syncthreads();
+          for (uint32_t k0 = tid; k0 < cnt; k0 += 4 * HOT_THREADS) {  // four loads in flight per thread
+            uint32_t p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = k0 + u * HOT_THREADS < cnt ? a.b.seg_occ[base + k0 + u * HOT_THREADS] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (p[u] >= wbase && p[u] < wend) atomicOr(&bitmap[(p[u] - wbase) >> 5], 1u << ((p[u] - wbase) & 31u));
+          }
         }
         __syncthreads();
         if (warp == 0) {  // exclusive prefix of the word popcounts: HOT_WORDS / 32 words per lane
@@ -502,137 +535,78 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
         __syncthreads();
         const uint32_t nwin = s_nwin;
         const uint32_t n_chunks = (nwin + hr - 1u) / hr;
-        // ---- the pipeline over chunks of 32 consecutive occurrences
-        if (is_loader) {
-          if (bulk) {
-            for (uint32_t c = 0; c < n_chunks; ++c) {
-              const uint32_t nv = min(hr, nwin - c * hr);
-              if (!failed && !mbar_wait(r16.empty(), r16.par() ^ 1u)) failed = true;
-              const bool valid = lane < nv;
-              const uint32_t occ = wbase + (valid ? sorted[c * hr + lane] : 0u);
-              const uint32_t orow = valid ? occ_out_row(a, occ) : 0u;
+        // ---- the pipeline over chunks of hr consecutive occurrences
+        if (warp == 0 && bulk) {
+          for (uint32_t c = 0; c < n_chunks; ++c, ++it) {
+            const uint32_t nv = min(hr, nwin - c * hr), stage = it % rs, par = (it / rs) & 1u;
+            if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
+            if (lane == 0) mbar_expect_tx(full0 + 8u * stage, nv * rowbytes);
+            __syncwarp();
+            for (uint32_t k0 = 0; k0 < hr; k0 += 32) {  // uniform trip count: shuffles and ballots are warp-wide
+              const uint32_t k = k0 + lane;
+              const bool valid = k < nv;
+              const uint32_t orow = valid ? occ_out_row(a, wbase + sorted[c * hr + k]) : 0u;
               const uint32_t prev = __shfl_up_sync(0xffffffffu, orow, 1);
               const bool head = valid && (lane == 0 || !contiguous || orow != prev + 1u);
               const uint32_t hm = __ballot_sync(0xffffffffu, head);
-              if (lane == 0) mbar_expect_tx(r16.full(), nv * rowbytes);
-              __syncwarp();
+              const uint32_t vm = __ballot_sync(0xffffffffu, valid);
               if (head) {
                 const uint32_t later = (lane == 31) ? 0u : (hm >> (lane + 1));
-                const uint32_t len = later ? (uint32_t)__ffs(later) : nv - lane;  // rows up to the next run's head
-                bulk_g2s(smem_u32(ring + ((size_t)r16.stage() * hr + lane) * rowbytes),
-                         gbytes + (size_t)(orow - src.slot_row0) * rowbytes, len * rowbytes, r16.full());
+                const uint32_t len = later ? (uint32_t)__ffs(later) : (uint32_t)__popc(vm) - lane;  // rows up to the next run's head
+                bulk_g2s(smem_u32(ring + ((size_t)stage * hr + k) * rowbytes),
+                         gbytes + (size_t)(orow - src.slot_row0) * rowbytes, len * rowbytes, full0 + 8u * stage);
               }
-              ++r16.it;
             }
-          } else {
-            r16.it += n_chunks;
           }
-        } else if (is_conv) {
-          for (uint32_t c = 0; c < n_chunks; ++c) {
-            const uint32_t nv = min(hr, nwin - c * hr);
-            if (!failed && !mbar_wait(r32.empty(), r32.par() ^ 1u)) failed = true;
-            if (bulk && !failed && !mbar_wait(r16.full(), r16.par())) failed = true;
-            float* fac = s_fac[r32.stage()];
-            if (src.do_sqrt) {  // the sample's 1/sqrt(n ids), one lane per row
-              if (ctid < nv) fac[ctid] = grad_prep(src, a, occ_out_row(a, wbase + sorted[c * hr + ctid])).sqrt_f;
-              conv_barrier();
-            }
-            float* dst = cring + (size_t)r32.stage() * hr * t.dim;
-            const unsigned char* srows = ring + (size_t)r16.stage() * hr * rowbytes;
-            const uint32_t cw = warp - 1u;  // converter warp: rows cw, cw + 3, ...; its lanes cover a row's element pairs
-            if (t.dim % 2 == 0) {
-              for (uint32_t k0 = cw; k0 < nv; k0 += 4u * HOT_CONV_WARPS) {  // four independent rows per round
-                const unsigned char* rp[4];
-                float f[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const uint32_t k = k0 + (uint32_t)u * HOT_CONV_WARPS;
-                  const uint32_t kk = k < nv ? k : k0;
-                  f[u] = src.do_sqrt ? fac[kk] : 1.0f;
-                  if (bulk) rp[u] = srows + (size_t)kk * rowbytes;
-                  else rp[u] = gbytes + (size_t)(occ_out_row(a, wbase + sorted[c * hr + kk]) - src.slot_row0) * rowbytes;
-                }
-                for (uint32_t col = lane; col < half_dim; col += 32) {
-                  float2 v[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    if (F16) v[u] = __half22float2(clamp_h2(reinterpret_cast<const __half2*>(rp[u])[col]));
-                    else v[u] = reinterpret_cast<const float2*>(rp[u])[col];
-                  }
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const uint32_t k = k0 + (uint32_t)u * HOT_CONV_WARPS;
-                    if (k < nv) {
-                      if (src.do_scale) {
-                        v[u].x = __fmul_rn(v[u].x, src.inv_scale);
-                        v[u].y = __fmul_rn(v[u].y, src.inv_scale);
-                      }
-                      if (src.do_sqrt) {
-                        v[u].x = __fmul_rn(v[u].x, f[u]);
-                        v[u].y = __fmul_rn(v[u].y, f[u]);
-                      }
-                      reinterpret_cast<float2*>(dst + (size_t)k * t.dim)[col] = v[u];
-                    }
-                  }
-                }
-              }
-            } else {
-              for (uint32_t k = cw; k < nv; k += HOT_CONV_WARPS) {
-                const unsigned char* rp = bulk ? srows + (size_t)k * rowbytes
-                                               : gbytes + (size_t)(occ_out_row(a, wbase + sorted[c * hr + k]) - src.slot_row0) * rowbytes;
-                for (uint32_t col = lane; col < t.dim; col += 32) {
-                  float v = F16 ? clamp_f16(__half2float(reinterpret_cast<const __half*>(rp)[col])) : reinterpret_cast<const float*>(rp)[col];
-                  if (src.do_scale) v = __fmul_rn(v, src.inv_scale);
-                  if (src.do_sqrt) v = __fmul_rn(v, fac[k]);
-                  dst[(size_t)k * t.dim + col] = v;
-                }
-              }
-            }
-            conv_barrier();  // every converter is done with both stages
-            if (ctid == 0) {
-              mbar_arrive(r32.full());             // the chain may add this stage
-              if (bulk) mbar_arrive(r16.empty());  // the loader may refill the f16 stage
-            }
-            ++r16.it;
-            ++r32.it;
-          }
-        } else {
-          // ---- chain: the prepared rows in ascending order, one dependent add per row and element
-          for (uint32_t c = 0; c < n_chunks; ++c) {
-            const uint32_t nv = min(hr, nwin - c * hr);
-            if (!failed && !mbar_wait(r32.full(), r32.par())) failed = true;
-            const float* rows = cring + (size_t)r32.stage() * hr * t.dim + e0;
+        } else if (warp == 1) {
+          // ---- chain: the rows in ascending order, one dependent add per row and element
+          for (uint32_t c = 0; c < n_chunks; ++c, ++it) {
+            const uint32_t nv = min(hr, nwin - c * hr), stage = it % rs, par = (it / rs) & 1u;
+            if (bulk && !failed && !mbar_wait(full0 + 8u * stage, par)) failed = true;
+            const unsigned char* rows = ring + (size_t)stage * hr * rowbytes;
             if (own) {
-              uint32_t k = 0;
-              for (; k + 8 <= nv; k += 8) {
+              for (uint32_t k = 0; k < nv; k += 8) {  // eight rows per round: loads first, then the dependent adds
                 float g[8][EPL];
+                float f[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) RowElems<-1, EPL>::template ld<EPL>(rows + (size_t)(k + u) * t.dim, g[u]);
+                for (int u = 0; u < 8; ++u) {
+                  const uint32_t kk = k + u < nv ? k + u : k;
+                  f[u] = 1.0f;
+                  if (bulk && src.plain) {
+                    read_elems<EPL, F16>(g[u], rows + (size_t)kk * rowbytes, e0);
+                  } else {
+                    const uint32_t orow = occ_out_row(a, wbase + sorted[c * hr + kk]);
+                    if (src.do_sqrt) f[u] = grad_prep(src, a, orow).sqrt_f;
+                    read_elems<EPL, F16>(g[u], bulk ? rows + (size_t)kk * rowbytes : gbytes + (size_t)(orow - src.slot_row0) * rowbytes, e0);
+                  }
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
+                  if (k + u < nv) {
 #pragma unroll
-                  for (int q = 0; q < EPL; ++q) acc[q] = __fadd_rn(acc[q], g[u][q]);
-              }
-              for (; k < nv; ++k) {
-                float g[EPL];
-                RowElems<-1, EPL>::template ld<EPL>(rows + (size_t)k * t.dim, g);
-#pragma unroll
-                for (int q = 0; q < EPL; ++q) acc[q] = __fadd_rn(acc[q], g[q]);
+                    for (int q = 0; q < EPL; ++q) {
+                      float v = g[u][q];
+                      if (src.do_scale) v = __fmul_rn(v, src.inv_scale);
+                      if (src.do_sqrt) v = __fmul_rn(v, f[u]);
+                      acc[q] = __fadd_rn(acc[q], v);
+                    }
+                  }
               }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(r32.empty());  // the stage may be refilled
-            ++r16.it;
-            ++r32.it;
+            if (bulk) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(empty0 + 8u * stage);  // the stage may be refilled
+            }
           }
+        } else if (warp == 0) {
+          it += n_chunks;
         }
-        // roles that skipped the loops above keep their ring counters in step
-        if (is_loader) r32.it += n_chunks;
+        // (warps 2, 3 wait at the next barrier)
       }
       // ---- the optimizer step on this pass's elements (chain warp)
       if (SEND) {
-        if (is_chain && own) RowElems<-1, EPL>::template st<EPL>(prow + e0, acc);
-      } else if (is_chain && own) {
+        if (warp == 1 && own) RowElems<-1, EPL>::template st<EPL>(prow + e0, acc);
+      } else if (warp == 1 && own) {
         RowElems<-1, EPL> rc;
         rc.load(prow, e0, t, op);
         if (op.kind == PB_OPT_ADAGRAD_VW) {
@@ -643,7 +617,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
         rc.store(prow, e0, t, op);
       }
     }
-    if (!SEND && op.kind == PB_OPT_ADAGRAD_VW && is_chain) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
+    if (!SEND && op.kind == PB_OPT_ADAGRAD_VW && warp == 1) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
       __syncwarp();
       if (lane == 0) {
         float gs = __fdiv_rn(vw_dot(vstage, t.dim), (float)t.dim);
@@ -681,14 +655,15 @@ template <int EPL, bool F16, bool SEND>
 static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
                        const ReduceArgs& a, uint32_t bulk, cudaStream_t st) {
   const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
-  uint32_t hr = HOT_ROWS;  // rows per stage: fewer when a row is very long
-  while (hr > 1 && (size_t)hr * t.dim * 4u > 16u * 1024u) hr >>= 1;
-  const size_t stage16 = (size_t)hr * rowbytes, stage32 = (size_t)hr * t.dim * 4u;
-  uint32_t rs = 8, cs = 4;
-  while (rs > 2 && rs * stage16 > 32u * 1024u) rs >>= 1;
-  while (cs > 2 && cs * stage32 > 32u * 1024u) cs >>= 1;
+  uint32_t hr = 64;  // rows per stage (a multiple of 32, or a power of two below it for very long rows)
+  while (hr > 1 && (size_t)hr * rowbytes > 16u * 1024u) hr >>= 1;
+  uint32_t rs = 4;
+  if (getenv("PB_HOT_RS")) rs = (uint32_t)atoi(getenv("PB_HOT_RS"));
+  if (getenv("PB_HOT_HR")) hr = (uint32_t)atoi(getenv("PB_HOT_HR"));
+  if (rs > 8) rs = 8;
+  if (rs < 2) rs = 2;
   if (!bulk) rs = 1;
-  const size_t smem = (bulk ? rs * stage16 : 0) + cs * stage32 + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
+  const size_t smem = (bulk ? (size_t)rs * hr * rowbytes : 0) + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
   auto kern = k_reduce_hot<EPL, F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
@@ -697,13 +672,13 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured[dev] = smem;
   }
-  uint32_t per_sm = (uint32_t)(200u * 1024u / (smem + 24u * 1024u));  // + the kernel's static shared memory
-  if (per_sm > 2) per_sm = 2;
+  uint32_t per_sm = (uint32_t)(200u * 1024u / (smem + 20u * 1024u));  // + the kernel's static shared memory
+  if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   const uint32_t cap_blocks = cdiv(a.b.n, PB_WARM_MAX + 1);  // at most this many hot items exist
   uint32_t grid = 148u * per_sm;
   if (grid > cap_blocks) grid = cap_blocks ? cap_blocks : 1;
-  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, rs, cs, bulk, hr);
+  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, rs, bulk, hr);
 }
 
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,

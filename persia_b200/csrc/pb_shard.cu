@@ -79,12 +79,17 @@ __global__ void __launch_bounds__(256) k_route_items(SlotsDev sl, BatchDev b, Xc
       x.err[0] = 1u;  // the pair needs more than cap slots: the caller re-runs the batch with a larger cap
     }
   }
-  const ItemSlots is = block_item_slots(b, valid, cnt);
+  uint32_t slot = 0, hot_nwords = 0;
+  if (valid && cnt > PB_WARM_MAX) {
+    slot = slot_of_occ(sl, first);
+    hot_nwords = (sl.occ_off[slot + 1] - sl.occ_off[slot] + 31u) / 32u;
+  }
+  const ItemSlots is = block_item_slots(b, valid, cnt, hot_nwords);
   if (valid) {
     *(reinterpret_cast<uint2*>(&b.set[cell]) + 2) = make_uint2(target, is.base);  // target, base
     if (is.cls == 1) b.cold[is.pos] = make_uint2(target, first);
     else if (is.cls == 2) b.warm[is.pos] = make_uint4(target, is.base, cnt, 0u);
-    else if (is.cls == 3) b.hot[is.pos] = make_uint4(target, is.base, cnt, 0u);
+    else if (is.cls == 3) b.hot[is.pos] = make_uint4(target, is.base, cnt, slot);
   }
 }
 
@@ -200,34 +205,13 @@ __global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev 
 // One-id layouts: a pure copy of the f16 row.  Ragged layouts: f32 rows summed in sample order, sqrt scaling, RNE.
 // TRAIN: files every occurrence of a repeated sign into the sign's list, like k_gather_items.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void file_occ(const BatchDev& b, uint32_t cell, uint32_t count, uint32_t base, uint32_t occ) {
-  if (count > 1) b.seg_occ[base + atomicAdd(&b.set[cell].cursor, 1u)] = occ;
-}
-
 template <bool TRAIN>
-__global__ void __launch_bounds__(256) k_expand_copy(uint32_t dim, BatchDev b, XchgDev x, uint32_t n_out,
+__global__ void __launch_bounds__(256) k_expand_copy(uint32_t dim, SlotsDev sl, BatchDev b, XchgDev x, uint32_t n_out,
                                                      __half* __restrict__ out, uint32_t lanes) {
   // `lanes` lanes per output row, 16 bytes per lane and step
   if (TRAIN) {  // one occurrence per thread first (the grid has at least n_out threads), one atomic per warp and sign
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((gt & ~31u) < n_out) {
-      const uint32_t lane = threadIdx.x & 31;
-      uint32_t fc = 0xFFFFFFFFu, fbase = 0;
-      if (gt < n_out) {
-        fc = b.occ_set[gt];
-        const uint4 flo = *reinterpret_cast<const uint4*>(&b.set[fc]);
-        fbase = (reinterpret_cast<const uint4*>(&b.set[fc]) + 1)->y;
-        if (flo.z <= 1) fc = 0xFFFFFFFFu;
-      }
-      const uint32_t peers = __match_any_sync(0xffffffffu, fc);
-      if (fc != 0xFFFFFFFFu) {
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t at = 0;
-        if (lane == leader) at = atomicAdd(&b.set[fc].cursor, (uint32_t)__popc(peers));
-        at = __shfl_sync(peers, at, leader);
-        b.seg_occ[fbase + at + __popc(peers & ((1u << lane) - 1u))] = gt;
-      }
-    }
+    if ((gt & ~31u) < n_out) file_occurrences_warp(b, sl, gt, gt < n_out);
   }
   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / lanes;
   const uint32_t l = threadIdx.x % lanes;
@@ -256,7 +240,7 @@ __global__ void __launch_bounds__(256) k_expand_pool(uint32_t dim, SlotsDev sl, 
   if (TRAIN && lane == 0) {
     for (uint32_t j = beg; j < end; ++j) {
       const uint32_t cell = b.occ_set[j];
-      file_occ(b, cell, b.set[cell].count, b.set[cell].base, j);
+      file_occurrence(b, sl, cell, occ_ref(b, cell), j);
     }
   }
   for (uint32_t e = lane; e < dim; e += G) {
@@ -374,8 +358,8 @@ void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& 
     while (lanes < words && lanes < 32) lanes <<= 1;
     uint32_t grid = cdiv((uint64_t)n_out * lanes, 256);
     if (grid < cdiv(n_out, 256)) grid = cdiv(n_out, 256);
-    if (training) PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<true>), grid, 256, 0, st, t.dim, b, x, n_out, out, lanes);
-    else PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<false>), grid, 256, 0, st, t.dim, b, x, n_out, out, lanes);
+    if (training) PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<true>), grid, 256, 0, st, t.dim, sl, b, x, n_out, out, lanes);
+    else PB_LAUNCH_F(FAM_GATHER, (k_expand_copy<false>), grid, 256, 0, st, t.dim, sl, b, x, n_out, out, lanes);
     return;
   }
   uint32_t G = 1;

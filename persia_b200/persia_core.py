@@ -120,7 +120,7 @@ class _State:
                 sh.set_optimizer(**self.optimizer)
             if self.hyper is not None:
                 sh.configure(**self.hyper)
-            g = self.groups[dim] = {"shard": sh, "ctx": {}, "device": dev}
+            g = self.groups[dim] = {"shard": sh, "ctx": {}, "device": dev, "lock": threading.RLock()}
         return g
 
     def all_groups(self):
@@ -323,7 +323,8 @@ class _Pending:
 
     def release(self):
         for g, ctx, _, _ in self.parts:
-            g["ctx"].setdefault(ctx._pool_key, []).append(ctx)
+            if ctx is not None:  # sharded groups keep their one context inside the worker
+                g["ctx"].setdefault(ctx._pool_key, []).append(ctx)
         self.parts = []
 
 
@@ -382,12 +383,15 @@ def _flatten(feats, batch):
     return ids, row_off, slot_off
 
 
-_GPU_LOCK = threading.RLock()  # the C library keeps per-table host state: one caller at a time
+_STATE_LOCK = threading.RLock()  # configuration / group creation; GPU work takes the lock of the table it touches
+_BACKWARDS = []                   # live Backward engines (direct lookups wait for their queues to drain)
 
 
-def _forward(batch, device_id, training):
-    with _GPU_LOCK:
-        return _forward_locked(batch, device_id, training)
+def _forward(batch, device_id, training, direct=False):
+    if direct:  # forward_directly (forward.rs:782-831) carries no staleness permit: see every update already handed over
+        for b in list(_BACKWARDS):
+            b.flush()
+    return _forward_locked(batch, device_id, training)
 
 
 def _forward_locked(batch, device_id, training):
@@ -427,10 +431,12 @@ def _forward_locked(batch, device_id, training):
         sc = _S.by_name[n]
         if sc.embedding_summation:
             continue
-        g = _S.group(sc.dim)
+        with _STATE_LOCK:
+            g = _S.group(sc.dim)
         key = ("raw", n)
         pool = g["ctx"].setdefault(key, [])
         ids, row_off, _ = _flatten([(n, x)], B)
+        g["lock"].acquire()
         if pool and pool[-1]._cap >= max(len(ids), B):
             ctx = pool.pop()
         else:
@@ -448,13 +454,30 @@ def _forward_locked(batch, device_id, training):
             pending.parts.append((g, ctx, [n], True))
         else:
             pool.append(ctx)
+        g["lock"].release()
     for dim in sorted({_S.by_name[n].dim for n, _ in feats if _S.by_name[n].embedding_summation}):
         part = [(n, x) for n, x in feats if _S.by_name[n].dim == dim and _S.by_name[n].embedding_summation]
         names = [n for n, _ in part]
-        g = _S.group(dim)
+        with _STATE_LOCK:
+            g = _S.group(dim)
         key = tuple(names)
         pool = g["ctx"].setdefault(key, [])
         ids, row_off, slot_off = _flatten(part, B)
+        if (_S.replica_size or 1) > 1:  # R GPUs: the embedding worker's fan-out runs inside the sharded worker
+            with g["lock"]:
+                wk = _sharded_worker(g, dim, names, B, ids, row_off, slot_off, dev)
+                d_ids = torch.from_numpy(ids.view(np.int64)).to(dev, non_blocking=True)
+                d_off = torch.from_numpy(row_off.view(np.int32)).to(dev, non_blocking=True) if row_off is not None else None
+                out = wk.forward(d_ids, B, training=training, row_off=d_off, slot_occ_off=slot_off)
+                if wk.status()[0]:
+                    raise RuntimeError("a batch requested more distinct signs of one shard than the exchange holds: raise "
+                                       "PERSIA_B200_XCHG_CAP")
+            for i, n in enumerate(names):
+                by_slot[n] = out[i]
+            if training:
+                pending.parts.append((g, None, names, False))
+            continue
+        g["lock"].acquire()
         if pool:
             ctx = pool.pop()
         else:
@@ -472,10 +495,51 @@ def _forward_locked(batch, device_id, training):
             pending.parts.append((g, ctx, names, False))
         else:
             pool.append(ctx)
+        g["lock"].release()
     emb = [Embedding(None, raw=raw_out[n]) if n in raw_out else Embedding(Tensor(by_slot[n], n)) for n, _ in feats]
     to_dev = lambda items: [Tensor(torch.from_numpy(a).to(dev), n) for n, a in items]  # noqa: E731
     return PersiaTrainingBatch(to_dev(batch.non_id_type_features), emb, to_dev(batch.labels), batch.meta_data,
                                pending if training else None)
+
+
+def _sharded_worker(g, dim, names, B, ids, row_off, slot_off, dev):
+    """The dim group's ShardedEmbeddingWorker (persia_b200/worker.py), created by the first batch: a collective —
+    every rank's first lookup of the group must happen in the same step (it does: the ranks train in lockstep)."""
+    wk = g.get("worker")
+    if wk is not None:
+        if wk.names != tuple(names):
+            raise RuntimeError("on R GPUs every batch must carry the same summation slots of a dim, in the same order")
+        return wk
+    import torch.distributed as dist
+
+    from .worker import ShardedEmbeddingWorker as W
+
+    if not dist.is_initialized():
+        raise RuntimeError("replica_size > 1 needs torch.distributed (TrainCtx initialises it; else call init_process_group)")
+    R = dist.get_world_size()
+    slots = [_S.by_name[n] for n in names]
+    cap = int(os.environ.get("PERSIA_B200_XCHG_CAP", 0))
+    if not cap:  # from this first batch: distinct signs per owner, largest over the ranks, with a generous margin
+        counts = np.zeros(R, np.int64)
+        spacing = np.uint64((1 << (64 - _S.prefix_bit)) - 1)
+        for i, sc in enumerate(slots):
+            x = ids[slot_off[i]:slot_off[i + 1]]
+            u = np.unique(x % spacing + np.uint64(sc.index_prefix) if sc.index_prefix else x)
+            counts += np.bincount((farmhash64_np(u) % np.uint64(R)).astype(np.int64), minlength=R)
+        t = torch.tensor([int(counts.max())], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cap = (int(int(t) * 1.5) + 1024 + 7) // 8 * 8
+    ragged = row_off is not None
+    per_sample = max(1, -(-len(ids) // max(1, len(names) * B)))
+    max_batch = int(os.environ.get("PERSIA_B200_MAX_BATCH", B))
+    wk = W.distributed(len(names), dim, [sc.index_prefix for sc in slots], _S.capacity, cap, _S.optimizer or {}, dev,
+                       hyper=_S.hyper, max_batch=max(B, max_batch), sqrt_scaling=[sc.sqrt_scaling for sc in slots],
+                       rows_f32=ragged, prefix_bit=_S.prefix_bit, max_ids_per_sample=2 * per_sample if ragged else 1)
+    wk.names = tuple(names)
+    wk.shard.set_eviction()
+    g["shard"].close()
+    g["shard"], g["worker"] = wk.shard, wk
+    return wk
 
 
 class PersiaTrainingBatch:  # forward.rs:256-306, #[pyclass(dict)]: python attaches attributes to it
@@ -529,15 +593,101 @@ class GradientBatch:  # backward.rs:60-106
         self._grads[slot_name] = (int(data_ptr), tuple(shape), bool(is_f16_gradient), float(scale_factor))
 
 
-class Backward:  # backward.rs:357-405
+class Backward:  # backward.rs:203-405
+    """The NN worker's backward engine: `update_id_type_feature_gradient_batched` hands the gradient batch to a bounded
+    queue (backward.rs:357-405; the reference's first stage copies the gradients to the host there — here they stay
+    on the device, the raw pointers are simply passed on) and returns; `num_backward_worker` threads take batches off
+    the queue, enqueue pb_backward on the table's stream and give the staleness permit back (backward.rs:304-354).
+    A failing update is logged and the batch dropped, as in the reference (backward.rs:332-339).  Before `launch`
+    (or after `shutdown`) updates are applied in the caller's thread."""
+
     def __init__(self, queue_size):
-        self.queue_size = queue_size
+        self.queue_size = max(1, int(queue_size))
+        self._q = queue.Queue(maxsize=self.queue_size)
+        self._threads = []
+        self._running = False
+        self.dropped = 0
 
     def launch(self, num_backward_worker):
-        return None
+        if self._running:
+            return
+        self._running = True
+        for i in range(max(1, int(num_backward_worker))):
+            t = threading.Thread(target=self._worker, name=f"persia-backward-{i}", daemon=True)
+            t.start()
+            self._threads.append(t)
+        _BACKWARDS.append(self)
 
     def shutdown(self):
-        return None
+        if not self._running:
+            return
+        self.flush()
+        self._running = False
+        for _ in self._threads:
+            self._q.put(None)
+        for t in self._threads:
+            t.join(timeout=10)
+        self._threads = []
+        if self in _BACKWARDS:
+            _BACKWARDS.remove(self)
+
+    def flush(self):
+        """Returns once every gradient batch handed over so far has been enqueued on the GPU."""
+        if self._running:
+            self._q.join()
+
+    def _worker(self):
+        import torch
+
+        if _S.device_id is not None:
+            torch.cuda.set_device(_S.device_id)  # every helper thread selects the device itself (backward.rs:240-244)
+        while True:
+            item = self._q.get()
+            try:
+                if item is None:
+                    return
+                try:
+                    self._apply(*item)
+                except Exception as e:  # noqa: BLE001 — logged and dropped, the trainer goes on (backward.rs:332-339)
+                    self.dropped += 1
+                    sys.stderr.write(f"[persia_b200] update_gradient_batched failed, batch dropped: {e!r}\n")
+            finally:
+                self._q.task_done()
+
+    @staticmethod
+    def _apply(p, grads, permit):
+        try:
+            for g, ctx, names, is_raw in p.parts:
+                with g["lock"]:
+                    if is_raw:  # [U, dim] gradient of the distinct-sign table (persia/ctx.py:970-980)
+                        item = grads.get(names[0])
+                        if item is None:
+                            ctx.backward_raw(g["shard"], None)
+                        else:
+                            ptr, shape, is16, sc = item
+                            ctx.backward_raw(g["shard"], ptr, scale=sc, is_f16=is16)
+                        continue
+                    ptrs, scales, f16 = [], [], None
+                    for n in names:
+                        item = grads.get(n)
+                        if item is None:
+                            ptrs.append(None)
+                            scales.append(1.0)
+                            continue
+                        ptr, shape, is16, sc = item
+                        if f16 is not None and f16 != is16:
+                            raise RuntimeError("gradients of one batch must share a dtype")
+                        f16 = is16
+                        ptrs.append(ptr)
+                        scales.append(sc)
+                    if g.get("worker") is not None:
+                        g["worker"].backward_ptrs(ptrs, bool(f16), scales)
+                    else:
+                        ctx.backward_ptrs(g["shard"], ptrs, bool(f16), scales)
+        finally:
+            p.release()
+            if permit is not None:  # the update is enqueued: the batch no longer counts as in flight (backward.rs:341-343)
+                permit.release()
 
     def update_id_type_feature_gradient_batched(self, gradients):
         p, gradients._pending = gradients._pending, None
@@ -546,36 +696,10 @@ class Backward:  # backward.rs:357-405
             if permit is not None:
                 permit.release()
             raise RuntimeError("cannot find gradient batch")
-        _GPU_LOCK.acquire()
-        try:
-            for g, ctx, names, is_raw in p.parts:
-                if is_raw:  # [U, dim] gradient of the distinct-sign table (persia/ctx.py:970-980)
-                    item = gradients._grads.get(names[0])
-                    if item is None:
-                        ctx.backward_raw(g["shard"], None)
-                    else:
-                        ptr, shape, is16, sc = item
-                        ctx.backward_raw(g["shard"], ptr, scale=sc, is_f16=is16)
-                    continue
-                ptrs, scales, f16 = [], [], None
-                for n in names:
-                    item = gradients._grads.get(n)
-                    if item is None:
-                        ptrs.append(None)
-                        scales.append(1.0)
-                        continue
-                    ptr, shape, is16, sc = item
-                    if f16 is not None and f16 != is16:
-                        raise RuntimeError("gradients of one batch must share a dtype")
-                    f16 = is16
-                    ptrs.append(ptr)
-                    scales.append(sc)
-                ctx.backward_ptrs(g["shard"], ptrs, bool(f16), scales)
-        finally:
-            p.release()
-            _GPU_LOCK.release()
-            if permit is not None:  # the update is enqueued: the batch no longer counts as in flight (backward.rs:341-343)
-                permit.release()
+        if self._running:
+            self._q.put((p, gradients._grads, permit))  # blocks when the queue is full (bounded channel)
+        else:
+            self._apply(p, gradients._grads, permit)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -701,9 +825,8 @@ class Forward:  # forward.rs:833-907 over persia_b200.engine.ForwardEngine (reor
 # ---------------------------------------------------------------------------------------------------------
 class PersiaCommonContext:
     def __init__(self, num_coroutines_worker, replica_index, replica_size, device_id=None):
-        if replica_size != 1:
-            raise RuntimeError("persia_core over libpersia_b200: one process per box in round 1 "
-                               "(use persia_b200.worker.ShardedEmbeddingWorker for R GPUs)")
+        # replica_size > 1: one process per GPU; the dim groups are then served by ShardedEmbeddingWorkers (rows
+        # hash-sharded over the ranks, summation slots only), created by the first batch
         _S.replica_index, _S.replica_size = int(replica_index), int(replica_size)
         if device_id is not None:
             _S.device_id = int(device_id)
@@ -786,10 +909,10 @@ class PersiaCommonContext:
             g["shard"].configure(**_S.hyper)
 
     def get_embedding_from_data(self, batch, device_id=None):  # forward_directly (forward.rs:782-831)
-        return _forward(batch, device_id, training=True)
+        return _forward(batch, device_id, training=True, direct=True)
 
     def get_embedding_from_bytes(self, data, device_id=None):
-        return _forward(PersiaBatch._from_bytes(bytes(data)), device_id, training=True)
+        return _forward(PersiaBatch._from_bytes(bytes(data)), device_id, training=True, direct=True)
 
     def read_from_file(self, file_path):
         with open(file_path, "rb") as f:
@@ -799,6 +922,19 @@ class PersiaCommonContext:
         os.makedirs(file_dir, exist_ok=True)
         with open(os.path.join(file_dir, file_name), "wb") as f:
             f.write(bytes(content))
+
+    def get_entries(self, signs, dim):
+        """Not part of the reference surface: reads back whole entries (embedding ++ optimizer state) of the given signs
+        from the table of `dim` (tests; the reference has no read-back besides dump)."""
+        import torch
+
+        g = _S.group(int(dim))
+        dev = torch.device("cuda", g["device"])
+        with g["lock"]:
+            ent, found = g["shard"].get_entries(torch.from_numpy(np.ascontiguousarray(signs, np.uint64).view(np.int64)).to(dev))
+            if not bool(found.all()):
+                raise RuntimeError("sign not resident")
+            return ent.cpu().numpy()
 
     def set_embedding(self, embeddings):  # lib.rs:433-449: [(sign, emb f32 ndarray, opt f32 ndarray)]
         import torch

@@ -167,6 +167,12 @@ class ShardedEmbeddingWorker:
                                              self._st(), int(phases)))
         return status
 
+    def backward_ptrs(self, ptrs, is_f16, scales=None):
+        """GradientBatch form (persia-core/src/backward.rs:86-105): raw device pointers, None = skipped slot."""
+        arr = (C.c_void_p * self.S)(*[(int(p) if p else None) for p in ptrs])
+        sc = (C.c_float * self.S)(*[float(v) for v in scales]) if scales is not None else None
+        N.check(self.lib.pb_backward_sharded(self.shard.h, self.ctx.h, self.h, arr, int(bool(is_f16)), sc, None, self._st(), 0))
+
     @staticmethod
     def group_forward(workers, ids, batch, training=True, row_offs=None, slot_occ_offs=None, outs=None):
         """Virtual ranks of one GPU, driven by one host thread: every phase is enqueued for all ranks before the next."""

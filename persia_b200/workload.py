@@ -74,3 +74,39 @@ def algorithmic_bytes_per_id(dim, state_floats, phase="total"):
     parts["backward"] = parts["grad_in"] + parts["update"]
     parts["total"] = parts["partition"] + parts["forward"] + parts["backward"]
     return parts[phase]
+
+
+def make_dlrm_tower(n_slots, dim, n_dense=13, bottom=(512, 256), top=(1024, 1024, 512, 256)):
+    """A DLRM-style dense tower (the caller of the path, not part of it): bottom MLP over the dense features, pairwise
+    dot-product interaction between its output and the n_slots pooled embeddings, top MLP to one logit.  Called as
+    `model(non_id_type_tensors, embedding_tensors)` like every PERSIA model (persia/ctx.py:446-448; shape after
+    examples/src/adult-income/model.py and the MLPerf DLRM)."""
+    import torch
+    from torch import nn
+
+    class DLRMTower(nn.Module):
+        def __init__(self):
+            super().__init__()
+            layers, d = [], n_dense
+            for h in tuple(bottom) + (dim,):
+                layers += [nn.Linear(d, h), nn.ReLU()]
+                d = h
+            self.bottom = nn.Sequential(*layers)
+            n_vec = n_slots + 1
+            self.register_buffer("tri", torch.triu_indices(n_vec, n_vec, offset=1), persistent=False)
+            layers, d = [], dim + n_vec * (n_vec - 1) // 2
+            for h in top:
+                layers += [nn.Linear(d, h), nn.ReLU()]
+                d = h
+            layers.append(nn.Linear(d, 1))
+            self.top = nn.Sequential(*layers)
+
+        def forward(self, non_id_type_tensors, embedding_tensors):
+            dense = non_id_type_tensors[0].float()
+            x = self.bottom(dense)                                                    # [B, dim]
+            vecs = torch.stack([x] + [e.float() for e in embedding_tensors], dim=1)  # [B, n_slots + 1, dim]
+            inter = torch.bmm(vecs, vecs.transpose(1, 2))                             # pooled-embedding x dense-bottom interaction
+            z = torch.cat([x, inter[:, self.tri[0], self.tri[1]]], dim=1)
+            return self.top(z).squeeze(-1)
+
+    return DLRMTower()

@@ -4,7 +4,7 @@ export CUDA_DEVICE_MAX_CONNECTIONS=32
 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r2i_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/r2i_pytest.log
 grep -E "passed|failed|FAILED|pytest exit|Mismatched" gpurun_out/r2i_pytest.log | tail -20
-timeout 900 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err
+timeout 900 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --no-model-leg > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err
 echo "bench exit $?"; tail -5 gpurun_out/r2i_bench.err; python - <<'PY'
 import json
 try:
@@ -18,7 +18,7 @@ try:
     print(" m whole",r["metric_leg"]["whole_step"])
 except Exception as e: print("no json",e)
 PY
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2i_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --no-parity > gpurun_out/r2i_ncu.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2i_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph --no-parity --no-model-leg > gpurun_out/r2i_ncu.log 2>&1
 python - <<'PY'
 import csv,re,collections
 lines=[l for l in open('gpurun_out/r2i_launches.csv') if not l.startswith('==')]

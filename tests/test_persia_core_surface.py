@@ -42,8 +42,9 @@ def test_module_layout_matches_prelude(pc):
                  "read_from_file", "dump_to_file", "set_embedding"):
         assert callable(getattr(ctx, name)), name
     assert isinstance(ctx.master_addr, str)
-    with pytest.raises(RuntimeError):
-        PersiaCommonContext(10, 0, 2, None)
+    two = PersiaCommonContext(10, 1, 2, None)  # R GPUs: accepted; the sharded worker is built by the first batch
+    assert two.get_embedding_worker_addr_list() == ["local"]
+    PersiaCommonContext(10, 0, 1, None)
 
 
 def test_prefix_rule_and_batch_semantics(pc):
