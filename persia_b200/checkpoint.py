@@ -166,35 +166,81 @@ def dump_shards(dst_dir, shards, replica_index=0, replica_size=1, chunk=1 << 20)
             f.write(done_yaml(replica_size, len(shards)))
 
 
-def load_shards(src_dir, shards_by_dim, replica_index=0, chunk=1 << 20):
-    """EmbeddingModelManager.load_embedding_from_dir for one replica: every `.emb` of `s{replica_index}` is read and
-    its entries are inserted in list order.  shards_by_dim: {embedding_dim: EmbeddingShard}.  Returns the number of
-    entries loaded.  Errors mirror the reference's (lib.rs:343-372)."""
+def checkpoint_info(src_dir):
+    """load_embedding_checkpoint_info (persia-model-manager/src/lib.rs:200-240): the `embedding_dump_done` marker of the
+    checkpoint (the root's, else shard 0's) -> (num_shards, num_internal_shards)."""
+    for path in (os.path.join(src_dir, DONE_FILE), os.path.join(src_dir, "s0", DONE_FILE)):
+        if os.path.isfile(path):
+            info = {}
+            for line in open(path):
+                if ":" in line and not line.startswith(" "):
+                    k, v = line.split(":", 1)
+                    if v.strip().isdigit():
+                        info[k.strip()] = int(v.strip())
+            if "num_shards" in info:
+                return info["num_shards"], info.get("num_internal_shards", 1)
+    raise RuntimeError(f"LoadingFromUncompeleteCheckpoint({src_dir!r})")
+
+
+def _farmhash64(x):
+    """farmhash 1.1.5 hash64 of the 8 LE bytes of each u64 (sign_to_shard_modulo, embedding_worker_service/mod.rs:341-345)."""
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    k2 = np.uint64(0x9AE16A3B2F90404F)
+    mul = k2 + np.uint64(16)
+
+    def rotr(v, s):
+        return (v >> np.uint64(s)) | (v << np.uint64(64 - s))
+
+    with np.errstate(over="ignore"):
+        a = x + k2
+        c = rotr(x, 37) * mul + a
+        d = (rotr(a, 25) + x) * mul
+        h = (c ^ d) * mul
+        h ^= h >> np.uint64(47)
+        g = (d ^ h) * mul
+        g ^= g >> np.uint64(47)
+        return g * mul
+
+
+def load_shards(src_dir, shards_by_dim, replica_index=0, replica_size=1, chunk=1 << 20):
+    """EmbeddingWorker::load (embedding_worker_service/mod.rs:1150-1259).  A checkpoint written by as many shards as there
+    are replicas now is loaded shard by shard: replica r reads `s{r}` (load_embedding_via_emb_servers ->
+    EmbeddingModelManager.load_embedding_from_dir, lib.rs:259-273).  Any other shard count goes "via the embedding
+    worker": every `.emb` of every shard directory is read and its entries are re-sharded by sign exactly as
+    set_embedding does (farmhash64(sign) % replica_size, mod.rs:1197-1259); here every replica reads all files and
+    keeps what it owns.  shards_by_dim: {embedding_dim: EmbeddingShard}.  Returns the number of entries loaded into
+    this replica.  Errors mirror the reference's (lib.rs:343-372)."""
     import torch
 
-    shard_dir = os.path.join(src_dir, f"s{replica_index}")
-    if not os.path.isfile(os.path.join(shard_dir, DONE_FILE)):
-        raise RuntimeError(f"LoadingFromUncompeleteCheckpoint({shard_dir!r})")
-    files = sorted(x for x in os.listdir(shard_dir) if x.endswith(".emb"))
-    if not files:
-        raise RuntimeError(f"LoadingFromUncompeleteCheckpoint({shard_dir!r})")
+    num_shards, _ = checkpoint_info(src_dir)
+    reshard = num_shards != replica_size
+    dirs = [os.path.join(src_dir, f"s{k}") for k in range(num_shards)] if reshard else [os.path.join(src_dir, f"s{replica_index}")]
     total = 0
-    for name in files:
-        with open(os.path.join(shard_dir, name), "rb") as f:
-            signs, dims, entries = decode_list(f.read())
-        for dim in np.unique(dims):
-            sh = shards_by_dim.get(int(dim))
-            if sh is None:
-                raise RuntimeError(f"checkpoint holds dim-{int(dim)} embeddings but no slot has that dim")
-            pick = np.nonzero(dims == dim)[0]
-            lens = {entries[i].size for i in pick}
-            if lens != {sh.entry_len}:
-                raise RuntimeError(f"dim-{int(dim)} entries of {sorted(lens)} floats, the registered optimizer needs "
-                                   f"{sh.entry_len} (embedding ++ state)")
-            for lo in range(0, pick.size, chunk):
-                sel = pick[lo:lo + chunk]
-                ent = torch.from_numpy(np.stack([entries[i] for i in sel])).to(sh.device)
-                sg = torch.from_numpy(signs[sel].view(np.int64)).to(sh.device)
-                sh.set_entries(sg, ent)
-            total += pick.size
+    for shard_dir in dirs:
+        if not os.path.isfile(os.path.join(shard_dir, DONE_FILE)):
+            raise RuntimeError(f"LoadingFromUncompeleteCheckpoint({shard_dir!r})")
+        files = sorted(x for x in os.listdir(shard_dir) if x.endswith(".emb"))
+        if not files:
+            raise RuntimeError(f"LoadingFromUncompeleteCheckpoint({shard_dir!r})")
+        for name in files:
+            with open(os.path.join(shard_dir, name), "rb") as f:
+                signs, dims, entries = decode_list(f.read())
+            keep = np.ones(signs.size, bool)
+            if reshard and replica_size > 1:
+                keep = (_farmhash64(signs) % np.uint64(replica_size)) == np.uint64(replica_index)
+            for dim in np.unique(dims[keep]) if keep.any() else []:
+                sh = shards_by_dim.get(int(dim))
+                if sh is None:
+                    raise RuntimeError(f"checkpoint holds dim-{int(dim)} embeddings but no slot has that dim")
+                pick = np.nonzero((dims == dim) & keep)[0]
+                lens = {entries[i].size for i in pick}
+                if lens != {sh.entry_len}:
+                    raise RuntimeError(f"dim-{int(dim)} entries of {sorted(lens)} floats, the registered optimizer needs "
+                                       f"{sh.entry_len} (embedding ++ state)")
+                for lo in range(0, pick.size, chunk):
+                    sel = pick[lo:lo + chunk]
+                    ent = torch.from_numpy(np.stack([entries[i] for i in sel])).to(sh.device)
+                    sg = torch.from_numpy(signs[sel].view(np.int64)).to(sh.device)
+                    sh.set_entries(sg, ent)
+                total += pick.size
     return total

@@ -13,7 +13,6 @@ staleness rules (persia_b200/engine.py), `Backward` applies updates in the calle
 write and read the reference's `.emb` checkpoint files (persia_b200/checkpoint.py).
 """
 import os
-import pickle
 import queue
 import sys
 import threading
@@ -294,15 +293,25 @@ class PersiaBatch:  # data.rs:142-266
     def add_meta(self, data=None):
         self.meta_data = bytes(data) if data is not None else None
 
-    def to_bytes(self):
-        return pickle.dumps({"n": self.non_id_type_features, "l": self.labels, "e": self.embedding_tensor,
-                             "m": self.meta_data, "b": self._batch_id})
+    def to_bytes(self):  # data.rs:256-258: the persia-speedy encoding of PersiaBatchImpl (persia_b200/speedy.py)
+        from . import speedy
+
+        e = self.embedding_tensor
+        if e is None and self.id_type_features:
+            raise RuntimeError("call converted_id_type_features2embedding_tensor before to_bytes")
+        return speedy.encode_batch(self.non_id_type_features, e, self.labels, self.meta_data, self._batch_id)
 
     @staticmethod
-    def _from_bytes(b):
-        d = pickle.loads(b)
+    def _from_bytes(b):  # lib.rs:400-407 get_embedding_from_bytes: PersiaBatchImpl::read_from_buffer
+        from . import speedy
+
+        try:
+            non_id, idf, labels, meta, batch_id = speedy.decode_batch(b)
+        except speedy.SpeedyError as e:
+            raise RuntimeError(f"PersiaBatch deserialization failed: {e}")
         p = PersiaBatch()
-        p.non_id_type_features, p.labels, p.embedding_tensor, p.meta_data, p._batch_id = d["n"], d["l"], d["e"], d["m"], d["b"]
+        p.non_id_type_features, p.labels, p.meta_data, p._batch_id = non_id, labels, meta, batch_id
+        p.embedding_tensor = idf if idf is None or idf[0] == "ids" else ("ref", idf[1])
         p.id_type_features = None
         return p
 
@@ -863,7 +872,7 @@ class PersiaCommonContext:
         from . import checkpoint as CK
 
         _S.ensure_config()
-        CK.dump_shards(dst_dir, [g["shard"] for g in _S.all_groups()])
+        CK.dump_shards(dst_dir, [g["shard"] for g in _S.all_groups()], _S.replica_index or 0, max(1, _S.replica_size or 1))
 
     def load(self, src_dir):  # lib.rs:368-378 -> PS load (mod.rs:460-466)
         from . import checkpoint as CK
@@ -872,7 +881,7 @@ class PersiaCommonContext:
         if _S.optimizer is None:
             raise RuntimeError("optimizer not registered: the entry layout (embedding ++ state) is unknown")
         dims = sorted({s.dim for s in _S.slots})
-        CK.load_shards(src_dir, {d: _S.group(d)["shard"] for d in dims})
+        CK.load_shards(src_dir, {d: _S.group(d)["shard"] for d in dims}, _S.replica_index or 0, max(1, _S.replica_size or 1))
 
     def wait_for_serving(self):
         return None

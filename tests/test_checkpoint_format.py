@@ -181,3 +181,53 @@ def test_decoder_follows_any_list_the_reference_can_produce(seed, capacity):
     assert dims.tolist() == [d[1] for d in want]
     for e, d in zip(entries, want):
         assert e.tolist() == d[0]
+
+
+class _FakeShard:
+    """Stands in for EmbeddingShard on the CPU: records what load_shards hands to set_entries."""
+
+    def __init__(self, dim, entry_len):
+        import torch
+
+        self.dim, self.entry_len, self.device = dim, entry_len, torch.device("cpu")
+        self.got = {}
+
+    def set_entries(self, signs, ent):
+        for s, e in zip(signs.numpy().view(np.uint64).tolist(), ent.numpy()):
+            self.got[s] = e.copy()
+
+
+def test_load_reshards_when_the_shard_count_changed(tmp_path, oracle):
+    """A checkpoint written by 3 parameter servers loaded by 2 (and by 1): every entry lands on the replica that
+    farmhash64(sign) % replica_size names (embedding_worker_service/mod.rs:1150-1259), nothing is lost or duplicated;
+    the same count loads shard by shard."""
+    from persia_b200 import checkpoint as CK
+
+    rng = np.random.default_rng(5)
+    dim, L, n_old = 4, 8, 3
+    signs = rng.integers(1, 1 << 60, size=500, dtype=np.uint64)
+    ent = rng.standard_normal((signs.size, L)).astype(np.float32)
+    old_owner = oracle.shard_of(signs, n_old)
+    for r in range(n_old):
+        d = tmp_path / f"s{r}"
+        d.mkdir()
+        m = old_owner == r
+        (d / f"replica_{r}_shard_0.emb").write_bytes(CK.encode_list(signs[m], ent[m], dim))
+        (d / CK.DONE_FILE).write_text(CK.done_yaml(n_old, 1))
+    (tmp_path / CK.DONE_FILE).write_text(CK.done_yaml(n_old, 1))
+    assert CK.checkpoint_info(str(tmp_path)) == (n_old, 1)
+    for new_size in (2, 1):
+        seen = {}
+        for r in range(new_size):
+            sh = _FakeShard(dim, L)
+            n = CK.load_shards(str(tmp_path), {dim: sh}, replica_index=r, replica_size=new_size)
+            assert n == len(sh.got)
+            want_owner = oracle.shard_of(np.array(sorted(sh.got), np.uint64), new_size)
+            assert (want_owner == r).all()
+            seen.update(sh.got)
+        assert len(seen) == signs.size
+        for s, e in zip(signs.tolist(), ent):
+            assert np.array_equal(seen[s], e)
+    sh = _FakeShard(dim, L)  # same shard count: replica 1 reads s1 only
+    assert CK.load_shards(str(tmp_path), {dim: sh}, replica_index=1, replica_size=3) == int((old_owner == 1).sum())
+    assert set(sh.got) == set(signs[old_owner == 1].tolist())
