@@ -331,32 +331,33 @@ __global__ void __launch_bounds__(256) k_reduce_cold(TableDev t, OptimDev op, Hy
 }
 
 // ------------------------------------------------------------------------------------------------
-// hot items: counting-sort order + a cp.async.bulk / mbarrier ring, one CTA per item
+// hot items: counting-sort order, then producer warps -> shared-memory ring of PREPARED rows -> chain warp(s)
 //
-//   order     The forward already set one bit per occurrence in the item's bitmap over its slot's samples (hot_bits,
-//             k_gather_items) — a counting sort that costs B/32 words.  Here the words are loaded (and zeroed for the
-//             next batch), prefix-summed and expanded into the ascending list of sample numbers in shared memory.
-//             (Items that found no room in the bitmap pool come with an unsorted occurrence list instead and set the
-//             bits here.)
-//   loader    (warp 0) streams the gradient rows of HOT_ROWS consecutive occurrences per stage into the ring with
-//             cp.async.bulk, completion in bytes on the stage's mbarrier.  Runs of adjacent samples (the rule for the
-//             signs of a tiny slot) go as ONE copy: the copy engine is bound by operations, not bytes, at this size.
-//   chain     (warp 1) waits for a stage and adds its rows in order: per row one shared-memory load, the EW's value
-//             preparation (f16 -> f32 with +-inf clamped, 1/scale, sqrt factor; mod.rs:751-778) and one dependent FADD
-//             per element — the floor for a strictly sequential f32 sum — then performs the optimizer step.
-//   warps 2, 3 only help with the order phase.
+// A strictly sequential f32 sum costs one dependent FADD (4 cycles) per row and element whatever else happens; the head
+// of the Zipf curve and the signs of a tiny slot have thousands of rows, so everything that is not that FADD is taken
+// off the chain:
+//   order      The forward already set one bit per occurrence in the item's bitmap over its slot's samples (hot_bits,
+//              k_gather_items) — a counting sort that costs B/32 words.  Here the words are loaded (and zeroed for the
+//              next batch), prefix-summed and expanded into the ascending list of sample numbers in shared memory.
+//              (Items that found no room in the bitmap pool come with an unsorted occurrence list and set the bits here.)
+//   producers  (HOT_WARPS - CH warps) take chunks of R consecutive occurrences round robin: 16-byte loads of the
+//              gradient rows straight from global memory, eight in flight per lane, then the EW's value preparation
+//              (f16 -> f32 with +-inf clamped, 1/scale, sqrt factor; mod.rs:751-778) and the f32 values go to the
+//              chunk's ring slot; every lane arrives on the slot's `full` mbarrier.
+//   chain      (CH warps, 128 columns each) waits for the slot and adds its rows in order: one LDS.128 and four
+//              dependent FADDs per row — nothing else — then arrives on `empty`; finally the optimizer step.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t HOT_WIN = 8192;   // samples per bitmap window
 constexpr uint32_t HOT_WORDS = HOT_WIN / 32;
-constexpr uint32_t HOT_THREADS = 128;
+constexpr uint32_t HOT_THREADS = 256;
+constexpr uint32_t HOT_WARPS = HOT_THREADS / 32;
+constexpr uint32_t HOT_MAX_SLOTS = 8;      // ring slots
+constexpr uint32_t HOT_COLS = 512;         // columns per pass (4 chain warps x 128)
 constexpr uint32_t WAIT_SPINS = 1u << 22;  // bounded waits: a lost completion voids the batch (CTR_ERR) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -375,12 +376,6 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
-// rows: global -> shared, completion counted in bytes on the stage's mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
 
 // +-inf -> +-65504 (persia-common lib.rs:163-180), two halves per instruction; finite halves are inside already
 __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
@@ -388,64 +383,121 @@ __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
   return __hmin2(__hmax2(v, __hneg2(lim)), lim);
 }
 
-// EPL consecutive gradient elements of a row (shared memory or global) -> f32, clamped
-template <int EPL, bool F16>
-__device__ __forceinline__ void read_elems(float (&g)[EPL], const unsigned char* rowp, uint32_t e0) {
-  if constexpr (F16) {
-    const __half* p = reinterpret_cast<const __half*>(rowp) + e0;
-    if constexpr (EPL == 8) {
-      uint4 raw = *reinterpret_cast<const uint4*>(p);
-      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+struct HotGeom {
+  uint32_t cols;      // columns of this pass
+  uint32_t stride;    // floats per ring row (cols rounded up to 4)
+  uint32_t R;         // rows per ring slot
+  uint32_t S;         // ring slots
+  uint32_t CH;        // chain warps
+  uint32_t vec;       // producer mode: 1 = 16-byte loads (8 halves / 4 floats), 0 = element by element
+  uint32_t vshift;    // log2(vectors per row) when that is a power of two, else 32
+};
+
+// one chunk: rows k0 .. k0+nv-1 of the sorted list, columns [col0, col0+cols) -> prepared f32 in the ring slot
+template <bool F16>
+__device__ __forceinline__ void produce_chunk(float* slot, const HotGeom& g, const ItemSrc& src, const ReduceArgs& a,
+                                              const uint16_t* sorted, uint32_t k0, uint32_t nv, uint32_t wbase,
+                                              uint32_t col0, uint32_t dim, uint32_t lane) {
+  // per row of the chunk (lane = row): gradient row number and the sample's sqrt factor
+  uint32_t my_row = 0;
+  float my_f = 1.0f;
+  if (lane < nv) {
+    const uint32_t orow = occ_out_row(a, wbase + sorted[k0 + lane]);
+    my_row = orow - src.slot_row0;
+    if (src.do_sqrt) my_f = grad_prep(src, a, orow).sqrt_f;
+  }
+  const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
+  constexpr uint32_t EV = F16 ? 8u : 4u;  // elements per 16-byte vector
+  if (g.vec) {
+    const uint32_t nvr = g.cols / EV;     // vectors per row
+    const uint32_t total = nv * nvr;
+    for (uint32_t v0 = 0; v0 < total; v0 += 256u) {  // eight loads in flight per lane
+      uint4 raw[8];
+      uint32_t rr[8], cc[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 x = __half22float2(clamp_h2(h[q]));
-        g[2 * q] = x.x;
-        g[2 * q + 1] = x.y;
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t v = v0 + (uint32_t)j * 32u + lane;
+        const bool ok = v < total;
+        rr[j] = !ok ? 0u : (g.vshift < 32u ? v >> g.vshift : v / nvr);
+        cc[j] = !ok ? 0xFFFFFFFFu : (g.vshift < 32u ? v & (nvr - 1u) : v % nvr);
+        const uint32_t grow = __shfl_sync(0xffffffffu, my_row, rr[j]);
+        if (ok)
+          raw[j] = __ldg(reinterpret_cast<const uint4*>(gbytes + ((size_t)grow * dim + col0 + cc[j] * EV) * (F16 ? 2u : 4u)));
       }
-    } else if constexpr (EPL == 4) {
-      uint2 raw = *reinterpret_cast<const uint2*>(p);
-      const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float2 x = __half22float2(clamp_h2(h[q]));
-        g[2 * q] = x.x;
-        g[2 * q + 1] = x.y;
+      for (int j = 0; j < 8; ++j) {
+        const float f = __shfl_sync(0xffffffffu, my_f, rr[j]);
+        if (cc[j] == 0xFFFFFFFFu) continue;
+        float x[EV];
+        if constexpr (F16) {
+          const __half2* h = reinterpret_cast<const __half2*>(&raw[j]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 y = __half22float2(clamp_h2(h[q]));
+            x[2 * q] = y.x;
+            x[2 * q + 1] = y.y;
+          }
+        } else {
+          x[0] = __uint_as_float(raw[j].x); x[1] = __uint_as_float(raw[j].y);
+          x[2] = __uint_as_float(raw[j].z); x[3] = __uint_as_float(raw[j].w);
+        }
+        if (src.do_scale) {
+#pragma unroll
+          for (uint32_t q = 0; q < EV; ++q) x[q] = __fmul_rn(x[q], src.inv_scale);
+        }
+        if (src.do_sqrt) {
+#pragma unroll
+          for (uint32_t q = 0; q < EV; ++q) x[q] = __fmul_rn(x[q], f);
+        }
+        float4* dst = reinterpret_cast<float4*>(slot + (size_t)rr[j] * g.stride + cc[j] * EV);
+        dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+        if constexpr (F16) dst[1] = make_float4(x[4], x[5], x[6], x[7]);
       }
-    } else if constexpr (EPL == 2) {
-      float2 x = __half22float2(clamp_h2(*reinterpret_cast<const __half2*>(p)));
-      g[0] = x.x;
-      g[1] = x.y;
-    } else {
-      g[0] = clamp_f16(__half2float(p[0]));
     }
   } else {
-    RowElems<-1, EPL>::template ld<EPL>(reinterpret_cast<const float*>(rowp) + e0, g);
+    const uint32_t total = nv * g.cols;
+    for (uint32_t i0 = 0; i0 < total; i0 += 32u) {  // uniform trip count: the shuffles are warp-wide
+      const uint32_t i = i0 + lane;
+      const bool ok = i < total;
+      const uint32_t r = ok ? i / g.cols : 0u, c = ok ? i % g.cols : 0u;
+      const uint32_t grow = __shfl_sync(0xffffffffu, my_row, r);
+      const float f = __shfl_sync(0xffffffffu, my_f, r);
+      if (!ok) continue;
+      const size_t e = (size_t)grow * dim + col0 + c;
+      float x = F16 ? clamp_f16(__half2float(reinterpret_cast<const __half*>(gbytes)[e])) : reinterpret_cast<const float*>(gbytes)[e];
+      if (src.do_scale) x = __fmul_rn(x, src.inv_scale);
+      if (src.do_sqrt) x = __fmul_rn(x, f);
+      slot[(size_t)r * g.stride + c] = x;
+    }
   }
 }
 
-template <int EPL, bool F16, bool SEND>
-__global__ void __launch_bounds__(HOT_THREADS, 4) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
-                                                              ReduceArgs a, uint32_t rs, uint32_t bulk, uint32_t hr) {
+template <bool F16, bool SEND>
+__global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+                                                              ReduceArgs a, HotGeom geo) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
   __shared__ uint32_t s_item, s_nwin;
   __shared__ uint32_t bitmap[HOT_WORDS], wpre[HOT_WORDS];
   __shared__ uint16_t sorted[HOT_WIN];
-  __shared__ __align__(8) uint64_t bars[16];  // ring full[0..8), empty[8..16)
-  const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
-  unsigned char* ring = smem_raw;  // [rs][hr][rowbytes] landed gradient rows (bulk mode)
-  float* vstage = reinterpret_cast<float*>(smem_raw + (bulk ? (size_t)rs * hr * rowbytes : 0));  // [dim] Adagrad-vectorwise dot
+  __shared__ __align__(8) uint64_t bars[2 * HOT_MAX_SLOTS];  // full[0..8), empty[8..16)
+  float* ring = reinterpret_cast<float*>(smem_raw);                     // [S][R][stride] prepared rows
+  float* vstage = ring + (size_t)geo.S * geo.R * geo.stride;            // [dim] Adagrad-vectorwise dot
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t CH = geo.CH, PW = HOT_WARPS - CH;
   if (tid == 0) {
-    for (uint32_t s = 0; s < 16; ++s) mbar_init(smem_u32(bars + s), 1u);
+    for (uint32_t s = 0; s < HOT_MAX_SLOTS; ++s) {
+      mbar_init(smem_u32(bars + s), 32u);                       // every lane of the producing warp
+      mbar_init(smem_u32(bars + HOT_MAX_SLOTS + s), 32u * CH);  // every lane of every chain warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   build_dead_mask(dead, gr, a, sl.n_slots);  // ends with __syncthreads
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 8);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + HOT_MAX_SLOTS);
   const uint32_t n_hot = a.b.cnt[BC_HOT];
   uint32_t* next = a.b.cnt + BC_NEXT + PB_MAX_SLOTS + a.round;
-  const uint32_t n_pass = (t.dim + 32u * EPL - 1u) / (32u * EPL);
-  uint32_t it = 0;  // ring stages used so far: loader and chain count the same chunks
+  const uint32_t n_pass = (t.dim + HOT_COLS - 1u) / HOT_COLS;
+  uint32_t it = 0;  // ring chunks so far: producers and chain count the same chunks
   bool failed = false;
   for (;;) {
     __syncthreads();  // s_item, bitmap and sorted are free again
@@ -472,27 +524,26 @@ __global__ void __launch_bounds__(HOT_THREADS, 4) k_reduce_hot(TableDev t, Optim
       continue;
     }
     const ItemSrc src = item_src(sl, gr, a, slot);
-    const bool contiguous = !a.occ_outrow;  // one id per sample: the gradient row of occurrence lo + b is row b
-    const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
     float* prow = SEND ? send_grad_ptr(a.x, row, t.dim) : t.rows + (size_t)row * t.stride;
     StepCtx sc;
     sc.vw_state = sc.r1 = sc.r2 = 0.0f;
     if (!SEND) sc = step_ctx(prow, t, op, gr, slot);
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
-      const uint32_t e0 = (pass * 32u + lane) * EPL;
-      const bool own = e0 < t.dim;  // chain lanes past the row's end idle
-      float acc[EPL];
-#pragma unroll
-      for (int q = 0; q < EPL; ++q) acc[q] = 0.0f;
+      const uint32_t col0 = pass * HOT_COLS;
+      HotGeom g = geo;
+      g.cols = min(geo.cols, t.dim - col0);
+      const uint32_t e0 = col0 + (warp * 32u + lane) * 4u;  // chain lanes: four columns each
+      const bool own = warp < CH && e0 < t.dim;
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       for (uint32_t wbase = lo; wbase < hi; wbase += HOT_WIN) {
         const uint32_t wend = min(hi, wbase + HOT_WIN);
         const uint32_t n_words = (wend - wbase + 31u) / 32u;
         // ---- the item's occurrences inside this window, ascending
         if (bm_mode) {
-          uint32_t* g = a.b.hot_bits + base + (wbase - lo) / 32u;
+          uint32_t* gw = a.b.hot_bits + base + (wbase - lo) / 32u;
           for (uint32_t w = tid; w < HOT_WORDS; w += HOT_THREADS) {
-            bitmap[w] = w < n_words ? g[w] : 0u;
-            if (w < n_words && pass + 1 == n_pass) g[w] = 0u;  // all zero again for the next batch
+            bitmap[w] = w < n_words ? gw[w] : 0u;
+            if (w < n_words && pass + 1 == n_pass) gw[w] = 0u;  // all zero again for the next batch
           }
         } else {
           for (uint32_t w = tid; w < HOT_WORDS; w += HOT_THREADS) bitmap[w] = 0u;
@@ -534,92 +585,91 @@ __global__ void __launch_bounds__(HOT_THREADS, 4) k_reduce_hot(TableDev t, Optim
         }
         __syncthreads();
         const uint32_t nwin = s_nwin;
-        const uint32_t n_chunks = (nwin + hr - 1u) / hr;
-        // ---- the pipeline over chunks of hr consecutive occurrences
-        if (warp == 0 && bulk) {
-          for (uint32_t c = 0; c < n_chunks; ++c, ++it) {
-            const uint32_t nv = min(hr, nwin - c * hr), stage = it % rs, par = (it / rs) & 1u;
+        const uint32_t n_chunks = (nwin + g.R - 1u) / g.R;
+        if (warp >= CH) {
+          // ---- producers: chunk c belongs to warp CH + (it % PW)
+          const uint32_t me = warp - CH;
+          for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t i = it + c;
+            if (i % PW != me) continue;
+            const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
             if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
-            if (lane == 0) mbar_expect_tx(full0 + 8u * stage, nv * rowbytes);
-            __syncwarp();
-            for (uint32_t k0 = 0; k0 < hr; k0 += 32) {  // uniform trip count: shuffles and ballots are warp-wide
-              const uint32_t k = k0 + lane;
-              const bool valid = k < nv;
-              const uint32_t orow = valid ? occ_out_row(a, wbase + sorted[c * hr + k]) : 0u;
-              const uint32_t prev = __shfl_up_sync(0xffffffffu, orow, 1);
-              const bool head = valid && (lane == 0 || !contiguous || orow != prev + 1u);
-              const uint32_t hm = __ballot_sync(0xffffffffu, head);
-              const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-              if (head) {
-                const uint32_t later = (lane == 31) ? 0u : (hm >> (lane + 1));
-                const uint32_t len = later ? (uint32_t)__ffs(later) : (uint32_t)__popc(vm) - lane;  // rows up to the next run's head
-                bulk_g2s(smem_u32(ring + ((size_t)stage * hr + k) * rowbytes),
-                         gbytes + (size_t)(orow - src.slot_row0) * rowbytes, len * rowbytes, full0 + 8u * stage);
-              }
-            }
+            produce_chunk<F16>(ring + (size_t)stage * g.R * g.stride, g, src, a, sorted, c * g.R, nv, wbase, col0, t.dim, lane);
+            mbar_arrive(full0 + 8u * stage);
           }
-        } else if (warp == 1) {
+        } else {
           // ---- chain: the rows in ascending order, one dependent add per row and element
-          for (uint32_t c = 0; c < n_chunks; ++c, ++it) {
-            const uint32_t nv = min(hr, nwin - c * hr), stage = it % rs, par = (it / rs) & 1u;
-            if (bulk && !failed && !mbar_wait(full0 + 8u * stage, par)) failed = true;
-            const unsigned char* rows = ring + (size_t)stage * hr * rowbytes;
+          for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t i = it + c;
+            const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
+            if (!failed && !mbar_wait(full0 + 8u * stage, par)) failed = true;
             if (own) {
-              for (uint32_t k = 0; k < nv; k += 8) {  // eight rows per round: loads first, then the dependent adds
-                float g[8][EPL];
-                float f[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                  const uint32_t kk = k + u < nv ? k + u : k;
-                  f[u] = 1.0f;
-                  if (bulk && src.plain) {
-                    read_elems<EPL, F16>(g[u], rows + (size_t)kk * rowbytes, e0);
-                  } else {
-                    const uint32_t orow = occ_out_row(a, wbase + sorted[c * hr + kk]);
-                    if (src.do_sqrt) f[u] = grad_prep(src, a, orow).sqrt_f;
-                    read_elems<EPL, F16>(g[u], bulk ? rows + (size_t)kk * rowbytes : gbytes + (size_t)(orow - src.slot_row0) * rowbytes, e0);
-                  }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (k + u < nv) {
-#pragma unroll
-                    for (int q = 0; q < EPL; ++q) {
-                      float v = g[u][q];
-                      if (src.do_scale) v = __fmul_rn(v, src.inv_scale);
-                      if (src.do_sqrt) v = __fmul_rn(v, f[u]);
-                      acc[q] = __fadd_rn(acc[q], v);
-                    }
-                  }
+              const float* rp = ring + (size_t)stage * g.R * g.stride + (e0 - col0);
+              // groups of eight rows, double buffered: the next group's loads are in flight under this group's adds
+              float4 va[8], vb[8];
+              const uint32_t full = nv & ~7u;
+              uint32_t k = 0;
+#define PB_HOT_LOAD(V, K0)                                                                          \
+  _Pragma("unroll") for (int u = 0; u < 8; ++u) V[u] = *reinterpret_cast<const float4*>(rp + (size_t)((K0) + u) * g.stride);
+#define PB_HOT_ADD(V)                                                                               \
+  _Pragma("unroll") for (int u = 0; u < 8; ++u) {                                                   \
+    acc[0] = __fadd_rn(acc[0], V[u].x); acc[1] = __fadd_rn(acc[1], V[u].y);                         \
+    acc[2] = __fadd_rn(acc[2], V[u].z); acc[3] = __fadd_rn(acc[3], V[u].w);                         \
+  }
+              if (full) { PB_HOT_LOAD(va, 0) }
+              while (k < full) {
+                if (k + 8 < full) { PB_HOT_LOAD(vb, k + 8) }
+                PB_HOT_ADD(va)
+                k += 8;
+                if (k >= full) break;
+                if (k + 8 < full) { PB_HOT_LOAD(va, k + 8) }
+                PB_HOT_ADD(vb)
+                k += 8;
+              }
+#undef PB_HOT_LOAD
+#undef PB_HOT_ADD
+              for (; k < nv; ++k) {
+                const float4 v = *reinterpret_cast<const float4*>(rp + (size_t)k * g.stride);
+                acc[0] = __fadd_rn(acc[0], v.x); acc[1] = __fadd_rn(acc[1], v.y);
+                acc[2] = __fadd_rn(acc[2], v.z); acc[3] = __fadd_rn(acc[3], v.w);
               }
             }
-            if (bulk) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(empty0 + 8u * stage);  // the stage may be refilled
-            }
+            mbar_arrive(empty0 + 8u * stage);  // the slot may be refilled
           }
-        } else if (warp == 0) {
-          it += n_chunks;
         }
-        // (warps 2, 3 wait at the next barrier)
+        it += n_chunks;
       }
-      // ---- the optimizer step on this pass's elements (chain warp)
-      if (SEND) {
-        if (warp == 1 && own) RowElems<-1, EPL>::template st<EPL>(prow + e0, acc);
-      } else if (warp == 1 && own) {
-        RowElems<-1, EPL> rc;
-        rc.load(prow, e0, t, op);
-        if (op.kind == PB_OPT_ADAGRAD_VW) {
+      // ---- the optimizer step on this pass's columns (chain warps).  Columns past dim (dim % 4 != 0) were summed from
+      // the ring's padding and are dropped here.
+      if (own) {
+        const uint32_t nq = min(4u, t.dim - e0);
+        if (SEND) {
+          if (nq == 4) RowElems<-1, 4>::template st<4>(prow + e0, acc);
+          else for (uint32_t q = 0; q < nq; ++q) prow[e0 + q] = acc[q];
+        } else if (nq == 4) {
+          RowElems<-1, 4> rc;
+          rc.load(prow, e0, t, op);
+          if (op.kind == PB_OPT_ADAGRAD_VW) {
 #pragma unroll
-          for (int q = 0; q < EPL; ++q) vstage[e0 + q] = acc[q];
+            for (int q = 0; q < 4; ++q) vstage[e0 + q] = acc[q];
+          }
+          rc.step(e0, acc, t, op, hy, sc);
+          rc.store(prow, e0, t, op);
+        } else {
+          for (uint32_t q = 0; q < nq; ++q) {
+            RowElems<-1, 1> rc;
+            float one[1] = {acc[q]};
+            rc.load(prow, e0 + q, t, op);
+            if (op.kind == PB_OPT_ADAGRAD_VW) vstage[e0 + q] = acc[q];
+            rc.step(e0 + q, one, t, op, hy, sc);
+            rc.store(prow, e0 + q, t, op);
+          }
         }
-        rc.step(e0, acc, t, op, hy, sc);
-        rc.store(prow, e0, t, op);
       }
     }
-    if (!SEND && op.kind == PB_OPT_ADAGRAD_VW && warp == 1) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
-      __syncwarp();
-      if (lane == 0) {
+    if (!SEND && op.kind == PB_OPT_ADAGRAD_VW) {  // state = state*mom + dot(g,g)/dim (optim.rs:280-283)
+      __syncthreads();                            // every chain warp staged its columns
+      if (tid == 0) {
         float gs = __fdiv_rn(vw_dot(vstage, t.dim), (float)t.dim);
         prow[t.dim] = __fadd_rn(__fmul_rn(sc.vw_state, op.mom), gs);
       }
@@ -651,20 +701,29 @@ static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev
 #undef PB_K
 }
 
-template <int EPL, bool F16, bool SEND>
+template <bool F16, bool SEND>
 static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
-                       const ReduceArgs& a, uint32_t bulk, cudaStream_t st) {
-  const uint32_t rowbytes = t.dim * (F16 ? 2u : 4u);
-  uint32_t hr = 64;  // rows per stage (a multiple of 32, or a power of two below it for very long rows)
-  while (hr > 1 && (size_t)hr * rowbytes > 16u * 1024u) hr >>= 1;
-  uint32_t rs = 4;
-  if (getenv("PB_HOT_RS")) rs = (uint32_t)atoi(getenv("PB_HOT_RS"));
-  if (getenv("PB_HOT_HR")) hr = (uint32_t)atoi(getenv("PB_HOT_HR"));
-  if (rs > 8) rs = 8;
-  if (rs < 2) rs = 2;
-  if (!bulk) rs = 1;
-  const size_t smem = (bulk ? (size_t)rs * hr * rowbytes : 0) + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
-  auto kern = k_reduce_hot<EPL, F16, SEND>;
+                       const ReduceArgs& a, uint32_t vec, cudaStream_t st) {
+  HotGeom g;
+  g.cols = t.dim < HOT_COLS ? t.dim : HOT_COLS;
+  g.stride = (g.cols + 3u) & ~3u;
+  g.CH = (g.cols + 127u) / 128u;
+  g.S = HOT_MAX_SLOTS;
+  uint32_t slot_bytes = 8192;
+  if (getenv("PB_HOT_SLOTS")) g.S = (uint32_t)atoi(getenv("PB_HOT_SLOTS"));
+  if (getenv("PB_HOT_SLOT_BYTES")) slot_bytes = (uint32_t)atoi(getenv("PB_HOT_SLOT_BYTES"));
+  if (g.S > HOT_MAX_SLOTS) g.S = HOT_MAX_SLOTS;
+  if (g.S < 2) g.S = 2;
+  g.R = slot_bytes / (g.stride * 4u);
+  if (g.R > 32u) g.R = 32u;  // a chunk's rows are described by the lanes of the producing warp
+  if (g.R < 1u) g.R = 1u;
+  g.vec = vec;
+  const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
+  g.vshift = 32u;
+  if (vec && nvr && !(nvr & (nvr - 1u)))
+    for (g.vshift = 0; (1u << g.vshift) < nvr; ++g.vshift) {}
+  const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
+  auto kern = k_reduce_hot<F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -672,13 +731,13 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured[dev] = smem;
   }
-  uint32_t per_sm = (uint32_t)(200u * 1024u / (smem + 20u * 1024u));  // + the kernel's static shared memory
-  if (per_sm > 4) per_sm = 4;
+  uint32_t per_sm = (uint32_t)(224u * 1024u / (smem + 21u * 1024u));  // + the kernel's static shared memory
+  if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   const uint32_t cap_blocks = cdiv(a.b.n, PB_WARM_MAX + 1);  // at most this many hot items exist
   uint32_t grid = 148u * per_sm;
   if (grid > cap_blocks) grid = cap_blocks ? cap_blocks : 1;
-  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, rs, bulk, hr);
+  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, g);
 }
 
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
@@ -690,30 +749,18 @@ void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& 
   uint32_t G = (uint32_t)Gi < 4u ? 4u : (uint32_t)Gi;
   // hot items first in time when they have their own stream: they are the long poles
   {
-    const uint32_t dim = t.dim;
-    int epl;
-    if (dim % 2 == 0 && dim <= 64) epl = 2;
-    else if (dim % 4 == 0 && dim <= 128) epl = 4;
-    else if (dim % 8 == 0) epl = 8;
-    else if (dim % 2 == 0 && dim > 64) epl = 2;  // several passes
-    else epl = 1;
-    const uint32_t rowbytes = dim * (f16 ? 2u : 4u);
-    uint32_t bulk = rowbytes % 16u == 0 ? 1u : 0u;
-    for (uint32_t s = 0; s < sl.n_slots && bulk; ++s)
-      if (gr.ptr[s] && (reinterpret_cast<uintptr_t>(gr.ptr[s]) & 15u)) bulk = 0;  // cp.async.bulk needs 16 B alignment
-    if (getenv("PB_HOT_NO_BULK")) bulk = 0;
-#define PB_H(E)                                                                         \
-  case E:                                                                               \
-    if (send) {                                                                         \
-      if (f16) hot_launch<E, true, true>(t, op, hy, sl, gr, a, bulk, st_hot);           \
-      else hot_launch<E, false, true>(t, op, hy, sl, gr, a, bulk, st_hot);              \
-    } else {                                                                            \
-      if (f16) hot_launch<E, true, false>(t, op, hy, sl, gr, a, bulk, st_hot);          \
-      else hot_launch<E, false, false>(t, op, hy, sl, gr, a, bulk, st_hot);             \
-    }                                                                                   \
-    break;
-    switch (epl) { PB_H(1) PB_H(2) PB_H(4) PB_H(8) }
-#undef PB_H
+    const uint32_t ev = f16 ? 8u : 4u;  // the producers' 16-byte loads need whole vectors and aligned rows
+    uint32_t hv = t.dim % ev == 0 ? 1u : 0u;
+    for (uint32_t s = 0; s < sl.n_slots && hv; ++s)
+      if (gr.ptr[s] && (reinterpret_cast<uintptr_t>(gr.ptr[s]) & 15u)) hv = 0;
+    if (getenv("PB_HOT_NO_VEC")) hv = 0;
+    if (send) {
+      if (f16) hot_launch<true, true>(t, op, hy, sl, gr, a, hv, st_hot);
+      else hot_launch<false, true>(t, op, hy, sl, gr, a, hv, st_hot);
+    } else {
+      if (f16) hot_launch<true, false>(t, op, hy, sl, gr, a, hv, st_hot);
+      else hot_launch<false, false>(t, op, hy, sl, gr, a, hv, st_hot);
+    }
   }
   if (vec == 4) {
     if (f16) items_dispatch<4, true>(t, op, hy, sl, gr, a, G, st, send);
