@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-roofline-leg", action="store_true", help="N = 1: skip the configs[1] (dim 64) leg")
     ap.add_argument("--no-model-leg", action="store_true", help="N = 1: skip the TrainCtx + DLRM tower leg (e2e_model)")
     ap.add_argument("--no-parity", action="store_true", help="skip the replay of captured steps against the oracle")
+    ap.add_argument("--no-staleness", action="store_true", help="skip the 2 / 4 batches-in-flight measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying CUDA graphs")
     return ap.parse_args()
 
@@ -477,11 +478,61 @@ def run_leg(args, torch, dim, B, rows, name, want_kernels, want_parity):
         parity = None
         if want_parity:
             parity = parity_single(torch, sh, run, outs, ids_host, grads_all, pf, S, B, dim, dev, stream)
+
+    # ---- embedding_staleness > 1 (persia/ctx.py:1021-1040: that many batches between lookup and update): J batches in
+    # flight, each with its own context, stream and graphs.  Not the parity configuration (the reference is not
+    # deterministic there either); reported beside `value`, which stays at staleness 1.
+    in_flight = {}
+    if use_graph and not args.no_staleness:
+        for J in (2, 4):
+            if n_sets < J:
+                break
+            ctxs = [SH.BatchContext(n_occ, n_occ, pf, device=dev) for _ in range(J)]
+            streams = [torch.cuda.Stream(device=dev) for _ in range(J)]
+            gs = [[None] * n_sets for _ in range(J)]
+            for j in range(J):
+                with torch.cuda.stream(streams[j]):
+                    for k in range(j, n_sets, J):
+                        ctxs[j].forward(sh, ids_dev[k], slot_off, B, training=True, out=outs[k])
+                        ctxs[j].backward(sh, grads[k])
+                        streams[j].synchronize()
+                        gph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gph, stream=streams[j]):
+                            ctxs[j].forward(sh, ids_dev[k], slot_off, B, training=True, out=outs[k])
+                            ctxs[j].backward(sh, grads[k])
+                        gs[j][k] = gph
+            torch.cuda.synchronize()
+
+            def fly(n):
+                for i in range(n):
+                    k = i % n_sets
+                    j = k % J
+                    with torch.cuda.stream(streams[j]):
+                        gs[j][k].replay()
+
+            fly(Wm)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            done = [torch.cuda.Event() for _ in range(J)]
+            ev[0].record(streams[0])
+            for j in range(1, J):
+                streams[j].wait_event(ev[0])
+            fly(K)
+            for j in range(1, J):
+                done[j].record(streams[j])
+                streams[0].wait_event(done[j])
+            ev[1].record(streams[0])
+            torch.cuda.synchronize()
+            in_flight[str(J)] = {"ms_per_step": ev[0].elapsed_time(ev[1]) / K,
+                                 "samples_per_s": B * K / (ev[0].elapsed_time(ev[1]) * 1e-3)}
+            del gs
+            for c in ctxs:
+                c.close()
     wait_errors = sh.counters()["wait_errors"]
     assert wait_errors == 0, "an in-kernel wait gave up: the run is void"
     res.update(ms_per_step=ms / K, ms_per_step_reps=reps, ms_e2e=ms_e2e / K, launches_per_step=launches_per_step,
                stats=stats, kernels=kern, clocks=clocks, resident=resident, t_fill=round(t_fill, 2), parity=parity,
-               n_sets=n_sets, graph=graphs is not None,
+               n_sets=n_sets, graph=graphs is not None, in_flight=in_flight,
                l2="inputs larger than L2: %.1f GB table + %d rotating id/grad/output sets (%.0f MB)" % (
                    resident * 4.0 * 2 * dim / 1e9, n_sets, n_sets * 2 * n_occ * dim * 2 / 1e6))
     del graphs, e2e_graphs
@@ -656,6 +707,10 @@ def single_gpu(args, torch):
                 "launch": ("CUDA graph replay, one graph per buffer set" if leg["graph"] else "kernel by kernel") +
                           "; pb_backward forks the hot-sign reduce onto the context's own stream",
                 "reduce_order": "reference order for every multiplicity (bit-exact vs the oracle)",
+                "batches_in_flight": {"note": "embedding_staleness 2 / 4: that many batches in flight on their own contexts and "
+                                              "streams over the same table; `value` is staleness 1 (the parity configuration)",
+                                      **leg["in_flight"],
+                                      "roofline_leg": roof_leg["in_flight"] if roof_leg else None},
                 "roofline_leg": None if not roof_leg else {
                     "workload": "configs[1]: 26 slots, 1e8 rows, dim 64, batch 4096, Adagrad", "ms_per_step": roof_leg["ms_per_step"],
                     "samples_per_s": 4096 / (roof_leg["ms_per_step"] * 1e-3), "ms_per_step_repetitions": roof_leg["ms_per_step_reps"],

@@ -113,7 +113,8 @@ struct pb_ctx {
   float* vw_stage = nullptr;
   size_t vw_stage_floats = 0;
   cudaStream_t side = nullptr;  // hot items + scratch-set clearing run beside the main stream during pb_backward
-  cudaEvent_t ev_fork = nullptr, ev_nan = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;  // the warm items, beside the cold ones
+  cudaEvent_t ev_fork = nullptr, ev_nan = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   // raw slot (pb_forward_raw / pb_backward_raw): allocated on first use
   uint32_t* occ_cell = nullptr;
   RawWork raw{};
@@ -556,6 +557,8 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
     e = cudaDeviceSynchronize();
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_nan, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
@@ -578,6 +581,8 @@ int pb_ctx_destroy(pb_ctx* c) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->side) cudaStreamDestroy(c->side);
+  if (c->side2) cudaStreamDestroy(c->side2);
+  if (c->ev_join2) cudaEventDestroy(c->ev_join2);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_nan) cudaEventDestroy(c->ev_nan);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -741,6 +746,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
   launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
   PB_CUDA(cudaEventRecord(c->ev_nan, st));
   PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_nan, 0));
+  PB_CUDA(cudaStreamWaitEvent(c->side2, c->ev_nan, 0));
   ReduceArgs a;
   std::memset(&a, 0, sizeof(a));
   a.b = c->b;
@@ -758,10 +764,14 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     for (uint32_t s = 0; s < S; ++s)
       if (c->round_of[s] == r) a.round_mask[s >> 5] |= 1u << (s & 31);
     // one round (no shared feature groups, the usual case): hot items run beside the others; several: one after another
-    launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, c->n_rounds == 1 ? c->side : st);
+    // the items of a round are distinct rows, whatever their list.
+    const bool one = c->n_rounds == 1;
+    launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, one ? c->side : st, one ? c->side2 : st, false);
   }
   PB_CUDA(cudaEventRecord(c->ev_join, c->side));
   PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+  PB_CUDA(cudaEventRecord(c->ev_join2, c->side2));
+  PB_CUDA(cudaStreamWaitEvent(st, c->ev_join2, 0));
   drop_pending(c);
   PB_CUDA(cudaGetLastError());
   return PB_OK;
@@ -957,6 +967,7 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
   launch_nan_scan(gr, S, c->batch * t->d.dim, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);  // per slot, on the requester (mod.rs:731-746)
   PB_CUDA(cudaEventRecord(c->ev_nan, st));
   PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_nan, 0));
+  PB_CUDA(cudaStreamWaitEvent(c->side2, c->ev_nan, 0));
   ReduceArgs a;
   std::memset(&a, 0, sizeof(a));
   a.b = c->b;
@@ -969,9 +980,12 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
   a.round = 0;
   for (uint32_t s = 0; s < S; ++s) a.round_mask[s >> 5] |= 1u << (s & 31);
   a.x = x->d;
-  launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, c->side, true);  // requester: gradients -> owners' areas
+  PB_CUDA(cudaStreamWaitEvent(c->side2, c->ev_nan, 0));
+  launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, c->side, c->side2, true);  // requester: gradients -> owners' areas
   PB_CUDA(cudaEventRecord(c->ev_join, c->side));
   PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+  PB_CUDA(cudaEventRecord(c->ev_join2, c->side2));
+  PB_CUDA(cudaStreamWaitEvent(st, c->ev_join2, 0));
   launch_signal(x->d, XC_FLAG_GRAD, nullptr, st);
   }
   if (!(phases & PB_PHASE_SERVE)) {

@@ -130,7 +130,7 @@ void launch_nan_scan(const GradsDev& gr, uint32_t n_slots, uint32_t elems_per_sl
 // pb_reduce.cu: cold + warm items on `st`, hot items on `st_hot` (may equal st)
 // send: sharded requester — a.x names the owners' receive areas, no row is touched here
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
-                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot,
+                         const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot, cudaStream_t st_warm,
                          bool send = false);
 // pb_shard.cu
 void launch_route_items(bool training, const SlotsDev& sl, const BatchDev& b, const XchgDev& x, cudaStream_t st);

@@ -683,18 +683,18 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
 // ------------------------------------------------------------------------------------------------
 template <int VEC, bool F16>
 static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
-                           const ReduceArgs& a, uint32_t G, cudaStream_t st, bool send) {
+                           const ReduceArgs& a, uint32_t G, cudaStream_t st, cudaStream_t st_warm, bool send) {
   // grids sized for the worst case (every occurrence its own item); blocks past the list lengths return at once
   const uint32_t per_block = 256u / G;
   const uint32_t grid_cold = cdiv(a.b.n, per_block), grid_warm = cdiv(a.b.n / 2 + 1, per_block);
   if (send) {
-    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_warm<VEC, F16, PB_OPT_SGD, true>), grid_warm, 256, 0, st, t, op, hy, sl, gr, a, G);
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_warm<VEC, F16, PB_OPT_SGD, true>), grid_warm, 256, 0, st_warm, t, op, hy, sl, gr, a, G);
     PB_LAUNCH_F(FAM_UPDATE, (k_reduce_cold<VEC, F16, PB_OPT_SGD, true>), grid_cold, 256, 0, st, t, op, hy, sl, gr, a, G);
     return;
   }
 #define PB_K(KK)                                                                                                   \
   case KK:                                                                                                         \
-    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_warm<VEC, F16, KK, false>), grid_warm, 256, 0, st, t, op, hy, sl, gr, a, G); \
+    PB_LAUNCH_F(FAM_UPDATE, (k_reduce_warm<VEC, F16, KK, false>), grid_warm, 256, 0, st_warm, t, op, hy, sl, gr, a, G); \
     PB_LAUNCH_F(FAM_UPDATE, (k_reduce_cold<VEC, F16, KK, false>), grid_cold, 256, 0, st, t, op, hy, sl, gr, a, G); \
     break;
   switch (op.kind) { PB_K(PB_OPT_SGD) PB_K(PB_OPT_ADAGRAD) PB_K(PB_OPT_ADAGRAD_VW) PB_K(PB_OPT_ADAM) }
@@ -742,7 +742,7 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
 
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,
                          const GradsDev& gr, bool f16, const ReduceArgs& a, cudaStream_t st, cudaStream_t st_hot,
-                         bool send) {
+                         cudaStream_t st_warm, bool send) {
   if (!a.b.n) return;
   int vec, Gi;
   vec_group(t.dim, vec, Gi);
@@ -763,11 +763,11 @@ void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& 
     }
   }
   if (vec == 4) {
-    if (f16) items_dispatch<4, true>(t, op, hy, sl, gr, a, G, st, send);
-    else items_dispatch<4, false>(t, op, hy, sl, gr, a, G, st, send);
+    if (f16) items_dispatch<4, true>(t, op, hy, sl, gr, a, G, st, st_warm, send);
+    else items_dispatch<4, false>(t, op, hy, sl, gr, a, G, st, st_warm, send);
   } else {
-    if (f16) items_dispatch<1, true>(t, op, hy, sl, gr, a, G, st, send);
-    else items_dispatch<1, false>(t, op, hy, sl, gr, a, G, st, send);
+    if (f16) items_dispatch<1, true>(t, op, hy, sl, gr, a, G, st, st_warm, send);
+    else items_dispatch<1, false>(t, op, hy, sl, gr, a, G, st, st_warm, send);
   }
 }
 

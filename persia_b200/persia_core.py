@@ -932,15 +932,19 @@ class PersiaCommonContext:
         with open(os.path.join(file_dir, file_name), "wb") as f:
             f.write(bytes(content))
 
-    def get_entries(self, signs, dim):
+    def get_entries(self, signs, dim, missing_ok=False):
         """Not part of the reference surface: reads back whole entries (embedding ++ optimizer state) of the given signs
-        from the table of `dim` (tests; the reference has no read-back besides dump)."""
+        from the table of `dim` (tests; the reference has no read-back besides dump).  missing_ok: a list with None
+        for the signs this replica does not hold."""
         import torch
 
         g = _S.group(int(dim))
         dev = torch.device("cuda", g["device"])
         with g["lock"]:
             ent, found = g["shard"].get_entries(torch.from_numpy(np.ascontiguousarray(signs, np.uint64).view(np.int64)).to(dev))
+            if missing_ok:
+                f, e = found.cpu().numpy().astype(bool), ent.cpu().numpy()
+                return [e[k] if f[k] else None for k in range(e.shape[0])]
             if not bool(found.all()):
                 raise RuntimeError("sign not resident")
             return ent.cpu().numpy()
