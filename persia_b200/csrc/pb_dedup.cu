@@ -34,38 +34,41 @@ __global__ void __launch_bounds__(256) k_dedup(SlotsDev sl, BatchDev b, const ui
   const bool valid = i < b.n;
   uint32_t idx = 0xFFFFFFFFu;
   bool won = false, special_sign = false;
+  // the warp's occurrences of one (slot, sign) go to the set ONCE: a tiny-cardinality slot repeats a sign thousands of
+  // times, and same-address atomics serialise in L2.  (32 consecutive occurrences span at most two slots; the slot
+  // number is part of the match through the prefix or, without one, through a second match on the slot.)
+  uint64_t sign = 0ULL;
+  uint32_t slot = 0xFFFFFFFFu;
   if (valid) {
-    uint64_t sign = ids[i];
-    const uint32_t slot = slot_of_occ(sl, i);
+    sign = ids[i];
+    slot = slot_of_occ(sl, i);
     if (PREFIX) {
       const uint64_t p = sl.prefix[slot];
       if (p) sign = mod_mersenne(sign, sl.spacing_bits) + p;  // indices_add_prefix, mod.rs:402-429
     }
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, sign) & __match_any_sync(0xffffffffu, slot);
+  const uint32_t leader = __ffs(peers) - 1;
+  if (valid && lane == leader) {
     uint32_t size;
     const uint32_t off = set_region(sl, slot, size);
     const bool special = sign == KEY_EMPTY;
     special_sign = special;
     const unsigned long long stored = special ? 0ULL : sign;
     idx = special ? off + size : off + __umulhi((uint32_t)(mix64(sign) >> 32), size);
-    for (;;) {
-      volatile unsigned long long* pk = reinterpret_cast<volatile unsigned long long*>(&b.set[idx].key);
-      unsigned long long k = *pk;
-      if (k == stored) break;
-      if (k == KEY_EMPTY) {
-        const unsigned long long old = atomicCAS(&b.set[idx].key, KEY_EMPTY, stored);
-        if (old == KEY_EMPTY) {
-          won = true;
-          break;
-        }
-        if (old == stored) break;
+    for (;;) {  // one round trip per probed cell: the CAS returns what the cell holds
+      const unsigned long long old = atomicCAS(&b.set[idx].key, KEY_EMPTY, stored);
+      if (old == KEY_EMPTY) {
+        won = true;
+        break;
       }
+      if (old == stored) break;
       if (!special) idx = (idx + 1 == off + size) ? off : idx + 1;  // the region has more cells than the slot has ids
     }
-    b.occ_set[i] = idx;
+    atomicAdd(&b.set[idx].count, (uint32_t)__popc(peers));
   }
-  __syncwarp();
-  const uint32_t peers = __match_any_sync(0xffffffffu, idx);
-  if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&b.set[idx].count, (uint32_t)__popc(peers));
+  idx = __shfl_sync(0xffffffffu, idx, leader);
+  if (valid) b.occ_set[i] = idx;
   // item numbers: one global atomic per BLOCK (same-address atomics with a return serialise in L2 at several cycles
   // each: one per warp — thousands on one word — was most of this kernel's time)
   __shared__ uint32_t s_won, s_base;
@@ -97,38 +100,41 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 4) k_probe_items(TableDev t, HyperDev hy, OptimDev op, SlotsDev slots, BatchDev b) {
   const uint32_t tick = t.counters[CTR_TICK];
   const uint32_t n_items = b.cnt[BC_ITEMS];
-  if (blockIdx.x * (blockDim.x / BUCKET) >= n_items) return;  // whole block (the grid is sized for the worst case)
   const uint32_t sub = threadIdx.x % BUCKET;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t gshift = lane & ~(BUCKET - 1);
-  const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) / BUCKET;
-  const bool valid = u < n_items;
-  uint64_t sign = 0ULL;
-  uint32_t cell = 0, cnt = 0, first = 0;
-  if (valid && sub == 0) {
-    cell = b.item_cell[u];
-    const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);        // key (2 words), count, cursor
-    const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);  // target, base, first, item
-    sign = (hi.w >> 31) ? KEY_EMPTY : ((uint64_t)lo.x | ((uint64_t)lo.y << 32));
-    cnt = lo.z;
-    first = hi.z;
-  }
-  sign = __shfl_sync(0xffffffffu, sign, gshift);
-  const ProbeOut r = probe_group<MODE>(t, hy, op, sign, valid, tick, sub, gshift);
-  const bool head = valid && sub == 0;
-  if (MODE != MODE_TRAIN) cnt = 0;  // inference: nothing is kept for a backward
-  uint32_t slot = 0, hot_nwords = 0;
-  if (head && cnt > PB_WARM_MAX) {
-    slot = slot_of_occ(slots, first);
-    hot_nwords = (slots.occ_off[slot + 1] - slots.occ_off[slot] + 31u) / 32u;
-  }
-  const ItemSlots sl = block_item_slots(b, head, cnt, hot_nwords);
-  if (head) {
-    *(reinterpret_cast<uint2*>(&b.set[cell]) + 2) = make_uint2(r.row, sl.base);  // target, base
-    if (r.row == ROW_NONE && MODE != MODE_SET) atomicAdd(&t.counters[CTR_MISS], 1u);  // index_miss_count, per distinct sign
-    if (sl.cls == 1) b.cold[sl.pos] = make_uint2(r.row, first);
-    else if (sl.cls == 2) b.warm[sl.pos] = make_uint4(r.row, sl.base, cnt, 0u);
-    else if (sl.cls == 3) b.hot[sl.pos] = make_uint4(r.row, sl.base, cnt, slot);
+  constexpr uint32_t PER_BLOCK = 256u / BUCKET;
+  // a few blocks per SM stride over the items (their number lives on the device); whole blocks leave together
+  for (uint32_t u0 = blockIdx.x * PER_BLOCK; u0 < n_items; u0 += gridDim.x * PER_BLOCK) {
+    const uint32_t u = u0 + threadIdx.x / BUCKET;
+    const bool valid = u < n_items;
+    uint64_t sign = 0ULL;
+    uint32_t cell = 0, cnt = 0, first = 0;
+    if (valid && sub == 0) {
+      cell = b.item_cell[u];
+      const uint4 lo = *reinterpret_cast<const uint4*>(&b.set[cell]);        // key (2 words), count, cursor
+      const uint4 hi = *(reinterpret_cast<const uint4*>(&b.set[cell]) + 1);  // target, base, first, item
+      sign = (hi.w >> 31) ? KEY_EMPTY : ((uint64_t)lo.x | ((uint64_t)lo.y << 32));
+      cnt = lo.z;
+      first = hi.z;
+    }
+    sign = __shfl_sync(0xffffffffu, sign, gshift);
+    const ProbeOut r = probe_group<MODE>(t, hy, op, sign, valid, tick, sub, gshift);
+    const bool head = valid && sub == 0;
+    if (MODE != MODE_TRAIN) cnt = 0;  // inference: nothing is kept for a backward
+    uint32_t slot = 0, hot_nwords = 0;
+    if (head && cnt > PB_WARM_MAX) {
+      slot = slot_of_occ(slots, first);
+      hot_nwords = (slots.occ_off[slot + 1] - slots.occ_off[slot] + 31u) / 32u;
+    }
+    const ItemSlots sl = block_item_slots(b, head, cnt, hot_nwords);
+    if (head) {
+      *(reinterpret_cast<uint2*>(&b.set[cell]) + 2) = make_uint2(r.row, sl.base);  // target, base
+      if (r.row == ROW_NONE && MODE != MODE_SET) atomicAdd(&t.counters[CTR_MISS], 1u);  // index_miss_count, per distinct sign
+      if (sl.cls == 1) b.cold[sl.pos] = make_uint2(r.row, first);
+      else if (sl.cls == 2) b.warm[sl.pos] = make_uint4(r.row, sl.base, cnt, 0u);
+      else if (sl.cls == 3) b.hot[sl.pos] = make_uint4(r.row, sl.base, cnt, slot);
+    }
   }
 }
 
@@ -273,7 +279,8 @@ void launch_dedup(const SlotsDev& sl, const BatchDev& b, const uint64_t* ids, cu
 void launch_probe_items(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const SlotsDev& sl,
                         const BatchDev& b, cudaStream_t st) {
   if (!b.n) return;
-  const uint32_t grid = cdiv((uint64_t)b.n * BUCKET, 256);  // worst case U = N; blocks past the item count return at once
+  uint32_t grid = cdiv((uint64_t)b.n * BUCKET, 256);  // worst case U = N
+  if (grid > 148u * 4u) grid = 148u * 4u;              // the blocks stride over the items
   if (training) PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_TRAIN>), grid, 256, 0, st, t, hy, op, sl, b);
   else PB_LAUNCH_F(FAM_PROBE, (k_probe_items<MODE_FIND>), grid, 256, 0, st, t, hy, op, sl, b);
 }

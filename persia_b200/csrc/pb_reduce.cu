@@ -222,7 +222,7 @@ __device__ __forceinline__ void step_item(const TableDev& t, const OptimDev& op,
 // ---- warm items: one lane group per item; the group sorts the item's <= 32 occurrences (rank by counting), then adds
 // them in order.  Items are assigned statically (a shared work counter would be thousands of same-address atomics).
 template <int VEC, bool F16, int KIND, bool SEND>
-__global__ void __launch_bounds__(256) k_reduce_warm(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+__global__ void __launch_bounds__(256, 3) k_reduce_warm(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
                                                      ReduceArgs a, uint32_t G) {
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
   __shared__ uint32_t sortbuf[64][2 * PB_WARM_MAX];  // per lane group (G >= 4): unsorted | sorted occurrences
@@ -231,38 +231,40 @@ __global__ void __launch_bounds__(256) k_reduce_warm(TableDev t, OptimDev op, Hy
   build_dead_mask(dead, gr, a, sl.n_slots);
   const uint32_t lane = threadIdx.x % G, grp = threadIdx.x / G, wl = threadIdx.x & 31;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
-  const uint32_t w = blockIdx.x * (blockDim.x / G) + grp;
-  if (w >= n_warm) return;  // whole group
   uint32_t* raw = sortbuf[grp];
   uint32_t* srt = raw + PB_WARM_MAX;
-  const uint4 d = a.b.warm[w];
-  const uint32_t row = d.x, base = d.y, cnt = d.z;
-  for (uint32_t l = lane; l < cnt; l += G) raw[l] = a.b.seg_occ[base + l];
-  __syncwarp(gmask);
-  for (uint32_t l = lane; l < cnt; l += G) {  // occurrences are distinct numbers
-    const uint32_t p = raw[l];
-    uint32_t r = 0;
-    for (uint32_t m = 0; m < cnt; ++m) r += raw[m] < p;
-    srt[r] = p;
-  }
-  __syncwarp(gmask);
-  const uint32_t slot = slot_of_occ(sl, srt[0]);
-  if (SEND) {
-    if (row == ROW_NONE) return;  // the item found no room in its owner's segment (flagged in k_route_items)
-    if (slot_dead(dead, slot)) {
-      if (lane == 0) *send_gok_ptr(a.x, row) = 0u;
-    } else {
-      send_item<VEC, F16>(t, sl, gr, a, row, slot, cnt, lane, G, [&](uint32_t k) { return srt[k]; });
+  // the grid holds a few blocks per SM; a group strides over the list (its length lives on the device)
+  for (uint32_t w = blockIdx.x * (blockDim.x / G) + grp; w < n_warm; w += gridDim.x * (blockDim.x / G)) {
+    __syncwarp(gmask);  // the previous item's sorted list is no longer read
+    const uint4 d = a.b.warm[w];
+    const uint32_t row = d.x, base = d.y, cnt = d.z;
+    for (uint32_t l = lane; l < cnt; l += G) raw[l] = a.b.seg_occ[base + l];
+    __syncwarp(gmask);
+    for (uint32_t l = lane; l < cnt; l += G) {  // occurrences are distinct numbers
+      const uint32_t p = raw[l];
+      uint32_t r = 0;
+      for (uint32_t m = 0; m < cnt; ++m) r += raw[m] < p;
+      srt[r] = p;
     }
-    return;
+    __syncwarp(gmask);
+    const uint32_t slot = slot_of_occ(sl, srt[0]);
+    if (SEND) {
+      if (row == ROW_NONE) continue;  // the item found no room in its owner's segment (flagged in k_route_items)
+      if (slot_dead(dead, slot)) {
+        if (lane == 0) *send_gok_ptr(a.x, row) = 0u;
+      } else {
+        send_item<VEC, F16>(t, sl, gr, a, row, slot, cnt, lane, G, [&](uint32_t k) { return srt[k]; });
+      }
+      continue;
+    }
+    if (slot_dead(dead, slot)) continue;
+    if (row >= t.capacity) {
+      if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
+      continue;
+    }
+    float* stage = a.vw_stage ? a.vw_stage + (size_t)(n_cold + w) * t.dim : nullptr;
+    step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, row, slot, cnt, lane, G, gmask, stage, [&](uint32_t k) { return srt[k]; });
   }
-  if (slot_dead(dead, slot)) return;
-  if (row >= t.capacity) {
-    if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
-    return;
-  }
-  float* stage = a.vw_stage ? a.vw_stage + (size_t)(n_cold + w) * t.dim : nullptr;
-  step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, row, slot, cnt, lane, G, gmask, stage, [&](uint32_t k) { return srt[k]; });
 }
 
 // ---- cold items (one occurrence — the majority): nothing to reduce.  One lane group per item, nothing but two
@@ -277,56 +279,57 @@ __global__ void __launch_bounds__(256) k_reduce_cold(TableDev t, OptimDev op, Hy
   build_dead_mask(dead, gr, a, sl.n_slots);
   const uint32_t lane = threadIdx.x % G, wl = threadIdx.x & 31;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
-  const uint32_t w = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
-  if (w >= n_cold) return;
-  const uint2 d = a.b.cold[w];
-  const uint32_t slot = slot_of_occ(sl, d.y);
   const uint32_t nvec = t.dim / VEC;
-  const ItemSrc src = item_src(sl, gr, a, slot);
-  const uint32_t orow = occ_out_row(a, d.y);
-  const GradPrep prep = grad_prep(src, a, orow);
-  const size_t gelem = (size_t)(orow - src.slot_row0) * t.dim;
-  if (SEND) {
-    if (d.x == ROW_NONE) return;
-    const bool off = slot_dead(dead, slot);
-    if (lane == 0) *send_gok_ptr(a.x, d.x) = off ? 0u : 1u;
-    if (off) return;
-    float* dst = send_grad_ptr(a.x, d.x, t.dim);
+  // the grid holds a few blocks per SM; a group strides over the list (its length lives on the device)
+  for (uint32_t w = blockIdx.x * (blockDim.x / G) + threadIdx.x / G; w < n_cold; w += gridDim.x * (blockDim.x / G)) {
+    const uint2 d = a.b.cold[w];
+    const uint32_t slot = slot_of_occ(sl, d.y);
+    const ItemSrc src = item_src(sl, gr, a, slot);
+    const uint32_t orow = occ_out_row(a, d.y);
+    const GradPrep prep = grad_prep(src, a, orow);
+    const size_t gelem = (size_t)(orow - src.slot_row0) * t.dim;
+    if (SEND) {
+      if (d.x == ROW_NONE) continue;
+      const bool off = slot_dead(dead, slot);
+      if (lane == 0) *send_gok_ptr(a.x, d.x) = off ? 0u : 1u;
+      if (off) continue;
+      float* dst = send_grad_ptr(a.x, d.x, t.dim);
+      for (uint32_t c = lane; c < nvec; c += G) {
+        float g[VEC], acc[VEC];
+        load_grad_elems<VEC, F16>(g, src.gbase, gelem, c * VEC);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;
+        add_prepared<VEC>(acc, g, prep, src.plain);
+        store_vec<VEC>(dst + c * VEC, acc);
+      }
+      continue;
+    }
+    if (slot_dead(dead, slot)) continue;
+    if (d.x >= t.capacity) {
+      if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
+      continue;
+    }
+    if (KIND == PB_OPT_ADAGRAD_VW) {  // needs the whole reduced gradient staged for the dot
+      const uint32_t occ = d.y;
+      step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, d.x, slot, 1u, lane, G, gmask, a.vw_stage + (size_t)w * t.dim,
+                                [&](uint32_t) { return occ; });
+      continue;
+    }
+    float* prow = t.rows + (size_t)d.x * t.stride;
+    StepCtx sc;
+    sc.vw_state = sc.r1 = sc.r2 = 0.0f;
+    if (KIND == PB_OPT_ADAM) sc = step_ctx(prow, t, op, gr, slot);
     for (uint32_t c = lane; c < nvec; c += G) {
+      RowElems<KIND, VEC> rc;
       float g[VEC], acc[VEC];
+      rc.load(prow, c * VEC, t, op);
       load_grad_elems<VEC, F16>(g, src.gbase, gelem, c * VEC);
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;
+      for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;  // the reference adds into a zeroed row (-0 -> +0)
       add_prepared<VEC>(acc, g, prep, src.plain);
-      store_vec<VEC>(dst + c * VEC, acc);
+      rc.step(c * VEC, acc, t, op, hy, sc);
+      rc.store(prow, c * VEC, t, op);
     }
-    return;
-  }
-  if (slot_dead(dead, slot)) return;
-  if (d.x >= t.capacity) {
-    if (lane == 0 && !a.quiet_miss) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);
-    return;
-  }
-  if (KIND == PB_OPT_ADAGRAD_VW) {  // needs the whole reduced gradient staged for the dot
-    const uint32_t occ = d.y;
-    step_item<VEC, F16, KIND>(t, op, hy, sl, gr, a, d.x, slot, 1u, lane, G, gmask, a.vw_stage + (size_t)w * t.dim,
-                              [&](uint32_t) { return occ; });
-    return;
-  }
-  float* prow = t.rows + (size_t)d.x * t.stride;
-  StepCtx sc;
-  sc.vw_state = sc.r1 = sc.r2 = 0.0f;
-  if (KIND == PB_OPT_ADAM) sc = step_ctx(prow, t, op, gr, slot);
-  for (uint32_t c = lane; c < nvec; c += G) {
-    RowElems<KIND, VEC> rc;
-    float g[VEC], acc[VEC];
-    rc.load(prow, c * VEC, t, op);
-    load_grad_elems<VEC, F16>(g, src.gbase, gelem, c * VEC);
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) acc[q] = 0.0f;  // the reference adds into a zeroed row (-0 -> +0)
-    add_prepared<VEC>(acc, g, prep, src.plain);
-    rc.step(c * VEC, acc, t, op, hy, sc);
-    rc.store(prow, c * VEC, t, op);
   }
 }
 
@@ -393,69 +396,82 @@ struct HotGeom {
   uint32_t vshift;    // log2(vectors per row) when that is a power of two, else 32
 };
 
-// one chunk: rows k0 .. k0+nv-1 of the sorted list, columns [col0, col0+cols) -> prepared f32 in the ring slot
+// one chunk: rows k0 .. k0+nv-1 of the sorted list, columns [col0, col0+cols) -> prepared f32 in the ring slot.
+// Vector mode: R * (vectors per row) <= 256, i.e. at most eight 16-byte loads per lane, all issued before the first
+// conversion; vector v = j * 32 + lane of the chunk is row v / nvr, vector v % nvr of the row (POW2: by shift and
+// mask).  Rows nv .. the next multiple of four are written as zeros: the chain adds whole groups of four rows, and
+// x + (+0) = x for every x the accumulator can hold (it starts at +0, so it is never -0).
+template <bool F16, bool POW2>
+__device__ __forceinline__ void produce_vec(float* slot, const HotGeom& g, const ItemSrc& src, uint32_t my_row, float my_f,
+                                            uint32_t nv, uint32_t col0, uint32_t dim, uint32_t lane) {
+  constexpr uint32_t EV = F16 ? 8u : 4u;  // elements per 16-byte vector
+  const unsigned char* gcol = reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)col0 * (F16 ? 2u : 4u);
+  const uint32_t rowbytes = dim * (F16 ? 2u : 4u);
+  const uint32_t nvr = g.cols / EV, total = g.R * nvr, nv4 = (nv + 3u) & ~3u;
+  uint4 raw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t v = (uint32_t)j * 32u + lane;
+    const uint32_t r = POW2 ? v >> g.vshift : v / nvr, c = POW2 ? v & (nvr - 1u) : v % nvr;
+    const uint32_t grow = __shfl_sync(0xffffffffu, my_row, r & 31u);
+    raw[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (v < total && r < nv) raw[j] = __ldg(reinterpret_cast<const uint4*>(gcol + (size_t)grow * rowbytes + c * 16u));
+  }
+  const bool prep = src.do_scale || src.do_sqrt;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t v = (uint32_t)j * 32u + lane;
+    const uint32_t r = POW2 ? v >> g.vshift : v / nvr, c = POW2 ? v & (nvr - 1u) : v % nvr;
+    float f = 1.0f;
+    if (prep) f = __shfl_sync(0xffffffffu, my_f, r & 31u);
+    if (v >= total || r >= nv4) continue;
+    float x[EV];
+    if constexpr (F16) {
+      const __half2* h = reinterpret_cast<const __half2*>(&raw[j]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 y = __half22float2(clamp_h2(h[q]));
+        x[2 * q] = y.x;
+        x[2 * q + 1] = y.y;
+      }
+    } else {
+      x[0] = __uint_as_float(raw[j].x); x[1] = __uint_as_float(raw[j].y);
+      x[2] = __uint_as_float(raw[j].z); x[3] = __uint_as_float(raw[j].w);
+    }
+    if (prep) {
+      if (src.do_scale) {
+#pragma unroll
+        for (uint32_t q = 0; q < EV; ++q) x[q] = __fmul_rn(x[q], src.inv_scale);
+      }
+      if (src.do_sqrt) {
+#pragma unroll
+        for (uint32_t q = 0; q < EV; ++q) x[q] = __fmul_rn(x[q], f);
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(slot + (size_t)r * g.stride + c * EV);
+    dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+    if constexpr (F16) dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+  }
+}
+
 template <bool F16>
 __device__ __forceinline__ void produce_chunk(float* slot, const HotGeom& g, const ItemSrc& src, const ReduceArgs& a,
                                               const uint16_t* sorted, uint32_t k0, uint32_t nv, uint32_t wbase,
                                               uint32_t col0, uint32_t dim, uint32_t lane) {
   // per row of the chunk (lane = row): gradient row number and the sample's sqrt factor
   uint32_t my_row = 0;
-  float my_f = 1.0f;
+  float my_f = 0.0f;  // (zero rows stay zero)
   if (lane < nv) {
     const uint32_t orow = occ_out_row(a, wbase + sorted[k0 + lane]);
     my_row = orow - src.slot_row0;
-    if (src.do_sqrt) my_f = grad_prep(src, a, orow).sqrt_f;
+    my_f = src.do_sqrt ? grad_prep(src, a, orow).sqrt_f : 1.0f;
   }
-  const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
-  constexpr uint32_t EV = F16 ? 8u : 4u;  // elements per 16-byte vector
   if (g.vec) {
-    const uint32_t nvr = g.cols / EV;     // vectors per row
-    const uint32_t total = nv * nvr;
-    for (uint32_t v0 = 0; v0 < total; v0 += 256u) {  // eight loads in flight per lane
-      uint4 raw[8];
-      uint32_t rr[8], cc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t v = v0 + (uint32_t)j * 32u + lane;
-        const bool ok = v < total;
-        rr[j] = !ok ? 0u : (g.vshift < 32u ? v >> g.vshift : v / nvr);
-        cc[j] = !ok ? 0xFFFFFFFFu : (g.vshift < 32u ? v & (nvr - 1u) : v % nvr);
-        const uint32_t grow = __shfl_sync(0xffffffffu, my_row, rr[j]);
-        if (ok)
-          raw[j] = __ldg(reinterpret_cast<const uint4*>(gbytes + ((size_t)grow * dim + col0 + cc[j] * EV) * (F16 ? 2u : 4u)));
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float f = __shfl_sync(0xffffffffu, my_f, rr[j]);
-        if (cc[j] == 0xFFFFFFFFu) continue;
-        float x[EV];
-        if constexpr (F16) {
-          const __half2* h = reinterpret_cast<const __half2*>(&raw[j]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 y = __half22float2(clamp_h2(h[q]));
-            x[2 * q] = y.x;
-            x[2 * q + 1] = y.y;
-          }
-        } else {
-          x[0] = __uint_as_float(raw[j].x); x[1] = __uint_as_float(raw[j].y);
-          x[2] = __uint_as_float(raw[j].z); x[3] = __uint_as_float(raw[j].w);
-        }
-        if (src.do_scale) {
-#pragma unroll
-          for (uint32_t q = 0; q < EV; ++q) x[q] = __fmul_rn(x[q], src.inv_scale);
-        }
-        if (src.do_sqrt) {
-#pragma unroll
-          for (uint32_t q = 0; q < EV; ++q) x[q] = __fmul_rn(x[q], f);
-        }
-        float4* dst = reinterpret_cast<float4*>(slot + (size_t)rr[j] * g.stride + cc[j] * EV);
-        dst[0] = make_float4(x[0], x[1], x[2], x[3]);
-        if constexpr (F16) dst[1] = make_float4(x[4], x[5], x[6], x[7]);
-      }
-    }
+    if (g.vshift < 32u) produce_vec<F16, true>(slot, g, src, my_row, my_f, nv, col0, dim, lane);
+    else produce_vec<F16, false>(slot, g, src, my_row, my_f, nv, col0, dim, lane);
   } else {
-    const uint32_t total = nv * g.cols;
+    const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
+    const uint32_t nv4 = min(g.R, (nv + 3u) & ~3u), total = nv4 * g.cols;
     for (uint32_t i0 = 0; i0 < total; i0 += 32u) {  // uniform trip count: the shuffles are warp-wide
       const uint32_t i = i0 + lane;
       const bool ok = i < total;
@@ -463,10 +479,13 @@ __device__ __forceinline__ void produce_chunk(float* slot, const HotGeom& g, con
       const uint32_t grow = __shfl_sync(0xffffffffu, my_row, r);
       const float f = __shfl_sync(0xffffffffu, my_f, r);
       if (!ok) continue;
-      const size_t e = (size_t)grow * dim + col0 + c;
-      float x = F16 ? clamp_f16(__half2float(reinterpret_cast<const __half*>(gbytes)[e])) : reinterpret_cast<const float*>(gbytes)[e];
-      if (src.do_scale) x = __fmul_rn(x, src.inv_scale);
-      if (src.do_sqrt) x = __fmul_rn(x, f);
+      float x = 0.0f;
+      if (r < nv) {
+        const size_t e = (size_t)grow * dim + col0 + c;
+        x = F16 ? clamp_f16(__half2float(reinterpret_cast<const __half*>(gbytes)[e])) : reinterpret_cast<const float*>(gbytes)[e];
+        if (src.do_scale) x = __fmul_rn(x, src.inv_scale);
+        if (src.do_sqrt) x = __fmul_rn(x, f);
+      }
       slot[(size_t)r * g.stride + c] = x;
     }
   }
@@ -532,6 +551,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
       const uint32_t col0 = pass * HOT_COLS;
       HotGeom g = geo;
       g.cols = min(geo.cols, t.dim - col0);
+      if (g.cols != geo.cols) g.vec = 0;  // the lane map is for full column blocks; a short last block goes element by element
       const uint32_t e0 = col0 + (warp * 32u + lane) * 4u;  // chain lanes: four columns each
       const bool own = warp < CH && e0 < t.dim;
       float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -605,34 +625,32 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
             if (!failed && !mbar_wait(full0 + 8u * stage, par)) failed = true;
             if (own) {
               const float* rp = ring + (size_t)stage * g.R * g.stride + (e0 - col0);
-              // groups of eight rows, double buffered: the next group's loads are in flight under this group's adds
-              float4 va[8], vb[8];
-              const uint32_t full = nv & ~7u;
-              uint32_t k = 0;
-#define PB_HOT_LOAD(V, K0)                                                                          \
-  _Pragma("unroll") for (int u = 0; u < 8; ++u) V[u] = *reinterpret_cast<const float4*>(rp + (size_t)((K0) + u) * g.stride);
-#define PB_HOT_ADD(V)                                                                               \
-  _Pragma("unroll") for (int u = 0; u < 8; ++u) {                                                   \
-    acc[0] = __fadd_rn(acc[0], V[u].x); acc[1] = __fadd_rn(acc[1], V[u].y);                         \
-    acc[2] = __fadd_rn(acc[2], V[u].z); acc[3] = __fadd_rn(acc[3], V[u].w);                         \
+              // groups of four rows (the producer padded the chunk with zero rows), three groups in flight: the loads of
+              // group g + 2 are issued before the adds of group g
+              const uint32_t G = (nv + 3u) >> 2;
+              float4 va[4], vb[4], vc[4];
+#define PB_HOT_LOAD(V, GI)                                                                                \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) V[u] = *reinterpret_cast<const float4*>(rp + (size_t)((GI) * 4u + u) * g.stride);
+#define PB_HOT_ADD(V)                                                                                     \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                         \
+    acc[0] = __fadd_rn(acc[0], V[u].x); acc[1] = __fadd_rn(acc[1], V[u].y);                               \
+    acc[2] = __fadd_rn(acc[2], V[u].z); acc[3] = __fadd_rn(acc[3], V[u].w);                               \
   }
-              if (full) { PB_HOT_LOAD(va, 0) }
-              while (k < full) {
-                if (k + 8 < full) { PB_HOT_LOAD(vb, k + 8) }
+              PB_HOT_LOAD(va, 0)
+              if (G > 1) { PB_HOT_LOAD(vb, 1) }
+              for (uint32_t gi = 0;;) {
+                if (gi + 2 < G) { PB_HOT_LOAD(vc, gi + 2) }
                 PB_HOT_ADD(va)
-                k += 8;
-                if (k >= full) break;
-                if (k + 8 < full) { PB_HOT_LOAD(va, k + 8) }
+                if (++gi >= G) break;
+                if (gi + 2 < G) { PB_HOT_LOAD(va, gi + 2) }
                 PB_HOT_ADD(vb)
-                k += 8;
+                if (++gi >= G) break;
+                if (gi + 2 < G) { PB_HOT_LOAD(vb, gi + 2) }
+                PB_HOT_ADD(vc)
+                if (++gi >= G) break;
               }
 #undef PB_HOT_LOAD
 #undef PB_HOT_ADD
-              for (; k < nv; ++k) {
-                const float4 v = *reinterpret_cast<const float4*>(rp + (size_t)k * g.stride);
-                acc[0] = __fadd_rn(acc[0], v.x); acc[1] = __fadd_rn(acc[1], v.y);
-                acc[2] = __fadd_rn(acc[2], v.z); acc[3] = __fadd_rn(acc[3], v.w);
-              }
             }
             mbar_arrive(empty0 + 8u * stage);  // the slot may be refilled
           }
@@ -686,7 +704,9 @@ static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev
                            const ReduceArgs& a, uint32_t G, cudaStream_t st, cudaStream_t st_warm, bool send) {
   // grids sized for the worst case (every occurrence its own item); blocks past the list lengths return at once
   const uint32_t per_block = 256u / G;
-  const uint32_t grid_cold = cdiv(a.b.n, per_block), grid_warm = cdiv(a.b.n / 2 + 1, per_block);
+  uint32_t grid_cold = cdiv(a.b.n, per_block), grid_warm = cdiv(a.b.n / 2 + 1, per_block);
+  if (grid_cold > 148u * 6u) grid_cold = 148u * 6u;  // groups stride over their list
+  if (grid_warm > 148u * 3u) grid_warm = 148u * 3u;
   if (send) {
     PB_LAUNCH_F(FAM_UPDATE, (k_reduce_warm<VEC, F16, PB_OPT_SGD, true>), grid_warm, 256, 0, st_warm, t, op, hy, sl, gr, a, G);
     PB_LAUNCH_F(FAM_UPDATE, (k_reduce_cold<VEC, F16, PB_OPT_SGD, true>), grid_cold, 256, 0, st, t, op, hy, sl, gr, a, G);
@@ -716,12 +736,20 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
   if (g.S < 2) g.S = 2;
   g.R = slot_bytes / (g.stride * 4u);
   if (g.R > 32u) g.R = 32u;  // a chunk's rows are described by the lanes of the producing warp
-  if (g.R < 1u) g.R = 1u;
   g.vec = vec;
-  const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
+  if (vec) {  // at most eight 16-byte loads per producer lane and chunk
+    const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
+    if (g.R * nvr > 256u) g.R = 256u / nvr;
+  }
+  g.R &= ~3u;  // the chain adds groups of four rows
+  if (g.R < 4u) g.R = 4u;
   g.vshift = 32u;
-  if (vec && nvr && !(nvr & (nvr - 1u)))
-    for (g.vshift = 0; (1u << g.vshift) < nvr; ++g.vshift) {}
+  if (vec) {
+    const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
+    if (g.R * nvr > 256u) g.vec = 0;  // (rows longer than 64 vectors per pass: element by element)
+    if (!(nvr & (nvr - 1u)))
+      for (g.vshift = 0; (1u << g.vshift) < nvr; ++g.vshift) {}
+  }
   const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
   auto kern = k_reduce_hot<F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
