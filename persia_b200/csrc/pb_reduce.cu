@@ -334,33 +334,47 @@ __global__ void __launch_bounds__(256) k_reduce_cold(TableDev t, OptimDev op, Hy
 }
 
 // ------------------------------------------------------------------------------------------------
-// hot items: counting-sort order, then producer warps -> shared-memory ring of PREPARED rows -> chain warp(s)
+// hot items: counting-sort order, then a three-stage shared-memory pipeline per item
 //
 // A strictly sequential f32 sum costs one dependent FADD (4 cycles) per row and element whatever else happens; the head
 // of the Zipf curve and the signs of a tiny slot have thousands of rows, so everything that is not that FADD is taken
-// off the chain:
+// off the chain, and a single warp only sustains an instruction every few cycles, so the rest is spread over warps:
 //   order      The forward already set one bit per occurrence in the item's bitmap over its slot's samples (hot_bits,
 //              k_gather_items) — a counting sort that costs B/32 words.  Here the words are loaded (and zeroed for the
 //              next batch), prefix-summed and expanded into the ascending list of sample numbers in shared memory.
 //              (Items that found no room in the bitmap pool come with an unsorted occurrence list and set the bits here.)
-//   producers  (HOT_WARPS - CH warps) take chunks of R consecutive occurrences round robin: 16-byte loads of the
-//              gradient rows straight from global memory, eight in flight per lane, then the EW's value preparation
-//              (f16 -> f32 with +-inf clamped, 1/scale, sqrt factor; mod.rs:751-778) and the f32 values go to the
-//              chunk's ring slot; every lane arrives on the slot's `full` mbarrier.
-//   chain      (CH warps, 128 columns each) waits for the slot and adds its rows in order: one LDS.128 and four
-//              dependent FADDs per row — nothing else — then arrives on `empty`; finally the optimizer step.
+//   loader     (one warp) streams the raw gradient rows, R per chunk, into the RAW ring with cp.async.bulk (SASS:
+//              UBLKCP), completion counted in bytes on the chunk's mbarrier; no registers, no waiting: ten chunks are in
+//              flight.  Runs of adjacent samples (the rule for the signs of a tiny slot) go as ONE copy — the copy
+//              engine is bound by operations, not bytes, at this size.
+//   converters (the other warps, a chunk each, round robin) turn a landed chunk into PREPARED f32 rows in the second
+//              ring: the EW's value preparation (f16 -> f32 with +-inf clamped, 1/scale, sqrt factor; mod.rs:751-778).
+//   chain      (CH warps, 128 columns each) waits for the prepared chunk and adds its rows in order: one LDS.128 and four
+//              dependent FADDs per row — nothing else — then performs the optimizer step.
+// Gradients that cannot be bulk-copied (rows not a multiple of 16 bytes, unaligned tensors, rows longer than one pass)
+// take the direct mode: the producer warps load from global memory themselves (16-byte or element loads).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t HOT_WIN = 8192;   // samples per bitmap window
 constexpr uint32_t HOT_WORDS = HOT_WIN / 32;
 constexpr uint32_t HOT_THREADS = 256;
 constexpr uint32_t HOT_WARPS = HOT_THREADS / 32;
-constexpr uint32_t HOT_MAX_SLOTS = 8;      // ring slots
+constexpr uint32_t HOT_MAX_SLOTS = 8;      // prepared-ring slots
+constexpr uint32_t HOT_MAX_RAW = 12;       // raw-ring slots
 constexpr uint32_t HOT_COLS = 512;         // columns per pass (4 chain warps x 128)
 constexpr uint32_t WAIT_SPINS = 1u << 22;  // bounded waits: a lost completion voids the batch (CTR_ERR) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// rows: global -> shared, completion counted in bytes on the chunk's mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -390,7 +404,9 @@ struct HotGeom {
   uint32_t cols;      // columns of this pass
   uint32_t stride;    // floats per ring row (cols rounded up to 4)
   uint32_t R;         // rows per ring slot
-  uint32_t S;         // ring slots
+  uint32_t S;         // prepared-ring slots
+  uint32_t SR;        // raw-ring slots (bulk mode; 0 = direct mode)
+  uint32_t rowbytes;  // bytes of a gradient row
   uint32_t CH;        // chain warps
   uint32_t vec;       // producer mode: 1 = 16-byte loads (8 halves / 4 floats), 0 = element by element
   uint32_t vshift;    // log2(vectors per row) when that is a power of two, else 32
@@ -491,28 +507,89 @@ __device__ __forceinline__ void produce_chunk(float* slot, const HotGeom& g, con
   }
 }
 
+// bulk mode, converter: a landed chunk (dense [R][dim] raw rows) -> prepared f32 rows (dense [R][dim]); vector v of the
+// chunk is bytes [16 v, 16 v + 16) of the raw slot.  fac: the rows' sqrt factors (written by the loader) when the slot
+// scales by 1/sqrt(ids per sample).  Rows nv .. the next multiple of four become zeros (see produce_vec).
+template <bool F16>
+__device__ __forceinline__ void convert_chunk(float* dst, const unsigned char* raw, const float* fac, const HotGeom& g,
+                                              const ItemSrc& src, uint32_t nv, uint32_t lane) {
+  constexpr uint32_t EV = F16 ? 8u : 4u;
+  const uint32_t nvr = g.cols / EV, nv4 = (nv + 3u) & ~3u;
+  const uint32_t live = nv * nvr, total = nv4 * nvr;
+  const bool prep = src.do_scale || src.do_sqrt;
+  for (uint32_t v0 = 0; v0 < total; v0 += 256u) {
+    uint4 x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t v = v0 + (uint32_t)j * 32u + lane;
+      x[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (v < live) x[j] = *reinterpret_cast<const uint4*>(raw + (size_t)v * 16u);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t v = v0 + (uint32_t)j * 32u + lane;
+      if (v >= total) continue;
+      float y[EV];
+      if constexpr (F16) {
+        const __half2* h = reinterpret_cast<const __half2*>(&x[j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 z = __half22float2(clamp_h2(h[q]));
+          y[2 * q] = z.x;
+          y[2 * q + 1] = z.y;
+        }
+      } else {
+        y[0] = __uint_as_float(x[j].x); y[1] = __uint_as_float(x[j].y);
+        y[2] = __uint_as_float(x[j].z); y[3] = __uint_as_float(x[j].w);
+      }
+      if (prep && v < live) {  // (the zero rows stay zero)
+        if (src.do_scale) {
+#pragma unroll
+          for (uint32_t q = 0; q < EV; ++q) y[q] = __fmul_rn(y[q], src.inv_scale);
+        }
+        if (src.do_sqrt) {
+          const float f = fac[g.vshift < 32u ? v >> g.vshift : v / nvr];
+#pragma unroll
+          for (uint32_t q = 0; q < EV; ++q) y[q] = __fmul_rn(y[q], f);
+        }
+      }
+      float4* o = reinterpret_cast<float4*>(dst + (size_t)v * EV);
+      o[0] = make_float4(y[0], y[1], y[2], y[3]);
+      if constexpr (F16) o[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+  }
+}
+
 template <bool F16, bool SEND>
 __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
-                                                              ReduceArgs a, HotGeom geo) {
+                                                              ReduceArgs a, HotGeom geo, unsigned long long* trace) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
   __shared__ uint32_t s_item, s_nwin;
   __shared__ uint32_t bitmap[HOT_WORDS], wpre[HOT_WORDS];
   __shared__ uint16_t sorted[HOT_WIN];
-  __shared__ __align__(8) uint64_t bars[2 * HOT_MAX_SLOTS];  // full[0..8), empty[8..16)
+  __shared__ __align__(8) uint64_t bars[2 * HOT_MAX_SLOTS + 2 * HOT_MAX_RAW];  // full | empty | raw full | raw empty
   float* ring = reinterpret_cast<float*>(smem_raw);                     // [S][R][stride] prepared rows
   float* vstage = ring + (size_t)geo.S * geo.R * geo.stride;            // [dim] Adagrad-vectorwise dot
+  float* facs = vstage + ((t.dim + 3u) & ~3u);                          // [SR][32] sqrt factors of the rows of a raw slot
+  unsigned char* rawring = reinterpret_cast<unsigned char*>(facs + geo.SR * 32u);  // [SR][R][rowbytes] (16-byte aligned)
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t CH = geo.CH, PW = HOT_WARPS - CH;
+  const bool bulk = geo.SR != 0;
+  const uint32_t CH = geo.CH, PW = HOT_WARPS - CH - (bulk ? 1u : 0u);  // producers (direct) / converters (bulk)
   if (tid == 0) {
     for (uint32_t s = 0; s < HOT_MAX_SLOTS; ++s) {
       mbar_init(smem_u32(bars + s), 32u);                       // every lane of the producing warp
       mbar_init(smem_u32(bars + HOT_MAX_SLOTS + s), 32u * CH);  // every lane of every chain warp
     }
+    for (uint32_t s = 0; s < HOT_MAX_RAW; ++s) {
+      mbar_init(smem_u32(bars + 2 * HOT_MAX_SLOTS + s), 1u);                  // the loader's expect_tx + the bytes
+      mbar_init(smem_u32(bars + 2 * HOT_MAX_SLOTS + HOT_MAX_RAW + s), 32u);   // every lane of the converting warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   build_dead_mask(dead, gr, a, sl.n_slots);  // ends with __syncthreads
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + HOT_MAX_SLOTS);
+  const uint32_t rfull0 = smem_u32(bars + 2 * HOT_MAX_SLOTS), rempty0 = smem_u32(bars + 2 * HOT_MAX_SLOTS + HOT_MAX_RAW);
   const uint32_t n_hot = a.b.cnt[BC_HOT];
   uint32_t* next = a.b.cnt + BC_NEXT + PB_MAX_SLOTS + a.round;
   const uint32_t n_pass = (t.dim + HOT_COLS - 1u) / HOT_COLS;
@@ -524,6 +601,11 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
     __syncthreads();
     const uint32_t h = s_item;
     if (h >= n_hot) break;
+    if (trace && tid == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[8 * h] = now;
+    }
     const uint4 d = a.b.hot[h];
     const uint32_t row = d.x, cnt = d.z, slot = d.w;
     const bool bm_mode = d.y >> 31;
@@ -606,8 +688,61 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
         __syncthreads();
         const uint32_t nwin = s_nwin;
         const uint32_t n_chunks = (nwin + g.R - 1u) / g.R;
-        if (warp >= CH) {
-          // ---- producers: chunk c belongs to warp CH + (it % PW)
+        if (trace && tid == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          trace[8 * h + 1] = now;
+        }
+        if (warp >= CH && bulk && warp == CH) {
+          // ---- loader: 32 rows per round (32 / R chunks), one bulk copy per run of adjacent gradient rows
+          const bool contiguous = !a.occ_outrow;  // one id per sample: the gradient row of occurrence lo + b is row b
+          const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
+          const uint32_t cpr = 32u / g.R;  // chunks per round
+          for (uint32_t c0 = 0; c0 < n_chunks; c0 += cpr) {
+            for (uint32_t q = 0; q < cpr && c0 + q < n_chunks; ++q) {  // the round's slots must be free; announce their bytes
+              const uint32_t i = it + c0 + q, rs = i % g.SR, rpar = (i / g.SR) & 1u;
+              if (!failed && !mbar_wait(rempty0 + 8u * rs, rpar ^ 1u)) failed = true;
+            }
+            const uint32_t k = c0 * g.R + lane;  // this lane's row of the window
+            const bool valid = k < nwin;
+            const uint32_t orow = valid ? occ_out_row(a, wbase + sorted[k]) : 0u;
+            const uint32_t i = it + k / g.R, rs = i % g.SR, kr = k % g.R;
+            if (src.do_sqrt && valid) facs[rs * 32u + kr] = grad_prep(src, a, orow).sqrt_f;
+            __syncwarp();
+            if (valid && kr == 0) mbar_expect_tx(rfull0 + 8u * rs, min(g.R, nwin - k) * g.rowbytes);
+            __syncwarp();
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, orow, 1);
+            const bool head = valid && (lane == 0 || kr == 0 || !contiguous || orow != prev + 1u);
+            const uint32_t hm = __ballot_sync(0xffffffffu, head);
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            if (head) {
+              const uint32_t later = (lane == 31) ? 0u : (hm >> (lane + 1));
+              const uint32_t len = later ? (uint32_t)__ffs(later) : (uint32_t)__popc(vm) - lane;  // rows up to the next head
+              bulk_g2s(smem_u32(rawring + ((size_t)rs * g.R + kr) * g.rowbytes),
+                       gbytes + (size_t)(orow - src.slot_row0) * g.rowbytes, len * g.rowbytes, rfull0 + 8u * rs);
+            }
+            if (trace && c0 == 0 && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 4] = now; }
+
+          }
+        } else if (warp >= CH && bulk) {
+          // ---- converters: chunk c belongs to warp CH + 1 + (it % PW)
+          const uint32_t me = warp - CH - 1u;
+          for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t i = it + c;
+            if (i % PW != me) continue;
+            const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
+            const uint32_t rs = i % g.SR, rpar = (i / g.SR) & 1u;
+            if (!failed && !mbar_wait(rfull0 + 8u * rs, rpar)) failed = true;          // the raw rows have landed
+            if (trace && c == 0 && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 5] = now; }
+            if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;   // the prepared slot is free
+            convert_chunk<F16>(ring + (size_t)stage * g.R * g.stride, rawring + (size_t)rs * g.R * g.rowbytes, facs + rs * 32u,
+                               g, src, nv, lane);
+            if (trace && c == 0 && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 6] = now; }
+            mbar_arrive(full0 + 8u * stage);
+            mbar_arrive(rempty0 + 8u * rs);
+          }
+        } else if (warp >= CH) {
+          // ---- producers (direct mode): chunk c belongs to warp CH + (it % PW)
           const uint32_t me = warp - CH;
           for (uint32_t c = 0; c < n_chunks; ++c) {
             const uint32_t i = it + c;
@@ -623,6 +758,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
             const uint32_t i = it + c;
             const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
             if (!failed && !mbar_wait(full0 + 8u * stage, par)) failed = true;
+            if (trace && c == 0 && tid == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 7] = now; }
             if (own) {
               const float* rp = ring + (size_t)stage * g.R * g.stride + (e0 - col0);
               // groups of four rows (the producer padded the chunk with zero rows), three groups in flight: the loads of
@@ -656,6 +792,12 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
           }
         }
         it += n_chunks;
+      }
+      if (trace && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        trace[8 * h + 2] = now;
+        trace[8 * h + 3] = ((unsigned long long)blockIdx.x << 32) | cnt;
       }
       // ---- the optimizer step on this pass's columns (chain warps).  Columns past dim (dim % 4 != 0) were summed from
       // the ring's padding and are dropped here.
@@ -721,6 +863,9 @@ static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev
 #undef PB_K
 }
 
+static unsigned long long* g_hot_trace = nullptr;  // debugging aid: per hot item {start, sorted, summed} globaltimer stamps
+void set_hot_trace(unsigned long long* p) { g_hot_trace = p; }
+
 template <bool F16, bool SEND>
 static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
                        const ReduceArgs& a, uint32_t vec, cudaStream_t st) {
@@ -728,29 +873,38 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
   g.cols = t.dim < HOT_COLS ? t.dim : HOT_COLS;
   g.stride = (g.cols + 3u) & ~3u;
   g.CH = (g.cols + 127u) / 128u;
-  g.S = HOT_MAX_SLOTS;
-  uint32_t slot_bytes = 8192;
-  if (getenv("PB_HOT_SLOTS")) g.S = (uint32_t)atoi(getenv("PB_HOT_SLOTS"));
-  if (getenv("PB_HOT_SLOT_BYTES")) slot_bytes = (uint32_t)atoi(getenv("PB_HOT_SLOT_BYTES"));
-  if (g.S > HOT_MAX_SLOTS) g.S = HOT_MAX_SLOTS;
-  if (g.S < 2) g.S = 2;
-  g.R = slot_bytes / (g.stride * 4u);
-  if (g.R > 32u) g.R = 32u;  // a chunk's rows are described by the lanes of the producing warp
+  g.rowbytes = t.dim * (F16 ? 2u : 4u);
   g.vec = vec;
-  if (vec) {  // at most eight 16-byte loads per producer lane and chunk
-    const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
-    if (g.R * nvr > 256u) g.R = 256u / nvr;
-  }
-  g.R &= ~3u;  // the chain adds groups of four rows
-  if (g.R < 4u) g.R = 4u;
+  const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
   g.vshift = 32u;
-  if (vec) {
-    const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
-    if (g.R * nvr > 256u) g.vec = 0;  // (rows longer than 64 vectors per pass: element by element)
-    if (!(nvr & (nvr - 1u)))
-      for (g.vshift = 0; (1u << g.vshift) < nvr; ++g.vshift) {}
+  if (vec && nvr && !(nvr & (nvr - 1u)))
+    for (g.vshift = 0; (1u << g.vshift) < nvr; ++g.vshift) {}
+  // bulk mode: whole rows by cp.async.bulk (16-byte rows and tensors: `vec`), one pass, R a power of two
+  const bool bulk = vec && t.dim <= HOT_COLS && !getenv("PB_HOT_NO_BULK");
+  size_t raw_bytes = 0;
+  if (bulk) {
+    g.R = 32u;
+    while (g.R > 4u && g.R * g.rowbytes > 4096u) g.R >>= 1;
+    g.S = 4;
+    g.SR = 10;
+    if (getenv("PB_HOT_SLOTS")) g.S = (uint32_t)atoi(getenv("PB_HOT_SLOTS"));
+    if (getenv("PB_HOT_RAW")) g.SR = (uint32_t)atoi(getenv("PB_HOT_RAW"));
+    if (g.S > HOT_MAX_SLOTS) g.S = HOT_MAX_SLOTS;
+    if (g.S < 2) g.S = 2;
+    if (g.SR > HOT_MAX_RAW) g.SR = HOT_MAX_RAW;
+    if (g.SR < 2) g.SR = 2;
+    raw_bytes = (size_t)g.SR * g.R * g.rowbytes + (size_t)g.SR * 32u * 4u;
+  } else {
+    g.S = HOT_MAX_SLOTS;
+    g.SR = 0;
+    g.R = 8192u / (g.stride * 4u);
+    if (g.R > 32u) g.R = 32u;  // a chunk's rows are described by the lanes of the producing warp
+    if (vec && g.R * nvr > 256u) g.R = 256u / nvr;  // at most eight 16-byte loads per producer lane and chunk
+    g.R &= ~3u;  // the chain adds groups of four rows
+    if (g.R < 4u) g.R = 4u;
+    if (vec && g.R * nvr > 256u) g.vec = 0;  // (rows longer than 64 vectors per pass: element by element)
   }
-  const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
+  const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u + raw_bytes;
   auto kern = k_reduce_hot<F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
@@ -765,7 +919,7 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
   const uint32_t cap_blocks = cdiv(a.b.n, PB_WARM_MAX + 1);  // at most this many hot items exist
   uint32_t grid = 148u * per_sm;
   if (grid > cap_blocks) grid = cap_blocks ? cap_blocks : 1;
-  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, g);
+  PB_LAUNCH_F(FAM_HOT, kern, grid, HOT_THREADS, smem, st, t, op, hy, sl, gr, a, g, g_hot_trace);
 }
 
 void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl,

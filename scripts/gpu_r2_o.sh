@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export CUDA_DEVICE_MAX_CONNECTIONS=32
+timeout 300 python scripts/hot_trace.py 64 4096 > gpurun_out/r2o_trace64.txt 2>&1; cat gpurun_out/r2o_trace64.txt | tail -26
