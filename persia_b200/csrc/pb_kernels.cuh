@@ -30,6 +30,7 @@ struct GradsDev {
 // Filled by the forward (dedup -> probe -> gather), consumed by the backward.  A distinct (sign, slot) pair of the
 // batch is an "item"; the occurrences of an item with count > 1 are listed in seg_occ[base, base + count) in
 // arbitrary order (the reducing kernels put them in ascending order, the reference's summation order).
+constexpr uint32_t PB_HUGE_MIN = 256;  // hot items above this are the long poles of the backward: they start first
 constexpr uint32_t PB_WARM_MAX = 32;  // items of 2..PB_WARM_MAX occurrences are reduced by a lane group, larger ones by a CTA
 enum {
   BC_ITEMS = 0,  // distinct items of the batch
@@ -37,7 +38,7 @@ enum {
   BC_WARM,       // items of 2..PB_WARM_MAX occurrences
   BC_HOT,        // items of more
   BC_SEG,        // entries of seg_occ handed out
-  BC_SENT,       // (unused)
+  BC_HUGE,       // hot items of more than PB_HUGE_MIN occurrences: listed from the END of `hot`, reduced first
   BC_HOTW,       // words of the hot-item bitmap pool handed out
   BC_PEER = 8,
   BC_NEXT = 24,  // work cursors of the reducing kernels: [round] warm, [PB_MAX_SLOTS + round] hot
@@ -53,6 +54,7 @@ struct BatchDev {
   uint4* hot;           // [n/PB_WARM_MAX] (target, base | bitmap word offset + bit 31, count, slot)
   uint32_t* hot_bits;   // [hot_words] one bit per sample of the slot for hot items in bitmap mode (all zero between batches)
   uint32_t hot_words;
+  uint32_t hot_cap;     // entries of `hot`
   uint32_t* cnt;        // BC_* words
   uint32_t n;           // id occurrences of the batch
 };

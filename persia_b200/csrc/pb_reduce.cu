@@ -334,47 +334,38 @@ __global__ void __launch_bounds__(256) k_reduce_cold(TableDev t, OptimDev op, Hy
 }
 
 // ------------------------------------------------------------------------------------------------
-// hot items: counting-sort order, then a three-stage shared-memory pipeline per item
+// hot items: counting-sort order, then producer warps -> shared-memory ring of PREPARED rows -> chain warp(s)
 //
-// A strictly sequential f32 sum costs one dependent FADD (4 cycles) per row and element whatever else happens; the head
-// of the Zipf curve and the signs of a tiny slot have thousands of rows, so everything that is not that FADD is taken
-// off the chain, and a single warp only sustains an instruction every few cycles, so the rest is spread over warps:
+// A strictly sequential f32 sum costs one dependent FADD per row and element whatever else happens (measured: 6.6
+// cycles per row for a warp that does nothing but LDS + FADD, scripts/ubench/hot_ubench.cu); the head of the Zipf curve
+// and the signs of a tiny slot have thousands of rows.  A lone warp sustains only an instruction every ~2 cycles, so
+// everything that is not that FADD is taken off the chain and spread over the block's other warps:
 //   order      The forward already set one bit per occurrence in the item's bitmap over its slot's samples (hot_bits,
 //              k_gather_items) — a counting sort that costs B/32 words.  Here the words are loaded (and zeroed for the
 //              next batch), prefix-summed and expanded into the ascending list of sample numbers in shared memory.
 //              (Items that found no room in the bitmap pool come with an unsorted occurrence list and set the bits here.)
-//   loader     (one warp) streams the raw gradient rows, R per chunk, into the RAW ring with cp.async.bulk (SASS:
-//              UBLKCP), completion counted in bytes on the chunk's mbarrier; no registers, no waiting: ten chunks are in
-//              flight.  Runs of adjacent samples (the rule for the signs of a tiny slot) go as ONE copy — the copy
-//              engine is bound by operations, not bytes, at this size.
-//   converters (the other warps, a chunk each, round robin) turn a landed chunk into PREPARED f32 rows in the second
-//              ring: the EW's value preparation (f16 -> f32 with +-inf clamped, 1/scale, sqrt factor; mod.rs:751-778).
-//   chain      (CH warps, 128 columns each) waits for the prepared chunk and adds its rows in order: one LDS.128 and four
-//              dependent FADDs per row — nothing else — then performs the optimizer step.
-// Gradients that cannot be bulk-copied (rows not a multiple of 16 bytes, unaligned tensors, rows longer than one pass)
-// take the direct mode: the producer warps load from global memory themselves (16-byte or element loads).
+//   producers  (HOT_WARPS - CH warps) take chunks of R consecutive occurrences round robin: 16-byte loads of the
+//              gradient rows straight from global memory, eight in flight per lane, then the EW's value preparation
+//              (f16 -> f32 with +-inf clamped, 1/scale, sqrt factor; mod.rs:751-778) and the f32 values go to the
+//              chunk's ring slot; every lane arrives on the slot's `full` mbarrier.  The common case (one id per
+//              sample, no scaling) has its own lean loop: ~25 instructions per 16 bytes is what bounds a producer.
+//   chain      (CH warps, 32 * EPL columns each) waits for the slot and adds its rows in order: one LDS and EPL
+//              dependent FADDs per row — nothing else — then arrives on `empty`; finally the optimizer step.
+// Measured alternatives (profiles/r2_hot_ubench_*.txt): cp.async.bulk of the rows into a raw ring + converter warps is
+// bound by the copy engine's issue rate (~60 cycles per 128-byte copy and SM), a single warp doing load + convert + add
+// by the instruction stream (~40 cycles per row).
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t HOT_WIN = 8192;   // samples per bitmap window
 constexpr uint32_t HOT_WORDS = HOT_WIN / 32;
 constexpr uint32_t HOT_THREADS = 256;
 constexpr uint32_t HOT_WARPS = HOT_THREADS / 32;
-constexpr uint32_t HOT_MAX_SLOTS = 8;      // prepared-ring slots
-constexpr uint32_t HOT_MAX_RAW = 12;       // raw-ring slots
+constexpr uint32_t HOT_MAX_SLOTS = 8;      // ring slots
 constexpr uint32_t HOT_COLS = 512;         // columns per pass (4 chain warps x 128)
 constexpr uint32_t WAIT_SPINS = 1u << 22;  // bounded waits: a lost completion voids the batch (CTR_ERR) instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// rows: global -> shared, completion counted in bytes on the chunk's mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -394,6 +385,24 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return false;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  return now;
+}
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+
 // +-inf -> +-65504 (persia-common lib.rs:163-180), two halves per instruction; finite halves are inside already
 __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
   const __half2 lim = __floats2half2_rn(65504.0f, 65504.0f);
@@ -404,9 +413,9 @@ struct HotGeom {
   uint32_t cols;      // columns of this pass
   uint32_t stride;    // floats per ring row (cols rounded up to 4)
   uint32_t R;         // rows per ring slot
-  uint32_t S;         // prepared-ring slots
-  uint32_t SR;        // raw-ring slots (bulk mode; 0 = direct mode)
+  uint32_t S;         // ring slots
   uint32_t rowbytes;  // bytes of a gradient row
+  uint32_t lean;      // the producers' lean loop applies (16-byte vectors, power-of-two vectors per row <= 32)
   uint32_t CH;        // chain warps
   uint32_t vec;       // producer mode: 1 = 16-byte loads (8 halves / 4 floats), 0 = element by element
   uint32_t vshift;    // log2(vectors per row) when that is a power of two, else 32
@@ -507,90 +516,84 @@ __device__ __forceinline__ void produce_chunk(float* slot, const HotGeom& g, con
   }
 }
 
-// bulk mode, converter: a landed chunk (dense [R][dim] raw rows) -> prepared f32 rows (dense [R][dim]); vector v of the
-// chunk is bytes [16 v, 16 v + 16) of the raw slot.  fac: the rows' sqrt factors (written by the loader) when the slot
-// scales by 1/sqrt(ids per sample).  Rows nv .. the next multiple of four become zeros (see produce_vec).
+// the producers' lean loop: one id per sample (the gradient row of sample b is row b), no scaling.  Vector j of a lane is
+// row (j * 32 + lane) >> vshift of the chunk, 16-byte vector (j * 32 + lane) & (nvr - 1) of the row; the row number comes
+// straight from the sorted list.  Rows nv .. the next multiple of four are written as zeros (see produce_vec).  Split in
+// two so that a producer has its NEXT chunk's loads in flight while it converts this one.
+__device__ __forceinline__ void lean_load(uint4 (&raw)[8], const HotGeom& g, const unsigned char* gcol0, const uint16_t* sorted,
+                                          uint32_t nv, uint32_t lane) {
+  const uint32_t nvr_mask = (1u << g.vshift) - 1u;
+  const uint32_t r0 = lane >> g.vshift, rstep = 32u >> g.vshift;
+  const unsigned char* gc = gcol0 + (lane & nvr_mask) * 16u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t r = (uint32_t)j * rstep + r0;
+    raw[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < nv) raw[j] = __ldg(reinterpret_cast<const uint4*>(gc + (size_t)sorted[r] * g.rowbytes));
+  }
+}
 template <bool F16>
-__device__ __forceinline__ void convert_chunk(float* dst, const unsigned char* raw, const float* fac, const HotGeom& g,
-                                              const ItemSrc& src, uint32_t nv, uint32_t lane) {
+__device__ __forceinline__ void lean_store(float* slot, const uint4 (&raw)[8], const HotGeom& g, uint32_t nv, uint32_t lane) {
   constexpr uint32_t EV = F16 ? 8u : 4u;
-  const uint32_t nvr = g.cols / EV, nv4 = (nv + 3u) & ~3u;
-  const uint32_t live = nv * nvr, total = nv4 * nvr;
-  const bool prep = src.do_scale || src.do_sqrt;
-  for (uint32_t v0 = 0; v0 < total; v0 += 256u) {
-    uint4 x[8];
+  const uint32_t nvr_mask = (1u << g.vshift) - 1u, nv4 = (nv + 3u) & ~3u;
+  const uint32_t r0 = lane >> g.vshift, rstep = 32u >> g.vshift;
+  float* sc = slot + (lane & nvr_mask) * EV;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t v = v0 + (uint32_t)j * 32u + lane;
-      x[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (v < live) x[j] = *reinterpret_cast<const uint4*>(raw + (size_t)v * 16u);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t v = v0 + (uint32_t)j * 32u + lane;
-      if (v >= total) continue;
-      float y[EV];
-      if constexpr (F16) {
-        const __half2* h = reinterpret_cast<const __half2*>(&x[j]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 z = __half22float2(clamp_h2(h[q]));
-          y[2 * q] = z.x;
-          y[2 * q + 1] = z.y;
-        }
-      } else {
-        y[0] = __uint_as_float(x[j].x); y[1] = __uint_as_float(x[j].y);
-        y[2] = __uint_as_float(x[j].z); y[3] = __uint_as_float(x[j].w);
-      }
-      if (prep && v < live) {  // (the zero rows stay zero)
-        if (src.do_scale) {
-#pragma unroll
-          for (uint32_t q = 0; q < EV; ++q) y[q] = __fmul_rn(y[q], src.inv_scale);
-        }
-        if (src.do_sqrt) {
-          const float f = fac[g.vshift < 32u ? v >> g.vshift : v / nvr];
-#pragma unroll
-          for (uint32_t q = 0; q < EV; ++q) y[q] = __fmul_rn(y[q], f);
-        }
-      }
-      float4* o = reinterpret_cast<float4*>(dst + (size_t)v * EV);
-      o[0] = make_float4(y[0], y[1], y[2], y[3]);
-      if constexpr (F16) o[1] = make_float4(y[4], y[5], y[6], y[7]);
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t r = (uint32_t)j * rstep + r0;
+    if (r >= nv4) continue;  // (r grows with j: past the chunk's rows)
+    float4* dst = reinterpret_cast<float4*>(sc + (size_t)r * g.stride);
+    if constexpr (F16) {
+      const __half2* h = reinterpret_cast<const __half2*>(&raw[j]);
+      const float2 y0 = __half22float2(clamp_h2(h[0])), y1 = __half22float2(clamp_h2(h[1]));
+      const float2 y2 = __half22float2(clamp_h2(h[2])), y3 = __half22float2(clamp_h2(h[3]));
+      dst[0] = make_float4(y0.x, y0.y, y1.x, y1.y);
+      dst[1] = make_float4(y2.x, y2.y, y3.x, y3.y);
+    } else {
+      dst[0] = make_float4(__uint_as_float(raw[j].x), __uint_as_float(raw[j].y), __uint_as_float(raw[j].z), __uint_as_float(raw[j].w));
     }
   }
 }
 
-template <bool F16, bool SEND>
-__global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
+// the chain's straight-line block: RB rows loaded, then added in order.  (A loop with the loads and adds of different
+// groups interleaved under branches measured 18 cycles per row, this 6.6: the compiler must see the loads far ahead.)
+template <int EPL, int RB>
+__device__ __forceinline__ void chain_block(float (&acc)[EPL], const float* rp, uint32_t stride) {
+  float v[RB][EPL];
+#pragma unroll
+  for (int u = 0; u < RB; ++u) RowElems<-1, EPL>::template ld<EPL>(rp + (size_t)u * stride, v[u]);
+#pragma unroll
+  for (int u = 0; u < RB; ++u) {
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) acc[q] = __fadd_rn(acc[q], v[u][q]);
+  }
+}
+
+template <int EPL, bool F16, bool SEND>
+__global__ void __launch_bounds__(HOT_THREADS, 1) k_reduce_hot(TableDev t, OptimDev op, HyperDev hy, SlotsDev sl, GradsDev gr,
                                                               ReduceArgs a, HotGeom geo, unsigned long long* trace) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t dead[PB_MAX_SLOTS / 32];
   __shared__ uint32_t s_item, s_nwin;
   __shared__ uint32_t bitmap[HOT_WORDS], wpre[HOT_WORDS];
   __shared__ uint16_t sorted[HOT_WIN];
-  __shared__ __align__(8) uint64_t bars[2 * HOT_MAX_SLOTS + 2 * HOT_MAX_RAW];  // full | empty | raw full | raw empty
+  __shared__ __align__(8) uint64_t bars[2 * HOT_MAX_SLOTS];  // full[0..8), empty[8..16)
   float* ring = reinterpret_cast<float*>(smem_raw);                     // [S][R][stride] prepared rows
   float* vstage = ring + (size_t)geo.S * geo.R * geo.stride;            // [dim] Adagrad-vectorwise dot
-  float* facs = vstage + ((t.dim + 3u) & ~3u);                          // [SR][32] sqrt factors of the rows of a raw slot
-  unsigned char* rawring = reinterpret_cast<unsigned char*>(facs + geo.SR * 32u);  // [SR][R][rowbytes] (16-byte aligned)
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool bulk = geo.SR != 0;
-  const uint32_t CH = geo.CH, PW = HOT_WARPS - CH - (bulk ? 1u : 0u);  // producers (direct) / converters (bulk)
+  // PW producers share S slots: PW <= S keeps a producer from running two rounds ahead of the chain (the parity of a
+  // slot's barrier only tells odd rounds from even ones)
+  const uint32_t CH = geo.CH, PW = HOT_WARPS - CH;
   if (tid == 0) {
     for (uint32_t s = 0; s < HOT_MAX_SLOTS; ++s) {
       mbar_init(smem_u32(bars + s), 32u);                       // every lane of the producing warp
       mbar_init(smem_u32(bars + HOT_MAX_SLOTS + s), 32u * CH);  // every lane of every chain warp
     }
-    for (uint32_t s = 0; s < HOT_MAX_RAW; ++s) {
-      mbar_init(smem_u32(bars + 2 * HOT_MAX_SLOTS + s), 1u);                  // the loader's expect_tx + the bytes
-      mbar_init(smem_u32(bars + 2 * HOT_MAX_SLOTS + HOT_MAX_RAW + s), 32u);   // every lane of the converting warp
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   build_dead_mask(dead, gr, a, sl.n_slots);  // ends with __syncthreads
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + HOT_MAX_SLOTS);
-  const uint32_t rfull0 = smem_u32(bars + 2 * HOT_MAX_SLOTS), rempty0 = smem_u32(bars + 2 * HOT_MAX_SLOTS + HOT_MAX_RAW);
-  const uint32_t n_hot = a.b.cnt[BC_HOT];
+  const uint32_t n_huge = a.b.cnt[BC_HUGE], n_hot = a.b.cnt[BC_HOT] + n_huge;  // the huge items first
   uint32_t* next = a.b.cnt + BC_NEXT + PB_MAX_SLOTS + a.round;
   const uint32_t n_pass = (t.dim + HOT_COLS - 1u) / HOT_COLS;
   uint32_t it = 0;  // ring chunks so far: producers and chain count the same chunks
@@ -601,12 +604,8 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
     __syncthreads();
     const uint32_t h = s_item;
     if (h >= n_hot) break;
-    if (trace && tid == 0) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      trace[8 * h] = now;
-    }
-    const uint4 d = a.b.hot[h];
+    if (trace && tid == 0) trace[8 * h] = globaltimer_ns();
+    const uint4 d = a.b.hot[h < n_huge ? a.b.hot_cap - 1u - h : h - n_huge];
     const uint32_t row = d.x, cnt = d.z, slot = d.w;
     const bool bm_mode = d.y >> 31;
     const uint32_t base = d.y & 0x7FFFFFFFu;  // first bitmap word of the item, or first entry of its occurrence list
@@ -633,10 +632,13 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
       const uint32_t col0 = pass * HOT_COLS;
       HotGeom g = geo;
       g.cols = min(geo.cols, t.dim - col0);
-      if (g.cols != geo.cols) g.vec = 0;  // the lane map is for full column blocks; a short last block goes element by element
-      const uint32_t e0 = col0 + (warp * 32u + lane) * 4u;  // chain lanes: four columns each
+      if (g.cols != geo.cols) g.vec = g.lean = 0;  // a short last column block goes element by element
+      const bool lean = g.lean && src.plain;
+      const uint32_t e0 = col0 + (warp * 32u + lane) * EPL;  // chain lanes: EPL columns each
       const bool own = warp < CH && e0 < t.dim;
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      float acc[EPL];
+#pragma unroll
+      for (int q = 0; q < EPL; ++q) acc[q] = 0.0f;
       for (uint32_t wbase = lo; wbase < hi; wbase += HOT_WIN) {
         const uint32_t wend = min(hi, wbase + HOT_WIN);
         const uint32_t n_words = (wend - wbase + 31u) / 32u;
@@ -688,130 +690,92 @@ __global__ void __launch_bounds__(HOT_THREADS, 2) k_reduce_hot(TableDev t, Optim
         __syncthreads();
         const uint32_t nwin = s_nwin;
         const uint32_t n_chunks = (nwin + g.R - 1u) / g.R;
-        if (trace && tid == 0) {
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          trace[8 * h + 1] = now;
-        }
-        if (warp >= CH && bulk && warp == CH) {
-          // ---- loader: 32 rows per round (32 / R chunks), one bulk copy per run of adjacent gradient rows
-          const bool contiguous = !a.occ_outrow;  // one id per sample: the gradient row of occurrence lo + b is row b
-          const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
-          const uint32_t cpr = 32u / g.R;  // chunks per round
-          for (uint32_t c0 = 0; c0 < n_chunks; c0 += cpr) {
-            for (uint32_t q = 0; q < cpr && c0 + q < n_chunks; ++q) {  // the round's slots must be free; announce their bytes
-              const uint32_t i = it + c0 + q, rs = i % g.SR, rpar = (i / g.SR) & 1u;
-              if (!failed && !mbar_wait(rempty0 + 8u * rs, rpar ^ 1u)) failed = true;
-            }
-            const uint32_t k = c0 * g.R + lane;  // this lane's row of the window
-            const bool valid = k < nwin;
-            const uint32_t orow = valid ? occ_out_row(a, wbase + sorted[k]) : 0u;
-            const uint32_t i = it + k / g.R, rs = i % g.SR, kr = k % g.R;
-            if (src.do_sqrt && valid) facs[rs * 32u + kr] = grad_prep(src, a, orow).sqrt_f;
-            __syncwarp();
-            if (valid && kr == 0) mbar_expect_tx(rfull0 + 8u * rs, min(g.R, nwin - k) * g.rowbytes);
-            __syncwarp();
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, orow, 1);
-            const bool head = valid && (lane == 0 || kr == 0 || !contiguous || orow != prev + 1u);
-            const uint32_t hm = __ballot_sync(0xffffffffu, head);
-            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
-            if (head) {
-              const uint32_t later = (lane == 31) ? 0u : (hm >> (lane + 1));
-              const uint32_t len = later ? (uint32_t)__ffs(later) : (uint32_t)__popc(vm) - lane;  // rows up to the next head
-              bulk_g2s(smem_u32(rawring + ((size_t)rs * g.R + kr) * g.rowbytes),
-                       gbytes + (size_t)(orow - src.slot_row0) * g.rowbytes, len * g.rowbytes, rfull0 + 8u * rs);
-            }
-            if (trace && c0 == 0 && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 4] = now; }
-
-          }
-        } else if (warp >= CH && bulk) {
-          // ---- converters: chunk c belongs to warp CH + 1 + (it % PW)
-          const uint32_t me = warp - CH - 1u;
-          for (uint32_t c = 0; c < n_chunks; ++c) {
-            const uint32_t i = it + c;
-            if (i % PW != me) continue;
-            const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
-            const uint32_t rs = i % g.SR, rpar = (i / g.SR) & 1u;
-            if (!failed && !mbar_wait(rfull0 + 8u * rs, rpar)) failed = true;          // the raw rows have landed
-            if (trace && c == 0 && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 5] = now; }
-            if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;   // the prepared slot is free
-            convert_chunk<F16>(ring + (size_t)stage * g.R * g.stride, rawring + (size_t)rs * g.R * g.rowbytes, facs + rs * 32u,
-                               g, src, nv, lane);
-            if (trace && c == 0 && lane == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 6] = now; }
-            mbar_arrive(full0 + 8u * stage);
-            mbar_arrive(rempty0 + 8u * rs);
-          }
-        } else if (warp >= CH) {
-          // ---- producers (direct mode): chunk c belongs to warp CH + (it % PW)
+        if (trace && tid == 0) trace[8 * h + 1] = globaltimer_ns();
+        if (warp >= CH) {
+          // ---- producers: chunk c belongs to warp CH + (it % PW)
           const uint32_t me = warp - CH;
-          for (uint32_t c = 0; c < n_chunks; ++c) {
-            const uint32_t i = it + c;
-            if (i % PW != me) continue;
-            const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
-            if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
-            produce_chunk<F16>(ring + (size_t)stage * g.R * g.stride, g, src, a, sorted, c * g.R, nv, wbase, col0, t.dim, lane);
-            mbar_arrive(full0 + 8u * stage);
+          // lean: gradient row of sample b of the slot is row b (+ the window's offset inside the slot)
+          const unsigned char* gcol0 = reinterpret_cast<const unsigned char*>(src.gbase) +
+                                       ((size_t)(wbase - src.slot_row0) * t.dim + col0) * (F16 ? 2u : 4u);
+          if (lean) {
+            // two chunks in flight per producer: the loads of the next one are issued before this one is converted
+            uint4 ra[8], rb[8];
+            uint32_t c = (me + PW - it % PW) % PW;  // my first chunk of this window
+            if (c < n_chunks) lean_load(ra, g, gcol0, sorted + c * g.R, min(g.R, nwin - c * g.R), lane);
+            while (c < n_chunks) {
+              const uint32_t c2 = c + PW, c3 = c2 + PW;
+              if (c2 < n_chunks) lean_load(rb, g, gcol0, sorted + c2 * g.R, min(g.R, nwin - c2 * g.R), lane);
+              {
+                const uint32_t i = it + c, stage = i % g.S, par = (i / g.S) & 1u;
+                if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
+                lean_store<F16>(ring + (size_t)stage * g.R * g.stride, ra, g, min(g.R, nwin - c * g.R), lane);
+                mbar_arrive(full0 + 8u * stage);
+              }
+              if (c2 >= n_chunks) break;
+              if (c3 < n_chunks) lean_load(ra, g, gcol0, sorted + c3 * g.R, min(g.R, nwin - c3 * g.R), lane);
+              {
+                const uint32_t i = it + c2, stage = i % g.S, par = (i / g.S) & 1u;
+                if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
+                lean_store<F16>(ring + (size_t)stage * g.R * g.stride, rb, g, min(g.R, nwin - c2 * g.R), lane);
+                mbar_arrive(full0 + 8u * stage);
+              }
+              c = c3;
+            }
+          } else {
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+              const uint32_t i = it + c;
+              if (i % PW != me) continue;
+              const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
+              if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
+              produce_chunk<F16>(ring + (size_t)stage * g.R * g.stride, g, src, a, sorted, c * g.R, nv, wbase, col0, t.dim, lane);
+              mbar_arrive(full0 + 8u * stage);
+            }
           }
-        } else {
+        } else if (n_chunks) {
           // ---- chain: the rows in ascending order, one dependent add per row and element
+          long long tw = 0, ta = 0;
           for (uint32_t c = 0; c < n_chunks; ++c) {
             const uint32_t i = it + c;
             const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
+            const long long c0 = trace ? clock64() : 0;
             if (!failed && !mbar_wait(full0 + 8u * stage, par)) failed = true;
-            if (trace && c == 0 && tid == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trace[8 * h + 7] = now; }
+            if (trace) { const long long c1 = clock64(); tw += c1 - c0; ta -= c1; }
             if (own) {
               const float* rp = ring + (size_t)stage * g.R * g.stride + (e0 - col0);
-              // groups of four rows (the producer padded the chunk with zero rows), three groups in flight: the loads of
-              // group g + 2 are issued before the adds of group g
-              const uint32_t G = (nv + 3u) >> 2;
-              float4 va[4], vb[4], vc[4];
-#define PB_HOT_LOAD(V, GI)                                                                                \
-  _Pragma("unroll") for (int u = 0; u < 4; ++u) V[u] = *reinterpret_cast<const float4*>(rp + (size_t)((GI) * 4u + u) * g.stride);
-#define PB_HOT_ADD(V)                                                                                     \
-  _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                         \
-    acc[0] = __fadd_rn(acc[0], V[u].x); acc[1] = __fadd_rn(acc[1], V[u].y);                               \
-    acc[2] = __fadd_rn(acc[2], V[u].z); acc[3] = __fadd_rn(acc[3], V[u].w);                               \
-  }
-              PB_HOT_LOAD(va, 0)
-              if (G > 1) { PB_HOT_LOAD(vb, 1) }
-              for (uint32_t gi = 0;;) {
-                if (gi + 2 < G) { PB_HOT_LOAD(vc, gi + 2) }
-                PB_HOT_ADD(va)
-                if (++gi >= G) break;
-                if (gi + 2 < G) { PB_HOT_LOAD(va, gi + 2) }
-                PB_HOT_ADD(vb)
-                if (++gi >= G) break;
-                if (gi + 2 < G) { PB_HOT_LOAD(vb, gi + 2) }
-                PB_HOT_ADD(vc)
-                if (++gi >= G) break;
+              if (nv == g.R && g.R == 32u) {  // whole chunk: one straight-line block
+                chain_block<EPL, 32>(acc, rp, g.stride);
+              } else if (nv == g.R && g.R == 16u) {
+                chain_block<EPL, 16>(acc, rp, g.stride);
+              } else if (nv == g.R && g.R == 8u) {
+                chain_block<EPL, 8>(acc, rp, g.stride);
+              } else {  // the item's last chunk (the producer padded it with zero rows to a multiple of four)
+                for (uint32_t r = 0; r < nv; r += 4) chain_block<EPL, 4>(acc, rp + (size_t)r * g.stride, g.stride);
               }
-#undef PB_HOT_LOAD
-#undef PB_HOT_ADD
             }
             mbar_arrive(empty0 + 8u * stage);  // the slot may be refilled
+            if (trace) ta += clock64();
           }
+          if (trace && tid == 0) { trace[8 * h + 4] = (unsigned long long)tw; trace[8 * h + 5] = (unsigned long long)ta; }
         }
         it += n_chunks;
       }
       if (trace && tid == 0) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        trace[8 * h + 2] = now;
+        trace[8 * h + 2] = globaltimer_ns();
         trace[8 * h + 3] = ((unsigned long long)blockIdx.x << 32) | cnt;
       }
-      // ---- the optimizer step on this pass's columns (chain warps).  Columns past dim (dim % 4 != 0) were summed from
-      // the ring's padding and are dropped here.
+      // ---- the optimizer step on this pass's columns (chain warps).  Columns past dim (dim % EPL != 0) were summed
+      // from the ring's padding and are dropped here.
       if (own) {
-        const uint32_t nq = min(4u, t.dim - e0);
+        const uint32_t nq = min((uint32_t)EPL, t.dim - e0);
         if (SEND) {
-          if (nq == 4) RowElems<-1, 4>::template st<4>(prow + e0, acc);
+          if (nq == EPL) RowElems<-1, EPL>::template st<EPL>(prow + e0, acc);
           else for (uint32_t q = 0; q < nq; ++q) prow[e0 + q] = acc[q];
-        } else if (nq == 4) {
-          RowElems<-1, 4> rc;
+        } else if (nq == EPL) {
+          RowElems<-1, EPL> rc;
           rc.load(prow, e0, t, op);
           if (op.kind == PB_OPT_ADAGRAD_VW) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) vstage[e0 + q] = acc[q];
+            for (int q = 0; q < EPL; ++q) vstage[e0 + q] = acc[q];
           }
           rc.step(e0, acc, t, op, hy, sc);
           rc.store(prow, e0, t, op);
@@ -866,46 +830,31 @@ static void items_dispatch(const TableDev& t, const OptimDev& op, const HyperDev
 static unsigned long long* g_hot_trace = nullptr;  // debugging aid: per hot item {start, sorted, summed} globaltimer stamps
 void set_hot_trace(unsigned long long* p) { g_hot_trace = p; }
 
-template <bool F16, bool SEND>
+template <int EPL, bool F16, bool SEND>
 static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy, const SlotsDev& sl, const GradsDev& gr,
                        const ReduceArgs& a, uint32_t vec, cudaStream_t st) {
   HotGeom g;
   g.cols = t.dim < HOT_COLS ? t.dim : HOT_COLS;
   g.stride = (g.cols + 3u) & ~3u;
-  g.CH = (g.cols + 127u) / 128u;
+  g.CH = (g.cols + 32u * EPL - 1u) / (32u * EPL);
   g.rowbytes = t.dim * (F16 ? 2u : 4u);
   g.vec = vec;
   const uint32_t nvr = g.cols / (F16 ? 8u : 4u);
   g.vshift = 32u;
   if (vec && nvr && !(nvr & (nvr - 1u)))
     for (g.vshift = 0; (1u << g.vshift) < nvr; ++g.vshift) {}
-  // bulk mode: whole rows by cp.async.bulk (16-byte rows and tensors: `vec`), one pass, R a power of two
-  const bool bulk = vec && t.dim <= HOT_COLS && !getenv("PB_HOT_NO_BULK");
-  size_t raw_bytes = 0;
-  if (bulk) {
-    g.R = 32u;
-    while (g.R > 4u && g.R * g.rowbytes > 4096u) g.R >>= 1;
-    g.S = 4;
-    g.SR = 10;
-    if (getenv("PB_HOT_SLOTS")) g.S = (uint32_t)atoi(getenv("PB_HOT_SLOTS"));
-    if (getenv("PB_HOT_RAW")) g.SR = (uint32_t)atoi(getenv("PB_HOT_RAW"));
-    if (g.S > HOT_MAX_SLOTS) g.S = HOT_MAX_SLOTS;
-    if (g.S < 2) g.S = 2;
-    if (g.SR > HOT_MAX_RAW) g.SR = HOT_MAX_RAW;
-    if (g.SR < 2) g.SR = 2;
-    raw_bytes = (size_t)g.SR * g.R * g.rowbytes + (size_t)g.SR * 32u * 4u;
-  } else {
-    g.S = HOT_MAX_SLOTS;
-    g.SR = 0;
-    g.R = 8192u / (g.stride * 4u);
-    if (g.R > 32u) g.R = 32u;  // a chunk's rows are described by the lanes of the producing warp
-    if (vec && g.R * nvr > 256u) g.R = 256u / nvr;  // at most eight 16-byte loads per producer lane and chunk
-    g.R &= ~3u;  // the chain adds groups of four rows
-    if (g.R < 4u) g.R = 4u;
-    if (vec && g.R * nvr > 256u) g.vec = 0;  // (rows longer than 64 vectors per pass: element by element)
-  }
-  const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u + raw_bytes;
-  auto kern = k_reduce_hot<F16, SEND>;
+  g.S = HOT_MAX_SLOTS;
+  uint32_t slot_bytes = 8192;
+  if (getenv("PB_HOT_SLOT_BYTES")) slot_bytes = (uint32_t)atoi(getenv("PB_HOT_SLOT_BYTES"));
+  g.R = slot_bytes / (g.stride * 4u);
+  if (g.R > 32u) g.R = 32u;  // a chunk's rows are described by the lanes of the producing warp
+  if (vec && g.R * nvr > 256u) g.R = 256u / nvr;  // at most eight 16-byte loads per producer lane and chunk
+  g.R &= ~3u;  // the chain adds groups of four rows
+  if (g.R < 4u) g.R = 4u;
+  if (vec && g.R * nvr > 256u) g.vec = 0;  // (rows longer than 64 vectors per pass: element by element)
+  g.lean = g.vec && g.vshift <= 5u && t.dim <= HOT_COLS && !a.occ_outrow && !getenv("PB_HOT_NO_LEAN");
+  const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
+  auto kern = k_reduce_hot<EPL, F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -913,9 +862,10 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured[dev] = smem;
   }
-  uint32_t per_sm = (uint32_t)(224u * 1024u / (smem + 21u * 1024u));  // + the kernel's static shared memory
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
+  // one block per SM: a producer keeps two chunks (64 registers of loads) in flight, which needs the whole register
+  // file share of a 256-thread block
+  uint32_t per_sm = 1;
+  if (getenv("PB_HOT_PER_SM")) per_sm = (uint32_t)atoi(getenv("PB_HOT_PER_SM"));
   const uint32_t cap_blocks = cdiv(a.b.n, PB_WARM_MAX + 1);  // at most this many hot items exist
   uint32_t grid = 148u * per_sm;
   if (grid > cap_blocks) grid = cap_blocks ? cap_blocks : 1;
@@ -936,13 +886,17 @@ void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& 
     for (uint32_t s = 0; s < sl.n_slots && hv; ++s)
       if (gr.ptr[s] && (reinterpret_cast<uintptr_t>(gr.ptr[s]) & 15u)) hv = 0;
     if (getenv("PB_HOT_NO_VEC")) hv = 0;
-    if (send) {
-      if (f16) hot_launch<true, true>(t, op, hy, sl, gr, a, hv, st_hot);
-      else hot_launch<false, true>(t, op, hy, sl, gr, a, hv, st_hot);
-    } else {
-      if (f16) hot_launch<true, false>(t, op, hy, sl, gr, a, hv, st_hot);
-      else hot_launch<false, false>(t, op, hy, sl, gr, a, hv, st_hot);
-    }
+    // chain lanes own 2 columns (one or two chain warps) up to 128 columns, 4 above
+#define PB_H(E)                                                                 \
+  if (send) {                                                                   \
+    if (f16) hot_launch<E, true, true>(t, op, hy, sl, gr, a, hv, st_hot);       \
+    else hot_launch<E, false, true>(t, op, hy, sl, gr, a, hv, st_hot);          \
+  } else {                                                                      \
+    if (f16) hot_launch<E, true, false>(t, op, hy, sl, gr, a, hv, st_hot);      \
+    else hot_launch<E, false, false>(t, op, hy, sl, gr, a, hv, st_hot);         \
+  }
+    if (t.dim <= 128u && t.dim % 2u == 0) { PB_H(2) } else { PB_H(4) }
+#undef PB_H
   }
   if (vec == 4) {
     if (f16) items_dispatch<4, true>(t, op, hy, sl, gr, a, G, st, st_warm, send);

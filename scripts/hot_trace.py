@@ -47,11 +47,11 @@ cnt = t[:, 3] & 0xFFFFFFFF
 blk = t[:, 3] >> 32
 print("backward ms", e0.elapsed_time(e1), "hot items", len(t), "span us", (t[:, 2].max() - t0) / 1e3)
 order = np.argsort(-cnt)
-print("  cnt  blk  start_us  order_us  sum_us  ns/row | first chunk: issued landed converted chain-got (us after order)")
+print("  cnt  blk  start_us  order_us  sum_us  ns/row | chain: wait_cyc add_cyc | producer 0: wait_cyc work_cyc (per its chunks)")
 for i in list(order[:12]) + list(order[-4:]):
-    print("%5d %4d %8.2f %8.2f %8.2f %7.1f | %6.2f %6.2f %6.2f %6.2f" % (
+    print("%5d %4d %8.2f %8.2f %8.2f %7.1f | %8d %8d | %8d %8d" % (
         cnt[i], blk[i], (t[i, 0] - t0) / 1e3, (t[i, 1] - t[i, 0]) / 1e3, (t[i, 2] - t[i, 1]) / 1e3, (t[i, 2] - t[i, 1]) / max(1, cnt[i]),
-        (t[i, 4] - t[i, 1]) / 1e3, (t[i, 5] - t[i, 1]) / 1e3, (t[i, 6] - t[i, 1]) / 1e3, (t[i, 7] - t[i, 1]) / 1e3))
+        t[i, 4], t[i, 5], t[i, 6], t[i, 7]))
 late = np.argsort(-t[:, 2])[:6]
 print("last to finish:")
 for i in late:

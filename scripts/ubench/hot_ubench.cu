@@ -267,6 +267,73 @@ __global__ void __launch_bounds__(NT, 1) k_bench2(int mode, int n_chunks, const 
   if (warp == 0) out[blockIdx.x * 64 + lane * 2] = acc[0] + acc[1];
 }
 
+// the product kernel's chain loop shape: runtime stride, runtime group count, three groups in flight
+__device__ __forceinline__ void chain_rt(float (&acc)[2], const float* rp, uint32_t stride, uint32_t nv) {
+  const uint32_t G = (nv + 3u) >> 2;
+  float2 va[4], vb[4], vc[4];
+#define LD(V, GI) _Pragma("unroll") for (int u = 0; u < 4; ++u) V[u] = *reinterpret_cast<const float2*>(rp + (size_t)((GI) * 4u + u) * stride);
+#define AD(V) _Pragma("unroll") for (int u = 0; u < 4; ++u) { acc[0] = __fadd_rn(acc[0], V[u].x); acc[1] = __fadd_rn(acc[1], V[u].y); }
+  LD(va, 0)
+  if (G > 1) { LD(vb, 1) }
+  for (uint32_t gi = 0;;) {
+    if (gi + 2 < G) { LD(vc, gi + 2) }
+    AD(va)
+    if (++gi >= G) break;
+    if (gi + 2 < G) { LD(va, gi + 2) }
+    AD(vb)
+    if (++gi >= G) break;
+    if (gi + 2 < G) { LD(vb, gi + 2) }
+    AD(vc)
+    if (++gi >= G) break;
+  }
+#undef LD
+#undef AD
+}
+__global__ void __launch_bounds__(256, 2) k_bench3(int mode, int n_chunks, uint32_t stride, uint32_t nv, const __half* g, float* out, long long* cyc) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[64];
+  __shared__ uint16_t sorted[4096];
+  float* ring = reinterpret_cast<float*>(smem);  // 8 x 8 KB
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 8);
+  if (tid == 0) {
+    for (int s = 0; s < 8; ++s) { mbar_init(full0 + 8 * s, 32); mbar_init(empty0 + 8 * s, 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (uint32_t i = tid; i < 8 * 8192 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3f800000u;
+  for (uint32_t i = tid; i < 4096; i += 256) sorted[i] = (uint16_t)((i * 2 + (i * 7) % 2) % 4096);
+  __syncthreads();
+  const unsigned char* gb = reinterpret_cast<const unsigned char*>(g) + (size_t)(blockIdx.x % 296) * 4096 * 128;
+  const long long t0 = clock64();
+  float acc[2] = {0, 0};
+  if (mode == 12) {
+    if (warp == 0) {
+      for (int c = 0; c < n_chunks; ++c) chain_rt(acc, ring + (c & 7) * 2048 + lane * 2, stride, nv);
+      __syncwarp();
+      if (lane == 0) cyc[blockIdx.x] = clock64() - t0;
+    }
+  } else {  // 13: pipeline with the product's chain; 7 lean producers
+    if (warp == 0) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t st = c & 7, par = (c >> 3) & 1;
+        mbar_wait(full0 + 8 * st, par);
+        chain_rt(acc, ring + st * 2048 + lane * 2, stride, nv);
+        mbar_arrive(empty0 + 8 * st);
+      }
+      if (lane == 0) cyc[blockIdx.x] = clock64() - t0;
+    } else {
+      for (int c = 0; c < n_chunks; ++c) {
+        if (c % 7 != (int)warp - 1) continue;
+        const uint32_t st = c & 7, par = (c >> 3) & 1;
+        mbar_wait(empty0 + 8 * st, par ^ 1);
+        produce_lean(ring + st * 2048, gb, sorted, (c * 32) % 4096, lane);
+        mbar_arrive(full0 + 8 * st);
+      }
+    }
+  }
+  if (warp == 0) out[(blockIdx.x % 296) * 64 + lane * 2] = acc[0] + acc[1];
+}
+
 int main(int argc, char** argv) {
   setvbuf(stdout, NULL, _IONBF, 0);
   const int only = argc > 1 ? atoi(argv[1]) : -1;
@@ -327,6 +394,25 @@ int main(int argc, char** argv) {
         printf("blocks %3d  %-44s threads %4d : %7.1f cycles/chunk avg, %7.1f max  (%.1f /row)\n", g_blocks, names2[mode - 7], nt,
                (double)sum / g_blocks / 128, (double)mx / 128, (double)sum / g_blocks / 128 / 32);
       }
+    }
+  }
+  cudaFuncSetAttribute(k_bench3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  for (int g_blocks : {1, 148, 296}) {
+    for (int mode : {12, 13}) {
+      if (only >= 0 && mode != only) continue;
+      std::vector<long long> h(grid);
+      for (int rep = 0; rep < 3; ++rep) {
+        cudaMemset(cyc, 0, grid * 8);
+        k_bench3<<<g_blocks, 256, smem2>>>(mode, 128, 64, 32, g, out, cyc);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+      }
+      cudaMemcpy(h.data(), cyc, grid * 8, cudaMemcpyDeviceToHost);
+      long long mx = 0, sum = 0;
+      for (int b = 0; b < g_blocks; ++b) { mx = h[b] > mx ? h[b] : mx; sum += h[b]; }
+      printf("blocks %3d  %-44s : %7.1f cycles/chunk avg, %7.1f max  (%.1f /row)\n", g_blocks,
+             mode == 12 ? "product chain loop alone" : "pipeline: 7 lean producers + product chain", (double)sum / g_blocks / 128,
+             (double)mx / 128, (double)sum / g_blocks / 128 / 32);
     }
   }
   return 0;
