@@ -519,6 +519,7 @@ def _sharded_worker(g, dim, names, B, ids, row_off, slot_off, dev):
         if wk.names != tuple(names):
             raise RuntimeError("on R GPUs every batch must carry the same summation slots of a dim, in the same order")
         return wk
+    import torch
     import torch.distributed as dist
 
     from .worker import ShardedEmbeddingWorker as W
