@@ -783,7 +783,9 @@ struct pb_xchg {
   int device = 0;
   uint32_t dim = 0;
   XchgDev d{};
-  uint32_t* mem = nullptr;  // epoch | waited | own_cnt | err | own_row
+  uint32_t* mem = nullptr;  // epoch | waited | own_cnt | err | own_row | uwin
+  UCell* ucell = nullptr;   // rows of the step's requests (owner side)
+  bool u_dirty = false;     // a training lookup filled ucell and its update has not run (abandoned batch)
 };
 
 namespace {
@@ -828,9 +830,13 @@ int pb_xchg_create(int device, uint32_t R, uint32_t rank, uint32_t cap, uint32_t
   d.rank = rank;
   d.cap = cap;
   d.row_f32 = rows_f32 ? 1 : 0;
-  const size_t words = XC_WORDS + (size_t)XC_WORDS * PB_MAX_RANKS + PB_MAX_RANKS + 4 + (size_t)R * cap;
+  const size_t words = XC_WORDS + (size_t)XC_WORDS * PB_MAX_RANKS + PB_MAX_RANKS + 4 + 2 * (size_t)R * cap;
   cudaError_t e = cudaMalloc(&x->mem, 4 * words);
   if (e == cudaSuccess) e = cudaMemset(x->mem, 0, 4 * words);
+  uint32_t ucells = 1024;
+  while ((size_t)ucells < 2 * (size_t)R * cap) ucells <<= 1;
+  if (e == cudaSuccess) e = cudaMalloc(&x->ucell, sizeof(UCell) * (size_t)ucells);
+
   if (e != cudaSuccess) {
     delete x;
     return fail(PB_ERR_CUDA, std::string("pb_xchg_create: ") + cudaGetErrorString(e));
@@ -840,6 +846,11 @@ int pb_xchg_create(int device, uint32_t R, uint32_t rank, uint32_t cap, uint32_t
   d.own_cnt = d.waited + (size_t)XC_WORDS * PB_MAX_RANKS;
   d.err = d.own_cnt + PB_MAX_RANKS;
   d.own_row = d.err + 4;
+  d.uwin = d.own_row + (size_t)R * cap;
+  d.ucell = x->ucell;
+  d.ucells = ucells;
+  launch_uclear(d, nullptr);
+  PB_CUDA(cudaDeviceSynchronize());
   *out = x;
   return PB_OK;
 }
@@ -849,6 +860,7 @@ int pb_xchg_destroy(pb_xchg* x) {
   DeviceGuard g(x->device);
   cudaDeviceSynchronize();
   if (x->mem) cudaFree(x->mem);
+  if (x->ucell) cudaFree(x->ucell);
   delete x;
   return PB_OK;
 }
@@ -906,7 +918,9 @@ int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids
   }
   if (phases & PB_PHASE_SERVE) {
     launch_wait(x->d, XC_FLAG_SIGN, -1, st);
+    if (training && x->u_dirty) launch_uclear(x->d, st);  // a training batch whose gradients never came left its rows noted
     launch_owner_lookup(training != 0, t->d, t->hy, t->op, x->d, st);    // owner: rows -> requesters' areas
+    if (training) x->u_dirty = true;
     launch_signal(x->d, XC_FLAG_ROW, nullptr, st);
   }
   if (!(phases & PB_PHASE_FINISH)) {
@@ -993,10 +1007,17 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
     PB_CUDA(cudaGetLastError());
     return PB_OK;
   }
-  for (uint32_t src = 0; src < x->d.R; ++src) {  // owner: the R requests, one after another in rank order
-    launch_wait(x->d, XC_FLAG_GRAD, (int)src, st);
-    launch_owner_update(t->d, t->op, t->hy, x->d, src, st);
+  if (t->op.kind == PB_OPT_ADAGRAD_VW) {  // (needs the whole gradient's dot per step) one request after another
+    for (uint32_t src = 0; src < x->d.R; ++src) {
+      launch_wait(x->d, XC_FLAG_GRAD, (int)src, st);
+      launch_owner_update(t->d, t->op, t->hy, x->d, src, st);
+    }
+    launch_uclear(x->d, st);
+  } else {  // owner: the R requests in one launch, every row stepped in rank order
+    launch_wait(x->d, XC_FLAG_GRAD, -1, st);
+    launch_owner_update_all(t->d, t->op, t->hy, x->d, st);
   }
+  x->u_dirty = false;
   drop_pending(c);
   PB_CUDA(cudaGetLastError());
   return PB_OK;

@@ -69,6 +69,13 @@ struct BatchDev {
 //   gok    [R][cap] u32         1 = apply the gradient, 0 = the slot was skipped / held a NaN
 enum { XC_FLAG_SIGN = 0, XC_FLAG_ROW, XC_FLAG_GRAD, XC_COUNT, XC_WORDS };
 constexpr uint32_t PB_MAX_RANKS = 16;
+// owner side, one step: the distinct rows the R requests touch (k_owner_lookup fills it, k_owner_update_all empties it)
+struct __align__(16) UCell {
+  uint32_t row;               // ROW_NONE = empty
+  uint32_t mask;              // sources that asked for the row
+  uint32_t k[PB_MAX_RANKS];   // the row's index in each such source's request
+  uint32_t pad[2];
+};
 struct XchgDev {
   uint64_t base[PB_MAX_RANKS];
   uint64_t off_sign, off_row, off_grad, off_gok;  // byte offsets inside an area (ctrl at 0)
@@ -78,6 +85,9 @@ struct XchgDev {
   uint32_t* own_row;   // [R][cap] row of every received sign (forward -> backward)
   uint32_t* own_cnt;   // [R] signs received per source (copied out of ctrl: the next request may overwrite it early)
   uint32_t* err;       // [0] a pair needed more than cap slots, [1] a wait gave up
+  UCell* ucell;        // [ucells] rows of the step's requests, hashed by row number
+  uint32_t* uwin;      // [R][cap] the cell a request's sign opened (it was the first to ask for the row), else ROW_NONE
+  uint32_t ucells;     // a power of two >= 2 R cap
 };
 
 // arguments of the backward kernels (pb_reduce.cu)
@@ -143,6 +153,8 @@ void launch_owner_lookup(bool training, const TableDev& t, const HyperDev& hy, c
 void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& b, const XchgDev& x,
                          const uint32_t* row_off, uint32_t n_out, uint32_t batch, bool training, void* out_f16,
                          cudaStream_t st);
+void launch_uclear(const XchgDev& x, cudaStream_t st);
+void launch_owner_update_all(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, cudaStream_t st);
 void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,
                          cudaStream_t st);
 // n_ptr (optional): the live count on the device (<= n); tick/nan_tick (optional): skip everything when equal

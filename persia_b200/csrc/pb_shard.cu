@@ -26,6 +26,8 @@
 
 namespace pb {
 
+constexpr uint32_t UWIN_MISS = 0xFFFFFFFDu;  // uwin: the sign has no storage (its gradient counts as a miss)
+
 __device__ __forceinline__ uint32_t* x_ctrl(const XchgDev& x, uint32_t q) { return reinterpret_cast<uint32_t*>(x.base[q]); }
 __device__ __forceinline__ uint64_t* x_sign(const XchgDev& x, uint32_t q) {
   return reinterpret_cast<uint64_t*>(x.base[q] + x.off_sign);
@@ -166,6 +168,22 @@ __global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev 
     if (sub == 0) {
       x.own_row[j] = r.row;
       if (r.row == ROW_NONE) atomicAdd(&t.counters[CTR_MISS], 1u);
+      if (MODE == MODE_TRAIN) {
+        // the backward steps every row ONCE for all the requests that hold it (in rank order): note who asked
+        uint32_t won = ROW_NONE;
+        if (r.row < t.capacity) {
+          uint32_t idx = (r.row * 0x9E3779B1u) & (x.ucells - 1u);
+          for (;;) {
+            const uint32_t old = atomicCAS(&x.ucell[idx].row, ROW_NONE, r.row);
+            if (old == ROW_NONE) won = idx;
+            if (old == ROW_NONE || old == r.row) break;
+            idx = (idx + 1u) & (x.ucells - 1u);
+          }
+          atomicOr(&x.ucell[idx].mask, 1u << src);
+          x.ucell[idx].k[src] = k;
+        }
+        x.uwin[j] = r.row < t.capacity ? won : UWIN_MISS;
+      }
     }
     const float* row = t.rows + (size_t)(r.row < t.capacity ? r.row : 0u) * t.stride;
     const bool have = r.row < t.capacity;
@@ -254,6 +272,108 @@ __global__ void __launch_bounds__(256) k_expand_pool(uint32_t dim, SlotsDev sl, 
       acc = __fadd_rn(acc, v);
     }
     out[(size_t)gid * dim + e] = __float2half_rn(__fmul_rn(acc, scale));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// owner, backward: update_gradient_mixed of the step's R requests (PS mod.rs:359-427) in ONE launch.  The reference
+// serves the requests one after another; a row that several requests hold is stepped once per request, in the order
+// the requests arrive — here: rank order.  A lane group takes a row (through the request that opened its cell in the
+// forward), keeps it in registers and applies the holders' gradients in rank order, each a full optimizer step on the
+// result of the previous one: the same arithmetic as R sequential passes, one read and one write of the row.
+// The rule is ONE holder, and that holder is the opener itself: its row number, apply word and gradient are all at the
+// request's own index, so the row, the gradient and the cell's holder mask are fetched together, two dependent memory
+// round trips per row in all.  Signs without storage are counted (gradient_id_miss_count).  The cell goes back to empty.
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256, 3) k_owner_update_all(TableDev t, OptimDev op, HyperDev hy, XchgDev x, uint32_t G) {
+  __shared__ uint32_t s_cnt[PB_MAX_RANKS];
+  if (threadIdx.x < PB_MAX_RANKS) s_cnt[threadIdx.x] = threadIdx.x < x.R ? x.own_cnt[threadIdx.x] : 0u;
+  __syncthreads();
+  const uint32_t wl = threadIdx.x & 31u, lane = wl % G, gi = wl / G, n_g = 32u / G;
+  const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
+  const uint32_t nvec = t.dim / VEC;
+  const uint32_t total = x.R * x.cap;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float* grads = reinterpret_cast<const float*>(x.base[x.rank] + x.off_grad);
+  const uint32_t* gok = reinterpret_cast<const uint32_t*>(x.base[x.rank] + x.off_gok);
+  constexpr uint32_t J = 8;  // requests looked at per warp and round: their rows are stepped by the warp's lane groups
+  for (uint32_t j0 = warp * J; j0 < total; j0 += n_warps * J) {
+    // ---- lanes 0..J-1: did request j open a row's cell; its row and apply word (three independent loads)
+    uint32_t w = ROW_NONE, crow = 0, cok = 0;
+    if (wl < J) {
+      const uint32_t j = j0 + wl;
+      if (j < total && j % x.cap < s_cnt[j / x.cap]) {
+        w = x.uwin[j];
+        crow = x.own_row[j];
+        cok = gok[j];
+        if (w == UWIN_MISS) {
+          if (cok != 0u) atomicAdd(&t.counters[CTR_GRAD_MISS], 1u);  // gradient_id_miss_count (PS mod.rs:401-403)
+          w = ROW_NONE;
+        }
+      }
+    }
+    uint32_t winners = __ballot_sync(0xffffffffu, w != ROW_NONE);
+    // ---- the lane groups take the rows, n_g at a time
+    while (winners) {
+      const uint32_t mine = __fns(winners, 0, gi + 1);  // this group's row of the round (0xFFFFFFFF: none left)
+      for (uint32_t q = 0; q < n_g && winners; ++q) winners &= winners - 1u;
+      const uint32_t bl = mine < 32u ? mine : 0u;
+      const uint32_t idx = __shfl_sync(0xffffffffu, w, bl), row = __shfl_sync(0xffffffffu, crow, bl);
+      const uint32_t ok1 = __shfl_sync(0xffffffffu, cok, bl);
+      if (mine >= 32u) continue;
+      const uint32_t j = j0 + mine, me = j / x.cap;
+      UCell* cell = x.ucell + idx;
+      float* prow = t.rows + (size_t)row * t.stride;
+      StepCtx sc;
+      sc.vw_state = sc.r1 = sc.r2 = 0.0f;
+      for (uint32_t c = lane; c < nvec; c += G) {
+        // the holder mask, the row and the opener's gradient: one round trip
+        const uint32_t mask = cell->mask;
+        RowElems<-1, VEC> rc;
+        rc.load(prow, c * VEC, t, op);
+        float g1[VEC];
+        load_vec<VEC>(grads + (size_t)j * t.dim + c * VEC, g1);
+        if (mask == (1u << me)) {  // the opener is the only holder
+          if (ok1) {
+            rc.step(c * VEC, g1, t, op, hy, sc);
+            rc.store(prow, c * VEC, t, op);
+          }
+          continue;
+        }
+        for (uint32_t m = mask; m;) {  // holders in rank order, four at a time: index, apply word, gradient — each stage
+          uint32_t src[4], at[4], ok[4];  // issued for all four before the next
+          float g[4][VEC];
+          int n = 0;
+          for (; n < 4 && m; ++n, m &= m - 1u) src[n] = (uint32_t)__ffs(m) - 1u;
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v < n) at[v] = src[v] * x.cap + cell->k[src[v]];
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v < n) ok[v] = gok[at[v]];  // 0: that requester skipped the slot (NaN gradient or add_skipped_gradient)
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v < n && ok[v]) load_vec<VEC>(grads + (size_t)at[v] * t.dim + c * VEC, g[v]);
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v < n && ok[v]) rc.step(c * VEC, g[v], t, op, hy, sc);
+        }
+        rc.store(prow, c * VEC, t, op);
+      }
+      __syncwarp(gmask);
+      if (lane == 0) {  // every lane of the group has read the cell: it goes back to empty
+        cell->row = ROW_NONE;
+        cell->mask = 0u;
+      }
+    }
+  }
+}
+
+__global__ void k_uclear(XchgDev x) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < x.ucells; i += gridDim.x * blockDim.x) {
+    x.ucell[i].row = ROW_NONE;
+    x.ucell[i].mask = 0u;
   }
 }
 
@@ -374,6 +494,18 @@ void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& 
     else PB_E(false, false);
   }
 #undef PB_E
+}
+
+void launch_uclear(const XchgDev& x, cudaStream_t st) { PB_LAUNCH(k_uclear, 148 * 4, 256, 0, st, x); }
+
+void launch_owner_update_all(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, cudaStream_t st) {
+  int vec, Gi;
+  vec_group(t.dim, vec, Gi);
+  const uint32_t G = (uint32_t)Gi;
+  const uint32_t full = cdiv((uint64_t)x.R * x.cap * 4u, 256);  // a warp per eight requests
+  const uint32_t grid = full < 148u * 6u ? full : 148u * 6u;
+  if (vec == 4) PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<4>), grid, 256, 0, st, t, op, hy, x, G);
+  else PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<1>), grid, 256, 0, st, t, op, hy, x, G);
 }
 
 void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,
