@@ -412,7 +412,8 @@ __device__ __forceinline__ __half2 clamp_h2(__half2 v) {
 struct HotGeom {
   uint32_t cols;      // columns of this pass
   uint32_t stride;    // floats per ring row (cols rounded up to 4)
-  uint32_t R;         // rows per ring slot
+  uint32_t R;         // rows per ring slot (chunk): one or two halves of R1 rows
+  uint32_t R1;        // rows a producer prepares at a time (its lanes describe them: <= 32)
   uint32_t S;         // ring slots
   uint32_t rowbytes;  // bytes of a gradient row
   uint32_t lean;      // the producers' lean loop applies (16-byte vectors, power-of-two vectors per row <= 32)
@@ -432,7 +433,7 @@ __device__ __forceinline__ void produce_vec(float* slot, const HotGeom& g, const
   constexpr uint32_t EV = F16 ? 8u : 4u;  // elements per 16-byte vector
   const unsigned char* gcol = reinterpret_cast<const unsigned char*>(src.gbase) + (size_t)col0 * (F16 ? 2u : 4u);
   const uint32_t rowbytes = dim * (F16 ? 2u : 4u);
-  const uint32_t nvr = g.cols / EV, total = g.R * nvr, nv4 = (nv + 3u) & ~3u;
+  const uint32_t nvr = g.cols / EV, total = g.R1 * nvr, nv4 = (nv + 3u) & ~3u;
   uint4 raw[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -496,7 +497,7 @@ __device__ __forceinline__ void produce_chunk(float* slot, const HotGeom& g, con
     else produce_vec<F16, false>(slot, g, src, my_row, my_f, nv, col0, dim, lane);
   } else {
     const unsigned char* gbytes = reinterpret_cast<const unsigned char*>(src.gbase);
-    const uint32_t nv4 = min(g.R, (nv + 3u) & ~3u), total = nv4 * g.cols;
+    const uint32_t nv4 = min(g.R1, (nv + 3u) & ~3u), total = nv4 * g.cols;
     for (uint32_t i0 = 0; i0 < total; i0 += 32u) {  // uniform trip count: the shuffles are warp-wide
       const uint32_t i = i0 + lane;
       const bool ok = i < total;
@@ -697,39 +698,24 @@ __global__ void __launch_bounds__(HOT_THREADS, 1) k_reduce_hot(TableDev t, Optim
           // lean: gradient row of sample b of the slot is row b (+ the window's offset inside the slot)
           const unsigned char* gcol0 = reinterpret_cast<const unsigned char*>(src.gbase) +
                                        ((size_t)(wbase - src.slot_row0) * t.dim + col0) * (F16 ? 2u : 4u);
-          if (lean) {
-            // two chunks in flight per producer: the loads of the next one are issued before this one is converted
-            uint4 ra[8], rb[8];
-            uint32_t c = (me + PW - it % PW) % PW;  // my first chunk of this window
-            if (c < n_chunks) lean_load(ra, g, gcol0, sorted + c * g.R, min(g.R, nwin - c * g.R), lane);
-            while (c < n_chunks) {
-              const uint32_t c2 = c + PW, c3 = c2 + PW;
-              if (c2 < n_chunks) lean_load(rb, g, gcol0, sorted + c2 * g.R, min(g.R, nwin - c2 * g.R), lane);
-              {
-                const uint32_t i = it + c, stage = i % g.S, par = (i / g.S) & 1u;
-                if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
-                lean_store<F16>(ring + (size_t)stage * g.R * g.stride, ra, g, min(g.R, nwin - c * g.R), lane);
-                mbar_arrive(full0 + 8u * stage);
-              }
-              if (c2 >= n_chunks) break;
-              if (c3 < n_chunks) lean_load(ra, g, gcol0, sorted + c3 * g.R, min(g.R, nwin - c3 * g.R), lane);
-              {
-                const uint32_t i = it + c2, stage = i % g.S, par = (i / g.S) & 1u;
-                if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
-                lean_store<F16>(ring + (size_t)stage * g.R * g.stride, rb, g, min(g.R, nwin - c2 * g.R), lane);
-                mbar_arrive(full0 + 8u * stage);
-              }
-              c = c3;
-            }
-          } else {
-            for (uint32_t c = 0; c < n_chunks; ++c) {
-              const uint32_t i = it + c;
-              if (i % PW != me) continue;
-              const uint32_t nv = min(g.R, nwin - c * g.R), stage = i % g.S, par = (i / g.S) & 1u;
+          // a chunk is one or two halves of R1 rows; a producer has both halves' loads in flight before it converts
+          for (uint32_t c = (me + PW - it % PW) % PW; c < n_chunks; c += PW) {
+            const uint32_t i = it + c, stage = i % g.S, par = (i / g.S) & 1u;
+            const uint32_t nv = min(g.R, nwin - c * g.R), h0 = min(g.R1, nv), h1 = nv - h0;
+            float* slotp = ring + (size_t)stage * g.R * g.stride;
+            if (lean) {
+              uint4 ra[8], rb[8];
+              lean_load(ra, g, gcol0, sorted + c * g.R, h0, lane);
+              if (h1) lean_load(rb, g, gcol0, sorted + c * g.R + g.R1, h1, lane);
               if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
-              produce_chunk<F16>(ring + (size_t)stage * g.R * g.stride, g, src, a, sorted, c * g.R, nv, wbase, col0, t.dim, lane);
-              mbar_arrive(full0 + 8u * stage);
+              lean_store<F16>(slotp, ra, g, h0, lane);
+              if (h1) lean_store<F16>(slotp + (size_t)g.R1 * g.stride, rb, g, h1, lane);
+            } else {
+              if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
+              produce_chunk<F16>(slotp, g, src, a, sorted, c * g.R, h0, wbase, col0, t.dim, lane);
+              if (h1) produce_chunk<F16>(slotp + (size_t)g.R1 * g.stride, g, src, a, sorted, c * g.R + g.R1, h1, wbase, col0, t.dim, lane);
             }
+            mbar_arrive(full0 + 8u * stage);
           }
         } else if (n_chunks) {
           // ---- chain: the rows in ascending order, one dependent add per row and element
@@ -742,7 +728,10 @@ __global__ void __launch_bounds__(HOT_THREADS, 1) k_reduce_hot(TableDev t, Optim
             if (trace) { const long long c1 = clock64(); tw += c1 - c0; ta -= c1; }
             if (own) {
               const float* rp = ring + (size_t)stage * g.R * g.stride + (e0 - col0);
-              if (nv == g.R && g.R == 32u) {  // whole chunk: one straight-line block
+              if (nv == g.R && g.R == 64u) {  // whole chunk: straight-line blocks
+                chain_block<EPL, 32>(acc, rp, g.stride);
+                chain_block<EPL, 32>(acc, rp + (size_t)32u * g.stride, g.stride);
+              } else if (nv == g.R && g.R == 32u) {
                 chain_block<EPL, 32>(acc, rp, g.stride);
               } else if (nv == g.R && g.R == 16u) {
                 chain_block<EPL, 16>(acc, rp, g.stride);
@@ -853,6 +842,9 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
   if (g.R < 4u) g.R = 4u;
   if (vec && g.R * nvr > 256u) g.vec = 0;  // (rows longer than 64 vectors per pass: element by element)
   g.lean = g.vec && g.vshift <= 5u && t.dim <= HOT_COLS && !a.occ_outrow && !getenv("PB_HOT_NO_LEAN");
+  // every chunk costs the chain a barrier round trip (~500 cycles measured) whatever its size: two halves per chunk
+  g.R1 = g.R;
+  if (g.R1 * g.stride * 4u <= 8192u && !getenv("PB_HOT_ONE_HALF")) g.R = 2u * g.R1;
   const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
   auto kern = k_reduce_hot<EPL, F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
