@@ -305,22 +305,20 @@ def kernel_bytes(stats, dim, state):
     """Algorithmic bytes per launch from the batch's MEASURED multiplicities (with U as observed):
     N id occurrences, U distinct (slot, sign) pairs of which `cold` occur once and `hot` more than 32 times."""
     n, u = stats["occurrences"], stats["items"]
-    cold, warm, hot, rep = stats["cold"], stats["warm"], stats["hot"], stats["repeated_occurrences"]
+    cold, warm, hot, seg = stats["cold"], stats["warm"], stats["hot"], stats["repeated_occurrences"]
     row = 4 * (dim + state)
-    # `rep` = occurrences of the repeated signs; its split between warm (2..32 each) and hot (> 32 each) items is not
-    # recorded: take the smallest hot share consistent with the counts, which makes the k_reduce_items figure the
-    # LARGEST consistent one for its time — never flatter the hot kernel, never the dominant one by more than the
-    # bound allows (both are printed).
-    hot_occ = max(33 * hot, rep - 32 * warm) if hot else 0
-    hot_occ = min(hot_occ, max(0, rep - 2 * warm))
-    warm_occ = rep - hot_occ
+    # occurrence lists hold the warm items' occurrences (hot items are filed in the bitmap pool, which is sized to hold
+    # every one of them): warm occurrences = list entries, hot occurrences = the rest
+    warm_occ = seg
+    hot_occ = max(0, n - cold - seg) if hot else 0
     return {
         "k_dedup": n * (8 + 4) + u * 8,                          # ids in, set cell out, distinct list
         "k_probe_items": u * 16,                                 # one index cell per distinct sign
         "k_gather_items": u * 4 * dim + n * 2 * dim,             # each distinct row once + f16 outputs
         "k_nan_scan": n * 2 * dim,
-        "k_reduce_items": (cold + warm) * (16 + 2 * row) + (cold + warm_occ) * 2 * dim,
-        "k_reduce_hot": hot * (16 + 2 * row) + hot_occ * 2 * dim,
+        "k_reduce_cold": cold * (8 + 2 * row + 2 * dim),
+        "k_reduce_warm": warm * (16 + 2 * row) + warm_occ * (4 + 2 * dim),
+        "k_reduce_hot": hot * (16 + 2 * row) + hot_occ * 2 * dim + hot * 0,
         "worst_case_backward": n * (2 * dim + 16 + 2 * row),
         "whole_step": n * (20 + 2 * dim + 2 * dim) + u * (16 + 4 * dim + 16 + 2 * row),
         "whole_step_worst_case": n * W.algorithmic_bytes_per_id(dim, state, "total"),
@@ -423,16 +421,17 @@ def run_leg(args, torch, dim, B, rows, name, want_kernels, want_parity):
         if want_kernels:
             # per-kernel durations: CUDA events around every launch of ONE family at a time on its launching stream
             # (bracketing all launches at once makes the host the bottleneck and small kernels read high)
-            fam_names = ["k_probe_items", "k_dedup", "k_gather_items", "k_nan_scan", "k_reduce_hot", "k_reduce_items", "other"]
+            fam_names = ["k_probe_items", "k_dedup", "k_gather_items", "k_nan_scan", "k_reduce_hot", "k_reduce_cold", "other",
+                         "k_reduce_warm"]
             n_prof = min(K, 40)
             kern = {}
-            for f in range(6):
+            for f in (0, 1, 2, 3, 4, 5, 7):
                 lib.pb_profile_enable(1 << f)
                 for i in range(n_prof):
                     step(i % n_sets)
-                fam_ms = (C.c_double * 7)()
-                fam_cnt = (C.c_uint64 * 7)()
-                N.check(lib.pb_profile_read(fam_ms, fam_cnt, 7))
+                fam_ms = (C.c_double * 8)()
+                fam_cnt = (C.c_uint64 * 8)()
+                N.check(lib.pb_profile_read(fam_ms, fam_cnt, 8))
                 lib.pb_profile_enable(0)
                 if fam_cnt[f]:
                     kern[fam_names[f]] = {"us": 1e3 * fam_ms[f] / fam_cnt[f], "launches_per_step": fam_cnt[f] / n_prof}
@@ -592,23 +591,25 @@ def roofline_from(leg, peak, peak_src, label):
             gbs = by[k] / (v["us"] * 1e-6) / 1e9
             table[k] = {"us": round(v["us"], 2), "algorithmic_bytes": int(by[k]), "achieved_gbs": round(gbs, 1),
                         "frac": round(gbs / peak, 4)}
-    dom = "k_reduce_items"
+    dom = "k_reduce_cold"  # the kernel that moves the most bytes: row in, row out, gradient in, for every sign seen once
     ach = table.get(dom, {}).get("achieved_gbs")
-    us = kern.get(dom, {}).get("us")
-    worst = by["worst_case_backward"] / (us * 1e-6) / 1e9 if us else None
     step_s = leg["ms_per_step"] * 1e-3
+    hot_max = max(1, st.get("max_multiplicity", 0))
     return {
-        "bound": "hbm", "kernel": "k_reduce_items (A8+A9 of the signs occurring <= 32 times: in-order gradient reduce + Adagrad "
-                                  "step + weight bound) on " + label,
+        "bound": "hbm", "kernel": "k_reduce_cold (A8+A9 of the signs occurring once in the batch — most distinct signs: gradient "
+                                  "prepared, Adagrad step + weight bound on the resident row) on " + label,
         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-        "frac_worst_case": (worst / peak) if worst else None,
+        "frac_worst_case": by["whole_step_worst_case"] / step_s / 1e9 / peak,
         "traffic": None,
-        "traffic_note": "not measured by this run: see profiles/ for the ncu --set full capture of this command "
-                        "(dram__bytes_read.sum + dram__bytes_write.sum of the same kernel) and its command line",
+        "traffic_note": "not measured by this run: profiles/ holds the ncu --set full capture of this command "
+                        "(dram__bytes_read.sum + dram__bytes_write.sum per kernel) and its command line",
         "peak_source": peak_src,
-        "bytes_model": "measured multiplicities of the batch: N occurrences, U distinct (slot, sign) pairs; "
-                       "k_reduce_items = (cold+warm items) x (16 + 8(D+S)) + their occurrences x 2D; frac_worst_case "
-                       "divides the U = N backward bytes N x (2D + 16 + 8(D+S)) by the same time",
+        "bytes_model": "measured multiplicities of the batch: N occurrences, U distinct (slot, sign) pairs, of which `cold` occur "
+                       "once, `warm` 2..32 times (their occurrences are counted), `hot` more.  k_reduce_cold = cold x (8 + "
+                       "8(D+S) + 2D); k_reduce_warm = warm x (16 + 8(D+S)) + their occurrences x (4 + 2D); k_reduce_hot = hot x "
+                       "(16 + 8(D+S)) + their occurrences x 2D.  frac_worst_case: the whole step's U = N bytes (SURVEY 8d) over "
+                       "the measured step time.  k_reduce_hot is not bandwidth-bound: the reference's summation order makes a "
+                       "sign's occurrences one dependent f32 add after another (its floor is the largest multiplicity x ~7 cycles)",
         "unique_fraction": st["items"] / max(1, st["occurrences"]), "batch_stats": st,
         "kernels": table,
         "whole_step": {"ms": leg["ms_per_step"], "samples_per_s": B / step_s,

@@ -285,14 +285,15 @@ __global__ void __launch_bounds__(256) k_expand_pool(uint32_t dim, SlotsDev sl, 
 // request's own index, so the row, the gradient and the cell's holder mask are fetched together, two dependent memory
 // round trips per row in all.  Signs without storage are counted (gradient_id_miss_count).  The cell goes back to empty.
 // ------------------------------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(256, 3) k_owner_update_all(TableDev t, OptimDev op, HyperDev hy, XchgDev x, uint32_t G) {
+template <int VEC, int CPL, int KIND>
+__global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) k_owner_update_all(TableDev t, OptimDev op, HyperDev hy, XchgDev x, uint32_t G) {
+  // G lanes per row, CPL chunks of VEC floats per lane (G * CPL * VEC == dim): few lanes per row keep the per-row
+  // bookkeeping off most of the warp, and a lane has CPL independent loads in flight
   __shared__ uint32_t s_cnt[PB_MAX_RANKS];
   if (threadIdx.x < PB_MAX_RANKS) s_cnt[threadIdx.x] = threadIdx.x < x.R ? x.own_cnt[threadIdx.x] : 0u;
   __syncthreads();
   const uint32_t wl = threadIdx.x & 31u, lane = wl % G, gi = wl / G, n_g = 32u / G;
   const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
-  const uint32_t nvec = t.dim / VEC;
   const uint32_t total = x.R * x.cap;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const float* grads = reinterpret_cast<const float*>(x.base[x.rank] + x.off_grad);
@@ -327,39 +328,53 @@ __global__ void __launch_bounds__(256, 3) k_owner_update_all(TableDev t, OptimDe
       float* prow = t.rows + (size_t)row * t.stride;
       StepCtx sc;
       sc.vw_state = sc.r1 = sc.r2 = 0.0f;
-      for (uint32_t c = lane; c < nvec; c += G) {
-        // the holder mask, the row and the opener's gradient: one round trip
-        const uint32_t mask = cell->mask;
-        RowElems<-1, VEC> rc;
-        rc.load(prow, c * VEC, t, op);
-        float g1[VEC];
-        load_vec<VEC>(grads + (size_t)j * t.dim + c * VEC, g1);
-        if (mask == (1u << me)) {  // the opener is the only holder
-          if (ok1) {
-            rc.step(c * VEC, g1, t, op, hy, sc);
-            rc.store(prow, c * VEC, t, op);
-          }
-          continue;
-        }
-        for (uint32_t m = mask; m;) {  // holders in rank order, four at a time: index, apply word, gradient — each stage
-          uint32_t src[4], at[4], ok[4];  // issued for all four before the next
-          float g[4][VEC];
-          int n = 0;
-          for (; n < 4 && m; ++n, m &= m - 1u) src[n] = (uint32_t)__ffs(m) - 1u;
+      // the holder mask, the row and the opener's gradient: one round trip
+      const uint32_t mask = cell->mask;
+      RowElems<KIND, VEC> rc[CPL];
+      float g1[CPL][VEC];
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
+      for (int u = 0; u < CPL; ++u) {
+        const uint32_t e = ((uint32_t)u * G + lane) * VEC;
+        rc[u].load(prow, e, t, op);
+        load_vec<VEC>(grads + (size_t)j * t.dim + e, g1[u]);
+      }
+      if (mask == (1u << me)) {  // the opener is the only holder (the rule)
+        if (ok1) {
+#pragma unroll
+          for (int u = 0; u < CPL; ++u) {
+            const uint32_t e = ((uint32_t)u * G + lane) * VEC;
+            rc[u].step(e, g1[u], t, op, hy, sc);
+            rc[u].store(prow, e, t, op);
+          }
+        }
+      } else {
+        for (uint32_t m = mask; m;) {  // holders in rank order, two at a time: index, apply word, gradient — each stage
+          uint32_t at[2], ok[2];       // issued for both before the next
+          float g[2][CPL][VEC];
+          int n = 0;
+          uint32_t src[2];
+          for (; n < 2 && m; ++n, m &= m - 1u) src[n] = (uint32_t)__ffs(m) - 1u;
+#pragma unroll
+          for (int v = 0; v < 2; ++v)
             if (v < n) at[v] = src[v] * x.cap + cell->k[src[v]];
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
+          for (int v = 0; v < 2; ++v)
             if (v < n) ok[v] = gok[at[v]];  // 0: that requester skipped the slot (NaN gradient or add_skipped_gradient)
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
-            if (v < n && ok[v]) load_vec<VEC>(grads + (size_t)at[v] * t.dim + c * VEC, g[v]);
+          for (int v = 0; v < 2; ++v)
+            if (v < n && ok[v]) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
-            if (v < n && ok[v]) rc.step(c * VEC, g[v], t, op, hy, sc);
+              for (int u = 0; u < CPL; ++u) load_vec<VEC>(grads + (size_t)at[v] * t.dim + ((uint32_t)u * G + lane) * VEC, g[v][u]);
+            }
+#pragma unroll
+          for (int v = 0; v < 2; ++v)
+            if (v < n && ok[v]) {
+#pragma unroll
+              for (int u = 0; u < CPL; ++u) rc[u].step(((uint32_t)u * G + lane) * VEC, g[v][u], t, op, hy, sc);
+            }
         }
-        rc.store(prow, c * VEC, t, op);
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) rc[u].store(prow, ((uint32_t)u * G + lane) * VEC, t, op);
       }
       __syncwarp(gmask);
       if (lane == 0) {  // every lane of the group has read the cell: it goes back to empty
@@ -498,14 +513,30 @@ void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& 
 
 void launch_uclear(const XchgDev& x, cudaStream_t st) { PB_LAUNCH(k_uclear, 148 * 4, 256, 0, st, x); }
 
+void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,
+                         cudaStream_t st);
+
+template <int VEC, int CPL>
+static void owner_update_all_kind(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t G,
+                                  uint32_t grid, cudaStream_t st) {
+  if (op.kind == PB_OPT_SGD) PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<VEC, CPL, PB_OPT_SGD>), grid, 256, 0, st, t, op, hy, x, G);
+  else if (op.kind == PB_OPT_ADAGRAD) PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<VEC, CPL, PB_OPT_ADAGRAD>), grid, 256, 0, st, t, op, hy, x, G);
+  else PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<VEC, CPL, -1>), grid, 256, 0, st, t, op, hy, x, G);
+}
+
 void launch_owner_update_all(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, cudaStream_t st) {
   int vec, Gi;
-  vec_group(t.dim, vec, Gi);
-  const uint32_t G = (uint32_t)Gi;
+  vec_group(t.dim, vec, Gi);  // Gi lanes cover a row with one chunk each (a power of two <= 32)
   const uint32_t full = cdiv((uint64_t)x.R * x.cap * 4u, 256);  // a warp per eight requests
   const uint32_t grid = full < 148u * 6u ? full : 148u * 6u;
-  if (vec == 4) PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<4>), grid, 256, 0, st, t, op, hy, x, G);
-  else PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<1>), grid, 256, 0, st, t, op, hy, x, G);
+  const uint32_t nvec = t.dim / (uint32_t)vec;
+  const bool exact = (uint32_t)Gi == nvec;  // (rows longer than 32 chunks keep one chunk per lane and stride)
+  if (vec == 4 && exact) owner_update_all_kind<4, 1>(t, op, hy, x, (uint32_t)Gi, grid, st);
+  else if (vec == 1 && exact) owner_update_all_kind<1, 1>(t, op, hy, x, (uint32_t)Gi, grid, st);
+  else {  // long or odd rows: one request after another with the striding kernel
+    for (uint32_t src = 0; src < x.R; ++src) launch_owner_update(t, op, hy, x, src, st);
+    launch_uclear(x, st);
+  }
 }
 
 void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,
