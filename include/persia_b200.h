@@ -118,6 +118,11 @@ int pb_add_prefix(const uint64_t* d_ids, uint32_t n, const uint32_t* h_slot_occ_
                   uint32_t n_slots, uint32_t prefix_bit, uint64_t* d_out, void* stream);
 /* sign_to_shard_modulo (embedding_worker_service/mod.rs:341-345): farmhash64(sign LE bytes) % R. */
 int pb_shard_of(const uint64_t* d_signs, uint32_t n, uint32_t R, uint32_t* d_shard, void* stream);
+/* indices_to_hashstack_indices (embedding_worker_service/mod.rs:347-400): every id becomes `rounds` keys,
+ * d_out[i * rounds + r] = farmhash64^(r+1)(id_i) % embedding_size + r * embedding_size (a sample's ids stay together:
+ * sample_num_signs grows by `rounds`, :393-397; the caller scales its row offsets).  The regrouping per hashed key
+ * is the forward's per-batch dedup. */
+int pb_hash_stack(const uint64_t* d_ids, uint32_t n, uint32_t rounds, uint64_t embedding_size, uint64_t* d_out, void* stream);
 /* farmhash64 of each 8-byte little-endian value (hash-stack building block, :364). */
 int pb_farmhash64(const uint64_t* d_in, uint32_t n, uint64_t* d_out, void* stream);
 /* indices_to_sharded_indices (embedding_worker_service/mod.rs:454-479) as a stable partition:

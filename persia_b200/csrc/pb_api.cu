@@ -506,6 +506,14 @@ int pb_farmhash64(const uint64_t* d_in, uint32_t n, uint64_t* d_out, void* strea
   return PB_OK;
 }
 
+int pb_hash_stack(const uint64_t* d_ids, uint32_t n, uint32_t rounds, uint64_t embedding_size, uint64_t* d_out, void* stream) {
+  if (n && (!d_ids || !d_out)) return fail(PB_ERR_INVALID, "null argument");
+  if (rounds == 0 || embedding_size == 0) return fail(PB_ERR_INVALID, "hash_stack_rounds and embedding_size must be > 0");
+  launch_hash_stack(d_ids, n, rounds, embedding_size, d_out, (cudaStream_t)stream);
+  PB_CUDA(cudaGetLastError());
+  return PB_OK;
+}
+
 uint64_t pb_partition_workspace(uint32_t n) { return partition_workspace_bytes(n); }
 
 int pb_partition_by_shard(const uint64_t* d_signs, uint32_t n, uint32_t R, uint32_t* d_perm, uint32_t* d_counts,

@@ -295,4 +295,22 @@ void launch_shard_of(const uint64_t* signs, uint32_t n, uint32_t R, uint32_t* sh
   if (n) PB_LAUNCH(k_shard_of, cdiv(n, 256), 256, 0, st, signs, n, R, shard, hash);
 }
 
+// A1: indices_to_hashstack_indices (embedding_worker_service/mod.rs:347-400) as an id expansion: every id becomes
+// `rounds` keys, key_r = farmhash64^(r+1)(id) % embedding_size + r * embedding_size, laid out id-major so that a
+// sample's ids stay together (sample_num_signs grows by the same factor, :393-397).  The regrouping of occurrences
+// per hashed key that the reference does next is the per-batch dedup of the forward (pb_dedup.cu).
+__global__ void __launch_bounds__(256) k_hash_stack(const uint64_t* __restrict__ ids, uint32_t n, uint32_t rounds,
+                                                    uint64_t size, uint64_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t h = ids[i];
+  for (uint32_t r = 0; r < rounds; ++r) {
+    h = farmhash64_u64(h);
+    out[(size_t)i * rounds + r] = h % size + (uint64_t)r * size;
+  }
+}
+void launch_hash_stack(const uint64_t* ids, uint32_t n, uint32_t rounds, uint64_t size, uint64_t* out, cudaStream_t st) {
+  if (n) PB_LAUNCH(k_hash_stack, cdiv(n, 256), 256, 0, st, ids, n, rounds, size, out);
+}
+
 }  // namespace pb

@@ -153,6 +153,7 @@ void launch_owner_lookup(bool training, const TableDev& t, const HyperDev& hy, c
 void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& b, const XchgDev& x,
                          const uint32_t* row_off, uint32_t n_out, uint32_t batch, bool training, void* out_f16,
                          cudaStream_t st);
+void launch_hash_stack(const uint64_t* ids, uint32_t n, uint32_t rounds, uint64_t size, uint64_t* out, cudaStream_t st);
 void launch_uclear(const XchgDev& x, cudaStream_t st);
 void launch_owner_update_all(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, cudaStream_t st);
 void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,

@@ -64,6 +64,7 @@ SYMBOLS = {
     "pb_table_export_signs": (_i32, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "pb_add_prefix": (_i32, [_vp, _u32, C.POINTER(_u32), C.POINTER(_u64), _u32, _u32, _vp, _vp]),
     "pb_shard_of": (_i32, [_vp, _u32, _u32, _vp, _vp]),
+    "pb_hash_stack": (_i32, [_vp, _u32, _u32, _u64, _vp, _vp]),
     "pb_farmhash64": (_i32, [_vp, _u32, _vp, _vp]),
     "pb_partition_by_shard": (_i32, [_vp, _u32, _u32, _vp, _vp, _vp, _u64, _vp]),
     "pb_partition_workspace": (_u64, [_u32]),

@@ -392,6 +392,36 @@ def _flatten(feats, batch):
     return ids, row_off, slot_off
 
 
+def _to_device_ids(ids, row_off, slot_off, slots, B, dev):
+    """Flat host ids of one dim group -> device ids, with indices_to_hashstack_indices (embedding_worker_service/mod.rs:
+    347-400) applied ON THE DEVICE to the slots that configure it (pb_hash_stack): every id becomes `rounds` keys next to
+    each other, so the slot's samples hold `rounds` times as many ids (sample_num_signs, :393-397) and the CSR offsets
+    are scaled on the host.  Returns (d_ids, row_off, slot_off)."""
+    import torch
+
+    d_raw = torch.from_numpy(ids.view(np.int64)).to(dev, non_blocking=True)
+    rounds = [max(1, sc.hash_stack_rounds) for sc in slots]
+    if all(r == 1 for r in rounds):
+        return d_raw, row_off, slot_off
+    n_in = [slot_off[i + 1] - slot_off[i] for i in range(len(slots))]
+    new_off = [0]
+    for n, r in zip(n_in, rounds):
+        new_off.append(new_off[-1] + n * r)
+    d_out = torch.empty(new_off[-1], dtype=torch.int64, device=dev)
+    for i, sc in enumerate(slots):
+        src = d_raw[slot_off[i]:slot_off[i + 1]]
+        dst = d_out[new_off[i]:new_off[i + 1]]
+        if rounds[i] == 1:
+            dst.copy_(src)
+        elif n_in[i]:
+            SH.hash_stack(src, rounds[i], sc.hash_stack_embedding_size, out=dst)
+    counts = np.ones(len(slots) * B, np.int64) if row_off is None else np.diff(row_off.astype(np.int64))
+    counts = counts * np.repeat(np.array(rounds, np.int64), B)
+    new_row_off = np.zeros(counts.size + 1, np.uint32)
+    new_row_off[1:] = np.cumsum(counts)
+    return d_out, new_row_off, new_off
+
+
 _STATE_LOCK = threading.RLock()  # configuration / group creation; GPU work takes the lock of the table it touches
 _BACKWARDS = []                   # live Backward engines (direct lookups wait for their queues to drain)
 
@@ -432,7 +462,6 @@ def _forward_locked(batch, device_id, training):
         sc = _S.by_name[name]
         if not sc.embedding_summation and sc.hash_stack_rounds > 0:
             raise RuntimeError(f"slot {name}: a raw (embedding_summation: false) slot with hash_stack is not supported")
-    feats = [(n, _hashstack(x, _S.by_name[n]) if _S.by_name[n].hash_stack_rounds > 0 else x) for n, x in feats]
     pending = _Pending()
     by_slot = {}
     raw_out = {}
@@ -472,10 +501,13 @@ def _forward_locked(batch, device_id, training):
         key = tuple(names)
         pool = g["ctx"].setdefault(key, [])
         ids, row_off, slot_off = _flatten(part, B)
+        slots = [_S.by_name[n] for n in names]
         if (_S.replica_size or 1) > 1:  # R GPUs: the embedding worker's fan-out runs inside the sharded worker
             with g["lock"]:
+                d_ids, row_off, slot_off = _to_device_ids(ids, row_off, slot_off, slots, B, dev)
+                if g.get("worker") is None and any(sc.hash_stack_rounds > 0 for sc in slots):
+                    ids = d_ids.cpu().numpy().view(np.uint64)  # (the first batch sizes the exchange from its keys)
                 wk = _sharded_worker(g, dim, names, B, ids, row_off, slot_off, dev)
-                d_ids = torch.from_numpy(ids.view(np.int64)).to(dev, non_blocking=True)
                 d_off = torch.from_numpy(row_off.view(np.int32)).to(dev, non_blocking=True) if row_off is not None else None
                 out = wk.forward(d_ids, B, training=training, row_off=d_off, slot_occ_off=slot_off)
                 if wk.status()[0]:
@@ -487,15 +519,15 @@ def _forward_locked(batch, device_id, training):
                 pending.parts.append((g, None, names, False))
             continue
         g["lock"].acquire()
-        if pool:
+        d_ids, row_off, slot_off = _to_device_ids(ids, row_off, slot_off, slots, B, dev)
+        if pool and pool[-1]._cap >= d_ids.numel():
             ctx = pool.pop()
         else:
-            cap = max(len(ids), len(names) * max(B, 1), 1)
+            cap = max(int(d_ids.numel()), len(names) * max(B, 1), 1)
             ctx = SH.BatchContext(max(cap * 2, 1024), max(len(names) * max(B, 1) * 2, 1024),
                                   [_S.by_name[n].index_prefix for n in names],
                                   [_S.by_name[n].sqrt_scaling for n in names], _S.prefix_bit, dev)
-            ctx._pool_key = key
-        d_ids = torch.from_numpy(ids.view(np.int64)).to(dev, non_blocking=True)
+            ctx._pool_key, ctx._cap = key, max(cap * 2, 1024)
         d_off = torch.from_numpy(row_off.view(np.int32)).to(dev, non_blocking=True) if row_off is not None else None
         out = ctx.forward(g["shard"], d_ids, slot_off, B, row_off=d_off, training=training)
         for i, n in enumerate(names):

@@ -274,6 +274,16 @@ def shard_of(signs, R):
     return out
 
 
+def hash_stack(ids, rounds, embedding_size, out=None):
+    """indices_to_hashstack_indices (mod.rs:347-400) on the device: [n] ids -> [n * rounds] keys, id-major."""
+    lib = N.load()
+    ids = _as_i64_bits(ids)
+    if out is None:
+        out = torch.empty(ids.numel() * int(rounds), dtype=torch.int64, device=ids.device)
+    N.check(lib.pb_hash_stack(_ptr(ids), ids.numel(), int(rounds), int(embedding_size), _ptr(out), _stream(ids.device)))
+    return out
+
+
 def farmhash64(x):
     lib = N.load()
     x = _as_i64_bits(x)

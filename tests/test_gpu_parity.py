@@ -57,6 +57,27 @@ def test_farmhash_prefix_shard_bit_exact(torch_cuda, pb, oracle):
     np.testing.assert_array_equal(_np_u64(pb.add_prefix(d, offs, pf, prefix_bit=8)), want)
 
 
+def test_hash_stack_on_device_matches_reference_vector(torch_cuda, pb):
+    """A1 on the device (pb_hash_stack): the reference's own vector (embedding_worker_service/mod.rs:1570-1613, in
+    tests/golden/farmhash64_kat.json) and, at size, the chained farmhash modulo rule."""
+    import json
+    import os
+
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "farmhash64_kat.json")))
+    ids = np.array([int(k) for k in fx["hashstack_rounds2_size10"]], np.uint64)
+    got = _np_u64(pb.hash_stack(to_dev_ids(ids, DEV), 2, 10)).reshape(-1, 2)
+    assert got.tolist() == [list(v) for v in fx["hashstack_rounds2_size10"].values()]
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 2**63, size=50000, dtype=np.uint64)
+    d = to_dev_ids(x, DEV)
+    got = _np_u64(pb.hash_stack(d, 3, 1000003)).reshape(-1, 3)
+    h = d
+    for r in range(3):
+        h = pb.farmhash64(h)
+        np.testing.assert_array_equal(got[:, r], _np_u64(h) % np.uint64(1000003) + np.uint64(r * 1000003))
+    assert pb.hash_stack(to_dev_ids(np.zeros(0, np.uint64), DEV), 2, 10).numel() == 0
+
+
 @pytest.mark.parametrize("n,R", [(0, 2), (1, 1), (1000, 2), (100003, 8), (300000, 3)])
 def test_partition_by_shard_stable(torch_cuda, pb, oracle, n, R):
     rng = np.random.default_rng(n + R)
