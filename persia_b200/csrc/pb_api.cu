@@ -774,7 +774,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
       if (c->round_of[s] == r) a.round_mask[s >> 5] |= 1u << (s & 31);
     // one round (no shared feature groups, the usual case): hot items run beside the others; several: one after another
     // the items of a round are distinct rows, whatever their list.
-    const bool one = c->n_rounds == 1;
+    const bool one = c->n_rounds == 1 && !profiling();  // (timed alone when the bench instruments a family)
     launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, one ? c->side : st, one ? c->side2 : st, false);
   }
   PB_CUDA(cudaEventRecord(c->ev_join, c->side));
@@ -1004,7 +1004,8 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
   for (uint32_t s = 0; s < S; ++s) a.round_mask[s >> 5] |= 1u << (s & 31);
   a.x = x->d;
   PB_CUDA(cudaStreamWaitEvent(c->side2, c->ev_nan, 0));
-  launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, c->side, c->side2, true);  // requester: gradients -> owners' areas
+  launch_reduce_items(t->d, t->op, t->hy, sl, gr, is_f16 != 0, a, st, profiling() ? st : c->side, profiling() ? st : c->side2,
+                      true);  // requester: gradients -> owners' areas
   PB_CUDA(cudaEventRecord(c->ev_join, c->side));
   PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   PB_CUDA(cudaEventRecord(c->ev_join2, c->side2));

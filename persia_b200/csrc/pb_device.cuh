@@ -51,6 +51,7 @@ static inline void vec_group(uint32_t dim, int& vec, int& G) {
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
+bool profiling();  // a kernel family is being timed: the backward then runs its kernels one after another
 void prof_begin(int family, cudaStream_t st);
 void prof_end(cudaStream_t st);
 void count_launch();

@@ -196,6 +196,7 @@ void launch_export_signs(const TableDev& t, uint64_t* signs, uint32_t* recency, 
 void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, uint32_t keep, uint32_t* ev, cudaStream_t st);
 uint64_t launch_count();
 enum { FAM_PROBE = 0, FAM_DEDUP, FAM_GATHER, FAM_NAN, FAM_HOT, FAM_UPDATE, FAM_OTHER, FAM_WARM, FAM_COUNT };
+bool profiling();  // a kernel family is being timed: the backward then runs its kernels one after another
 void profile_enable(uint32_t family_mask);
 void profile_read(double* ms, uint64_t* count, int n_families);
 

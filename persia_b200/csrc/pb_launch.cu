@@ -44,6 +44,8 @@ void prof_end(cudaStream_t st) {
   cudaEventRecord(g_prof.ev[2 * g_prof.used + 1], st);
   g_prof.used++;
 }
+bool profiling() { return g_prof.mask != 0; }
+
 void profile_enable(uint32_t family_mask) {
   g_prof.mask = family_mask;
   g_prof.used = 0;

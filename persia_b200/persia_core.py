@@ -399,6 +399,8 @@ def _to_device_ids(ids, row_off, slot_off, slots, B, dev):
     are scaled on the host.  Returns (d_ids, row_off, slot_off)."""
     import torch
 
+    from . import shard as SH
+
     d_raw = torch.from_numpy(ids.view(np.int64)).to(dev, non_blocking=True)
     rounds = [max(1, sc.hash_stack_rounds) for sc in slots]
     if all(r == 1 for r in rounds):
