@@ -547,7 +547,8 @@ int pb_ctx_create(int device, uint32_t max_occurrences, uint32_t max_out_rows, p
   A((void**)&c->b.seg_occ, 4 * n);
   A((void**)&c->b.cold, 8 * n);
   A((void**)&c->b.warm, 16 * (n / 2 + 1));
-  c->b.hot_cap = n / (PB_WARM_MAX + 1) + 1;
+  c->b.giant_cap = n / PB_GIANT_MIN + 1;
+  c->b.hot_cap = n / (PB_WARM_MAX + 1) + 1 + c->b.giant_cap;
   A((void**)&c->b.hot, 16 * (size_t)c->b.hot_cap);
   c->b.hot_words = (uint32_t)(n < 4096 ? 4096 : n);  // 32 bits of pool per id occurrence the context can hold
   A((void**)&c->b.hot_bits, 4 * (size_t)c->b.hot_words);
@@ -628,7 +629,7 @@ int pb_ctx_batch_stats(pb_ctx* c, uint32_t h_out[6], void* stream) {
   h_out[0] = w[BC_ITEMS];
   h_out[1] = w[BC_COLD];
   h_out[2] = w[BC_WARM];
-  h_out[3] = w[BC_HOT] + w[BC_HUGE];
+  h_out[3] = w[BC_HOT] + w[BC_HUGE] + w[BC_GIANT];
   h_out[4] = w[BC_SEG];
   h_out[5] = c->n_occ;
   return PB_OK;

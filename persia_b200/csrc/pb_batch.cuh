@@ -17,18 +17,19 @@ struct ItemSlots {
 // hot_nwords: words of a bitmap over the item's slot (one bit per sample); a hot item gets one from the pool when
 // it fits (base = bit 31 | word offset) and an occurrence list otherwise.
 __device__ __forceinline__ ItemSlots block_item_slots(const BatchDev& b, bool head, uint32_t cnt, uint32_t hot_nwords) {
-  __shared__ uint32_t s_n[5], s_g[5];  // cold, warm, hot, huge, occurrence-list entries
-  if (threadIdx.x < 5) s_n[threadIdx.x] = 0;
+  __shared__ uint32_t s_n[6], s_g[6];  // cold, warm, hot, huge, giant, occurrence-list entries
+  if (threadIdx.x < 6) s_n[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   ItemSlots r;
-  // list: 1 cold, 2 warm, 3 hot, 4 huge (hot items above PB_HUGE_MIN: numbered apart, listed from the end of `hot`)
-  const uint32_t list = !head || cnt == 0 ? 0u : (cnt == 1 ? 1u : (cnt <= PB_WARM_MAX ? 2u : (cnt <= PB_HUGE_MIN ? 3u : 4u)));
+  // list: 1 cold, 2 warm, 3 hot, 4 huge, 5 giant (the long chains are numbered apart and listed from the end of `hot`:
+  // the reducing kernel starts them first)
+  const uint32_t list = !head || cnt == 0 ? 0u : (cnt == 1 ? 1u : (cnt <= PB_WARM_MAX ? 2u : (cnt <= PB_HUGE_MIN ? 3u : (cnt <= PB_GIANT_MIN ? 4u : 5u))));
   r.cls = list > 3u ? 3u : list;
   r.pos = r.base = 0;
   uint32_t off = 0, seg = 0;
 #pragma unroll
-  for (uint32_t c = 1; c <= 4; ++c) {
+  for (uint32_t c = 1; c <= 5; ++c) {
     const uint32_t m = __ballot_sync(0xffffffffu, list == c);
     uint32_t w = 0;
     if (m && lane == 0) w = atomicAdd(&s_n[c - 1], (uint32_t)__popc(m));
@@ -41,16 +42,18 @@ __device__ __forceinline__ ItemSlots block_item_slots(const BatchDev& b, bool he
     bm_off = atomicAdd(&b.cnt[BC_HOTW], hot_nwords);
     bitmap = bm_off + hot_nwords <= b.hot_words;
   }
-  if (r.cls >= 2 && !bitmap) seg = atomicAdd(&s_n[4], cnt);
+  if (r.cls >= 2 && !bitmap) seg = atomicAdd(&s_n[5], cnt);
   __syncthreads();
-  if (threadIdx.x < 5 && s_n[threadIdx.x]) {
-    const uint32_t which = threadIdx.x == 0 ? BC_COLD : threadIdx.x == 1 ? BC_WARM : threadIdx.x == 2 ? BC_HOT : threadIdx.x == 3 ? BC_HUGE : BC_SEG;
+  if (threadIdx.x < 6 && s_n[threadIdx.x]) {
+    const uint32_t which = threadIdx.x == 0 ? BC_COLD : threadIdx.x == 1 ? BC_WARM : threadIdx.x == 2 ? BC_HOT
+                           : threadIdx.x == 3 ? BC_HUGE : threadIdx.x == 4 ? BC_GIANT : BC_SEG;
     s_g[threadIdx.x] = atomicAdd(&b.cnt[which], s_n[threadIdx.x]);
   }
   __syncthreads();
   if (list) r.pos = s_g[list - 1] + off;
-  if (list == 4) r.pos = b.hot_cap - 1u - r.pos;
-  if (r.cls >= 2) r.base = bitmap ? (0x80000000u | bm_off) : s_g[4] + seg;
+  if (list == 5) r.pos = b.hot_cap - 1u - r.pos;  // (a batch holds at most n / PB_GIANT_MIN giants: giant_cap)
+  else if (list == 4) r.pos = b.hot_cap - 1u - b.giant_cap - r.pos;
+  if (r.cls >= 2) r.base = bitmap ? (0x80000000u | bm_off) : s_g[5] + seg;
   return r;
 }
 

@@ -30,6 +30,7 @@ struct GradsDev {
 // Filled by the forward (dedup -> probe -> gather), consumed by the backward.  A distinct (sign, slot) pair of the
 // batch is an "item"; the occurrences of an item with count > 1 are listed in seg_occ[base, base + count) in
 // arbitrary order (the reducing kernels put them in ascending order, the reference's summation order).
+constexpr uint32_t PB_GIANT_MIN = 1024;  // the few longest chains of a batch: listed in the top giant_cap entries of `hot`
 constexpr uint32_t PB_HUGE_MIN = 256;  // hot items above this are the long poles of the backward: they start first
 constexpr uint32_t PB_WARM_MAX = 32;  // items of 2..PB_WARM_MAX occurrences are reduced by a lane group, larger ones by a CTA
 enum {
@@ -40,6 +41,7 @@ enum {
   BC_SEG,        // entries of seg_occ handed out
   BC_HUGE,       // hot items of more than PB_HUGE_MIN occurrences: listed from the END of `hot`, reduced first
   BC_HOTW,       // words of the hot-item bitmap pool handed out
+  BC_GIANT,      // hot items of more than PB_GIANT_MIN occurrences: the very first to be reduced
   BC_PEER = 8,
   BC_NEXT = 24,  // work cursors of the reducing kernels: [round] warm, [PB_MAX_SLOTS + round] hot
   BC_COUNT = BC_NEXT + 2 * PB_MAX_SLOTS
@@ -55,6 +57,7 @@ struct BatchDev {
   uint32_t* hot_bits;   // [hot_words] one bit per sample of the slot for hot items in bitmap mode (all zero between batches)
   uint32_t hot_words;
   uint32_t hot_cap;     // entries of `hot`
+  uint32_t giant_cap;   // of which the top ones are reserved for the giants (n / PB_GIANT_MIN + 1)
   uint32_t* cnt;        // BC_* words
   uint32_t n;           // id occurrences of the batch
 };

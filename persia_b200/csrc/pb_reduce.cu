@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 1) k_reduce_hot(TableDev t, Optim
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // PW producers share S slots: PW <= S keeps a producer from running two rounds ahead of the chain (the parity of a
   // slot's barrier only tells odd rounds from even ones)
-  const uint32_t CH = geo.CH, PW = HOT_WARPS - CH;
+  const uint32_t CH = geo.CH, PW = min(HOT_WARPS - CH, geo.S);
   if (tid == 0) {
     for (uint32_t s = 0; s < HOT_MAX_SLOTS; ++s) {
       mbar_init(smem_u32(bars + s), 32u);                       // every lane of the producing warp
@@ -594,7 +594,8 @@ __global__ void __launch_bounds__(HOT_THREADS, 1) k_reduce_hot(TableDev t, Optim
   }
   build_dead_mask(dead, gr, a, sl.n_slots);  // ends with __syncthreads
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + HOT_MAX_SLOTS);
-  const uint32_t n_huge = a.b.cnt[BC_HUGE], n_hot = a.b.cnt[BC_HOT] + n_huge;  // the huge items first
+  const uint32_t n_giant = a.b.cnt[BC_GIANT], n_huge = a.b.cnt[BC_HUGE];  // the longest chains first
+  const uint32_t n_hot = a.b.cnt[BC_HOT] + n_huge + n_giant;
   uint32_t* next = a.b.cnt + BC_NEXT + PB_MAX_SLOTS + a.round;
   const uint32_t n_pass = (t.dim + HOT_COLS - 1u) / HOT_COLS;
   uint32_t it = 0;  // ring chunks so far: producers and chain count the same chunks
@@ -606,7 +607,8 @@ __global__ void __launch_bounds__(HOT_THREADS, 1) k_reduce_hot(TableDev t, Optim
     const uint32_t h = s_item;
     if (h >= n_hot) break;
     if (trace && tid == 0) trace[8 * h] = globaltimer_ns();
-    const uint4 d = a.b.hot[h < n_huge ? a.b.hot_cap - 1u - h : h - n_huge];
+    const uint4 d = a.b.hot[h < n_giant ? a.b.hot_cap - 1u - h
+                                        : (h < n_giant + n_huge ? a.b.hot_cap - 1u - a.b.giant_cap - (h - n_giant) : h - n_giant - n_huge)];
     const uint32_t row = d.x, cnt = d.z, slot = d.w;
     const bool bm_mode = d.y >> 31;
     const uint32_t base = d.y & 0x7FFFFFFFu;  // first bitmap word of the item, or first entry of its occurrence list
@@ -699,21 +701,29 @@ __global__ void __launch_bounds__(HOT_THREADS, 1) k_reduce_hot(TableDev t, Optim
           const unsigned char* gcol0 = reinterpret_cast<const unsigned char*>(src.gbase) +
                                        ((size_t)(wbase - src.slot_row0) * t.dim + col0) * (F16 ? 2u : 4u);
           // a chunk is one or two halves of R1 rows; a producer has both halves' loads in flight before it converts
-          for (uint32_t c = (me + PW - it % PW) % PW; c < n_chunks; c += PW) {
+          for (uint32_t c = me < PW ? (me + PW - it % PW) % PW : n_chunks; c < n_chunks; c += PW) {  // (warps past PW idle)
             const uint32_t i = it + c, stage = i % g.S, par = (i / g.S) & 1u;
-            const uint32_t nv = min(g.R, nwin - c * g.R), h0 = min(g.R1, nv), h1 = nv - h0;
+            const uint32_t nv = min(g.R, nwin - c * g.R);
             float* slotp = ring + (size_t)stage * g.R * g.stride;
+            const uint16_t* srt = sorted + c * g.R;
             if (lean) {
+              // the chunk's parts of R1 rows ping-pong between two register sets: part k + 2 is loaded as soon as part k has
+              // been converted, so two parts' loads are always in flight
               uint4 ra[8], rb[8];
-              lean_load(ra, g, gcol0, sorted + c * g.R, h0, lane);
-              if (h1) lean_load(rb, g, gcol0, sorted + c * g.R + g.R1, h1, lane);
+              const uint32_t np = (nv + g.R1 - 1u) / g.R1;  // parts of this chunk (<= 4)
+              lean_load(ra, g, gcol0, srt, min(g.R1, nv), lane);
+              if (np > 1) lean_load(rb, g, gcol0, srt + g.R1, min(g.R1, nv - g.R1), lane);
               if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
-              lean_store<F16>(slotp, ra, g, h0, lane);
-              if (h1) lean_store<F16>(slotp + (size_t)g.R1 * g.stride, rb, g, h1, lane);
+              lean_store<F16>(slotp, ra, g, min(g.R1, nv), lane);
+              if (np > 2) lean_load(ra, g, gcol0, srt + 2u * g.R1, min(g.R1, nv - 2u * g.R1), lane);
+              if (np > 1) lean_store<F16>(slotp + (size_t)g.R1 * g.stride, rb, g, min(g.R1, nv - g.R1), lane);
+              if (np > 3) lean_load(rb, g, gcol0, srt + 3u * g.R1, min(g.R1, nv - 3u * g.R1), lane);
+              if (np > 2) lean_store<F16>(slotp + (size_t)2u * g.R1 * g.stride, ra, g, min(g.R1, nv - 2u * g.R1), lane);
+              if (np > 3) lean_store<F16>(slotp + (size_t)3u * g.R1 * g.stride, rb, g, min(g.R1, nv - 3u * g.R1), lane);
             } else {
               if (!failed && !mbar_wait(empty0 + 8u * stage, par ^ 1u)) failed = true;
-              produce_chunk<F16>(slotp, g, src, a, sorted, c * g.R, h0, wbase, col0, t.dim, lane);
-              if (h1) produce_chunk<F16>(slotp + (size_t)g.R1 * g.stride, g, src, a, sorted, c * g.R + g.R1, h1, wbase, col0, t.dim, lane);
+              for (uint32_t r0 = 0; r0 < nv; r0 += g.R1)
+                produce_chunk<F16>(slotp + (size_t)r0 * g.stride, g, src, a, sorted, c * g.R + r0, min(g.R1, nv - r0), wbase, col0, t.dim, lane);
             }
             mbar_arrive(full0 + 8u * stage);
           }
@@ -844,7 +854,10 @@ static void hot_launch(const TableDev& t, const OptimDev& op, const HyperDev& hy
   g.lean = g.vec && g.vshift <= 5u && t.dim <= HOT_COLS && !a.occ_outrow && !getenv("PB_HOT_NO_LEAN");
   // every chunk costs the chain a barrier round trip (~500 cycles measured) whatever its size: two halves per chunk
   g.R1 = g.R;
-  if (g.R1 * g.stride * 4u <= 8192u && !getenv("PB_HOT_ONE_HALF")) g.R = 2u * g.R1;
+  if (!getenv("PB_HOT_ONE_HALF")) {  // 64 rows per chunk where the slot stays within 32 KB
+    while (g.R < 64u && 2u * g.R * g.stride * 4u <= 32768u) g.R *= 2u;
+    if (g.R * g.stride * 4u > 16384u) g.S = 6;  // 6 x 32 KB (the producers must not outnumber the slots)
+  }
   const size_t smem = (size_t)g.S * g.R * g.stride * 4u + (((size_t)t.dim + 3u) & ~(size_t)3u) * 4u;
   auto kern = k_reduce_hot<EPL, F16, SEND>;
   static size_t configured[64] = {0};  // per instantiation and device
