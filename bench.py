@@ -351,6 +351,7 @@ def run_leg(args, torch, dim, B, rows, name, want_kernels, want_parity):
 
     # ---- rotating buffer sets: ids, gradients, outputs (together > L2) ; pinned host ids for e2e
     n_sets = max(2, args.sets)
+    n_sets += n_sets % 2  # (the e2e staging buffers alternate with the sets)
     ids_host = W.make_batches(2, card, B, n_sets, args.alpha)
     ids_pinned = torch.from_numpy(ids_host.view(np.int64)).pin_memory()
     ids_dev = [ids_pinned[k].to(dev) for k in range(n_sets)]
@@ -436,40 +437,72 @@ def run_leg(args, torch, dim, B, rows, name, want_kernels, want_parity):
                 if fam_cnt[f]:
                     kern[fam_names[f]] = {"us": 1e3 * fam_ms[f] / fam_cnt[f], "launches_per_step": fam_cnt[f] / n_prof}
 
-        # ---- e2e: host ids (pinned) -> H2D -> forward -> backward -> D2H of the per-slot status, every step
-        status_host = torch.empty(S, dtype=torch.int32).pin_memory()
-        ids_stage = torch.empty(n_occ, dtype=torch.int64, device=dev)
+        # ---- e2e: host ids (pinned) -> H2D -> forward -> backward -> D2H of the per-slot status, every step, a host sync
+        # per step (the caller reads every step's status, one step behind the launches).  The ids of step i + 1 are copied on a copy
+        # stream while step i computes (the reference's Forward engine prefetches batches the same way, forward.rs:470-
+        # 780); every copy is inside the timed region.
+        status_host = [torch.empty(S, dtype=torch.int32).pin_memory() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ids_stage = [torch.empty(n_occ, dtype=torch.int64, device=dev) for _ in range(2)]
         out_e2e = outs[0]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_body(k):
-            ids_stage.copy_(ids_pinned[k], non_blocking=True)
-            ctx.forward(sh, ids_stage, slot_off, B, training=True, out=out_e2e)
+        def e2e_compute(k):
+            ctx.forward(sh, ids_stage[k % 2], slot_off, B, training=True, out=out_e2e)
             st = ctx.backward(sh, grads[k], want_status=True)
-            status_host.copy_(st, non_blocking=True)
+            status_host[k % 2].copy_(st, non_blocking=True)
+
+        def e2e_copy(k):  # enqueue the H2D of set k into its staging buffer once the step that last used it is done
+            b = k % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[b])
+                ids_stage[b].copy_(ids_pinned[k], non_blocking=True)
+                ev_copied[b].record(copy_stream)
 
         e2e_graphs = None
-        if use_graph:  # the whole call sequence incl. the H2D / D2H copies is one graph per pinned input buffer
-            e2e_body(0)
+        if use_graph:  # forward + backward + the status D2H of a step are one graph per buffer set
+            for b in range(2):
+                ids_stage[b].copy_(ids_pinned[b])
+            e2e_compute(0)
             stream.synchronize()
             e2e_graphs = []
             for k in range(n_sets):
                 gph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gph, stream=stream):
-                    e2e_body(k)
+                    e2e_compute(k)
                 e2e_graphs.append(gph)
+        for b in range(2):
+            ev_free[b].record(stream)
+        stream.synchronize()
 
-        def e2e_step(k):
-            if e2e_graphs is not None:
-                e2e_graphs[k].replay()
-            else:
-                e2e_body(k)
-            stream.synchronize()  # the caller reads the status: one host sync per step, as persia's backward does
+        seen = [0]
 
-        for i in range(Wm):
-            e2e_step(i % n_sets)
+        def e2e_run(n):
+            e2e_copy(0)
+            for i in range(n):
+                k = i % n_sets
+                e2e_copy((i + 1) % n_sets)  # the next step's ids travel while this step computes
+                stream.wait_event(ev_copied[k % 2])
+                if e2e_graphs is not None:
+                    e2e_graphs[k].replay()
+                else:
+                    e2e_compute(k)
+                ev_free[k % 2].record(stream)
+                ev_done[k % 2].record(stream)
+                if i:  # the host reads every step's status, one step behind the launches (two pinned result buffers)
+                    ev_done[(k - 1) % 2].synchronize()
+                    seen[0] += int(status_host[(k - 1) % 2][0] >= 0)
+            ev_done[(n - 1) % n_sets % 2].synchronize()
+            seen[0] += int(status_host[(n - 1) % n_sets % 2][0] >= 0)
+            copy_stream.synchronize()
+
+        assert n_sets % 2 == 0, "the staging buffers alternate with the buffer sets"
+        e2e_run(Wm)
+        torch.cuda.synchronize()
         e0.record(stream)
-        for i in range(K):
-            e2e_step(i % n_sets)
+        e2e_run(K)
         e1.record(stream)
         torch.cuda.synchronize()
         ms_e2e = e0.elapsed_time(e1)
@@ -719,7 +752,7 @@ def single_gpu(args, torch):
         "clocks": leg["clocks"],
         "e2e": {"value": B / (leg["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_occ * 8,
                 "d2h_bytes_per_step": S * 4, "ms_per_step": leg["ms_e2e"],
-                "path": "pinned host ids -> H2D -> pb_forward -> pb_backward -> D2H slot status, host sync every step"},
+                "path": "pinned host ids -> H2D (copy stream, one step ahead) -> pb_forward -> pb_backward -> D2H slot status read by the host every step, one step behind the launches"},
         "e2e_model": e2e_model,
         "gpu_launches": leg["launches_per_step"] * K,
         "parity_checked": bool(leg["parity"] and leg["parity"]["checked"]), "parity": leg["parity"],

@@ -92,6 +92,7 @@ def run(args, rank, local_rank, world, B_):
     pf = W.index_prefixes(S)
     n_occ = S * B
     n_sets = max(2, args.sets)
+    n_sets += n_sets % 2  # (the e2e staging buffers alternate with the sets)
     all_ids = None
     ids_host = W.make_batches(100 + rank, card, B, n_sets, args.alpha)  # every rank draws its own samples
     cap = ShardedEmbeddingWorker.calibrate_cap([ids_host[k] for k in range(n_sets)], B, pf, world)
@@ -184,18 +185,39 @@ def run(args, rank, local_rank, world, B_):
 
     # ---- e2e: pinned host ids -> H2D -> sharded forward + backward -> D2H of the slot status, host sync every step;
     # the same captured graph mechanism, with the copies inside
-    ids_stage = torch.empty(n_occ, dtype=torch.int64, device=dev)
-    status_host = torch.empty(S, dtype=torch.int32).pin_memory()
+    # the ids of step i + 1 travel on a copy stream while step i computes (the reference's Forward engine prefetches
+    # batches the same way); every copy is inside the timed region
+    ids_stage = [torch.empty(n_occ, dtype=torch.int64, device=dev) for _ in range(2)]
+    status_host = [torch.empty(S, dtype=torch.int32).pin_memory() for _ in range(2)]
     status_dev = torch.empty(S, dtype=torch.int32, device=dev)
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    last = [None]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    assert n_sets % 2 == 0, "the staging buffers alternate with the buffer sets"
 
     def e2e_body(k):
-        ids_stage.copy_(ids_pinned[k], non_blocking=True)
-        wk.forward(ids_stage, B, training=True, out=outs[0])
+        wk.forward(ids_stage[k % 2], B, training=True, out=outs[0])
         wk.backward(grads[k], want_status=True, status=status_dev)
-        status_host.copy_(status_dev, non_blocking=True)
+        status_host[k % 2].copy_(status_dev, non_blocking=True)
+
+    staged = {}
+
+    def e2e_copy(k):
+        b = k % 2
+        if staged.get(b) == ("set", k):
+            return
+        staged[b] = ("set", k)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[b])
+            ids_stage[b].copy_(ids_pinned[k], non_blocking=True)
+            ev_copied[b].record(copy_stream)
 
     e2e_graphs = None
     with torch.cuda.stream(gstream):
+        for b in range(2):
+            ids_stage[b].copy_(ids_pinned[b])
         e2e_body(0)
         gstream.synchronize()
         dist.barrier()
@@ -206,16 +228,28 @@ def run(args, rank, local_rank, world, B_):
                 with torch.cuda.graph(gph, stream=gstream, capture_error_mode="thread_local"):
                     e2e_body(k)
                 e2e_graphs.append(gph)
+        for b in range(2):
+            ev_free[b].record(gstream)
     torch.cuda.synchronize()
     dist.barrier()
+    e2e_copy(0)
 
     def e2e_step(k):
+        e2e_copy(k)                 # (already under way, except for the first step of a loop)
         with torch.cuda.stream(gstream):
+            gstream.wait_event(ev_copied[k % 2])
             if e2e_graphs is not None:
                 e2e_graphs[k].replay()
             else:
                 e2e_body(k)
-        gstream.synchronize()
+            ev_free[k % 2].record(gstream)
+            ev_done[k % 2].record(gstream)
+        staged.pop(k % 2, None)
+        e2e_copy((k + 1) % n_sets)  # the next step's ids travel while this step computes
+        if last[0] is not None:     # the host reads every step's status, one step behind the launches
+            ev_done[last[0]].synchronize()
+            assert int(status_host[last[0]][0]) >= -1
+        last[0] = k % 2
 
     for i in range(Wm):
         e2e_step(i % n_sets)
@@ -291,7 +325,7 @@ def run(args, rank, local_rank, world, B_):
             "clocks": clocks,
             "e2e": {"value": GB / (ms_e2e / K * 1e-3), "unit": B_.UNIT, "h2d_bytes_per_step": n_occ * 8 * world,
                     "d2h_bytes_per_step": S * 4 * world, "ms_per_step": ms_e2e / K,
-                    "path": "pinned host ids -> H2D -> pb_forward_sharded -> pb_backward_sharded -> D2H slot status (one CUDA "
+                    "path": "pinned host ids -> H2D (copy stream, one step ahead) -> pb_forward_sharded -> pb_backward_sharded -> D2H slot status (one CUDA "
                             "graph per rank), host sync every step"},
             "gpu_launches": launches_per_step * K,
             "parity_checked": bool(parity and parity["checked"]), "parity": parity,
