@@ -666,6 +666,8 @@ def model_leg(args, torch, steps, warmup):
     PC.set_embedding_config({"slots_config": {n: {"dim": dim} for n in names}})
     card = W.scaled_cardinalities(int(min(args.rows, 2e7)), S)
     torch.manual_seed(0)
+    prev_precision = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")  # the dense tower's GEMMs on the tensor cores (TF32); the sparse path is untouched
     model = W.make_dlrm_tower(S, dim, n_dense=n_dense).cuda()
     dense_opt = torch.optim.SGD(model.parameters(), lr=0.01)
     loss_fn = torch.nn.BCEWithLogitsLoss()
@@ -699,9 +701,10 @@ def model_leg(args, torch, steps, warmup):
     res = {"value": B * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps, "steps": steps,
            "first_loss": float(losses[0]), "last_loss": float(losses[-1]),
            "path": f"numpy batch -> api.PersiaBatch -> TrainCtx.get_embedding_from_data -> DLRM tower ({sum(p.numel() for p in model.parameters())} "
-                   f"dense parameters, fp32) -> BCE -> TrainCtx.backward (dense SGD + sparse Adagrad); {int(min(args.rows, 2e7)):.3g}-id key space, "
+                   f"dense parameters, fp32 weights, TF32 matmuls) -> BCE -> TrainCtx.backward (dense SGD + sparse Adagrad); {int(min(args.rows, 2e7)):.3g}-id key space, "
                    "rows admitted on the fly", "h2d_bytes_per_step": S * B * 8 + B * n_dense * 4 + B * 4}
     PC.reset()
+    torch.set_float32_matmul_precision(prev_precision)
     torch.cuda.empty_cache()
     return res
 

@@ -411,8 +411,15 @@ class TrainCtx(EmbeddingCtx):  # ctx.py:655-1055
             if grad is not None:
                 grad_slots.append(grad)
                 gradient_batch.add_gradient(name, grad.data_ptr(), grad.shape, is_f16, loss_scale)
+        # The reference synchronises the device here (ctx.py:995-996): its backward engine copies the gradients to the host
+        # on another stream.  Here the engine's workers enqueue pb_backward on the SAME stream the autograd kernels ran on
+        # (the device's default stream), after them in host order, so stream order already makes the gradients ready;
+        # grad_queue keeps the tensors alive until the update has been enqueued.  Should the caller have run autograd on
+        # another stream, the event recorded here orders the worker's stream after it.
         if self.device_id is not None:
-            torch.cuda.synchronize()
+            ready = torch.cuda.Event()
+            ready.record()
+            gradient_batch._ready = ready
         self.backward_engine.update_id_type_feature_gradient_batched(gradient_batch)
         self.grad_queue.put(grad_slots)
         return finite

@@ -699,8 +699,12 @@ class Backward:  # backward.rs:203-405
                 self._q.task_done()
 
     @staticmethod
-    def _apply(p, grads, permit):
+    def _apply(p, grads, permit, ready=None):
         try:
+            if ready is not None:  # the gradients were produced on the caller's stream: this thread's stream follows it
+                import torch
+
+                torch.cuda.current_stream().wait_event(ready)
             for g, ctx, names, is_raw in p.parts:
                 with g["lock"]:
                     if is_raw:  # [U, dim] gradient of the distinct-sign table (persia/ctx.py:970-980)
@@ -740,10 +744,11 @@ class Backward:  # backward.rs:203-405
             if permit is not None:
                 permit.release()
             raise RuntimeError("cannot find gradient batch")
+        ready = getattr(gradients, "_ready", None)
         if self._running:
-            self._q.put((p, gradients._grads, permit))  # blocks when the queue is full (bounded channel)
+            self._q.put((p, gradients._grads, permit, ready))  # blocks when the queue is full (bounded channel)
         else:
-            self._apply(p, gradients._grads, permit)
+            self._apply(p, gradients._grads, permit, ready)
 
 
 # ---------------------------------------------------------------------------------------------------------
