@@ -93,7 +93,8 @@ def make_dlrm_tower(n_slots, dim, n_dense=13, bottom=(512, 256), top=(1024, 1024
                 d = h
             self.bottom = nn.Sequential(*layers)
             n_vec = n_slots + 1
-            self.register_buffer("tri", torch.triu_indices(n_vec, n_vec, offset=1), persistent=False)
+            tri = torch.triu_indices(n_vec, n_vec, offset=1)
+            self.register_buffer("tri_flat", tri[0] * n_vec + tri[1], persistent=False)  # upper triangle of the Gram matrix
             layers, d = [], dim + n_vec * (n_vec - 1) // 2
             for h in top:
                 layers += [nn.Linear(d, h), nn.ReLU()]
@@ -104,9 +105,10 @@ def make_dlrm_tower(n_slots, dim, n_dense=13, bottom=(512, 256), top=(1024, 1024
         def forward(self, non_id_type_tensors, embedding_tensors):
             dense = non_id_type_tensors[0].float()
             x = self.bottom(dense)                                                    # [B, dim]
-            vecs = torch.stack([x] + [e.float() for e in embedding_tensors], dim=1)  # [B, n_slots + 1, dim]
+            e = torch.stack(list(embedding_tensors), dim=1).float()                   # one stack of the f16 slots, one cast
+            vecs = torch.cat([x.unsqueeze(1), e], dim=1)                              # [B, n_slots + 1, dim]
             inter = torch.bmm(vecs, vecs.transpose(1, 2))                             # pooled-embedding x dense-bottom interaction
-            z = torch.cat([x, inter[:, self.tri[0], self.tri[1]]], dim=1)
+            z = torch.cat([x, inter.flatten(1).index_select(1, self.tri_flat)], dim=1)
             return self.top(z).squeeze(-1)
 
     return DLRMTower()
