@@ -261,6 +261,30 @@ def run(args, rank, local_rank, world, B_):
     assert not overflowed, "a (source, owner) pair needed more than cap slots: raise the margin of calibrate_cap"
     assert not gave_up and counters["wait_errors"] == 0, "a wait for a peer gave up: the run is void"
 
+    # ---- where a step's time goes on this rank: CUDA events around every launch of ONE kernel family at a time (eager
+    # launches; the backward's kernels then run one after another).  Family 8 is the time spent waiting for peers' flags.
+    fam_names = {0: "k_owner_lookup", 1: "k_dedup", 2: "k_expand", 3: "k_nan_scan", 4: "k_reduce_hot<send>", 5: "k_reduce_cold<send>",
+                 7: "k_reduce_warm<send>", 8: "k_wait (peers)", 9: "k_route_items + k_signal", 10: "k_owner_update_all"}
+    kern = {}
+    if not args.no_kernel_table:
+        import ctypes as C
+
+        n_prof = 10
+        for f in sorted(fam_names):
+            dist.barrier()
+            lib.pb_profile_enable(1 << f)
+            with torch.cuda.stream(gstream):
+                for i in range(n_prof):
+                    eager_step(i % n_sets)
+            fam_ms = (C.c_double * 11)()
+            fam_cnt = (C.c_uint64 * 11)()
+            N.check(lib.pb_profile_read(fam_ms, fam_cnt, 11))
+            lib.pb_profile_enable(0)
+            if fam_cnt[f]:
+                kern[fam_names[f]] = {"us_per_step": round(1e3 * fam_ms[f] / n_prof, 1), "launches_per_step": fam_cnt[f] / n_prof}
+        torch.cuda.synchronize()
+        dist.barrier()
+
     parity = None
     if not args.no_parity:
         sets = (0, 1)
@@ -315,6 +339,7 @@ def run(args, rank, local_rank, world, B_):
             "run": {"ms_per_step_repetitions": reps, "resident_rows_rank0": resident, "table_fill_seconds": round(t_fill, 2),
                     "l2": "inputs larger than L2: %.1f GB table per GPU + %d rotating id/grad/output sets" % (
                         resident * 4.0 * 2 * dim / 1e9, n_sets),
+                    "kernels_rank0": kern,
                     "exchange": "slots per (source, owner) pair: %d (calibrated on the batches, +15%%); distinct signs per "
                                 "batch on rank 0: %d of %d occurrences" % (cap, stats["items"], stats["occurrences"]),
                     "launch": "whole step (compute kernels, peer stores, flag waits) = one CUDA graph per rank" if graphs is not None else "kernel by kernel",

@@ -237,9 +237,9 @@ uint64_t pb_launch_count(void);
 /* Bench instrumentation: launches of the kernel families selected by the bit mask are bracketed by CUDA events on
  * their stream (0 = off).  pb_profile_read synchronises the device and returns summed milliseconds and launch
  * counts per family: 0 probe/admit, 1 dedup, 2 gather+pool, 3 NaN scan, 4 reduce+update of hot signs (> 32 occurrences),
- * 5 update of the signs that occur once (and the owner's update on the sharded path), 6 other, 7 reduce+update of the
- * signs of 2..32 occurrences. */
-#define PB_PROFILE_FAMILIES 8
+ * 5 update of the signs that occur once, 6 other, 7 reduce+update of the signs of 2..32 occurrences; sharded path: 8 waits
+ * for peers' flags, 9 route + signals, 10 the owner's update (its lookup counts as 0, the expand as 2). */
+#define PB_PROFILE_FAMILIES 11
 int pb_profile_enable(int family_mask);
 int pb_profile_read(double* h_ms, uint64_t* h_count, int n_families);
 

@@ -886,6 +886,7 @@ int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids
                        const uint32_t* h_slot_occ_off, uint32_t batch, int training, void* d_out_f16, void* stream,
                        int phases) {
   if (phases == 0) phases = PB_PHASE_ALL;
+  const bool all = phases == PB_PHASE_ALL;
   if (!t || !c || !x || !h_slot_occ_off || !d_out_f16 || (n_occ && !d_ids)) return fail(PB_ERR_INVALID, "null argument");
   if (!c->has_slots) return fail(PB_ERR_STATE, "pb_ctx_set_slots not called");
   if (t->device != c->device || t->device != x->device) return fail(PB_ERR_INVALID, "table, context and exchange live on different devices");
@@ -923,20 +924,22 @@ int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids
     c->b.n = n_occ;
     launch_dedup(sl, c->b, d_ids, st);
     launch_route_items(training != 0, sl, c->b, x->d, st);               // requester: signs -> owners' areas
-    launch_signal(x->d, XC_FLAG_SIGN, c->b.cnt + BC_PEER, st);
+    if (all) launch_signal_wait(x->d, XC_FLAG_SIGN, c->b.cnt + BC_PEER, st);  // (one launch when no phase split is asked for)
+    else launch_signal(x->d, XC_FLAG_SIGN, c->b.cnt + BC_PEER, st);
   }
   if (phases & PB_PHASE_SERVE) {
-    launch_wait(x->d, XC_FLAG_SIGN, -1, st);
+    if (!all) launch_wait(x->d, XC_FLAG_SIGN, -1, st);
     if (training && x->u_dirty) launch_uclear(x->d, st);  // a training batch whose gradients never came left its rows noted
     launch_owner_lookup(training != 0, t->d, t->hy, t->op, x->d, st);    // owner: rows -> requesters' areas
     if (training) x->u_dirty = true;
-    launch_signal(x->d, XC_FLAG_ROW, nullptr, st);
+    if (all) launch_signal_wait(x->d, XC_FLAG_ROW, nullptr, st);
+    else launch_signal(x->d, XC_FLAG_ROW, nullptr, st);
   }
   if (!(phases & PB_PHASE_FINISH)) {
     PB_CUDA(cudaGetLastError());
     return PB_OK;
   }
-  launch_wait(x->d, XC_FLAG_ROW, -1, st);
+  if (!all) launch_wait(x->d, XC_FLAG_ROW, -1, st);
   launch_expand_items(t->d, sl, c->b, x->d, d_row_off, (uint32_t)n_out, batch, training != 0, d_out_f16, st);
   if (training) {
     c->n_occ = n_occ;
@@ -1011,7 +1014,8 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
   PB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   PB_CUDA(cudaEventRecord(c->ev_join2, c->side2));
   PB_CUDA(cudaStreamWaitEvent(st, c->ev_join2, 0));
-  launch_signal(x->d, XC_FLAG_GRAD, nullptr, st);
+  if (phases == PB_PHASE_ALL && t->op.kind != PB_OPT_ADAGRAD_VW) launch_signal_wait(x->d, XC_FLAG_GRAD, nullptr, st);
+  else launch_signal(x->d, XC_FLAG_GRAD, nullptr, st);
   }
   if (!(phases & PB_PHASE_SERVE)) {
     PB_CUDA(cudaGetLastError());
@@ -1024,7 +1028,7 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
     }
     launch_uclear(x->d, st);
   } else {  // owner: the R requests in one launch, every row stepped in rank order
-    launch_wait(x->d, XC_FLAG_GRAD, -1, st);
+    if (phases != PB_PHASE_ALL) launch_wait(x->d, XC_FLAG_GRAD, -1, st);
     launch_owner_update_all(t->d, t->op, t->hy, x->d, st);
   }
   x->u_dirty = false;

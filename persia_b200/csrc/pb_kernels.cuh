@@ -151,6 +151,7 @@ void launch_reduce_items(const TableDev& t, const OptimDev& op, const HyperDev& 
 void launch_route_items(bool training, const SlotsDev& sl, const BatchDev& b, const XchgDev& x, cudaStream_t st);
 void launch_signal(const XchgDev& x, int phase, const uint32_t* counts, cudaStream_t st);
 void launch_wait(const XchgDev& x, int phase, int src /* -1: every source */, cudaStream_t st);
+void launch_signal_wait(const XchgDev& x, int phase, const uint32_t* counts, cudaStream_t st);
 void launch_owner_lookup(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const XchgDev& x,
                          cudaStream_t st);
 void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& b, const XchgDev& x,
@@ -198,7 +199,7 @@ void launch_export_signs(const TableDev& t, uint64_t* signs, uint32_t* recency, 
                          cudaStream_t st);
 void launch_evict(const TableDev& t, uint32_t low_water, uint32_t target_free, uint32_t keep, uint32_t* ev, cudaStream_t st);
 uint64_t launch_count();
-enum { FAM_PROBE = 0, FAM_DEDUP, FAM_GATHER, FAM_NAN, FAM_HOT, FAM_UPDATE, FAM_OTHER, FAM_WARM, FAM_COUNT };
+enum { FAM_PROBE = 0, FAM_DEDUP, FAM_GATHER, FAM_NAN, FAM_HOT, FAM_UPDATE, FAM_OTHER, FAM_WARM, FAM_WAIT, FAM_ROUTE, FAM_OWNER, FAM_COUNT };
 bool profiling();  // a kernel family is being timed: the backward then runs its kernels one after another
 void profile_enable(uint32_t family_mask);
 void profile_read(double* ms, uint64_t* count, int n_families);

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_route_items(SlotsDev sl, BatchDev b, Xc
 #ifndef PB_WAIT_SPINS
 #define PB_WAIT_SPINS (1u << 25)
 #endif
-__global__ void k_signal(XchgDev x, int phase, const uint32_t* __restrict__ counts) {
+__device__ __forceinline__ void signal_phase(const XchgDev& x, int phase, const uint32_t* __restrict__ counts) {
   __shared__ uint32_t e_s;
   if (threadIdx.x == 0) {
     e_s = x.epoch[phase] + 1;
@@ -118,8 +118,7 @@ __global__ void k_signal(XchgDev x, int phase, const uint32_t* __restrict__ coun
     *reinterpret_cast<volatile uint32_t*>(&ctrl[phase * PB_MAX_RANKS + x.rank]) = e_s;
   }
 }
-
-__global__ void k_wait(XchgDev x, int phase, int src) {
+__device__ __forceinline__ void wait_phase(const XchgDev& x, int phase, int src) {
   const uint32_t q = threadIdx.x;
   if (q >= x.R || (src >= 0 && q != (uint32_t)src)) return;
   uint32_t* w = &x.waited[phase * PB_MAX_RANKS + q];
@@ -134,6 +133,13 @@ __global__ void k_wait(XchgDev x, int phase, int src) {
     }
   }
   __threadfence_system();
+}
+__global__ void k_signal(XchgDev x, int phase, const uint32_t* __restrict__ counts) { signal_phase(x, phase, counts); }
+__global__ void k_wait(XchgDev x, int phase, int src) { wait_phase(x, phase, src); }
+// one process per GPU: a phase's signal is directly followed by the wait for the peers' — one launch
+__global__ void k_signal_wait(XchgDev x, int phase, const uint32_t* __restrict__ counts) {
+  signal_phase(x, phase, counts);
+  wait_phase(x, phase, -1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,15 +207,25 @@ __global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev 
     } else {
       __half* dst = reinterpret_cast<__half*>(x_row(x, src)) + slot * t.dim;
       if (t.dim % 4 == 0) {
-        for (uint32_t e = sub * 4; e < t.dim; e += BUCKET * 4) {
-          float4 v = have ? __ldcg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          // the EW adds the row into a zeroed f32 row, then converts (mod.rs:555-561, persia-common lib.rs:157-161)
-          __half2 a = __floats2half2_rn(__fadd_rn(0.0f, v.x), __fadd_rn(0.0f, v.y));
-          __half2 c = __floats2half2_rn(__fadd_rn(0.0f, v.z), __fadd_rn(0.0f, v.w));
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&a);
-          pk.y = *reinterpret_cast<uint32_t*>(&c);
-          *reinterpret_cast<uint2*>(dst + e) = pk;
+        for (uint32_t e0 = sub * 4; e0 < t.dim; e0 += BUCKET * 4 * 4) {  // four 16-byte loads in flight per lane
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t e = e0 + (uint32_t)u * BUCKET * 4;
+            v[u] = (have && e < t.dim) ? __ldcg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t e = e0 + (uint32_t)u * BUCKET * 4;
+            if (e >= t.dim) break;
+            // the EW adds the row into a zeroed f32 row, then converts (mod.rs:555-561, persia-common lib.rs:157-161)
+            __half2 a = __floats2half2_rn(__fadd_rn(0.0f, v[u].x), __fadd_rn(0.0f, v[u].y));
+            __half2 c = __floats2half2_rn(__fadd_rn(0.0f, v[u].z), __fadd_rn(0.0f, v[u].w));
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&a);
+            pk.y = *reinterpret_cast<uint32_t*>(&c);
+            *reinterpret_cast<uint2*>(dst + e) = pk;
+          }
         }
       } else {
         for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = __float2half_rn(__fadd_rn(0.0f, have ? __ldcg(row + e) : 0.0f));
@@ -460,15 +476,20 @@ __global__ void __launch_bounds__(256) k_owner_update(TableDev t, OptimDev op, H
 void launch_route_items(bool training, const SlotsDev& sl, const BatchDev& b, const XchgDev& x, cudaStream_t st) {
   if (!b.n) return;
   const uint32_t grid = cdiv(b.n, 256);  // worst case U = N; blocks past the item count return at once
-  if (training) PB_LAUNCH_F(FAM_PROBE, (k_route_items<true>), grid, 256, 0, st, sl, b, x);
-  else PB_LAUNCH_F(FAM_PROBE, (k_route_items<false>), grid, 256, 0, st, sl, b, x);
+  if (training) PB_LAUNCH_F(FAM_ROUTE, (k_route_items<true>), grid, 256, 0, st, sl, b, x);
+  else PB_LAUNCH_F(FAM_ROUTE, (k_route_items<false>), grid, 256, 0, st, sl, b, x);
 }
 
 void launch_signal(const XchgDev& x, int phase, const uint32_t* counts, cudaStream_t st) {
-  PB_LAUNCH(k_signal, 1, 32, 0, st, x, phase, counts);
+  PB_LAUNCH_F(FAM_ROUTE, k_signal, 1, 32, 0, st, x, phase, counts);
 }
 
-void launch_wait(const XchgDev& x, int phase, int src, cudaStream_t st) { PB_LAUNCH(k_wait, 1, 32, 0, st, x, phase, src); }
+void launch_signal_wait(const XchgDev& x, int phase, const uint32_t* counts, cudaStream_t st) {
+  PB_LAUNCH_F(FAM_WAIT, k_signal_wait, 1, 32, 0, st, x, phase, counts);
+}
+void launch_wait(const XchgDev& x, int phase, int src, cudaStream_t st) {
+  PB_LAUNCH_F(FAM_WAIT, k_wait, 1, 32, 0, st, x, phase, src);
+}
 
 void launch_owner_lookup(bool training, const TableDev& t, const HyperDev& hy, const OptimDev& op, const XchgDev& x,
                          cudaStream_t st) {
@@ -519,9 +540,9 @@ void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& 
 template <int VEC, int CPL>
 static void owner_update_all_kind(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t G,
                                   uint32_t grid, cudaStream_t st) {
-  if (op.kind == PB_OPT_SGD) PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<VEC, CPL, PB_OPT_SGD>), grid, 256, 0, st, t, op, hy, x, G);
-  else if (op.kind == PB_OPT_ADAGRAD) PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<VEC, CPL, PB_OPT_ADAGRAD>), grid, 256, 0, st, t, op, hy, x, G);
-  else PB_LAUNCH_F(FAM_UPDATE, (k_owner_update_all<VEC, CPL, -1>), grid, 256, 0, st, t, op, hy, x, G);
+  if (op.kind == PB_OPT_SGD) PB_LAUNCH_F(FAM_OWNER, (k_owner_update_all<VEC, CPL, PB_OPT_SGD>), grid, 256, 0, st, t, op, hy, x, G);
+  else if (op.kind == PB_OPT_ADAGRAD) PB_LAUNCH_F(FAM_OWNER, (k_owner_update_all<VEC, CPL, PB_OPT_ADAGRAD>), grid, 256, 0, st, t, op, hy, x, G);
+  else PB_LAUNCH_F(FAM_OWNER, (k_owner_update_all<VEC, CPL, -1>), grid, 256, 0, st, t, op, hy, x, G);
 }
 
 void launch_owner_update_all(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, cudaStream_t st) {
