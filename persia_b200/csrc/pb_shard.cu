@@ -206,26 +206,44 @@ __global__ void __launch_bounds__(256, PB_PROBE_BLOCKS) k_owner_lookup(TableDev 
       }
     } else {
       __half* dst = reinterpret_cast<__half*>(x_row(x, src)) + slot * t.dim;
-      if (t.dim % 4 == 0) {
-        for (uint32_t e0 = sub * 4; e0 < t.dim; e0 += BUCKET * 4 * 4) {  // four 16-byte loads in flight per lane
-          float4 v[4];
+      if (t.dim % 8 == 0) {
+        // a lane converts 8 consecutive floats into one 16-byte store: the group's stores are 128 contiguous bytes —
+        // whole NVLink write packets when the requester is a peer; two such chunks (four loads) in flight per lane
+        for (uint32_t e0 = sub * 8; e0 < t.dim; e0 += BUCKET * 8 * 2) {
+          float4 v[2][2];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t e = e0 + (uint32_t)u * BUCKET * 4;
-            v[u] = (have && e < t.dim) ? __ldcg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t e = e0 + (uint32_t)u * BUCKET * 8;
+            const bool in = have && e < t.dim;
+            v[u][0] = in ? __ldcg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u][1] = in ? __ldcg(reinterpret_cast<const float4*>(row + e + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t e = e0 + (uint32_t)u * BUCKET * 4;
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t e = e0 + (uint32_t)u * BUCKET * 8;
             if (e >= t.dim) break;
             // the EW adds the row into a zeroed f32 row, then converts (mod.rs:555-561, persia-common lib.rs:157-161)
-            __half2 a = __floats2half2_rn(__fadd_rn(0.0f, v[u].x), __fadd_rn(0.0f, v[u].y));
-            __half2 c = __floats2half2_rn(__fadd_rn(0.0f, v[u].z), __fadd_rn(0.0f, v[u].w));
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&a);
-            pk.y = *reinterpret_cast<uint32_t*>(&c);
-            *reinterpret_cast<uint2*>(dst + e) = pk;
+            __half2 h0 = __floats2half2_rn(__fadd_rn(0.0f, v[u][0].x), __fadd_rn(0.0f, v[u][0].y));
+            __half2 h1 = __floats2half2_rn(__fadd_rn(0.0f, v[u][0].z), __fadd_rn(0.0f, v[u][0].w));
+            __half2 h2 = __floats2half2_rn(__fadd_rn(0.0f, v[u][1].x), __fadd_rn(0.0f, v[u][1].y));
+            __half2 h3 = __floats2half2_rn(__fadd_rn(0.0f, v[u][1].z), __fadd_rn(0.0f, v[u][1].w));
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(dst + e) = pk;
           }
+        }
+      } else if (t.dim % 4 == 0) {
+        for (uint32_t e = sub * 4; e < t.dim; e += BUCKET * 4) {
+          float4 v = have ? __ldcg(reinterpret_cast<const float4*>(row + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          __half2 a = __floats2half2_rn(__fadd_rn(0.0f, v.x), __fadd_rn(0.0f, v.y));
+          __half2 c = __floats2half2_rn(__fadd_rn(0.0f, v.z), __fadd_rn(0.0f, v.w));
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&a);
+          pk.y = *reinterpret_cast<uint32_t*>(&c);
+          *reinterpret_cast<uint2*>(dst + e) = pk;
         }
       } else {
         for (uint32_t e = sub; e < t.dim; e += BUCKET) dst[e] = __float2half_rn(__fadd_rn(0.0f, have ? __ldcg(row + e) : 0.0f));
