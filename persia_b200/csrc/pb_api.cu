@@ -794,6 +794,10 @@ struct pb_xchg {
   XchgDev d{};
   uint32_t* mem = nullptr;  // epoch | waited | own_cnt | err | own_row | uwin
   UCell* ucell = nullptr;   // rows of the step's requests (owner side)
+  uint64_t* akeys = nullptr;  // Adam: the table's feature-group prefixes on the device
+  uint32_t* apresent = nullptr;
+  float* apow = nullptr;
+  size_t akeys_uploaded = 0;
   bool u_dirty = false;     // a training lookup filled ucell and its update has not run (abandoned batch)
 };
 
@@ -845,6 +849,10 @@ int pb_xchg_create(int device, uint32_t R, uint32_t rank, uint32_t cap, uint32_t
   uint32_t ucells = 1024;
   while ((size_t)ucells < 2 * (size_t)R * cap) ucells <<= 1;
   if (e == cudaSuccess) e = cudaMalloc(&x->ucell, sizeof(UCell) * (size_t)ucells);
+  if (e == cudaSuccess) e = cudaMalloc(&x->akeys, sizeof(uint64_t) * PB_ADAM_KEYS);
+  if (e == cudaSuccess) e = cudaMalloc(&x->apresent, sizeof(uint32_t) * PB_MAX_RANKS * (PB_ADAM_KEYS / 32));
+  if (e == cudaSuccess) e = cudaMemset(x->apresent, 0, sizeof(uint32_t) * PB_MAX_RANKS * (PB_ADAM_KEYS / 32));
+  if (e == cudaSuccess) e = cudaMalloc(&x->apow, sizeof(float) * 2 * PB_MAX_RANKS * PB_ADAM_KEYS);
 
   if (e != cudaSuccess) {
     delete x;
@@ -858,6 +866,9 @@ int pb_xchg_create(int device, uint32_t R, uint32_t rank, uint32_t cap, uint32_t
   d.uwin = d.own_row + (size_t)R * cap;
   d.ucell = x->ucell;
   d.ucells = ucells;
+  d.akeys = x->akeys;
+  d.apresent = x->apresent;
+  d.apow = x->apow;
   launch_uclear(d, nullptr);
   PB_CUDA(cudaDeviceSynchronize());
   *out = x;
@@ -870,6 +881,9 @@ int pb_xchg_destroy(pb_xchg* x) {
   cudaDeviceSynchronize();
   if (x->mem) cudaFree(x->mem);
   if (x->ucell) cudaFree(x->ucell);
+  if (x->akeys) cudaFree(x->akeys);
+  if (x->apresent) cudaFree(x->apresent);
+  if (x->apow) cudaFree(x->apow);
   delete x;
   return PB_OK;
 }
@@ -893,7 +907,6 @@ int pb_forward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const uint64_t* d_ids
   if (x->dim != t->cfg.dim) return fail(PB_ERR_INVALID, "the exchange was sized for another embedding dim");
   if (batch > 65535) return fail(PB_ERR_BATCH, "batch size cannot be larger than 65535");
   if (c->n_rounds != 1) return fail(PB_ERR_INVALID, "slots sharing a feature group are not supported on the sharded path");
-  if (t->has_op && t->op.kind == PB_OPT_ADAM) return fail(PB_ERR_INVALID, "Adam is not supported on the sharded path yet");
   if (d_row_off && !x->d.row_f32) return fail(PB_ERR_INVALID, "ragged layouts need an exchange created with f32 rows");
   uint32_t S = c->slots.n_slots;
   uint64_t n_out = (uint64_t)S * batch;
@@ -1029,6 +1042,18 @@ int pb_backward_sharded(pb_table* t, pb_ctx* c, pb_xchg* x, const void* const* h
     launch_uclear(x->d, st);
   } else {  // owner: the R requests in one launch, every row stepped in rank order
     if (phases != PB_PHASE_ALL) launch_wait(x->d, XC_FLAG_GRAD, -1, st);
+    if (t->op.kind == PB_OPT_ADAM) {  // every request advances the beta powers of the feature groups it holds here
+      for (uint32_t s = 0; s < S; ++s)
+        if (adam_index(t, c->slots.prefix[s]) < 0) return fail(PB_ERR_CAPACITY, "more feature groups than Adam beta-power pairs");
+      if (x->akeys_uploaded != t->adam_keys.size()) {  // (first steps only: not inside a graph capture)
+        PB_CUDA(cudaStreamSynchronize(st));
+        PB_CUDA(cudaMemcpy(x->akeys, t->adam_keys.data(), sizeof(uint64_t) * t->adam_keys.size(), cudaMemcpyHostToDevice));
+        x->akeys_uploaded = t->adam_keys.size();
+      }
+      x->d.n_akeys = (uint32_t)t->adam_keys.size();
+      x->d.amask = ~sl.spacing;
+      launch_owner_adam(x->d, t->adam_dev, t->op.b1, t->op.b2, st);
+    }
     launch_owner_update_all(t->d, t->op, t->hy, x->d, st);
   }
   x->u_dirty = false;

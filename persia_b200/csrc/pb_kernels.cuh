@@ -72,6 +72,7 @@ struct BatchDev {
 //   gok    [R][cap] u32         1 = apply the gradient, 0 = the slot was skipped / held a NaN
 enum { XC_FLAG_SIGN = 0, XC_FLAG_ROW, XC_FLAG_GRAD, XC_COUNT, XC_WORDS };
 constexpr uint32_t PB_MAX_RANKS = 16;
+constexpr uint32_t PB_ADAM_KEYS = 256;  // beta-power pairs per table; the last one serves pb_update
 // owner side, one step: the distinct rows the R requests touch (k_owner_lookup fills it, k_owner_update_all empties it)
 struct __align__(16) UCell {
   uint32_t row;               // ROW_NONE = empty
@@ -91,6 +92,13 @@ struct XchgDev {
   UCell* ucell;        // [ucells] rows of the step's requests, hashed by row number
   uint32_t* uwin;      // [R][cap] the cell a request's sign opened (it was the first to ask for the row), else ROW_NONE
   uint32_t ucells;     // a power of two >= 2 R cap
+  // Adam on the owner: feature groups (index prefixes) of the table, the groups each request holds, and the (beta1^t,
+  // beta2^t) pair every request's signs of a group use (get_batch_level_state, optim.rs:151-197)
+  const uint64_t* akeys;  // [n_akeys] prefixes, position = pair number of the table
+  uint32_t n_akeys;
+  uint64_t amask;         // the prefix bits of a sign
+  uint32_t* apresent;     // [R][PB_ADAM_KEYS / 32] groups among the signs request s applies
+  float* apow;            // [R][PB_ADAM_KEYS][2]
 };
 
 // arguments of the backward kernels (pb_reduce.cu)
@@ -158,6 +166,7 @@ void launch_expand_items(const TableDev& t, const SlotsDev& sl, const BatchDev& 
                          const uint32_t* row_off, uint32_t n_out, uint32_t batch, bool training, void* out_f16,
                          cudaStream_t st);
 void launch_hash_stack(const uint64_t* ids, uint32_t n, uint32_t rounds, uint64_t size, uint64_t* out, cudaStream_t st);
+void launch_owner_adam(const XchgDev& x, float* table_pow, float b1, float b2, cudaStream_t st);
 void launch_uclear(const XchgDev& x, cudaStream_t st);
 void launch_owner_update_all(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, cudaStream_t st);
 void launch_owner_update(const TableDev& t, const OptimDev& op, const HyperDev& hy, const XchgDev& x, uint32_t src,
@@ -167,7 +176,6 @@ void launch_update_direct(const TableDev& t, const OptimDev& op, const HyperDev&
                           const float* grads, uint32_t n, const float* adam_pair, cudaStream_t st,
                           const uint32_t* n_ptr = nullptr, const uint32_t* tick = nullptr,
                           const uint32_t* nan_tick = nullptr);
-constexpr uint32_t PB_ADAM_KEYS = 256;  // beta-power pairs per table; the last one serves pb_update
 struct AdamKeys {
   uint8_t idx[PB_MAX_SLOTS];
   uint32_t n;

@@ -310,6 +310,60 @@ __global__ void __launch_bounds__(256) k_expand_pool(uint32_t dim, SlotsDev sl, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// owner, backward, Adam: get_batch_level_state per request (optim.rs:151-197).  A request advances the accumulated
+// (beta1^t, beta2^t) of every feature group that occurs among the signs it applies on THIS parameter server, once,
+// and all its signs of the group use the advanced pair.  k_owner_adam_present finds the groups per request (block-level
+// bit sets: a few global atomics per block), k_owner_adam_pows walks the requests in rank order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t adam_key_of(const XchgDev& x, uint64_t sign) {
+  const uint64_t m = sign & x.amask;
+  for (uint32_t g = 0; g < x.n_akeys; ++g)
+    if (x.akeys[g] == m) return g;
+  return PB_ADAM_KEYS - 1u;  // (a group the table has never seen in a forward: cannot hold rows)
+}
+__global__ void __launch_bounds__(256) k_owner_adam_present(XchgDev x) {
+  __shared__ uint32_t bits[PB_MAX_RANKS][PB_ADAM_KEYS / 32];
+  for (uint32_t i = threadIdx.x; i < PB_MAX_RANKS * (PB_ADAM_KEYS / 32); i += blockDim.x) (&bits[0][0])[i] = 0u;
+  __syncthreads();
+  const uint32_t total = x.R * x.cap;
+  const uint32_t* gok = reinterpret_cast<const uint32_t*>(x.base[x.rank] + x.off_gok);
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+    const uint32_t src = j / x.cap, k = j % x.cap;
+    if (k >= x.own_cnt[src] || gok[j] == 0u) continue;
+    const uint32_t g = adam_key_of(x, x_sign(x, x.rank)[j]);
+    atomicOr(&bits[src][g >> 5], 1u << (g & 31u));
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < x.R * (PB_ADAM_KEYS / 32); i += blockDim.x) {
+    const uint32_t v = (&bits[0][0])[(i / (PB_ADAM_KEYS / 32)) * (PB_ADAM_KEYS / 32) + i % (PB_ADAM_KEYS / 32)];
+    if (v) atomicOr(&x.apresent[i], v);
+  }
+}
+__global__ void k_owner_adam_pows(XchgDev x, float* table_pow, float b1, float b2) {
+  const uint32_t g = threadIdx.x;
+  if (g >= PB_ADAM_KEYS) return;
+  float p1 = table_pow[2 * g], p2 = table_pow[2 * g + 1];
+  for (uint32_t s = 0; s < x.R; ++s) {
+    uint32_t* w = &x.apresent[s * (PB_ADAM_KEYS / 32) + (g >> 5)];
+    if ((*w >> (g & 31u)) & 1u) {
+      p1 = __fmul_rn(p1, b1);
+      p2 = __fmul_rn(p2, b2);
+    }
+    x.apow[(s * PB_ADAM_KEYS + g) * 2] = p1;
+    x.apow[(s * PB_ADAM_KEYS + g) * 2 + 1] = p2;
+  }
+  table_pow[2 * g] = p1;
+  table_pow[2 * g + 1] = p2;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < x.R * (PB_ADAM_KEYS / 32); i += blockDim.x) x.apresent[i] = 0u;  // for the next step
+}
+void launch_owner_adam(const XchgDev& x, float* table_pow, float b1, float b2, cudaStream_t st) {
+  const uint32_t full = cdiv((uint64_t)x.R * x.cap, 256);
+  PB_LAUNCH(k_owner_adam_present, full < 148u * 2u ? full : 148u * 2u, 256, 0, st, x);
+  PB_LAUNCH(k_owner_adam_pows, 1, PB_ADAM_KEYS, 0, st, x, table_pow, b1, b2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // owner, backward: update_gradient_mixed of the step's R requests (PS mod.rs:359-427) in ONE launch.  The reference
 // serves the requests one after another; a row that several requests hold is stepped once per request, in the order
 // the requests arrive — here: rank order.  A lane group takes a row (through the request that opened its cell in the
@@ -362,6 +416,14 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) k_owner_update_all(Tabl
       float* prow = t.rows + (size_t)row * t.stride;
       StepCtx sc;
       sc.vw_state = sc.r1 = sc.r2 = 0.0f;
+      uint32_t akey = 0;
+      if (op.kind == PB_OPT_ADAM) akey = adam_key_of(x, x_sign(x, x.rank)[j]);  // the row's feature group
+#define PB_ADAM_CTX(SRC)                                                                     \
+  if (op.kind == PB_OPT_ADAM) {                                                              \
+    const float* pw = x.apow + ((size_t)(SRC) * PB_ADAM_KEYS + akey) * 2u;                   \
+    sc.r1 = __fdiv_rn(1.0f, __fsub_rn(1.0f, pw[0]));                                         \
+    sc.r2 = __fdiv_rn(1.0f, __fsub_rn(1.0f, pw[1]));                                         \
+  }
       // the holder mask, the row and the opener's gradient: one round trip
       const uint32_t mask = cell->mask;
       RowElems<KIND, VEC> rc[CPL];
@@ -374,6 +436,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) k_owner_update_all(Tabl
       }
       if (mask == (1u << me)) {  // the opener is the only holder (the rule)
         if (ok1) {
+          PB_ADAM_CTX(me)
 #pragma unroll
           for (int u = 0; u < CPL; ++u) {
             const uint32_t e = ((uint32_t)u * G + lane) * VEC;
@@ -403,6 +466,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) k_owner_update_all(Tabl
 #pragma unroll
           for (int v = 0; v < 2; ++v)
             if (v < n && ok[v]) {
+              PB_ADAM_CTX(src[v])
 #pragma unroll
               for (int u = 0; u < CPL; ++u) rc[u].step(((uint32_t)u * G + lane) * VEC, g[v][u], t, op, hy, sc);
             }
@@ -410,6 +474,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) k_owner_update_all(Tabl
 #pragma unroll
         for (int u = 0; u < CPL; ++u) rc[u].store(prow, ((uint32_t)u * G + lane) * VEC, t, op);
       }
+#undef PB_ADAM_CTX
       __syncwarp(gmask);
       if (lane == 0) {  // every lane of the group has read the cell: it goes back to empty
         cell->row = ROW_NONE;

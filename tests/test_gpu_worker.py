@@ -42,6 +42,9 @@ def _optim(N, oracle, kind):
     if kind == oracle.ADAGRAD:
         return (dict(kind=N.OPT_ADAGRAD, lr=0.02, initialization=0.01, eps=1e-10),
                 oracle.Optim(oracle.ADAGRAD, lr=0.02, init_acc=0.01, eps=1e-10))
+    if kind == oracle.ADAM:
+        return (dict(kind=N.OPT_ADAM, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8),
+                oracle.Optim(oracle.ADAM, lr=0.01, b1=0.9, b2=0.999, eps=1e-8))
     return (dict(kind=N.OPT_ADAGRAD_VW, lr=0.02, initialization=0.01, eps=1e-10),
             oracle.Optim(oracle.ADAGRAD_VW, lr=0.02, init_acc=0.01, eps=1e-10))
 
@@ -83,7 +86,8 @@ def _check_rows(torch, oracle, ws, w, signs, R):
 
 
 @pytest.mark.parametrize("R,dim,kind,f32", [(2, 64, 0, False), (2, 128, 1, False), (4, 128, 1, False), (8, 128, 1, False),
-                                            (3, 16, 2, True), (2, 12, 0, False), (1, 64, 1, False)])
+                                            (3, 16, 2, True), (2, 12, 0, False), (1, 64, 1, False),
+                                            (2, 32, 3, False), (4, 16, 3, True)])  # Adam: beta powers per feature group and request
 def test_virtual_ranks_match_oracle(torch_cuda, oracle, R, dim, kind, f32):
     from persia_b200.worker import ShardedEmbeddingWorker as W
 
