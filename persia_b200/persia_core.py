@@ -464,6 +464,8 @@ def _forward_locked(batch, device_id, training):
         sc = _S.by_name[name]
         if not sc.embedding_summation and sc.hash_stack_rounds > 0:
             raise RuntimeError(f"slot {name}: a raw (embedding_summation: false) slot with hash_stack is not supported")
+        if not sc.embedding_summation and (_S.replica_size or 1) > 1:
+            raise RuntimeError(f"slot {name}: raw (embedding_summation: false) slots are not supported on replica_size > 1 yet")
     pending = _Pending()
     by_slot = {}
     raw_out = {}
