@@ -718,6 +718,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
     if (gr.do_scale[s] && !std::isfinite(inv)) return fail(PB_ERR_INVALID, "scale on gradient must be finite");
     gr.inv_scale[s] = inv;
   }
+  AdamKeys adam_keys{};
   if (t->op.kind == PB_OPT_ADAM) {  // get_batch_level_state: one power step per request and feature group
     AdamKeys keys{};
     for (uint32_t s = 0; s < S; ++s) {
@@ -730,7 +731,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
       if (!done) keys.idx[keys.n++] = (uint8_t)k;
     }
     gr.adam_pow = t->adam_dev;
-    launch_adam_advance(t->adam_dev, keys, t->op.b1, t->op.b2, st);
+    adam_keys = keys;  // advanced below, once the NaN marks of this request are known
   }
   float* vw = nullptr;
   if (t->op.kind == PB_OPT_ADAGRAD_VW) {
@@ -754,6 +755,7 @@ int pb_backward(pb_table* t, pb_ctx* c, const void* const* h_grads, int is_f16, 
   }
   uint32_t elems = c->batch * t->d.dim;
   launch_nan_scan(gr, S, elems, is_f16 != 0, c->dev_tick, c->nan_tick, d_slot_status, st);
+  if (adam_keys.n) launch_adam_advance(t->adam_dev, adam_keys, t->op.b1, t->op.b2, st, &gr, S, c->dev_tick, c->nan_tick);
   PB_CUDA(cudaEventRecord(c->ev_nan, st));
   PB_CUDA(cudaStreamWaitEvent(c->side, c->ev_nan, 0));
   PB_CUDA(cudaStreamWaitEvent(c->side2, c->ev_nan, 0));

@@ -181,7 +181,8 @@ struct AdamKeys {
   uint32_t n;
 };
 void launch_adam_fill(float* pow, float b1, float b2, cudaStream_t st);
-void launch_adam_advance(float* pow, const AdamKeys& keys, float b1, float b2, cudaStream_t st);
+void launch_adam_advance(float* pow, const AdamKeys& keys, float b1, float b2, cudaStream_t st, const GradsDev* gr = nullptr,
+                         uint32_t n_slots = 0, const uint32_t* tick = nullptr, const uint32_t* nan_tick = nullptr);
 uint32_t raw_scan_tiles(uint32_t n);
 void launch_raw_forward(const TableDev& t, const SlotsDev& sl, const uint64_t* ids, uint32_t n,
                         const uint32_t* row_off, const uint32_t* occ_sample, uint32_t batch, uint32_t fixed,

@@ -114,17 +114,29 @@ __global__ void k_adam_fill(float* pow, float b1, float b2) {
     pow[2 * i + 1] = b2;
   }
 }
-__global__ void k_adam_advance(float* pow, AdamKeys keys, float b1, float b2) {
+// gr / tick / nan_tick (optional): a feature group advances only if one of its slots is applied by this request — a slot
+// skipped for a NaN gradient sends nothing to the parameter server (mod.rs:731-746), so it cannot advance the powers
+__global__ void k_adam_advance(float* pow, AdamKeys keys, float b1, float b2, GradsDev gr, uint32_t n_slots,
+                               const uint32_t* __restrict__ tick, const uint32_t* __restrict__ nan_tick) {
   uint32_t i = threadIdx.x;
   if (i < keys.n) {
-    float* p = pow + 2u * keys.idx[i];
-    p[0] = __fmul_rn(p[0], b1);
-    p[1] = __fmul_rn(p[1], b2);
+    bool applied = nan_tick == nullptr;
+    if (!applied) {
+      const uint32_t now = *tick;
+      for (uint32_t s = 0; s < n_slots; ++s) applied |= gr.ptr[s] && gr.pow_idx[s] == keys.idx[i] && nan_tick[s] != now;
+    }
+    if (applied) {
+      float* p = pow + 2u * keys.idx[i];
+      p[0] = __fmul_rn(p[0], b1);
+      p[1] = __fmul_rn(p[1], b2);
+    }
   }
 }
 void launch_adam_fill(float* pow, float b1, float b2, cudaStream_t st) { PB_LAUNCH(k_adam_fill, 1, PB_ADAM_KEYS, 0, st, pow, b1, b2); }
-void launch_adam_advance(float* pow, const AdamKeys& keys, float b1, float b2, cudaStream_t st) {
-  if (keys.n) PB_LAUNCH(k_adam_advance, 1, PB_MAX_SLOTS, 0, st, pow, keys, b1, b2);
+void launch_adam_advance(float* pow, const AdamKeys& keys, float b1, float b2, cudaStream_t st, const GradsDev* gr,
+                         uint32_t n_slots, const uint32_t* tick, const uint32_t* nan_tick) {
+  GradsDev none{};
+  if (keys.n) PB_LAUNCH(k_adam_advance, 1, PB_MAX_SLOTS, 0, st, pow, keys, b1, b2, gr ? *gr : none, n_slots, tick, gr ? nan_tick : nullptr);
 }
 
 void launch_slot_status(const GradsDev& gr, uint32_t n_slots, const uint32_t* tick, const uint32_t* nan_tick,

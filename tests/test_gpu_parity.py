@@ -554,6 +554,18 @@ def test_adam_training_bit_exact(torch_cuda, pb, oracle, dim):
         _entries_equal(torch, s, w, t)
 
 
+def test_adam_nan_and_skipped_slots_do_not_advance_their_group(torch_cuda, pb, oracle):
+    """A slot dropped for a NaN gradient (mod.rs:731-746) or skipped sends nothing to the parameter server, so its
+    feature group's beta powers stay where they are for that request (get_batch_level_state only sees the signs sent)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(91)
+    S, B, dim, card = 3, 200, 16, [30, 500, 5000]
+    s, ctx, w, _ = _pair(pb, oracle, S, dim, oracle.ADAM, optim_kw=dict(lr=0.01, b1=0.9, b2=0.999, eps=1e-8))
+    touched = _train_steps(torch, s, ctx, w, rng, S, B, dim, card, steps=6, nan_slot=(2, 1), skip_slot=(3, 0))
+    for t in touched:
+        _entries_equal(torch, s, w, t)
+
+
 def test_adam_graph_replay_advances_beta_powers(torch_cuda, pb, oracle):
     """The beta powers live on the device: a captured forward+backward replayed k times equals k oracle steps."""
     torch = torch_cuda
