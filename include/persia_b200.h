@@ -82,6 +82,14 @@ int pb_table_clear(pb_table* t, void* stream);
 int pb_table_set_eviction(pb_table* t, uint32_t check_every, uint64_t low_water, uint64_t target_free, uint32_t keep_batches);
 /* floats per resident row: dim + optimizer state (emb_entry.rs:17-25 `inner`). */
 int pb_table_entry_len(pb_table* t, uint32_t* h_out);
+/* Host-DRAM tier (BASELINE.json configs[4]: the embedding holder's DRAM behind a GPU-resident working set): release the
+ * least recently used rows until `want_free` rows are free, like the capacity sweep (rows touched by the last
+ * max(keep_batches, pending batches + 1) requests stay), but WRITE EVERY VICTIM OUT first: its sign to d_signs[k] and its
+ * whole entry (embedding ++ optimizer state, pb_entry_len floats) to d_entries[k].  Victims beyond max_n stay resident;
+ * *d_count = victims found (<= max_n were released).  The caller keeps the pairs (persia_b200/tier.py) and brings a sign
+ * back with pb_set_rows before its next lookup.  Enqueued on `stream`. */
+int pb_table_spill(pb_table* t, uint64_t want_free, uint32_t keep_batches, uint64_t* d_signs, float* d_entries, uint32_t max_n,
+                   uint32_t* d_count, void* stream);
 /* counters since creation / clear: [0] resident rows (admitted - evicted), [1] distinct signs of a request that missed
  * (infer) or were not admitted (index_miss_count), [2] gradient ids not found (gradient_id_miss_count), [3] admissions
  * refused because the shard is full, [4] in-kernel waits that gave up (must stay 0: a non-zero value voids the batch
