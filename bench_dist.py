@@ -63,6 +63,69 @@ def _check_parity(rank, world, wk, replay, outs, all_ids, all_grads, pf, S, B, d
     return bad_out, bad_rows, int(signs.size)
 
 
+def model_leg_dist(args, rank, world, local_rank, B_, steps=30, warmup=8):
+    """e2e_model at N > 1: persia_b200.api.TrainCtx on every rank — DDP dense tower (persia/distributed.py:174-191), the
+    embeddings behind PersiaCommonContext(replica_size = world) served by a ShardedEmbeddingWorker — driven from host numpy
+    batches, wall clock around the loop, max over ranks."""
+    from persia_b200 import api
+    from persia_b200 import persia_core as PC
+    from persia_b200 import workload as W
+
+    S, B, dim, n_dense = args.slots, args.batch, args.dim, 13
+    names = [f"C{i + 1}" for i in range(S)]
+    dev = torch.device("cuda", local_rank)
+    PC.reset()
+    PC._S.capacity = int(2e7 / world) + (1 << 20)
+    PC.set_embedding_config({"slots_config": {n: {"dim": dim} for n in names}})
+    card = W.scaled_cardinalities(int(2e7), S)
+    torch.manual_seed(0)
+    prev_precision = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+    model = W.make_dlrm_tower(S, dim, n_dense=n_dense).cuda()
+    dense_opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    loss_fn = torch.nn.BCEWithLogitsLoss()
+    n_pool = 8
+    ids_pool = W.make_batches(7 + rank, card, B, n_pool, args.alpha).reshape(n_pool, S, B)
+    rng = np.random.default_rng(11 + rank)
+    dense_pool = rng.standard_normal((n_pool, B, n_dense)).astype(np.float32)
+    label_pool = (rng.random((n_pool, B, 1)) < 0.25).astype(np.float32)
+    try:
+        with api.TrainCtx(model=model, embedding_optimizer=api.Adagrad(lr=0.01, initial_accumulator_value=0.01, eps=1e-10),
+                          dense_optimizer=dense_opt, device_id=local_rank, mixed_precision=False) as ctx:
+            def step(k):
+                pb = api.PersiaBatch([api.IDTypeFeatureWithSingleID(names[i], ids_pool[k, i]) for i in range(S)],
+                                     non_id_type_features=[api.NonIDTypeFeature(dense_pool[k], name="dense")],
+                                     labels=[api.Label(label_pool[k], name="click")], requires_grad=True)
+                out, labels = ctx.forward(ctx.get_embedding_from_data(pb))
+                loss = loss_fn(out, labels[0].squeeze(1))
+                ctx.backward(loss)
+                return loss
+
+            for i in range(warmup):
+                step(i % n_pool)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.time()
+            first = last = None
+            for i in range(steps):
+                last = step(i % n_pool)
+                first = last if first is None else first
+            ctx.backward_engine.flush()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.time() - t0], device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.barrier()
+    finally:
+        PC.reset()
+        torch.set_float32_matmul_precision(prev_precision)
+    dt = float(dt)
+    return {"value": B * world * steps / dt, "unit": B_.UNIT, "ms_per_step": 1e3 * dt / steps, "steps": steps,
+            "first_loss_rank0": float(first.detach()), "last_loss_rank0": float(last.detach()),
+            "path": "numpy batch -> api.PersiaBatch -> TrainCtx.get_embedding_from_data (ShardedEmbeddingWorker over %d GPUs) -> "
+                    "DLRM tower under DistributedDataParallel (TF32 matmuls) -> BCE -> TrainCtx.backward (dense SGD all-reduce + "
+                    "sparse Adagrad on the owners); 2e7-id key space, rows admitted on the fly; wall clock, max over ranks" % world}
+
+
 def run(args, rank, local_rank, world, B_):
     from persia_b200 import native as N
     from persia_b200 import shard as SH
@@ -325,6 +388,7 @@ def run(args, rank, local_rank, world, B_):
                           "outputs it serves are bit-identical to the oracle (R parameter servers, the R requests of a "
                           "step applied in rank order)"}
 
+    line = None
     if rank == 0:
         ms_per_step = ms / K
         GB = B * world
@@ -360,10 +424,43 @@ def run(args, rank, local_rank, world, B_):
                          "bytes_model": "measured multiplicities of rank 0's batch (see bench.py kernel_bytes); NVLink bytes not counted"},
             "cpu_baseline": None,
         }
-        print(json.dumps(line))
-        sys.stdout.flush()
-    # ---- orderly teardown: graphs first (they reference the exchange areas), then the worker, then the process group;
-    # a watchdog ends the process if a driver-level teardown stalls after everything has been reported
+    # ---- the measured line is complete; what follows (teardown of the 100 GB tables, then the TrainCtx / DDP leg) can
+    # only add to it: a watchdog prints the line as it stands and ends the process if any of it stalls
+    printed = threading.Event()
+
+    def emit(extra):
+        if printed.is_set():
+            return
+        printed.set()
+        if rank == 0:
+            line["e2e_model"] = extra
+            print(json.dumps(line))
+            sys.stdout.flush()
+
+    def line_watchdog():
+        if not printed.wait(300):
+            sys.stderr.write("[bench] teardown / e2e_model leg stalled: reporting without it\n")
+            sys.stderr.flush()
+            emit({"error": "the e2e_model leg (or the teardown before it) did not finish within 300 s"})
+            os._exit(0)
+
+    threading.Thread(target=line_watchdog, daemon=True).start()
+    # orderly teardown of the timed path: graphs first (they reference the exchange areas), then the worker
+    dist.barrier()
+    torch.cuda.synchronize()
+    del graphs, e2e_graphs
+    torch.cuda.synchronize()
+    wk.close()
+    del wk
+    torch.cuda.empty_cache()
+    dist.barrier()
+    if args.no_model_leg:
+        emit(None)
+    else:
+        try:
+            emit(model_leg_dist(args, rank, world, local_rank, B_))
+        except Exception as e:  # noqa: BLE001 — reported, never fatal for the measured line
+            emit({"error": repr(e)[:300]})
     done = threading.Event()
 
     def watchdog():
@@ -373,12 +470,6 @@ def run(args, rank, local_rank, world, B_):
             os._exit(0)
 
     threading.Thread(target=watchdog, daemon=True).start()
-    dist.barrier()
-    torch.cuda.synchronize()
-    del graphs, e2e_graphs
-    torch.cuda.synchronize()
-    wk.close()
-    del wk
     dist.barrier()
     dist.destroy_process_group()
     done.set()
